@@ -1,0 +1,134 @@
+"""TEST INFRASTRUCTURE ONLY. ctypes wrapper around oracle/_ref/libref3dworld.so, i.e. the UNMODIFIED reference
+objects (src/mesh_gen.cpp, src/erosion.cpp, src/upsurface.cpp, vendored GLM) linked with the driver in oracle/refbuild/.
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import this."""
+import ctypes as C
+import os
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "_ref", "libref3dworld.so")
+
+HMAP_DEFAULT = [1000.0, 0, 0, 0, 1000.0, 0, 0, 0, 0, 0, 0, 0, 0, 0]  # hmap_params_t defaults, src/mesh.h:85-88
+HMAP_FIELDS = ["plat_bot", "plat_h", "plat_s", "plat_max", "crat_h", "crat_s", "crack_lo", "crack_hi", "crack_d",
+               "sine_mag", "sine_freq", "sine_bias", "volcano_width", "volcano_height"]
+
+
+class Scene(C.Structure):
+    _fields_ = [("mesh_x", C.c_int), ("mesh_y", C.c_int), ("mesh_z", C.c_int),
+                ("xss", C.c_float), ("yss", C.c_float), ("zss", C.c_float),
+                ("mesh_scale", C.c_float), ("mesh_height_scale", C.c_float),
+                ("gen_mode", C.c_int), ("gen_shape", C.c_int), ("freq_filter", C.c_int), ("seed", C.c_int),
+                ("rgen_index", C.c_int), ("glaciate", C.c_int), ("custom_glaciate_exp", C.c_float),
+                ("hmap", C.c_float * 14), ("zmax_est", C.c_float), ("mesh_scale_z", C.c_float)]
+
+
+class Erosion(C.Structure):
+    _fields_ = [(n, C.c_float) for n in ("erode_amount", "water_plane_z", "half_dxy", "zmin", "zmax", "relh_adj_tex", "clip_hd1")]
+
+
+def available():
+    return os.path.exists(LIB_PATH)
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        L = C.CDLL(LIB_PATH)
+        fp = C.POINTER(C.c_float)
+        L.ref_setup.argtypes = [C.POINTER(Scene), C.c_int]
+        L.ref_get_start_eval_sin.restype = C.c_int
+        for n in ("ref_get_dx", "ref_get_dy", "ref_get_mesh_height", "ref_get_half_dxy", "ref_get_zmax_est", "ref_get_water_z_height"):
+            getattr(L, n).restype = C.c_float
+        L.ref_set_zmax_est.argtypes = [C.c_float]
+        L.ref_set_start_eval_sin.argtypes = [C.c_int]
+        L.ref_get_max_threads.restype = C.c_int
+        L.ref_heightgen.argtypes = [C.c_float] * 4 + [C.c_uint, C.c_uint, C.c_int, C.c_int, C.c_int, C.c_void_p]
+        L.ref_get_noise_zval.argtypes = [C.c_float, C.c_float, C.c_int, C.c_int]
+        L.ref_get_noise_zval.restype = C.c_float
+        L.ref_eval_mesh_sin_terms.argtypes = [C.c_float, C.c_float]
+        L.ref_eval_mesh_sin_terms.restype = C.c_float
+        for n, k in (("ref_glm_simplex2", 2), ("ref_glm_perlin2", 2), ("ref_glm_simplex3", 3), ("ref_glm_perlin3", 3)):
+            getattr(L, n).argtypes = [C.c_float] * k
+            getattr(L, n).restype = C.c_float
+        L.ref_apply_erosion.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_uint, C.POINTER(Erosion)]
+        L.ref_noise3d_rdata.argtypes = [C.c_int, C.c_int, C.c_float, C.c_float, C.c_void_p]
+        L.ref_noise3d_point.argtypes = [C.c_int, C.c_int] + [C.c_float] * 5
+        L.ref_noise3d_point.restype = C.c_float
+        L.ref_voxel_fill.argtypes = [C.c_uint] * 3 + [C.c_void_p] * 3 + [C.c_float, C.c_float, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p]
+        L.ref_get_rx_ry.argtypes = [fp, fp]
+        _lib = L
+    return _lib
+
+
+def setup(mesh=(128, 128, 1), scene=(4.0, 4.0, 4.0), mesh_scale=1.0, mesh_height_scale=1.0, mode=0, shape=0, freq_filter=2,
+          seed=0, rgen_index=0, glaciate=1, custom_glaciate_exp=0.0, hmap=None, zmax_est=0.0, mesh_scale_z=1.0, gen_sine_table=True):
+    s = Scene()
+    s.mesh_x, s.mesh_y, s.mesh_z = mesh
+    s.xss, s.yss, s.zss = scene
+    s.mesh_scale, s.mesh_height_scale = mesh_scale, mesh_height_scale
+    s.gen_mode, s.gen_shape, s.freq_filter, s.seed, s.rgen_index, s.glaciate = mode, shape, freq_filter, seed, rgen_index, glaciate
+    s.custom_glaciate_exp = custom_glaciate_exp
+    h = list(HMAP_DEFAULT)
+    if hmap:
+        for k, v in hmap.items():
+            h[HMAP_FIELDS.index(k)] = v
+    for i, v in enumerate(h):
+        s.hmap[i] = v
+    s.zmax_est, s.mesh_scale_z = zmax_est, mesh_scale_z
+    lib().ref_setup(C.byref(s), int(gen_sine_table))
+    return s
+
+
+def sin_table():
+    out = np.empty(65536, np.float32)
+    lib().ref_get_sin_table(out.ctypes.data_as(C.c_void_p))
+    return out
+
+
+def sine_params():
+    out = np.empty((90, 5), np.float32)
+    lib().ref_get_sine_params(out.ctypes.data_as(C.c_void_p))
+    return out
+
+
+def set_sine_params(p):
+    p = np.ascontiguousarray(p, np.float32)
+    assert p.shape == (90, 5)
+    lib().ref_set_sine_params(p.ctypes.data_as(C.c_void_p))
+
+
+def rx_ry():
+    rx, ry = C.c_float(), C.c_float()
+    lib().ref_get_rx_ry(C.byref(rx), C.byref(ry))
+    return rx.value, ry.value
+
+
+def heightgen(x0, y0, dx, dy, nx, ny, cache_values=0, glaciate=1, min_start_sin=0):
+    out = np.empty((ny, nx), np.float32)
+    lib().ref_heightgen(x0, y0, dx, dy, nx, ny, cache_values, glaciate, min_start_sin, out.ctypes.data_as(C.c_void_p))
+    return out
+
+
+def apply_erosion(h, min_zval, num_iters, erode_amount=1.0, water_plane_z=0.0, half_dxy=0.0625, zmin=-1.0, zmax=1.0, relh_adj_tex=0.0, clip_hd1=0.5):
+    h = np.array(h, np.float32, order="C", copy=True)
+    ys, xs = h.shape
+    p = Erosion(erode_amount, water_plane_z, half_dxy, zmin, zmax, relh_adj_tex, clip_hd1)
+    lib().ref_apply_erosion(h.ctypes.data_as(C.c_void_p), xs, ys, min_zval, num_iters, C.byref(p))
+    return h
+
+
+def noise3d_rdata(rs1, rs2, mag, freq):
+    out = np.empty(420, np.float32)
+    lib().ref_noise3d_rdata(rs1, rs2, mag, freq, out.ctypes.data_as(C.c_void_p))
+    return out
+
+
+def voxel_fill(nx, ny, nz, lo_pos, vsz, offset, mag, freq, normalize_to_1, rs1, rs2, gen_mode, zscale):
+    out = np.empty((ny, nx, nz), np.float32)
+    a = [np.asarray(v, np.float32) for v in (lo_pos, vsz, offset)]
+    lib().ref_voxel_fill(nx, ny, nz, *[v.ctypes.data_as(C.c_void_p) for v in a], mag, freq, int(normalize_to_1), rs1, rs2, gen_mode, zscale,
+                         out.ctypes.data_as(C.c_void_p))
+    return out
