@@ -1,0 +1,184 @@
+/* tw3d.h - C ABI of the B200-native terrain hot path (drop-in for fegennari/3DWorld's procedural height / erosion / voxel-density path).
+ *
+ * The reference has no FFI layer: its boundary is a C++ class + free-function surface. Every entry point below
+ * names the reference interface it replaces (file:line relative to the reference root). A C++ adapter that re-exposes the exact reference
+ * signatures (mesh_xy_grid_cache_t, apply_erosion, noise_gen_3d, voxel_manager::create_procedural) on top of this ABI lives in
+ * 3dworld_b200/host/tw3d_adapter.h; INTEGRATION.md shows the binding a 3DWorld maintainer would add.
+ *
+ * Conventions: plain pointers and sizes only; every function returns 0 (TW_OK) or a negative tw_status (no assert()/exit() as in the
+ * reference); data pointers may be HOST or DEVICE pointers (detected with cudaPointerGetAttributes) - host buffers are staged through
+ * pinned memory inside the call; all arithmetic is fp32 with the reference's rounding sequence (no FMA contraction where it could change a
+ * result), so outputs are bit-identical to the reference CPU path built with its makefile flags (-O3, no -march).
+ * There is NO CPU fallback: without a CUDA device tw_create fails with TW_ERR_NO_DEVICE.
+ */
+#ifndef TW3D_H
+#define TW3D_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TW_ABI_VERSION 1
+
+typedef enum tw_status {
+	TW_OK = 0,
+	TW_ERR_NO_DEVICE = -1,   /* no CUDA device / driver: the product path refuses to run (no CPU fallback) */
+	TW_ERR_CUDA      = -2,   /* a CUDA runtime call failed; see tw_last_error() */
+	TW_ERR_ARG       = -3,   /* invalid argument (the reference would assert) */
+	TW_ERR_STATE     = -4,   /* tables not set (tw_set_sin_table / tw_set_sine_params) */
+	TW_ERR_NOT_READY = -5    /* tw_heightgen_2d_poll: result not available yet (mirrors build_arrays() returning 0 with no_wait) */
+} tw_status;
+
+/* mesh_gen_mode values, src/3DWorld.h:1399 */
+enum { TW_MGEN_SINE = 0, TW_MGEN_SIMPLEX = 1, TW_MGEN_PERLIN = 2, TW_MGEN_SIMPLEX_GPU = 3, TW_MGEN_DWARP_GPU = 4 };
+
+#define TW_F_TABLE_SIZE   90      /* NUM_FREQ_COMP*N_RAND_SIN2, src/mesh_gen.cpp:14,16,30 */
+#define TW_SIN_TABLE_SIZE 65536   /* 2*TSIZE, src/sinf.h:8 */
+#define TW_N3D_RDATA      420     /* SINE_DATA_SIZE, src/upsurface.h:14-16 */
+#define TW_N3D_SINES      60      /* TOT_NUM_SINES */
+
+typedef struct tw_ctx tw_ctx;   /* one per (thread, device): owns a CUDA stream, the uploaded tables and scratch buffers */
+
+/* hmap_params_t, src/mesh.h:85-89 (same field order) */
+typedef struct tw_hmap_params {
+	float plat_bot, plat_h, plat_s, plat_max, crat_h, crat_s;
+	float crack_lo, crack_hi, crack_d, sine_mag, sine_freq, sine_bias, volcano_width, volcano_height;
+} tw_hmap_params;
+
+/* Every reference global the height path reads, as one explicit POD. */
+typedef struct tw_height_params {
+	int   gen_mode;            /* mesh_gen_mode (force_sine_mode => pass TW_MGEN_SINE) */
+	int   gen_shape;           /* mesh_gen_shape: 0 linear, 1 billowy, 2 ridged */
+	int   start_eval_sin;      /* compute_scale() result, src/mesh_gen.cpp:544-548 (tw_compute_scale) */
+	int   glaciate;            /* GLACIATE global: apply_glaciate() is a no-op when 0, src/mesh_gen.cpp:380-385 */
+	float mesh_scale;          /* mesh_scale */
+	float mesh_scale_z_inv;    /* mesh_scale_z_inv */
+	float dx_val_inv, dy_val_inv; /* DX_VAL_INV, DY_VAL_INV, src/matrix_ops.cpp:77-78 */
+	float mesh_height;         /* MESH_HEIGHT = 0.1*Z_SCENE_SIZE, src/matrix_ops.cpp:70 */
+	float mesh_height_scale;   /* mesh_height_scale */
+	float zmax_est;            /* zmax_est; zmax_est2 / zmax_est2_inv are derived exactly as set_zmax_est() does, src/mesh_gen.cpp:162-167 */
+	float custom_glaciate_exp; /* custom_glaciate_exp (0 => cube) */
+	float rx, ry;              /* gen_rx_ry() result, src/mesh_gen.cpp:581-586 (tw_gen_rx_ry); hoisted out of the per-cell loop */
+	tw_hmap_params hmap;       /* hmap_params */
+} tw_height_params;
+
+/* mesh_xy_grid_cache_t::build_arrays(x0,y0,dx,dy,nx,ny) arguments, src/mesh_gen.cpp:588 */
+typedef struct tw_grid2d {
+	float x0, y0, dx, dy;
+	uint32_t nx, ny;
+} tw_grid2d;
+
+typedef struct tw_minmax { float zmin, zmax; } tw_minmax;
+
+/* The scalars apply_erosion() reads from globals: erode_amount, water_plane_z, HALF_DXY (src/erosion.cpp:11,98) and, through
+ * get_bare_ls_tid() (src/Textures.cpp:1284-1287), zmin, zmax, relh_adj_tex, clip_hd1. */
+typedef struct tw_erosion_params {
+	float erode_amount, water_plane_z, half_dxy, zmin, zmax, relh_adj_tex, clip_hd1;
+} tw_erosion_params;
+
+/* voxel_grid geometry (src/voxels.cpp:91-108) + create_procedural() arguments (src/voxels.cpp:278) */
+typedef struct tw_voxel_params {
+	uint32_t nx, ny, nz;
+	float lo_pos[3], vsz[3], offset[3];
+	float mag, freq;
+	int   gen_mode;            /* TW_MGEN_SINE, TW_MGEN_SIMPLEX or TW_MGEN_PERLIN (GPU modes 3/4 evaluate the CPU simplex formula) */
+	int   normalize_to_1;
+	int   rseed1, rseed2;      /* noise_gen_3d seeds (sine mode) */
+	int   octaves;             /* max(1, MAX_FREQ_BINS - mesh_freq_filter), src/voxels.cpp:333 (GLM modes) */
+	float rx, ry;              /* gen_rx_ry() (GLM modes) */
+	float zscale;              /* (invert ? -1 : 1)*z_gradient/(nz-1), src/voxels.cpp:284 */
+	/* optional fused attenuation pass (src/voxels.cpp:403-482); atten_mode 0 = none, 1 = top only (atten_top_mode 0), 2 = 5 edges, 3/4/5 = sphere */
+	int   atten_mode;
+	float atten_val, atten_inner_radius;
+} tw_voxel_params;
+
+/* ---- context ---- */
+int  tw_abi_version(void);
+int  tw_create(int device, tw_ctx **out);
+void tw_destroy(tw_ctx *ctx);
+const char *tw_last_error(const tw_ctx *ctx);
+int  tw_sync(tw_ctx *ctx);                         /* cudaStreamSynchronize on the context stream */
+void *tw_stream(tw_ctx *ctx);                      /* the cudaStream_t all work of this context is issued on */
+uint64_t tw_launch_count(const tw_ctx *ctx);       /* kernels launched by this context so far (bench.py gpu_launches) */
+
+/* ---- host-side table generation (bit-exact restatements; tiny, run once) ---- */
+/* create_sin_table(), src/mesh_gen.cpp:72-81: tab[i]=sinf(i/sscale), tab[i+32768]=cosf(i/sscale) with the host libm. */
+void tw_build_sin_table(float *tab65536);
+/* compute_scale(), src/mesh_gen.cpp:544-548 */
+int  tw_compute_scale(float mesh_scale, int mesh_freq_filter);
+/* rand_gen_t state (src/rand_gen.h:29): pass the same object to successive tw_gen_sine_params calls to reproduce the reference's
+ * function-static generator (src/mesh_gen.cpp:237). Initial state {1,1}. */
+typedef struct tw_rng { int64_t rseed1, rseed2; } tw_rng;
+/* gen_rand_sine_table_entries() + apply_mesh_rand_seed(), src/mesh_gen.cpp:213-254 */
+void tw_gen_sine_params(tw_rng *rgen, float scaled_height, int mesh_x_size, int mesh_y_size, float x_scene_size, float y_scene_size,
+                        int mesh_seed, int mesh_rgen_index, int mesh_gen_mode, float mesh_start_mag, float mesh_start_freq,
+                        float mesh_mag_mult, float mesh_freq_mult, float *sine_params450);
+/* gen_rx_ry(), src/mesh_gen.cpp:581-586 */
+void tw_gen_rx_ry(int mesh_seed, int mesh_rgen_index, int mesh_gen_mode, float *rx, float *ry);
+/* noise_gen_3d::set_rand_seeds + gen_sines, src/upsurface.cpp:16-38 */
+void tw_noise3d_gen_sines(int rseed1, int rseed2, float mag, float freq, float *rdata420);
+/* get_water_z_height(), src/mesh_gen.cpp:507-512 (water_h_off/water_h_off_rel as arguments) */
+float tw_water_z_height(float zmax_est, int glaciate, float custom_glaciate_exp, float water_h_off, float water_h_off_rel);
+
+/* ---- table upload ---- */
+/* sin_table (src/sinf.h:11). tab==NULL: build with tw_build_sin_table. Also builds the 1e6-entry cos/sin direction table used by the
+ * erosion random-direction fallback (src/erosion.cpp:84-87) from the host libm so device results match the host bit for bit. */
+int tw_set_sin_table(tw_ctx *ctx, const float *tab65536);
+/* sinTable[90][5] (src/mesh_gen.cpp:40) */
+int tw_set_sine_params(tw_ctx *ctx, const float *sine_params450);
+
+/* ---- 2-D height generation: build_arrays + enable_glaciate + eval_index over the whole grid ----
+ * Replaces mesh_xy_grid_cache_t::{build_arrays,enable_glaciate,eval_index} (src/mesh.h:39-41, src/mesh_gen.cpp:588-650,754-792) as used by
+ * heightmap_t::proc_gen (src/heightmap.cpp:130-151), tile_t::create_zvals (src/tiled_mesh.cpp:467-515) and gen_mesh_sine_table
+ * (src/mesh_gen.cpp:201-210); for gen modes 3/4 it is the backend behind run_gpu_simplex/cache_gpu_simplex_vals (src/mesh_gen.cpp:652-695).
+ * out[y*nx + x] = eval_index(x, y, min_start_sin); mm (optional, host pointer) receives min/max over the grid (fused reduction). */
+int tw_heightgen_2d(tw_ctx *ctx, const tw_grid2d *grid, const tw_height_params *p, int enable_glaciate, int min_start_sin,
+                    float *out, tw_minmax *mm);
+/* Asynchronous pair mirroring the reference's no_wait contract (src/mesh_gen.cpp:597-603, src/tiled_mesh.cpp:2393-2402):
+ * launch returns immediately; poll returns TW_ERR_NOT_READY until the result (and host copy, if out is a host pointer) is complete. */
+int tw_heightgen_2d_launch(tw_ctx *ctx, const tw_grid2d *grid, const tw_height_params *p, int enable_glaciate, int min_start_sin,
+                           float *out, tw_minmax *mm);
+int tw_heightgen_2d_poll(tw_ctx *ctx, int wait);
+
+/* Batched tile form of tile_t::create_zvals' height fill (src/tiled_mesh.cpp:458-464,495-514): tile t covers
+ * build_arrays(origins[2t]-mesh_x_size/2, origins[2t+1]-mesh_y_size/2, dx, dy, zvsize, zvsize) with glaciate enabled;
+ * out[t*zvsize*zvsize + y*zvsize + x]. origins is a HOST array of ntiles (x1,y1) pairs. mm (optional, host) = ntiles entries. */
+int tw_heightgen_tiles(tw_ctx *ctx, const int32_t *origins_xy, uint32_t ntiles, int mesh_x_size, int mesh_y_size, float dx, float dy,
+                       uint32_t zvsize, const tw_height_params *p, float *out, tw_minmax *mm);
+
+/* ---- hydraulic erosion ----
+ * Replaces apply_erosion(float *heightmap, int xsize, int ysize, float min_zval, unsigned num_iters) (src/function_registry.h:354,
+ * src/erosion.cpp:14-164): in place, row-major x-fastest, droplets applied in the reference's serial order (iter = 0..num_iters-1;
+ * this is the OMP_NUM_THREADS=1 order, the only deterministic one - SURVEY.md section 0). Early-out as the reference when
+ * num_iters==0 or erode_amount<=0. */
+int tw_erode(tw_ctx *ctx, float *heightmap, int xsize, int ysize, float min_zval, uint32_t num_iters, const tw_erosion_params *p);
+/* The same on ntiles independent heightmaps stored back to back (tile_t::create_zvals semantics, src/tiled_mesh.cpp:515): every tile
+ * gets droplets 0..num_iters-1 exactly as a separate apply_erosion() call would. min_zvals: HOST array of ntiles values, or NULL to use
+ * min_zval_all for every tile. */
+int tw_erode_tiles(tw_ctx *ctx, float *heightmaps, uint32_t ntiles, int xsize, int ysize, const float *min_zvals, float min_zval_all,
+                   uint32_t num_iters, const tw_erosion_params *p);
+/* droplet steps executed by the last tw_erode/tw_erode_tiles call (sum over droplets; for roofline byte accounting) */
+uint64_t tw_last_erosion_steps(const tw_ctx *ctx);
+
+/* ---- 3-D voxel density ----
+ * Replaces the fill loop of voxel_manager::create_procedural (src/voxels.cpp:278-346) + noise_gen_3d::{gen_xyz_vals,get_val}
+ * (src/upsurface.cpp:41-70); out[z + (x + y*nx)*nz] (src/voxels.h:141-144). rdata420: noise_gen_3d::rdata (sine mode; host pointer;
+ * NULL => generated from rseed1/rseed2/mag/freq with tw_noise3d_gen_sines). */
+int tw_voxel_fill(tw_ctx *ctx, const tw_voxel_params *vp, const float *rdata420, float *out);
+
+/* ---- next rows: heightmap quantise, fused streaming passes ----
+ * heightmap_t::from_floats 16-bit pack (src/heightmap.cpp:205-215, src/Textures.cpp:1889-1893): v=(h-add)*(1/mult);
+ * out[2i+1]=trunc(v), out[2i]=trunc(256*(v-trunc(v))). Returns TW_ERR_ARG if any v is outside [0,256) (the reference asserts). */
+int tw_heightmap_from_floats_u16(tw_ctx *ctx, const float *vals, size_t n, float val_mult, float val_add, uint8_t *out2n);
+/* heightmap_t::to_floats 16-bit unpack (src/heightmap.cpp:191-203) */
+int tw_heightmap_to_floats_u16(tw_ctx *ctx, const uint8_t *data2n, size_t n, float val_mult, float val_add, float *vals);
+/* min/max over a float array (get_heightmap_z_range, src/map_view.cpp:399-407) */
+int tw_minmax_f32(tw_ctx *ctx, const float *vals, size_t n, tw_minmax *mm);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TW3D_H */

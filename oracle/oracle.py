@@ -1,0 +1,179 @@
+"""TEST INFRASTRUCTURE ONLY. ctypes wrapper around oracle/_build/libterrain_oracle.so (the plain-C restatement of the
+reference terrain hot path, see terrain_oracle.h). Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+--impl reference legs may import this; the product package never does."""
+import ctypes as C
+import os
+import subprocess
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "_build", "libterrain_oracle.so")
+
+
+# ---- POD mirrors of include/tw3d.h (types only) ----
+class HmapParams(C.Structure):
+    _fields_ = [(n, C.c_float) for n in ("plat_bot", "plat_h", "plat_s", "plat_max", "crat_h", "crat_s", "crack_lo", "crack_hi",
+                                         "crack_d", "sine_mag", "sine_freq", "sine_bias", "volcano_width", "volcano_height")]
+
+
+class HeightParams(C.Structure):
+    _fields_ = [("gen_mode", C.c_int), ("gen_shape", C.c_int), ("start_eval_sin", C.c_int), ("glaciate", C.c_int),
+                ("mesh_scale", C.c_float), ("mesh_scale_z_inv", C.c_float), ("dx_val_inv", C.c_float), ("dy_val_inv", C.c_float),
+                ("mesh_height", C.c_float), ("mesh_height_scale", C.c_float), ("zmax_est", C.c_float),
+                ("custom_glaciate_exp", C.c_float), ("rx", C.c_float), ("ry", C.c_float), ("hmap", HmapParams)]
+
+
+class Grid2D(C.Structure):
+    _fields_ = [("x0", C.c_float), ("y0", C.c_float), ("dx", C.c_float), ("dy", C.c_float), ("nx", C.c_uint32), ("ny", C.c_uint32)]
+
+
+class MinMax(C.Structure):
+    _fields_ = [("zmin", C.c_float), ("zmax", C.c_float)]
+
+
+class ErosionParams(C.Structure):
+    _fields_ = [(n, C.c_float) for n in ("erode_amount", "water_plane_z", "half_dxy", "zmin", "zmax", "relh_adj_tex", "clip_hd1")]
+
+
+class VoxelParams(C.Structure):
+    _fields_ = [("nx", C.c_uint32), ("ny", C.c_uint32), ("nz", C.c_uint32),
+                ("lo_pos", C.c_float * 3), ("vsz", C.c_float * 3), ("offset", C.c_float * 3),
+                ("mag", C.c_float), ("freq", C.c_float), ("gen_mode", C.c_int), ("normalize_to_1", C.c_int),
+                ("rseed1", C.c_int), ("rseed2", C.c_int), ("octaves", C.c_int), ("rx", C.c_float), ("ry", C.c_float),
+                ("zscale", C.c_float), ("atten_mode", C.c_int), ("atten_val", C.c_float), ("atten_inner_radius", C.c_float)]
+
+
+class Rng(C.Structure):
+    _fields_ = [("rseed1", C.c_int64), ("rseed2", C.c_int64)]
+
+
+def hmap_params(**kw):
+    h = HmapParams(1000.0, 0, 0, 0, 1000.0, 0, 0, 0, 0, 0, 0, 0, 0, 0)  # hmap_params_t defaults, src/mesh.h:85-88
+    for k, v in kw.items():
+        setattr(h, k, v)
+    return h
+
+
+def build(force=False):
+    if force or not os.path.exists(LIB_PATH) or os.path.getmtime(LIB_PATH) < os.path.getmtime(os.path.join(_HERE, "terrain_oracle.c")):
+        subprocess.check_call(["bash", os.path.join(_HERE, "build_oracle.sh")], stdout=subprocess.DEVNULL)
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        L = C.CDLL(LIB_PATH)
+        vp = C.c_void_p
+        L.to_rng_rand.argtypes = [C.POINTER(Rng)]
+        L.to_rng_rand.restype = C.c_int
+        L.to_rng_randd.argtypes = [C.POINTER(Rng)]
+        L.to_rng_randd.restype = C.c_double
+        L.to_rng_rand_float.argtypes = [C.POINTER(Rng)]
+        L.to_rng_rand_float.restype = C.c_float
+        L.to_build_sin_table.argtypes = [vp]
+        L.to_compute_scale.argtypes = [C.c_float, C.c_int]
+        L.to_compute_scale.restype = C.c_int
+        L.to_gen_sine_params.argtypes = [C.POINTER(Rng), C.c_float, C.c_int, C.c_int, C.c_float, C.c_float, C.c_int, C.c_int, C.c_int,
+                                         C.c_float, C.c_float, C.c_float, C.c_float, vp]
+        L.to_gen_rx_ry.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float)]
+        L.to_water_z_height.argtypes = [C.c_float, C.c_int, C.c_float, C.c_float, C.c_float]
+        L.to_water_z_height.restype = C.c_float
+        for n, k in (("to_simplex2", 2), ("to_perlin2", 2), ("to_simplex3", 3), ("to_perlin3", 3)):
+            getattr(L, n).argtypes = [C.c_float] * k
+            getattr(L, n).restype = C.c_float
+        L.to_get_noise_zval.argtypes = [C.c_float, C.c_float, C.POINTER(HeightParams)]
+        L.to_get_noise_zval.restype = C.c_float
+        L.to_eval_mesh_sin_terms.argtypes = [C.c_float, C.c_float, vp, vp, C.c_int]
+        L.to_eval_mesh_sin_terms.restype = C.c_float
+        L.to_heightgen_2d.argtypes = [C.POINTER(Grid2D), C.POINTER(HeightParams), vp, vp, C.c_int, C.c_int, vp, C.c_int]
+        L.to_apply_erosion.argtypes = [vp, C.c_int, C.c_int, C.c_float, C.c_uint, C.POINTER(ErosionParams)]
+        L.to_apply_erosion.restype = C.c_ulonglong
+        L.to_noise3d_gen_sines.argtypes = [C.c_int, C.c_int, C.c_float, C.c_float, vp]
+        L.to_noise3d_get_val_pt.argtypes = [vp, vp, C.c_float, C.c_float, C.c_float]
+        L.to_noise3d_get_val_pt.restype = C.c_float
+        L.to_voxel_fill.argtypes = [C.POINTER(VoxelParams), vp, vp, vp, C.c_int]
+        L.to_from_floats_u16.argtypes = [vp, C.c_size_t, C.c_float, C.c_float, vp]
+        L.to_from_floats_u16.restype = C.c_size_t
+        L.to_to_floats_u16.argtypes = [vp, C.c_size_t, C.c_float, C.c_float, vp]
+        _lib = L
+    return _lib
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+_SIN_TABLE = None
+
+
+def sin_table():
+    global _SIN_TABLE
+    if _SIN_TABLE is None:
+        t = np.empty(65536, np.float32)
+        lib().to_build_sin_table(_p(t))
+        _SIN_TABLE = t
+    return _SIN_TABLE
+
+
+def compute_scale(mesh_scale, freq_filter):
+    return lib().to_compute_scale(mesh_scale, freq_filter)
+
+
+def gen_sine_params(scaled_height, mesh=(128, 128), scene=(4.0, 4.0), seed=0, rgen_index=0, mode=0, rng=None,
+                    start_mag=0.02, start_freq=240.0, mag_mult=2.0, freq_mult=0.5):
+    rng = rng if rng is not None else Rng(1, 1)
+    out = np.empty((90, 5), np.float32)
+    lib().to_gen_sine_params(C.byref(rng), scaled_height, mesh[0], mesh[1], scene[0], scene[1], seed, rgen_index, mode,
+                             start_mag, start_freq, mag_mult, freq_mult, _p(out))
+    return out
+
+
+def gen_rx_ry(seed, rgen_index, mode):
+    rx, ry = C.c_float(), C.c_float()
+    lib().to_gen_rx_ry(seed, rgen_index, mode, C.byref(rx), C.byref(ry))
+    return rx.value, ry.value
+
+
+def heightgen_2d(grid, hp, sine_params=None, enable_glaciate=1, min_start_sin=0, nthreads=0):
+    out = np.empty((grid.ny, grid.nx), np.float32)
+    sp = np.ascontiguousarray(sine_params if sine_params is not None else np.zeros((90, 5)), np.float32)
+    lib().to_heightgen_2d(C.byref(grid), C.byref(hp), _p(sin_table()), _p(sp), int(enable_glaciate), int(min_start_sin), _p(out), nthreads)
+    return out
+
+
+def apply_erosion(h, min_zval, num_iters, ep):
+    h = np.array(h, np.float32, order="C", copy=True)
+    ys, xs = h.shape
+    steps = lib().to_apply_erosion(_p(h), xs, ys, min_zval, num_iters, C.byref(ep))
+    return h, int(steps)
+
+
+def noise3d_gen_sines(rs1, rs2, mag, freq):
+    out = np.empty(420, np.float32)
+    lib().to_noise3d_gen_sines(rs1, rs2, mag, freq, _p(out))
+    return out
+
+
+def voxel_fill(vp, rdata=None, nthreads=0):
+    out = np.empty((vp.ny, vp.nx, vp.nz), np.float32)
+    rd = None if rdata is None else np.ascontiguousarray(rdata, np.float32)
+    lib().to_voxel_fill(C.byref(vp), None if rd is None else _p(rd), _p(sin_table()), _p(out), nthreads)
+    return out
+
+
+def from_floats_u16(vals, val_mult, val_add):
+    vals = np.ascontiguousarray(vals, np.float32).ravel()
+    out = np.empty(2 * vals.size, np.uint8)
+    bad = lib().to_from_floats_u16(_p(vals), vals.size, val_mult, val_add, _p(out))
+    return out, int(bad)
+
+
+def to_floats_u16(data, val_mult, val_add):
+    data = np.ascontiguousarray(data, np.uint8).ravel()
+    out = np.empty(data.size // 2, np.float32)
+    lib().to_to_floats_u16(_p(data), out.size, val_mult, val_add, _p(out))
+    return out

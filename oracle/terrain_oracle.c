@@ -1,0 +1,688 @@
+/* TEST INFRASTRUCTURE ONLY - see terrain_oracle.h. CPU restatement of the reference terrain hot path, pinned bit-for-bit against
+ * the unmodified reference objects (oracle/_ref). Build: gcc -O2 -ffp-contract=off -fno-fast-math -fopenmp -shared -fPIC.
+ * "ref:" comments give the reference file:line (relative to the 3DWorld root) each block follows. */
+#include "terrain_oracle.h"
+#include <math.h>
+#include <float.h>
+#include <stdlib.h>
+#include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+/* ------------------------------------------------------------------ RNG (ref: src/rand_gen.h:22-26) */
+static void rng_step(tw_rng *r) {
+	long s1 = (long)r->rseed1, s2 = (long)r->rseed2;
+	if ((s1 = 40014*(s1%53668) - 12211*(s1/53668)) < 0) s1 += 2147483563;
+	if ((s2 = 40692*(s2%52774) - 3791 *(s2/52774)) < 0) s2 += 2147483399;
+	r->rseed1 = s1; r->rseed2 = s2;
+}
+void to_rng_set(tw_rng *r, long s1, long s2) {r->rseed1 = s1; r->rseed2 = s2;}
+int to_rng_rand(tw_rng *r) { /* ref: src/rand_gen.h:66-70, T=int */
+	rng_step(r);
+	int v = (int)r->rseed1 - (int)r->rseed2;
+	if (v < 1) v += 2147483562;
+	return v;
+}
+double to_rng_randd(tw_rng *r) { /* ref: src/gen_object.cpp:377-381, T=double */
+	rng_step(r);
+	double v = (double)r->rseed1 - (double)r->rseed2;
+	if (v < 1) v += 2147483562;
+	return v/2147483563.;
+}
+float to_rng_rand_float(tw_rng *r) {return (float)(0.000001*(to_rng_rand(r)%1000000));} /* ref: src/rand_gen.h:86 */
+float to_rng_rand_uniform(tw_rng *r, float a, float b) {return a + (b - a)*(float)to_rng_randd(r);} /* ref: src/rand_gen.h:90 */
+
+/* ------------------------------------------------------------------ sin table (ref: src/sinf.h:8-20, src/mesh_gen.cpp:72-81) */
+#define TSIZE 32768
+static const float PI_F = 3.141592654f;                 /* ref: src/3DWorld.h:43 */
+static float two_pi(void) {return (float)(2.0*PI_F);}   /* ref: src/3DWorld.h:129 */
+static float sscale_f(void) {return (float)TSIZE/two_pi();} /* ref: src/sinf.h:9 */
+
+void to_build_sin_table(float *tab) {
+	float const sscale = sscale_f();
+	for (unsigned i = 0; i < TSIZE; ++i) {
+		tab[i]       = sinf((float)i/sscale);
+		tab[i+TSIZE] = cosf((float)i/sscale);
+	}
+}
+float to_sinf_lut(const float *tab, float v) {
+	float const sscale = sscale_f();
+	return (v < 0) ? -tab[((int)(sscale*(-v)))&(TSIZE-1)] : tab[((int)(sscale*v))&(TSIZE-1)];
+}
+float to_cosf_lut(const float *tab, float v) {
+	float const sscale = sscale_f();
+	return tab[TSIZE + (((int)(sscale*fabsf(v)))&(TSIZE-1))];
+}
+
+/* ------------------------------------------------------------------ host-side parameter generation */
+int to_compute_scale(float mesh_scale, int mesh_freq_filter) { /* ref: src/mesh_gen.cpp:544-548 */
+	int const iscale = (int)log2f(mesh_scale);
+	int v = iscale + mesh_freq_filter;
+	if (v > 9-3) v = 9-3;
+	if (v < 0) v = 0;
+	return 10*v;
+}
+
+static void apply_mesh_rand_seed(tw_rng *r, int mesh_seed, int mesh_rgen_index, int mode) { /* ref: src/mesh_gen.cpp:213-216 */
+	if (mesh_seed != 0) {to_rng_set(r, mesh_seed, 12345);}
+	else if (mode != TW_MGEN_SINE) {to_rng_set(r, mesh_rgen_index+1, 12345);}
+}
+
+void to_gen_sine_params(tw_rng *rgen, float scaled_height, int MX, int MY, float XSS, float YSS, int mesh_seed, int mesh_rgen_index,
+	int mode, float start_mag, float start_freq, float mag_mult, float freq_mult, float *T) /* ref: src/mesh_gen.cpp:219-254 */
+{
+	float xf_scale = (float)MY/(float)MX, yf_scale = (float)(1.0/xf_scale);
+	if (XSS > YSS) yf_scale *= (float)YSS/(float)XSS;
+	if (YSS > XSS) xf_scale *= (float)XSS/(float)YSS;
+	float mags[9], freqs[9];
+	freqs[0] = start_freq; mags[0] = start_mag;
+	for (int i = 1; i < 9; ++i) {freqs[i] = freqs[i-1]*freq_mult; mags[i] = mags[i-1]*mag_mult;}
+	float const mesh_h = (float)(scaled_height/sqrt(0.1*10));
+	apply_mesh_rand_seed(rgen, mesh_seed, mesh_rgen_index, mode);
+	for (int l = 0; l < 9; ++l) {
+		float const x_freq = freqs[l]/((float)MX), y_freq = freqs[l]/((float)MY);
+		float const mheight = mags[l]*mesh_h;
+		for (int i = 0; i < 10; ++i) {
+			float *e = T + 5*(l*10 + i);
+			e[0] = to_rng_rand_uniform(rgen, 0.2f, 1.0f)*mheight;
+			e[1] = to_rng_rand_float(rgen)*two_pi();
+			e[2] = to_rng_rand_float(rgen)*two_pi();
+			e[3] = to_rng_rand_uniform(rgen, 0.1f, 1.0f)*x_freq*yf_scale;
+			e[4] = to_rng_rand_uniform(rgen, 0.1f, 1.0f)*y_freq*xf_scale;
+		}
+	}
+}
+
+void to_gen_rx_ry(int mesh_seed, int mesh_rgen_index, int mode, float *rx, float *ry) { /* ref: src/mesh_gen.cpp:581-586 */
+	tw_rng r; to_rng_set(&r, 1, 1);
+	apply_mesh_rand_seed(&r, mesh_seed, mesh_rgen_index, mode);
+	*rx = (float)(to_rng_rand_float(&r) + 1.0);
+	*ry = (float)(to_rng_rand_float(&r) + 1.0);
+}
+
+static float do_glaciate_exp(float v, float custom) {return (custom == 0.0f) ? v*v*v : powf(v, custom);} /* ref: src/mesh_gen.cpp:358-360 */
+
+float to_water_z_height(float zmax_est, int glaciate, float custom, float water_h_off, float water_h_off_rel) { /* ref: src/mesh_gen.cpp:362,507-512 */
+	float t = 0.42f + water_h_off_rel;                   /* W_PLANE_Z */
+	float wpz = (t < 1.0f) ? t : 1.0f; wpz = (0.0f < wpz) ? wpz : 0.0f; /* CLIP_TO_01 = max(0.0f, min(1.0f, x)) */
+	if (glaciate) {wpz = do_glaciate_exp(wpz, custom);}
+	float const zmax_est2 = (float)(2.0*zmax_est);
+	return wpz*zmax_est2 - zmax_est + water_h_off;
+}
+
+/* ------------------------------------------------------------------ GLM noise (ref: dependencies/glm/glm/detail/_noise.hpp:15-84) */
+static inline float mod289f(float x) {return x - floorf(x*(1.0f/289.0f))*289.0f;}
+static inline float permutef(float x) {return mod289f(((x*34.0f) + 1.0f)*x);}
+static inline float tinvsqrt(float r) {return 1.79284291400159f - 0.85373472095314f*r;}
+static inline float fadef(float t) {return (t*t*t)*(t*(t*6.0f - 15.0f) + 10.0f);}
+static inline float glm_modf(float a, float b) {return a - b*floorf(a/b);}     /* ref: detail/func_common.inl:216 */
+static inline float fractf(float x) {return x - floorf(x);}                     /* ref: detail/func_common.inl:188 */
+static inline float mixf(float x, float y, float a) {return x + a*(y - x);}      /* ref: detail/func_common.inl:129 */
+static inline float glm_max(float x, float y) {return (x < y) ? y : x;}          /* ref: detail/func_common.inl:28 */
+static inline float glm_min(float x, float y) {return (y < x) ? y : x;}          /* ref: detail/func_common.inl:19 */
+static inline float glm_step(float edge, float x) {return (x < edge) ? 0.0f : 1.0f;} /* ref: detail/func_common.inl:252,545 */
+
+float to_simplex2(float vx, float vy) { /* ref: gtc/noise.inl:592-646 */
+	float const Cx = 0.211324865405187f, Cy = 0.366025403784439f, Cz = -0.577350269189626f, Cw = 0.024390243902439f;
+	float const s = vx*Cy + vy*Cy;
+	float ix = floorf(vx + s), iy = floorf(vy + s);
+	float const t = ix*Cx + iy*Cx;
+	float const x0x = vx - ix + t, x0y = vy - iy + t;
+	float const i1x = (x0x > x0y) ? 1.0f : 0.0f, i1y = (x0x > x0y) ? 0.0f : 1.0f;
+	float x12x = x0x + Cx, x12y = x0y + Cx, x12z = x0x + Cz, x12w = x0y + Cz;
+	x12x = x12x - i1x; x12y = x12y - i1y;
+	ix = glm_modf(ix, 289.0f); iy = glm_modf(iy, 289.0f);
+	float const q0 = permutef(iy + 0.0f), q1 = permutef(iy + i1y), q2 = permutef(iy + 1.0f);
+	float const p0 = permutef(q0 + ix + 0.0f), p1 = permutef(q1 + ix + i1x), p2 = permutef(q2 + ix + 1.0f);
+	float m0 = glm_max(0.5f - (x0x*x0x + x0y*x0y), 0.0f);
+	float m1 = glm_max(0.5f - (x12x*x12x + x12y*x12y), 0.0f);
+	float m2 = glm_max(0.5f - (x12z*x12z + x12w*x12w), 0.0f);
+	m0 = m0*m0; m1 = m1*m1; m2 = m2*m2;
+	m0 = m0*m0; m1 = m1*m1; m2 = m2*m2;
+	float const X0 = 2.0f*fractf(p0*Cw) - 1.0f, X1 = 2.0f*fractf(p1*Cw) - 1.0f, X2 = 2.0f*fractf(p2*Cw) - 1.0f;
+	float const h0 = fabsf(X0) - 0.5f, h1 = fabsf(X1) - 0.5f, h2 = fabsf(X2) - 0.5f;
+	float const ox0 = floorf(X0 + 0.5f), ox1 = floorf(X1 + 0.5f), ox2 = floorf(X2 + 0.5f);
+	float const a00 = X0 - ox0, a01 = X1 - ox1, a02 = X2 - ox2;
+	m0 *= 1.79284291400159f - 0.85373472095314f*(a00*a00 + h0*h0);
+	m1 *= 1.79284291400159f - 0.85373472095314f*(a01*a01 + h1*h1);
+	m2 *= 1.79284291400159f - 0.85373472095314f*(a02*a02 + h2*h2);
+	float const gx = a00*x0x + h0*x0y, gy = a01*x12x + h1*x12y, gz = a02*x12z + h2*x12w;
+	return 130.0f*(m0*gx + m1*gy + m2*gz);
+}
+
+float to_perlin2(float Px, float Py) { /* ref: gtc/noise.inl:25-62 */
+	float const flx = floorf(Px), fly = floorf(Py);
+	float Pix = flx + 0.0f, Piy = fly + 0.0f, Piz = flx + 1.0f, Piw = fly + 1.0f;
+	float const frx = fractf(Px), fry = fractf(Py);
+	float const Pfx = frx - 0.0f, Pfy = fry - 0.0f, Pfz = frx - 1.0f, Pfw = fry - 1.0f;
+	Pix = glm_modf(Pix, 289.0f); Piy = glm_modf(Piy, 289.0f); Piz = glm_modf(Piz, 289.0f); Piw = glm_modf(Piw, 289.0f);
+	float const ix[4] = {Pix, Piz, Pix, Piz}, iy[4] = {Piy, Piy, Piw, Piw};
+	float const fx[4] = {Pfx, Pfz, Pfx, Pfz}, fy[4] = {Pfy, Pfy, Pfw, Pfw};
+	float gx[4], gy[4];
+	for (int k = 0; k < 4; ++k) {
+		float const i = permutef(permutef(ix[k]) + iy[k]);
+		float g = 2.0f*fractf(i/41.0f) - 1.0f;
+		gy[k] = fabsf(g) - 0.5f;
+		float const tx = floorf(g + 0.5f);
+		gx[k] = g - tx;
+	}
+	/* g00=(gx0,gy0) g10=(gx1,gy1) g01=(gx2,gy2) g11=(gx3,gy3); norm = (g00,g01,g10,g11) */
+	float const n_00 = tinvsqrt(gx[0]*gx[0] + gy[0]*gy[0]), n_01 = tinvsqrt(gx[2]*gx[2] + gy[2]*gy[2]);
+	float const n_10 = tinvsqrt(gx[1]*gx[1] + gy[1]*gy[1]), n_11 = tinvsqrt(gx[3]*gx[3] + gy[3]*gy[3]);
+	float const g00x = gx[0]*n_00, g00y = gy[0]*n_00, g01x = gx[2]*n_01, g01y = gy[2]*n_01;
+	float const g10x = gx[1]*n_10, g10y = gy[1]*n_10, g11x = gx[3]*n_11, g11y = gy[3]*n_11;
+	float const n00 = g00x*fx[0] + g00y*fy[0];
+	float const n10 = g10x*fx[1] + g10y*fy[1];
+	float const n01 = g01x*fx[2] + g01y*fy[2];
+	float const n11 = g11x*fx[3] + g11y*fy[3];
+	float const fdx = fadef(Pfx), fdy = fadef(Pfy);
+	float const nx0 = mixf(n00, n10, fdx), nx1 = mixf(n01, n11, fdx);
+	float const nxy = mixf(nx0, nx1, fdy);
+	return 2.3f*nxy;
+}
+
+float to_perlin3(float Px, float Py, float Pz) { /* ref: gtc/noise.inl:66-133 */
+	float P[3] = {Px, Py, Pz}, Pi0[3], Pi1[3], Pf0[3], Pf1[3];
+	for (int d = 0; d < 3; ++d) {
+		float const fl = floorf(P[d]);
+		Pi0[d] = mod289f(fl); Pi1[d] = mod289f(fl + 1.0f);
+		Pf0[d] = fractf(P[d]); Pf1[d] = Pf0[d] - 1.0f;
+	}
+	float const ix[4] = {Pi0[0], Pi1[0], Pi0[0], Pi1[0]}, iy[4] = {Pi0[1], Pi0[1], Pi1[1], Pi1[1]};
+	float g0[4][3], g1[4][3]; /* [corner][x,y,z] for z0 and z1 planes; corner order 000,100,010,110 */
+	for (int k = 0; k < 4; ++k) {
+		float const ixy = permutef(permutef(ix[k]) + iy[k]);
+		for (int zz = 0; zz < 2; ++zz) {
+			float const ixyz = permutef(ixy + (zz ? Pi1[2] : Pi0[2]));
+			float gx = ixyz*(float)(1.0/7.0);
+			float gy = fractf(floorf(gx)*(float)(1.0/7.0)) - 0.5f;
+			gx = fractf(gx);
+			float const gz = 0.5f - fabsf(gx) - fabsf(gy);
+			float const sz = glm_step(gz, 0.0f);
+			gx -= sz*(glm_step(0.0f, gx) - 0.5f);
+			gy -= sz*(glm_step(0.0f, gy) - 0.5f);
+			float *g = zz ? g1[k] : g0[k];
+			g[0] = gx; g[1] = gy; g[2] = gz;
+		}
+	}
+	/* norm0 = taylorInvSqrt(dot(g000),dot(g010),dot(g100),dot(g110)) - each corner scaled by its own norm */
+	for (int k = 0; k < 4; ++k) {
+		float *g = g0[k]; float n = tinvsqrt(g[0]*g[0] + g[1]*g[1] + g[2]*g[2]); g[0] *= n; g[1] *= n; g[2] *= n;
+		g = g1[k];        n = tinvsqrt(g[0]*g[0] + g[1]*g[1] + g[2]*g[2]);       g[0] *= n; g[1] *= n; g[2] *= n;
+	}
+	float const n000 = g0[0][0]*Pf0[0] + g0[0][1]*Pf0[1] + g0[0][2]*Pf0[2];
+	float const n100 = g0[1][0]*Pf1[0] + g0[1][1]*Pf0[1] + g0[1][2]*Pf0[2];
+	float const n010 = g0[2][0]*Pf0[0] + g0[2][1]*Pf1[1] + g0[2][2]*Pf0[2];
+	float const n110 = g0[3][0]*Pf1[0] + g0[3][1]*Pf1[1] + g0[3][2]*Pf0[2];
+	float const n001 = g1[0][0]*Pf0[0] + g1[0][1]*Pf0[1] + g1[0][2]*Pf1[2];
+	float const n101 = g1[1][0]*Pf1[0] + g1[1][1]*Pf0[1] + g1[1][2]*Pf1[2];
+	float const n011 = g1[2][0]*Pf0[0] + g1[2][1]*Pf1[1] + g1[2][2]*Pf1[2];
+	float const n111 = g1[3][0]*Pf1[0] + g1[3][1]*Pf1[1] + g1[3][2]*Pf1[2];
+	float const fx = fadef(Pf0[0]), fy = fadef(Pf0[1]), fz = fadef(Pf0[2]);
+	float const nz0 = mixf(n000, n001, fz), nz1 = mixf(n100, n101, fz), nz2 = mixf(n010, n011, fz), nz3 = mixf(n110, n111, fz);
+	float const nyz0 = mixf(nz0, nz2, fy), nyz1 = mixf(nz1, nz3, fy);
+	return 2.2f*mixf(nyz0, nyz1, fx);
+}
+
+float to_simplex3(float vx, float vy, float vz) { /* ref: gtc/noise.inl:649-721 */
+	float const Cx = (float)(1.0/6.0), Cy = (float)(1.0/3.0);
+	float const Dx = 0.0f, Dy = 0.5f, Dz = 1.0f, Dw = 2.0f;
+	float const s = vx*Cy + vy*Cy + vz*Cy;
+	float i[3] = {floorf(vx + s), floorf(vy + s), floorf(vz + s)};
+	float const t = i[0]*Cx + i[1]*Cx + i[2]*Cx;
+	float const x0[3] = {vx - i[0] + t, vy - i[1] + t, vz - i[2] + t};
+	float const g[3] = {glm_step(x0[1], x0[0]), glm_step(x0[2], x0[1]), glm_step(x0[0], x0[2])};
+	float const l[3] = {1.0f - g[0], 1.0f - g[1], 1.0f - g[2]};
+	float const lz[3] = {l[2], l[0], l[1]};
+	float i1[3], i2[3], x1[3], x2[3], x3[3];
+	for (int d = 0; d < 3; ++d) {
+		i1[d] = glm_min(g[d], lz[d]); i2[d] = glm_max(g[d], lz[d]);
+		x1[d] = x0[d] - i1[d] + Cx; x2[d] = x0[d] - i2[d] + Cy; x3[d] = x0[d] - Dy;
+	}
+	for (int d = 0; d < 3; ++d) {i[d] = mod289f(i[d]);}
+	float const oz[4] = {0.0f, i1[2], i2[2], 1.0f}, oy[4] = {0.0f, i1[1], i2[1], 1.0f}, ox[4] = {0.0f, i1[0], i2[0], 1.0f};
+	float p[4];
+	for (int k = 0; k < 4; ++k) {p[k] = permutef(permutef(permutef(i[2] + oz[k]) + i[1] + oy[k]) + i[0] + ox[k]);}
+	float const n_ = 0.142857142857f;
+	float const nsx = n_*Dw - Dx, nsy = n_*Dy - Dz, nsz = n_*Dz - Dx;
+	float X[4], Y[4], H[4];
+	for (int k = 0; k < 4; ++k) {
+		float const j  = p[k] - 49.0f*floorf(p[k]*nsz*nsz);
+		float const x_ = floorf(j*nsz);
+		float const y_ = floorf(j - 7.0f*x_);
+		X[k] = x_*nsx + nsy; Y[k] = y_*nsx + nsy;
+		H[k] = 1.0f - fabsf(X[k]) - fabsf(Y[k]);
+	}
+	float const b0[4] = {X[0], X[1], Y[0], Y[1]}, b1[4] = {X[2], X[3], Y[2], Y[3]};
+	float s0[4], s1[4], sh[4];
+	for (int k = 0; k < 4; ++k) {s0[k] = floorf(b0[k])*2.0f + 1.0f; s1[k] = floorf(b1[k])*2.0f + 1.0f; sh[k] = -glm_step(H[k], 0.0f);}
+	float const a0[4] = {b0[0] + s0[0]*sh[0], b0[2] + s0[2]*sh[0], b0[1] + s0[1]*sh[1], b0[3] + s0[3]*sh[1]};
+	float const a1[4] = {b1[0] + s1[0]*sh[2], b1[2] + s1[2]*sh[2], b1[1] + s1[1]*sh[3], b1[3] + s1[3]*sh[3]};
+	float P0[3] = {a0[0], a0[1], H[0]}, P1[3] = {a0[2], a0[3], H[1]}, P2[3] = {a1[0], a1[1], H[2]}, P3[3] = {a1[2], a1[3], H[3]};
+	float *PP[4] = {P0, P1, P2, P3};
+	for (int k = 0; k < 4; ++k) {
+		float *q = PP[k]; float const n = tinvsqrt(q[0]*q[0] + q[1]*q[1] + q[2]*q[2]);
+		q[0] *= n; q[1] *= n; q[2] *= n;
+	}
+	float const *XX[4] = {x0, x1, x2, x3};
+	float m[4], d[4];
+	for (int k = 0; k < 4; ++k) {
+		float const *x = XX[k];
+		m[k] = glm_max(0.6f - (x[0]*x[0] + x[1]*x[1] + x[2]*x[2]), 0.0f);
+		m[k] = m[k]*m[k];
+		d[k] = PP[k][0]*x[0] + PP[k][1]*x[1] + PP[k][2]*x[2];
+	}
+	float const mm0 = m[0]*m[0], mm1 = m[1]*m[1], mm2 = m[2]*m[2], mm3 = m[3]*m[3];
+	return 42.0f*((mm0*d[0] + mm1*d[1]) + (mm2*d[2] + mm3*d[3]));
+}
+
+/* ------------------------------------------------------------------ 2-D height path */
+static inline float std_min(float a, float b) {return (b < a) ? b : a;} /* std::min */
+static inline float std_max(float a, float b) {return (a < b) ? b : a;} /* std::max */
+
+static void postproc_noise_zval(float *zval, const tw_hmap_params *h) { /* ref: src/mesh_gen.cpp:555-562 */
+	float z = *zval;
+	if (z > h->plat_bot) {z = h->plat_bot + h->plat_h*(z - h->plat_bot) + std_min(h->plat_max, h->plat_s*(z - h->plat_bot));}
+	if (z > h->crat_h  ) {z = h->crat_h - h->crat_s*(z - h->crat_h);}
+	if (z > h->crack_lo && z < h->crack_hi) {z -= h->crack_d*std_min(z - h->crack_lo, h->crack_hi - z);}
+	*zval = z;
+}
+static void apply_noise_shape_final(float *noise, int shape, const tw_hmap_params *h) { /* ref: src/mesh_gen.cpp:564-571 */
+	switch (shape) {
+	case 1: *noise = (float)(fabsf(*noise) - 2.0); break;
+	case 2: *noise = (float)(3.5 - fabsf(*noise)); break;
+	default: break;
+	}
+	postproc_noise_zval(noise, h);
+}
+static float get_hmap_scale(const tw_height_params *p) { /* ref: src/mesh_gen.cpp:550-553 */
+	int const m = p->gen_mode;
+	float const scale = (m == TW_MGEN_SIMPLEX || m == TW_MGEN_SIMPLEX_GPU || m == TW_MGEN_DWARP_GPU) ? 16.0f : 32.0f;
+	return scale*p->mesh_height*p->mesh_height_scale*p->mesh_scale_z_inv;
+}
+static float gen_noise(float xv, float yv, const tw_height_params *p) { /* ref: src/mesh_gen.cpp:706-730 */
+	float zval = 0.0f, mag = 1.0f, freq = 1.0f, rx = p->rx, ry = p->ry;
+	unsigned const end_octave = 9 - p->start_eval_sin/10;
+	float const lacunarity = 1.92f, gain = 0.5f;
+	int const mode = p->gen_mode;
+	for (unsigned i = 0; i < end_octave; ++i) {
+		float const px = freq*xv + rx, py = freq*yv + ry;
+		float noise = (mode == TW_MGEN_SIMPLEX || mode == TW_MGEN_SIMPLEX_GPU || mode == TW_MGEN_DWARP_GPU) ? to_simplex2(px, py) : to_perlin2(px, py);
+		switch (p->gen_shape) {
+		case 1: noise = (float)(fabsf(noise) - 0.40); break;
+		case 2: noise = (float)(0.45 - fabsf(noise)); break;
+		default: break;
+		}
+		zval += mag*noise;
+		mag  *= gain;
+		freq *= lacunarity;
+		rx   *= 1.5f;
+		ry   *= 1.5f;
+	}
+	return zval;
+}
+float to_get_noise_zval(float xval, float yval, const tw_height_params *p) { /* ref: src/mesh_gen.cpp:734-751 */
+	float const xy_scale = 0.0007f*p->mesh_scale;
+	float xv = xy_scale*xval, yv = xy_scale*yval;
+	if (p->gen_mode == TW_MGEN_DWARP_GPU) {
+		float const scale = 0.2f;
+		float const dx1 = gen_noise((float)(xv + 0.0), (float)(yv + 0.0), p);
+		float const dy1 = gen_noise((float)(xv + 5.2), (float)(yv + 1.3), p);
+		float const dx2 = gen_noise((float)((xv + scale*dx1) + 1.7), (float)((yv + scale*dy1) + 9.2), p);
+		float const dy2 = gen_noise((float)((xv + scale*dx1) + 8.3), (float)((yv + scale*dy1) + 2.8), p);
+		xv += scale*dx2; yv += scale*dy2;
+	}
+	float zval = gen_noise(xv, yv, p);
+	postproc_noise_zval(&zval, &p->hmap);
+	return zval*get_hmap_scale(p);
+}
+float to_eval_mesh_sin_terms(float xv, float yv, const float *tab, const float *T, int start) { /* ref: src/mesh_gen.cpp:797-805 */
+	float zval = 0.0f;
+	for (int k = start; k < 90; ++k) {
+		float const *s = T + 5*k;
+		zval += s[0]*to_sinf_lut(tab, s[3]*yv + s[1])*to_sinf_lut(tab, s[4]*xv + s[2]);
+	}
+	return zval;
+}
+static float get_volcano_height(float xi, float yi, const tw_height_params *p, const float *tab) { /* ref: src/mesh_gen.cpp:364-372 */
+	float const freq = p->mesh_scale/p->hmap.volcano_width, x = freq*xi, y = freq*yi, dist = sqrtf(x*x + y*y);
+	if (dist > 2.0) return 0.0f;
+	float const val = to_cosf_lut(tab, x)*to_cosf_lut(tab, y);
+	double const hd = 400.0*(val - 0.999);
+	float const hole = (float)((0.0 < hd) ? hd : 0.0);
+	float const peak = (float)(0.08*val/std_max(0.04f, dist));
+	return p->hmap.volcano_height*std_max(0.0f, (peak - hole))*p->mesh_scale_z_inv;
+}
+
+void to_heightgen_2d(const tw_grid2d *g, const tw_height_params *p, const float *tab, const float *T, int enable_glaciate,
+	int min_start_sin, float *out, int nthreads)
+{
+	unsigned const nx = g->nx, ny = g->ny;
+	float const dx = g->dx, dy = g->dy;
+	float const mx0 = dx*g->x0, my0 = dy*g->y0, mdx = dx, mdy = dy; /* ref: src/mesh_gen.cpp:591 */
+	int const F = 90, start = p->start_eval_sin;
+	float *xy = NULL, *smt = NULL;
+	float sine_offset = 0.0f;
+	if (p->gen_mode == TW_MGEN_SINE) { /* ref: src/mesh_gen.cpp:604-626 */
+		xy = (float *)calloc((size_t)(nx + ny)*F, sizeof(float));
+		float const msx = p->mesh_scale*p->dx_val_inv, msy = p->mesh_scale*p->dy_val_inv, ms2 = (float)(0.5*p->mesh_scale);
+		for (int k = start; k < F; ++k) {
+			float const *s = T + 5*k;
+			float const x_mult = msx*s[4], y_mult = msy*s[3], y_scale = p->mesh_scale_z_inv*s[0];
+			float const x_const = ms2*s[4] + s[2] + x_mult*mx0, y_const = ms2*s[3] + s[1] + y_mult*my0;
+			float const xmdx = x_mult*dx, ymdy = y_mult*dy;
+			for (unsigned i = 0; i < nx; ++i) {xy[(size_t)i*F + k] = to_sinf_lut(tab, xmdx*(float)i + x_const);}
+			for (unsigned i = 0; i < ny; ++i) {xy[((size_t)nx + i)*F + k] = y_scale*to_sinf_lut(tab, ymdy*(float)i + y_const);}
+		}
+	}
+	if (enable_glaciate && p->hmap.sine_mag != 0.0f) { /* ref: src/mesh_gen.cpp:640-650 */
+		smt = (float *)malloc((size_t)(nx + ny)*sizeof(float));
+		sine_offset = p->hmap.sine_bias*p->mesh_scale_z_inv;
+		float const sm_scale = p->hmap.sine_mag*p->mesh_scale_z_inv, freq = p->mesh_scale*p->hmap.sine_freq;
+		for (unsigned x = 0; x < nx; ++x) {smt[x] = sm_scale*to_cosf_lut(tab, ((float)x*mdx + mx0)*p->dx_val_inv*freq);}
+		for (unsigned y = 0; y < ny; ++y) {smt[nx + y] = to_cosf_lut(tab, ((float)y*mdy + my0)*p->dy_val_inv*freq);}
+	}
+	float const zmax_est = p->zmax_est, zmax_est2 = (float)(2.0*zmax_est), zmax_est2_inv = (float)(1.0/zmax_est2); /* ref: :162-167 */
+	int const start_ix = (start > min_start_sin) ? start : min_start_sin;
+#ifdef _OPENMP
+	if (nthreads <= 0) nthreads = omp_get_max_threads();
+#endif
+	(void)nthreads;
+#pragma omp parallel for schedule(static,1) num_threads(nthreads)
+	for (int y = 0; y < (int)ny; ++y) {
+		for (unsigned x = 0; x < nx; ++x) { /* ref: eval_index, src/mesh_gen.cpp:754-792 */
+			float zval = 0.0f;
+			if (p->gen_mode != TW_MGEN_SINE) {
+				float const xval = ((float)x*mdx + mx0)*p->dx_val_inv, yval = ((float)y*mdy + my0)*p->dy_val_inv;
+				zval += to_get_noise_zval(xval, yval, p);
+			}
+			else {
+				float const *xptr = xy + (size_t)x*F, *yptr = xy + ((size_t)nx + y)*F;
+				for (int i = start_ix; i < F; ++i) {zval += xptr[i]*yptr[i];}
+				apply_noise_shape_final(&zval, p->gen_shape, &p->hmap);
+			}
+			if (enable_glaciate) {
+				if (p->glaciate) { /* apply_glaciate, ref: src/mesh_gen.cpp:380-385 */
+					float const relh = (zval + zmax_est)*zmax_est2_inv;
+					zval = do_glaciate_exp(relh, p->custom_glaciate_exp)*zmax_est2 - zmax_est;
+				}
+				if (p->hmap.sine_mag > 0.0f) {
+					zval += smt[x]*smt[nx + y] + sine_offset;
+					if (p->hmap.volcano_width > 0.0f && p->hmap.volcano_height > 0.0f) {
+						zval += get_volcano_height(((float)x*mdx + mx0)*p->dx_val_inv, ((float)y*mdy + my0)*p->dy_val_inv, p, tab);
+					}
+				}
+			}
+			out[(size_t)y*nx + x] = zval;
+		}
+	}
+	free(xy); free(smt);
+}
+
+/* ------------------------------------------------------------------ erosion (ref: src/erosion.cpp:14-164) */
+unsigned long long to_apply_erosion(float *heightmap, int xsize, int ysize, float min_zval, unsigned num_iters, const tw_erosion_params *ep)
+{
+	float const erode_amount = ep->erode_amount;
+	if (num_iters == 0 || erode_amount <= 0.0) return 0;
+	float const Kq=10, Kw=0.001f, Kr=0.9f, Kd=0.02f, Ki=0.1f, minSlope=0.05f, g=20, Kg=g*2;
+	int const PAD = 4, NX = xsize+2*PAD, NY = ysize+2*PAD;
+	unsigned const MAX_PATH_LEN = 4*NX*NY;
+	float *mh = (float *)malloc((size_t)NX*NY*sizeof(float));
+	unsigned long long steps = 0;
+	for (int y = 0; y < NY; ++y) {
+		int yy = y-PAD; if (yy > ysize-1) yy = ysize-1; if (yy < 0) yy = 0;
+		for (int x = 0; x < NX; ++x) {
+			int xx = x-PAD; if (xx > xsize-1) xx = xsize-1; if (xx < 0) xx = 0;
+			mh[(size_t)y*NX + x] = heightmap[xx + (size_t)yy*xsize];
+		}
+	}
+#define CLAMPI(v, hi) (((v) < (hi)) ? (((v) > 0) ? (v) : 0) : (hi))
+#define HMAP_INDEX(x, y) ((size_t)NX*CLAMPI((y), NY-1) + CLAMPI((x), NX-1))
+#define HMAP(x, y) mh[HMAP_INDEX(x, y)]
+#define DEPOSIT_AT(X, Z, W) { \
+	float const delta = ds*erode_amount*(W); \
+	size_t const ix = HMAP_INDEX((X), (Z)); \
+	if (!((X) < 0 || (Z) < 0 || (X) >= NX || (Z) >= NY)) {mh[ix] += delta;} \
+}
+#define DEPOSIT(H) \
+	DEPOSIT_AT(xi  , zi  , (1-xf)*(1-zf)) \
+	DEPOSIT_AT(xi+1, zi  ,    xf *(1-zf)) \
+	DEPOSIT_AT(xi  , zi+1, (1-xf)*   zf ) \
+	DEPOSIT_AT(xi+1, zi+1,    xf *   zf ) \
+	(H)+=ds;
+	float const tp = two_pi();
+	for (int iter = 0; iter < (int)num_iters; ++iter) {
+		tw_rng rgen; to_rng_set(&rgen, iter+11, 79*iter+121);
+		int xi = PAD + (to_rng_rand(&rgen)%xsize);
+		int zi = PAD + (to_rng_rand(&rgen)%ysize);
+		float xp=xi, zp=zi, xf=0, zf=0, s=0, v=0, w=1, dx=0, dz=0;
+		float h=HMAP(xi, zi), h00=h, h10=HMAP(xi+1, zi), h01=HMAP(xi, zi+1), h11=HMAP(xi+1, zi+1);
+		unsigned numMoves = 0;
+		for (; numMoves < MAX_PATH_LEN; ++numMoves) {
+			++steps;
+			float gx=h00+h01-h10-h11, gz=h00+h10-h01-h11;
+			dx=(dx-gx)*Ki+gx;
+			dz=(dz-gz)*Ki+gz;
+			float dl=sqrtf(dx*dx+dz*dz);
+			if (dl<=FLT_EPSILON) {
+				float a=to_rng_rand_float(&rgen)*tp;
+				dx=cosf(a); dz=sinf(a);
+			}
+			else {dx/=dl; dz/=dl;}
+			float nxp=xp+dx, nzp=zp+dz;
+			int nxi=(int)floorf(nxp), nzi=(int)floorf(nzp);
+			float nxf=nxp-nxi, nzf=nzp-nzi;
+			float nh00=HMAP(nxi, nzi), nh10=HMAP(nxi+1, nzi), nh01=HMAP(nxi, nzi+1), nh11=HMAP(nxi+1, nzi+1);
+			float nh=(nh00*(1-nxf)+nh10*nxf)*(1-nzf)+(nh01*(1-nxf)+nh11*nxf)*nzf;
+			if (std_max(std_max(nh00, nh10), std_max(nh01, nh11)) < ep->water_plane_z - ep->half_dxy) break;
+			int const outside = (xi < 0 || zi < 0 || xi >= NX || zi >= NY);
+			if (nh>=h || outside) {
+				float ds=(nh-h)+0.001f;
+				if (ds>=s || outside) {
+					ds=s;
+					DEPOSIT(h)
+					s=0;
+					break;
+				}
+				DEPOSIT(h)
+				s-=ds;
+				v=0;
+			}
+			float dh=h-nh;
+			float slope=dh;
+			float q=std_max(slope, minSlope)*v*w*Kq;
+			float ds=s-q;
+			if (ds>=0) {
+				ds*=Kd;
+				DEPOSIT(dh)
+				s-=ds;
+			}
+			else {
+				ds*=-Kr;
+				ds=std_min(ds, dh*0.99f);
+				{ /* get_bare_ls_tid(nh) == ROCK_TEX ? 0.5 : 2.0, ref: src/Textures.cpp:1284-1287 */
+					float const relh = ep->relh_adj_tex + (nh - ep->zmin)/(ep->zmax - ep->zmin);
+					ds = (float)(ds*((relh > ep->clip_hd1) ? 0.5 : 2.0));
+				}
+				for (int z=zi-1; z<=zi+2; ++z) {
+					float zo=z-zp, zo2=zo*zo;
+					for (int x=xi-1; x<=xi+2; ++x) {
+						float xo=x-xp;
+						float wgt=1-(xo*xo+zo2)*0.25f;
+						if (wgt<=0) continue;
+						wgt*=0.1591549430918953f;
+						float const delta=ds*erode_amount*wgt;
+						mh[HMAP_INDEX(x, z)]-=delta;
+					}
+				}
+				dh-=ds;
+				s+=ds;
+			}
+			v=sqrtf(v*v+Kg*dh);
+			w*=1-Kw;
+			xp=nxp; zp=nzp; xi=nxi; zi=nzi; xf=nxf; zf=nzf;
+			h=nh; h00=nh00; h10=nh10; h01=nh01; h11=nh11;
+		}
+	}
+	for (int y = 0; y < ysize; ++y) {
+		for (int x = 0; x < xsize; ++x) {heightmap[(size_t)y*xsize + x] = std_max(min_zval, mh[(size_t)(y+PAD)*NX + x+PAD]);}
+	}
+	free(mh);
+	return steps;
+}
+
+/* ------------------------------------------------------------------ 3-D noise / voxels */
+void to_noise3d_gen_sines(int rs1, int rs2, float mag, float freq, float *rdata) { /* ref: src/upsurface.cpp:16-38 */
+	tw_rng r; to_rng_set(&r, rs1, rs2);
+	float const tp = two_pi();
+	for (unsigned i = 0; i < 5; ++i) {
+		for (unsigned j = 0; j < 12; ++j) {
+			float *e = rdata + 7*(12*i + j);
+			e[0] = to_rng_rand_uniform(&r, 0.2f, 1.0f)*mag;
+			e[1] = to_rng_rand_uniform(&r, 0.1f, 1.0f)*freq;
+			e[2] = (float)(to_rng_randd(&r)*tp);
+			e[3] = to_rng_rand_uniform(&r, 0.1f, 1.0f)*freq;
+			e[4] = (float)(to_rng_randd(&r)*tp);
+			e[5] = to_rng_rand_uniform(&r, 0.1f, 1.0f)*freq;
+			e[6] = (float)(to_rng_randd(&r)*tp);
+		}
+		mag  *= 0.5f;
+		freq /= 0.4f;
+	}
+}
+float to_noise3d_get_val_pt(const float *rdata, const float *tab, float px, float py, float pz) { /* ref: src/upsurface.cpp:73-85 */
+	float val = 0.0f;
+	for (unsigned k = 0; k < 60; ++k) {
+		float const *e = rdata + 7*k;
+		float const x = to_sinf_lut(tab, e[1]*px + e[2]);
+		float const y = to_sinf_lut(tab, e[3]*py + e[4]);
+		float const z = to_sinf_lut(tab, e[5]*pz + e[6]);
+		val += e[0]*x*y*z;
+	}
+	return val;
+}
+
+static inline float clip_pm1(float x) {return std_max(-1.0f, std_min(1.0f, x));} /* CLIP_TO_pm1, ref: src/3DWorld.h:149 */
+
+void to_voxel_fill(const tw_voxel_params *vp, const float *rdata_in, const float *tab, float *out, int nthreads)
+{
+	unsigned const nx = vp->nx, ny = vp->ny, nz = vp->nz, num[3] = {nx, ny, nz};
+	float rdata[420];
+	float *xyz[3] = {NULL, NULL, NULL};
+	if (vp->gen_mode == TW_MGEN_SINE) {
+		if (rdata_in) {memcpy(rdata, rdata_in, sizeof(rdata));} else {to_noise3d_gen_sines(vp->rseed1, vp->rseed2, vp->mag, vp->freq, rdata);}
+		for (unsigned d = 0; d < 3; ++d) { /* gen_xyz_vals, ref: src/upsurface.cpp:41-57 */
+			xyz[d] = (float *)malloc((size_t)60*num[d]*sizeof(float));
+			float val = vp->lo_pos[d] + vp->offset[d];
+			for (unsigned i = 0; i < num[d]; ++i) {
+				for (unsigned k = 0; k < 60; ++k) {
+					unsigned const index2 = 7*k + 2*d;
+					float v = to_sinf_lut(tab, rdata[index2+1]*val + rdata[index2+2]);
+					if (d == 0) {v *= rdata[index2];}
+					xyz[d][(size_t)i*60 + k] = v;
+				}
+				val += vp->vsz[d];
+			}
+		}
+	}
+#ifdef _OPENMP
+	if (nthreads <= 0) nthreads = omp_get_max_threads();
+#endif
+	(void)nthreads;
+	float const rx = vp->rx, ry = vp->ry;
+#pragma omp parallel for schedule(static,1) num_threads(nthreads)
+	for (int y = 0; y < (int)ny; ++y) { /* ref: src/voxels.cpp:312-345 */
+		for (unsigned x = 0; x < nx; ++x) {
+			for (unsigned z = 0; z < nz; ++z) {
+				float val = 0.0f;
+				if (vp->gen_mode == TW_MGEN_SINE) { /* get_val(x,y,z,tables), ref: src/upsurface.cpp:60-70 */
+					float const *xv = xyz[0] + (size_t)x*60, *yv = xyz[1] + (size_t)y*60, *zv = xyz[2] + (size_t)z*60;
+					for (unsigned k = 0; k < 60; ++k) {val += xv[k]*yv[k]*zv[k];}
+				}
+				else {
+					float const px = ((float)x*vp->vsz[0] + vp->lo_pos[0]) + vp->offset[0];
+					float const py = ((float)y*vp->vsz[1] + vp->lo_pos[1]) + vp->offset[1];
+					float const pz = ((float)z*vp->vsz[2] + vp->lo_pos[2]) + vp->offset[2];
+					float nmag = vp->mag, nfreq = (float)(0.25*vp->freq);
+					float const lacunarity = 1.92f, gain = 0.5f;
+					for (int n = 0; n < vp->octaves; ++n) {
+						float const nvx = nfreq*px + rx, nvy = nfreq*py + ry, nvz = nfreq*pz + (rx - ry);
+						val   += nmag*((vp->gen_mode == TW_MGEN_PERLIN) ? to_perlin3(nvx, nvy, nvz) : to_simplex3(nvx, nvy, nvz));
+						nmag  *= gain;
+						nfreq *= lacunarity;
+					}
+				}
+				val += (float)z*vp->zscale;
+				if (vp->normalize_to_1) {val = clip_pm1(val);}
+				out[z + ((size_t)x + (size_t)y*nx)*nz] = val;
+			}
+		}
+	}
+	for (int d = 0; d < 3; ++d) {free(xyz[d]);}
+	/* optional attenuation passes, ref: src/voxels.cpp:403-482 */
+	float const aval = vp->atten_val;
+	if (vp->atten_mode == 2) { /* atten_at_edges */
+#pragma omp parallel for schedule(static) num_threads(nthreads)
+		for (int y = 0; y < (int)ny; ++y) {
+			float const vy = (float)(1.0 - 2.0*fabs(y - 0.5*ny)/(float)ny);
+			for (unsigned x = 0; x < nx; ++x) {
+				float const vx = (float)(1.0 - 2.0*fabs(x - 0.5*nx)/(float)nx);
+				for (unsigned z = 0; z < nz; ++z) {
+					float const vz = (float)(1.0 - 2.0*fabs(z - 0.5*nz)/(float)nz), v = 0.25f - vx*vy*vz;
+					if (v > 0.0) {float *o = out + z + ((size_t)x + (size_t)y*nx)*nz; *o = (float)(*o + 8.0*aval*v);}
+				}
+			}
+		}
+	}
+	else if (vp->atten_mode == 1) { /* atten_at_top_only, atten_top_mode 0 */
+#pragma omp parallel for schedule(static) num_threads(nthreads)
+		for (int y = 0; y < (int)ny; ++y) {
+			for (unsigned x = 0; x < nx; ++x) {
+				for (unsigned z = 0; z < nz; ++z) {
+					float const z_atten = (float)(z/(float)nz - 0.75);
+					if (z_atten > 0.0) {float *o = out + z + ((size_t)x + (size_t)y*nx)*nz; *o += aval*z_atten;}
+				}
+			}
+		}
+	}
+	else if (vp->atten_mode >= 3 && vp->atten_mode <= 5) { /* atten_to_sphere(val, inner_radius, atten_inner=(mode>=4), no_atten_zbot=(mode==5)) */
+		float const two_nz_inv = (float)(2.0/(float)nz), inner_radius = vp->atten_inner_radius;
+		int const atten_inner = (vp->atten_mode >= 4), no_atten_zbot = (vp->atten_mode == 5);
+#pragma omp parallel for schedule(static) num_threads(nthreads)
+		for (int y = 0; y < (int)ny; ++y) {
+			float const vy = (float)(2.0*fabs(y - 0.5*ny)/(float)ny);
+			for (unsigned x = 0; x < nx; ++x) {
+				float const vx = (float)(2.0*fabs(x - 0.5*nx)/(float)nx);
+				for (unsigned z = 0; z < nz; ++z) {
+					float const deltaz = (float)(z - 0.5*nz), zval = no_atten_zbot ? std_max(0.0f, deltaz) : fabsf(deltaz);
+					float const vz = zval*two_nz_inv, radius = sqrtf(vx*vx + vy*vy + vz*vz);
+					float adj = 0.0f;
+					if (radius > inner_radius) {adj = (radius - inner_radius)/(1.0f - inner_radius);}
+					else if (atten_inner) {adj = (radius - inner_radius)/inner_radius;}
+					out[z + ((size_t)x + (size_t)y*nx)*nz] += aval*adj;
+				}
+			}
+		}
+	}
+}
+
+/* ------------------------------------------------------------------ heightmap 16-bit pack (ref: src/heightmap.cpp:191-215, src/Textures.cpp:1889-1893) */
+size_t to_from_floats_u16(const float *vals, size_t n, float val_mult, float val_add, unsigned char *out) {
+	float const val_div = (float)(1.0/val_mult);
+	size_t bad = 0;
+	for (size_t i = 0; i < n; ++i) {
+		float const v = (vals[i] - val_add)*val_div;
+		if (!(v >= 0.0 && v < 256.0)) {++bad; out[2*i] = out[2*i+1] = 0; continue;}
+		unsigned char const high_bits = (unsigned char)v;
+		out[2*i+1] = high_bits;
+		out[2*i]   = (unsigned char)(256.0f*(v - (float)high_bits));
+	}
+	return bad;
+}
+void to_to_floats_u16(const unsigned char *data, size_t n, float val_mult, float val_add, float *vals) {
+	for (size_t i = 0; i < n; ++i) {
+		float v = (float)(data[2*i]/256.0 + data[2*i+1]);
+		vals[i] = val_mult*v + val_add;
+	}
+}
