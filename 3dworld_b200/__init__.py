@@ -1,0 +1,286 @@
+"""3dworld_b200 - B200-native terrain hot path of fegennari/3DWorld (height generation, droplet erosion, voxel density).
+
+The product is the C-ABI shared library lib3dworld_b200.so (hand-written sm_100a CUDA, include/tw3d.h); the C++ adapter with the
+reference's own class/function signatures is host/tw3d_adapter.h. This Python module is only the thin ctypes binding that tests and
+bench.py drive the library through. There is no CPU fallback: importing works anywhere (so the ABI can be inspected), but creating a
+Context without a CUDA device raises, and a missing library raises at import.
+
+Import with importlib (the package name starts with a digit):  tw = importlib.import_module("3dworld_b200")
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib3dworld_b200.so")
+
+MGEN_SINE, MGEN_SIMPLEX, MGEN_PERLIN, MGEN_SIMPLEX_GPU, MGEN_DWARP_GPU = range(5)
+TW_OK, TW_ERR_NO_DEVICE, TW_ERR_CUDA, TW_ERR_ARG, TW_ERR_STATE, TW_ERR_NOT_READY = 0, -1, -2, -3, -4, -5
+
+
+class TwError(RuntimeError):
+    def __init__(self, status, msg):
+        super().__init__("tw3d status %d: %s" % (status, msg))
+        self.status = status
+
+
+# ---- POD mirrors of include/tw3d.h ----
+class HmapParams(C.Structure):
+    _fields_ = [(n, C.c_float) for n in ("plat_bot", "plat_h", "plat_s", "plat_max", "crat_h", "crat_s", "crack_lo", "crack_hi",
+                                         "crack_d", "sine_mag", "sine_freq", "sine_bias", "volcano_width", "volcano_height")]
+
+
+class HeightParams(C.Structure):
+    _fields_ = [("gen_mode", C.c_int), ("gen_shape", C.c_int), ("start_eval_sin", C.c_int), ("glaciate", C.c_int),
+                ("mesh_scale", C.c_float), ("mesh_scale_z_inv", C.c_float), ("dx_val_inv", C.c_float), ("dy_val_inv", C.c_float),
+                ("mesh_height", C.c_float), ("mesh_height_scale", C.c_float), ("zmax_est", C.c_float),
+                ("custom_glaciate_exp", C.c_float), ("rx", C.c_float), ("ry", C.c_float), ("hmap", HmapParams)]
+
+
+class Grid2D(C.Structure):
+    _fields_ = [("x0", C.c_float), ("y0", C.c_float), ("dx", C.c_float), ("dy", C.c_float), ("nx", C.c_uint32), ("ny", C.c_uint32)]
+
+
+class MinMax(C.Structure):
+    _fields_ = [("zmin", C.c_float), ("zmax", C.c_float)]
+
+
+class ErosionParams(C.Structure):
+    _fields_ = [(n, C.c_float) for n in ("erode_amount", "water_plane_z", "half_dxy", "zmin", "zmax", "relh_adj_tex", "clip_hd1")]
+
+
+class VoxelParams(C.Structure):
+    _fields_ = [("nx", C.c_uint32), ("ny", C.c_uint32), ("nz", C.c_uint32),
+                ("lo_pos", C.c_float * 3), ("vsz", C.c_float * 3), ("offset", C.c_float * 3),
+                ("mag", C.c_float), ("freq", C.c_float), ("gen_mode", C.c_int), ("normalize_to_1", C.c_int),
+                ("rseed1", C.c_int), ("rseed2", C.c_int), ("octaves", C.c_int), ("rx", C.c_float), ("ry", C.c_float),
+                ("zscale", C.c_float), ("atten_mode", C.c_int), ("atten_val", C.c_float), ("atten_inner_radius", C.c_float)]
+
+
+class Rng(C.Structure):
+    _fields_ = [("rseed1", C.c_int64), ("rseed2", C.c_int64)]
+
+
+def hmap_params(**kw):
+    """hmap_params_t with the reference defaults (src/mesh.h:85-88)."""
+    h = HmapParams(1000.0, 0, 0, 0, 1000.0, 0, 0, 0, 0, 0, 0, 0, 0, 0)
+    for k, v in kw.items():
+        setattr(h, k, v)
+    return h
+
+
+# every symbol include/tw3d.h declares (tests check the library exports exactly these)
+ABI_SYMBOLS = ["tw_abi_version", "tw_create", "tw_destroy", "tw_last_error", "tw_sync", "tw_stream", "tw_launch_count",
+               "tw_build_sin_table", "tw_compute_scale", "tw_gen_sine_params", "tw_gen_rx_ry", "tw_noise3d_gen_sines",
+               "tw_water_z_height", "tw_set_sin_table", "tw_set_sine_params", "tw_heightgen_2d", "tw_heightgen_2d_launch",
+               "tw_heightgen_2d_poll", "tw_heightgen_tiles", "tw_erode", "tw_erode_tiles", "tw_last_erosion_steps", "tw_voxel_fill",
+               "tw_heightmap_from_floats_u16", "tw_heightmap_to_floats_u16", "tw_minmax_f32"]
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise ImportError("3dworld_b200: %s is missing - build it with `python 3dworld_b200/build.py` (or __graft_entry__.build()); "
+                          "there is no CPU fallback" % LIB_PATH)
+    L = C.CDLL(LIB_PATH)
+    vp, fp = C.c_void_p, C.POINTER(C.c_float)
+    L.tw_create.argtypes = [C.c_int, C.POINTER(vp)]
+    L.tw_destroy.argtypes = [vp]
+    L.tw_destroy.restype = None
+    L.tw_last_error.argtypes = [vp]
+    L.tw_last_error.restype = C.c_char_p
+    L.tw_sync.argtypes = [vp]
+    L.tw_stream.argtypes = [vp]
+    L.tw_stream.restype = vp
+    L.tw_launch_count.argtypes = [vp]
+    L.tw_launch_count.restype = C.c_uint64
+    L.tw_build_sin_table.argtypes = [vp]
+    L.tw_build_sin_table.restype = None
+    L.tw_compute_scale.argtypes = [C.c_float, C.c_int]
+    L.tw_gen_sine_params.argtypes = [C.POINTER(Rng), C.c_float, C.c_int, C.c_int, C.c_float, C.c_float, C.c_int, C.c_int, C.c_int,
+                                     C.c_float, C.c_float, C.c_float, C.c_float, vp]
+    L.tw_gen_sine_params.restype = None
+    L.tw_gen_rx_ry.argtypes = [C.c_int, C.c_int, C.c_int, fp, fp]
+    L.tw_gen_rx_ry.restype = None
+    L.tw_noise3d_gen_sines.argtypes = [C.c_int, C.c_int, C.c_float, C.c_float, vp]
+    L.tw_noise3d_gen_sines.restype = None
+    L.tw_water_z_height.argtypes = [C.c_float, C.c_int, C.c_float, C.c_float, C.c_float]
+    L.tw_water_z_height.restype = C.c_float
+    L.tw_set_sin_table.argtypes = [vp, vp]
+    L.tw_set_sine_params.argtypes = [vp, vp]
+    hg = [vp, C.POINTER(Grid2D), C.POINTER(HeightParams), C.c_int, C.c_int, vp, C.POINTER(MinMax)]
+    L.tw_heightgen_2d.argtypes = hg
+    L.tw_heightgen_2d_launch.argtypes = hg
+    L.tw_heightgen_2d_poll.argtypes = [vp, C.c_int]
+    L.tw_heightgen_tiles.argtypes = [vp, vp, C.c_uint32, C.c_int, C.c_int, C.c_float, C.c_float, C.c_uint32, C.POINTER(HeightParams), vp, vp]
+    L.tw_erode.argtypes = [vp, vp, C.c_int, C.c_int, C.c_float, C.c_uint32, C.POINTER(ErosionParams)]
+    L.tw_erode_tiles.argtypes = [vp, vp, C.c_uint32, C.c_int, C.c_int, vp, C.c_float, C.c_uint32, C.POINTER(ErosionParams)]
+    L.tw_last_erosion_steps.argtypes = [vp]
+    L.tw_last_erosion_steps.restype = C.c_uint64
+    L.tw_voxel_fill.argtypes = [vp, C.POINTER(VoxelParams), vp, vp]
+    L.tw_heightmap_from_floats_u16.argtypes = [vp, vp, C.c_size_t, C.c_float, C.c_float, vp]
+    L.tw_heightmap_to_floats_u16.argtypes = [vp, vp, C.c_size_t, C.c_float, C.c_float, vp]
+    L.tw_minmax_f32.argtypes = [vp, vp, C.c_size_t, C.POINTER(MinMax)]
+    return L
+
+
+lib = _load()
+
+
+def _ptr(a):
+    """Raw address of a numpy array (host) or a torch tensor (host or CUDA)."""
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        assert a.flags["C_CONTIGUOUS"]
+        return C.c_void_p(a.ctypes.data)
+    if hasattr(a, "data_ptr"):
+        assert a.is_contiguous()
+        return C.c_void_p(a.data_ptr())
+    raise TypeError(type(a))
+
+
+# ---- host-side helpers (no GPU needed) ----
+def build_sin_table():
+    t = np.empty(65536, np.float32)
+    lib.tw_build_sin_table(_ptr(t))
+    return t
+
+
+def compute_scale(mesh_scale, mesh_freq_filter):
+    return lib.tw_compute_scale(mesh_scale, mesh_freq_filter)
+
+
+def gen_sine_params(scaled_height, mesh=(128, 128), scene=(4.0, 4.0), seed=0, rgen_index=0, mode=0, rng=None,
+                    start_mag=0.02, start_freq=240.0, mag_mult=2.0, freq_mult=0.5):
+    rng = rng if rng is not None else Rng(1, 1)
+    out = np.empty((90, 5), np.float32)
+    lib.tw_gen_sine_params(C.byref(rng), scaled_height, mesh[0], mesh[1], scene[0], scene[1], seed, rgen_index, mode,
+                           start_mag, start_freq, mag_mult, freq_mult, _ptr(out))
+    return out
+
+
+def gen_rx_ry(seed, rgen_index, mode):
+    rx, ry = C.c_float(), C.c_float()
+    lib.tw_gen_rx_ry(seed, rgen_index, mode, C.byref(rx), C.byref(ry))
+    return rx.value, ry.value
+
+
+def noise3d_gen_sines(rs1, rs2, mag, freq):
+    out = np.empty(420, np.float32)
+    lib.tw_noise3d_gen_sines(rs1, rs2, mag, freq, _ptr(out))
+    return out
+
+
+def water_z_height(zmax_est, glaciate=1, custom_glaciate_exp=0.0, water_h_off=0.0, water_h_off_rel=0.0):
+    return lib.tw_water_z_height(zmax_est, glaciate, custom_glaciate_exp, water_h_off, water_h_off_rel)
+
+
+class Context:
+    """One tw_ctx (device + stream + uploaded tables). All compute goes through the C ABI."""
+
+    def __init__(self, device=0, sin_table=None):
+        h = C.c_void_p()
+        rc = lib.tw_create(device, C.byref(h))
+        if rc != TW_OK:
+            raise TwError(rc, "tw_create failed (no CUDA device? this library has no CPU fallback)")
+        self._h = h
+        self.device = device
+        self._check(lib.tw_set_sin_table(self._h, _ptr(sin_table)))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib.tw_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def _check(self, rc):
+        if rc != TW_OK:
+            raise TwError(rc, lib.tw_last_error(self._h).decode())
+
+    @property
+    def stream(self):
+        return lib.tw_stream(self._h)
+
+    @property
+    def launch_count(self):
+        return int(lib.tw_launch_count(self._h))
+
+    def sync(self):
+        self._check(lib.tw_sync(self._h))
+
+    def set_sine_params(self, sp):
+        sp = np.ascontiguousarray(sp, np.float32)
+        assert sp.size == 450
+        self._check(lib.tw_set_sine_params(self._h, _ptr(sp)))
+
+    def heightgen_2d(self, grid, hp, enable_glaciate=1, min_start_sin=0, out=None, want_minmax=False):
+        if out is None:
+            out = np.empty((grid.ny, grid.nx), np.float32)
+        mm = MinMax() if want_minmax else None
+        self._check(lib.tw_heightgen_2d(self._h, C.byref(grid), C.byref(hp), int(enable_glaciate), int(min_start_sin), _ptr(out),
+                                        C.byref(mm) if mm else None))
+        return (out, (mm.zmin, mm.zmax)) if want_minmax else out
+
+    def heightgen_2d_launch(self, grid, hp, enable_glaciate, min_start_sin, out, mm=None):
+        self._check(lib.tw_heightgen_2d_launch(self._h, C.byref(grid), C.byref(hp), int(enable_glaciate), int(min_start_sin), _ptr(out),
+                                               C.byref(mm) if mm is not None else None))
+
+    def heightgen_2d_poll(self, wait=False):
+        rc = lib.tw_heightgen_2d_poll(self._h, int(wait))
+        if rc == TW_ERR_NOT_READY:
+            return False
+        self._check(rc)
+        return True
+
+    def heightgen_tiles(self, origins_xy, mesh_size, dx, dy, zvsize, hp, out=None, want_minmax=False):
+        org = np.ascontiguousarray(origins_xy, np.int32).reshape(-1, 2)
+        nt = org.shape[0]
+        if out is None:
+            out = np.empty((nt, zvsize, zvsize), np.float32)
+        mm = np.empty((nt, 2), np.float32) if want_minmax else None
+        self._check(lib.tw_heightgen_tiles(self._h, _ptr(org), nt, mesh_size[0], mesh_size[1], dx, dy, zvsize, C.byref(hp), _ptr(out), _ptr(mm)))
+        return (out, mm) if want_minmax else out
+
+    def erode(self, h, min_zval, num_iters, ep):
+        """In place on h (numpy [ys, xs] or CUDA tensor)."""
+        ys, xs = h.shape
+        self._check(lib.tw_erode(self._h, _ptr(h), xs, ys, min_zval, num_iters, C.byref(ep)))
+        return h
+
+    def erode_tiles(self, tiles, num_iters, ep, min_zvals=None, min_zval_all=0.0):
+        nt, ys, xs = tiles.shape
+        mz = None if min_zvals is None else np.ascontiguousarray(min_zvals, np.float32)
+        self._check(lib.tw_erode_tiles(self._h, _ptr(tiles), nt, xs, ys, _ptr(mz), min_zval_all, num_iters, C.byref(ep)))
+        return tiles
+
+    @property
+    def last_erosion_steps(self):
+        return int(lib.tw_last_erosion_steps(self._h))
+
+    def voxel_fill(self, vp, rdata=None, out=None):
+        if out is None:
+            out = np.empty((vp.ny, vp.nx, vp.nz), np.float32)
+        rd = None if rdata is None else np.ascontiguousarray(rdata, np.float32)
+        self._check(lib.tw_voxel_fill(self._h, C.byref(vp), _ptr(rd), _ptr(out)))
+        return out
+
+    def from_floats_u16(self, vals, val_mult, val_add, out=None):
+        n = int(np.prod(vals.shape))
+        if out is None:
+            out = np.empty(2 * n, np.uint8)
+        self._check(lib.tw_heightmap_from_floats_u16(self._h, _ptr(vals), n, val_mult, val_add, _ptr(out)))
+        return out
+
+    def to_floats_u16(self, data, val_mult, val_add, out=None):
+        n = int(np.prod(data.shape)) // 2
+        if out is None:
+            out = np.empty(n, np.float32)
+        self._check(lib.tw_heightmap_to_floats_u16(self._h, _ptr(data), n, val_mult, val_add, _ptr(out)))
+        return out
+
+    def minmax(self, vals):
+        mm = MinMax()
+        self._check(lib.tw_minmax_f32(self._h, _ptr(vals), int(np.prod(vals.shape)), C.byref(mm)))
+        return mm.zmin, mm.zmax

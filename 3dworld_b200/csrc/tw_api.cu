@@ -1,0 +1,368 @@
+// tw_api.cu - the extern "C" boundary (include/tw3d.h): context management, host/device pointer staging, and dispatch to the kernels.
+// There is deliberately NO CPU path in this library: without a CUDA device tw_create fails and nothing else can be called.
+#include "tw_internal.h"
+#include <stdarg.h>
+#include <stdlib.h>
+#include <new>
+#include <vector>
+
+extern "C" void twi_build_dir_table(float *cs2x1e6);
+
+int tw_set_error(tw_ctx *ctx, int status, const char *fmt, ...) {
+	if (ctx) {
+		va_list ap; va_start(ap, fmt);
+		vsnprintf(ctx->err, sizeof(ctx->err), fmt, ap);
+		va_end(ap);
+	}
+	return status;
+}
+
+int tw_reserve(tw_ctx *ctx, int slot, size_t bytes) {
+	if (ctx->scratch_bytes[slot] >= bytes) return TW_OK;
+	TW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	if (ctx->d_scratch[slot]) {TW_CUDA(ctx, cudaFree(ctx->d_scratch[slot])); ctx->d_scratch[slot] = nullptr; ctx->scratch_bytes[slot] = 0;}
+	size_t const rounded = (bytes + ((size_t)1 << 20) - 1) & ~(((size_t)1 << 20) - 1);
+	TW_CUDA(ctx, cudaMalloc(&ctx->d_scratch[slot], rounded));
+	ctx->scratch_bytes[slot] = rounded;
+	return TW_OK;
+}
+
+int tw_reserve_pinned(tw_ctx *ctx, size_t bytes) {
+	if (ctx->pinned_bytes >= bytes) return TW_OK;
+	TW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	if (ctx->h_pinned) {TW_CUDA(ctx, cudaFreeHost(ctx->h_pinned)); ctx->h_pinned = nullptr; ctx->pinned_bytes = 0;}
+	TW_CUDA(ctx, cudaMallocHost(&ctx->h_pinned, bytes));
+	ctx->pinned_bytes = bytes;
+	return TW_OK;
+}
+
+bool tw_is_device_ptr(const void *p) {
+	cudaPointerAttributes a;
+	if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {cudaGetLastError(); return false;}
+	return (a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged);
+}
+
+namespace {
+
+// slot-2 layout (small device scalars)
+constexpr size_t OFF_MM = 0, OFF_BAD = 64, OFF_TILES = 4096;
+
+int check_ctx(tw_ctx *ctx) {
+	if (!ctx) return TW_ERR_ARG;
+	cudaError_t e = cudaSetDevice(ctx->device);
+	if (e != cudaSuccess) return tw_set_error(ctx, TW_ERR_CUDA, "cudaSetDevice(%d): %s", ctx->device, cudaGetErrorString(e));
+	return TW_OK;
+}
+
+int finish_pending(tw_ctx *ctx) { // complete an outstanding tw_heightgen_2d_launch before other work reuses the scratch buffers
+	if (ctx->async.pending) {return tw_heightgen_2d_poll(ctx, 1);}
+	return TW_OK;
+}
+
+int read_minmax(tw_ctx *ctx, const unsigned *d_mm, tw_minmax *mm, uint32_t n) { // synchronous
+	int rc = tw_reserve_pinned(ctx, (size_t)n*2*sizeof(unsigned));
+	if (rc) return rc;
+	TW_CUDA(ctx, cudaMemcpyAsync(ctx->h_pinned, d_mm, (size_t)n*2*sizeof(unsigned), cudaMemcpyDeviceToHost, ctx->stream));
+	TW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	unsigned const *u = (unsigned const *)ctx->h_pinned;
+	for (uint32_t i = 0; i < n; ++i) {mm[i].zmin = tw_ord2f(u[2*i]); mm[i].zmax = tw_ord2f(u[2*i+1]);}
+	return TW_OK;
+}
+
+int validate_height(tw_ctx *ctx, const tw_grid2d *g, const tw_height_params *p, const float *out) {
+	if (!g || !p || !out) return tw_set_error(ctx, TW_ERR_ARG, "null argument");
+	if (g->nx == 0 || g->ny == 0) return tw_set_error(ctx, TW_ERR_ARG, "nx, ny must be > 0 (reference asserts, src/mesh_gen.cpp:589)");
+	if (p->gen_mode < 0 || p->gen_mode > TW_MGEN_DWARP_GPU) return tw_set_error(ctx, TW_ERR_ARG, "bad gen_mode %d", p->gen_mode);
+	if (p->start_eval_sin < 0 || p->start_eval_sin > TW_F_TABLE_SIZE) return tw_set_error(ctx, TW_ERR_ARG, "start_eval_sin out of range (src/mesh_gen.cpp:590)");
+	if (!ctx->have_sin) return tw_set_error(ctx, TW_ERR_STATE, "tw_set_sin_table() has not been called");
+	return TW_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+int tw_abi_version(void) {return TW_ABI_VERSION;}
+
+int tw_create(int device, tw_ctx **out) {
+	if (!out) return TW_ERR_ARG;
+	*out = nullptr;
+	int ndev = 0;
+	if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {cudaGetLastError(); return TW_ERR_NO_DEVICE;}
+	if (device < 0 || device >= ndev) return TW_ERR_ARG;
+	if (cudaSetDevice(device) != cudaSuccess) {cudaGetLastError(); return TW_ERR_CUDA;}
+	tw_ctx *ctx = new (std::nothrow) tw_ctx();
+	if (!ctx) return TW_ERR_CUDA;
+	ctx->device = device;
+	if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {delete ctx; cudaGetLastError(); return TW_ERR_CUDA;}
+	if (cudaEventCreateWithFlags(&ctx->async.done, cudaEventDisableTiming) != cudaSuccess) {cudaStreamDestroy(ctx->stream); delete ctx; cudaGetLastError(); return TW_ERR_CUDA;}
+	*out = ctx;
+	return TW_OK;
+}
+
+void tw_destroy(tw_ctx *ctx) {
+	if (!ctx) return;
+	cudaSetDevice(ctx->device);
+	cudaStreamSynchronize(ctx->stream);
+	for (int i = 0; i < 3; ++i) {if (ctx->d_scratch[i]) cudaFree(ctx->d_scratch[i]);}
+	if (ctx->d_sin_table) cudaFree(ctx->d_sin_table);
+	if (ctx->d_dir_table) cudaFree(ctx->d_dir_table);
+	if (ctx->d_sine_params) cudaFree(ctx->d_sine_params);
+	if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+	if (ctx->async.done) cudaEventDestroy(ctx->async.done);
+	cudaStreamDestroy(ctx->stream);
+	delete ctx;
+}
+
+const char *tw_last_error(const tw_ctx *ctx) {return ctx ? ctx->err : "null context";}
+void *tw_stream(tw_ctx *ctx) {return ctx ? (void *)ctx->stream : nullptr;}
+uint64_t tw_launch_count(const tw_ctx *ctx) {return ctx ? ctx->launches : 0;}
+uint64_t tw_last_erosion_steps(const tw_ctx *ctx) {return ctx ? ctx->last_erosion_steps : 0;}
+
+int tw_sync(tw_ctx *ctx) {
+	int rc = check_ctx(ctx); if (rc) return rc;
+	TW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	return TW_OK;
+}
+
+int tw_set_sin_table(tw_ctx *ctx, const float *tab) {
+	int rc = check_ctx(ctx); if (rc) return rc;
+	std::vector<float> built;
+	if (!tab) {built.resize(TW_SIN_TABLE_SIZE); tw_build_sin_table(built.data()); tab = built.data();}
+	if (!ctx->d_sin_table) {TW_CUDA(ctx, cudaMalloc(&ctx->d_sin_table, TW_SIN_TABLE_SIZE*sizeof(float)));}
+	TW_CUDA(ctx, cudaMemcpyAsync(ctx->d_sin_table, tab, TW_SIN_TABLE_SIZE*sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+	if (!ctx->d_dir_table) {
+		std::vector<float> dir(2*1000000);
+		twi_build_dir_table(dir.data());
+		TW_CUDA(ctx, cudaMalloc(&ctx->d_dir_table, dir.size()*sizeof(float)));
+		TW_CUDA(ctx, cudaMemcpyAsync(ctx->d_dir_table, dir.data(), dir.size()*sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+		TW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	}
+	TW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	ctx->have_sin = true;
+	return TW_OK;
+}
+
+int tw_set_sine_params(tw_ctx *ctx, const float *sp) {
+	int rc = check_ctx(ctx); if (rc) return rc;
+	if (!sp) return tw_set_error(ctx, TW_ERR_ARG, "null sine_params");
+	if (!ctx->d_sine_params) {TW_CUDA(ctx, cudaMalloc(&ctx->d_sine_params, TW_F_TABLE_SIZE*5*sizeof(float)));}
+	memcpy(ctx->h_sine_params, sp, sizeof(ctx->h_sine_params));
+	TW_CUDA(ctx, cudaMemcpyAsync(ctx->d_sine_params, ctx->h_sine_params, sizeof(ctx->h_sine_params), cudaMemcpyHostToDevice, ctx->stream));
+	TW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	ctx->have_sine_params = true;
+	return TW_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ 2-D height
+int tw_heightgen_2d_launch(tw_ctx *ctx, const tw_grid2d *g, const tw_height_params *p, int enable_glaciate, int min_start_sin, float *out, tw_minmax *mm) {
+	int rc = check_ctx(ctx); if (rc) return rc;
+	rc = finish_pending(ctx); if (rc) return rc;
+	rc = validate_height(ctx, g, p, out); if (rc) return rc;
+	size_t const n = (size_t)g->nx*g->ny;
+	bool const dev_out = tw_is_device_ptr(out);
+	float *d_out = out;
+	if (!dev_out) {rc = tw_reserve(ctx, 0, n*sizeof(float)); if (rc) return rc; d_out = (float *)ctx->d_scratch[0];}
+	rc = tw_reserve(ctx, 2, OFF_TILES); if (rc) return rc;
+	unsigned *d_mm = mm ? (unsigned *)((char *)ctx->d_scratch[2] + OFF_MM) : nullptr;
+	if (d_mm) {rc = twi_init_minmax(ctx, d_mm, 1); if (rc) return rc;}
+	rc = twi_heightgen(ctx, g, p, enable_glaciate, min_start_sin, nullptr, 1, d_out, d_mm);
+	if (rc) return rc;
+	if (!dev_out) {TW_CUDA(ctx, cudaMemcpyAsync(out, d_out, n*sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));}
+	if (mm) {
+		rc = tw_reserve_pinned(ctx, 2*sizeof(unsigned)); if (rc) return rc;
+		TW_CUDA(ctx, cudaMemcpyAsync(ctx->h_pinned, d_mm, 2*sizeof(unsigned), cudaMemcpyDeviceToHost, ctx->stream));
+	}
+	TW_CUDA(ctx, cudaEventRecord(ctx->async.done, ctx->stream));
+	ctx->async.pending = true; ctx->async.host_mm = mm; ctx->async.n_mm = mm ? 1 : 0;
+	return TW_OK;
+}
+
+int tw_heightgen_2d_poll(tw_ctx *ctx, int wait) {
+	int rc = check_ctx(ctx); if (rc) return rc;
+	if (!ctx->async.pending) return TW_OK;
+	if (wait) {TW_CUDA(ctx, cudaEventSynchronize(ctx->async.done));}
+	else {
+		cudaError_t const e = cudaEventQuery(ctx->async.done);
+		if (e == cudaErrorNotReady) return TW_ERR_NOT_READY;
+		if (e != cudaSuccess) return tw_set_error(ctx, TW_ERR_CUDA, "cudaEventQuery: %s", cudaGetErrorString(e));
+	}
+	ctx->async.pending = false;
+	if (ctx->async.host_mm) {
+		unsigned const *u = (unsigned const *)ctx->h_pinned;
+		ctx->async.host_mm->zmin = tw_ord2f(u[0]); ctx->async.host_mm->zmax = tw_ord2f(u[1]);
+		ctx->async.host_mm = nullptr;
+	}
+	cudaError_t const e = cudaGetLastError();
+	if (e != cudaSuccess) return tw_set_error(ctx, TW_ERR_CUDA, "async height generation failed: %s", cudaGetErrorString(e));
+	return TW_OK;
+}
+
+int tw_heightgen_2d(tw_ctx *ctx, const tw_grid2d *g, const tw_height_params *p, int enable_glaciate, int min_start_sin, float *out, tw_minmax *mm) {
+	int rc = tw_heightgen_2d_launch(ctx, g, p, enable_glaciate, min_start_sin, out, mm);
+	if (rc) return rc;
+	return tw_heightgen_2d_poll(ctx, 1);
+}
+
+int tw_heightgen_tiles(tw_ctx *ctx, const int32_t *origins_xy, uint32_t ntiles, int mesh_x_size, int mesh_y_size, float dx, float dy,
+                       uint32_t zvsize, const tw_height_params *p, float *out, tw_minmax *mm)
+{
+	int rc = check_ctx(ctx); if (rc) return rc;
+	rc = finish_pending(ctx); if (rc) return rc;
+	if (!origins_xy || ntiles == 0) return tw_set_error(ctx, TW_ERR_ARG, "no tiles");
+	tw_grid2d g; g.x0 = 0; g.y0 = 0; g.dx = dx; g.dy = dy; g.nx = zvsize; g.ny = zvsize;
+	rc = validate_height(ctx, &g, p, out); if (rc) return rc;
+	size_t const tile_elems = (size_t)zvsize*zvsize, n = tile_elems*ntiles;
+	bool const dev_out = tw_is_device_ptr(out);
+	float *d_out = out;
+	if (!dev_out) {rc = tw_reserve(ctx, 0, n*sizeof(float)); if (rc) return rc; d_out = (float *)ctx->d_scratch[0];}
+	size_t const mm_bytes = (size_t)ntiles*2*sizeof(unsigned), org_bytes = (size_t)ntiles*sizeof(float2);
+	rc = tw_reserve(ctx, 2, OFF_TILES + mm_bytes + org_bytes); if (rc) return rc;
+	unsigned *d_mm = mm ? (unsigned *)((char *)ctx->d_scratch[2] + OFF_TILES) : nullptr;
+	float2 *d_org = (float2 *)((char *)ctx->d_scratch[2] + OFF_TILES + mm_bytes);
+	if (d_mm) {rc = twi_init_minmax(ctx, d_mm, ntiles); if (rc) return rc;}
+	// setup_height_gen_async: build_arrays((x0 - MESH_X_SIZE/2), (y0 - MESH_Y_SIZE/2), dx, dy, ...): int -> float, then mx0 = dx*x0 (src/tiled_mesh.cpp:461, src/mesh_gen.cpp:591)
+	if (p->gen_mode != TW_MGEN_SINE) {
+		std::vector<float2> org(ntiles);
+		for (uint32_t t = 0; t < ntiles; ++t) {
+			float const x0 = (float)(origins_xy[2*t] - mesh_x_size/2), y0 = (float)(origins_xy[2*t+1] - mesh_y_size/2);
+			org[t] = make_float2(dx*x0, dy*y0);
+		}
+		TW_CUDA(ctx, cudaMemcpyAsync(d_org, org.data(), org_bytes, cudaMemcpyHostToDevice, ctx->stream));
+		TW_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); // org is a local vector
+		uint32_t const zmax = 65535;
+		for (uint32_t t0 = 0; t0 < ntiles; t0 += zmax) { // gridDim.z limit
+			uint32_t const nt = (ntiles - t0 < zmax) ? ntiles - t0 : zmax;
+			rc = twi_heightgen(ctx, &g, p, 1, 0, d_org + t0, nt, d_out + (size_t)t0*tile_elems, d_mm ? d_mm + 2*(size_t)t0 : nullptr);
+			if (rc) return rc;
+		}
+	}
+	else { // sine tables depend on the tile origin: one table build + grid launch per tile
+		for (uint32_t t = 0; t < ntiles; ++t) {
+			g.x0 = (float)(origins_xy[2*t] - mesh_x_size/2); g.y0 = (float)(origins_xy[2*t+1] - mesh_y_size/2);
+			rc = twi_heightgen(ctx, &g, p, 1, 0, nullptr, 1, d_out + (size_t)t*tile_elems, d_mm ? d_mm + 2*(size_t)t : nullptr);
+			if (rc) return rc;
+		}
+	}
+	if (!dev_out) {TW_CUDA(ctx, cudaMemcpyAsync(out, d_out, n*sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));}
+	if (mm) {rc = read_minmax(ctx, d_mm, mm, ntiles); if (rc) return rc;}
+	TW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	return TW_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ erosion
+int tw_erode_tiles(tw_ctx *ctx, float *maps, uint32_t ntiles, int xsize, int ysize, const float *min_zvals, float min_zval_all,
+                   uint32_t num_iters, const tw_erosion_params *p)
+{
+	int rc = check_ctx(ctx); if (rc) return rc;
+	rc = finish_pending(ctx); if (rc) return rc;
+	if (!maps || !p) return tw_set_error(ctx, TW_ERR_ARG, "null argument");
+	if (xsize <= 0 || ysize <= 0 || ntiles == 0) return tw_set_error(ctx, TW_ERR_ARG, "empty heightmap");
+	if (num_iters == 0 || p->erode_amount <= 0.0) {ctx->last_erosion_steps = 0; return TW_OK;} // src/erosion.cpp:16
+	size_t const n = (size_t)xsize*ysize*ntiles;
+	bool const dev = tw_is_device_ptr(maps);
+	float *d_maps = maps;
+	if (!dev) {
+		rc = tw_reserve(ctx, 0, n*sizeof(float)); if (rc) return rc;
+		d_maps = (float *)ctx->d_scratch[0];
+		TW_CUDA(ctx, cudaMemcpyAsync(d_maps, maps, n*sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+	}
+	float *d_minz = nullptr;
+	if (min_zvals) {
+		rc = tw_reserve(ctx, 2, OFF_TILES + (size_t)ntiles*sizeof(float)); if (rc) return rc;
+		d_minz = (float *)((char *)ctx->d_scratch[2] + OFF_TILES);
+		TW_CUDA(ctx, cudaMemcpyAsync(d_minz, min_zvals, (size_t)ntiles*sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+		TW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	}
+	rc = twi_erode(ctx, d_maps, ntiles, xsize, ysize, d_minz, min_zval_all, num_iters, p);
+	if (rc) return rc;
+	if (!dev) {TW_CUDA(ctx, cudaMemcpyAsync(maps, d_maps, n*sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));}
+	TW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	return TW_OK;
+}
+
+int tw_erode(tw_ctx *ctx, float *heightmap, int xsize, int ysize, float min_zval, uint32_t num_iters, const tw_erosion_params *p) {
+	return tw_erode_tiles(ctx, heightmap, 1, xsize, ysize, nullptr, min_zval, num_iters, p);
+}
+
+// ------------------------------------------------------------------------------------------------ voxels
+int tw_voxel_fill(tw_ctx *ctx, const tw_voxel_params *vp, const float *rdata420, float *out) {
+	int rc = check_ctx(ctx); if (rc) return rc;
+	rc = finish_pending(ctx); if (rc) return rc;
+	if (!vp || !out) return tw_set_error(ctx, TW_ERR_ARG, "null argument");
+	if (!ctx->have_sin) return tw_set_error(ctx, TW_ERR_STATE, "tw_set_sin_table() has not been called");
+	if (vp->gen_mode < 0 || vp->gen_mode > TW_MGEN_DWARP_GPU) return tw_set_error(ctx, TW_ERR_ARG, "bad gen_mode");
+	size_t const n = (size_t)vp->nx*vp->ny*vp->nz;
+	bool const dev_out = tw_is_device_ptr(out);
+	float *d_out = out;
+	if (!dev_out) {rc = tw_reserve(ctx, 0, n*sizeof(float)); if (rc) return rc; d_out = (float *)ctx->d_scratch[0];}
+	rc = twi_voxel_fill(ctx, vp, rdata420, d_out);
+	if (rc) return rc;
+	if (!dev_out) {TW_CUDA(ctx, cudaMemcpyAsync(out, d_out, n*sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));}
+	TW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	return TW_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ streaming passes
+int tw_heightmap_from_floats_u16(tw_ctx *ctx, const float *vals, size_t n, float val_mult, float val_add, uint8_t *out2n) {
+	int rc = check_ctx(ctx); if (rc) return rc;
+	rc = finish_pending(ctx); if (rc) return rc;
+	if (!vals || !out2n || n == 0) return tw_set_error(ctx, TW_ERR_ARG, "null/empty argument");
+	bool const dev_in = tw_is_device_ptr(vals), dev_out = tw_is_device_ptr(out2n);
+	size_t const in_bytes = n*sizeof(float), out_bytes = 2*n;
+	size_t const need = (dev_in ? 0 : in_bytes) + (dev_out ? 0 : out_bytes);
+	if (need) {rc = tw_reserve(ctx, 0, need + 256); if (rc) return rc;}
+	rc = tw_reserve(ctx, 2, OFF_TILES); if (rc) return rc;
+	const float *d_in = vals; uint8_t *d_out = out2n;
+	char *s = (char *)ctx->d_scratch[0];
+	if (!dev_in) {d_in = (const float *)s; TW_CUDA(ctx, cudaMemcpyAsync(s, vals, in_bytes, cudaMemcpyHostToDevice, ctx->stream)); s += (in_bytes + 255) & ~(size_t)255;}
+	if (!dev_out) {d_out = (uint8_t *)s;}
+	unsigned *d_bad = (unsigned *)((char *)ctx->d_scratch[2] + OFF_BAD);
+	TW_CUDA(ctx, cudaMemsetAsync(d_bad, 0, sizeof(unsigned), ctx->stream));
+	rc = twi_from_floats_u16(ctx, d_in, n, val_mult, val_add, d_out, d_bad);
+	if (rc) return rc;
+	if (!dev_out) {TW_CUDA(ctx, cudaMemcpyAsync(out2n, d_out, out_bytes, cudaMemcpyDeviceToHost, ctx->stream));}
+	unsigned bad = 0;
+	TW_CUDA(ctx, cudaMemcpyAsync(&bad, d_bad, sizeof(bad), cudaMemcpyDeviceToHost, ctx->stream));
+	TW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	if (bad) return tw_set_error(ctx, TW_ERR_ARG, "from_floats: value outside [0,256) (the reference asserts, src/heightmap.cpp:211)");
+	return TW_OK;
+}
+
+int tw_heightmap_to_floats_u16(tw_ctx *ctx, const uint8_t *data2n, size_t n, float val_mult, float val_add, float *vals) {
+	int rc = check_ctx(ctx); if (rc) return rc;
+	rc = finish_pending(ctx); if (rc) return rc;
+	if (!vals || !data2n || n == 0) return tw_set_error(ctx, TW_ERR_ARG, "null/empty argument");
+	bool const dev_in = tw_is_device_ptr(data2n), dev_out = tw_is_device_ptr(vals);
+	size_t const in_bytes = 2*n, out_bytes = n*sizeof(float);
+	size_t const need = (dev_in ? 0 : in_bytes) + (dev_out ? 0 : out_bytes);
+	if (need) {rc = tw_reserve(ctx, 0, need + 256); if (rc) return rc;}
+	const uint8_t *d_in = data2n; float *d_out = vals;
+	char *s = (char *)ctx->d_scratch[0];
+	if (!dev_out) {d_out = (float *)s; s += (out_bytes + 255) & ~(size_t)255;}
+	if (!dev_in) {d_in = (const uint8_t *)s; TW_CUDA(ctx, cudaMemcpyAsync(s, data2n, in_bytes, cudaMemcpyHostToDevice, ctx->stream));}
+	rc = twi_to_floats_u16(ctx, d_in, n, val_mult, val_add, d_out);
+	if (rc) return rc;
+	if (!dev_out) {TW_CUDA(ctx, cudaMemcpyAsync(vals, d_out, out_bytes, cudaMemcpyDeviceToHost, ctx->stream));}
+	TW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	return TW_OK;
+}
+
+int tw_minmax_f32(tw_ctx *ctx, const float *vals, size_t n, tw_minmax *mm) {
+	int rc = check_ctx(ctx); if (rc) return rc;
+	rc = finish_pending(ctx); if (rc) return rc;
+	if (!vals || !mm || n == 0) return tw_set_error(ctx, TW_ERR_ARG, "null/empty argument");
+	const float *d_in = vals;
+	if (!tw_is_device_ptr(vals)) {
+		rc = tw_reserve(ctx, 0, n*sizeof(float)); if (rc) return rc;
+		TW_CUDA(ctx, cudaMemcpyAsync(ctx->d_scratch[0], vals, n*sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+		d_in = (const float *)ctx->d_scratch[0];
+	}
+	rc = tw_reserve(ctx, 2, OFF_TILES); if (rc) return rc;
+	unsigned *d_mm = (unsigned *)((char *)ctx->d_scratch[2] + OFF_MM);
+	rc = twi_init_minmax(ctx, d_mm, 1); if (rc) return rc;
+	rc = twi_minmax(ctx, d_in, n, d_mm); if (rc) return rc;
+	return read_minmax(ctx, d_mm, mm, 1);
+}
+
+} // extern "C"

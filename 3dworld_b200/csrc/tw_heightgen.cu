@@ -1,0 +1,385 @@
+// tw_heightgen.cu - 2-D height generation kernels (sm_100a).
+// Replaces mesh_xy_grid_cache_t::{build_arrays, enable_glaciate, eval_index} (src/mesh_gen.cpp:588-650,754-792) and
+// get_noise_zval/gen_noise (src/mesh_gen.cpp:706-751) evaluated over a whole grid (or a batch of tiles).
+//
+// Kernels:
+//   sine_tables_kernel   build_arrays sine branch (:604-626) + enable_glaciate cos terms (:640-650); k-major tables, LUT sin/cos
+//   sine_grid_kernel     eval_index sine branch (:766-781): z = sum_k X[k][x]*Y[k][y], sequential fp32 sum, register-tiled 4x4 per thread,
+//                        X/Y panels staged in shared memory; fused shape/postproc/glaciate/sine-bias/volcano + min/max
+//   noise_grid_kernel    eval_index noise branch (:761-764 -> get_noise_zval): per-cell fBm of simplex/perlin, optional domain warp,
+//                        fused postproc/scale/glaciate/sine-bias/volcano + min/max. Pure FP32 ALU work: 4 B/cell of HBM traffic.
+// All arithmetic keeps the reference's rounding sequence (this TU is compiled with -fmad=false; see tw_noise.cuh).
+#include "tw_internal.h"
+#include "tw_noise.cuh"
+
+namespace {
+
+constexpr int F_TABLE = TW_F_TABLE_SIZE;
+
+__device__ __forceinline__ float sinf_lut(const float *__restrict__ tab, float v) { // SINF, src/sinf.h:13-14
+	return (v < 0.0f) ? -__ldg(tab + (((int)(TW_SSCALE*(-v)))&(TW_TSIZE-1))) : __ldg(tab + (((int)(TW_SSCALE*v))&(TW_TSIZE-1)));
+}
+__device__ __forceinline__ float cosf_lut(const float *__restrict__ tab, float v) { // COSF, src/sinf.h:15
+	return __ldg(tab + TW_TSIZE + (((int)(TW_SSCALE*fabsf(v)))&(TW_TSIZE-1)));
+}
+__device__ __forceinline__ float smin(float a, float b) {return (b < a) ? b : a;} // std::min
+__device__ __forceinline__ float smax(float a, float b) {return (a < b) ? b : a;} // std::max
+
+// Everything a cell needs after the raw noise / sine sum, passed by value to the kernels (constant bank).
+struct PostParams {
+	tw_hmap_params h;
+	int   shape;                 // apply_noise_shape_final (sine path only)
+	int   need_postproc;         // hmap_params_t::need_postproc()
+	int   enable_glaciate;       // do_glaciate (enable_glaciate() called)
+	int   glaciate;              // GLACIATE global
+	float zmax_est, zmax_est2, zmax_est2_inv, custom_exp;
+	int   sine_on;               // hmap.sine_mag > 0
+	float sm_scale, sm_freq, sine_offset; // sine_mag*mszi, mesh_scale*sine_freq, sine_bias*mszi
+	int   volcano_on;
+	float volcano_freq;          // mesh_scale/volcano_width
+	float mesh_scale_z_inv;
+	float mdx, mdy, dx_inv, dy_inv; // grid step, DX_VAL_INV, DY_VAL_INV
+};
+
+__device__ __forceinline__ float postproc_noise_zval(float z, const tw_hmap_params &h) { // src/mesh_gen.cpp:555-562
+	if (z > h.plat_bot) {z = h.plat_bot + h.plat_h*(z - h.plat_bot) + smin(h.plat_max, h.plat_s*(z - h.plat_bot));}
+	if (z > h.crat_h  ) {z = h.crat_h - h.crat_s*(z - h.crat_h);}
+	if (z > h.crack_lo && z < h.crack_hi) {z -= h.crack_d*smin(z - h.crack_lo, h.crack_hi - z);}
+	return z;
+}
+
+__device__ __forceinline__ float volcano_height(float xi, float yi, const PostParams &P, const float *__restrict__ tab) { // src/mesh_gen.cpp:364-372
+	float const x = P.volcano_freq*xi, y = P.volcano_freq*yi, dist = __fsqrt_rn(x*x + y*y);
+	if ((double)dist > 2.0) return 0.0f;
+	float const val = cosf_lut(tab, x)*cosf_lut(tab, y);
+	double const hd = 400.0*((double)val - 0.999);
+	float const hole = (float)((0.0 < hd) ? hd : 0.0);
+	float const peak = (float)(0.08*(double)val/(double)smax(0.04f, dist));
+	return P.h.volcano_height*smax(0.0f, (peak - hole))*P.mesh_scale_z_inv;
+}
+
+// apply_glaciate (src/mesh_gen.cpp:380-385) + the sine bias / volcano terms of eval_index (src/mesh_gen.cpp:782-790).
+// smx/smy: the enable_glaciate() COSF terms for this cell (sm_scale*COSF(..x..), COSF(..y..)).
+__device__ __forceinline__ float glaciate_and_bias(float z, float smx, float smy, float cx, float cy, const PostParams &P, const float *__restrict__ tab) {
+	if (!P.enable_glaciate) return z;
+	if (P.glaciate) {
+		float const relh = (z + P.zmax_est)*P.zmax_est2_inv;
+		float const g = (P.custom_exp == 0.0f) ? relh*relh*relh : powf(relh, P.custom_exp); // powf: <= 2 ulp vs glibc for a custom exponent (documented)
+		z = g*P.zmax_est2 - P.zmax_est;
+	}
+	if (P.sine_on) {
+		z += smx*smy + P.sine_offset;
+		if (P.volcano_on) {z += volcano_height(cx, cy, P, tab);}
+	}
+	return z;
+}
+
+// block-level min/max -> global ordered-uint atomics
+__device__ __forceinline__ void block_minmax(float vmin, float vmax, unsigned *mm) {
+	for (int o = 16; o > 0; o >>= 1) {
+		vmin = fminf(vmin, __shfl_xor_sync(0xffffffffu, vmin, o));
+		vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
+	}
+	__shared__ float s_min[32], s_max[32];
+	int const tid = threadIdx.x + blockDim.x*(threadIdx.y + blockDim.y*threadIdx.z);
+	int const nw = (blockDim.x*blockDim.y*blockDim.z + 31) >> 5, w = tid >> 5, l = tid & 31;
+	if (l == 0) {s_min[w] = vmin; s_max[w] = vmax;}
+	__syncthreads();
+	if (w == 0) {
+		vmin = (l < nw) ? s_min[l] :  INFINITY;
+		vmax = (l < nw) ? s_max[l] : -INFINITY;
+		for (int o = 16; o > 0; o >>= 1) {
+			vmin = fminf(vmin, __shfl_xor_sync(0xffffffffu, vmin, o));
+			vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
+		}
+		if (l == 0) {atomicMin(mm, tw_f2ord(vmin)); atomicMax(mm + 1, tw_f2ord(vmax));}
+	}
+}
+
+// ------------------------------------------------------------------------------------------------ noise modes
+struct NoiseParams {
+	int   octaves;               // NUM_FREQ_COMP - start_eval_sin/N_RAND_SIN2
+	int   gen_shape;
+	float freq[9], mag[9], rx[9], ry[9]; // per-octave constants of gen_noise's loop (mag*=0.5, freq*=1.92, rx*=1.5, ry*=1.5), host-computed
+	float xy_scale;              // MESH_SCALE_FACTOR*mesh_scale
+	float hmap_scale;            // get_hmap_scale(mode)
+};
+
+template<bool SIMPLEX, int SHAPE>
+__device__ __forceinline__ float gen_noise(float xv, float yv, const NoiseParams &N) { // src/mesh_gen.cpp:706-730
+	float zval = 0.0f;
+#pragma unroll 1
+	for (int i = 0; i < N.octaves; ++i) {
+		float const px = N.freq[i]*xv + N.rx[i], py = N.freq[i]*yv + N.ry[i];
+		float noise = SIMPLEX ? twn::simplex2(px, py) : twn::perlin2(px, py);
+		if (SHAPE == 1) {noise = (float)((double)fabsf(noise) - 0.40);}
+		if (SHAPE == 2) {noise = (float)(0.45 - (double)fabsf(noise));}
+		zval = __fmaf_rn(N.mag[i], noise, zval); // mag is a power of two: mag*noise is exact, so fused == mul-then-add
+	}
+	return zval;
+}
+
+template<bool SIMPLEX, bool WARP, int SHAPE>
+__global__ void __launch_bounds__(256)
+noise_grid_kernel(float *__restrict__ out, unsigned nx, unsigned ny, float mx0_single, float my0_single, const float2 *__restrict__ tile_origins,
+	NoiseParams N, PostParams P, const float *__restrict__ sin_tab, unsigned *__restrict__ mm)
+{
+	unsigned const x = blockIdx.x*blockDim.x + threadIdx.x, y = blockIdx.y*blockDim.y + threadIdx.y, tile = blockIdx.z;
+	float mx0 = mx0_single, my0 = my0_single;
+	if (tile_origins) {float2 const o = __ldg(tile_origins + tile); mx0 = o.x; my0 = o.y;}
+	float z = 0.0f;
+	bool const valid = (x < nx && y < ny);
+	if (valid) {
+		// eval_index: xval((x*mdx + mx0)*DX_VAL_INV), src/mesh_gen.cpp:762
+		float const xval = ((float)x*P.mdx + mx0)*P.dx_inv, yval = ((float)y*P.mdy + my0)*P.dy_inv;
+		float xv = N.xy_scale*xval, yv = N.xy_scale*yval; // get_noise_zval, src/mesh_gen.cpp:737-738
+		if (WARP) { // domain warping, src/mesh_gen.cpp:740-747 ("xv+5.2" etc. are float+double adds rounded back to float)
+			float const scale = 0.2f;
+			float const dx1 = gen_noise<SIMPLEX, SHAPE>((float)((double)xv + 0.0), (float)((double)yv + 0.0), N);
+			float const dy1 = gen_noise<SIMPLEX, SHAPE>((float)((double)xv + 5.2), (float)((double)yv + 1.3), N);
+			float const wx = xv + scale*dx1, wy = yv + scale*dy1;
+			float const dx2 = gen_noise<SIMPLEX, SHAPE>((float)((double)wx + 1.7), (float)((double)wy + 9.2), N);
+			float const dy2 = gen_noise<SIMPLEX, SHAPE>((float)((double)wx + 8.3), (float)((double)wy + 2.8), N);
+			xv += scale*dx2; yv += scale*dy2;
+		}
+		z = gen_noise<SIMPLEX, SHAPE>(xv, yv, N);
+		if (P.need_postproc) {z = postproc_noise_zval(z, P.h);}
+		z = z*N.hmap_scale;
+		float smx = 0.0f, smy = 0.0f;
+		if (P.enable_glaciate && P.sine_on) { // enable_glaciate() terms, src/mesh_gen.cpp:647-649, evaluated per cell instead of tabulated
+			smx = P.sm_scale*cosf_lut(sin_tab, ((float)x*P.mdx + mx0)*P.dx_inv*P.sm_freq);
+			smy = cosf_lut(sin_tab, ((float)y*P.mdy + my0)*P.dy_inv*P.sm_freq);
+		}
+		z = glaciate_and_bias(z, smx, smy, xval, yval, P, sin_tab);
+		out[(size_t)tile*nx*ny + (size_t)y*nx + x] = z;
+	}
+	if (mm) {block_minmax(valid ? z : INFINITY, valid ? z : -INFINITY, mm + 2*tile);}
+}
+
+// ------------------------------------------------------------------------------------------------ sine-table mode
+struct SineTabParams {
+	float msx, msy, ms2, mesh_scale_z_inv; // mesh_scale*DX_VAL_INV, mesh_scale*DY_VAL_INV, 0.5*mesh_scale
+	float dx, dy, mx0, my0;
+	int   start;
+	unsigned nx, ny, xpitch, ypitch;       // table row pitches (floats)
+	// glaciate cos terms
+	int   sine_on; float sm_scale, sm_freq, dx_inv, dy_inv;
+};
+
+// X[k][i] = SINF(xmdx*i + x_const), Y[k][j] = y_scale*SINF(ymdy*j + y_const)  (src/mesh_gen.cpp:609-625); row F_TABLE holds the
+// enable_glaciate() terms (src/mesh_gen.cpp:647-649). grid = (ceil(max(nx,ny)/256), F_TABLE+1, 2[x|y])
+__global__ void sine_tables_kernel(float *__restrict__ Xt, float *__restrict__ Yt, const float *__restrict__ T, const float *__restrict__ sin_tab, SineTabParams S)
+{
+	unsigned const i = blockIdx.x*blockDim.x + threadIdx.x, k = blockIdx.y;
+	bool const is_y = (blockIdx.z != 0);
+	unsigned const n = is_y ? S.ny : S.nx;
+	if (i >= n) return;
+	if (k == F_TABLE) { // cos terms
+		if (!S.sine_on) return;
+		if (!is_y) {Xt[(size_t)k*S.xpitch + i] = S.sm_scale*cosf_lut(sin_tab, ((float)i*S.dx + S.mx0)*S.dx_inv*S.sm_freq);}
+		else       {Yt[(size_t)k*S.ypitch + i] = cosf_lut(sin_tab, ((float)i*S.dy + S.my0)*S.dy_inv*S.sm_freq);}
+		return;
+	}
+	if ((int)k < S.start) return; // never read
+	float const *s = T + 5*k;
+	if (!is_y) {
+		float const x_mult = S.msx*s[4];
+		float const x_const = S.ms2*s[4] + s[2] + x_mult*S.mx0;
+		float const xmdx = x_mult*S.dx;
+		Xt[(size_t)k*S.xpitch + i] = sinf_lut(sin_tab, xmdx*(float)i + x_const);
+	}
+	else {
+		float const y_mult = S.msy*s[3], y_scale = S.mesh_scale_z_inv*s[0];
+		float const y_const = S.ms2*s[3] + s[1] + y_mult*S.my0;
+		float const ymdy = y_mult*S.dy;
+		Yt[(size_t)k*S.ypitch + i] = y_scale*sinf_lut(sin_tab, ymdy*(float)i + y_const);
+	}
+}
+
+// 64x64 output tile per 256-thread block, 4x4 cells per thread (x strided by 16 so that a half-warp stores 16 consecutive floats).
+constexpr int ST = 64;          // tile edge
+constexpr int SK = 45;          // k-chunk staged in shared memory (2 chunks cover the 90 terms)
+
+__global__ void __launch_bounds__(256)
+sine_grid_kernel(float *__restrict__ out, unsigned nx, unsigned ny, const float *__restrict__ Xt, const float *__restrict__ Yt,
+	unsigned xpitch, unsigned ypitch, int start_ix, PostParams P, float mx0, float my0, const float *__restrict__ sin_tab, unsigned *__restrict__ mm)
+{
+	__shared__ float Xs[SK][ST], Ys[SK][ST];
+	unsigned const x_base = blockIdx.x*ST, y_base = blockIdx.y*ST;
+	int const tid = threadIdx.x, tx = tid & 15, ty = tid >> 4; // 16 x 16 threads
+	float acc[4][4];
+#pragma unroll
+	for (int a = 0; a < 4; ++a) {
+#pragma unroll
+		for (int b = 0; b < 4; ++b) {acc[a][b] = 0.0f;}
+	}
+	for (int k0 = start_ix; k0 < F_TABLE; k0 += SK) {
+		int const kn = min(SK, F_TABLE - k0);
+		__syncthreads();
+		for (int e = tid; e < kn*ST; e += 256) { // stage the X and Y panels (coalesced 256-byte rows)
+			int const kk = e / ST, c = e % ST;
+			unsigned const gx = x_base + c, gy = y_base + c;
+			Xs[kk][c] = (gx < nx) ? __ldg(Xt + (size_t)(k0 + kk)*xpitch + gx) : 0.0f;
+			Ys[kk][c] = (gy < ny) ? __ldg(Yt + (size_t)(k0 + kk)*ypitch + gy) : 0.0f;
+		}
+		__syncthreads();
+#pragma unroll 5
+		for (int kk = 0; kk < kn; ++kk) {
+			float xv[4];
+#pragma unroll
+			for (int b = 0; b < 4; ++b) {xv[b] = Xs[kk][tx + 16*b];}
+			float4 const yv4 = *reinterpret_cast<const float4 *>(&Ys[kk][ty*4]);
+			float const yv[4] = {yv4.x, yv4.y, yv4.z, yv4.w};
+#pragma unroll
+			for (int a = 0; a < 4; ++a) {
+#pragma unroll
+				for (int b = 0; b < 4; ++b) {acc[a][b] = acc[a][b] + xv[b]*yv[a];} // zval += xptr[i]*yptr[i]: separate mul and add (-fmad=false)
+			}
+		}
+	}
+	float vmin = INFINITY, vmax = -INFINITY;
+#pragma unroll
+	for (int a = 0; a < 4; ++a) {
+		unsigned const y = y_base + ty*4 + a;
+		if (y >= ny) continue;
+		float const smy = (P.enable_glaciate && P.sine_on) ? __ldg(Yt + (size_t)F_TABLE*ypitch + y) : 0.0f;
+#pragma unroll
+		for (int b = 0; b < 4; ++b) {
+			unsigned const x = x_base + tx + 16*b;
+			if (x >= nx) continue;
+			float z = acc[a][b];
+			if (P.shape == 1) {z = (float)((double)fabsf(z) - 2.0);}       // apply_noise_shape_final, src/mesh_gen.cpp:564-571
+			else if (P.shape == 2) {z = (float)(3.5 - (double)fabsf(z));}
+			if (P.need_postproc) {z = postproc_noise_zval(z, P.h);}
+			float const smx = (P.enable_glaciate && P.sine_on) ? __ldg(Xt + (size_t)F_TABLE*xpitch + x) : 0.0f;
+			float cx = 0.0f, cy = 0.0f;
+			if (P.volcano_on) {cx = ((float)x*P.mdx + mx0)*P.dx_inv; cy = ((float)y*P.mdy + my0)*P.dy_inv;}
+			z = glaciate_and_bias(z, smx, smy, cx, cy, P, sin_tab);
+			out[(size_t)y*nx + x] = z;
+			vmin = fminf(vmin, z); vmax = fmaxf(vmax, z);
+		}
+	}
+	if (mm) {block_minmax(vmin, vmax, mm);}
+}
+
+__global__ void init_minmax_kernel(unsigned *mm, uint32_t n) {
+	uint32_t const i = blockIdx.x*blockDim.x + threadIdx.x;
+	if (i < n) {mm[2*i] = 0xffffffffu; mm[2*i+1] = 0u;}
+}
+
+__global__ void minmax_kernel(const float *__restrict__ v, size_t n, unsigned *mm) {
+	float vmin = INFINITY, vmax = -INFINITY;
+	size_t const stride = (size_t)gridDim.x*blockDim.x;
+	for (size_t i = (size_t)blockIdx.x*blockDim.x + threadIdx.x; i < n; i += stride) {float const z = __ldg(v + i); vmin = fminf(vmin, z); vmax = fmaxf(vmax, z);}
+	block_minmax(vmin, vmax, mm);
+}
+
+template<bool SIMPLEX, bool WARP>
+void launch_noise(int shape, dim3 grid, dim3 block, cudaStream_t st, float *out, unsigned nx, unsigned ny, float mx0, float my0,
+	const float2 *origins, const NoiseParams &N, const PostParams &P, const float *tab, unsigned *mm)
+{
+	switch (shape) {
+	case 1:  noise_grid_kernel<SIMPLEX, WARP, 1><<<grid, block, 0, st>>>(out, nx, ny, mx0, my0, origins, N, P, tab, mm); break;
+	case 2:  noise_grid_kernel<SIMPLEX, WARP, 2><<<grid, block, 0, st>>>(out, nx, ny, mx0, my0, origins, N, P, tab, mm); break;
+	default: noise_grid_kernel<SIMPLEX, WARP, 0><<<grid, block, 0, st>>>(out, nx, ny, mx0, my0, origins, N, P, tab, mm); break;
+	}
+}
+
+} // namespace
+
+int twi_init_minmax(tw_ctx *ctx, unsigned *d_mm_ord, uint32_t n) {
+	init_minmax_kernel<<<(n + 255)/256, 256, 0, ctx->stream>>>(d_mm_ord, n);
+	TW_LAUNCH_CHECK(ctx);
+	return TW_OK;
+}
+
+int twi_minmax(tw_ctx *ctx, const float *d_vals, size_t n, unsigned *d_mm_ord) {
+	int const blocks = (int)((n + 255)/256 < 148*8 ? (n + 255)/256 : 148*8);
+	minmax_kernel<<<blocks > 0 ? blocks : 1, 256, 0, ctx->stream>>>(d_vals, n, d_mm_ord);
+	TW_LAUNCH_CHECK(ctx);
+	return TW_OK;
+}
+
+// Height generation for one grid (ntiles==0/1, d_tile_origins==nullptr) or a batch of equally sized tiles (noise modes only).
+int twi_heightgen(tw_ctx *ctx, const tw_grid2d *g, const tw_height_params *p, int enable_glaciate, int min_start_sin,
+                  const float2 *d_tile_origins, uint32_t ntiles, float *d_out, unsigned *d_mm_ord)
+{
+	unsigned const nx = g->nx, ny = g->ny;
+	float const dx = g->dx, dy = g->dy;
+	float const mx0 = dx*g->x0, my0 = dy*g->y0; // src/mesh_gen.cpp:591
+	if (ntiles == 0) ntiles = 1;
+
+	PostParams P;
+	memset(&P, 0, sizeof(P));
+	P.h = p->hmap;
+	P.shape = p->gen_shape;
+	P.need_postproc = 1; // get_noise_zval (:749) and apply_noise_shape_final (:570) call postproc_noise_zval unconditionally (3 compares at defaults)
+	P.enable_glaciate = (enable_glaciate != 0);
+	P.glaciate = (p->glaciate != 0);
+	P.zmax_est = p->zmax_est;
+	P.zmax_est2 = (float)(2.0*p->zmax_est);           // set_zmax_est, src/mesh_gen.cpp:162-167
+	P.zmax_est2_inv = (float)(1.0/P.zmax_est2);
+	P.custom_exp = p->custom_glaciate_exp;
+	P.sine_on = (p->hmap.sine_mag > 0.0f);
+	P.sm_scale = p->hmap.sine_mag*p->mesh_scale_z_inv;
+	P.sm_freq = p->mesh_scale*p->hmap.sine_freq;
+	P.sine_offset = p->hmap.sine_bias*p->mesh_scale_z_inv;
+	P.volcano_on = (p->hmap.volcano_width > 0.0f && p->hmap.volcano_height > 0.0f);
+	P.volcano_freq = P.volcano_on ? p->mesh_scale/p->hmap.volcano_width : 0.0f;
+	P.mesh_scale_z_inv = p->mesh_scale_z_inv;
+	P.mdx = dx; P.mdy = dy; P.dx_inv = p->dx_val_inv; P.dy_inv = p->dy_val_inv;
+
+	if (p->gen_mode != TW_MGEN_SINE) {
+		NoiseParams N;
+		memset(&N, 0, sizeof(N));
+		int const start = p->start_eval_sin;
+		if (start < 0 || start > F_TABLE) return tw_set_error(ctx, TW_ERR_ARG, "start_eval_sin %d out of range", start);
+		N.octaves = 9 - start/10;
+		N.gen_shape = p->gen_shape;
+		float mag = 1.0f, freq = 1.0f, rx = p->rx, ry = p->ry;
+		for (int i = 0; i < 9; ++i) { // loop-carried constants of gen_noise, src/mesh_gen.cpp:725-728
+			N.mag[i] = mag; N.freq[i] = freq; N.rx[i] = rx; N.ry[i] = ry;
+			mag *= 0.5f; freq *= 1.92f; rx *= 1.5f; ry *= 1.5f;
+		}
+		N.xy_scale = 0.0007f*p->mesh_scale; // MESH_SCALE_FACTOR, src/mesh_gen.cpp:23,737
+		bool const simplex = (p->gen_mode == TW_MGEN_SIMPLEX || p->gen_mode == TW_MGEN_SIMPLEX_GPU || p->gen_mode == TW_MGEN_DWARP_GPU);
+		N.hmap_scale = (simplex ? 16.0f : 32.0f)*p->mesh_height*p->mesh_height_scale*p->mesh_scale_z_inv; // get_hmap_scale, :550-553
+		dim3 const block(32, 8, 1), grid((nx + 31)/32, (ny + 7)/8, ntiles);
+		bool const warp = (p->gen_mode == TW_MGEN_DWARP_GPU);
+		if (p->gen_mode == TW_MGEN_PERLIN) {launch_noise<false, false>(p->gen_shape, grid, block, ctx->stream, d_out, nx, ny, mx0, my0, d_tile_origins, N, P, ctx->d_sin_table, d_mm_ord);}
+		else if (warp) {launch_noise<true, true >(p->gen_shape, grid, block, ctx->stream, d_out, nx, ny, mx0, my0, d_tile_origins, N, P, ctx->d_sin_table, d_mm_ord);}
+		else           {launch_noise<true, false>(p->gen_shape, grid, block, ctx->stream, d_out, nx, ny, mx0, my0, d_tile_origins, N, P, ctx->d_sin_table, d_mm_ord);}
+		TW_LAUNCH_CHECK(ctx);
+		return TW_OK;
+	}
+
+	// ---- sine-table mode ----
+	if (!ctx->have_sine_params) return tw_set_error(ctx, TW_ERR_STATE, "tw_set_sine_params() has not been called");
+	if (d_tile_origins && ntiles > 1) return tw_set_error(ctx, TW_ERR_ARG, "internal: sine mode tiles are issued one grid at a time");
+	unsigned const xpitch = (nx + 63) & ~63u, ypitch = (ny + 63) & ~63u;
+	size_t const tab_floats = (size_t)(F_TABLE + 1)*(xpitch + ypitch);
+	int rc = tw_reserve(ctx, 1, tab_floats*sizeof(float));
+	if (rc) return rc;
+	float *Xt = (float *)ctx->d_scratch[1], *Yt = Xt + (size_t)(F_TABLE + 1)*xpitch;
+	SineTabParams S;
+	memset(&S, 0, sizeof(S));
+	S.msx = p->mesh_scale*p->dx_val_inv; S.msy = p->mesh_scale*p->dy_val_inv; S.ms2 = (float)(0.5*p->mesh_scale);
+	S.mesh_scale_z_inv = p->mesh_scale_z_inv;
+	S.dx = dx; S.dy = dy; S.mx0 = mx0; S.my0 = my0;
+	S.start = p->start_eval_sin;
+	S.nx = nx; S.ny = ny; S.xpitch = xpitch; S.ypitch = ypitch;
+	S.sine_on = (enable_glaciate && p->hmap.sine_mag != 0.0f); S.sm_scale = P.sm_scale; S.sm_freq = P.sm_freq; S.dx_inv = p->dx_val_inv; S.dy_inv = p->dy_val_inv;
+	{
+		unsigned const nmax = nx > ny ? nx : ny;
+		dim3 const grid((nmax + 255)/256, F_TABLE + 1, 2);
+		sine_tables_kernel<<<grid, 256, 0, ctx->stream>>>(Xt, Yt, ctx->d_sine_params, ctx->d_sin_table, S);
+		TW_LAUNCH_CHECK(ctx);
+	}
+	int const start_ix = (p->start_eval_sin > min_start_sin) ? p->start_eval_sin : min_start_sin; // src/mesh_gen.cpp:769
+	{
+		dim3 const grid((nx + ST - 1)/ST, (ny + ST - 1)/ST, 1);
+		sine_grid_kernel<<<grid, 256, 0, ctx->stream>>>(d_out, nx, ny, Xt, Yt, xpitch, ypitch, start_ix, P, mx0, my0, ctx->d_sin_table, d_mm_ord);
+		TW_LAUNCH_CHECK(ctx);
+	}
+	return TW_OK;
+}

@@ -1,0 +1,82 @@
+// tw_internal.h - context object and helpers shared by the CUDA translation units of lib3dworld_b200.so
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+#include <stdio.h>
+#include <string.h>
+#include "../../include/tw3d.h"
+
+struct tw_async_state {
+	bool pending = false;
+	cudaEvent_t done = nullptr;
+	float *host_out = nullptr;      // user host buffer (nullptr => result stays on device)
+	tw_minmax *host_mm = nullptr;
+	uint32_t n_mm = 0;
+};
+
+struct tw_ctx {
+	int device = 0;
+	cudaStream_t stream = nullptr;
+	char err[512] = {0};
+	uint64_t launches = 0;
+	uint64_t last_erosion_steps = 0;
+	// uploaded tables
+	float  *d_sin_table = nullptr;     // [65536]  sin_table (src/sinf.h:11)
+	float2 *d_dir_table = nullptr;     // [1000000] (cosf(a_k), sinf(a_k)), a_k = float(1e-6*k)*TWO_PI, host libm (src/erosion.cpp:85-86)
+	float  *d_sine_params = nullptr;   // [450] sinTable
+	float   h_sine_params[TW_F_TABLE_SIZE*5];
+	bool have_sin = false, have_sine_params = false;
+	// growable device scratch
+	void  *d_scratch[3] = {nullptr, nullptr, nullptr}; // 0: generic output staging, 1: tables / padded heightmaps, 2: small (minmax, counters, origins)
+	size_t scratch_bytes[3] = {0, 0, 0};
+	// pinned host staging for small results
+	void  *h_pinned = nullptr;
+	size_t pinned_bytes = 0;
+	tw_async_state async;
+};
+
+int  tw_set_error(tw_ctx *ctx, int status, const char *fmt, ...);
+int  tw_reserve(tw_ctx *ctx, int slot, size_t bytes);           // grow d_scratch[slot]; returns TW_OK / TW_ERR_CUDA
+int  tw_reserve_pinned(tw_ctx *ctx, size_t bytes);
+bool tw_is_device_ptr(const void *p);
+
+#define TW_CUDA(ctx, call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { \
+	return tw_set_error((ctx), TW_ERR_CUDA, "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); } } while (0)
+#define TW_LAUNCH_CHECK(ctx) do { (ctx)->launches++; cudaError_t e_ = cudaGetLastError(); if (e_ != cudaSuccess) { \
+	return tw_set_error((ctx), TW_ERR_CUDA, "%s:%d kernel launch: %s", __FILE__, __LINE__, cudaGetErrorString(e_)); } } while (0)
+
+// ---- constants shared by host and device code (src/3DWorld.h:43,129; src/sinf.h:8-9) ----
+#define TW_TSIZE 32768
+constexpr float TW_PI_F     = 3.141592654f;
+constexpr float TW_TWO_PI_F = (float)(2.0*TW_PI_F);
+constexpr float TW_SSCALE   = (float)TW_TSIZE/TW_TWO_PI_F;
+
+// order-preserving float <-> uint encoding for atomicMin/atomicMax reductions
+__host__ __device__ inline unsigned tw_f2ord(float f) {
+#ifdef __CUDA_ARCH__
+	unsigned u = __float_as_uint(f);
+#else
+	unsigned u; memcpy(&u, &f, 4);
+#endif
+	return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__host__ __device__ inline float tw_ord2f(unsigned u) {
+	u = (u & 0x80000000u) ? (u & 0x7fffffffu) : ~u;
+#ifdef __CUDA_ARCH__
+	return __uint_as_float(u);
+#else
+	float f; memcpy(&f, &u, 4); return f;
+#endif
+}
+
+// entry points implemented in the individual .cu files (called from tw_api.cu)
+int twi_heightgen(tw_ctx *ctx, const tw_grid2d *g, const tw_height_params *p, int enable_glaciate, int min_start_sin,
+                  const float2 *d_tile_origins, uint32_t ntiles, float *d_out, unsigned *d_mm_ord);
+int twi_erode(tw_ctx *ctx, float *d_maps, uint32_t ntiles, int xsize, int ysize, const float *d_min_zvals, float min_zval_all,
+              uint32_t num_iters, const tw_erosion_params *p);
+int twi_voxel_fill(tw_ctx *ctx, const tw_voxel_params *vp, const float *rdata420, float *d_out);
+int twi_from_floats_u16(tw_ctx *ctx, const float *d_vals, size_t n, float val_mult, float val_add, uint8_t *d_out, unsigned *d_bad);
+int twi_to_floats_u16(tw_ctx *ctx, const uint8_t *d_data, size_t n, float val_mult, float val_add, float *d_vals);
+int twi_minmax(tw_ctx *ctx, const float *d_vals, size_t n, unsigned *d_mm_ord);
+int twi_init_minmax(tw_ctx *ctx, unsigned *d_mm_ord, uint32_t n);

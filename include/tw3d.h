@@ -23,6 +23,12 @@ extern "C" {
 
 #define TW_ABI_VERSION 1
 
+#if defined(__GNUC__)
+#define TW_API __attribute__((visibility("default")))
+#else
+#define TW_API
+#endif
+
 typedef enum tw_status {
 	TW_OK = 0,
 	TW_ERR_NO_DEVICE = -1,   /* no CUDA device / driver: the product path refuses to run (no CPU fallback) */
@@ -96,57 +102,57 @@ typedef struct tw_voxel_params {
 } tw_voxel_params;
 
 /* ---- context ---- */
-int  tw_abi_version(void);
-int  tw_create(int device, tw_ctx **out);
-void tw_destroy(tw_ctx *ctx);
-const char *tw_last_error(const tw_ctx *ctx);
-int  tw_sync(tw_ctx *ctx);                         /* cudaStreamSynchronize on the context stream */
-void *tw_stream(tw_ctx *ctx);                      /* the cudaStream_t all work of this context is issued on */
-uint64_t tw_launch_count(const tw_ctx *ctx);       /* kernels launched by this context so far (bench.py gpu_launches) */
+TW_API int  tw_abi_version(void);
+TW_API int  tw_create(int device, tw_ctx **out);
+TW_API void tw_destroy(tw_ctx *ctx);
+TW_API const char *tw_last_error(const tw_ctx *ctx);
+TW_API int  tw_sync(tw_ctx *ctx);                         /* cudaStreamSynchronize on the context stream */
+TW_API void *tw_stream(tw_ctx *ctx);                      /* the cudaStream_t all work of this context is issued on */
+TW_API uint64_t tw_launch_count(const tw_ctx *ctx);       /* kernels launched by this context so far (bench.py gpu_launches) */
 
 /* ---- host-side table generation (bit-exact restatements; tiny, run once) ---- */
 /* create_sin_table(), src/mesh_gen.cpp:72-81: tab[i]=sinf(i/sscale), tab[i+32768]=cosf(i/sscale) with the host libm. */
-void tw_build_sin_table(float *tab65536);
+TW_API void tw_build_sin_table(float *tab65536);
 /* compute_scale(), src/mesh_gen.cpp:544-548 */
-int  tw_compute_scale(float mesh_scale, int mesh_freq_filter);
+TW_API int  tw_compute_scale(float mesh_scale, int mesh_freq_filter);
 /* rand_gen_t state (src/rand_gen.h:29): pass the same object to successive tw_gen_sine_params calls to reproduce the reference's
  * function-static generator (src/mesh_gen.cpp:237). Initial state {1,1}. */
 typedef struct tw_rng { int64_t rseed1, rseed2; } tw_rng;
 /* gen_rand_sine_table_entries() + apply_mesh_rand_seed(), src/mesh_gen.cpp:213-254 */
-void tw_gen_sine_params(tw_rng *rgen, float scaled_height, int mesh_x_size, int mesh_y_size, float x_scene_size, float y_scene_size,
+TW_API void tw_gen_sine_params(tw_rng *rgen, float scaled_height, int mesh_x_size, int mesh_y_size, float x_scene_size, float y_scene_size,
                         int mesh_seed, int mesh_rgen_index, int mesh_gen_mode, float mesh_start_mag, float mesh_start_freq,
                         float mesh_mag_mult, float mesh_freq_mult, float *sine_params450);
 /* gen_rx_ry(), src/mesh_gen.cpp:581-586 */
-void tw_gen_rx_ry(int mesh_seed, int mesh_rgen_index, int mesh_gen_mode, float *rx, float *ry);
+TW_API void tw_gen_rx_ry(int mesh_seed, int mesh_rgen_index, int mesh_gen_mode, float *rx, float *ry);
 /* noise_gen_3d::set_rand_seeds + gen_sines, src/upsurface.cpp:16-38 */
-void tw_noise3d_gen_sines(int rseed1, int rseed2, float mag, float freq, float *rdata420);
+TW_API void tw_noise3d_gen_sines(int rseed1, int rseed2, float mag, float freq, float *rdata420);
 /* get_water_z_height(), src/mesh_gen.cpp:507-512 (water_h_off/water_h_off_rel as arguments) */
-float tw_water_z_height(float zmax_est, int glaciate, float custom_glaciate_exp, float water_h_off, float water_h_off_rel);
+TW_API float tw_water_z_height(float zmax_est, int glaciate, float custom_glaciate_exp, float water_h_off, float water_h_off_rel);
 
 /* ---- table upload ---- */
 /* sin_table (src/sinf.h:11). tab==NULL: build with tw_build_sin_table. Also builds the 1e6-entry cos/sin direction table used by the
  * erosion random-direction fallback (src/erosion.cpp:84-87) from the host libm so device results match the host bit for bit. */
-int tw_set_sin_table(tw_ctx *ctx, const float *tab65536);
+TW_API int tw_set_sin_table(tw_ctx *ctx, const float *tab65536);
 /* sinTable[90][5] (src/mesh_gen.cpp:40) */
-int tw_set_sine_params(tw_ctx *ctx, const float *sine_params450);
+TW_API int tw_set_sine_params(tw_ctx *ctx, const float *sine_params450);
 
 /* ---- 2-D height generation: build_arrays + enable_glaciate + eval_index over the whole grid ----
  * Replaces mesh_xy_grid_cache_t::{build_arrays,enable_glaciate,eval_index} (src/mesh.h:39-41, src/mesh_gen.cpp:588-650,754-792) as used by
  * heightmap_t::proc_gen (src/heightmap.cpp:130-151), tile_t::create_zvals (src/tiled_mesh.cpp:467-515) and gen_mesh_sine_table
  * (src/mesh_gen.cpp:201-210); for gen modes 3/4 it is the backend behind run_gpu_simplex/cache_gpu_simplex_vals (src/mesh_gen.cpp:652-695).
  * out[y*nx + x] = eval_index(x, y, min_start_sin); mm (optional, host pointer) receives min/max over the grid (fused reduction). */
-int tw_heightgen_2d(tw_ctx *ctx, const tw_grid2d *grid, const tw_height_params *p, int enable_glaciate, int min_start_sin,
+TW_API int tw_heightgen_2d(tw_ctx *ctx, const tw_grid2d *grid, const tw_height_params *p, int enable_glaciate, int min_start_sin,
                     float *out, tw_minmax *mm);
 /* Asynchronous pair mirroring the reference's no_wait contract (src/mesh_gen.cpp:597-603, src/tiled_mesh.cpp:2393-2402):
  * launch returns immediately; poll returns TW_ERR_NOT_READY until the result (and host copy, if out is a host pointer) is complete. */
-int tw_heightgen_2d_launch(tw_ctx *ctx, const tw_grid2d *grid, const tw_height_params *p, int enable_glaciate, int min_start_sin,
+TW_API int tw_heightgen_2d_launch(tw_ctx *ctx, const tw_grid2d *grid, const tw_height_params *p, int enable_glaciate, int min_start_sin,
                            float *out, tw_minmax *mm);
-int tw_heightgen_2d_poll(tw_ctx *ctx, int wait);
+TW_API int tw_heightgen_2d_poll(tw_ctx *ctx, int wait);
 
 /* Batched tile form of tile_t::create_zvals' height fill (src/tiled_mesh.cpp:458-464,495-514): tile t covers
  * build_arrays(origins[2t]-mesh_x_size/2, origins[2t+1]-mesh_y_size/2, dx, dy, zvsize, zvsize) with glaciate enabled;
  * out[t*zvsize*zvsize + y*zvsize + x]. origins is a HOST array of ntiles (x1,y1) pairs. mm (optional, host) = ntiles entries. */
-int tw_heightgen_tiles(tw_ctx *ctx, const int32_t *origins_xy, uint32_t ntiles, int mesh_x_size, int mesh_y_size, float dx, float dy,
+TW_API int tw_heightgen_tiles(tw_ctx *ctx, const int32_t *origins_xy, uint32_t ntiles, int mesh_x_size, int mesh_y_size, float dx, float dy,
                        uint32_t zvsize, const tw_height_params *p, float *out, tw_minmax *mm);
 
 /* ---- hydraulic erosion ----
@@ -154,29 +160,29 @@ int tw_heightgen_tiles(tw_ctx *ctx, const int32_t *origins_xy, uint32_t ntiles, 
  * src/erosion.cpp:14-164): in place, row-major x-fastest, droplets applied in the reference's serial order (iter = 0..num_iters-1;
  * this is the OMP_NUM_THREADS=1 order, the only deterministic one - SURVEY.md section 0). Early-out as the reference when
  * num_iters==0 or erode_amount<=0. */
-int tw_erode(tw_ctx *ctx, float *heightmap, int xsize, int ysize, float min_zval, uint32_t num_iters, const tw_erosion_params *p);
+TW_API int tw_erode(tw_ctx *ctx, float *heightmap, int xsize, int ysize, float min_zval, uint32_t num_iters, const tw_erosion_params *p);
 /* The same on ntiles independent heightmaps stored back to back (tile_t::create_zvals semantics, src/tiled_mesh.cpp:515): every tile
  * gets droplets 0..num_iters-1 exactly as a separate apply_erosion() call would. min_zvals: HOST array of ntiles values, or NULL to use
  * min_zval_all for every tile. */
-int tw_erode_tiles(tw_ctx *ctx, float *heightmaps, uint32_t ntiles, int xsize, int ysize, const float *min_zvals, float min_zval_all,
+TW_API int tw_erode_tiles(tw_ctx *ctx, float *heightmaps, uint32_t ntiles, int xsize, int ysize, const float *min_zvals, float min_zval_all,
                    uint32_t num_iters, const tw_erosion_params *p);
 /* droplet steps executed by the last tw_erode/tw_erode_tiles call (sum over droplets; for roofline byte accounting) */
-uint64_t tw_last_erosion_steps(const tw_ctx *ctx);
+TW_API uint64_t tw_last_erosion_steps(const tw_ctx *ctx);
 
 /* ---- 3-D voxel density ----
  * Replaces the fill loop of voxel_manager::create_procedural (src/voxels.cpp:278-346) + noise_gen_3d::{gen_xyz_vals,get_val}
  * (src/upsurface.cpp:41-70); out[z + (x + y*nx)*nz] (src/voxels.h:141-144). rdata420: noise_gen_3d::rdata (sine mode; host pointer;
  * NULL => generated from rseed1/rseed2/mag/freq with tw_noise3d_gen_sines). */
-int tw_voxel_fill(tw_ctx *ctx, const tw_voxel_params *vp, const float *rdata420, float *out);
+TW_API int tw_voxel_fill(tw_ctx *ctx, const tw_voxel_params *vp, const float *rdata420, float *out);
 
 /* ---- next rows: heightmap quantise, fused streaming passes ----
  * heightmap_t::from_floats 16-bit pack (src/heightmap.cpp:205-215, src/Textures.cpp:1889-1893): v=(h-add)*(1/mult);
  * out[2i+1]=trunc(v), out[2i]=trunc(256*(v-trunc(v))). Returns TW_ERR_ARG if any v is outside [0,256) (the reference asserts). */
-int tw_heightmap_from_floats_u16(tw_ctx *ctx, const float *vals, size_t n, float val_mult, float val_add, uint8_t *out2n);
+TW_API int tw_heightmap_from_floats_u16(tw_ctx *ctx, const float *vals, size_t n, float val_mult, float val_add, uint8_t *out2n);
 /* heightmap_t::to_floats 16-bit unpack (src/heightmap.cpp:191-203) */
-int tw_heightmap_to_floats_u16(tw_ctx *ctx, const uint8_t *data2n, size_t n, float val_mult, float val_add, float *vals);
+TW_API int tw_heightmap_to_floats_u16(tw_ctx *ctx, const uint8_t *data2n, size_t n, float val_mult, float val_add, float *vals);
 /* min/max over a float array (get_heightmap_z_range, src/map_view.cpp:399-407) */
-int tw_minmax_f32(tw_ctx *ctx, const float *vals, size_t n, tw_minmax *mm);
+TW_API int tw_minmax_f32(tw_ctx *ctx, const float *vals, size_t n, tw_minmax *mm);
 
 #ifdef __cplusplus
 }

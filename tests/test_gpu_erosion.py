@@ -1,0 +1,76 @@
+"""GPU parity: tw_erode / tw_erode_tiles (CUDA droplet kernel through the C ABI) vs the CPU oracle in the reference's serial droplet order."""
+import numpy as np
+import pytest
+
+from cases import convert, HM_CFG
+
+pytestmark = pytest.mark.gpu
+
+
+def _terrain(tw, scene, ctx, n, m, mode=1, seed=1):
+    cfg = scene.SceneConfig(mesh_gen_mode=mode, mesh_freq_filter=1, mesh_seed=seed, hmap=HM_CFG, zmax_est=2.0)
+    g = cfg.heightmap_grid(n, m)
+    return cfg, ctx.heightgen_2d(g, cfg.height_params())
+
+
+@pytest.mark.parametrize("n,m,iters", [(130, 130, 1000), (258, 258, 1000), (64, 200, 500), (17, 9, 200), (512, 512, 5000)])
+def test_erode_bit_exact(tw, scene, oracle, ctx, beq, n, m, iters):
+    cfg, z = _terrain(tw, scene, ctx, n, m)
+    zmin, zmax = float(z.min()), float(z.max())
+    for wpz, clip, ea in ((zmin - 10, 0.5, 1.0), ((zmin + zmax) / 2, 0.3, 1.0), (zmin + 0.2 * (zmax - zmin), 2.0, 0.5), (zmin - 10, -1.0, 1.0)):
+        ep = tw.ErosionParams(ea, wpz, 0.0625, zmin - 0.1, zmax + 0.1, 0.0, clip)
+        zc, steps = oracle.apply_erosion(z, zmin, iters, convert(ep, oracle.ErosionParams))
+        zg = ctx.erode(z.copy(), zmin, iters, ep)
+        assert beq(zg, zc) == 0, "max abs diff %g" % np.nanmax(np.abs(zg - zc))
+        assert ctx.last_erosion_steps == steps
+        assert (zg != z).any()
+
+
+def test_erode_disabled_and_flat(tw, oracle, ctx, beq):
+    z = np.zeros((100, 100), np.float32)
+    z[50:, :] = 0.001
+    ep = tw.ErosionParams(1.0, -5.0, 0.0625, -1.0, 1.0, 0.0, 0.5)
+    assert np.array_equal(ctx.erode(z.copy(), -1.0, 0, ep), z)                                      # num_iters == 0: no-op
+    assert np.array_equal(ctx.erode(z.copy(), -1.0, 10, tw.ErosionParams(0.0, -5.0, 0.0625, -1.0, 1.0, 0.0, 0.5)), z)  # erode_amount <= 0
+    zc, _ = oracle.apply_erosion(z, -1.0, 300, convert(ep, oracle.ErosionParams))   # flat ground: random-direction fallback (cos/sin table)
+    assert beq(ctx.erode(z.copy(), -1.0, 300, ep), zc) == 0
+    # min_zval clamp applies to untouched cells too
+    zc, _ = oracle.apply_erosion(z, 0.0005, 3, convert(ep, oracle.ErosionParams))
+    assert beq(ctx.erode(z.copy(), 0.0005, 3, ep), zc) == 0
+
+
+def test_erode_tiles_equals_separate_calls(tw, scene, oracle, ctx, beq):
+    # tile_t::create_zvals semantics: every tile eroded on its own with droplets 0..N-1 (src/tiled_mesh.cpp:515)
+    cfg = scene.SceneConfig(mesh_gen_mode=1, mesh_freq_filter=1, mesh_seed=1, hmap=HM_CFG, zmax_est=2.0, mesh_size=(64, 64, 1))
+    hp = cfg.height_params()
+    S, zv = 64, 66
+    origins = [(tx * S, ty * S) for ty in range(3) for tx in range(3)]
+    tiles = ctx.heightgen_tiles(origins, cfg.mesh_size, float(cfg.dx_val), float(cfg.dy_val), zv, hp)
+    zmin = float(tiles.min())
+    ep = tw.ErosionParams(1.0, zmin - 10.0, 0.0625, zmin - 0.1, float(tiles.max()) + 0.1, 0.0, 0.5)
+    ref_tiles = np.stack([oracle.apply_erosion(t, zmin, 400, convert(ep, oracle.ErosionParams))[0] for t in tiles])
+    got = ctx.erode_tiles(tiles.copy(), 400, ep, min_zval_all=zmin)
+    assert beq(got, ref_tiles) == 0
+    mz = np.linspace(zmin, zmin + 0.5, len(origins)).astype(np.float32)              # per-tile min_zval
+    ref_tiles = np.stack([oracle.apply_erosion(t, float(mz[i]), 50, convert(ep, oracle.ErosionParams))[0] for i, t in enumerate(tiles)])
+    assert beq(ctx.erode_tiles(tiles.copy(), 50, ep, min_zvals=mz), ref_tiles) == 0
+
+
+def test_erode_device_pointer(tw, scene, oracle, ctx, beq):
+    import torch
+    cfg, z = _terrain(tw, scene, ctx, 200, 150, mode=2)
+    zmin = float(z.min())
+    ep = tw.ErosionParams(1.0, zmin - 10.0, 0.0625, zmin - 0.1, float(z.max()) + 0.1, 0.0, 0.5)
+    zc, _ = oracle.apply_erosion(z, zmin, 800, convert(ep, oracle.ErosionParams))
+    zt = torch.from_numpy(z).cuda()
+    ctx.erode(zt, zmin, 800, ep)
+    assert beq(zt.cpu().numpy(), zc) == 0
+
+
+def test_erode_matches_linked_reference(tw, scene, ref, ctx, beq):
+    cfg, z = _terrain(tw, scene, ctx, 258, 258)
+    zmin, zmax = float(z.min()), float(z.max())
+    ref.lib().ref_set_threads(1)   # the only deterministic order
+    zr = ref.apply_erosion(z, zmin, 1000, water_plane_z=zmin - 10, zmin=zmin - 0.1, zmax=zmax + 0.1, clip_hd1=0.5)
+    zg = ctx.erode(z.copy(), zmin, 1000, tw.ErosionParams(1.0, zmin - 10, 0.0625, zmin - 0.1, zmax + 0.1, 0.0, 0.5))
+    assert beq(zg, zr) == 0

@@ -1,0 +1,121 @@
+"""GPU parity: tw_heightgen_2d / tw_heightgen_tiles (CUDA, through the C ABI) vs the CPU oracle - bit-exact for every gen mode."""
+import numpy as np
+import pytest
+
+from cases import convert, height_cases, HM_CFG
+
+pytestmark = pytest.mark.gpu
+
+
+def _run_case(tw, scene, oracle, ctx, kw, org, size, sp_cache={}):
+    cfg = scene.SceneConfig(**kw)
+    hp = cfg.height_params()
+    key = (cfg.mesh_seed, cfg.mesh_gen_mode)
+    if key not in sp_cache:
+        sp_cache[key] = cfg.sine_params()
+    sp = sp_cache[key]
+    x0, y0, dxm = org
+    g = tw.Grid2D(x0, y0, float(cfg.dx_val) * dxm, float(cfg.dy_val) * dxm, size[0], size[1])
+    ctx.set_sine_params(sp)
+    z_gpu, mm = ctx.heightgen_2d(g, hp, enable_glaciate=1, want_minmax=True)
+    z_cpu = oracle.heightgen_2d(convert(g, oracle.Grid2D), convert(hp, oracle.HeightParams), sp, 1, 0)
+    return z_gpu, z_cpu, mm
+
+
+@pytest.mark.parametrize("name,kw,org,size", height_cases(), ids=[c[0] for c in height_cases()])
+def test_heightgen_bit_exact(tw, scene, oracle, ctx, beq, name, kw, org, size):
+    z_gpu, z_cpu, mm = _run_case(tw, scene, oracle, ctx, kw, org, size)
+    assert beq(z_gpu, z_cpu) == 0, "max abs diff %g" % np.abs(z_gpu - z_cpu).max()
+    assert mm[0] == z_cpu.min() and mm[1] == z_cpu.max()   # fused min/max reduction
+
+
+def test_sine_min_start_sin_and_no_glaciate(tw, scene, oracle, ctx, beq):
+    cfg = scene.SceneConfig(mesh_gen_mode=0, mesh_freq_filter=0, mesh_seed=6, hmap=HM_CFG, zmax_est=1.5)
+    hp, sp = cfg.height_params(), cfg.sine_params()
+    ctx.set_sine_params(sp)
+    for nx, ny in ((1, 1), (3, 200), (257, 65), (64, 64)):
+        g = tw.Grid2D(-7.0, 11.0, float(cfg.dx_val), float(cfg.dy_val), nx, ny)
+        for mss in (0, 50, 20):
+            for gl in (0, 1):
+                zg = ctx.heightgen_2d(g, hp, enable_glaciate=gl, min_start_sin=mss)
+                zc = oracle.heightgen_2d(convert(g, oracle.Grid2D), convert(hp, oracle.HeightParams), sp, gl, mss)
+                assert beq(zg, zc) == 0
+
+
+def test_custom_glaciate_exp_within_tolerance(tw, scene, oracle, ctx):
+    # pow(relh, custom) uses CUDA powf vs glibc powf: not bit-exact by construction; north_star tolerance 1e-5 relative per cell
+    cfg = scene.SceneConfig(mesh_gen_mode=1, mesh_freq_filter=1, mesh_seed=1, hmap=HM_CFG, zmax_est=2.3, custom_glaciate_exp=2.5)
+    hp = cfg.height_params()
+    g = tw.Grid2D(-64, -64, float(cfg.dx_val), float(cfg.dy_val), 128, 128)
+    zg = ctx.heightgen_2d(g, hp)
+    zc = oracle.heightgen_2d(convert(g, oracle.Grid2D), convert(hp, oracle.HeightParams), None, 1, 0)
+    assert np.all(np.abs(zg - zc) <= 1e-5 * np.maximum(np.abs(zg), np.abs(zc)) + 1e-5 * cfg.zmax_est)
+
+
+def test_device_pointer_output_and_async(tw, scene, oracle, ctx, beq):
+    import torch
+    cfg = scene.SceneConfig(mesh_gen_mode=4, mesh_freq_filter=1, mesh_seed=1, hmap=HM_CFG, zmax_est=2.3)
+    hp = cfg.height_params()
+    g = cfg.heightmap_grid(96, 80)
+    out = torch.empty((80, 96), dtype=torch.float32, device="cuda")
+    mm = tw.MinMax()
+    ctx.heightgen_2d_launch(g, hp, 1, 0, out, mm)      # mirrors build_arrays(no_wait=1) ...
+    while not ctx.heightgen_2d_poll(wait=False):        # ... and the next-frame collection
+        pass
+    zc = oracle.heightgen_2d(convert(g, oracle.Grid2D), convert(hp, oracle.HeightParams), None, 1, 0)
+    assert beq(out.cpu().numpy(), zc) == 0
+    assert mm.zmin == zc.min() and mm.zmax == zc.max()
+
+
+@pytest.mark.parametrize("mode", [0, 1, 4])
+def test_tiles_match_per_tile_calls(tw, scene, oracle, ctx, beq, mode):
+    # tile_t::create_zvals height fill for a 3x2 block of tiles, zvsize = size+2 (src/tiled_mesh.cpp:302,458-464)
+    cfg = scene.SceneConfig(mesh_gen_mode=mode, mesh_freq_filter=1, mesh_seed=1, hmap=HM_CFG, zmax_est=2.3, mesh_size=(64, 64, 1))
+    hp, sp = cfg.height_params(), cfg.sine_params()
+    ctx.set_sine_params(sp)
+    S, zv = 64, 66
+    origins = [(tx * S - 7 * S, ty * S + 3 * S) for ty in range(2) for tx in range(3)]
+    tiles, mm = ctx.heightgen_tiles(origins, cfg.mesh_size, float(cfg.dx_val), float(cfg.dy_val), zv, hp, want_minmax=True)
+    for t, (x1, y1) in enumerate(origins):
+        g = oracle.Grid2D(float(x1 - S // 2), float(y1 - S // 2), float(cfg.dx_val), float(cfg.dy_val), zv, zv)
+        zc = oracle.heightgen_2d(g, convert(hp, oracle.HeightParams), sp, 1, 0)
+        assert beq(tiles[t], zc) == 0
+        assert mm[t, 0] == zc.min() and mm[t, 1] == zc.max()
+    # neighbouring tiles overlap by 2 cells and must agree exactly there (height is a pure function of global coordinates)
+    assert np.array_equal(tiles[0][:, S:S + 2], tiles[1][:, 0:2])
+
+
+def test_full_size_properties(tw, scene, oracle, ctx, beq):
+    """BASELINE config 2 at full size (8192^2, 8-octave domain warp): size-independent checks - a row band recomputed as its own grid
+    is bit-identical (pure function of global coordinates), an oracle-sized window matches the oracle, min/max equal a separate reduction."""
+    import torch
+    cfg = scene.SceneConfig(mesh_gen_mode=4, mesh_freq_filter=1, mesh_seed=1, hmap=HM_CFG, zmax_est=2.3)
+    hp = cfg.height_params()
+    N = 8192
+    g = cfg.heightmap_grid(N, N)
+    out = torch.empty((N, N), dtype=torch.float32, device="cuda")
+    _, mm = ctx.heightgen_2d(g, hp, out=out, want_minmax=True)
+    assert torch.isfinite(out).all()
+    assert mm == (out.min().item(), out.max().item())
+    assert mm == ctx.minmax(out)
+    y0, rows = 5000, 64
+    gb = tw.Grid2D(g.x0, g.y0 + y0, g.dx, g.dy, N, rows)
+    band = ctx.heightgen_2d(gb, hp)
+    assert beq(band, out[y0:y0 + rows].cpu().numpy()) == 0
+    gw = oracle.Grid2D(g.x0 + 4000, g.y0 + 6000, g.dx, g.dy, 96, 64)
+    zc = oracle.heightgen_2d(gw, convert(hp, oracle.HeightParams), None, 1, 0)
+    assert beq(out[6000:6064, 4000:4096].cpu().numpy(), zc) == 0
+
+
+def test_matches_linked_reference(tw, scene, ref, ctx, beq):
+    """Directly against the unmodified reference objects (oracle/_ref travels to the GPU box as a prebuilt .so)."""
+    for mode in (0, 1, 2, 4):
+        ref.setup(mode=mode, freq_filter=1, seed=1, zmax_est=2.3, hmap=HM_CFG)
+        cfg = scene.SceneConfig(mesh_gen_mode=mode, mesh_freq_filter=1, mesh_seed=1, hmap=HM_CFG, zmax_est=2.3)
+        hp = cfg.height_params()
+        sp = ref.sine_params()
+        ctx.set_sine_params(sp)
+        n = 80
+        zr = ref.heightgen(-n / 2, -n / 2, float(cfg.dx_val), float(cfg.dy_val), n, n, cache_values=0, glaciate=1)
+        zg = ctx.heightgen_2d(tw.Grid2D(-n / 2, -n / 2, float(cfg.dx_val), float(cfg.dy_val), n, n), hp)
+        assert beq(zg, zr) == 0

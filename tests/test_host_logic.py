@@ -1,0 +1,84 @@
+"""CPU: the product's host-side code (no GPU needed): C-ABI exports, loud failure without a device, host table generators vs the golden
+fixtures, the scene-config mirror, and the rank sharding used by bench.py."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+def test_library_exports_every_declared_symbol(tw):
+    hdr = open(os.path.join(ROOT, "include", "tw3d.h")).read()
+    declared = sorted(set(re.findall(r"TW_API[^;(]*?\b(tw_\w+)\s*\(", hdr)))
+    assert declared == sorted(tw.ABI_SYMBOLS)
+    out = subprocess.check_output(["nm", "-D", "--defined-only", tw.LIB_PATH], text=True)
+    exported = set(re.findall(r" T (tw_\w+)", out))
+    assert set(declared) <= exported, sorted(set(declared) - exported)
+    assert tw.lib.tw_abi_version() == 1
+
+
+def test_no_cpu_fallback(tw):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    h = C.c_void_p()
+    assert tw.lib.tw_create(0, C.byref(h)) == tw.TW_ERR_NO_DEVICE and not h.value
+    with pytest.raises(tw.TwError):
+        tw.Context(0)
+
+
+def test_product_never_imports_the_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "3dworld_b200")):
+        if os.path.basename(dirpath) == "build":
+            continue
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "terrain_oracle" not in src and "refapi" not in src and "oracle." not in src.replace("oracle.py", ""), os.path.join(dirpath, f)
+
+
+def test_host_generators_match_golden(tw, beq):
+    t = np.load(os.path.join(GOLD, "host_tables.npz"))
+    assert beq(tw.build_sin_table(), t["sin_table"]) == 0
+    for i in range(4):
+        mode, seed, idx, mx, my, sx, sy, mhs = t["sp%d_args" % i]
+        sh = np.float32(0.1) * np.float32(4.0) * np.float32(mhs)
+        sp = tw.gen_sine_params(sh, mesh=(int(mx), int(my)), scene=(float(sx), float(sy)), seed=int(seed), rgen_index=int(idx), mode=int(mode))
+        assert beq(sp, t["sp%d" % i]) == 0
+        assert beq(np.array(tw.gen_rx_ry(int(seed), int(idx), int(mode)), np.float32), t["rxry%d" % i]) == 0
+    assert beq(tw.noise3d_gen_sines(123, 456, 1.0, 1.0), t["rdata_123_456"]) == 0
+    assert beq(tw.noise3d_gen_sines(7, 9, 2.5, 0.3), t["rdata_7_9"]) == 0
+    k = np.load(os.path.join(GOLD, "kat.npz"))
+    rng = tw.Rng(1, 1)   # the reference's function-static generator in a fresh process
+    assert beq(tw.gen_sine_params(np.float32(0.4), rng=rng), k["sine_params_fresh_process"]) == 0
+    assert (rng.rseed1, rng.rseed2) != (1, 1)   # state advances: a second call yields a different table, as in the reference
+    assert beq(tw.gen_sine_params(np.float32(0.4), rng=rng), k["sine_params_fresh_process"]) != 0
+
+
+def test_host_generators_match_oracle(tw, oracle, beq):
+    for ms in (0.3, 1.0, 2.0, 4.0, 64.0, 1000.0):
+        for ff in range(-2, 8):
+            assert tw.compute_scale(ms, ff) == oracle.compute_scale(ms, ff)
+    assert tw.compute_scale(1.0, 1) == 10     # 8 octaves
+    for seed, idx, mode in ((0, 0, 0), (0, 5, 1), (7, 0, 4), (-3, 2, 2)):
+        assert tw.gen_rx_ry(seed, idx, mode) == oracle.gen_rx_ry(seed, idx, mode)
+    for args in ((1.0, 1, 0.0, 0.0, 0.0), (2.3, 1, 2.5, 0.1, 0.05), (0.5, 0, 0.0, 0.0, 0.7)):
+        assert tw.water_z_height(*args) == oracle.lib().to_water_z_height(*args)
+
+
+def test_scene_config(tw, scene):
+    cfg = scene.SceneConfig(mesh_gen_mode=4, mesh_freq_filter=1, mesh_seed=1, zmax_est=2.3)
+    hp = cfg.height_params()
+    assert float(cfg.dx_val) == 0.0625 and hp.dx_val_inv == 16.0 and hp.start_eval_sin == 10
+    assert abs(hp.mesh_height - 0.4) < 1e-7
+    g = cfg.heightmap_grid(8192, 8192)
+    assert (g.x0, g.y0, g.nx, g.ny) == (-4096.0, -4096.0, 8192, 8192)
+    ep = cfg.erosion_params()
+    assert ep.zmin == pytest.approx(-2.3) and 0.0 < ep.clip_hd1 < 1.0
+    vp = scene.voxel_landscape_params(scene.SceneConfig(scene_size=(16.0, 16.0, 4.0), mesh_size=(128, 128, 64)), 512, 512, 512)
+    assert vp.nx == 512 and vp.rseed2 == 456 and vp.vsz[0] > 0

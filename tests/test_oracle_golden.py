@@ -1,0 +1,121 @@
+"""CPU: the plain-C oracle reproduces the committed golden fixtures (outputs of the unmodified reference code) bit for bit."""
+import ctypes as C
+import os
+
+import numpy as np
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def load(name):
+    return np.load(os.path.join(GOLD, name))
+
+
+def hp_from_args(O, args, hmap, seed=1):
+    mode, shape, ff, gl = (int(v) for v in args[:4])
+    hp = O.HeightParams()
+    hp.gen_mode, hp.gen_shape, hp.start_eval_sin, hp.glaciate = mode, shape, O.compute_scale(1.0, ff), gl
+    hp.mesh_scale, hp.mesh_scale_z_inv = 1.0, 1.0
+    hp.dx_val_inv = hp.dy_val_inv = 16.0          # mesh 128, scene 4 => DX_VAL = 0.0625
+    hp.mesh_height, hp.mesh_height_scale = np.float32(0.1) * np.float32(4.0), 1.0
+    hp.zmax_est, hp.custom_glaciate_exp = 2.3, 0.0
+    hp.rx, hp.ry = O.gen_rx_ry(seed, 0, mode)
+    hp.hmap = O.HmapParams(*[float(v) for v in hmap])
+    return hp
+
+
+def test_kat_values_from_survey(oracle, beq):
+    k = load("kat.npz")
+    # eval_index(3,5) = 1.15601587 / -3.95350838 / 1.79742229, noise_gen_3d get_val = 1.25381982
+    assert abs(float(k["eval_index_3_5_mode0"]) - 1.15601587) < 5e-8
+    assert abs(float(k["eval_index_3_5_mode1"]) + 3.95350838) < 5e-7
+    assert abs(float(k["eval_index_3_5_mode2"]) - 1.79742229) < 5e-7
+    assert abs(float(k["noise3d_point"]) - 1.25381982) < 5e-7
+    sp = oracle.gen_sine_params(np.float32(0.4), seed=0, mode=0, rng=oracle.Rng(1, 1))
+    assert beq(sp, k["sine_params_fresh_process"]) == 0
+    for mode in (0, 1, 2):
+        hp = hp_from_args(oracle, [mode, 0, 0, 0], [1000.0, 0, 0, 0, 1000.0] + [0] * 9, seed=0)
+        z = oracle.heightgen_2d(oracle.Grid2D(0, 0, 0.0625, 0.0625, 8, 8), hp, sp, 0, 0)
+        assert np.float32(z[5, 3]) == k["eval_index_3_5_mode%d" % mode]
+    rd = oracle.noise3d_gen_sines(123, 456, 1.0, 1.0)
+    v = oracle.lib().to_noise3d_get_val_pt(rd.ctypes.data_as(C.c_void_p), oracle.sin_table().ctypes.data_as(C.c_void_p), 0.1, 0.2, 0.3)
+    assert np.float32(v) == k["noise3d_point"]
+
+
+def test_glm_noise(oracle, beq):
+    g = load("glm_noise.npz")
+    L = oracle.lib()
+    for name in ("simplex2", "perlin2", "simplex3", "perlin3"):
+        f = getattr(L, "to_" + name)
+        got = np.array([f(*[float(v) for v in p]) for p in g[name + "_in"]], np.float32)
+        assert beq(got, g[name + "_out"]) == 0, name
+
+
+def test_host_tables(oracle, beq):
+    t = load("host_tables.npz")
+    assert beq(oracle.sin_table(), t["sin_table"]) == 0
+    for i in range(4):
+        mode, seed, idx, mx, my, sx, sy, mhs = t["sp%d_args" % i]
+        sh = np.float32(0.1) * np.float32(4.0) * np.float32(mhs)
+        sp = oracle.gen_sine_params(sh, mesh=(int(mx), int(my)), scene=(float(sx), float(sy)), seed=int(seed), rgen_index=int(idx), mode=int(mode))
+        if int(seed) != 0 or int(mode) != 0:   # otherwise the reference's function-static rng state depends on call history
+            assert beq(sp, t["sp%d" % i]) == 0
+        assert beq(np.array(oracle.gen_rx_ry(int(seed), int(idx), int(mode)), np.float32), t["rxry%d" % i]) == 0
+    assert beq(oracle.noise3d_gen_sines(123, 456, 1.0, 1.0), t["rdata_123_456"]) == 0
+    assert beq(oracle.noise3d_gen_sines(7, 9, 2.5, 0.3), t["rdata_7_9"]) == 0
+
+
+def test_height_grids(oracle, beq):
+    h = load("height.npz")
+    for mode in range(5):
+        for shape in range(3):
+            n = "h_m%d_s%d" % (mode, shape)
+            a = h[n + "_args"]
+            hp = hp_from_args(oracle, a, h[n + "_hmap"])
+            g = oracle.Grid2D(a[4], a[5], 0.0625, 0.0625, int(a[6]), int(a[7]))
+            z = oracle.heightgen_2d(g, hp, h[n + "_sp"] if mode == 0 else None, 1, 0)
+            assert beq(z, h[n]) == 0, n
+    hp = hp_from_args(oracle, [0, 0, 2, 1], [1000.0, 0, 0, 0, 1000.0] + [0] * 9)
+    hp.mesh_height_scale, hp.zmax_est = 0.7, 0.5
+    z = oracle.heightgen_2d(oracle.Grid2D(-64, -64, 0.0625, 0.0625, 128, 128), hp, h["cfg1_sp"], 1, 0)
+    assert beq(z, h["cfg1"]) == 0
+
+
+def test_erosion(oracle, beq):
+    e = load("erosion.npz")
+    for key_in, keys in (("in0", ["0_%d" % i for i in range(3)]), ("mesh128_in", ["mesh128"])):
+        for k in keys:
+            a = e["args" + k] if k != "mesh128" else e["mesh128_args"]
+            ep = oracle.ErosionParams(*[float(v) for v in a[2:]])
+            out, steps = oracle.apply_erosion(e[key_in], float(a[0]), int(a[1]), ep)
+            exp = e["out" + k] if k != "mesh128" else e["mesh128_out"]
+            assert beq(out, exp) == 0, k
+            assert steps > 0
+
+
+def test_voxels(oracle, beq):
+    v = load("voxel.npz")
+    geo = v["geom"]
+    for mode in (0, 1, 2):
+        for name, norm, zs in (("v%d" % mode, 1, 0.0), ("v%d_unclamped" % mode, 0, 0.01)):
+            vp = oracle.VoxelParams()
+            vp.nx, vp.ny, vp.nz = 20, 12, 28
+            for d in range(3):
+                vp.lo_pos[d], vp.vsz[d], vp.offset[d] = geo[d], geo[3 + d], geo[6 + d]
+            vp.mag = vp.freq = 1.0
+            vp.gen_mode, vp.normalize_to_1, vp.rseed1, vp.rseed2, vp.octaves = mode, norm, 123, 456, 3
+            vp.rx, vp.ry = (float(x) for x in v["v%d_rxry" % mode])
+            vp.zscale = zs
+            assert beq(oracle.voxel_fill(vp), v[name]) == 0, name
+
+
+def test_u16_pack_roundtrip(oracle):
+    rng = np.random.default_rng(3)
+    vals = rng.uniform(10.0, 20.0, 1000).astype(np.float32)
+    mult, add = np.float32(10.0 / 255.0), np.float32(10.0)
+    packed, bad = oracle.from_floats_u16(vals, float(mult), float(add))
+    assert bad == 0
+    back = oracle.to_floats_u16(packed, float(mult), float(add))
+    assert np.abs(back - vals).max() <= float(mult) / 256.0 * 1.01 + 1e-6
+    _, bad = oracle.from_floats_u16(np.array([0.0], np.float32), 1.0, 1.0)   # v = -1: out of range
+    assert bad == 1

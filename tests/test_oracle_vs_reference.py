@@ -1,0 +1,79 @@
+"""CPU: the plain-C oracle vs the UNMODIFIED reference objects (oracle/_ref), bit for bit, on randomised inputs.
+This is what pins the oracle (the reference has no tests of its own for this path). Skipped when oracle/_ref is not built."""
+import numpy as np
+
+from cases import HM_ALL, HM_CFG
+
+
+def _hp(O, R, mode, shape, ff, seed, hmap, zmax_est, gl, custom=0.0, ms=1.0):
+    R.setup(mode=mode, shape=shape, freq_filter=ff, seed=seed, glaciate=gl, custom_glaciate_exp=custom, hmap=hmap, zmax_est=zmax_est, mesh_scale=ms)
+    RL = R.lib()
+    hp = O.HeightParams()
+    hp.gen_mode, hp.gen_shape, hp.start_eval_sin, hp.glaciate = mode, shape, O.compute_scale(ms, ff), gl
+    assert hp.start_eval_sin == RL.ref_get_start_eval_sin()
+    hp.mesh_scale, hp.mesh_scale_z_inv = ms, 1.0
+    hp.dx_val_inv, hp.dy_val_inv = 1.0 / np.float32(RL.ref_get_dx()), 1.0 / np.float32(RL.ref_get_dy())
+    hp.mesh_height, hp.mesh_height_scale = RL.ref_get_mesh_height(), 1.0
+    hp.zmax_est, hp.custom_glaciate_exp = zmax_est, custom
+    hp.rx, hp.ry = O.gen_rx_ry(seed, 0, mode)
+    assert (hp.rx, hp.ry) == R.rx_ry()
+    hp.hmap = O.hmap_params(**(hmap or {}))
+    return hp
+
+
+def test_glm_noise_random_points(oracle, ref, beq):
+    rng = np.random.default_rng(0)
+    for name, k in (("simplex2", 2), ("perlin2", 2), ("simplex3", 3), ("perlin3", 3)):
+        pts = (rng.standard_normal((4000, k)) * rng.choice([0.5, 3, 50, 1000, 1e5], (4000, 1))).astype(np.float32)
+        pts[:500] = np.round(pts[:500])
+        fr, fo = getattr(ref.lib(), "ref_glm_" + name), getattr(oracle.lib(), "to_" + name)
+        a = np.array([fr(*[float(v) for v in p]) for p in pts], np.float32)
+        b = np.array([fo(*[float(v) for v in p]) for p in pts], np.float32)
+        assert beq(a, b) == 0, name
+
+
+def test_heightgen_all_modes(oracle, ref, beq):
+    RL = ref.lib()
+    for mode in (0, 1, 2, 3, 4):
+        for shape in (0, 1, 2):
+            for ff, hmap, gl, custom, ms in ((1, HM_CFG, 1, 0.0, 1.0), (0, None, 0, 0.0, 1.0), (2, HM_ALL, 1, 0.0, 1.0), (1, HM_CFG, 1, 2.5, 1.0), (1, HM_ALL, 1, 0.0, 4.0)):
+                hp = _hp(oracle, ref, mode, shape, ff, 1, hmap, 2.3, gl, custom, ms)
+                sp = ref.sine_params()
+                n = 48 if mode == 4 else 80
+                for x0, y0, dxm in ((-n / 2, -n / 2, 1.0), (-50000.0, 70000.0, 3.0)):
+                    dx, dy = RL.ref_get_dx() * dxm, RL.ref_get_dy() * dxm
+                    zr = ref.heightgen(x0, y0, dx, dy, n, n - 7, cache_values=0, glaciate=1)
+                    zo = oracle.heightgen_2d(oracle.Grid2D(x0, y0, dx, dy, n, n - 7), hp, sp, 1, 0)
+                    assert beq(zr, zo) == 0, (mode, shape, ff, custom, ms, x0)
+
+
+def test_erosion_serial_order(oracle, ref, beq):
+    ref.lib().ref_set_threads(1)
+    ref.setup(mode=1, freq_filter=1, seed=1, zmax_est=2.0, hmap=HM_CFG)
+    RL = ref.lib()
+    for n, m, iters in ((130, 130, 1000), (64, 200, 500), (258, 258, 600)):
+        z = ref.heightgen(-n / 2, -m / 2, RL.ref_get_dx(), RL.ref_get_dy(), n, m, 0, 1)
+        zmin, zmax = float(z.min()), float(z.max())
+        for wpz, clip, ea in ((zmin - 10, 0.5, 1.0), ((zmin + zmax) / 2, 0.3, 1.0), (zmin - 10, -1.0, 0.5)):
+            zr = ref.apply_erosion(z, zmin, iters, erode_amount=ea, water_plane_z=wpz, zmin=zmin - 0.1, zmax=zmax + 0.1, clip_hd1=clip)
+            zo, _ = oracle.apply_erosion(z, zmin, iters, oracle.ErosionParams(ea, wpz, 0.0625, zmin - 0.1, zmax + 0.1, 0.0, clip))
+            assert beq(zr, zo) == 0
+    ref.lib().ref_set_threads(8)
+
+
+def test_voxel_fill(oracle, ref, beq):
+    lo, vsz, off = (-7.9, -7.8, -1.5), (0.4, 0.65, 0.11), (0.5, -0.25, 0.0)
+    for mode in (0, 1, 2):
+        for ff in (2, 0):
+            ref.setup(mode=mode, freq_filter=ff, seed=3)
+            rx, ry = ref.rx_ry()
+            for norm, zs in ((1, 0.0), (0, 0.01)):
+                zr = ref.voxel_fill(24, 10, 30, lo, vsz, off, 1.0, 1.0, norm, 123, 456, mode, zs)
+                vp = oracle.VoxelParams()
+                vp.nx, vp.ny, vp.nz = 24, 10, 30
+                for d in range(3):
+                    vp.lo_pos[d], vp.vsz[d], vp.offset[d] = lo[d], vsz[d], off[d]
+                vp.mag = vp.freq = 1.0
+                vp.gen_mode, vp.normalize_to_1, vp.rseed1, vp.rseed2, vp.octaves = mode, norm, 123, 456, max(1, 5 - ff)
+                vp.rx, vp.ry, vp.zscale = rx, ry, zs
+                assert beq(zr, oracle.voxel_fill(vp)) == 0
