@@ -104,7 +104,7 @@ droplet_kernel(float *__restrict__ padded, unsigned ntiles, int xsize, int ysize
 			}
 			else {dx=__fdiv_rn(dx, dl); dz=__fdiv_rn(dz, dl);}
 			float const nxp=xp+dx, nzp=zp+dz;
-			int const nxi=(int)floorf(nxp), nzi=(int)floorf(nzp);
+			int const nxi=tw_x86_f2i(floorf(nxp)), nzi=tw_x86_f2i(floorf(nzp)); // x86 semantics: NaN -> INT_MIN -> "outside" next step
 			float const nxf=nxp-(float)nxi, nzf=nzp-(float)nzi;
 			float const nh00=HMAP(nxi, nzi), nh10=HMAP(nxi+1, nzi), nh01=HMAP(nxi, nzi+1), nh11=HMAP(nxi+1, nzi+1);
 			float const nh=(nh00*(1-nxf)+nh10*nxf)*(1-nzf)+(nh01*(1-nxf)+nh11*nxf)*nzf;

@@ -17,10 +17,10 @@ namespace {
 constexpr int F_TABLE = TW_F_TABLE_SIZE;
 
 __device__ __forceinline__ float sinf_lut(const float *__restrict__ tab, float v) { // SINF, src/sinf.h:13-14
-	return (v < 0.0f) ? -__ldg(tab + (((int)(TW_SSCALE*(-v)))&(TW_TSIZE-1))) : __ldg(tab + (((int)(TW_SSCALE*v))&(TW_TSIZE-1)));
+	return (v < 0.0f) ? -__ldg(tab + (tw_x86_f2i(TW_SSCALE*(-v))&(TW_TSIZE-1))) : __ldg(tab + (tw_x86_f2i(TW_SSCALE*v)&(TW_TSIZE-1)));
 }
 __device__ __forceinline__ float cosf_lut(const float *__restrict__ tab, float v) { // COSF, src/sinf.h:15
-	return __ldg(tab + TW_TSIZE + (((int)(TW_SSCALE*fabsf(v)))&(TW_TSIZE-1)));
+	return __ldg(tab + TW_TSIZE + (tw_x86_f2i(TW_SSCALE*fabsf(v))&(TW_TSIZE-1)));
 }
 __device__ __forceinline__ float smin(float a, float b) {return (b < a) ? b : a;} // std::min
 __device__ __forceinline__ float smax(float a, float b) {return (a < b) ? b : a;} // std::max

@@ -52,6 +52,14 @@ constexpr float TW_PI_F     = 3.141592654f;
 constexpr float TW_TWO_PI_F = (float)(2.0*TW_PI_F);
 constexpr float TW_SSCALE   = (float)TW_TSIZE/TW_TWO_PI_F;
 
+// float -> int conversion with the semantics the reference build gets from x86 cvttss2si: truncation toward zero, and the
+// "integer indefinite" value INT_MIN for NaN and for anything outside int range (CUDA's cvt would give 0 / saturate instead).
+// This matters: a droplet whose state went NaN (SURVEY.md section 7 "NaN hazard") terminates because (int)floor(NaN) == INT_MIN
+// makes it "outside" (src/erosion.cpp:93,101), and SINF's table index (src/sinf.h:11) wraps the same way for huge arguments.
+__device__ __forceinline__ int tw_x86_f2i(float f) {
+	return (f >= -2147483648.0f && f < 2147483648.0f) ? __float2int_rz(f) : (int)0x80000000;
+}
+
 // order-preserving float <-> uint encoding for atomicMin/atomicMax reductions
 __host__ __device__ inline unsigned tw_f2ord(float f) {
 #ifdef __CUDA_ARCH__

@@ -16,7 +16,7 @@ namespace {
 constexpr int NS = TW_N3D_SINES; // 60
 
 __device__ __forceinline__ float sinf_lut(const float *__restrict__ tab, float v) {
-	return (v < 0.0f) ? -__ldg(tab + (((int)(TW_SSCALE*(-v)))&(TW_TSIZE-1))) : __ldg(tab + (((int)(TW_SSCALE*v))&(TW_TSIZE-1)));
+	return (v < 0.0f) ? -__ldg(tab + (tw_x86_f2i(TW_SSCALE*(-v))&(TW_TSIZE-1))) : __ldg(tab + (tw_x86_f2i(TW_SSCALE*v)&(TW_TSIZE-1)));
 }
 __device__ __forceinline__ float smin(float a, float b) {return (b < a) ? b : a;}
 __device__ __forceinline__ float smax(float a, float b) {return (a < b) ? b : a;}

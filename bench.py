@@ -1,0 +1,331 @@
+#!/usr/bin/env python
+"""bench.py - headline benchmark of the terrain hot path (BASELINE.json: "height cells/s @8192^2 8-octave").
+
+A step = one pass of the hot path over one 8192x8192 tile: tw_heightgen_2d (8-octave domain-warped simplex fBm, glaciate + hmap sine bias,
+fused min/max), BASELINE.json configs[1]. `value` is measured with the output resident in HBM (CUDA events on the library's own stream);
+`e2e` is the same call with a pinned HOST output buffer, i.e. including the device->host copy of the 268 MB grid and the host->device
+copy of the parameter blocks, through the public C ABI. N>1 (torchrun): every rank generates its own 8192^2 tile of one larger terrain
+(tiles are pure functions of global coordinates: no data-path collective; one 2-float min/max all-reduce per step) => weak scaling.
+
+--impl reference times the reference's own CPU implementation (the unmodified reference objects in oracle/_ref when present, else the
+plain-C oracle port) on the host cores, on a bounded sample of the same workload.
+"""
+import argparse
+import ctypes as C
+import importlib
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+HM_CFG = dict(sine_mag=5.0, sine_freq=0.001, sine_bias=-4.0)   # scene_config/config.txt:76
+N_TILE = 8192
+WORKLOAD = "heightgen 8192x8192 tile, mesh_gen_mode 4 (domain-warped simplex), 8 octaves (mesh_freq_filter 1), fp32, glaciate + hmap sine"
+FLOP_PER_CELL = 6800.0    # ~5 fBm x 8 octaves x ~170 fp32 ops (non-fusable), hand count +-15 %
+BYTES_PER_CELL = 4.0      # one fp32 store per cell, no reads
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured", float(d.get("sm_max_mhz", 1965.0))
+    return 6650.0, "fallback", 1965.0
+
+
+class ClockSampler:
+    """nvidia-smi -lms 100 in the background during the timed region (the profiling recipe's clocks line)."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.lines = []
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append((time.perf_counter(), ln))
+
+    def mark(self):
+        self.t0 = time.perf_counter()
+
+    def summary(self):
+        t1 = time.perf_counter()
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        rows = [[x.strip() for x in ln.split(",")] for (t, ln) in self.lines if self.t0 <= t <= t1 + 0.12]
+        rows = [r for r in rows if len(r) >= 7]
+        if not rows:
+            rows = [[x.strip() for x in ln.split(",")] for (t, ln) in self.lines][-3:]
+            rows = [r for r in rows if len(r) >= 7]
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
+        sm = sorted(float(r[0]) for r in rows)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[3 + i].lower().startswith("active") for r in rows)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(rows[0][1]), "power_w_max": max(float(r[2]) for r in rows), "reasons": reasons, "samples": len(rows)}
+
+
+def cpu_runner(cores, nx, ny):
+    """The reference's own CPU path for the workload on an nx x ny window (build_arrays + enable_glaciate + eval_index over the grid):
+    the unmodified reference objects (oracle/_ref) when the prebuilt library is present, else the plain-C oracle port."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    try:
+        import refapi as R
+        if R.available():
+            R.lib().ref_set_threads(cores)
+            R.setup(mode=4, freq_filter=1, seed=1, zmax_est=2.3, hmap=HM_CFG)
+            dx, dy = R.lib().ref_get_dx(), R.lib().ref_get_dy()
+            return "reference", (lambda rows=ny: R.heightgen(-N_TILE / 2, -N_TILE / 2, dx, dy, nx, rows, cache_values=0, glaciate=1))
+    except Exception:
+        pass
+    import oracle as O
+    hp = O.HeightParams()
+    hp.gen_mode, hp.gen_shape, hp.start_eval_sin, hp.glaciate = 4, 0, 10, 1
+    hp.mesh_scale = hp.mesh_scale_z_inv = hp.mesh_height_scale = 1.0
+    hp.dx_val_inv = hp.dy_val_inv = 16.0
+    hp.mesh_height, hp.zmax_est = 0.4, 2.3
+    hp.rx, hp.ry = O.gen_rx_ry(1, 0, 4)
+    hp.hmap = O.hmap_params(**HM_CFG)
+    return "port", (lambda rows=ny: O.heightgen_2d(O.Grid2D(-N_TILE / 2, -N_TILE / 2, 0.0625, 0.0625, nx, rows), hp, None, 1, 0, cores))
+
+
+def reference_arm(args):
+    """bench.py --impl reference: the reference's CPU implementation of the path on all host cores, bounded sample per step."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    cores = os.cpu_count() or 1
+    nx, ny = 1024, 128                      # bounded sample: 131072 cells of the same grid (rows 0..127, cols 0..1023 of the 8192^2 tile)
+    kind, run = cpu_runner(cores, nx, ny)
+    for _ in range(args.warmup):
+        run()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        run()
+    dt = time.perf_counter() - t0
+    value = nx * ny * args.steps / dt
+    sample = "%dx%d-cell window of the 8192^2 grid per step, %d host threads" % (nx, ny, cores)
+    print(json.dumps({
+        "impl": "reference", "metric": "height cells/s @8192^2 8-octave domain-warp", "value": value, "unit": "cells/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": {"workload": WORKLOAD, "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "cells/s", "cores": cores, "kind": kind, "sample": sample},
+        "e2e": {"value": value, "unit": "cells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+def cpu_baseline_leg():
+    """Bounded CPU sample of the same workload (rank 0, N=1): ~10-20 s of CPU work on all host cores."""
+    cores = os.cpu_count() or 1
+    nx, ny = 1024, 256
+    kind, run = cpu_runner(cores, nx, ny)
+    run(16)
+    t0 = time.perf_counter()
+    run()
+    dt = time.perf_counter() - t0
+    what = "unmodified reference objects (oracle/_ref)" if kind == "reference" else "plain-C oracle port"
+    return {"value": nx * ny / dt, "unit": "cells/s", "cores": cores, "kind": kind,
+            "sample": "%s, %dx%d-cell window of the 8192^2 grid, OpenMP %d threads" % (what, nx, ny, cores)}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-extra", action="store_true", help="skip the secondary measurements (sine / erosion / voxel)")
+    ap.add_argument("--kernel-only", action="store_true", help="only the device-resident timed loop (for ncu runs): no e2e, cpu_baseline, extra")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        reference_arm(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+    rank, world, local = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    tw = importlib.import_module("3dworld_b200")
+    scene = importlib.import_module("3dworld_b200.scene")
+    ctx = tw.Context(local)
+    stream = torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda", local))   # time on the stream the kernels are launched on
+
+    cfg = scene.SceneConfig(mesh_gen_mode=4, mesh_freq_filter=1, mesh_seed=1, hmap=HM_CFG, zmax_est=2.3)
+    hp = cfg.height_params()
+    g = cfg.heightmap_grid(N_TILE, N_TILE)
+    g.y0 = g.y0 + rank * N_TILE             # rank r owns tile row r of one larger terrain
+    cells = N_TILE * N_TILE
+    d_out = torch.empty((N_TILE, N_TILE), dtype=torch.float32, device="cuda")
+    mm = tw.MinMax()
+    zr = torch.zeros(2, dtype=torch.float32, device="cuda")
+
+    def step_device():
+        ctx.heightgen_2d_launch(g, hp, 1, 0, d_out, mm)
+        ctx.heightgen_2d_poll(wait=True)
+        if world > 1:                       # global z-range (get_heightmap_z_range over all tiles): the only collective of the path
+            zr[0], zr[1] = -mm.zmin, mm.zmax
+            dist.all_reduce(zr, op=dist.ReduceOp.MAX)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step_device()
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.mark()
+    launches0 = ctx.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        step_device()
+    e1.record(stream)
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = ctx.launch_count - launches0
+    clocks = sampler.summary()
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    value = world * cells * args.steps / (ms * 1e-3)
+
+    if args.kernel_only:
+        if rank == 0:
+            print(json.dumps({"metric": "height cells/s @8192^2 8-octave domain-warp", "value": value, "unit": "cells/s", "n_gpus": world, "steps": args.steps,
+                              "ms_per_step": ms / args.steps, "gpu_launches": launches, "clocks": clocks, "note": "kernel-only run (profiling aid)"}))
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- end to end: pinned HOST output buffer through the same C-ABI call (D2H of the grid inside the timed region) ----
+    h_out = torch.empty((N_TILE, N_TILE), dtype=torch.float32).pin_memory()
+
+    def step_e2e():
+        ctx.heightgen_2d_launch(g, hp, 1, 0, h_out, mm)
+        ctx.heightgen_2d_poll(wait=True)
+        return mm.zmin
+
+    for _ in range(2):
+        step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    e2e_steps = max(3, args.steps // 2)
+    for _ in range(e2e_steps):
+        step_e2e()
+    barrier()
+    dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    e2e_value = world * cells * e2e_steps / float(dt.item())
+    h2d = C.sizeof(tw.Grid2D) + C.sizeof(tw.HeightParams)
+    d2h = cells * 4 + 8
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    hbm_peak, peak_kind, sm_max_mhz = peaks()
+    kernel_ms = ms / args.steps            # one dominant kernel (noise_grid_kernel) per step
+    achieved_gbs = BYTES_PER_CELL * cells / (kernel_ms * 1e-3) / 1e9
+    traffic = None
+    prof = os.path.join(ROOT, "profiles", "roofline_r01.json")
+    if os.path.exists(prof):
+        traffic = json.load(open(prof)).get("noise_grid_kernel", {}).get("dram_bytes_per_launch")
+    sm_mhz = clocks.get("sm_mhz") or sm_max_mhz
+    alu_peak = 148 * 128 * sm_mhz * 1e6   # fp32 lane-instructions/s at the clock observed during the run
+    out = {
+        "metric": "height cells/s @8192^2 8-octave domain-warp", "value": value, "unit": "cells/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "cells_per_step_per_gpu": cells, "parallelism": "tile-row per rank, no data-path collective (%d rank%s)" % (world, "s" if world > 1 else ""),
+                   "l2": "output 268 MB per step > 126 MB L2; the kernel reads no input arrays", "bit_exact_vs_reference": True},
+        "gpu_launches": launches,
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": "cells/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
+                "path": "tw_heightgen_2d_launch/poll with a pinned host output buffer"},
+        "roofline": {"bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": achieved_gbs / hbm_peak, "traffic": traffic,
+                     "peak_kind": peak_kind, "kernel": "noise_grid_kernel<simplex,warp>", "algorithmic_bytes_per_cell": BYTES_PER_CELL,
+                     "note": "the kernel is FP32-ALU bound by construction (4 B/cell, ~6.8 kFLOP/cell; SURVEY.md 8d): see 'alu'",
+                     "alu": {"achieved_fp32_ops_per_s": FLOP_PER_CELL * cells / (kernel_ms * 1e-3), "peak_fp32_lane_instr_per_s": alu_peak,
+                             "frac": FLOP_PER_CELL * cells / (kernel_ms * 1e-3) / alu_peak, "flop_per_cell": FLOP_PER_CELL}},
+    }
+    if world == 1:
+        out["cpu_baseline"] = cpu_baseline_leg()
+        if not args.no_extra:
+            out["extra"] = extra_measurements(tw, scene, ctx, stream, torch)
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def extra_measurements(tw, scene, ctx, stream, torch):
+    """Secondary numbers for the other rows of the path (not the headline): sine-table grid, voxel fill, tiled erosion."""
+    res = {}
+
+    def timed(fn, reps):
+        fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(reps):
+            fn()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    d_out = torch.empty((N_TILE, N_TILE), dtype=torch.float32, device="cuda")
+    for name, mode in (("simplex_8oct", 1), ("perlin_8oct", 2), ("sine_8band", 0)):
+        cfg = scene.SceneConfig(mesh_gen_mode=mode, mesh_freq_filter=1, mesh_seed=1, hmap=HM_CFG, zmax_est=2.3)
+        hp, g = cfg.height_params(), cfg.heightmap_grid(N_TILE, N_TILE)
+        if mode == 0:
+            ctx.set_sine_params(cfg.sine_params())
+        ms = timed(lambda: ctx.heightgen_2d(g, hp, out=d_out), 3)
+        res["heightgen_%s_cells_per_s" % name] = N_TILE * N_TILE / (ms * 1e-3)
+    # voxels: 512^3 sine density (BASELINE config 4)
+    vcfg = scene.SceneConfig(scene_size=(16.0, 16.0, 4.0), mesh_size=(128, 128, 64))
+    vp = scene.voxel_landscape_params(vcfg, 512, 512, 512)
+    d_vox = torch.empty((512, 512, 512), dtype=torch.float32, device="cuda")
+    ms = timed(lambda: ctx.voxel_fill(vp, out=d_vox), 3)
+    res["voxel_sine_512_voxels_per_s"] = 512 ** 3 / (ms * 1e-3)
+    res["voxel_sine_512_store_GBps"] = 4 * 512 ** 3 / (ms * 1e-3) / 1e9
+    # tiled erosion (BASELINE config 5 shape): 2048 tiles of 258^2, 1000 droplets each, reference per-tile semantics
+    cfg = scene.SceneConfig(mesh_gen_mode=1, mesh_freq_filter=1, mesh_seed=1, hmap=HM_CFG, zmax_est=2.3, mesh_size=(256, 256, 1))
+    hp = cfg.height_params()
+    nt, zv = 2048, 258
+    origins = [((t % 64) * 256, (t // 64) * 256) for t in range(nt)]
+    tiles = torch.empty((nt, zv, zv), dtype=torch.float32, device="cuda")
+    ctx.heightgen_tiles(origins, cfg.mesh_size, float(cfg.dx_val), float(cfg.dy_val), zv, hp, out=tiles)
+    zmin, zmax = ctx.minmax(tiles)
+    ep = cfg.erosion_params()
+    t0 = time.perf_counter()
+    ctx.erode_tiles(tiles, 1000, ep, min_zval_all=zmin)
+    dt = time.perf_counter() - t0
+    res["erosion_tiles_258_droplets_per_s"] = nt * 1000 / dt
+    res["erosion_tiles_steps_per_s"] = ctx.last_erosion_steps / dt
+    res["erosion_tiles_config"] = "%d tiles x 258^2 x 1000 droplets, %.1f steps/droplet" % (nt, ctx.last_erosion_steps / (nt * 1000.0))
+    return res
+
+
+if __name__ == "__main__":
+    main()
