@@ -1,0 +1,252 @@
+// tw3d_adapter.h - C++ host adapter: the reference's own call surface for the terrain path, implemented on the C ABI (include/tw3d.h).
+//
+//   tw3d::mesh_xy_grid_cache_t   <->  mesh_xy_grid_cache_t                    src/mesh.h:22-45, src/mesh_gen.cpp:588-650,754-792
+//   tw3d::apply_erosion          <->  apply_erosion(float*,int,int,float,unsigned)   src/function_registry.h:354, src/erosion.cpp:14
+//   tw3d::noise_gen_3d           <->  noise_gen_3d::{set_rand_seeds,gen_sines}        src/upsurface.h:39-50
+//   tw3d::create_procedural      <->  voxel_manager::create_procedural               src/voxels.h:196, src/voxels.cpp:278-346
+//   tw3d::create_zvals_batch     <->  the height fill + erosion of tile_t::create_zvals for many tiles   src/tiled_mesh.cpp:467-515
+//
+// The reference reads ~20 globals on this path; here they are one explicit struct (scene_globals) set once per scene
+// with set_globals(). Same names, argument meaning and error behaviour as the reference: argument errors assert/abort like the
+// reference's assert()s (define TW3D_NO_ABORT to get a tw3d::error exception instead). Header-only; link with -l3dworld_b200.
+// No CPU fallback: all grid evaluation happens on the GPU through the C ABI; without a device ctx() fails.
+#pragma once
+#include <tw3d.h>
+#include <cassert>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+namespace tw3d {
+
+struct error : std::runtime_error {
+	int status;
+	error(int s, std::string const &m) : std::runtime_error(m), status(s) {}
+};
+
+// every reference global the path reads, under the reference's own names
+struct scene_globals {
+	int   mesh_gen_mode = TW_MGEN_SINE, mesh_gen_shape = 0, start_eval_sin = 0, GLACIATE = 1, mesh_seed = 0, mesh_rgen_index = 0;
+	float mesh_scale = 1.0f, mesh_scale_z_inv = 1.0f, DX_VAL_INV = 16.0f, DY_VAL_INV = 16.0f, MESH_HEIGHT = 0.4f, mesh_height_scale = 1.0f;
+	float zmax_est = 1.0f, custom_glaciate_exp = 0.0f;
+	tw_hmap_params hmap_params = {1000.0f, 0, 0, 0, 1000.0f, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+	int   MESH_X_SIZE = 128, MESH_Y_SIZE = 128;
+	// erosion (src/erosion.cpp:11,98; src/Textures.cpp:1284-1287)
+	float erode_amount = 1.0f, water_plane_z = 0.0f, HALF_DXY = 0.0625f, zmin = -1.0f, zmax = 1.0f, relh_adj_tex = 0.0f, clip_hd1 = 0.5f;
+};
+
+namespace detail {
+	inline void fail(int status, const char *what, tw_ctx *c) {
+		std::string msg = std::string(what) + ": " + (c ? tw_last_error(c) : "no context");
+#ifdef TW3D_NO_ABORT
+		throw error(status, msg);
+#else
+		if (status == TW_ERR_ARG) {fprintf(stderr, "tw3d: assertion failed: %s\n", msg.c_str()); abort();} // the reference asserts
+		throw error(status, msg);
+#endif
+	}
+	struct state_t {
+		scene_globals g;
+		std::vector<float> sin_table, sine_params;
+		unsigned generation = 0; // bumped by set_globals so that thread-local contexts re-upload the tables
+	};
+	inline state_t &state() {static state_t s; return s;}
+	struct tls_ctx {
+		tw_ctx *c = nullptr; unsigned generation = ~0u;
+		~tls_ctx() {if (c) tw_destroy(c);}
+	};
+}
+
+// thread-local context (a tw_ctx is not re-entrant); device from $TW3D_DEVICE (default 0)
+inline tw_ctx *ctx() {
+	static thread_local detail::tls_ctx t;
+	detail::state_t &s = detail::state();
+	if (!t.c) {
+		const char *dev = getenv("TW3D_DEVICE");
+		int const rc = tw_create(dev ? atoi(dev) : 0, &t.c);
+		if (rc != TW_OK) {t.c = nullptr; throw error(rc, "tw_create failed: no CUDA device (lib3dworld_b200 has no CPU fallback)");}
+	}
+	if (t.generation != s.generation) {
+		int rc = tw_set_sin_table(t.c, s.sin_table.empty() ? nullptr : s.sin_table.data());
+		if (rc == TW_OK && !s.sine_params.empty()) {rc = tw_set_sine_params(t.c, s.sine_params.data());}
+		if (rc != TW_OK) {detail::fail(rc, "table upload", t.c);}
+		t.generation = s.generation;
+	}
+	return t.c;
+}
+
+// sin_table: the reference's sin_table.data() (2*TSIZE floats) or nullptr to build it; sinTable: &sinTable[0][0] (90*5 floats) or nullptr
+inline void set_globals(scene_globals const &g, const float *sin_table = nullptr, const float *sinTable = nullptr) {
+	detail::state_t &s = detail::state();
+	s.g = g;
+	if (sin_table) {s.sin_table.assign(sin_table, sin_table + TW_SIN_TABLE_SIZE);}
+	if (sinTable)  {s.sine_params.assign(sinTable, sinTable + TW_F_TABLE_SIZE*5);}
+	++s.generation;
+}
+inline scene_globals const &globals() {return detail::state().g;}
+
+inline tw_height_params height_params_from_globals(int gen_mode, int gen_shape) {
+	scene_globals const &g = globals();
+	tw_height_params p;
+	memset(&p, 0, sizeof(p));
+	p.gen_mode = gen_mode; p.gen_shape = gen_shape; p.start_eval_sin = g.start_eval_sin; p.glaciate = g.GLACIATE;
+	p.mesh_scale = g.mesh_scale; p.mesh_scale_z_inv = g.mesh_scale_z_inv; p.dx_val_inv = g.DX_VAL_INV; p.dy_val_inv = g.DY_VAL_INV;
+	p.mesh_height = g.MESH_HEIGHT; p.mesh_height_scale = g.mesh_height_scale; p.zmax_est = g.zmax_est; p.custom_glaciate_exp = g.custom_glaciate_exp;
+	tw_gen_rx_ry(g.mesh_seed, g.mesh_rgen_index, gen_mode, &p.rx, &p.ry); // gen_rx_ry(), src/mesh_gen.cpp:581-586
+	p.hmap = g.hmap_params;
+	return p;
+}
+inline tw_erosion_params erosion_params_from_globals() {
+	scene_globals const &g = globals();
+	tw_erosion_params e = {g.erode_amount, g.water_plane_z, g.HALF_DXY, g.zmin, g.zmax, g.relh_adj_tex, g.clip_hd1};
+	return e;
+}
+
+// ------------------------------------------------------------------------------------------------ mesh_xy_grid_cache_t
+// Same interface and call order as the reference (build_arrays, then optionally enable_glaciate, then eval_index per cell). The grid is
+// evaluated on the GPU as a whole the first time a value is needed (or asynchronously when no_wait is set, mirroring the GLSL path:
+// build_arrays returns 0 while the job is in flight, src/mesh_gen.cpp:597-603) and eval_index reads the host copy.
+class mesh_xy_grid_cache_t {
+	mutable std::vector<float> vals;
+	mutable std::mutex mtx;
+	mutable bool have_vals = false, job_running = false;
+	mutable int vals_min_start = 0; mutable bool vals_glaciate = false;
+	tw_grid2d grid = {0, 0, 1, 1, 0, 0};
+	int gen_mode = TW_MGEN_SINE, gen_shape = 0;
+	bool do_glaciate = false, async_requested = false;
+
+	void launch(bool glaciate, int min_start_sin, bool wait) const {
+		tw_height_params const p = height_params_from_globals(gen_mode, gen_shape);
+		vals.resize((size_t)grid.nx*grid.ny);
+		tw_ctx *c = ctx();
+		int rc = tw_heightgen_2d_launch(c, &grid, &p, glaciate, min_start_sin, vals.data(), nullptr);
+		if (rc != TW_OK) {detail::fail(rc, "build_arrays", c);}
+		job_running = true; vals_glaciate = glaciate; vals_min_start = min_start_sin;
+		if (wait) {collect(true);}
+	}
+	bool collect(bool wait) const {
+		tw_ctx *c = ctx();
+		int const rc = tw_heightgen_2d_poll(c, wait ? 1 : 0);
+		if (rc == TW_ERR_NOT_READY) return false;
+		if (rc != TW_OK) {detail::fail(rc, "eval_index", c);}
+		job_running = false; have_vals = true;
+		return true;
+	}
+public:
+	bool build_arrays(float x0, float y0, float dx, float dy, unsigned nx, unsigned ny, bool cache_values=0, bool force_sine_mode=0, bool no_wait=0) {
+		assert(nx > 0 && ny > 0); // src/mesh_gen.cpp:589
+		std::lock_guard<std::mutex> lock(mtx);
+		scene_globals const &g = globals();
+		tw_grid2d const ng = {x0, y0, dx, dy, nx, ny};
+		int const mode = (force_sine_mode ? (int)TW_MGEN_SINE : g.mesh_gen_mode), shape = (force_sine_mode ? 0 : g.mesh_gen_shape);
+		bool const same = (memcmp(&ng, &grid, sizeof(grid)) == 0 && mode == gen_mode && shape == gen_shape);
+		if (job_running && !same) {collect(true);} // a different grid was in flight: drain it
+		if (!same) {have_vals = false;}
+		grid = ng; gen_mode = mode; gen_shape = shape;
+		do_glaciate = 0; // must call enable_glaciate() after this call if needed (src/mesh_gen.cpp:594)
+		async_requested = false;
+		if (gen_mode >= TW_MGEN_SIMPLEX_GPU && no_wait) { // GPU modes: launch now or report progress (src/mesh_gen.cpp:597-603)
+			if (job_running) {return collect(false);}
+			if (have_vals && vals_glaciate && vals_min_start == 0) return 1;
+			async_requested = true; // launched by enable_glaciate(), which setup_height_gen_async always calls next (src/tiled_mesh.cpp:462)
+			return 0;
+		}
+		if (cache_values) {have_vals = false; launch(false, 0, true); /* cached_vals hold un-glaciated values (src/mesh_gen.cpp:633) */}
+		return 1;
+	}
+	void enable_glaciate() {
+		std::lock_guard<std::mutex> lock(mtx);
+		do_glaciate = 1;
+		if (async_requested && !job_running) {have_vals = false; launch(true, 0, false); async_requested = false;}
+	}
+	float eval_index(unsigned x, unsigned y, int min_start_sin=0, bool use_cache=1) const {
+		assert(x < grid.nx && y < grid.ny); // src/mesh_gen.cpp:756
+		(void)use_cache;
+		int const mss = (gen_mode == TW_MGEN_SINE) ? min_start_sin : 0;
+		if (!(have_vals && !job_running && vals_glaciate == do_glaciate && vals_min_start == mss)) {
+			std::lock_guard<std::mutex> lock(mtx);
+			if (job_running) {collect(true);}
+			if (!(have_vals && vals_glaciate == do_glaciate && vals_min_start == mss)) {have_vals = false; launch(do_glaciate, mss, true);}
+		}
+		return vals[(size_t)y*grid.nx + x];
+	}
+	// whole-grid accessors (what the OpenMP eval_index loops of the reference's callers produce)
+	void get_grid(float *out, int min_start_sin=0) const {
+		(void)eval_index(0, 0, min_start_sin);
+		memcpy(out, vals.data(), vals.size()*sizeof(float));
+	}
+	void clear_context() {std::lock_guard<std::mutex> lock(mtx); if (job_running) {collect(true);} have_vals = false; vals.clear();}
+	void free_cshader() {}
+	~mesh_xy_grid_cache_t() {if (job_running) {try {collect(true);} catch (...) {}}}
+};
+
+// apply_erosion(float *heightmap, int xsize, int ysize, float min_zval, unsigned num_iters), src/function_registry.h:354
+inline void apply_erosion(float *heightmap, int xsize, int ysize, float min_zval, unsigned num_iters) {
+	tw_erosion_params const e = erosion_params_from_globals();
+	if (num_iters == 0 || e.erode_amount <= 0.0) return; // erosion disabled (src/erosion.cpp:16)
+	tw_ctx *c = ctx();
+	int const rc = tw_erode(c, heightmap, xsize, ysize, min_zval, num_iters, &e);
+	if (rc != TW_OK) {detail::fail(rc, "apply_erosion", c);}
+}
+
+// Height fill + per-tile erosion of tile_t::create_zvals for a batch of tiles (origins = tile x1,y1 pairs; zvals_out = ntiles*zvsize^2 floats)
+inline void create_zvals_batch(const int32_t *origins_xy, unsigned ntiles, unsigned zvsize, float dx, float dy, unsigned erosion_iters_tt, float *zvals_out, tw_minmax *mm = nullptr) {
+	scene_globals const &g = globals();
+	tw_height_params const p = height_params_from_globals(g.mesh_gen_mode, g.mesh_gen_shape);
+	tw_ctx *c = ctx();
+	int rc = tw_heightgen_tiles(c, origins_xy, ntiles, g.MESH_X_SIZE, g.MESH_Y_SIZE, dx, dy, zvsize, &p, zvals_out, (erosion_iters_tt == 0) ? mm : nullptr);
+	if (rc != TW_OK) {detail::fail(rc, "create_zvals_batch(height)", c);}
+	if (erosion_iters_tt > 0) {
+		tw_erosion_params const e = erosion_params_from_globals();
+		rc = tw_erode_tiles(c, zvals_out, ntiles, (int)zvsize, (int)zvsize, nullptr, g.zmin, erosion_iters_tt, &e); // apply_erosion(zvals, zvsize, zvsize, zmin, iters), src/tiled_mesh.cpp:515
+		if (rc != TW_OK) {detail::fail(rc, "create_zvals_batch(erosion)", c);}
+		if (mm) {for (unsigned t = 0; t < ntiles; ++t) {rc = tw_minmax_f32(c, zvals_out + (size_t)t*zvsize*zvsize, (size_t)zvsize*zvsize, mm + t); if (rc != TW_OK) {detail::fail(rc, "minmax", c);}}}
+	}
+}
+
+// noise_gen_3d: the table-generation half of the reference class (src/upsurface.h:39-50); grid evaluation goes through create_procedural
+class noise_gen_3d {
+	int rs1 = 1, rs2 = 1;
+public:
+	unsigned num_sines = 0;
+	float rdata[TW_N3D_RDATA] = {0};
+	void set_rand_seeds(int rs1_, int rs2_) {rs1 = rs1_; rs2 = rs2_;}
+	void gen_sines(float mag, float freq) {
+		assert(mag > 0.0 && freq > 0.0); // src/upsurface.cpp:19
+		tw_noise3d_gen_sines(rs1, rs2, mag, freq, rdata);
+		num_sines = TW_N3D_SINES;
+	}
+};
+
+// the part of voxel_grid<float> that create_procedural touches (src/voxels.h:100-160)
+struct voxel_grid_view {
+	unsigned nx, ny, nz;
+	float vsz[3], lo_pos[3];
+	std::vector<float> *data; // resized to nx*ny*nz, index z + (x + y*nx)*nz
+};
+
+// voxel_manager::create_procedural(mag, freq, offset, normalize_to_1, rseed1, rseed2, gen_mode, verbose) (src/voxels.cpp:278);
+// zscale = (params.invert ? -1.0 : 1.0)*params.z_gradient/(nz-1), mesh_freq_filter from the scene
+inline void create_procedural(voxel_grid_view const &v, float mag, float freq, const float offset[3], bool normalize_to_1, int rseed1, int rseed2,
+	int gen_mode, float zscale, int mesh_freq_filter)
+{
+	scene_globals const &g = globals();
+	tw_voxel_params vp;
+	memset(&vp, 0, sizeof(vp));
+	vp.nx = v.nx; vp.ny = v.ny; vp.nz = v.nz;
+	for (int d = 0; d < 3; ++d) {vp.lo_pos[d] = v.lo_pos[d]; vp.vsz[d] = v.vsz[d]; vp.offset[d] = offset[d];}
+	vp.mag = mag; vp.freq = freq; vp.gen_mode = gen_mode; vp.normalize_to_1 = normalize_to_1; vp.rseed1 = rseed1; vp.rseed2 = rseed2;
+	vp.octaves = (5 - mesh_freq_filter > 1) ? (5 - mesh_freq_filter) : 1; // max(1, MAX_FREQ_BINS - mesh_freq_filter), src/voxels.cpp:333
+	if (gen_mode != TW_MGEN_SINE) {tw_gen_rx_ry(g.mesh_seed, g.mesh_rgen_index, gen_mode, &vp.rx, &vp.ry);}
+	vp.zscale = zscale;
+	v.data->resize((size_t)v.nx*v.ny*v.nz);
+	tw_ctx *c = ctx();
+	int const rc = tw_voxel_fill(c, &vp, nullptr, v.data->data());
+	if (rc != TW_OK) {detail::fail(rc, "create_procedural", c);}
+}
+
+} // namespace tw3d

@@ -1,0 +1,75 @@
+"""The C++ host adapter (3dworld_b200/host/tw3d_adapter.h: reference class/function signatures on top of the C ABI).
+CPU: it compiles, links against lib3dworld_b200.so and fails loudly without a device. GPU: driven like the reference's callers
+(heightmap_t::proc_gen, tile_t::create_zvals incl. the no_wait protocol, create_procedural) and compared bit-for-bit with the oracle."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from cases import convert, HM_CFG
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EXE = os.path.join(ROOT, "tests", "cpp", "test_adapter")
+
+
+@pytest.fixture(scope="module")
+def exe(tw):
+    src = os.path.join(ROOT, "tests", "cpp", "test_adapter.cpp")
+    hdr = os.path.join(ROOT, "3dworld_b200", "host", "tw3d_adapter.h")
+    if not os.path.exists(EXE) or os.path.getmtime(EXE) < max(os.path.getmtime(src), os.path.getmtime(hdr), os.path.getmtime(tw.LIB_PATH)):
+        subprocess.check_call(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-I", os.path.join(ROOT, "include"), "-I", os.path.join(ROOT, "3dworld_b200", "host"),
+                               src, "-L" + os.path.join(ROOT, "3dworld_b200"), "-l3dworld_b200", "-Wl,-rpath," + os.path.join(ROOT, "3dworld_b200"), "-o", EXE])
+    return EXE
+
+
+def test_adapter_builds_and_refuses_without_device(exe):
+    import torch
+    out = subprocess.run([exe, "probe"], capture_output=True, text=True)
+    assert out.returncode == 0 and "abi 1" in out.stdout
+    assert ("device ok" in out.stdout) == torch.cuda.is_available()
+    if not torch.cuda.is_available():
+        assert "no device: status -1" in out.stdout          # TW_ERR_NO_DEVICE: no CPU fallback
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", [0, 1, 2, 4])
+def test_adapter_matches_oracle(exe, tw, scene, oracle, ctx, beq, tmp_path, mode):
+    path = str(tmp_path / "out.bin")
+    r = subprocess.run([exe, str(mode), path], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    data = np.fromfile(path, np.float32)
+    W, H, zv = 160, 96, 66
+    sizes = [W * H, W * H, zv * zv, 3 * zv * zv, 24 * 10 * 30]
+    assert data.size == sum(sizes)
+    parts = np.split(data, np.cumsum(sizes)[:-1])
+    cfg = scene.SceneConfig(mesh_gen_mode=mode, mesh_freq_filter=1, mesh_seed=1, hmap=HM_CFG, zmax_est=2.3)
+    hp = convert(cfg.height_params(), oracle.HeightParams)
+    sp = cfg.sine_params()
+    f32 = np.float32
+    # heightmap_t::proc_gen
+    z = oracle.heightgen_2d(oracle.Grid2D(-0.5 * W, -0.5 * H, 0.0625, 0.0625, W, H), hp, sp, 1, 0)
+    assert beq(parts[0], z) == 0
+    mn, mx = f32(z.min()), f32(z.max())
+    ep = oracle.ErosionParams(1.0, float(mn - f32(10.0)), 0.0625, float(mn - f32(0.1)), float(mx + f32(0.1)), 0.0, 0.5)
+    ze, _ = oracle.apply_erosion(z, float(mn), 700, ep)
+    assert beq(parts[1], ze) == 0
+    # tile_t::create_zvals (async protocol)
+    zt = oracle.heightgen_2d(oracle.Grid2D(float(5 * 64 - 64), float(-3 * 64 - 64), 0.0625, 0.0625, zv, zv), hp, sp, 1, 0)
+    assert beq(parts[2], zt) == 0
+    # batched tiles + per-tile erosion with min_zval = zmin global
+    exp = []
+    for x1, y1 in ((0, 0), (64, 0), (0, 64)):
+        t = oracle.heightgen_2d(oracle.Grid2D(float(x1 - 64), float(y1 - 64), 0.0625, 0.0625, zv, zv), hp, sp, 1, 0)
+        exp.append(oracle.apply_erosion(t, float(mn - f32(0.1)), 300, ep)[0])
+    assert beq(parts[3], np.stack(exp)) == 0
+    # create_procedural
+    vp = oracle.VoxelParams()
+    vp.nx, vp.ny, vp.nz = 24, 10, 30
+    for d, (lo, vs, off) in enumerate(zip((-7.9, -7.8, -1.5), (0.4, 0.65, 0.11), (0.5, -0.25, 0.0))):
+        vp.lo_pos[d], vp.vsz[d], vp.offset[d] = lo, vs, off
+    vmode = 1 if mode >= 3 else mode
+    vp.mag = vp.freq = 1.0
+    vp.gen_mode, vp.normalize_to_1, vp.rseed1, vp.rseed2, vp.octaves = vmode, 1, 123, 456, 3
+    vp.rx, vp.ry = oracle.gen_rx_ry(1, 0, vmode) if vmode != 0 else (0.0, 0.0)
+    assert beq(parts[4], oracle.voxel_fill(vp)) == 0
