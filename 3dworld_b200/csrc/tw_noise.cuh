@@ -15,13 +15,30 @@ namespace twn {
 
 __device__ __forceinline__ float mod289(float x)  {float const t = floorf(x*(1.0f/289.0f)); return __fmaf_rn(-t, 289.0f, x);}
 __device__ __forceinline__ float permute(float x) {return mod289(__fmaf_rn(x, 34.0f, 1.0f)*x);}
-// glm::mod(a, 289) = a - 289*floor(a/289) with a true division (func_common.inl:216); a is integer-valued, 289*floor() exact for |a| < 2^24
+// glm::mod(a, 289) = a - 289*floor(a/289) with a true division (func_common.inl:216), a integer-valued (a floor() result).
+// mod_div289: the literal form. mod_int289: division-free form that is bit-identical for every integer |a| < 2^22 (verified exhaustively
+// over all 8.4 M integers, tests/test_host_logic.py::test_division_free_forms): q = floor(a*RN(1/289)) is either floor(a/289) or, only
+// when a is a multiple of 289, one less (RN(1/289) > 1/289 and the product error stays below 1/289), so r = a - 289q (exact) needs one
+// conditional subtract. Callers guard the range and fall back to mod_div289 for astronomically large lattice indices.
 __device__ __forceinline__ float mod_div289(float a) {float const t = floorf(__fdiv_rn(a, 289.0f)); return a - 289.0f*t;}
+__device__ __forceinline__ float mod_int289(float a) {
+	float const q = floorf(a*(1.0f/289.0f));
+	float const r = __fmaf_rn(q, -289.0f, a); // exact: |q*289| < 2^23
+	return (r >= 289.0f) ? r - 289.0f : r;
+}
+constexpr float MOD_FAST_LIMIT = 4194304.0f; // 2^22
+// i/41 for integer i in [0,289): quotient by one Newton correction of i*RN(1/41); equals the IEEE quotient for all 289 inputs (same test)
+__device__ __forceinline__ float div41_small(float i) {
+	float const c = 1.0f/41.0f, q0 = i*c;
+	return __fmaf_rn(__fmaf_rn(-q0, 41.0f, i), c, q0);
+}
 __device__ __forceinline__ float tinvsqrt(float r) {return 1.79284291400159f - 0.85373472095314f*r;}
 __device__ __forceinline__ float fade(float t)    {return (t*t*t)*(t*(t*6.0f - 15.0f) + 10.0f);}
 __device__ __forceinline__ float fract(float x)   {return x - floorf(x);}
 __device__ __forceinline__ float mix(float x, float y, float a) {return x + a*(y - x);}
 __device__ __forceinline__ float gmax(float x, float y) {return (x < y) ? y : x;}   // glm::max
+// glm::max(x, 0) for the simplex falloff terms: fmaxf differs from (x < 0) ? 0 : x only when x is NaN, and then the final product is NaN either way
+__device__ __forceinline__ float gmax0(float x) {return fmaxf(x, 0.0f);}
 __device__ __forceinline__ float gmin(float x, float y) {return (y < x) ? y : x;}   // glm::min
 __device__ __forceinline__ float step(float edge, float x) {return (x < edge) ? 0.0f : 1.0f;}
 __device__ __forceinline__ float two_f_minus_1(float f) {return __fmaf_rn(2.0f, f, -1.0f);}
@@ -35,12 +52,13 @@ __device__ __forceinline__ float simplex2(float vx, float vy) {
 	bool  const xgt = (x0x > x0y);
 	float const i1x = xgt ? 1.0f : 0.0f, i1y = xgt ? 0.0f : 1.0f;
 	float const x12x = (x0x + Cx) - i1x, x12y = (x0y + Cx) - i1y, x12z = x0x + Cz, x12w = x0y + Cz;
-	ix = mod_div289(ix); iy = mod_div289(iy);   // results are in [0,289) and never -0, so the reference's "+ 0.0f" terms are no-ops
+	// results are in [0,289) and never -0, so the reference's "+ 0.0f" terms are no-ops
+	if (fmaxf(fabsf(ix), fabsf(iy)) < MOD_FAST_LIMIT) {ix = mod_int289(ix); iy = mod_int289(iy);} else {ix = mod_div289(ix); iy = mod_div289(iy);}
 	float const q0 = permute(iy), q1 = permute(iy + i1y), q2 = permute(iy + 1.0f);
 	float const p0 = permute(q0 + ix), p1 = permute(q1 + ix + i1x), p2 = permute(q2 + ix + 1.0f);
-	float m0 = gmax(0.5f - (x0x*x0x + x0y*x0y), 0.0f);
-	float m1 = gmax(0.5f - (x12x*x12x + x12y*x12y), 0.0f);
-	float m2 = gmax(0.5f - (x12z*x12z + x12w*x12w), 0.0f);
+	float m0 = gmax0(0.5f - (x0x*x0x + x0y*x0y));
+	float m1 = gmax0(0.5f - (x12x*x12x + x12y*x12y));
+	float m2 = gmax0(0.5f - (x12z*x12z + x12w*x12w));
 	m0 = m0*m0; m1 = m1*m1; m2 = m2*m2;
 	m0 = m0*m0; m1 = m1*m1; m2 = m2*m2;
 	float const X0 = two_f_minus_1(fract(p0*Cw)), X1 = two_f_minus_1(fract(p1*Cw)), X2 = two_f_minus_1(fract(p2*Cw));
@@ -55,7 +73,7 @@ __device__ __forceinline__ float simplex2(float vx, float vy) {
 
 __device__ __forceinline__ void perlin2_corner(float ix, float iy, float &gx, float &gy) {
 	float const i = permute(permute(ix) + iy);
-	float const g = two_f_minus_1(fract(__fdiv_rn(i, 41.0f)));
+	float const g = two_f_minus_1(fract(div41_small(i)));
 	gy = fabsf(g) - 0.5f;
 	gx = g - floorf(g + 0.5f);
 }
@@ -64,7 +82,9 @@ __device__ __forceinline__ float perlin2(float Px, float Py) {
 	float const flx = floorf(Px), fly = floorf(Py);
 	float const frx = Px - flx, fry = Py - fly;           // fract()
 	float const Pfz = frx - 1.0f, Pfw = fry - 1.0f;
-	float const Pix = mod_div289(flx), Piy = mod_div289(fly), Piz = mod_div289(flx + 1.0f), Piw = mod_div289(fly + 1.0f);
+	float Pix, Piy, Piz, Piw;
+	if (fmaxf(fabsf(flx), fabsf(fly)) < MOD_FAST_LIMIT - 1.0f) {Pix = mod_int289(flx); Piy = mod_int289(fly); Piz = mod_int289(flx + 1.0f); Piw = mod_int289(fly + 1.0f);}
+	else {Pix = mod_div289(flx); Piy = mod_div289(fly); Piz = mod_div289(flx + 1.0f); Piw = mod_div289(fly + 1.0f);}
 	float g00x, g00y, g10x, g10y, g01x, g01y, g11x, g11y;
 	perlin2_corner(Pix, Piy, g00x, g00y);
 	perlin2_corner(Piz, Piy, g10x, g10y);
@@ -159,8 +179,8 @@ __device__ __forceinline__ float simplex3(float vx, float vy, float vz) {
 	float const n0 = tinvsqrt(P0x*P0x + P0y*P0y + P0z*P0z), n1 = tinvsqrt(P1x*P1x + P1y*P1y + P1z*P1z);
 	float const n2 = tinvsqrt(P2x*P2x + P2y*P2y + P2z*P2z), n3 = tinvsqrt(P3x*P3x + P3y*P3y + P3z*P3z);
 	P0x *= n0; P0y *= n0; P0z *= n0; P1x *= n1; P1y *= n1; P1z *= n1; P2x *= n2; P2y *= n2; P2z *= n2; P3x *= n3; P3y *= n3; P3z *= n3;
-	float m0 = gmax(0.6f - (x0x*x0x + x0y*x0y + x0z*x0z), 0.0f), m1 = gmax(0.6f - (x1x*x1x + x1y*x1y + x1z*x1z), 0.0f);
-	float m2 = gmax(0.6f - (x2x*x2x + x2y*x2y + x2z*x2z), 0.0f), m3 = gmax(0.6f - (x3x*x3x + x3y*x3y + x3z*x3z), 0.0f);
+	float m0 = gmax0(0.6f - (x0x*x0x + x0y*x0y + x0z*x0z)), m1 = gmax0(0.6f - (x1x*x1x + x1y*x1y + x1z*x1z));
+	float m2 = gmax0(0.6f - (x2x*x2x + x2y*x2y + x2z*x2z)), m3 = gmax0(0.6f - (x3x*x3x + x3y*x3y + x3z*x3z));
 	m0 = m0*m0; m1 = m1*m1; m2 = m2*m2; m3 = m3*m3;
 	float const d0 = P0x*x0x + P0y*x0y + P0z*x0z, d1 = P1x*x1x + P1y*x1y + P1z*x1z;
 	float const d2 = P2x*x2x + P2y*x2y + P2z*x2z, d3 = P3x*x3x + P3y*x3y + P3z*x3z;

@@ -17,7 +17,7 @@ def _vp(tw, scene, mode, ff, nx, ny, nz, norm=1, zs=0.0, atten=0):
 
 
 @pytest.mark.parametrize("mode", [0, 1, 2])
-@pytest.mark.parametrize("dims", [(40, 24, 36), (9, 5, 130), (70, 3, 1)])
+@pytest.mark.parametrize("dims", [(40, 24, 36), (9, 5, 130), (70, 3, 2)])
 def test_voxel_fill_bit_exact(tw, scene, oracle, ctx, beq, mode, dims):
     for ff in (2, 0):
         for norm, zs in ((1, 0.0), (0, 0.01)):

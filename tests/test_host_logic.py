@@ -82,3 +82,27 @@ def test_scene_config(tw, scene):
     assert ep.zmin == pytest.approx(-2.3) and 0.0 < ep.clip_hd1 < 1.0
     vp = scene.voxel_landscape_params(scene.SceneConfig(scene_size=(16.0, 16.0, 4.0), mesh_size=(128, 128, 64)), 512, 512, 512)
     assert vp.nx == 512 and vp.rseed2 == 456 and vp.vsz[0] > 0
+
+
+def test_division_free_forms():
+    """csrc/tw_noise.cuh replaces glm::mod(a,289)'s true division and perlin's i/41 by division-free sequences; they must equal the IEEE
+    results for EVERY input in their guarded range (numpy fp32 arithmetic is IEEE round-to-nearest; a - q*289 is exact so no fma is needed)."""
+    f32 = np.float32
+    a = np.arange(-(1 << 22) + 1, 1 << 22, dtype=np.int64).astype(np.float32)
+    q = np.floor(a * (f32(1.0) / f32(289.0)))
+    r = a - q * f32(289.0)
+    r = np.where(r >= f32(289.0), r - f32(289.0), r)
+    ref = a - f32(289.0) * np.floor(a / f32(289.0))
+    assert np.array_equal(r, ref) and not np.signbit(r).any()
+    from fractions import Fraction
+
+    def fma(x, y, z):   # correctly rounded fp32 fma via exact rationals
+        v = Fraction(float(x)) * Fraction(float(y)) + Fraction(float(z))
+        c = f32(float(v))
+        cands = [np.nextafter(c, f32(-np.inf)), c, np.nextafter(c, f32(np.inf))]
+        return min(cands, key=lambda t: (abs(Fraction(float(t)) - v), int(f32(t).view(np.uint32)) & 1))
+    c41 = f32(1.0) / f32(41.0)
+    for i in range(289):
+        fi = f32(i)
+        q0 = fi * c41
+        assert fma(fma(-q0, f32(41.0), fi), c41, q0) == fi / f32(41.0)
