@@ -13,6 +13,7 @@
 // the random-direction fallback (:84-87) reads cos/sin from a 1e6-entry table built with the HOST libm (rand_float() has only 1e6 values).
 #include "tw_internal.h"
 #include <float.h>
+#include <stdlib.h>
 
 namespace {
 
@@ -26,12 +27,45 @@ struct EParams {
 	float erode_amount, wpz_minus_half_dxy, zmin, zrange, relh_adj_tex, clip_hd1;
 };
 
-__global__ void pad_kernel(const float *__restrict__ in, float *__restrict__ out, int xsize, int ysize, int NX, int NY) {
+// Also counts, per heightmap, the cells above the ocean-stop level (src/erosion.cpp:98): droplets that start below it die in one move, the
+// others walk downhill, so this count predicts the heightmap's total droplet work (correlation 0.95 on the BASELINE terrain) and is used to
+// schedule the heaviest heightmaps first (the work per heightmap is heavy-tailed: median 3, mean 26, max > 140 moves per droplet).
+__global__ void pad_kernel(const float *__restrict__ in, float *__restrict__ out, int xsize, int ysize, int NX, int NY, float work_level, unsigned *__restrict__ work) {
 	int const x = blockIdx.x*blockDim.x + threadIdx.x, y = blockIdx.y;
 	size_t const tile = blockIdx.z;
-	if (x >= NX) return;
-	int const sx = clampi(x - PAD, xsize - 1), sy = clampi(y - PAD, ysize - 1);
-	out[tile*NX*NY + (size_t)y*NX + x] = __ldg(in + tile*xsize*ysize + (size_t)sy*xsize + sx);
+	bool above = false;
+	if (x < NX) {
+		int const sx = clampi(x - PAD, xsize - 1), sy = clampi(y - PAD, ysize - 1);
+		float const v = __ldg(in + tile*xsize*ysize + (size_t)sy*xsize + sx);
+		out[tile*NX*NY + (size_t)y*NX + x] = v;
+		above = !(v < work_level);
+	}
+	unsigned const n = __popc(__ballot_sync(0xffffffffu, above));
+	if (work && n && (threadIdx.x & 31) == 0) {atomicAdd(work + tile, n);}
+}
+
+// counting sort of the heightmap indices by descending work estimate (256 bins; order within a bin is irrelevant: heightmaps are independent)
+constexpr int WORK_BINS = 256;
+__global__ void order_hist_kernel(const unsigned *__restrict__ work, unsigned nt, unsigned max_work, unsigned *__restrict__ hist) {
+	unsigned const t = blockIdx.x*blockDim.x + threadIdx.x;
+	if (t >= nt) return;
+	unsigned const bin = (WORK_BINS - 1) - min((unsigned)(WORK_BINS - 1), (unsigned)(((unsigned long long)work[t]*(WORK_BINS - 1))/max_work));
+	atomicAdd(hist + bin, 1u);
+}
+__global__ void order_scan_kernel(unsigned *__restrict__ hist) { // exclusive prefix sum of 256 bins, one warp
+	unsigned const lane = threadIdx.x;
+	unsigned v[WORK_BINS/32], sum = 0;
+	for (int i = 0; i < WORK_BINS/32; ++i) {v[i] = hist[lane*(WORK_BINS/32) + i]; sum += v[i];}
+	unsigned incl = sum;
+	for (int o = 1; o < 32; o <<= 1) {unsigned const n = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= (unsigned)o) incl += n;}
+	unsigned run = incl - sum;
+	for (int i = 0; i < WORK_BINS/32; ++i) {hist[lane*(WORK_BINS/32) + i] = run; run += v[i];}
+}
+__global__ void order_scatter_kernel(const unsigned *__restrict__ work, unsigned nt, unsigned max_work, unsigned *__restrict__ cursor, unsigned *__restrict__ order) {
+	unsigned const t = blockIdx.x*blockDim.x + threadIdx.x;
+	if (t >= nt) return;
+	unsigned const bin = (WORK_BINS - 1) - min((unsigned)(WORK_BINS - 1), (unsigned)(((unsigned long long)work[t]*(WORK_BINS - 1))/max_work));
+	order[atomicAdd(cursor + bin, 1u)] = t;
 }
 
 __global__ void unpad_kernel(const float *__restrict__ padded, float *__restrict__ out, int xsize, int ysize, int NX, int NY,
@@ -56,44 +90,66 @@ struct Rng {
 	}
 };
 
+// One heightmap per group of G lanes (G = 1, 2, 4, 8, 16, 32; 32/G heightmaps per warp). The droplet's scalar state is replicated in the
+// G lanes of its group (group-uniform control flow, no shuffles); the 4 deposit corners and the 16 brush cells are dealt round-robin to
+// the lanes of the group (c = sub, sub+G, ...: ascending c is the reference's z-outer/x-inner order, so G == 1 is literally the serial
+// loop). The droplet loop is flattened into one state machine per group (init-droplet / step) so that groups whose droplets end at
+// different times stay converged at the top of the loop. G trades redundant ALU work (G = 32: every lane repeats the ~250-instruction
+// step for ONE map) against memory coalescing and in-flight parallelism (G = 1: no redundancy, but 32 unrelated maps per load
+// instruction and 32x more maps needed to fill the machine); twi_erode picks G from the number of heightmaps.
+template<int G>
 __global__ void __launch_bounds__(128)
 droplet_kernel(float *__restrict__ padded, unsigned ntiles, int xsize, int ysize, unsigned num_iters, EParams E,
-	const float2 *__restrict__ dir_table, unsigned long long *__restrict__ steps_out)
+	const float2 *__restrict__ dir_table, unsigned long long *__restrict__ steps_out, const unsigned *__restrict__ order)
 {
+	constexpr int TPW = 32/G; // heightmaps per warp
+	int const lane = threadIdx.x & 31, sub = lane % G, grp = lane / G;
 	unsigned const warp = (blockIdx.x*blockDim.x + threadIdx.x) >> 5;
-	int const lane = threadIdx.x & 31;
-	if (warp >= ntiles) return;
+	unsigned const slot = warp*TPW + grp;                                       // position in the heaviest-first schedule
+	unsigned const tile = (slot < ntiles) ? (order ? __ldg(order + slot) : slot) : ntiles;
+	unsigned const gmask = (G == 32) ? 0xffffffffu : (((1u << (G & 31)) - 1u) << (grp*G));
 	int const NX = xsize + 2*PAD, NY = ysize + 2*PAD;
-	float *mh = padded + (size_t)warp*NX*NY;
+	float *mh = padded + (size_t)((tile < ntiles) ? tile : 0)*NX*NY;
 	float const Kq=10, Kw=0.001f, Kr=0.9f, Kd=0.02f, Ki=0.1f, minSlope=0.05f, g=20, Kg=g*2;
 	unsigned const MAX_PATH_LEN = 4u*(unsigned)NX*(unsigned)NY;
 	float const erode_amount = E.erode_amount;
 	unsigned long long steps = 0;
-	// lane-constant brush / deposit offsets
-	int const bx = (lane & 3) - 1, bz = ((lane >> 2) & 3) - 1;  // brush cell offsets for lanes 0..15
-	int const cx = lane & 1, cz = (lane >> 1) & 1;               // deposit corner for lanes 0..3
+	bool active = (tile < ntiles), in_droplet = false;
+	unsigned iter = 0, numMoves = 0;
+	Rng rgen; rgen.s1 = rgen.s2 = 1;
+	int xi = 0, zi = 0;
+	float xp=0, zp=0, xf=0, zf=0, s=0, v=0, w=1, dx=0, dz=0, h=0, h00=0, h10=0, h01=0, h11=0;
 
 #define HMAP(x, y) mh[(size_t)NX*clampi((y), NY-1) + clampi((x), NX-1)]
-	// DEPOSIT(H): src/erosion.cpp:42-54; lanes 0-3 own one corner each (inside cells are distinct => no aliasing)
+	// DEPOSIT(H): src/erosion.cpp:42-54; corner c of the 2x2 cell goes to lane c % G (inside cells are distinct => no aliasing between lanes)
 #define DEPOSIT(H) { \
-	if (lane < 4) { \
-		int const X = xi + cx, Z = zi + cz; \
-		float const W = (cx ? xf : (1-xf))*(cz ? zf : (1-zf)); \
+	_Pragma("unroll") \
+	for (int c = sub; c < 4; c += G) { \
+		int const X = xi + (c & 1), Z = zi + (c >> 1); \
+		float const W = ((c & 1) ? xf : (1-xf))*((c >> 1) ? zf : (1-zf)); \
 		float const delta = ds*erode_amount*W; \
-		if (!(X < 0 || Z < 0 || X >= NX || Z >= NY)) {mh[(size_t)NX*Z + X] += delta;} \
+		if ((unsigned)X < (unsigned)NX && (unsigned)Z < (unsigned)NY) {mh[NX*Z + X] += delta;} \
 	} \
-	__syncwarp(); \
+	if (G > 1) {__syncwarp(gmask);} \
 	(H) += ds; }
 
-	for (unsigned iter = 0; iter < num_iters; ++iter) {
-		Rng rgen; rgen.s1 = (int)iter + 11; rgen.s2 = 79*(int)iter + 121;
-		int xi = PAD + (rgen.rand()%xsize);
-		int zi = PAD + (rgen.rand()%ysize);
-		float xp=xi, zp=zi, xf=0, zf=0, s=0, v=0, w=1, dx=0, dz=0;
-		float h=HMAP(xi, zi), h00=h, h10=HMAP(xi+1, zi), h01=HMAP(xi, zi+1), h11=HMAP(xi+1, zi+1);
-
-		for (unsigned numMoves = 0; numMoves < MAX_PATH_LEN; ++numMoves) {
-			++steps;
+	for (;;) {
+		if (active && !in_droplet) { // next droplet of this group's heightmap (src/erosion.cpp:67-73)
+			if (iter >= num_iters) {active = false;}
+			else {
+				rgen.s1 = (int)iter + 11; rgen.s2 = 79*(int)iter + 121;
+				xi = PAD + (rgen.rand()%xsize);
+				zi = PAD + (rgen.rand()%ysize);
+				xp=xi; zp=zi; xf=0; zf=0; s=0; v=0; w=1; dx=0; dz=0;
+				h=HMAP(xi, zi); h00=h; h10=HMAP(xi+1, zi); h01=HMAP(xi, zi+1); h11=HMAP(xi+1, zi+1);
+				numMoves = 0; in_droplet = true; ++iter;
+			}
+		}
+		if (!__any_sync(0xffffffffu, active)) break;
+		if (!active) continue;
+		if (numMoves >= MAX_PATH_LEN) {in_droplet = false; continue;} // "droplet path is too long" (src/erosion.cpp:153)
+		++numMoves; ++steps;
+		{ // ---- one move of the droplet (src/erosion.cpp:76-152) ----
 			float const gx=h00+h01-h10-h11, gz=h00+h10-h01-h11;
 			dx=(dx-gx)*Ki+gx;
 			dz=(dz-gz)*Ki+gz;
@@ -104,20 +160,28 @@ droplet_kernel(float *__restrict__ padded, unsigned ntiles, int xsize, int ysize
 			}
 			else {dx=__fdiv_rn(dx, dl); dz=__fdiv_rn(dz, dl);}
 			float const nxp=xp+dx, nzp=zp+dz;
-			int const nxi=tw_x86_f2i(floorf(nxp)), nzi=tw_x86_f2i(floorf(nzp)); // x86 semantics: NaN -> INT_MIN -> "outside" next step
+			int nxi=__float2int_rd(nxp), nzi=__float2int_rd(nzp); // (int)floor(.)
+			if (!(fabsf(nxp) < 2147483648.0f && fabsf(nzp) < 2147483648.0f)) { // NaN / out of int range: x86 cvttss2si yields INT_MIN -> "outside" next step
+				nxi=tw_x86_f2i(floorf(nxp)); nzi=tw_x86_f2i(floorf(nzp));
+			}
 			float const nxf=nxp-(float)nxi, nzf=nzp-(float)nzi;
-			float const nh00=HMAP(nxi, nzi), nh10=HMAP(nxi+1, nzi), nh01=HMAP(nxi, nzi+1), nh11=HMAP(nxi+1, nzi+1);
+			float nh00, nh10, nh01, nh11;
+			if ((unsigned)nxi < (unsigned)(NX-1) && (unsigned)nzi < (unsigned)(NY-1)) { // common case: no clamping needed
+				float const *q = mh + (nzi*NX + nxi);
+				nh00 = q[0]; nh10 = q[1]; q += NX; nh01 = q[0]; nh11 = q[1];
+			}
+			else {nh00=HMAP(nxi, nzi); nh10=HMAP(nxi+1, nzi); nh01=HMAP(nxi, nzi+1); nh11=HMAP(nxi+1, nzi+1);}
 			float const nh=(nh00*(1-nxf)+nh10*nxf)*(1-nzf)+(nh01*(1-nxf)+nh11*nxf)*nzf;
-			if (smax(smax(nh00, nh10), smax(nh01, nh11)) < E.wpz_minus_half_dxy) break; // reached ocean water
+			if (smax(smax(nh00, nh10), smax(nh01, nh11)) < E.wpz_minus_half_dxy) {in_droplet = false; continue;} // reached ocean water
 
-			bool const outside = (xi < 0 || zi < 0 || xi >= NX || zi >= NY);
+			bool const outside = ((unsigned)xi >= (unsigned)NX || (unsigned)zi >= (unsigned)NY);
 			if (nh>=h || outside) {
 				float ds=(nh-h)+0.001f;
 				if (ds>=s || outside) {
 					ds=s;
 					DEPOSIT(h)
 					s=0;
-					break;
+					in_droplet = false; continue;
 				}
 				DEPOSIT(h)
 				s-=ds;
@@ -138,20 +202,21 @@ droplet_kernel(float *__restrict__ padded, unsigned ntiles, int xsize, int ysize
 					float const relh = E.relh_adj_tex + __fdiv_rn(nh - E.zmin, E.zrange);
 					ds *= (relh > E.clip_hd1) ? 0.5f : 2.0f;
 				}
-				bool const interior = (xi >= 1 && zi >= 1 && xi + 2 <= NX - 1 && zi + 2 <= NY - 1);
-				if (interior) { // 16 distinct cells: one lane each
-					if (lane < 16) {
-						int const x = xi + bx, z = zi + bz;
+				bool const interior = ((unsigned)(xi - 1) < (unsigned)(NX - 3) && (unsigned)(zi - 1) < (unsigned)(NY - 3));
+				if (interior || G == 1) { // 16 distinct cells dealt to the lanes of the group (G == 1: the reference's serial loop, clamped)
+#pragma unroll
+					for (int c = sub; c < 16; c += G) {
+						int const x = xi + (c & 3) - 1, z = zi + (c >> 2) - 1;
 						float const zo=(float)z-zp, zo2=zo*zo, xo=(float)x-xp;
 						float wgt=1-(xo*xo+zo2)*0.25f;
 						if (!(wgt<=0)) {
 							wgt*=0.1591549430918953f;
 							float const delta=ds*erode_amount*wgt;
-							mh[(size_t)NX*z + x]-=delta;
+							if (interior) {mh[NX*z + x]-=delta;} else {HMAP(x, z)-=delta;}
 						}
 					}
 				}
-				else if (lane == 0) { // border: clamped indices may alias, keep the reference's serial order
+				else if (sub == 0) { // border: clamped indices may alias, keep the reference's serial order
 					for (int z=zi-1; z<=zi+2; ++z) {
 						float const zo=(float)z-zp, zo2=zo*zo;
 						for (int x=xi-1; x<=xi+2; ++x) {
@@ -164,7 +229,7 @@ droplet_kernel(float *__restrict__ padded, unsigned ntiles, int xsize, int ysize
 						}
 					}
 				}
-				__syncwarp();
+				if (G > 1) {__syncwarp(gmask);}
 				dh-=ds;
 				s+=ds;
 			}
@@ -176,7 +241,22 @@ droplet_kernel(float *__restrict__ padded, unsigned ntiles, int xsize, int ysize
 	}
 #undef HMAP
 #undef DEPOSIT
-	if (lane == 0 && steps_out) {atomicAdd(steps_out, steps);}
+	if (sub == 0 && steps_out && steps) {atomicAdd(steps_out, steps);}
+}
+
+template<int G>
+void launch_droplets(cudaStream_t st, float *d_pad, unsigned nt, int xsize, int ysize, unsigned num_iters, EParams const &E, const float2 *dir, unsigned long long *d_steps, const unsigned *order) {
+	unsigned const warps_per_block = 2, tiles_per_block = warps_per_block*(32/G);
+	droplet_kernel<G><<<(nt + tiles_per_block - 1)/tiles_per_block, 32*warps_per_block, 0, st>>>(d_pad, nt, xsize, ysize, num_iters, E, dir, d_steps, order);
+}
+
+// lanes per heightmap: the smallest group that still gives ~12 warps per SM (148 SMs), see the kernel comment
+int pick_group(unsigned ntiles) {
+	const char *env = getenv("TW_EROSION_LANES");
+	if (env) {int const g = atoi(env); if (g == 1 || g == 2 || g == 4 || g == 8 || g == 16 || g == 32) return g;}
+	(void)ntiles;
+	return 32; // measured on B200 (tools/bench_erosion.py): G = 32 wins at every heightmap count up to 65536 - the step is a serial
+	           // dependency chain (latency-bound), so coalesced accesses and fewer resident maps beat the saved redundant ALU work
 }
 
 } // namespace
@@ -201,22 +281,48 @@ int twi_erode(tw_ctx *ctx, float *d_maps, uint32_t ntiles, int xsize, int ysize,
 	unsigned long long *d_steps = (unsigned long long *)((char *)ctx->d_scratch[2] + 2048);
 	TW_CUDA(ctx, cudaMemsetAsync(d_steps, 0, sizeof(unsigned long long), ctx->stream));
 
-	// process tiles in chunks so that the padded scratch stays below ~4 GiB
-	size_t const max_chunk_bytes = (size_t)4 << 30;
+	// process heightmaps in chunks so that the padded scratch stays within a third of the free device memory (each chunk has its own
+	// heaviest-first schedule and its own tail, so fewer, larger chunks are better)
+	size_t free_b = 0, total_b = 0;
+	TW_CUDA(ctx, cudaMemGetInfo(&free_b, &total_b));
+	size_t max_chunk_bytes = (free_b + ctx->scratch_bytes[1])/3;
+	if (max_chunk_bytes < ((size_t)1 << 30)) max_chunk_bytes = (size_t)1 << 30;
 	uint32_t chunk = (uint32_t)(max_chunk_bytes/(padded_elems*sizeof(float)));
 	if (chunk < 1) chunk = 1;
 	if (chunk > ntiles) chunk = ntiles;
 	if (chunk > 65535) chunk = 65535; // gridDim.z limit
-	rc = tw_reserve(ctx, 1, (size_t)chunk*padded_elems*sizeof(float));
+	// scratch: padded heightmaps + per-heightmap work estimate, 256-bin histogram, schedule
+	size_t const pad_bytes = ((size_t)chunk*padded_elems*sizeof(float) + 255) & ~(size_t)255;
+	size_t const sched_bytes = ((size_t)chunk*2 + WORK_BINS)*sizeof(unsigned);
+	rc = tw_reserve(ctx, 1, pad_bytes + sched_bytes);
 	if (rc) return rc;
 	float *d_pad = (float *)ctx->d_scratch[1];
+	unsigned *d_work = (unsigned *)((char *)ctx->d_scratch[1] + pad_bytes), *d_hist = d_work + chunk, *d_order = d_hist + WORK_BINS;
+	bool const schedule = (chunk > 148u*4u); // with few heightmaps everything is resident at once anyway
 	for (uint32_t t0 = 0; t0 < ntiles; t0 += chunk) {
 		uint32_t const nt = (ntiles - t0 < chunk) ? (ntiles - t0) : chunk;
 		float *maps = d_maps + (size_t)t0*xsize*ysize;
-		pad_kernel<<<dim3((NX + 255)/256, NY, nt), 256, 0, ctx->stream>>>(maps, d_pad, xsize, ysize, NX, NY);
+		if (schedule) {TW_CUDA(ctx, cudaMemsetAsync(d_work, 0, ((size_t)chunk + WORK_BINS)*sizeof(unsigned), ctx->stream));}
+		pad_kernel<<<dim3((NX + 255)/256, NY, nt), 256, 0, ctx->stream>>>(maps, d_pad, xsize, ysize, NX, NY, E.wpz_minus_half_dxy, schedule ? d_work : nullptr);
 		TW_LAUNCH_CHECK(ctx);
-		unsigned const warps_per_block = 4;
-		droplet_kernel<<<(nt + warps_per_block - 1)/warps_per_block, 32*warps_per_block, 0, ctx->stream>>>(d_pad, nt, xsize, ysize, num_iters, E, ctx->d_dir_table, d_steps);
+		if (schedule) {
+			unsigned const max_work = (unsigned)padded_elems;
+			order_hist_kernel<<<(nt + 255)/256, 256, 0, ctx->stream>>>(d_work, nt, max_work, d_hist);
+			TW_LAUNCH_CHECK(ctx);
+			order_scan_kernel<<<1, 32, 0, ctx->stream>>>(d_hist);
+			TW_LAUNCH_CHECK(ctx);
+			order_scatter_kernel<<<(nt + 255)/256, 256, 0, ctx->stream>>>(d_work, nt, max_work, d_hist, d_order);
+			TW_LAUNCH_CHECK(ctx);
+		}
+		if (!schedule) {d_order = nullptr;}
+		switch (pick_group(nt)) {
+		case 1:  launch_droplets<1 >(ctx->stream, d_pad, nt, xsize, ysize, num_iters, E, ctx->d_dir_table, d_steps, d_order); break;
+		case 2:  launch_droplets<2 >(ctx->stream, d_pad, nt, xsize, ysize, num_iters, E, ctx->d_dir_table, d_steps, d_order); break;
+		case 4:  launch_droplets<4 >(ctx->stream, d_pad, nt, xsize, ysize, num_iters, E, ctx->d_dir_table, d_steps, d_order); break;
+		case 8:  launch_droplets<8 >(ctx->stream, d_pad, nt, xsize, ysize, num_iters, E, ctx->d_dir_table, d_steps, d_order); break;
+		case 16: launch_droplets<16>(ctx->stream, d_pad, nt, xsize, ysize, num_iters, E, ctx->d_dir_table, d_steps, d_order); break;
+		default: launch_droplets<32>(ctx->stream, d_pad, nt, xsize, ysize, num_iters, E, ctx->d_dir_table, d_steps, d_order); break;
+		}
 		TW_LAUNCH_CHECK(ctx);
 		unpad_kernel<<<dim3((xsize + 255)/256, ysize, nt), 256, 0, ctx->stream>>>(d_pad, maps, xsize, ysize, NX, NY, d_min_zvals ? d_min_zvals + t0 : nullptr, min_zval_all);
 		TW_LAUNCH_CHECK(ctx);
