@@ -74,7 +74,7 @@ def hmap_params(**kw):
 ABI_SYMBOLS = ["tw_abi_version", "tw_create", "tw_destroy", "tw_last_error", "tw_sync", "tw_stream", "tw_launch_count",
                "tw_build_sin_table", "tw_compute_scale", "tw_gen_sine_params", "tw_gen_rx_ry", "tw_noise3d_gen_sines",
                "tw_water_z_height", "tw_set_sin_table", "tw_set_sine_params", "tw_heightgen_2d", "tw_heightgen_2d_launch",
-               "tw_heightgen_2d_poll", "tw_heightgen_tiles", "tw_erode", "tw_erode_tiles", "tw_last_erosion_steps", "tw_voxel_fill",
+               "tw_heightgen_2d_poll", "tw_heightgen_tiles", "tw_create_zvals_batch", "tw_erode", "tw_erode_tiles", "tw_last_erosion_steps", "tw_voxel_fill",
                "tw_heightmap_from_floats_u16", "tw_heightmap_to_floats_u16", "tw_minmax_f32"]
 
 
@@ -113,6 +113,8 @@ def _load():
     L.tw_heightgen_2d_launch.argtypes = hg
     L.tw_heightgen_2d_poll.argtypes = [vp, C.c_int]
     L.tw_heightgen_tiles.argtypes = [vp, vp, C.c_uint32, C.c_int, C.c_int, C.c_float, C.c_float, C.c_uint32, C.POINTER(HeightParams), vp, vp]
+    L.tw_create_zvals_batch.argtypes = [vp, vp, C.c_uint32, C.c_int, C.c_int, C.c_float, C.c_float, C.c_uint32, C.POINTER(HeightParams), C.c_uint32,
+                                        C.POINTER(ErosionParams), C.c_float, vp, vp]
     L.tw_erode.argtypes = [vp, vp, C.c_int, C.c_int, C.c_float, C.c_uint32, C.POINTER(ErosionParams)]
     L.tw_erode_tiles.argtypes = [vp, vp, C.c_uint32, C.c_int, C.c_int, vp, C.c_float, C.c_uint32, C.POINTER(ErosionParams)]
     L.tw_last_erosion_steps.argtypes = [vp]
@@ -241,6 +243,17 @@ class Context:
             out = np.empty((nt, zvsize, zvsize), np.float32)
         mm = np.empty((nt, 2), np.float32) if want_minmax else None
         self._check(lib.tw_heightgen_tiles(self._h, _ptr(org), nt, mesh_size[0], mesh_size[1], dx, dy, zvsize, C.byref(hp), _ptr(out), _ptr(mm)))
+        return (out, mm) if want_minmax else out
+
+    def create_zvals_batch(self, origins_xy, mesh_size, dx, dy, zvsize, hp, erosion_iters, ep, min_zval, out=None, want_minmax=False):
+        """Fused height fill + per-tile erosion (tile_t::create_zvals for a batch of tiles)."""
+        org = np.ascontiguousarray(origins_xy, np.int32).reshape(-1, 2)
+        nt = org.shape[0]
+        if out is None:
+            out = np.empty((nt, zvsize, zvsize), np.float32)
+        mm = np.empty((nt, 2), np.float32) if want_minmax else None
+        self._check(lib.tw_create_zvals_batch(self._h, _ptr(org), nt, mesh_size[0], mesh_size[1], dx, dy, zvsize, C.byref(hp), erosion_iters,
+                                              C.byref(ep), min_zval, _ptr(out), _ptr(mm)))
         return (out, mm) if want_minmax else out
 
     def erode(self, h, min_zval, num_iters, ep):

@@ -110,6 +110,7 @@ void tw_destroy(tw_ctx *ctx) {
 	if (ctx->d_sine_params) cudaFree(ctx->d_sine_params);
 	if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
 	if (ctx->async.done) cudaEventDestroy(ctx->async.done);
+	for (int i = 0; i < 2; ++i) {if (ctx->aux_stream[i]) cudaStreamDestroy(ctx->aux_stream[i]);}
 	cudaStreamDestroy(ctx->stream);
 	delete ctx;
 }
@@ -278,6 +279,85 @@ int tw_erode_tiles(tw_ctx *ctx, float *maps, uint32_t ntiles, int xsize, int ysi
 	if (rc) return rc;
 	if (!dev) {TW_CUDA(ctx, cudaMemcpyAsync(maps, d_maps, n*sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));}
 	TW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	return TW_OK;
+}
+
+int tw_create_zvals_batch(tw_ctx *ctx, const int32_t *origins_xy, uint32_t ntiles, int mesh_x_size, int mesh_y_size, float dx, float dy,
+                          uint32_t zvsize, const tw_height_params *p, uint32_t erosion_iters, const tw_erosion_params *ep, float min_zval,
+                          float *out, tw_minmax *mm)
+{
+	int rc = check_ctx(ctx); if (rc) return rc;
+	rc = finish_pending(ctx); if (rc) return rc;
+	if (!origins_xy || ntiles == 0 || !p || !out) return tw_set_error(ctx, TW_ERR_ARG, "null/empty argument");
+	bool const erode = (erosion_iters > 0 && ep && ep->erode_amount > 0.0);
+	ctx->last_erosion_steps = 0;
+	if (!erode) {return tw_heightgen_tiles(ctx, origins_xy, ntiles, mesh_x_size, mesh_y_size, dx, dy, zvsize, p, out, mm);}
+	tw_grid2d g; g.x0 = 0; g.y0 = 0; g.dx = dx; g.dy = dy; g.nx = zvsize; g.ny = zvsize;
+	rc = validate_height(ctx, &g, p, out); if (rc) return rc;
+	size_t const tile_elems = (size_t)zvsize*zvsize, n = tile_elems*ntiles;
+	bool const dev_out = tw_is_device_ptr(out);
+	if (p->gen_mode == TW_MGEN_SINE) { // sine tables live in the same scratch slot as the padded maps: no overlap, plain sequence
+		float *d_out = out;
+		if (!dev_out) {rc = tw_reserve(ctx, 0, n*sizeof(float)); if (rc) return rc; d_out = (float *)ctx->d_scratch[0];}
+		rc = tw_heightgen_tiles(ctx, origins_xy, ntiles, mesh_x_size, mesh_y_size, dx, dy, zvsize, p, d_out, nullptr); if (rc) return rc;
+		rc = tw_erode_tiles(ctx, d_out, ntiles, (int)zvsize, (int)zvsize, nullptr, min_zval, erosion_iters, ep); if (rc) return rc;
+		if (mm) {for (uint32_t t = 0; t < ntiles; ++t) {rc = tw_minmax_f32(ctx, d_out + (size_t)t*tile_elems, tile_elems, mm + t); if (rc) return rc;}}
+		if (!dev_out) {TW_CUDA(ctx, cudaMemcpy(out, d_out, n*sizeof(float), cudaMemcpyDeviceToHost));}
+		return TW_OK;
+	}
+	for (int i = 0; i < 2; ++i) {if (!ctx->aux_stream[i]) {TW_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->aux_stream[i], cudaStreamNonBlocking));}}
+	float *d_out = out;
+	if (!dev_out) {rc = tw_reserve(ctx, 0, n*sizeof(float)); if (rc) return rc; d_out = (float *)ctx->d_scratch[0];}
+	// chunking: 4 chunks when there are enough tiles (2 erosion streams x 2), bounded by a third of the free memory for the two padded scratch buffers
+	size_t free_b = 0, total_b = 0;
+	TW_CUDA(ctx, cudaMemGetInfo(&free_b, &total_b));
+	size_t budget = (free_b + ctx->scratch_bytes[1])/3/2;
+	if (budget < ((size_t)512 << 20)) budget = (size_t)512 << 20;
+	uint32_t chunk = (ntiles >= 4096) ? (ntiles + 3)/4 : ntiles;
+	uint32_t const cap = twi_erode_chunk_for(budget, chunk, (int)zvsize, (int)zvsize);
+	chunk = cap;
+	uint32_t const nchunks = (ntiles + chunk - 1)/chunk;
+	int const nes = (nchunks > 1) ? 2 : 1; // erosion streams / scratch buffers
+	size_t const sbytes = twi_erode_scratch_bytes(chunk, (int)zvsize, (int)zvsize);
+	rc = tw_reserve(ctx, 1, sbytes*nes); if (rc) return rc;
+	size_t const mm_bytes = (size_t)ntiles*2*sizeof(unsigned), org_bytes = (size_t)ntiles*sizeof(float2);
+	rc = tw_reserve(ctx, 2, OFF_TILES + mm_bytes + org_bytes); if (rc) return rc;
+	unsigned *d_mm = (unsigned *)((char *)ctx->d_scratch[2] + OFF_TILES);
+	float2 *d_org = (float2 *)((char *)ctx->d_scratch[2] + OFF_TILES + mm_bytes);
+	unsigned long long *d_steps = (unsigned long long *)((char *)ctx->d_scratch[2] + 2048);
+	{
+		std::vector<float2> org(ntiles);
+		for (uint32_t t = 0; t < ntiles; ++t) { // build_arrays((x1 - MESH_X_SIZE/2), (y1 - MESH_Y_SIZE/2), ...): int -> float, mx0 = dx*x0 (src/tiled_mesh.cpp:461, src/mesh_gen.cpp:591)
+			float const x0 = (float)(origins_xy[2*t] - mesh_x_size/2), y0 = (float)(origins_xy[2*t+1] - mesh_y_size/2);
+			org[t] = make_float2(dx*x0, dy*y0);
+		}
+		TW_CUDA(ctx, cudaMemcpyAsync(d_org, org.data(), org_bytes, cudaMemcpyHostToDevice, ctx->stream));
+		TW_CUDA(ctx, cudaMemsetAsync(d_steps, 0, sizeof(unsigned long long), ctx->stream));
+		TW_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); // org is a local vector; the aux streams must also see d_steps zeroed
+	}
+	std::vector<cudaEvent_t> ev(nchunks, nullptr);
+	int status = TW_OK;
+	for (uint32_t k = 0; k < nchunks && status == TW_OK; ++k) {
+		uint32_t const t0 = k*chunk, nt = (ntiles - t0 < chunk) ? (ntiles - t0) : chunk;
+		float *maps = d_out + (size_t)t0*tile_elems;
+		status = twi_heightgen(ctx, &g, p, 1, 0, d_org + t0, nt, maps, nullptr);           // generation on ctx->stream
+		if (status) break;
+		if (cudaEventCreateWithFlags(&ev[k], cudaEventDisableTiming) != cudaSuccess || cudaEventRecord(ev[k], ctx->stream) != cudaSuccess) {status = tw_set_error(ctx, TW_ERR_CUDA, "event"); break;}
+		cudaStream_t const es = ctx->aux_stream[k % nes];
+		if (cudaStreamWaitEvent(es, ev[k], 0) != cudaSuccess) {status = tw_set_error(ctx, TW_ERR_CUDA, "cudaStreamWaitEvent"); break;}
+		status = twi_erode_enqueue(ctx, es, (char *)ctx->d_scratch[1] + (size_t)(k % nes)*sbytes, chunk, maps, nt, (int)zvsize, (int)zvsize, nullptr, min_zval, erosion_iters, ep, d_steps);
+		if (status) break;
+		if (mm) {status = twi_minmax_tiles(ctx, es, maps, tile_elems, nt, d_mm + 2*(size_t)t0); if (status) break;}
+		if (!dev_out && cudaMemcpyAsync(out + (size_t)t0*tile_elems, maps, (size_t)nt*tile_elems*sizeof(float), cudaMemcpyDeviceToHost, es) != cudaSuccess) {status = tw_set_error(ctx, TW_ERR_CUDA, "D2H");}
+	}
+	cudaError_t e0 = cudaStreamSynchronize(ctx->stream), e1 = cudaStreamSynchronize(ctx->aux_stream[0]), e2 = cudaStreamSynchronize(ctx->aux_stream[1]);
+	for (cudaEvent_t e : ev) {if (e) cudaEventDestroy(e);}
+	if (status) return status;
+	if (e0 != cudaSuccess || e1 != cudaSuccess || e2 != cudaSuccess) return tw_set_error(ctx, TW_ERR_CUDA, "tile pipeline: %s", cudaGetErrorString(e0 != cudaSuccess ? e0 : (e1 != cudaSuccess ? e1 : e2)));
+	unsigned long long h_steps = 0;
+	TW_CUDA(ctx, cudaMemcpy(&h_steps, d_steps, sizeof(h_steps), cudaMemcpyDeviceToHost));
+	ctx->last_erosion_steps = h_steps;
+	if (mm) {rc = read_minmax(ctx, d_mm, mm, ntiles); if (rc) return rc;}
 	return TW_OK;
 }
 

@@ -261,6 +261,70 @@ int pick_group(unsigned ntiles) {
 
 } // namespace
 
+static EParams make_eparams(const tw_erosion_params *p) {
+	EParams E;
+	E.erode_amount = p->erode_amount;
+	E.wpz_minus_half_dxy = p->water_plane_z - p->half_dxy;
+	E.zmin = p->zmin; E.zrange = p->zmax - p->zmin;
+	E.relh_adj_tex = p->relh_adj_tex; E.clip_hd1 = p->clip_hd1;
+	return E;
+}
+
+size_t twi_erode_scratch_bytes(uint32_t chunk, int xsize, int ysize) {
+	size_t const padded_elems = (size_t)(xsize + 2*PAD)*(ysize + 2*PAD);
+	size_t const pad_bytes = ((size_t)chunk*padded_elems*sizeof(float) + 255) & ~(size_t)255;
+	return pad_bytes + (((size_t)chunk*2 + WORK_BINS)*sizeof(unsigned) + 255 & ~(size_t)255);
+}
+
+// Enqueue pad -> schedule -> droplets -> unpad for nt <= 65535 heightmaps on `st`, using `scratch` (twi_erode_scratch_bytes(capacity,..) bytes).
+// No synchronisation; d_steps (device counter) accumulates the droplet moves.
+int twi_erode_enqueue(tw_ctx *ctx, cudaStream_t st, void *scratch, uint32_t capacity, float *maps, uint32_t nt, int xsize, int ysize,
+                      const float *d_min_zvals, float min_zval_all, uint32_t num_iters, const tw_erosion_params *p, unsigned long long *d_steps)
+{
+	int const NX = xsize + 2*PAD, NY = ysize + 2*PAD;
+	size_t const padded_elems = (size_t)NX*NY;
+	EParams const E = make_eparams(p);
+	size_t const pad_bytes = ((size_t)capacity*padded_elems*sizeof(float) + 255) & ~(size_t)255;
+	float *d_pad = (float *)scratch;
+	unsigned *d_work = (unsigned *)((char *)scratch + pad_bytes), *d_hist = d_work + capacity, *d_order = d_hist + WORK_BINS;
+	bool const schedule = (nt > 148u*4u); // with few heightmaps everything is resident at once anyway
+	if (schedule) {TW_CUDA(ctx, cudaMemsetAsync(d_work, 0, ((size_t)capacity + WORK_BINS)*sizeof(unsigned), st));}
+	pad_kernel<<<dim3((NX + 255)/256, NY, nt), 256, 0, st>>>(maps, d_pad, xsize, ysize, NX, NY, E.wpz_minus_half_dxy, schedule ? d_work : nullptr);
+	TW_LAUNCH_CHECK(ctx);
+	if (schedule) {
+		unsigned const max_work = (unsigned)padded_elems;
+		order_hist_kernel<<<(nt + 255)/256, 256, 0, st>>>(d_work, nt, max_work, d_hist);
+		TW_LAUNCH_CHECK(ctx);
+		order_scan_kernel<<<1, 32, 0, st>>>(d_hist);
+		TW_LAUNCH_CHECK(ctx);
+		order_scatter_kernel<<<(nt + 255)/256, 256, 0, st>>>(d_work, nt, max_work, d_hist, d_order);
+		TW_LAUNCH_CHECK(ctx);
+	}
+	else {d_order = nullptr;}
+	switch (pick_group(nt)) {
+	case 1:  launch_droplets<1 >(st, d_pad, nt, xsize, ysize, num_iters, E, ctx->d_dir_table, d_steps, d_order); break;
+	case 2:  launch_droplets<2 >(st, d_pad, nt, xsize, ysize, num_iters, E, ctx->d_dir_table, d_steps, d_order); break;
+	case 4:  launch_droplets<4 >(st, d_pad, nt, xsize, ysize, num_iters, E, ctx->d_dir_table, d_steps, d_order); break;
+	case 8:  launch_droplets<8 >(st, d_pad, nt, xsize, ysize, num_iters, E, ctx->d_dir_table, d_steps, d_order); break;
+	case 16: launch_droplets<16>(st, d_pad, nt, xsize, ysize, num_iters, E, ctx->d_dir_table, d_steps, d_order); break;
+	default: launch_droplets<32>(st, d_pad, nt, xsize, ysize, num_iters, E, ctx->d_dir_table, d_steps, d_order); break;
+	}
+	TW_LAUNCH_CHECK(ctx);
+	unpad_kernel<<<dim3((xsize + 255)/256, ysize, nt), 256, 0, st>>>(d_pad, maps, xsize, ysize, NX, NY, d_min_zvals, min_zval_all);
+	TW_LAUNCH_CHECK(ctx);
+	return TW_OK;
+}
+
+// largest chunk (heightmaps per enqueue) whose scratch fits in `budget` bytes
+uint32_t twi_erode_chunk_for(size_t budget, uint32_t ntiles, int xsize, int ysize) {
+	size_t const per = (size_t)(xsize + 2*PAD)*(ysize + 2*PAD)*sizeof(float) + 2*sizeof(unsigned);
+	size_t c = budget/per;
+	if (c < 1) c = 1;
+	if (c > ntiles) c = ntiles;
+	if (c > 65535) c = 65535; // gridDim.z limit
+	return (uint32_t)c;
+}
+
 int twi_erode(tw_ctx *ctx, float *d_maps, uint32_t ntiles, int xsize, int ysize, const float *d_min_zvals, float min_zval_all,
               uint32_t num_iters, const tw_erosion_params *p)
 {
@@ -268,64 +332,24 @@ int twi_erode(tw_ctx *ctx, float *d_maps, uint32_t ntiles, int xsize, int ysize,
 	if (num_iters == 0 || p->erode_amount <= 0.0) return TW_OK; // erosion disabled, src/erosion.cpp:16
 	if (xsize <= 0 || ysize <= 0 || ntiles == 0) return tw_set_error(ctx, TW_ERR_ARG, "tw_erode: empty heightmap");
 	if (!ctx->d_dir_table) return tw_set_error(ctx, TW_ERR_STATE, "tw_set_sin_table() has not been called");
-	int const NX = xsize + 2*PAD, NY = ysize + 2*PAD;
-	size_t const padded_elems = (size_t)NX*NY;
-	EParams E;
-	E.erode_amount = p->erode_amount;
-	E.wpz_minus_half_dxy = p->water_plane_z - p->half_dxy;
-	E.zmin = p->zmin; E.zrange = p->zmax - p->zmin;
-	E.relh_adj_tex = p->relh_adj_tex; E.clip_hd1 = p->clip_hd1;
-
 	int rc = tw_reserve(ctx, 2, 4096);
 	if (rc) return rc;
 	unsigned long long *d_steps = (unsigned long long *)((char *)ctx->d_scratch[2] + 2048);
 	TW_CUDA(ctx, cudaMemsetAsync(d_steps, 0, sizeof(unsigned long long), ctx->stream));
-
 	// process heightmaps in chunks so that the padded scratch stays within a third of the free device memory (each chunk has its own
 	// heaviest-first schedule and its own tail, so fewer, larger chunks are better)
 	size_t free_b = 0, total_b = 0;
 	TW_CUDA(ctx, cudaMemGetInfo(&free_b, &total_b));
-	size_t max_chunk_bytes = (free_b + ctx->scratch_bytes[1])/3;
-	if (max_chunk_bytes < ((size_t)1 << 30)) max_chunk_bytes = (size_t)1 << 30;
-	uint32_t chunk = (uint32_t)(max_chunk_bytes/(padded_elems*sizeof(float)));
-	if (chunk < 1) chunk = 1;
-	if (chunk > ntiles) chunk = ntiles;
-	if (chunk > 65535) chunk = 65535; // gridDim.z limit
-	// scratch: padded heightmaps + per-heightmap work estimate, 256-bin histogram, schedule
-	size_t const pad_bytes = ((size_t)chunk*padded_elems*sizeof(float) + 255) & ~(size_t)255;
-	size_t const sched_bytes = ((size_t)chunk*2 + WORK_BINS)*sizeof(unsigned);
-	rc = tw_reserve(ctx, 1, pad_bytes + sched_bytes);
+	size_t budget = (free_b + ctx->scratch_bytes[1])/3;
+	if (budget < ((size_t)1 << 30)) budget = (size_t)1 << 30;
+	uint32_t const chunk = twi_erode_chunk_for(budget, ntiles, xsize, ysize);
+	rc = tw_reserve(ctx, 1, twi_erode_scratch_bytes(chunk, xsize, ysize));
 	if (rc) return rc;
-	float *d_pad = (float *)ctx->d_scratch[1];
-	unsigned *d_work = (unsigned *)((char *)ctx->d_scratch[1] + pad_bytes), *d_hist = d_work + chunk, *d_order = d_hist + WORK_BINS;
-	bool const schedule = (chunk > 148u*4u); // with few heightmaps everything is resident at once anyway
 	for (uint32_t t0 = 0; t0 < ntiles; t0 += chunk) {
 		uint32_t const nt = (ntiles - t0 < chunk) ? (ntiles - t0) : chunk;
-		float *maps = d_maps + (size_t)t0*xsize*ysize;
-		if (schedule) {TW_CUDA(ctx, cudaMemsetAsync(d_work, 0, ((size_t)chunk + WORK_BINS)*sizeof(unsigned), ctx->stream));}
-		pad_kernel<<<dim3((NX + 255)/256, NY, nt), 256, 0, ctx->stream>>>(maps, d_pad, xsize, ysize, NX, NY, E.wpz_minus_half_dxy, schedule ? d_work : nullptr);
-		TW_LAUNCH_CHECK(ctx);
-		if (schedule) {
-			unsigned const max_work = (unsigned)padded_elems;
-			order_hist_kernel<<<(nt + 255)/256, 256, 0, ctx->stream>>>(d_work, nt, max_work, d_hist);
-			TW_LAUNCH_CHECK(ctx);
-			order_scan_kernel<<<1, 32, 0, ctx->stream>>>(d_hist);
-			TW_LAUNCH_CHECK(ctx);
-			order_scatter_kernel<<<(nt + 255)/256, 256, 0, ctx->stream>>>(d_work, nt, max_work, d_hist, d_order);
-			TW_LAUNCH_CHECK(ctx);
-		}
-		if (!schedule) {d_order = nullptr;}
-		switch (pick_group(nt)) {
-		case 1:  launch_droplets<1 >(ctx->stream, d_pad, nt, xsize, ysize, num_iters, E, ctx->d_dir_table, d_steps, d_order); break;
-		case 2:  launch_droplets<2 >(ctx->stream, d_pad, nt, xsize, ysize, num_iters, E, ctx->d_dir_table, d_steps, d_order); break;
-		case 4:  launch_droplets<4 >(ctx->stream, d_pad, nt, xsize, ysize, num_iters, E, ctx->d_dir_table, d_steps, d_order); break;
-		case 8:  launch_droplets<8 >(ctx->stream, d_pad, nt, xsize, ysize, num_iters, E, ctx->d_dir_table, d_steps, d_order); break;
-		case 16: launch_droplets<16>(ctx->stream, d_pad, nt, xsize, ysize, num_iters, E, ctx->d_dir_table, d_steps, d_order); break;
-		default: launch_droplets<32>(ctx->stream, d_pad, nt, xsize, ysize, num_iters, E, ctx->d_dir_table, d_steps, d_order); break;
-		}
-		TW_LAUNCH_CHECK(ctx);
-		unpad_kernel<<<dim3((xsize + 255)/256, ysize, nt), 256, 0, ctx->stream>>>(d_pad, maps, xsize, ysize, NX, NY, d_min_zvals ? d_min_zvals + t0 : nullptr, min_zval_all);
-		TW_LAUNCH_CHECK(ctx);
+		rc = twi_erode_enqueue(ctx, ctx->stream, ctx->d_scratch[1], chunk, d_maps + (size_t)t0*xsize*ysize, nt, xsize, ysize,
+		                       d_min_zvals ? d_min_zvals + t0 : nullptr, min_zval_all, num_iters, p, d_steps);
+		if (rc) return rc;
 	}
 	unsigned long long h_steps = 0;
 	TW_CUDA(ctx, cudaMemcpyAsync(&h_steps, d_steps, sizeof(h_steps), cudaMemcpyDeviceToHost, ctx->stream));

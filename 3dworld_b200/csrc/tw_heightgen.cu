@@ -274,6 +274,16 @@ __global__ void minmax_kernel(const float *__restrict__ v, size_t n, unsigned *m
 	block_minmax(vmin, vmax, mm);
 }
 
+// one block per heightmap: min/max of tile t -> mm[2t], mm[2t+1] (ordered-uint encoding)
+__global__ void minmax_tiles_kernel(const float *__restrict__ v, size_t tile_elems, unsigned *mm) {
+	const float *t = v + (size_t)blockIdx.x*tile_elems;
+	if (threadIdx.x == 0) {mm[2*blockIdx.x] = 0xffffffffu; mm[2*blockIdx.x + 1] = 0u;}
+	__syncthreads();
+	float vmin = INFINITY, vmax = -INFINITY;
+	for (size_t i = threadIdx.x; i < tile_elems; i += blockDim.x) {float const z = __ldg(t + i); vmin = fminf(vmin, z); vmax = fmaxf(vmax, z);}
+	block_minmax(vmin, vmax, mm + 2*blockIdx.x);
+}
+
 template<bool SIMPLEX, bool WARP>
 void launch_noise(int shape, dim3 grid, dim3 block, cudaStream_t st, float *out, unsigned nx, unsigned ny, float mx0, float my0,
 	const float2 *origins, const NoiseParams &N, const PostParams &P, const float *tab, unsigned *mm)
@@ -289,6 +299,12 @@ void launch_noise(int shape, dim3 grid, dim3 block, cudaStream_t st, float *out,
 
 int twi_init_minmax(tw_ctx *ctx, unsigned *d_mm_ord, uint32_t n) {
 	init_minmax_kernel<<<(n + 255)/256, 256, 0, ctx->stream>>>(d_mm_ord, n);
+	TW_LAUNCH_CHECK(ctx);
+	return TW_OK;
+}
+
+int twi_minmax_tiles(tw_ctx *ctx, cudaStream_t st, const float *d_vals, size_t tile_elems, uint32_t nt, unsigned *d_mm_ord) {
+	minmax_tiles_kernel<<<nt, 256, 0, st>>>(d_vals, tile_elems, d_mm_ord);
 	TW_LAUNCH_CHECK(ctx);
 	return TW_OK;
 }

@@ -18,6 +18,7 @@ struct tw_async_state {
 struct tw_ctx {
 	int device = 0;
 	cudaStream_t stream = nullptr;
+	cudaStream_t aux_stream[2] = {nullptr, nullptr}; // erosion side of the fused tile pipeline (tw_create_zvals_batch)
 	char err[512] = {0};
 	uint64_t launches = 0;
 	uint64_t last_erosion_steps = 0;
@@ -83,8 +84,13 @@ int twi_heightgen(tw_ctx *ctx, const tw_grid2d *g, const tw_height_params *p, in
                   const float2 *d_tile_origins, uint32_t ntiles, float *d_out, unsigned *d_mm_ord);
 int twi_erode(tw_ctx *ctx, float *d_maps, uint32_t ntiles, int xsize, int ysize, const float *d_min_zvals, float min_zval_all,
               uint32_t num_iters, const tw_erosion_params *p);
+size_t   twi_erode_scratch_bytes(uint32_t chunk, int xsize, int ysize);
+uint32_t twi_erode_chunk_for(size_t budget, uint32_t ntiles, int xsize, int ysize);
+int twi_erode_enqueue(tw_ctx *ctx, cudaStream_t st, void *scratch, uint32_t capacity, float *maps, uint32_t nt, int xsize, int ysize,
+                      const float *d_min_zvals, float min_zval_all, uint32_t num_iters, const tw_erosion_params *p, unsigned long long *d_steps);
 int twi_voxel_fill(tw_ctx *ctx, const tw_voxel_params *vp, const float *rdata420, float *d_out);
 int twi_from_floats_u16(tw_ctx *ctx, const float *d_vals, size_t n, float val_mult, float val_add, uint8_t *d_out, unsigned *d_bad);
 int twi_to_floats_u16(tw_ctx *ctx, const uint8_t *d_data, size_t n, float val_mult, float val_add, float *d_vals);
 int twi_minmax(tw_ctx *ctx, const float *d_vals, size_t n, unsigned *d_mm_ord);
+int twi_minmax_tiles(tw_ctx *ctx, cudaStream_t st, const float *d_vals, size_t tile_elems, uint32_t nt, unsigned *d_mm_ord);
 int twi_init_minmax(tw_ctx *ctx, unsigned *d_mm_ord, uint32_t n);

@@ -197,15 +197,11 @@ inline void apply_erosion(float *heightmap, int xsize, int ysize, float min_zval
 inline void create_zvals_batch(const int32_t *origins_xy, unsigned ntiles, unsigned zvsize, float dx, float dy, unsigned erosion_iters_tt, float *zvals_out, tw_minmax *mm = nullptr) {
 	scene_globals const &g = globals();
 	tw_height_params const p = height_params_from_globals(g.mesh_gen_mode, g.mesh_gen_shape);
+	tw_erosion_params const e = erosion_params_from_globals();
 	tw_ctx *c = ctx();
-	int rc = tw_heightgen_tiles(c, origins_xy, ntiles, g.MESH_X_SIZE, g.MESH_Y_SIZE, dx, dy, zvsize, &p, zvals_out, (erosion_iters_tt == 0) ? mm : nullptr);
-	if (rc != TW_OK) {detail::fail(rc, "create_zvals_batch(height)", c);}
-	if (erosion_iters_tt > 0) {
-		tw_erosion_params const e = erosion_params_from_globals();
-		rc = tw_erode_tiles(c, zvals_out, ntiles, (int)zvsize, (int)zvsize, nullptr, g.zmin, erosion_iters_tt, &e); // apply_erosion(zvals, zvsize, zvsize, zmin, iters), src/tiled_mesh.cpp:515
-		if (rc != TW_OK) {detail::fail(rc, "create_zvals_batch(erosion)", c);}
-		if (mm) {for (unsigned t = 0; t < ntiles; ++t) {rc = tw_minmax_f32(c, zvals_out + (size_t)t*zvsize*zvsize, (size_t)zvsize*zvsize, mm + t); if (rc != TW_OK) {detail::fail(rc, "minmax", c);}}}
-	}
+	// apply_erosion(zvals.data(), zvsize, zvsize, zmin, erosion_iters_tt): min_zval is the global zmin (src/tiled_mesh.cpp:515)
+	int const rc = tw_create_zvals_batch(c, origins_xy, ntiles, g.MESH_X_SIZE, g.MESH_Y_SIZE, dx, dy, zvsize, &p, erosion_iters_tt, &e, g.zmin, zvals_out, mm);
+	if (rc != TW_OK) {detail::fail(rc, "create_zvals_batch", c);}
 }
 
 // noise_gen_3d: the table-generation half of the reference class (src/upsurface.h:39-50); grid evaluation goes through create_procedural

@@ -310,21 +310,34 @@ def extra_measurements(tw, scene, ctx, stream, torch):
     ms = timed(lambda: ctx.voxel_fill(vp, out=d_vox), 3)
     res["voxel_sine_512_voxels_per_s"] = 512 ** 3 / (ms * 1e-3)
     res["voxel_sine_512_store_GBps"] = 4 * 512 ** 3 / (ms * 1e-3) / 1e9
-    # tiled erosion (BASELINE config 5 shape): 2048 tiles of 258^2, 1000 droplets each, reference per-tile semantics
-    cfg = scene.SceneConfig(mesh_gen_mode=1, mesh_freq_filter=1, mesh_seed=1, hmap=HM_CFG, zmax_est=2.3, mesh_size=(256, 256, 1))
-    hp = cfg.height_params()
-    nt, zv = 2048, 258
-    origins = [((t % 64) * 256, (t // 64) * 256) for t in range(nt)]
+    # tiled terrain + erosion (BASELINE config 5 shape): 16384 tiles of 258^2 (a quarter of the 65536^2 grid), 1000 droplets per tile,
+    # reference per-tile semantics; tw_create_zvals_batch = chunked multi-stream pipeline (generation overlaps the droplet walks)
+    cfg = scene.SceneConfig(mesh_gen_mode=4, mesh_freq_filter=1, mesh_seed=1, hmap=HM_CFG, zmax_est=2.3, mesh_size=(256, 256, 1))
+    hp, ep = cfg.height_params(), cfg.erosion_params()
+    nt, zv = 16384, 258
+    origins = [((t % 128) * 256, (t // 128) * 256) for t in range(nt)]
     tiles = torch.empty((nt, zv, zv), dtype=torch.float32, device="cuda")
-    ctx.heightgen_tiles(origins, cfg.mesh_size, float(cfg.dx_val), float(cfg.dy_val), zv, hp, out=tiles)
-    zmin, zmax = ctx.minmax(tiles)
-    ep = cfg.erosion_params()
+    dxv, dyv = float(cfg.dx_val), float(cfg.dy_val)
+    ctx.create_zvals_batch(origins[:2048], cfg.mesh_size, dxv, dyv, zv, hp, 100, ep, ep.zmin, out=tiles[:2048])   # warm-up (allocations)
+    torch.cuda.synchronize()
     t0 = time.perf_counter()
-    ctx.erode_tiles(tiles, 1000, ep, min_zval_all=zmin)
-    dt = time.perf_counter() - t0
-    res["erosion_tiles_258_droplets_per_s"] = nt * 1000 / dt
-    res["erosion_tiles_steps_per_s"] = ctx.last_erosion_steps / dt
-    res["erosion_tiles_config"] = "%d tiles x 258^2 x 1000 droplets, %.1f steps/droplet" % (nt, ctx.last_erosion_steps / (nt * 1000.0))
+    ctx.heightgen_tiles(origins, cfg.mesh_size, dxv, dyv, zv, hp, out=tiles)
+    t_gen = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    ctx.erode_tiles(tiles, 1000, ep, min_zval_all=ep.zmin)
+    t_ero = time.perf_counter() - t0
+    steps = ctx.last_erosion_steps
+    t0 = time.perf_counter()
+    ctx.create_zvals_batch(origins, cfg.mesh_size, dxv, dyv, zv, hp, 1000, ep, ep.zmin, out=tiles)
+    t_fused = time.perf_counter() - t0
+    res["tiles_258_config"] = "%d tiles x 258^2, mode 4 8-octave + 1000 droplets/tile, %.1f moves/droplet" % (nt, steps / (nt * 1000.0))
+    res["tiles_heightgen_cells_per_s"] = nt * zv * zv / t_gen
+    res["tiles_erosion_droplets_per_s"] = nt * 1000 / t_ero
+    res["tiles_erosion_moves_per_s"] = steps / t_ero
+    res["tiles_fused_pipeline_s"] = t_fused
+    res["tiles_separate_calls_s"] = t_gen + t_ero
+    res["tiles_fused_cells_per_s"] = nt * zv * zv / t_fused
+    res["tiles_fused_droplets_per_s"] = nt * 1000 / t_fused
     return res
 
 

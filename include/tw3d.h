@@ -166,6 +166,13 @@ TW_API int tw_erode(tw_ctx *ctx, float *heightmap, int xsize, int ysize, float m
  * min_zval_all for every tile. */
 TW_API int tw_erode_tiles(tw_ctx *ctx, float *heightmaps, uint32_t ntiles, int xsize, int ysize, const float *min_zvals, float min_zval_all,
                    uint32_t num_iters, const tw_erosion_params *p);
+/* Fused tile pipeline = the height fill AND the per-tile erosion of tile_t::create_zvals (src/tiled_mesh.cpp:467-515) for a batch of tiles:
+ * exactly tw_heightgen_tiles followed by tw_erode_tiles(min_zval_all = min_zval), but issued in chunks on separate CUDA streams so that the
+ * latency-bound droplet walk of one chunk overlaps the ALU-bound height generation of the next. mm (optional, HOST, ntiles entries) receives
+ * the per-tile z range AFTER erosion (mzmin/mzmax). erosion_iters == 0 or erode_amount <= 0 => height fill only. */
+TW_API int tw_create_zvals_batch(tw_ctx *ctx, const int32_t *origins_xy, uint32_t ntiles, int mesh_x_size, int mesh_y_size, float dx, float dy,
+                          uint32_t zvsize, const tw_height_params *p, uint32_t erosion_iters, const tw_erosion_params *ep, float min_zval,
+                          float *out, tw_minmax *mm);
 /* droplet steps executed by the last tw_erode/tw_erode_tiles call (sum over droplets; for roofline byte accounting) */
 TW_API uint64_t tw_last_erosion_steps(const tw_ctx *ctx);
 

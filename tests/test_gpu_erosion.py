@@ -74,3 +74,33 @@ def test_erode_matches_linked_reference(tw, scene, ref, ctx, beq):
     zr = ref.apply_erosion(z, zmin, 1000, water_plane_z=zmin - 10, zmin=zmin - 0.1, zmax=zmax + 0.1, clip_hd1=0.5)
     zg = ctx.erode(z.copy(), zmin, 1000, tw.ErosionParams(1.0, zmin - 10, 0.0625, zmin - 0.1, zmax + 0.1, 0.0, 0.5))
     assert beq(zg, zr) == 0
+
+
+@pytest.mark.parametrize("nt_side,mode", [(3, 1), (70, 1), (66, 4), (5, 0)])
+def test_fused_tile_pipeline_equals_separate_calls(tw, scene, oracle, ctx, beq, nt_side, mode):
+    """tw_create_zvals_batch (chunked, multi-stream: generation of chunk k+1 overlaps the droplet walk of chunk k) == tw_heightgen_tiles +
+    tw_erode_tiles; 70x70 = 4900 tiles exercises the chunked/overlapped path and the heaviest-first schedule, spot-checked against the oracle."""
+    S, zv = 16, 18
+    cfg = scene.SceneConfig(mesh_gen_mode=mode, mesh_freq_filter=1, mesh_seed=1, hmap=HM_CFG, zmax_est=2.3, mesh_size=(S, S, 1), scene_size=(0.5, 0.5, 4.0))
+    hp, ep = cfg.height_params(), cfg.erosion_params()
+    if mode == 0:
+        ctx.set_sine_params(cfg.sine_params())
+    origins = [(tx * S * 40 - 3000, ty * S * 40 + 500) for ty in range(nt_side) for tx in range(nt_side)]   # spread out: ocean and mountain tiles
+    dx, dy = float(cfg.dx_val), float(cfg.dy_val)
+    sep = ctx.heightgen_tiles(origins, cfg.mesh_size, dx, dy, zv, hp)
+    raw = sep.copy()
+    ctx.erode_tiles(sep, 60, ep, min_zval_all=ep.zmin)
+    steps_sep = ctx.last_erosion_steps
+    fused, mm = ctx.create_zvals_batch(origins, cfg.mesh_size, dx, dy, zv, hp, 60, ep, ep.zmin, want_minmax=True)
+    assert beq(fused, sep) == 0
+    assert ctx.last_erosion_steps == steps_sep
+    assert np.array_equal(mm[:, 0], sep.min(axis=(1, 2))) and np.array_equal(mm[:, 1], sep.max(axis=(1, 2)))
+    for t in (0, len(origins) // 2, len(origins) - 1):
+        zc, _ = oracle.apply_erosion(raw[t], ep.zmin, 60, convert(ep, oracle.ErosionParams))
+        assert beq(fused[t], zc) == 0
+    import torch
+    dev = torch.empty((len(origins), zv, zv), dtype=torch.float32, device="cuda")
+    ctx.create_zvals_batch(origins, cfg.mesh_size, dx, dy, zv, hp, 60, ep, ep.zmin, out=dev)
+    assert beq(dev.cpu().numpy(), sep) == 0
+    no_erosion = ctx.create_zvals_batch(origins, cfg.mesh_size, dx, dy, zv, hp, 0, ep, ep.zmin)
+    assert beq(no_erosion, raw) == 0
