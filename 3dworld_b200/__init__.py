@@ -191,11 +191,15 @@ class Context:
         self._check(lib.tw_set_sin_table(self._h, _ptr(sin_table)))
 
     def close(self):
-        if getattr(self, "_h", None):
+        if getattr(self, "_h", None) and lib is not None:   # lib can already be gone at interpreter shutdown
             lib.tw_destroy(self._h)
-            self._h = None
+        self._h = None
 
-    __del__ = close
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
     def _check(self, rc):
         if rc != TW_OK:

@@ -305,15 +305,23 @@ int tw_create_zvals_batch(tw_ctx *ctx, const int32_t *origins_xy, uint32_t ntile
 		if (!dev_out) {TW_CUDA(ctx, cudaMemcpy(out, d_out, n*sizeof(float), cudaMemcpyDeviceToHost));}
 		return TW_OK;
 	}
-	for (int i = 0; i < 2; ++i) {if (!ctx->aux_stream[i]) {TW_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->aux_stream[i], cudaStreamNonBlocking));}}
+	if (!ctx->aux_stream[0]) { // the latency-bound droplet kernels get the higher priority so that they take SM slots as soon as the
+		int lo = 0, hi = 0;    // ALU-bound generation blocks of the next chunk retire, instead of queueing behind them
+		TW_CUDA(ctx, cudaDeviceGetStreamPriorityRange(&lo, &hi));
+		bool const prio = !(getenv("TW_PIPE_NOPRIO"));
+		for (int i = 0; i < 2; ++i) {TW_CUDA(ctx, cudaStreamCreateWithPriority(&ctx->aux_stream[i], cudaStreamNonBlocking, prio ? hi : lo));}
+	}
 	float *d_out = out;
 	if (!dev_out) {rc = tw_reserve(ctx, 0, n*sizeof(float)); if (rc) return rc; d_out = (float *)ctx->d_scratch[0];}
-	// chunking: 4 chunks when there are enough tiles (2 erosion streams x 2), bounded by a third of the free memory for the two padded scratch buffers
+	// chunking: measured on B200 (tools/bench_pipeline.py) every extra chunk adds its own droplet tail (the heaviest tile of a chunk is a
+	// serial chain of ~1e5 moves), which outweighs the generation/erosion overlap; so one chunk unless memory forces more (TW_PIPE_CHUNKS overrides)
 	size_t free_b = 0, total_b = 0;
 	TW_CUDA(ctx, cudaMemGetInfo(&free_b, &total_b));
 	size_t budget = (free_b + ctx->scratch_bytes[1])/3/2;
 	if (budget < ((size_t)512 << 20)) budget = (size_t)512 << 20;
-	uint32_t chunk = (ntiles >= 4096) ? (ntiles + 3)/4 : ntiles;
+	uint32_t want_chunks = 1;
+	if (const char *e = getenv("TW_PIPE_CHUNKS")) {int const v = atoi(e); if (v >= 1 && v <= 64) want_chunks = (uint32_t)v;}
+	uint32_t chunk = (ntiles >= 4096) ? (ntiles + want_chunks - 1)/want_chunks : ntiles;
 	uint32_t const cap = twi_erode_chunk_for(budget, chunk, (int)zvsize, (int)zvsize);
 	chunk = cap;
 	uint32_t const nchunks = (ntiles + chunk - 1)/chunk;

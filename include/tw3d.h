@@ -167,8 +167,9 @@ TW_API int tw_erode(tw_ctx *ctx, float *heightmap, int xsize, int ysize, float m
 TW_API int tw_erode_tiles(tw_ctx *ctx, float *heightmaps, uint32_t ntiles, int xsize, int ysize, const float *min_zvals, float min_zval_all,
                    uint32_t num_iters, const tw_erosion_params *p);
 /* Fused tile pipeline = the height fill AND the per-tile erosion of tile_t::create_zvals (src/tiled_mesh.cpp:467-515) for a batch of tiles:
- * exactly tw_heightgen_tiles followed by tw_erode_tiles(min_zval_all = min_zval), but issued in chunks on separate CUDA streams so that the
- * latency-bound droplet walk of one chunk overlaps the ALU-bound height generation of the next. mm (optional, HOST, ntiles entries) receives
+ * exactly tw_heightgen_tiles followed by tw_erode_tiles(min_zval_all = min_zval) in one call (one upload of the origins, one download of
+ * the result, per-tile z range fused). When memory forces several chunks, generation of chunk k+1 is issued on a separate stream and
+ * overlaps the droplet walk of chunk k. mm (optional, HOST, ntiles entries) receives
  * the per-tile z range AFTER erosion (mzmin/mzmax). erosion_iters == 0 or erode_amount <= 0 => height fill only. */
 TW_API int tw_create_zvals_batch(tw_ctx *ctx, const int32_t *origins_xy, uint32_t ntiles, int mesh_x_size, int mesh_y_size, float dx, float dy,
                           uint32_t zvsize, const tw_height_params *p, uint32_t erosion_iters, const tw_erosion_params *ep, float min_zval,
