@@ -42,6 +42,15 @@ bool tw_is_device_ptr(const void *p) {
 	return (a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged);
 }
 
+int twi_ensure_aux_streams(tw_ctx *ctx) {
+	if (ctx->aux_stream[0]) return TW_OK;
+	int lo = 0, hi = 0; // the latency-bound droplet kernels / band copies get the higher priority
+	TW_CUDA(ctx, cudaDeviceGetStreamPriorityRange(&lo, &hi));
+	bool const prio = !(getenv("TW_PIPE_NOPRIO"));
+	for (int i = 0; i < 2; ++i) {TW_CUDA(ctx, cudaStreamCreateWithPriority(&ctx->aux_stream[i], cudaStreamNonBlocking, prio ? hi : lo));}
+	return TW_OK;
+}
+
 namespace {
 
 // slot-2 layout (small device scalars)
@@ -167,9 +176,9 @@ int tw_heightgen_2d_launch(tw_ctx *ctx, const tw_grid2d *g, const tw_height_para
 	rc = tw_reserve(ctx, 2, OFF_TILES); if (rc) return rc;
 	unsigned *d_mm = mm ? (unsigned *)((char *)ctx->d_scratch[2] + OFF_MM) : nullptr;
 	if (d_mm) {rc = twi_init_minmax(ctx, d_mm, 1); if (rc) return rc;}
-	rc = twi_heightgen(ctx, g, p, enable_glaciate, min_start_sin, nullptr, 1, d_out, d_mm);
+	if (!dev_out) {rc = twi_ensure_aux_streams(ctx); if (rc) return rc;}
+	rc = twi_heightgen(ctx, g, p, enable_glaciate, min_start_sin, nullptr, 1, d_out, d_mm, dev_out ? nullptr : out); // host out: band-wise D2H overlapped with compute
 	if (rc) return rc;
-	if (!dev_out) {TW_CUDA(ctx, cudaMemcpyAsync(out, d_out, n*sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));}
 	if (mm) {
 		rc = tw_reserve_pinned(ctx, 2*sizeof(unsigned)); if (rc) return rc;
 		TW_CUDA(ctx, cudaMemcpyAsync(ctx->h_pinned, d_mm, 2*sizeof(unsigned), cudaMemcpyDeviceToHost, ctx->stream));
@@ -305,12 +314,7 @@ int tw_create_zvals_batch(tw_ctx *ctx, const int32_t *origins_xy, uint32_t ntile
 		if (!dev_out) {TW_CUDA(ctx, cudaMemcpy(out, d_out, n*sizeof(float), cudaMemcpyDeviceToHost));}
 		return TW_OK;
 	}
-	if (!ctx->aux_stream[0]) { // the latency-bound droplet kernels get the higher priority so that they take SM slots as soon as the
-		int lo = 0, hi = 0;    // ALU-bound generation blocks of the next chunk retire, instead of queueing behind them
-		TW_CUDA(ctx, cudaDeviceGetStreamPriorityRange(&lo, &hi));
-		bool const prio = !(getenv("TW_PIPE_NOPRIO"));
-		for (int i = 0; i < 2; ++i) {TW_CUDA(ctx, cudaStreamCreateWithPriority(&ctx->aux_stream[i], cudaStreamNonBlocking, prio ? hi : lo));}
-	}
+	rc = twi_ensure_aux_streams(ctx); if (rc) return rc;
 	float *d_out = out;
 	if (!dev_out) {rc = tw_reserve(ctx, 0, n*sizeof(float)); if (rc) return rc; d_out = (float *)ctx->d_scratch[0];}
 	// chunking: measured on B200 (tools/bench_pipeline.py) every extra chunk adds its own droplet tail (the heaviest tile of a chunk is a

@@ -121,10 +121,10 @@ __device__ __forceinline__ float gen_noise(float xv, float yv, const NoiseParams
 
 template<bool SIMPLEX, bool WARP, int SHAPE>
 __global__ void __launch_bounds__(256)
-noise_grid_kernel(float *__restrict__ out, unsigned nx, unsigned ny, float mx0_single, float my0_single, const float2 *__restrict__ tile_origins,
+noise_grid_kernel(float *__restrict__ out, unsigned nx, unsigned ny, unsigned y_off, float mx0_single, float my0_single, const float2 *__restrict__ tile_origins,
 	NoiseParams N, PostParams P, const float *__restrict__ sin_tab, unsigned *__restrict__ mm)
 {
-	unsigned const x = blockIdx.x*blockDim.x + threadIdx.x, y = blockIdx.y*blockDim.y + threadIdx.y, tile = blockIdx.z;
+	unsigned const x = blockIdx.x*blockDim.x + threadIdx.x, y = y_off + blockIdx.y*blockDim.y + threadIdx.y, tile = blockIdx.z; // y_off: first row of this band
 	float mx0 = mx0_single, my0 = my0_single;
 	if (tile_origins) {float2 const o = __ldg(tile_origins + tile); mx0 = o.x; my0 = o.y;}
 	float z = 0.0f;
@@ -202,10 +202,10 @@ constexpr int SK = 45;          // k-chunk staged in shared memory (2 chunks cov
 
 __global__ void __launch_bounds__(256)
 sine_grid_kernel(float *__restrict__ out, unsigned nx, unsigned ny, const float *__restrict__ Xt, const float *__restrict__ Yt,
-	unsigned xpitch, unsigned ypitch, int start_ix, PostParams P, float mx0, float my0, const float *__restrict__ sin_tab, unsigned *__restrict__ mm)
+	unsigned xpitch, unsigned ypitch, int start_ix, PostParams P, float mx0, float my0, const float *__restrict__ sin_tab, unsigned *__restrict__ mm, unsigned y_off)
 {
 	__shared__ float Xs[SK][ST], Ys[SK][ST];
-	unsigned const x_base = blockIdx.x*ST, y_base = blockIdx.y*ST;
+	unsigned const x_base = blockIdx.x*ST, y_base = y_off + blockIdx.y*ST;
 	int const tid = threadIdx.x, tx = tid & 15, ty = tid >> 4; // 16 x 16 threads
 	float acc[4][4];
 #pragma unroll
@@ -285,13 +285,13 @@ __global__ void minmax_tiles_kernel(const float *__restrict__ v, size_t tile_ele
 }
 
 template<bool SIMPLEX, bool WARP>
-void launch_noise(int shape, dim3 grid, dim3 block, cudaStream_t st, float *out, unsigned nx, unsigned ny, float mx0, float my0,
+void launch_noise(int shape, dim3 grid, dim3 block, cudaStream_t st, float *out, unsigned nx, unsigned ny, unsigned y_off, float mx0, float my0,
 	const float2 *origins, const NoiseParams &N, const PostParams &P, const float *tab, unsigned *mm)
 {
 	switch (shape) {
-	case 1:  noise_grid_kernel<SIMPLEX, WARP, 1><<<grid, block, 0, st>>>(out, nx, ny, mx0, my0, origins, N, P, tab, mm); break;
-	case 2:  noise_grid_kernel<SIMPLEX, WARP, 2><<<grid, block, 0, st>>>(out, nx, ny, mx0, my0, origins, N, P, tab, mm); break;
-	default: noise_grid_kernel<SIMPLEX, WARP, 0><<<grid, block, 0, st>>>(out, nx, ny, mx0, my0, origins, N, P, tab, mm); break;
+	case 1:  noise_grid_kernel<SIMPLEX, WARP, 1><<<grid, block, 0, st>>>(out, nx, ny, y_off, mx0, my0, origins, N, P, tab, mm); break;
+	case 2:  noise_grid_kernel<SIMPLEX, WARP, 2><<<grid, block, 0, st>>>(out, nx, ny, y_off, mx0, my0, origins, N, P, tab, mm); break;
+	default: noise_grid_kernel<SIMPLEX, WARP, 0><<<grid, block, 0, st>>>(out, nx, ny, y_off, mx0, my0, origins, N, P, tab, mm); break;
 	}
 }
 
@@ -317,8 +317,37 @@ int twi_minmax(tw_ctx *ctx, const float *d_vals, size_t n, unsigned *d_mm_ord) {
 }
 
 // Height generation for one grid (ntiles==0/1, d_tile_origins==nullptr) or a batch of equally sized tiles (noise modes only).
+// rows per band: whole grid unless the result goes to a host buffer and is large enough to be worth overlapping (>= 32 MB); bands are
+// multiples of 64 rows (the sine kernel's tile) and there are at most 16 of them
+static unsigned band_rows_for(tw_ctx *ctx, unsigned ny, unsigned nx, bool to_host) {
+	if (!to_host || (size_t)nx*ny*sizeof(float) < ((size_t)32 << 20) || !ctx->aux_stream[0]) return ny;
+	unsigned rows = ((ny + 15)/16 + 63) & ~63u;
+	return rows < 64 ? 64 : rows;
+}
+static int band_join(tw_ctx *ctx) { // ctx->stream waits for the band copies
+	cudaEvent_t ev;
+	TW_CUDA(ctx, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+	TW_CUDA(ctx, cudaEventRecord(ev, ctx->aux_stream[0]));
+	TW_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ev, 0));
+	TW_CUDA(ctx, cudaEventDestroy(ev));
+	return TW_OK;
+}
+
+// After the kernel of a row band has been issued on ctx->stream: copy that band to the host buffer on the copy stream (overlaps the next band)
+static int band_copy(tw_ctx *ctx, float *h_out, const float *d_out, unsigned nx, unsigned r0, unsigned r1) {
+	cudaEvent_t ev;
+	TW_CUDA(ctx, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+	TW_CUDA(ctx, cudaEventRecord(ev, ctx->stream));
+	TW_CUDA(ctx, cudaStreamWaitEvent(ctx->aux_stream[0], ev, 0));
+	TW_CUDA(ctx, cudaEventDestroy(ev));
+	TW_CUDA(ctx, cudaMemcpyAsync(h_out + (size_t)r0*nx, d_out + (size_t)r0*nx, (size_t)(r1 - r0)*nx*sizeof(float), cudaMemcpyDeviceToHost, ctx->aux_stream[0]));
+	return TW_OK;
+}
+
+// h_out_bands != nullptr (single grid only): the grid is issued in row bands and each finished band is copied to the host buffer on a second
+// stream while the next band computes; ctx->stream finally waits for the copies, so an event recorded on it covers the whole result.
 int twi_heightgen(tw_ctx *ctx, const tw_grid2d *g, const tw_height_params *p, int enable_glaciate, int min_start_sin,
-                  const float2 *d_tile_origins, uint32_t ntiles, float *d_out, unsigned *d_mm_ord)
+                  const float2 *d_tile_origins, uint32_t ntiles, float *d_out, unsigned *d_mm_ord, float *h_out_bands)
 {
 	unsigned const nx = g->nx, ny = g->ny;
 	float const dx = g->dx, dy = g->dy;
@@ -360,13 +389,18 @@ int twi_heightgen(tw_ctx *ctx, const tw_grid2d *g, const tw_height_params *p, in
 		N.xy_scale = 0.0007f*p->mesh_scale; // MESH_SCALE_FACTOR, src/mesh_gen.cpp:23,737
 		bool const simplex = (p->gen_mode == TW_MGEN_SIMPLEX || p->gen_mode == TW_MGEN_SIMPLEX_GPU || p->gen_mode == TW_MGEN_DWARP_GPU);
 		N.hmap_scale = (simplex ? 16.0f : 32.0f)*p->mesh_height*p->mesh_height_scale*p->mesh_scale_z_inv; // get_hmap_scale, :550-553
-		dim3 const block(32, 8, 1), grid((nx + 31)/32, (ny + 7)/8, ntiles);
 		bool const warp = (p->gen_mode == TW_MGEN_DWARP_GPU);
-		if (p->gen_mode == TW_MGEN_PERLIN) {launch_noise<false, false>(p->gen_shape, grid, block, ctx->stream, d_out, nx, ny, mx0, my0, d_tile_origins, N, P, ctx->d_sin_table, d_mm_ord);}
-		else if (warp) {launch_noise<true, true >(p->gen_shape, grid, block, ctx->stream, d_out, nx, ny, mx0, my0, d_tile_origins, N, P, ctx->d_sin_table, d_mm_ord);}
-		else           {launch_noise<true, false>(p->gen_shape, grid, block, ctx->stream, d_out, nx, ny, mx0, my0, d_tile_origins, N, P, ctx->d_sin_table, d_mm_ord);}
-		TW_LAUNCH_CHECK(ctx);
-		return TW_OK;
+		unsigned const band_rows = band_rows_for(ctx, ny, nx, h_out_bands != nullptr && ntiles == 1);
+		for (unsigned r0 = 0; r0 < ny; r0 += band_rows) {
+			unsigned const r1 = (ny - r0 < band_rows) ? ny : r0 + band_rows;
+			dim3 const block(32, 8, 1), grid((nx + 31)/32, (r1 - r0 + 7)/8, ntiles);
+			if (p->gen_mode == TW_MGEN_PERLIN) {launch_noise<false, false>(p->gen_shape, grid, block, ctx->stream, d_out, nx, ny, r0, mx0, my0, d_tile_origins, N, P, ctx->d_sin_table, d_mm_ord);}
+			else if (warp) {launch_noise<true, true >(p->gen_shape, grid, block, ctx->stream, d_out, nx, ny, r0, mx0, my0, d_tile_origins, N, P, ctx->d_sin_table, d_mm_ord);}
+			else           {launch_noise<true, false>(p->gen_shape, grid, block, ctx->stream, d_out, nx, ny, r0, mx0, my0, d_tile_origins, N, P, ctx->d_sin_table, d_mm_ord);}
+			TW_LAUNCH_CHECK(ctx);
+			if (h_out_bands) {int const rc = band_copy(ctx, h_out_bands, d_out, nx, r0, r1); if (rc) return rc;}
+		}
+		return h_out_bands ? band_join(ctx) : TW_OK;
 	}
 
 	// ---- sine-table mode ----
@@ -392,10 +426,13 @@ int twi_heightgen(tw_ctx *ctx, const tw_grid2d *g, const tw_height_params *p, in
 		TW_LAUNCH_CHECK(ctx);
 	}
 	int const start_ix = (p->start_eval_sin > min_start_sin) ? p->start_eval_sin : min_start_sin; // src/mesh_gen.cpp:769
-	{
-		dim3 const grid((nx + ST - 1)/ST, (ny + ST - 1)/ST, 1);
-		sine_grid_kernel<<<grid, 256, 0, ctx->stream>>>(d_out, nx, ny, Xt, Yt, xpitch, ypitch, start_ix, P, mx0, my0, ctx->d_sin_table, d_mm_ord);
+	unsigned const band_rows = band_rows_for(ctx, ny, nx, h_out_bands != nullptr);
+	for (unsigned r0 = 0; r0 < ny; r0 += band_rows) {
+		unsigned const r1 = (ny - r0 < band_rows) ? ny : r0 + band_rows;
+		dim3 const grid((nx + ST - 1)/ST, (r1 - r0 + ST - 1)/ST, 1);
+		sine_grid_kernel<<<grid, 256, 0, ctx->stream>>>(d_out, nx, ny, Xt, Yt, xpitch, ypitch, start_ix, P, mx0, my0, ctx->d_sin_table, d_mm_ord, r0);
 		TW_LAUNCH_CHECK(ctx);
+		if (h_out_bands) {int const rc = band_copy(ctx, h_out_bands, d_out, nx, r0, r1); if (rc) return rc;}
 	}
-	return TW_OK;
+	return h_out_bands ? band_join(ctx) : TW_OK;
 }
