@@ -5,6 +5,7 @@
 #include <stdlib.h>
 #include <new>
 #include <vector>
+#include <math.h>
 
 extern "C" void twi_build_dir_table(float *cs2x1e6);
 
@@ -256,6 +257,67 @@ int tw_heightgen_tiles(tw_ctx *ctx, const int32_t *origins_xy, uint32_t ntiles, 
 	}
 	if (!dev_out) {TW_CUDA(ctx, cudaMemcpyAsync(out, d_out, n*sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));}
 	if (mm) {rc = read_minmax(ctx, d_mm, mm, ntiles); if (rc) return rc;}
+	TW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	return TW_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ callers' tails
+int tw_tile_bounds_batch(tw_ctx *ctx, const float *zvals, uint32_t ntiles, uint32_t zvsize, float wpz_max, float dx_val, float dy_val, uint32_t size, tw_tile_bounds *out) {
+	int rc = check_ctx(ctx); if (rc) return rc;
+	rc = finish_pending(ctx); if (rc) return rc;
+	if (!zvals || !out || ntiles == 0 || zvsize < 4) return tw_set_error(ctx, TW_ERR_ARG, "null/empty argument");
+	if (ntiles > 65535) return tw_set_error(ctx, TW_ERR_ARG, "at most 65535 tiles per call");
+	size_t const n = (size_t)ntiles*zvsize*zvsize;
+	struct Sub {float zmin, zmax; int wx1, wy1, wx2, wy2;};
+	size_t const sub_bytes = (size_t)ntiles*16*sizeof(Sub);
+	const float *d_z = zvals;
+	bool const dev = tw_is_device_ptr(zvals);
+	rc = tw_reserve(ctx, 0, (dev ? 0 : n*sizeof(float)) + sub_bytes + 256); if (rc) return rc;
+	char *s0 = (char *)ctx->d_scratch[0];
+	if (!dev) {TW_CUDA(ctx, cudaMemcpyAsync(s0, zvals, n*sizeof(float), cudaMemcpyHostToDevice, ctx->stream)); d_z = (const float *)s0; s0 += (n*sizeof(float) + 255) & ~(size_t)255;}
+	rc = twi_tile_bounds(ctx, d_z, ntiles, zvsize, wpz_max, s0); if (rc) return rc;
+	std::vector<Sub> sub((size_t)ntiles*16);
+	TW_CUDA(ctx, cudaMemcpyAsync(sub.data(), s0, sub_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+	TW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	for (uint32_t t = 0; t < ntiles; ++t) { // combine the 16 sub-blocks exactly as the reference's loop does (src/tiled_mesh.cpp:517-540)
+		tw_tile_bounds &b = out[t];
+		b.mzmin = 100.0f; b.mzmax = -100.0f; b.mesh_dz = 0.0f; // FAR_DISTANCE
+		b.wx1 = b.wy1 = 2147483647; b.wx2 = b.wy2 = -1;
+		for (int k = 0; k < 16; ++k) {
+			Sub const &q = sub[(size_t)t*16 + k];
+			b.sub_zmin[k] = q.zmin; b.sub_zmax[k] = q.zmax;
+			float const range = q.zmax - q.zmin;
+			b.mesh_dz = (b.mesh_dz < range) ? range : b.mesh_dz;      // max_eq(mesh_dz, (szmax - szmin))
+			b.mzmin = (q.zmin < b.mzmin) ? q.zmin : b.mzmin;          // min(mzmin, szmin)
+			b.mzmax = (b.mzmax < q.zmax) ? q.zmax : b.mzmax;          // max(mzmax, szmax)
+			if (q.wx1 < b.wx1) b.wx1 = q.wx1; if (q.wy1 < b.wy1) b.wy1 = q.wy1;
+			if (q.wx2 > b.wx2) b.wx2 = q.wx2; if (q.wy2 > b.wy2) b.wy2 = q.wy2;
+		}
+		float const dz = b.mzmax - b.mzmin;
+		b.radius = 0.5*sqrtf((dx_val*dx_val + dy_val*dy_val)*size*size + dz*dz); // src/tiled_mesh.cpp:541
+	}
+	return TW_OK;
+}
+
+int tw_glaciate_mesh(tw_ctx *ctx, float *mesh, int nx, int ny, int xoff2, int yoff2, int mesh_x_size, int mesh_y_size, const tw_height_params *p, tw_minmax *zbottom_ztop) {
+	int rc = check_ctx(ctx); if (rc) return rc;
+	rc = finish_pending(ctx); if (rc) return rc;
+	if (!mesh || !p || nx <= 0 || ny <= 0 || ny > 65535) return tw_set_error(ctx, TW_ERR_ARG, "bad argument");
+	if (!ctx->have_sin) return tw_set_error(ctx, TW_ERR_STATE, "tw_set_sin_table() has not been called");
+	size_t const n = (size_t)nx*ny;
+	bool const dev = tw_is_device_ptr(mesh);
+	float *d_mesh = mesh;
+	if (!dev) {
+		rc = tw_reserve(ctx, 0, n*sizeof(float)); if (rc) return rc;
+		d_mesh = (float *)ctx->d_scratch[0];
+		TW_CUDA(ctx, cudaMemcpyAsync(d_mesh, mesh, n*sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+	}
+	rc = tw_reserve(ctx, 2, OFF_TILES); if (rc) return rc;
+	unsigned *d_mm = (unsigned *)((char *)ctx->d_scratch[2] + OFF_MM);
+	rc = twi_init_minmax(ctx, d_mm, 1); if (rc) return rc;
+	rc = twi_glaciate_mesh(ctx, d_mesh, nx, ny, xoff2, yoff2, mesh_x_size, mesh_y_size, p, d_mm); if (rc) return rc;
+	if (!dev) {TW_CUDA(ctx, cudaMemcpyAsync(mesh, d_mesh, n*sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));}
+	if (zbottom_ztop) {return read_minmax(ctx, d_mm, zbottom_ztop, 1);}
 	TW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
 	return TW_OK;
 }

@@ -89,6 +89,8 @@ size_t   twi_erode_scratch_bytes(uint32_t chunk, int xsize, int ysize);
 uint32_t twi_erode_chunk_for(size_t budget, uint32_t ntiles, int xsize, int ysize);
 int twi_erode_enqueue(tw_ctx *ctx, cudaStream_t st, void *scratch, uint32_t capacity, float *maps, uint32_t nt, int xsize, int ysize,
                       const float *d_min_zvals, float min_zval_all, uint32_t num_iters, const tw_erosion_params *p, unsigned long long *d_steps);
+int twi_tile_bounds(tw_ctx *ctx, const float *d_zvals, uint32_t ntiles, uint32_t zvsize, float wpz_max, void *d_sub);
+int twi_glaciate_mesh(tw_ctx *ctx, float *d_mesh, int nx, int ny, int xoff2, int yoff2, int MX, int MY, const tw_height_params *p, unsigned *d_mm);
 int twi_voxel_fill(tw_ctx *ctx, const tw_voxel_params *vp, const float *rdata420, float *d_out);
 int twi_from_floats_u16(tw_ctx *ctx, const float *d_vals, size_t n, float val_mult, float val_add, uint8_t *d_out, unsigned *d_bad);
 int twi_to_floats_u16(tw_ctx *ctx, const uint8_t *d_data, size_t n, float val_mult, float val_add, float *d_vals);

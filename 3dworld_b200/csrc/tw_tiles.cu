@@ -1,0 +1,112 @@
+// tw_tiles.cu - the pieces of the reference's callers that sit right next to the generators (sm_100a):
+//   tile_bounds_kernel     tail of tile_t::create_zvals (src/tiled_mesh.cpp:517-540): 4x4 sub-block min/max (inclusive ends), water bbox
+//   glaciate_mesh_kernel   glaciate() of the ground-mode mesh (src/mesh_gen.cpp:388-404): apply_glaciate + apply_mesh_sine per cell + zbottom/ztop
+// Both are single streaming passes over data that is already resident (4 B/cell read, glaciate also 4 B/cell written): HBM/L2-bound.
+#include "tw_internal.h"
+
+namespace {
+
+__device__ __forceinline__ float cosf_lut(const float *__restrict__ tab, float v) { // COSF, src/sinf.h:15
+	return __ldg(tab + TW_TSIZE + (tw_x86_f2i(TW_SSCALE*fabsf(v))&(TW_TSIZE-1)));
+}
+__device__ __forceinline__ float smin(float a, float b) {return (b < a) ? b : a;}
+__device__ __forceinline__ float smax(float a, float b) {return (a < b) ? b : a;}
+
+struct SubBounds {float zmin, zmax; int wx1, wy1, wx2, wy2;};
+
+// grid (16 sub-blocks, ntiles), 256 threads: min/max and under-water bbox of the (block_size+1)^2 cells of one sub-block
+__global__ void __launch_bounds__(256)
+tile_bounds_kernel(const float *__restrict__ zvals, unsigned zvsize, float wpz_max, SubBounds *__restrict__ out) {
+	unsigned const sb = blockIdx.x, tile = blockIdx.y, xx = sb & 3, yy = sb >> 2, bs = zvsize/4, w = bs + 1;
+	const float *z = zvals + (size_t)tile*zvsize*zvsize;
+	float vmin = 100.0f, vmax = -100.0f; // FAR_DISTANCE, src/3DWorld.h:116
+	int wx1 = 2147483647, wy1 = 2147483647, wx2 = -1, wy2 = -1;
+	for (unsigned i = threadIdx.x; i < w*w; i += blockDim.x) {
+		unsigned const x = xx*bs + i % w, y = yy*bs + i / w;
+		float const v = __ldg(z + (size_t)y*zvsize + x);
+		vmin = smin(vmin, v); vmax = smax(vmax, v);
+		if (v < wpz_max) {wx1 = min(wx1, (int)x); wy1 = min(wy1, (int)y); wx2 = max(wx2, (int)x); wy2 = max(wy2, (int)y);}
+	}
+	for (int o = 16; o > 0; o >>= 1) {
+		vmin = fminf(vmin, __shfl_xor_sync(0xffffffffu, vmin, o)); vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
+		wx1 = min(wx1, __shfl_xor_sync(0xffffffffu, wx1, o)); wy1 = min(wy1, __shfl_xor_sync(0xffffffffu, wy1, o));
+		wx2 = max(wx2, __shfl_xor_sync(0xffffffffu, wx2, o)); wy2 = max(wy2, __shfl_xor_sync(0xffffffffu, wy2, o));
+	}
+	__shared__ SubBounds s[8];
+	int const warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	if (lane == 0) {s[warp] = SubBounds{vmin, vmax, wx1, wy1, wx2, wy2};}
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		SubBounds r = s[0];
+		for (int i = 1; i < 8; ++i) {
+			r.zmin = fminf(r.zmin, s[i].zmin); r.zmax = fmaxf(r.zmax, s[i].zmax);
+			r.wx1 = min(r.wx1, s[i].wx1); r.wy1 = min(r.wy1, s[i].wy1); r.wx2 = max(r.wx2, s[i].wx2); r.wy2 = max(r.wy2, s[i].wy2);
+		}
+		out[(size_t)tile*16 + sb] = r;
+	}
+}
+
+struct GlacParams {
+	int   glaciate; float zmax_est, zmax_est2, zmax_est2_inv, custom_exp;
+	int   sine_on; float sine_mag, sine_bias, freq, mszi;
+	int   volcano_on; float volcano_freq, volcano_height;
+	int   nx, ny, x_shift, y_shift; // x_shift = xoff2 - MESH_X_SIZE/2
+};
+
+__device__ __forceinline__ float volcano_height(float xi, float yi, const GlacParams &P, const float *__restrict__ tab) { // src/mesh_gen.cpp:364-372
+	float const x = P.volcano_freq*xi, y = P.volcano_freq*yi, dist = __fsqrt_rn(x*x + y*y);
+	if ((double)dist > 2.0) return 0.0f;
+	float const val = cosf_lut(tab, x)*cosf_lut(tab, y);
+	double const hd = 400.0*((double)val - 0.999);
+	float const hole = (float)((0.0 < hd) ? hd : 0.0);
+	float const peak = (float)(0.08*(double)val/(double)smax(0.04f, dist));
+	return P.volcano_height*smax(0.0f, (peak - hole))*P.mszi;
+}
+
+__global__ void __launch_bounds__(256)
+glaciate_mesh_kernel(float *__restrict__ mesh, GlacParams P, const float *__restrict__ tab, unsigned *__restrict__ mm) {
+	int const j = blockIdx.x*blockDim.x + threadIdx.x, i = blockIdx.y;
+	float vmin = INFINITY, vmax = -INFINITY;
+	if (j < P.nx) {
+		float z = mesh[(size_t)i*P.nx + j];
+		if (P.glaciate) { // apply_glaciate, src/mesh_gen.cpp:380-385
+			float const relh = (z + P.zmax_est)*P.zmax_est2_inv;
+			float const g = (P.custom_exp == 0.0f) ? relh*relh*relh : powf(relh, P.custom_exp);
+			z = g*P.zmax_est2 - P.zmax_est;
+		}
+		if (P.sine_on) { // apply_mesh_sine(zval, float(j + xoff2 - MESH_X_SIZE/2), float(i + yoff2 - MESH_Y_SIZE/2)), src/mesh_gen.cpp:373-379,398
+			float const x = (float)(j + P.x_shift), y = (float)(i + P.y_shift);
+			z += (P.sine_mag*cosf_lut(tab, x*P.freq)*cosf_lut(tab, y*P.freq) + P.sine_bias)*P.mszi;
+			if (P.volcano_on) {z += volcano_height(x, y, P, tab);}
+		}
+		mesh[(size_t)i*P.nx + j] = z;
+		vmin = vmax = z;
+	}
+	for (int o = 16; o > 0; o >>= 1) {
+		vmin = fminf(vmin, __shfl_xor_sync(0xffffffffu, vmin, o)); vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
+	}
+	if (mm && (threadIdx.x & 31) == 0 && vmin <= vmax) {atomicMin(mm, tw_f2ord(vmin)); atomicMax(mm + 1, tw_f2ord(vmax));}
+}
+
+} // namespace
+
+int twi_tile_bounds(tw_ctx *ctx, const float *d_zvals, uint32_t ntiles, uint32_t zvsize, float wpz_max, void *d_sub /* ntiles*16*24 bytes */) {
+	tile_bounds_kernel<<<dim3(16, ntiles), 256, 0, ctx->stream>>>(d_zvals, zvsize, wpz_max, (SubBounds *)d_sub);
+	TW_LAUNCH_CHECK(ctx);
+	return TW_OK;
+}
+
+int twi_glaciate_mesh(tw_ctx *ctx, float *d_mesh, int nx, int ny, int xoff2, int yoff2, int MX, int MY, const tw_height_params *p, unsigned *d_mm) {
+	GlacParams P;
+	memset(&P, 0, sizeof(P));
+	P.glaciate = (p->glaciate != 0);
+	P.zmax_est = p->zmax_est; P.zmax_est2 = (float)(2.0*p->zmax_est); P.zmax_est2_inv = (float)(1.0/P.zmax_est2); P.custom_exp = p->custom_glaciate_exp;
+	P.sine_on = (p->hmap.sine_mag > 0.0f); P.sine_mag = p->hmap.sine_mag; P.sine_bias = p->hmap.sine_bias;
+	P.freq = p->mesh_scale*p->hmap.sine_freq; P.mszi = p->mesh_scale_z_inv;
+	P.volcano_on = (p->hmap.volcano_width > 0.0f && p->hmap.volcano_height > 0.0f);
+	P.volcano_freq = P.volcano_on ? p->mesh_scale/p->hmap.volcano_width : 0.0f; P.volcano_height = p->hmap.volcano_height;
+	P.nx = nx; P.ny = ny; P.x_shift = xoff2 - MX/2; P.y_shift = yoff2 - MY/2;
+	glaciate_mesh_kernel<<<dim3((nx + 255)/256, ny), 256, 0, ctx->stream>>>(d_mesh, P, ctx->d_sin_table, d_mm);
+	TW_LAUNCH_CHECK(ctx);
+	return TW_OK;
+}

@@ -141,3 +141,39 @@ def voxel_landscape_params(cfg, nx, ny, nz, zbottom=None, czmin=None, mag=1.0, f
     vp.zscale = float(f32((-1.0 if invert else 1.0) * z_gradient / (nz - 1)))
     vp.atten_mode, vp.atten_val, vp.atten_inner_radius = 0, 0.0, 0.0
     return vp
+
+
+def gen_mesh(ctx, cfg, erosion_iters=0, xoff2=0, yoff2=0, sine_rng=None):
+    """gen_mesh(surface_type=0, keep_sin_table=0, update_zvals=1) in ground mode (src/mesh_gen.cpp:257-355): sine-table entries ->
+    gen_mesh_sine_table (:201-210) -> calc_zminmax -> estimate_zminmax (:447-485, a 128x128 probe of the equation) -> set_zvals (:494-504) ->
+    glaciate() (:388-404) -> apply_erosion(mesh, X, Y, zbottom, erosion_iters) (:443). All grids are evaluated on the GPU through `ctx`.
+    Returns (mesh[MY, MX], dict(zmin, zmax, zmax_est, zbottom, ztop, water_plane_z), sine_params). cfg.zmax_est is updated."""
+    MX, MY = cfg.mesh_size[0], cfg.mesh_size[1]
+    sp = cfg.sine_params(rng=sine_rng)
+    ctx.set_sine_params(sp)
+    hp = cfg.height_params()
+    dx, dy = float(cfg.dx_val), float(cfg.dy_val)
+    mesh, (zmin, zmax) = ctx.heightgen_2d(Grid2D(float(xoff2 - MX // 2), float(yoff2 - MY // 2), dx, dy, MX, MY), hp, enable_glaciate=0, want_minmax=True)
+    zmin, zmax = f32(zmin), f32(zmax)
+    zmax_est = max(zmax, -zmin)
+    if zmax == zmin:
+        zmax_est = f32(float(zmax_est) + 1.0E-6)
+    else:
+        xy_scene = f32(0.5) * (f32(cfg.scene_size[0]) + f32(cfg.scene_size[1]))
+        rm_scale = float(f32(1000.0 * float(xy_scene) / float(f32(cfg.mesh_scale))))
+        probe = ctx.heightgen_2d(Grid2D(0.0, 0.0, rm_scale, rm_scale, 128, 128), hp, enable_glaciate=0)
+        zmax_est = max(zmax_est, f32(np.abs(probe).max()))
+        if cfg.mesh_gen_mode != MGEN_SINE:
+            zmax_est = f32(float(zmax_est) * 1.2)
+        zmax_est = f32(1.1 * float(zmax_est))
+    zbottom, ztop = zmin, zmax                      # set_zvals
+    zmin, zmax = -zmax_est, zmax_est
+    cfg.zmax_est = float(zmax_est)
+    hp = cfg.height_params()
+    wpz = cfg.water_plane_z()
+    if cfg.glaciate:
+        zbottom, ztop = ctx.glaciate_mesh(mesh, xoff2, yoff2, (MX, MY), hp)
+    ep = cfg.erosion_params(zmin=float(zmin), zmax=float(zmax))
+    if erosion_iters > 0:
+        ctx.erode(mesh, float(zbottom), erosion_iters, ep)
+    return mesh, dict(zmin=float(zmin), zmax=float(zmax), zmax_est=float(zmax_est), zbottom=float(zbottom), ztop=float(ztop), water_plane_z=float(wpz)), sp

@@ -85,6 +85,15 @@ typedef struct tw_erosion_params {
 	float erode_amount, water_plane_z, half_dxy, zmin, zmax, relh_adj_tex, clip_hd1;
 } tw_erosion_params;
 
+/* what tile_t::create_zvals derives from the finished zvals (src/tiled_mesh.cpp:517-540): sub_zmin/sub_zmax[yy][xx] of the 4x4 sub-blocks
+ * (block_size = zvsize/4, inclusive ends), mzmin/mzmax, mesh_dz = max sub-block range, bounding radius, and the bbox (tile-local cell
+ * indices) of the cells below wpz_max; wx1 > wx2 when no cell is under water. */
+typedef struct tw_tile_bounds {
+	float sub_zmin[16], sub_zmax[16];
+	float mzmin, mzmax, mesh_dz, radius;
+	int32_t wx1, wy1, wx2, wy2;
+} tw_tile_bounds;
+
 /* voxel_grid geometry (src/voxels.cpp:91-108) + create_procedural() arguments (src/voxels.cpp:278) */
 typedef struct tw_voxel_params {
 	uint32_t nx, ny, nz;
@@ -154,6 +163,14 @@ TW_API int tw_heightgen_2d_poll(tw_ctx *ctx, int wait);
  * out[t*zvsize*zvsize + y*zvsize + x]. origins is a HOST array of ntiles (x1,y1) pairs. mm (optional, host) = ntiles entries. */
 TW_API int tw_heightgen_tiles(tw_ctx *ctx, const int32_t *origins_xy, uint32_t ntiles, int mesh_x_size, int mesh_y_size, float dx, float dy,
                        uint32_t zvsize, const tw_height_params *p, float *out, tw_minmax *mm);
+
+/* Tail of tile_t::create_zvals (src/tiled_mesh.cpp:517-540) for ntiles finished tiles: zvals host or device, out = HOST array of ntiles. */
+TW_API int tw_tile_bounds_batch(tw_ctx *ctx, const float *zvals, uint32_t ntiles, uint32_t zvsize, float wpz_max, float dx_val, float dy_val,
+                         uint32_t size, tw_tile_bounds *out);
+/* glaciate() of the ground-mode mesh (src/mesh_gen.cpp:388-404): apply_glaciate + apply_mesh_sine(x = j + xoff2 - MESH_X_SIZE/2, ...) per
+ * cell, in place (mesh host or device, row-major nx*ny); zbottom_ztop (optional, host) receives min/max of the result. */
+TW_API int tw_glaciate_mesh(tw_ctx *ctx, float *mesh, int nx, int ny, int xoff2, int yoff2, int mesh_x_size, int mesh_y_size,
+                     const tw_height_params *p, tw_minmax *zbottom_ztop);
 
 /* ---- hydraulic erosion ----
  * Replaces apply_erosion(float *heightmap, int xsize, int ysize, float min_zval, unsigned num_iters) (src/function_registry.h:354,

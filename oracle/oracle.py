@@ -43,6 +43,11 @@ class VoxelParams(C.Structure):
                 ("zscale", C.c_float), ("atten_mode", C.c_int), ("atten_val", C.c_float), ("atten_inner_radius", C.c_float)]
 
 
+class TileBounds(C.Structure):
+    _fields_ = [("sub_zmin", C.c_float * 16), ("sub_zmax", C.c_float * 16), ("mzmin", C.c_float), ("mzmax", C.c_float), ("mesh_dz", C.c_float),
+                ("radius", C.c_float), ("wx1", C.c_int32), ("wy1", C.c_int32), ("wx2", C.c_int32), ("wy2", C.c_int32)]
+
+
 class Rng(C.Structure):
     _fields_ = [("rseed1", C.c_int64), ("rseed2", C.c_int64)]
 
@@ -90,6 +95,10 @@ def lib():
         L.to_eval_mesh_sin_terms.argtypes = [C.c_float, C.c_float, vp, vp, C.c_int]
         L.to_eval_mesh_sin_terms.restype = C.c_float
         L.to_heightgen_2d.argtypes = [C.POINTER(Grid2D), C.POINTER(HeightParams), vp, vp, C.c_int, C.c_int, vp, C.c_int]
+        L.to_glaciate_mesh.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(HeightParams), vp, C.POINTER(C.c_float), C.POINTER(C.c_float)]
+        L.to_gen_mesh.argtypes = [C.POINTER(Rng), C.POINTER(HeightParams), C.c_int, C.c_int, C.c_float, C.c_float, C.c_int, C.c_int, C.c_int, C.c_int,
+                                  C.c_float, C.c_float, C.c_float, C.c_float, C.c_uint, C.POINTER(ErosionParams), vp, vp, vp, vp]
+        L.to_tile_bounds.argtypes = [vp, C.c_uint, C.c_uint, C.c_float, C.c_float, C.c_float, C.c_uint, vp]
         L.to_apply_erosion.argtypes = [vp, C.c_int, C.c_int, C.c_float, C.c_uint, C.POINTER(ErosionParams)]
         L.to_apply_erosion.restype = C.c_ulonglong
         L.to_noise3d_gen_sines.argtypes = [C.c_int, C.c_int, C.c_float, C.c_float, vp]
@@ -142,6 +151,27 @@ def heightgen_2d(grid, hp, sine_params=None, enable_glaciate=1, min_start_sin=0,
     out = np.empty((grid.ny, grid.nx), np.float32)
     sp = np.ascontiguousarray(sine_params if sine_params is not None else np.zeros((90, 5)), np.float32)
     lib().to_heightgen_2d(C.byref(grid), C.byref(hp), _p(sin_table()), _p(sp), int(enable_glaciate), int(min_start_sin), _p(out), nthreads)
+    return out
+
+
+def gen_mesh(hp, mesh=(128, 128), scene=(4.0, 4.0), seed=0, rgen_index=0, xoff2=0, yoff2=0, dx=0.0625, dy=0.0625, erosion_iters=0, ep=None, rng=None,
+             water_h_off=0.0, water_h_off_rel=0.0):
+    """to_gen_mesh: returns (mesh, zvals6 dict, sine_params); hp.zmax_est and ep.water_plane_z/zmin/zmax are outputs."""
+    rng = rng if rng is not None else Rng(1, 1)
+    ep = ep if ep is not None else ErosionParams(1.0, 0.0, 0.0625, -1.0, 1.0, 0.0, 0.5)
+    out = np.empty((mesh[1], mesh[0]), np.float32)
+    sp = np.empty((90, 5), np.float32)
+    z6 = np.empty(6, np.float32)
+    lib().to_gen_mesh(C.byref(rng), C.byref(hp), mesh[0], mesh[1], scene[0], scene[1], seed, rgen_index, xoff2, yoff2, dx, dy, water_h_off, water_h_off_rel,
+                      erosion_iters, C.byref(ep), _p(sin_table()), _p(sp), _p(out), _p(z6))
+    return out, dict(zip(("zmin", "zmax", "zmax_est", "zbottom", "ztop", "water_plane_z"), (float(v) for v in z6))), sp
+
+
+def tile_bounds(tiles, wpz_max, dx_val, dy_val, size):
+    tiles = np.ascontiguousarray(tiles, np.float32)
+    nt, zv = tiles.shape[0], tiles.shape[1]
+    out = (TileBounds * nt)()
+    lib().to_tile_bounds(_p(tiles), nt, zv, wpz_max, dx_val, dy_val, size, C.cast(out, C.c_void_p))
     return out
 
 

@@ -59,6 +59,7 @@ def lib():
         L.ref_noise3d_point.restype = C.c_float
         L.ref_voxel_fill.argtypes = [C.c_uint] * 3 + [C.c_void_p] * 3 + [C.c_float, C.c_float, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p]
         L.ref_get_rx_ry.argtypes = [fp, fp]
+        L.ref_gen_mesh.argtypes = [C.c_uint, C.POINTER(Erosion), C.c_void_p, C.c_void_p]
         _lib = L
     return _lib
 
@@ -132,3 +133,12 @@ def voxel_fill(nx, ny, nz, lo_pos, vsz, offset, mag, freq, normalize_to_1, rs1, 
     lib().ref_voxel_fill(nx, ny, nz, *[v.ctypes.data_as(C.c_void_p) for v in a], mag, freq, int(normalize_to_1), rs1, rs2, gen_mode, zscale,
                          out.ctypes.data_as(C.c_void_p))
     return out
+
+
+def gen_mesh(mesh_xy, erosion_iters=0, erode_amount=1.0, relh_adj_tex=0.0, clip_hd1=0.5):
+    """The reference's own gen_mesh(0,0,1) (call setup(..., gen_sine_table=False) first: gen_mesh regenerates the table itself)."""
+    out = np.empty((mesh_xy[1], mesh_xy[0]), np.float32)
+    z6 = np.empty(6, np.float32)
+    p = Erosion(erode_amount, 0.0, 0.0, 0.0, 0.0, relh_adj_tex, clip_hd1)
+    lib().ref_gen_mesh(erosion_iters, C.byref(p), out.ctypes.data_as(C.c_void_p), z6.ctypes.data_as(C.c_void_p))
+    return out, dict(zip(("zmin", "zmax", "zmax_est", "zbottom", "ztop", "water_plane_z"), (float(v) for v in z6)))

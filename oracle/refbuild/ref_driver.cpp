@@ -171,3 +171,20 @@ void ref_voxel_fill(unsigned nx, unsigned ny, unsigned nz, const float lo_pos[3]
 }
 
 } // extern "C"
+
+// ---- ground-mode driver: the reference's own gen_mesh() (src/mesh_gen.cpp:257-355) = sine table + estimate_zminmax + glaciate + apply_erosion ----
+void gen_mesh(int surface_type, int keep_sin_table, int update_zvals);
+extern float **mesh_height;
+extern "C" {
+void set_scene_constants_stub2();
+// call after ref_setup(.., gen_sine_table=0): gen_mesh() regenerates the sine table itself (keep_sin_table=0), exactly as gen_scene() does
+void ref_gen_mesh(unsigned erosion_iters_, const ref_erosion_t *p, float *out, float *zvals6) { // out: MESH_Y_SIZE*MESH_X_SIZE floats; zvals6: zmin, zmax, zmax_est, zbottom, ztop, water_plane_z
+	extern unsigned erosion_iters;
+	set_scene_constants_stub2();
+	erosion_iters = erosion_iters_;
+	erode_amount = p->erode_amount; relh_adj_tex_stub = p->relh_adj_tex; clip_hd1_stub = p->clip_hd1; // water_plane_z, zmin, zmax are set by gen_mesh itself (set_zvals)
+	gen_mesh(0, 0, 1);
+	memcpy(out, mesh_height[0], (size_t)MESH_X_SIZE*MESH_Y_SIZE*sizeof(float));
+	zvals6[0] = zmin; zvals6[1] = zmax; zvals6[2] = zmax_est; zvals6[3] = zbottom; zvals6[4] = ztop; zvals6[5] = water_plane_z;
+}
+}

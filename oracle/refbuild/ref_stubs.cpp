@@ -53,3 +53,34 @@ void compute_shader_t::end_shader() {}
 void compute_shader_t::setup_and_run(unsigned &, bool, bool, bool) {}
 void compute_shader_t::prep_for_read_pixels(bool) {}
 void compute_shader_t::read_float_vals(vector<float> &, bool, bool) {}
+
+// ---- additional engine globals referenced by gen_mesh() and its helpers (src/3DWorld.cpp:89-133, src/matrix_ops.cpp:20-45); ground mode,
+// no scrolling, no heightmap files, camera in the air (camera_mode 0 => update_temperature() returns early) ----
+#include "heightmap.h"
+float **mesh_height = nullptr;
+unsigned char **mesh_draw = nullptr;
+int xoff2(0), yoff2(0), world_mode(WMODE_GROUND), scrolling(0), read_landscape(0), read_heightmap(0), do_read_mesh(0), invert_mh_image(0);
+int mesh_scale_change(0), camera_mode(0), MESH_SIZE[3] = {0}, XY_MULT_SIZE(0), XY_SUM_SIZE(0);
+unsigned erosion_iters(0);
+bool combined_gu(0);
+float LARGE_ZVAL(0), CLOUD_CEILING(0), mesh_file_scale(1.0), mesh_file_tz(0.0), read_mesh_zmm(0.0), disabled_mesh_z(FAR_DISTANCE);
+float temperature(20.0), univ_temp(20.0), init_temperature(20.0);
+char *mh_filename(nullptr), *mesh_file(nullptr);
+point mesh_origin, camera_pos, camera_origin, surface_pos;
+rand_gen_t global_rand_gen;
+
+extern "C" void set_scene_constants_stub2() { // the rest of set_scene_constants() + alloc_matrices() for mesh_height (src/matrix_ops.cpp:57-100)
+	MESH_SIZE[0] = MESH_X_SIZE; MESH_SIZE[1] = MESH_Y_SIZE; MESH_SIZE[2] = MESH_Z_SIZE;
+	XY_MULT_SIZE = MESH_X_SIZE*MESH_Y_SIZE; XY_SUM_SIZE = MESH_X_SIZE + MESH_Y_SIZE;
+	CLOUD_CEILING = CLOUD_CEILING0*Z_SCENE_SIZE;
+	LARGE_ZVAL    = 100.0f*CLOUD_CEILING;
+	if (mesh_height) {delete [] mesh_height[0]; delete [] mesh_height; mesh_height = nullptr;}
+	matrix_gen_2d(mesh_height);
+}
+void checked_fclose(FILE *fp) {if (fp) fclose(fp);}
+bool open_file(FILE *&fp, char const *const fn, std::string const &file_type, char const *const mode) {fp = nullptr; return 0;}
+void texture_t::resize(int, int) {}
+void texture_t::load(int, bool, bool, bool) {}
+void texture_t::gl_delete() {}
+void texture_t::free_client_mem() {}
+float heightmap_t::get_heightmap_value(unsigned, unsigned) const {return 0.0;}

@@ -420,6 +420,107 @@ void to_heightgen_2d(const tw_grid2d *g, const tw_height_params *p, const float 
 	free(xy); free(smt);
 }
 
+/* ------------------------------------------------------------------ ground-mode mesh (ref: src/mesh_gen.cpp:257-355,373-404,447-504) */
+static void apply_mesh_sine(float *zval, float x, float y, const tw_height_params *p, const float *tab) { /* ref: src/mesh_gen.cpp:373-379 */
+	if (p->hmap.sine_mag > 0.0) {
+		float const freq = p->mesh_scale*p->hmap.sine_freq;
+		*zval += (p->hmap.sine_mag*to_cosf_lut(tab, x*freq)*to_cosf_lut(tab, y*freq) + p->hmap.sine_bias)*p->mesh_scale_z_inv;
+		if (p->hmap.volcano_width > 0.0 && p->hmap.volcano_height > 0.0) {*zval += get_volcano_height(x, y, p, tab);}
+	}
+}
+void to_glaciate_mesh(float *mesh, int nx, int ny, int xoff2, int yoff2, int MX, int MY, const tw_height_params *p, const float *tab, float *zbottom, float *ztop)
+{
+	float const zmax_est = p->zmax_est, zmax_est2 = (float)(2.0*zmax_est), zmax_est2_inv = (float)(1.0/zmax_est2);
+	float zb = *zbottom, zt = *ztop;
+	for (int i = 0; i < ny; ++i) {
+		for (int j = 0; j < nx; ++j) {
+			float zval = mesh[(size_t)i*nx + j];
+			if (p->glaciate) {
+				float const relh = (zval + zmax_est)*zmax_est2_inv;
+				zval = do_glaciate_exp(relh, p->custom_glaciate_exp)*zmax_est2 - zmax_est;
+			}
+			apply_mesh_sine(&zval, (float)(j + xoff2 - MX/2), (float)(i + yoff2 - MY/2), p, tab);
+			mesh[(size_t)i*nx + j] = zval;
+			zb = std_min(zb, zval);
+			zt = std_max(zt, zval);
+		}
+	}
+	*zbottom = zb; *ztop = zt;
+}
+void to_gen_mesh(tw_rng *sine_rng, tw_height_params *p, int MX, int MY, float XSS, float YSS, int mesh_seed, int mesh_rgen_index, int xoff2, int yoff2,
+	float dx_val, float dy_val, float water_h_off, float water_h_off_rel, unsigned erosion_iters, tw_erosion_params *ep, const float *tab,
+	float *T, float *mesh, float *zvals6)
+{
+	float const scaled_height = p->mesh_height*p->mesh_height_scale;              /* :267 */
+	float const LARGE_ZVAL = 100.0f*(1.5f*(p->mesh_height/0.10f));               /* only used as the min/max seed */
+	to_gen_sine_params(sine_rng, scaled_height, MX, MY, XSS, YSS, mesh_seed, mesh_rgen_index, p->gen_mode, 0.02f, 240.0f, 2.0f, 0.5f, T);
+	tw_grid2d g = {(float)(xoff2 - MX/2), (float)(yoff2 - MY/2), dx_val, dy_val, (uint32_t)MX, (uint32_t)MY}; /* gen_mesh_sine_table, :201-210 */
+	to_heightgen_2d(&g, p, tab, T, 0, 0, mesh, 1);
+	float zmin = mesh[0], zmax = mesh[0];                                             /* calc_zminmax */
+	for (size_t i = 0; i < (size_t)MX*MY; ++i) {zmin = std_min(zmin, mesh[i]); zmax = std_max(zmax, mesh[i]);}
+	/* estimate_zminmax(using_eq=1), :447-485 */
+	float zmax_est = std_max(zmax, -zmin);
+	float zbottom, ztop;
+	if (zmax == zmin) {zmax_est = (float)(zmax_est + 1.0E-6);}
+	else {
+		float const XY_SCENE_SIZE = 0.5f*(XSS + YSS);
+		float const rm_scale = (float)(1000.0*XY_SCENE_SIZE/p->mesh_scale);
+		tw_grid2d ge = {0.0f, 0.0f, rm_scale, rm_scale, 128, 128};
+		float *probe = (float *)malloc(128*128*sizeof(float));
+		to_heightgen_2d(&ge, p, tab, T, 0, 0, probe, 1);
+		for (unsigned i = 0; i < 128*128; ++i) {zmax_est = std_max(zmax_est, (float)fabs(probe[i]));}
+		free(probe);
+		if (p->gen_mode != TW_MGEN_SINE) {zmax_est = (float)(zmax_est*1.2);}
+		zmax_est = (float)(1.1*zmax_est);
+	}
+	/* set_zvals, :494-504 (the early-return branch above skips it in the reference; zbottom/ztop then keep their previous values - we use zmin/zmax) */
+	zbottom = zmin; ztop = zmax;
+	zmin = -zmax_est; zmax = zmax_est;
+	p->zmax_est = zmax_est;
+	float const water_plane_z = to_water_z_height(zmax_est, p->glaciate, p->custom_glaciate_exp, water_h_off, water_h_off_rel);
+	/* gen_terrain_map, :434-444 */
+	if (p->glaciate) {zbottom = LARGE_ZVAL; ztop = -LARGE_ZVAL; to_glaciate_mesh(mesh, MX, MY, xoff2, yoff2, MX, MY, p, tab, &zbottom, &ztop);}
+	ep->water_plane_z = water_plane_z; ep->zmin = zmin; ep->zmax = zmax;
+	to_apply_erosion(mesh, MX, MY, zbottom, erosion_iters, ep);
+	zvals6[0] = zmin; zvals6[1] = zmax; zvals6[2] = zmax_est; zvals6[3] = zbottom; zvals6[4] = ztop; zvals6[5] = water_plane_z;
+}
+
+/* ------------------------------------------------------------------ tile bounds (ref: src/tiled_mesh.cpp:517-540) */
+void to_tile_bounds(const float *zvals_all, unsigned ntiles, unsigned zvsize, float wpz_max, float dx_val, float dy_val, unsigned size, tw_tile_bounds *out)
+{
+	float const FAR_DISTANCE = 100.0f;
+	unsigned const block_size = zvsize/4;
+	for (unsigned t = 0; t < ntiles; ++t) {
+		const float *zvals = zvals_all + (size_t)t*zvsize*zvsize;
+		tw_tile_bounds *b = out + t;
+		b->mzmin = FAR_DISTANCE; b->mzmax = -FAR_DISTANCE; b->mesh_dz = 0.0f;
+		b->wx1 = b->wy1 = 2147483647; b->wx2 = b->wy2 = -1;
+		for (unsigned yy = 0; yy < 4; ++yy) {
+			for (unsigned xx = 0; xx < 4; ++xx) {
+				unsigned const x_end = (xx+1)*block_size, y_end = (yy+1)*block_size;
+				float szmin = FAR_DISTANCE, szmax = -FAR_DISTANCE;
+				for (unsigned y = yy*block_size; y <= y_end; ++y) {
+					for (unsigned x = xx*block_size; x <= x_end; ++x) {
+						float const z = zvals[y*zvsize + x];
+						szmin = std_min(szmin, z); szmax = std_max(szmax, z);
+						if (z < wpz_max) {
+							if ((int)x < b->wx1) {b->wx1 = (int)x;}
+							if ((int)y < b->wy1) {b->wy1 = (int)y;}
+							if ((int)x > b->wx2) {b->wx2 = (int)x;}
+							if ((int)y > b->wy2) {b->wy2 = (int)y;}
+						}
+					}
+				}
+				b->sub_zmin[yy*4 + xx] = szmin; b->sub_zmax[yy*4 + xx] = szmax;
+				b->mesh_dz = std_max(b->mesh_dz, (szmax - szmin)); /* max_eq */
+				b->mzmin = std_min(b->mzmin, szmin);
+				b->mzmax = std_max(b->mzmax, szmax);
+			}
+		}
+		b->radius = (float)(0.5*sqrtf((dx_val*dx_val + dy_val*dy_val)*size*size + (b->mzmax - b->mzmin)*(b->mzmax - b->mzmin)));
+	}
+}
+
 /* ------------------------------------------------------------------ erosion (ref: src/erosion.cpp:14-164) */
 unsigned long long to_apply_erosion(float *heightmap, int xsize, int ysize, float min_zval, unsigned num_iters, const tw_erosion_params *ep)
 {

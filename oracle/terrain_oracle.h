@@ -50,6 +50,19 @@ float to_eval_mesh_sin_terms(float xv, float yv, const float *sin_table, const f
 void to_heightgen_2d(const tw_grid2d *g, const tw_height_params *p, const float *sin_table, const float *sine_params450,
                      int enable_glaciate, int min_start_sin, float *out, int nthreads);
 
+/* glaciate() of the ground-mode mesh (src/mesh_gen.cpp:388-404: apply_glaciate + apply_mesh_sine per cell, zbottom/ztop), in place */
+void to_glaciate_mesh(float *mesh, int nx, int ny, int xoff2, int yoff2, int mesh_x_size, int mesh_y_size, const tw_height_params *p,
+                      const float *sin_table, float *zbottom, float *ztop);
+/* gen_mesh(surface_type=0, keep_sin_table=0, update_zvals=1) in ground mode (src/mesh_gen.cpp:257-355): sine-table entries, mesh fill,
+ * estimate_zminmax (:447-485), set_zvals (:494-504), glaciate, apply_erosion. p_inout->zmax_est is an output. zvals6: zmin, zmax,
+ * zmax_est, zbottom, ztop, water_plane_z as the globals stand afterwards. ep_partial: erode_amount, relh_adj_tex, clip_hd1, half_dxy are
+ * inputs; water_plane_z/zmin/zmax are filled from set_zvals. */
+void to_gen_mesh(tw_rng *sine_rng, tw_height_params *p_inout, int mesh_x_size, int mesh_y_size, float x_scene_size, float y_scene_size,
+                 int mesh_seed, int mesh_rgen_index, int xoff2, int yoff2, float dx_val, float dy_val, float water_h_off, float water_h_off_rel,
+                 unsigned erosion_iters, tw_erosion_params *ep_partial, const float *sin_table, float *sine_params450_out, float *mesh_out, float *zvals6);
+/* 4x4 sub-block z ranges + water bbox of tile_t::create_zvals (src/tiled_mesh.cpp:517-540); out: ntiles x tw_tile_bounds */
+void to_tile_bounds(const float *zvals, unsigned ntiles, unsigned zvsize, float wpz_max, float dx_val, float dy_val, unsigned size, tw_tile_bounds *out);
+
 /* apply_erosion, src/erosion.cpp:14-164 (serial droplet order) ; returns total droplet steps */
 unsigned long long to_apply_erosion(float *heightmap, int xsize, int ysize, float min_zval, unsigned num_iters, const tw_erosion_params *p);
 

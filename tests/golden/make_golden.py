@@ -74,6 +74,14 @@ for mode in (0, 1, 2, 3, 4):
 R.setup(mode=0, freq_filter=2, seed=6, glaciate=1, mesh_height_scale=0.7, zmax_est=0.5)
 d["cfg1_sp"] = R.sine_params()
 d["cfg1"] = R.heightgen(-64, -64, RL.ref_get_dx(), RL.ref_get_dy(), 128, 128, cache_values=0, glaciate=1)
+# the reference's own gen_mesh() (ground mode): BASELINE config 1 = 128x128 sine mesh, mesh_seed 6, glaciate, mesh_freq_filter 2, mesh_height 0.7,
+# with and without erosion; plus a simplex-mode mesh. zvals = zmin, zmax, zmax_est, zbottom, ztop, water_plane_z after the call.
+for name, (mode, seed, ff, hmap, iters, mhs) in (("gm_cfg1", (0, 6, 2, {}, 0, 0.7)), ("gm_cfg1_eroded", (0, 6, 2, HM_CFG, 2000, 0.7)), ("gm_simplex", (1, 3, 1, HM_CFG, 500, 1.0))):
+    R.setup(mode=mode, freq_filter=ff, seed=seed, glaciate=1, mesh_height_scale=mhs, hmap=hmap, gen_sine_table=False)
+    m, z6 = R.gen_mesh((128, 128), erosion_iters=iters)
+    d[name] = m
+    d[name + "_zvals"] = np.array([z6[k] for k in ("zmin", "zmax", "zmax_est", "zbottom", "ztop", "water_plane_z")], np.float32)
+    d[name + "_args"] = np.array([mode, seed, ff, iters, mhs, hmap.get("sine_mag", 0.0), hmap.get("sine_freq", 0.0), hmap.get("sine_bias", 0.0)], np.float64)
 np.savez_compressed(os.path.join(HERE, "height.npz"), **d)
 
 # ---- erosion ----

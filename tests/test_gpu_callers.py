@@ -1,0 +1,53 @@
+"""GPU parity for the callers' pieces next to the generators: gen_mesh() ground-mode flow (BASELINE config 1) and the tail of
+tile_t::create_zvals (sub-block z ranges, water bbox), through the C ABI, vs the oracle / golden fixtures of the reference's gen_mesh()."""
+import os
+
+import numpy as np
+import pytest
+
+from cases import convert, HM_CFG
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.mark.parametrize("name", ["gm_cfg1", "gm_cfg1_eroded", "gm_simplex"])
+def test_gen_mesh_matches_reference_golden(tw, scene, ctx, beq, name):
+    h = np.load(os.path.join(GOLD, "height.npz"))
+    mode, seed, ff, iters, mhs, smag, sfreq, sbias = h[name + "_args"]
+    hmap = dict(sine_mag=float(smag), sine_freq=float(sfreq), sine_bias=float(sbias)) if smag else {}
+    cfg = scene.SceneConfig(mesh_gen_mode=int(mode), mesh_freq_filter=int(ff), mesh_seed=int(seed), mesh_height=float(mhs), hmap=hmap)
+    cfg.clip_hd1 = lambda: 0.5           # the fixture was generated with clip_hd1 = 0.5, relh_adj_tex = 0
+    mesh, z, _ = scene.gen_mesh(ctx, cfg, erosion_iters=int(iters))
+    assert beq(mesh, h[name]) == 0
+    got = np.array([z[k] for k in ("zmin", "zmax", "zmax_est", "zbottom", "ztop", "water_plane_z")], np.float32)
+    assert beq(got, h[name + "_zvals"]) == 0
+
+
+def test_gen_mesh_matches_oracle_with_offsets(tw, scene, oracle, ctx, beq):
+    for mode, seed, xoff2, yoff2 in ((0, 6, 37, -512), (2, 9, -1000, 250)):
+        cfg = scene.SceneConfig(mesh_gen_mode=mode, mesh_freq_filter=1, mesh_seed=seed, hmap=dict(HM_CFG, volcano_width=300.0, volcano_height=2.0))
+        cfg.clip_hd1 = lambda: 0.4
+        mesh, z, sp = scene.gen_mesh(ctx, cfg, erosion_iters=300, xoff2=xoff2, yoff2=yoff2)
+        cfg2 = scene.SceneConfig(mesh_gen_mode=mode, mesh_freq_filter=1, mesh_seed=seed, hmap=dict(HM_CFG, volcano_width=300.0, volcano_height=2.0))
+        hp = convert(cfg2.height_params(), oracle.HeightParams)
+        mo, zo, spo = oracle.gen_mesh(hp, seed=seed, xoff2=xoff2, yoff2=yoff2, erosion_iters=300, ep=oracle.ErosionParams(1.0, 0.0, 0.0625, 0.0, 0.0, 0.0, 0.4))
+        assert beq(sp, spo) == 0 and beq(mesh, mo) == 0
+        assert all(np.float32(z[k]) == np.float32(zo[k]) for k in zo)
+
+
+def test_tile_bounds(tw, scene, oracle, ctx):
+    cfg = scene.SceneConfig(mesh_gen_mode=1, mesh_freq_filter=1, mesh_seed=1, hmap=HM_CFG, zmax_est=2.3, mesh_size=(128, 128, 1))
+    hp = cfg.height_params()
+    for S in (128, 64):
+        zv = S + 2
+        origins = [(tx * S * 3, ty * S * 5 - 2000) for ty in range(4) for tx in range(5)]
+        tiles = ctx.heightgen_tiles(origins, (S, S), float(cfg.dx_val), float(cfg.dy_val), zv, hp)
+        wpz_max = float(np.median(tiles))        # get_max_sea_level(): about half the cells under water
+        got = ctx.tile_bounds(tiles, wpz_max, float(cfg.dx_val), float(cfg.dy_val), S)
+        exp = oracle.tile_bounds(tiles, wpz_max, float(cfg.dx_val), float(cfg.dy_val), S)
+        for g, e in zip(got, exp):
+            assert bytes(g) == bytes(e)
+        import torch
+        got_dev = ctx.tile_bounds(torch.from_numpy(tiles).cuda(), wpz_max, float(cfg.dx_val), float(cfg.dy_val), S)
+        assert all(bytes(g) == bytes(e) for g, e in zip(got_dev, exp))

@@ -119,3 +119,34 @@ def test_u16_pack_roundtrip(oracle):
     assert np.abs(back - vals).max() <= float(mult) / 256.0 * 1.01 + 1e-6
     _, bad = oracle.from_floats_u16(np.array([0.0], np.float32), 1.0, 1.0)   # v = -1: out of range
     assert bad == 1
+
+
+def _gen_mesh_case(O, args):
+    mode, seed, ff, iters, mhs, smag, sfreq, sbias = args
+    hp = O.HeightParams()
+    hp.gen_mode, hp.gen_shape, hp.start_eval_sin, hp.glaciate = int(mode), 0, O.compute_scale(1.0, int(ff)), 1
+    hp.mesh_scale = hp.mesh_scale_z_inv = 1.0
+    hp.dx_val_inv = hp.dy_val_inv = 16.0
+    hp.mesh_height, hp.mesh_height_scale, hp.zmax_est = np.float32(0.1) * np.float32(4.0), float(mhs), 1.0
+    hp.rx, hp.ry = O.gen_rx_ry(int(seed), 0, int(mode))
+    hp.hmap = O.hmap_params(sine_mag=float(smag), sine_freq=float(sfreq), sine_bias=float(sbias))
+    return hp, int(seed), int(iters)
+
+
+def test_gen_mesh_ground_mode(oracle, beq):
+    """BASELINE config 1 (128x128 sine mesh, seed 6, glaciate, freq filter 2, mesh_height 0.7) through the whole gen_mesh() flow:
+    sine table, mesh fill, estimate_zminmax probe, set_zvals, glaciate(), apply_erosion - against the reference's own gen_mesh()."""
+    h = load("height.npz")
+    for name in ("gm_cfg1", "gm_cfg1_eroded", "gm_simplex"):
+        hp, seed, iters = _gen_mesh_case(oracle, h[name + "_args"])
+        mesh, z6, _ = oracle.gen_mesh(hp, seed=seed, erosion_iters=iters, ep=oracle.ErosionParams(1.0, 0.0, 0.0625, 0.0, 0.0, 0.0, 0.5))
+        assert beq(mesh, h[name]) == 0, name
+        assert beq(np.array([z6[k] for k in ("zmin", "zmax", "zmax_est", "zbottom", "ztop", "water_plane_z")], np.float32), h[name + "_zvals"]) == 0
+
+
+def test_tile_bounds_small_case(oracle):
+    z = np.arange(36, dtype=np.float32).reshape(1, 6, 6)           # zvsize 6 -> block_size 1: sub-block (yy,xx) covers rows yy..yy+1, cols xx..xx+1
+    b = oracle.tile_bounds(z, 7.5, 0.0625, 0.0625, 4)[0]
+    assert list(b.sub_zmin)[:4] == [0.0, 1.0, 2.0, 3.0] and list(b.sub_zmax)[:4] == [7.0, 8.0, 9.0, 10.0]
+    assert (b.mzmin, b.mzmax, b.mesh_dz) == (0.0, 28.0, 7.0)     # cells beyond index 4 are never visited (last row/column is not rendered)
+    assert (b.wx1, b.wy1, b.wx2, b.wy2) == (0, 0, 4, 1)            # z < 7.5: rows 0 (cols 0..4) and row 1 (cols 0,1)

@@ -77,3 +77,22 @@ def test_voxel_fill(oracle, ref, beq):
                 vp.gen_mode, vp.normalize_to_1, vp.rseed1, vp.rseed2, vp.octaves = mode, norm, 123, 456, max(1, 5 - ff)
                 vp.rx, vp.ry, vp.zscale = rx, ry, zs
                 assert beq(zr, oracle.voxel_fill(vp)) == 0
+
+
+def test_gen_mesh_ground_mode(oracle, ref, beq):
+    """The reference's own gen_mesh(0,0,1) (linked unmodified) vs the oracle's restatement of the whole ground-mode flow."""
+    ref.lib().ref_set_threads(1)
+    for mode, seed, ff, hmap, iters, mhs in ((0, 6, 2, {}, 0, 0.7), (0, 6, 2, HM_CFG, 1500, 0.7), (1, 3, 1, HM_CFG, 400, 1.0), (2, 5, 1, {}, 300, 1.0)):   # GPU gen modes 3/4 need a GL shader inside the reference's gen_mesh
+        ref.setup(mode=mode, freq_filter=ff, seed=seed, glaciate=1, mesh_height_scale=mhs, hmap=hmap, gen_sine_table=False)
+        zr, z6r = ref.gen_mesh((128, 128), erosion_iters=iters)
+        hp = oracle.HeightParams()
+        hp.gen_mode, hp.gen_shape, hp.start_eval_sin, hp.glaciate = mode, 0, oracle.compute_scale(1.0, ff), 1
+        hp.mesh_scale = hp.mesh_scale_z_inv = 1.0
+        hp.dx_val_inv = hp.dy_val_inv = 16.0
+        hp.mesh_height, hp.mesh_height_scale, hp.zmax_est = np.float32(0.1) * np.float32(4.0), mhs, 1.0
+        hp.rx, hp.ry = oracle.gen_rx_ry(seed, 0, mode)
+        hp.hmap = oracle.hmap_params(**hmap)
+        zo, z6o, _ = oracle.gen_mesh(hp, seed=seed, erosion_iters=iters, ep=oracle.ErosionParams(1.0, 0.0, 0.0625, 0.0, 0.0, 0.0, 0.5))
+        assert beq(zr, zo) == 0, (mode, seed)
+        assert all(np.float32(z6r[k]) == np.float32(z6o[k]) for k in z6r), (z6r, z6o)
+    ref.lib().ref_set_threads(8)
