@@ -254,9 +254,11 @@ void launch_droplets(cudaStream_t st, float *d_pad, unsigned nt, int xsize, int 
 int pick_group(unsigned ntiles) {
 	const char *env = getenv("TW_EROSION_LANES");
 	if (env) {int const g = atoi(env); if (g == 1 || g == 2 || g == 4 || g == 8 || g == 16 || g == 32) return g;}
-	(void)ntiles;
-	return 32; // measured on B200 (tools/bench_erosion.py): G = 32 wins at every heightmap count up to 65536 - the step is a serial
-	           // dependency chain (latency-bound), so coalesced accesses and fewer resident maps beat the saved redundant ALU work
+	// measured on B200 (tools/bench_erosion.py, 258^2 tiles, heaviest-first schedule): 16384 maps: G=32 0.18 s, G=16 0.23 s, G=8 0.27 s;
+	// 65536 maps: G=32 0.53 s, G=16 0.40 s, G=8 0.40 s. With >= ~16k warps the kernel is issue-bound (78 % issue slots at G=32), so sharing a
+	// warp between maps pays; below that it is latency/tail-bound and one warp per map is fastest. => smallest G >= 8 that keeps 16384 warps.
+	for (int g = 8; g < 32; g *= 2) {if ((unsigned long long)ntiles*g >= 32ull*16384ull) return g;}
+	return 32;
 }
 
 } // namespace
