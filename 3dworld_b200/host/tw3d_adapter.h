@@ -13,6 +13,7 @@
 #pragma once
 #include <tw3d.h>
 #include <cassert>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -202,6 +203,67 @@ inline void create_zvals_batch(const int32_t *origins_xy, unsigned ntiles, unsig
 	// apply_erosion(zvals.data(), zvsize, zvsize, zmin, erosion_iters_tt): min_zval is the global zmin (src/tiled_mesh.cpp:515)
 	int const rc = tw_create_zvals_batch(c, origins_xy, ntiles, g.MESH_X_SIZE, g.MESH_Y_SIZE, dx, dy, zvsize, &p, erosion_iters_tt, &e, g.zmin, zvals_out, mm);
 	if (rc != TW_OK) {detail::fail(rc, "create_zvals_batch", c);}
+}
+
+// ------------------------------------------------------------------------------------------------ gen_mesh (ground mode)
+// gen_mesh(surface_type=0, keep_sin_table=0, update_zvals=1) for WMODE_GROUND (src/mesh_gen.cpp:257-355): regenerates the sine table from
+// the function-static generator state (pass the same tw_rng across calls), fills mesh_height, estimates zmax_est from a 128x128 probe of the
+// equation (estimate_zminmax, :447-485), sets the z globals (set_zvals, :494-504), glaciates (:388-404) and erodes (:443).
+// The derived globals are written back into scene_globals (zmax_est, zmin, zmax, water_plane_z) exactly as the reference leaves them.
+struct gen_mesh_result {float zmin, zmax, zmax_est, zbottom, ztop, water_plane_z;};
+
+inline gen_mesh_result gen_mesh(float *mesh_height /* MESH_Y_SIZE x MESH_X_SIZE, row-major */, tw_rng &sine_rng, float x_scene_size, float y_scene_size,
+	unsigned erosion_iters, int xoff2 = 0, int yoff2 = 0, float dx_val = 0.0f, float dy_val = 0.0f, float water_h_off = 0.0f, float water_h_off_rel = 0.0f)
+{
+	scene_globals g = globals();
+	int const MX = g.MESH_X_SIZE, MY = g.MESH_Y_SIZE;
+	if (dx_val == 0.0f) {dx_val = 1.0f/g.DX_VAL_INV;}
+	if (dy_val == 0.0f) {dy_val = 1.0f/g.DY_VAL_INV;}
+	std::vector<float> sinTable(TW_F_TABLE_SIZE*5);
+	tw_gen_sine_params(&sine_rng, g.MESH_HEIGHT*g.mesh_height_scale, MX, MY, x_scene_size, y_scene_size, g.mesh_seed, g.mesh_rgen_index, g.mesh_gen_mode,
+	                   0.02f, 240.0f, 2.0f, 0.5f, sinTable.data());
+	set_globals(g, nullptr, sinTable.data());
+	tw_ctx *c = ctx();
+	tw_height_params p = height_params_from_globals(g.mesh_gen_mode, g.mesh_gen_shape);
+	tw_grid2d const grid = {(float)(xoff2 - MX/2), (float)(yoff2 - MY/2), dx_val, dy_val, (uint32_t)MX, (uint32_t)MY}; // gen_mesh_sine_table, :201-210
+	tw_minmax mm;
+	int rc = tw_heightgen_2d(c, &grid, &p, 0, 0, mesh_height, &mm);
+	if (rc != TW_OK) {detail::fail(rc, "gen_mesh", c);}
+	float zmin = mm.zmin, zmax = mm.zmax;                        // calc_zminmax
+	float zmax_est = (zmax < -zmin) ? -zmin : zmax;              // set_zmax_est(max(zmax, -zmin))
+	if (zmax == zmin) {zmax_est = zmax_est + 1.0E-6;}
+	else {
+		float const XY_SCENE_SIZE(0.5f*(x_scene_size + y_scene_size));
+		float const rm_scale(1000.0*XY_SCENE_SIZE/g.mesh_scale);
+		tw_grid2d const probe = {0.0f, 0.0f, rm_scale, rm_scale, 128, 128};   // EST_RAND_PARAM
+		std::vector<float> h(128*128);
+		rc = tw_heightgen_2d(c, &probe, &p, 0, 0, h.data(), nullptr);
+		if (rc != TW_OK) {detail::fail(rc, "estimate_zminmax", c);}
+		for (float v : h) {float const a(std::fabs(v)); zmax_est = (zmax_est < a) ? a : zmax_est;}
+		if (g.mesh_gen_mode != TW_MGEN_SINE) {zmax_est *= 1.2;}
+		zmax_est = 1.1*zmax_est;
+	}
+	gen_mesh_result r;
+	r.zbottom = zmin; r.ztop = zmax;                              // set_zvals
+	r.zmin = -zmax_est; r.zmax = zmax_est; r.zmax_est = zmax_est;
+	r.water_plane_z = tw_water_z_height(zmax_est, g.GLACIATE, g.custom_glaciate_exp, water_h_off, water_h_off_rel);
+	g.zmax_est = zmax_est; g.zmin = r.zmin; g.zmax = r.zmax; g.water_plane_z = r.water_plane_z;
+	set_globals(g);
+	p.zmax_est = zmax_est;
+	if (g.GLACIATE) { // gen_terrain_map -> glaciate()
+		rc = tw_glaciate_mesh(c, mesh_height, MX, MY, xoff2, yoff2, MX, MY, &p, &mm);
+		if (rc != TW_OK) {detail::fail(rc, "glaciate", c);}
+		r.zbottom = mm.zmin; r.ztop = mm.zmax;
+	}
+	apply_erosion(mesh_height, MX, MY, r.zbottom, erosion_iters);
+	return r;
+}
+
+// tail of tile_t::create_zvals for a batch of finished tiles (sub_zmin/sub_zmax, mzmin/mzmax, mesh_dz, radius, water bbox), src/tiled_mesh.cpp:517-541
+inline void tile_bounds(const float *zvals, unsigned ntiles, unsigned zvsize, float wpz_max, float dx_val, float dy_val, unsigned size, tw_tile_bounds *out) {
+	tw_ctx *c = ctx();
+	int const rc = tw_tile_bounds_batch(c, zvals, ntiles, zvsize, wpz_max, dx_val, dy_val, size, out);
+	if (rc != TW_OK) {detail::fail(rc, "tile_bounds", c);}
 }
 
 // noise_gen_3d: the table-generation half of the reference class (src/upsurface.h:39-50); grid evaluation goes through create_procedural

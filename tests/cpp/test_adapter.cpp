@@ -83,6 +83,21 @@ int main(int argc, char **argv) {
 		float const offset[3] = {0.5f, -0.25f, 0.0f};
 		tw3d::create_procedural(v, 1.0f, 1.0f, offset, true, 123, 456, (mode >= 3 ? 1 : mode), 0.0f, 2);
 		dump(f, vox);
+
+		// --- gen_mesh(): BASELINE config 1 (128x128 sine mesh, mesh_seed 6, glaciate, mesh_freq_filter 2, mesh_height 0.7) + 2000 droplets ---
+		if (mode == 0) {
+			tw3d::scene_globals g1;
+			g1.mesh_gen_mode = 0; g1.mesh_seed = 6; g1.start_eval_sin = tw_compute_scale(1.0f, 2); g1.mesh_height_scale = 0.7f;
+			g1.hmap_params.sine_mag = 5.0f; g1.hmap_params.sine_freq = 0.001f; g1.hmap_params.sine_bias = -4.0f;
+			g1.clip_hd1 = 0.5f; g1.relh_adj_tex = 0.0f;
+			tw3d::set_globals(g1);
+			tw_rng srng = {1, 1};
+			std::vector<float> mesh(128*128);
+			tw3d::gen_mesh_result const r = tw3d::gen_mesh(mesh.data(), srng, 4.0f, 4.0f, 2000);
+			dump(f, mesh);
+			std::vector<float> z6 = {r.zmin, r.zmax, r.zmax_est, r.zbottom, r.ztop, r.water_plane_z};
+			dump(f, z6);
+		}
 	}
 	catch (tw3d::error const &e) {fprintf(stderr, "tw3d error %d: %s\n", e.status, e.what()); fclose(f); return 2;}
 	fclose(f);
