@@ -63,6 +63,11 @@ class TileBounds(C.Structure):
                 ("radius", C.c_float), ("wx1", C.c_int32), ("wy1", C.c_int32), ("wx2", C.c_int32), ("wy2", C.c_int32)]
 
 
+class HeightmapInfo(C.Structure):
+    _fields_ = [("min_z", C.c_float), ("max_z", C.c_float), ("val_mult", C.c_float), ("val_add", C.c_float), ("mesh_file_scale", C.c_float),
+                ("mesh_file_tz", C.c_float), ("erosion_moves", C.c_uint64)]
+
+
 class Rng(C.Structure):
     _fields_ = [("rseed1", C.c_int64), ("rseed2", C.c_int64)]
 
@@ -80,7 +85,7 @@ ABI_SYMBOLS = ["tw_abi_version", "tw_create", "tw_destroy", "tw_last_error", "tw
                "tw_build_sin_table", "tw_compute_scale", "tw_gen_sine_params", "tw_gen_rx_ry", "tw_noise3d_gen_sines",
                "tw_water_z_height", "tw_set_sin_table", "tw_set_sine_params", "tw_heightgen_2d", "tw_heightgen_2d_launch",
                "tw_heightgen_2d_poll", "tw_heightgen_tiles", "tw_create_zvals_batch", "tw_tile_bounds_batch", "tw_glaciate_mesh", "tw_erode", "tw_erode_tiles", "tw_last_erosion_steps", "tw_voxel_fill",
-               "tw_heightmap_from_floats_u16", "tw_heightmap_to_floats_u16", "tw_minmax_f32"]
+               "tw_heightmap_from_floats_u16", "tw_heightmap_to_floats_u16", "tw_proc_gen_heightmap", "tw_minmax_f32"]
 
 
 def _load():
@@ -129,6 +134,8 @@ def _load():
     L.tw_voxel_fill.argtypes = [vp, C.POINTER(VoxelParams), vp, vp]
     L.tw_heightmap_from_floats_u16.argtypes = [vp, vp, C.c_size_t, C.c_float, C.c_float, vp]
     L.tw_heightmap_to_floats_u16.argtypes = [vp, vp, C.c_size_t, C.c_float, C.c_float, vp]
+    L.tw_proc_gen_heightmap.argtypes = [vp, C.c_uint32, C.c_uint32, C.c_float, C.c_float, C.POINTER(HeightParams), C.c_uint32, C.POINTER(ErosionParams), vp, vp,
+                                        C.POINTER(HeightmapInfo)]
     L.tw_minmax_f32.argtypes = [vp, vp, C.c_size_t, C.POINTER(MinMax)]
     return L
 
@@ -317,6 +324,14 @@ class Context:
             out = np.empty(n, np.float32)
         self._check(lib.tw_heightmap_to_floats_u16(self._h, _ptr(data), n, val_mult, val_add, _ptr(out)))
         return out
+
+    def proc_gen_heightmap(self, width, height, dx_val, dy_val, hp, erosion_iters, ep, data16=None, vals=None):
+        """heightmap_t::proc_gen in one call; returns (16-bit image bytes, info, vals or None)."""
+        if data16 is None:
+            data16 = np.empty(2 * width * height, np.uint8)
+        info = HeightmapInfo()
+        self._check(lib.tw_proc_gen_heightmap(self._h, width, height, dx_val, dy_val, C.byref(hp), erosion_iters, C.byref(ep), _ptr(data16), _ptr(vals), C.byref(info)))
+        return data16, info, vals
 
     def minmax(self, vals):
         mm = MinMax()

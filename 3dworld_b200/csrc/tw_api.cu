@@ -502,6 +502,59 @@ int tw_heightmap_to_floats_u16(tw_ctx *ctx, const uint8_t *data2n, size_t n, flo
 	return TW_OK;
 }
 
+int tw_proc_gen_heightmap(tw_ctx *ctx, uint32_t width, uint32_t height, float dx_val, float dy_val, const tw_height_params *p,
+                          uint32_t erosion_iters, const tw_erosion_params *ep, uint8_t *data16, float *vals, tw_heightmap_info *info)
+{
+	int rc = check_ctx(ctx); if (rc) return rc;
+	rc = finish_pending(ctx); if (rc) return rc;
+	if (!p || !data16 || width == 0 || height == 0) return tw_set_error(ctx, TW_ERR_ARG, "null/empty argument");
+	tw_grid2d g; g.x0 = -0.5*width; g.y0 = -0.5*height; g.dx = dx_val; g.dy = dy_val; g.nx = width; g.ny = height; // src/heightmap.cpp:135
+	size_t const n = (size_t)width*height;
+	bool const vals_dev = (vals && tw_is_device_ptr(vals)), out_dev = tw_is_device_ptr(data16);
+	// slot 0: [vals (if not given on the device)] [u16 image (if not given on the device)]
+	size_t const vbytes = (n*sizeof(float) + 255) & ~(size_t)255;
+	rc = tw_reserve(ctx, 0, (vals_dev ? 0 : vbytes) + (out_dev ? 0 : 2*n) + 256); if (rc) return rc;
+	char *s0 = (char *)ctx->d_scratch[0];
+	float *d_vals = vals_dev ? vals : (float *)s0;
+	if (!vals_dev) {s0 += vbytes;}
+	uint8_t *d_img = out_dev ? data16 : (uint8_t *)s0;
+	rc = validate_height(ctx, &g, p, d_vals); if (rc) return rc;
+	rc = tw_reserve(ctx, 2, OFF_TILES); if (rc) return rc;
+	unsigned *d_mm = (unsigned *)((char *)ctx->d_scratch[2] + OFF_MM);
+	tw_minmax mm;
+	rc = twi_init_minmax(ctx, d_mm, 1); if (rc) return rc;
+	rc = twi_heightgen(ctx, &g, p, 1, 0, nullptr, 1, d_vals, d_mm); if (rc) return rc;
+	rc = read_minmax(ctx, d_mm, &mm, 1); if (rc) return rc;
+	uint64_t moves = 0;
+	if (erosion_iters > 0 && ep && ep->erode_amount > 0.0) { // run_erosion: min_zval = min over vals (src/heightmap.cpp:155-156)
+		rc = twi_erode(ctx, d_vals, 1, (int)width, (int)height, nullptr, mm.zmin, erosion_iters, ep); if (rc) return rc;
+		moves = ctx->last_erosion_steps;
+		rc = twi_init_minmax(ctx, d_mm, 1); if (rc) return rc;
+		rc = twi_minmax(ctx, d_vals, n, d_mm); if (rc) return rc;
+		rc = read_minmax(ctx, d_mm, &mm, 1); if (rc) return rc; // get_heightmap_z_range
+	}
+	float const min_z = mm.zmin, max_z = mm.zmax;
+	float const TOLERANCE = 1.0E-12, READ_MESH_H_SCALE = 0.0008; // src/3DWorld.h:50, src/mesh_gen.cpp:22
+	float const dzr = max_z - min_z, dz = (TOLERANCE < dzr) ? dzr : TOLERANCE; // max(TOLERANCE, (max_z - min_z))
+	float const dz255 = dz/255.0;                                             // set_mesh_height_scales_for_zval_range(min_z, dz/255.0)
+	float const mesh_file_scale = dz255/(READ_MESH_H_SCALE*p->mesh_height_scale*p->mesh_scale_z_inv);
+	float const mesh_file_tz    = min_z/p->mesh_scale_z_inv;
+	float const val_mult = READ_MESH_H_SCALE*p->mesh_height_scale*mesh_file_scale*p->mesh_scale_z_inv; // get_mh_texture_mult()
+	float const val_add  = mesh_file_tz*p->mesh_scale_z_inv;                                             // get_mh_texture_add()
+	unsigned *d_bad = (unsigned *)((char *)ctx->d_scratch[2] + OFF_BAD);
+	TW_CUDA(ctx, cudaMemsetAsync(d_bad, 0, sizeof(unsigned), ctx->stream));
+	rc = twi_from_floats_u16(ctx, d_vals, n, val_mult, val_add, d_img, d_bad); if (rc) return rc;
+	if (!out_dev) {TW_CUDA(ctx, cudaMemcpyAsync(data16, d_img, 2*n, cudaMemcpyDeviceToHost, ctx->stream));}
+	if (vals && !vals_dev) {TW_CUDA(ctx, cudaMemcpyAsync(vals, d_vals, n*sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));}
+	unsigned bad = 0;
+	TW_CUDA(ctx, cudaMemcpyAsync(&bad, d_bad, sizeof(bad), cudaMemcpyDeviceToHost, ctx->stream));
+	TW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	ctx->last_erosion_steps = moves;
+	if (info) {info->min_z = min_z; info->max_z = max_z; info->val_mult = val_mult; info->val_add = val_add; info->mesh_file_scale = mesh_file_scale; info->mesh_file_tz = mesh_file_tz; info->erosion_moves = moves;}
+	if (bad) return tw_set_error(ctx, TW_ERR_ARG, "from_floats: value outside [0,256) (the reference asserts, src/heightmap.cpp:211)");
+	return TW_OK;
+}
+
 int tw_minmax_f32(tw_ctx *ctx, const float *vals, size_t n, tw_minmax *mm) {
 	int rc = check_ctx(ctx); if (rc) return rc;
 	rc = finish_pending(ctx); if (rc) return rc;

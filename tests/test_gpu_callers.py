@@ -51,3 +51,54 @@ def test_tile_bounds(tw, scene, oracle, ctx):
         import torch
         got_dev = ctx.tile_bounds(torch.from_numpy(tiles).cuda(), wpz_max, float(cfg.dx_val), float(cfg.dy_val), S)
         assert all(bytes(g) == bytes(e) for g, e in zip(got_dev, exp))
+
+
+def _oracle_proc_gen(oracle, cfg, hp_o, w, h, iters, ep_o):
+    """heightmap_t::proc_gen restated from the pinned oracle pieces (src/heightmap.cpp:130-215, src/mesh_gen.cpp:120-131)."""
+    f32 = np.float32
+    vals = oracle.heightgen_2d(oracle.Grid2D(-0.5 * w, -0.5 * h, float(cfg.dx_val), float(cfg.dy_val), w, h), hp_o, None, 1, 0)
+    moves = 0
+    if iters:
+        vals, moves = oracle.apply_erosion(vals, float(vals.min()), iters, ep_o)
+    min_z, max_z = f32(vals.min()), f32(vals.max())
+    dz = max(f32(1.0E-12), f32(max_z - min_z))
+    dz255 = f32(float(dz) / 255.0)
+    mhs, mszi, R = f32(hp_o.mesh_height_scale), f32(hp_o.mesh_scale_z_inv), f32(0.0008)
+    mfs = f32(dz255 / f32(f32(R * mhs) * mszi))
+    mtz = f32(min_z / mszi)
+    mult, add = f32(f32(f32(R * mhs) * mfs) * mszi), f32(mtz * mszi)
+    img, bad = oracle.from_floats_u16(vals, float(mult), float(add))
+    assert bad == 0
+    return img, vals, (float(min_z), float(max_z), float(mult), float(add)), moves
+
+
+@pytest.mark.parametrize("mode,iters,w,h", [(1, 0, 320, 200), (4, 800, 256, 256), (0, 500, 130, 258)])
+def test_proc_gen_heightmap(tw, scene, oracle, ctx, beq, mode, iters, w, h):
+    cfg = scene.SceneConfig(mesh_gen_mode=mode, mesh_freq_filter=1, mesh_seed=1, hmap=HM_CFG, zmax_est=2.3)
+    hp, ep = cfg.height_params(), cfg.erosion_params()
+    if mode == 0:
+        ctx.set_sine_params(cfg.sine_params())
+        hp_sp = cfg.sine_params()
+    img_o, vals_o, (mn, mx, mult, add), moves = _oracle_proc_gen_sp(oracle, cfg, hp, w, h, iters, ep, cfg.sine_params() if mode == 0 else None)
+    vals = np.empty((h, w), np.float32)
+    img, info, _ = ctx.proc_gen_heightmap(w, h, float(cfg.dx_val), float(cfg.dy_val), hp, iters, ep, vals=vals)
+    assert beq(vals, vals_o) == 0
+    assert (info.min_z, info.max_z, info.val_mult, info.val_add) == (mn, mx, mult, add)
+    assert info.erosion_moves == moves
+    assert np.array_equal(img, img_o)
+    import torch
+    d_img = torch.empty(2 * w * h, dtype=torch.uint8, device="cuda")
+    ctx.proc_gen_heightmap(w, h, float(cfg.dx_val), float(cfg.dy_val), hp, iters, ep, data16=d_img)
+    assert np.array_equal(d_img.cpu().numpy(), img_o)
+
+
+def _oracle_proc_gen_sp(oracle, cfg, hp, w, h, iters, ep, sp):
+    hp_o, ep_o = convert(hp, oracle.HeightParams), convert(ep, oracle.ErosionParams)
+    if sp is None:
+        return _oracle_proc_gen(oracle, cfg, hp_o, w, h, iters, ep_o)
+    orig = oracle.heightgen_2d
+    try:
+        oracle.heightgen_2d = lambda g, p, _sp, gl, mss: orig(g, p, sp, gl, mss)
+        return _oracle_proc_gen(oracle, cfg, hp_o, w, h, iters, ep_o)
+    finally:
+        oracle.heightgen_2d = orig

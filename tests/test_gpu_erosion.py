@@ -104,3 +104,20 @@ def test_fused_tile_pipeline_equals_separate_calls(tw, scene, oracle, ctx, beq, 
     assert beq(dev.cpu().numpy(), sep) == 0
     no_erosion = ctx.create_zvals_batch(origins, cfg.mesh_size, dx, dy, zv, hp, 0, ep, ep.zmin)
     assert beq(no_erosion, raw) == 0
+
+
+def test_full_size_single_map_8192(tw, scene, oracle, ctx, beq):
+    """BASELINE config 3 at full size: apply_erosion on the 8192^2 map, 1000 droplets, bit-exact against the oracle (the oracle's cost
+    here is its 540 MB of padded copies, ~1 s)."""
+    import torch
+    cfg = scene.SceneConfig(mesh_gen_mode=1, mesh_freq_filter=1, mesh_seed=1, hmap=HM_CFG, zmax_est=2.3)
+    hp, ep = cfg.height_params(), cfg.erosion_params()
+    N = 8192
+    d = torch.empty((N, N), dtype=torch.float32, device="cuda")
+    _, (zmin, zmax) = ctx.heightgen_2d(cfg.heightmap_grid(N, N), hp, out=d, want_minmax=True)
+    z = d.cpu().numpy()
+    zc, moves = oracle.apply_erosion(z, zmin, 1000, convert(ep, oracle.ErosionParams))
+    ctx.erode(d, zmin, 1000, ep)
+    assert ctx.last_erosion_steps == moves
+    assert beq(d.cpu().numpy(), zc) == 0
+    assert (zc != z).sum() > 1000
