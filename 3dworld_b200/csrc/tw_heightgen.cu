@@ -11,6 +11,8 @@
 // All arithmetic keeps the reference's rounding sequence (this TU is compiled with -fmad=false; see tw_noise.cuh).
 #include "tw_internal.h"
 #include "tw_noise.cuh"
+#include "tw_noise2.cuh"
+#include <stdlib.h>
 
 namespace {
 
@@ -103,6 +105,7 @@ struct NoiseParams {
 	float freq[9], mag[9], rx[9], ry[9]; // per-octave constants of gen_noise's loop (mag*=0.5, freq*=1.92, rx*=1.5, ry*=1.5), host-computed
 	float xy_scale;              // MESH_SCALE_FACTOR*mesh_scale
 	float hmap_scale;            // get_hmap_scale(mode)
+	float freq_last, rsum_last;  // freq / (rx+ry) of the last octave: bound of the lattice coordinates (packed-path range guard)
 };
 
 template<bool SIMPLEX, int SHAPE>
@@ -154,6 +157,90 @@ noise_grid_kernel(float *__restrict__ out, unsigned nx, unsigned ny, unsigned y_
 		out[(size_t)tile*nx*ny + (size_t)y*nx + x] = z;
 	}
 	if (mm) {block_minmax(valid ? z : INFINITY, valid ? z : -INFINITY, mm + 2*tile);}
+}
+
+// ---- packed variant: two horizontally adjacent cells per thread on FFMA2/FMUL2/FADD2 (see tw_noise2.cuh) ----
+// |lattice coordinate| < 2^22 for every octave of this fBm call (needed by the packed floor / division-free mod); NaN-safe
+__device__ __forceinline__ bool noise_lattice_in_range(float2 xv, float2 yv, const NoiseParams &N) {
+	float const bx = (fabsf(xv.x) + fabsf(yv.x))*N.freq_last + N.rsum_last, by = (fabsf(xv.y) + fabsf(yv.y))*N.freq_last + N.rsum_last;
+	return (bx < 2097152.0f && by < 2097152.0f); // |p + s| <= 1.37*(|px|+|py|) < 2^22, and floor(p)+1 stays in range for Perlin
+}
+
+template<bool SIMPLEX, int SHAPE>
+__device__ __forceinline__ float2 gen_noise2(float2 xv, float2 yv, const NoiseParams &N) { // gen_noise (src/mesh_gen.cpp:706-730) for two cells
+	float2 zval = make_float2(0.0f, 0.0f);
+	if (noise_lattice_in_range(xv, yv, N)) {
+#pragma unroll 1
+		for (int i = 0; i < N.octaves; ++i) {
+			float2 const px = twn2::add2(twn2::mul2(xv, N.freq[i]), N.rx[i]), py = twn2::add2(twn2::mul2(yv, N.freq[i]), N.ry[i]);
+			float2 noise = SIMPLEX ? twn2::simplex2(px, py) : twn2::perlin2(px, py);
+			if (SHAPE == 1) {noise = make_float2((float)((double)fabsf(noise.x) - 0.40), (float)((double)fabsf(noise.y) - 0.40));}
+			if (SHAPE == 2) {noise = make_float2((float)(0.45 - (double)fabsf(noise.x)), (float)(0.45 - (double)fabsf(noise.y)));}
+			zval = twn2::fma2(noise, N.mag[i], zval); // mag is a power of two: exact product
+		}
+	}
+	else {zval = make_float2(gen_noise<SIMPLEX, SHAPE>(xv.x, yv.x, N), gen_noise<SIMPLEX, SHAPE>(xv.y, yv.y, N));} // astronomically far out: scalar path with the literal division
+	return zval;
+}
+
+__device__ __forceinline__ float dadd(float a, double b) {return (float)((double)a + b);} // float + double literal, rounded back (src/mesh_gen.cpp:742-745)
+
+template<bool SIMPLEX, bool WARP, int SHAPE>
+__global__ void __launch_bounds__(256)
+noise_grid2_kernel(float *__restrict__ out, unsigned nx, unsigned ny, unsigned y_off, float mx0_single, float my0_single, const float2 *__restrict__ tile_origins,
+	NoiseParams N, PostParams P, const float *__restrict__ sin_tab, unsigned *__restrict__ mm)
+{
+	unsigned const x = 2*(blockIdx.x*blockDim.x + threadIdx.x), y = y_off + blockIdx.y*blockDim.y + threadIdx.y, tile = blockIdx.z;
+	float mx0 = mx0_single, my0 = my0_single;
+	if (tile_origins) {float2 const o = __ldg(tile_origins + tile); mx0 = o.x; my0 = o.y;}
+	bool const valid0 = (x < nx && y < ny), valid1 = (x + 1 < nx && y < ny);
+	float z0 = 0.0f, z1 = 0.0f;
+	if (valid0) { // the second cell of an odd-width row is computed (at x+1) and dropped
+		using namespace twn2;
+		float2 const xs = make_float2((float)x, (float)(x + 1));
+		float2 const xval = mul2(add2(mul2(xs, P.mdx), mx0), P.dx_inv);           // (x*mdx + mx0)*DX_VAL_INV, src/mesh_gen.cpp:762
+		float const yval1 = ((float)y*P.mdy + my0)*P.dy_inv;
+		float2 xv = mul2(xval, N.xy_scale), yv = splat(N.xy_scale*yval1);             // get_noise_zval, src/mesh_gen.cpp:737-738
+		if (WARP) { // domain warping, src/mesh_gen.cpp:740-747
+			float const scale = 0.2f;
+			float2 const dx1 = gen_noise2<SIMPLEX, SHAPE>(make_float2(dadd(xv.x, 0.0), dadd(xv.y, 0.0)), make_float2(dadd(yv.x, 0.0), dadd(yv.y, 0.0)), N);
+			float2 const dy1 = gen_noise2<SIMPLEX, SHAPE>(make_float2(dadd(xv.x, 5.2), dadd(xv.y, 5.2)), make_float2(dadd(yv.x, 1.3), dadd(yv.y, 1.3)), N);
+			float2 const wx = add2(xv, mul2(dx1, scale)), wy = add2(yv, mul2(dy1, scale));
+			float2 const dx2 = gen_noise2<SIMPLEX, SHAPE>(make_float2(dadd(wx.x, 1.7), dadd(wx.y, 1.7)), make_float2(dadd(wy.x, 9.2), dadd(wy.y, 9.2)), N);
+			float2 const dy2 = gen_noise2<SIMPLEX, SHAPE>(make_float2(dadd(wx.x, 8.3), dadd(wx.y, 8.3)), make_float2(dadd(wy.x, 2.8), dadd(wy.y, 2.8)), N);
+			xv = add2(xv, mul2(dx2, scale)); yv = add2(yv, mul2(dy2, scale));
+		}
+		float2 const zz = gen_noise2<SIMPLEX, SHAPE>(xv, yv, N);
+		float const smy = (P.enable_glaciate && P.sine_on) ? cosf_lut(sin_tab, ((float)y*P.mdy + my0)*P.dy_inv*P.sm_freq) : 0.0f;
+		z0 = zz.x; z1 = zz.y;
+		if (P.need_postproc) {z0 = postproc_noise_zval(z0, P.h); z1 = postproc_noise_zval(z1, P.h);}
+		z0 = z0*N.hmap_scale; z1 = z1*N.hmap_scale;
+		float smx0 = 0.0f, smx1 = 0.0f;
+		if (P.enable_glaciate && P.sine_on) { // enable_glaciate() terms, src/mesh_gen.cpp:647-649
+			smx0 = P.sm_scale*cosf_lut(sin_tab, ((float)x*P.mdx + mx0)*P.dx_inv*P.sm_freq);
+			smx1 = P.sm_scale*cosf_lut(sin_tab, ((float)(x + 1)*P.mdx + mx0)*P.dx_inv*P.sm_freq);
+		}
+		z0 = glaciate_and_bias(z0, smx0, smy, xval.x, yval1, P, sin_tab);
+		z1 = glaciate_and_bias(z1, smx1, smy, xval.y, yval1, P, sin_tab);
+		float *o = out + (size_t)tile*nx*ny + (size_t)y*nx + x;
+		if (valid1 && ((reinterpret_cast<size_t>(o) & 7) == 0)) {*reinterpret_cast<float2 *>(o) = make_float2(z0, z1);}
+		else {o[0] = z0; if (valid1) {o[1] = z1;}}
+	}
+	if (mm) {
+		float const lo = fminf(valid0 ? z0 : INFINITY, valid1 ? z1 : INFINITY), hi = fmaxf(valid0 ? z0 : -INFINITY, valid1 ? z1 : -INFINITY);
+		block_minmax(lo, hi, mm + 2*tile);
+	}
+}
+
+template<bool SIMPLEX, bool WARP>
+void launch_noise2(int shape, dim3 grid, dim3 block, cudaStream_t st, float *out, unsigned nx, unsigned ny, unsigned y_off, float mx0, float my0,
+	const float2 *origins, const NoiseParams &N, const PostParams &P, const float *tab, unsigned *mm)
+{
+	switch (shape) {
+	case 1:  noise_grid2_kernel<SIMPLEX, WARP, 1><<<grid, block, 0, st>>>(out, nx, ny, y_off, mx0, my0, origins, N, P, tab, mm); break;
+	case 2:  noise_grid2_kernel<SIMPLEX, WARP, 2><<<grid, block, 0, st>>>(out, nx, ny, y_off, mx0, my0, origins, N, P, tab, mm); break;
+	default: noise_grid2_kernel<SIMPLEX, WARP, 0><<<grid, block, 0, st>>>(out, nx, ny, y_off, mx0, my0, origins, N, P, tab, mm); break;
+	}
 }
 
 // ------------------------------------------------------------------------------------------------ sine-table mode
@@ -386,6 +473,7 @@ int twi_heightgen(tw_ctx *ctx, const tw_grid2d *g, const tw_height_params *p, in
 			N.mag[i] = mag; N.freq[i] = freq; N.rx[i] = rx; N.ry[i] = ry;
 			mag *= 0.5f; freq *= 1.92f; rx *= 1.5f; ry *= 1.5f;
 		}
+		N.freq_last = N.freq[N.octaves > 0 ? N.octaves - 1 : 0]; N.rsum_last = N.rx[N.octaves > 0 ? N.octaves - 1 : 0] + N.ry[N.octaves > 0 ? N.octaves - 1 : 0];
 		N.xy_scale = 0.0007f*p->mesh_scale; // MESH_SCALE_FACTOR, src/mesh_gen.cpp:23,737
 		bool const simplex = (p->gen_mode == TW_MGEN_SIMPLEX || p->gen_mode == TW_MGEN_SIMPLEX_GPU || p->gen_mode == TW_MGEN_DWARP_GPU);
 		N.hmap_scale = (simplex ? 16.0f : 32.0f)*p->mesh_height*p->mesh_height_scale*p->mesh_scale_z_inv; // get_hmap_scale, :550-553
@@ -393,6 +481,16 @@ int twi_heightgen(tw_ctx *ctx, const tw_grid2d *g, const tw_height_params *p, in
 		unsigned const band_rows = band_rows_for(ctx, ny, nx, h_out_bands != nullptr && ntiles == 1);
 		for (unsigned r0 = 0; r0 < ny; r0 += band_rows) {
 			unsigned const r1 = (ny - r0 < band_rows) ? ny : r0 + band_rows;
+			static bool const use_scalar = (getenv("TW_NOISE_SCALAR") != nullptr); // A/B switch: one cell per thread, scalar FMUL/FADD
+			if (!use_scalar) { // two cells per thread on packed fp32x2 instructions
+				dim3 const block(32, 8, 1), grid((nx + 63)/64, (r1 - r0 + 7)/8, ntiles);
+				if (p->gen_mode == TW_MGEN_PERLIN) {launch_noise2<false, false>(p->gen_shape, grid, block, ctx->stream, d_out, nx, ny, r0, mx0, my0, d_tile_origins, N, P, ctx->d_sin_table, d_mm_ord);}
+				else if (warp) {launch_noise2<true, true >(p->gen_shape, grid, block, ctx->stream, d_out, nx, ny, r0, mx0, my0, d_tile_origins, N, P, ctx->d_sin_table, d_mm_ord);}
+				else           {launch_noise2<true, false>(p->gen_shape, grid, block, ctx->stream, d_out, nx, ny, r0, mx0, my0, d_tile_origins, N, P, ctx->d_sin_table, d_mm_ord);}
+				TW_LAUNCH_CHECK(ctx);
+				if (h_out_bands) {int const rc = band_copy(ctx, h_out_bands, d_out, nx, r0, r1); if (rc) return rc;}
+				continue;
+			}
 			dim3 const block(32, 8, 1), grid((nx + 31)/32, (r1 - r0 + 7)/8, ntiles);
 			if (p->gen_mode == TW_MGEN_PERLIN) {launch_noise<false, false>(p->gen_shape, grid, block, ctx->stream, d_out, nx, ny, r0, mx0, my0, d_tile_origins, N, P, ctx->d_sin_table, d_mm_ord);}
 			else if (warp) {launch_noise<true, true >(p->gen_shape, grid, block, ctx->stream, d_out, nx, ny, r0, mx0, my0, d_tile_origins, N, P, ctx->d_sin_table, d_mm_ord);}

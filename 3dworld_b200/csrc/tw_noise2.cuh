@@ -1,0 +1,126 @@
+// tw_noise2.cuh - two-cells-per-thread versions of glm::simplex(vec2) / glm::perlin(vec2) on Blackwell's packed fp32x2 instructions
+// (FFMA2 / FMUL2, sm_100+: `fma/mul.rn.f32x2`): one instruction performs the same IEEE operation on two independent cells, so the
+// reference's unfused multiply/add arithmetic needs half the issue slots (tools/mb/f32x2b.cu: FFMA2 issues at half rate, i.e. the fp32
+// lane throughput is unchanged - the gain is on the instruction-issue side, which is what bounds the scalar kernel).
+//
+// Every operation is the same IEEE round-to-nearest op as in tw_noise.cuh, element-wise (see that file for the exactness arguments of the
+// hand-placed fused forms). Additional equivalences used here:
+//   * a + b        == fma(a, 1, b),  a - b == fma(b, -1, a)   (products by +-1 are exact) - with the 1 hidden from ptxas, see below.
+// Packed instructions issue at half rate (one FFMA2 per two cycles per SM sub-partition, measured): the fp32 lane throughput is unchanged, but
+// they free half of the issue slots, which is what the scalar kernel was bound by (88 % issue, 65 % FMA pipe). floor() stays scalar FRND on
+// the XU pipe, which runs beside the FMA pipe.
+// The caller guarantees |lattice coordinate| < 2^22 (noise_lattice_in_range, needed by the division-free mod); otherwise it uses the
+// scalar path of tw_noise.cuh.
+#pragma once
+#include <cuda_runtime.h>
+#include "tw_noise.cuh"
+
+namespace twn2 {
+
+typedef float2 f2;
+typedef unsigned long long u64;
+
+// Multiplicative identities that ptxas must NOT know: ptxas 12.9 contracts mul.rn.f32x2 + add.rn.f32x2 into one FFMA2 even with explicit
+// .rn qualifiers and --fmad=false, and it also rewrites fma(x, 1.0, y) / fma(x, y, -0.0) back into add / mul first (verified on SASS,
+// tools/mb/). A fused multiply-add rounds once where the reference rounds twice, so every packed ADD here is issued as
+// fma(x, ONE, y) and every packed SUBTRACT as fma(y, -ONE, x) with ONE read from constant memory at run time: the products x*1 and y*(-1)
+// are exact, so the result is the IEEE sum, and because the multiplier is opaque there is no mul+add pattern left to contract.
+// The bit-exact parity tests (tests/test_gpu_heightgen.py) are the guard for this.
+__constant__ float2 TW_ONE2    = { 1.0f,  1.0f};
+__constant__ float2 TW_NEGONE2 = {-1.0f, -1.0f};
+
+__device__ __forceinline__ u64 pk(f2 a) {u64 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a.x), "f"(a.y)); return r;}
+__device__ __forceinline__ f2 unpk(u64 r) {f2 a; asm("mov.b64 {%0, %1}, %2;" : "=f"(a.x), "=f"(a.y) : "l"(r)); return a;}
+__device__ __forceinline__ f2 splat(float v) {return make_float2(v, v);}
+__device__ __forceinline__ f2 raw_fma(f2 a, f2 b, f2 c) {u64 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(pk(a)), "l"(pk(b)), "l"(pk(c))); return unpk(d);}
+__device__ __forceinline__ f2 mul2(f2 a, f2 b) {u64 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(pk(a)), "l"(pk(b))); return unpk(d);}
+__device__ __forceinline__ f2 mul2(f2 a, float b) {return mul2(a, splat(b));}
+__device__ __forceinline__ f2 add2(f2 a, f2 b) {return raw_fma(a, TW_ONE2, b);}                 // a + b  (see above)
+__device__ __forceinline__ f2 add2(f2 a, float b) {return raw_fma(a, TW_ONE2, splat(b));}
+__device__ __forceinline__ f2 sub2(f2 a, f2 b) {return raw_fma(b, TW_NEGONE2, a);}              // a - b
+__device__ __forceinline__ f2 rsub2(float a, f2 b) {return raw_fma(b, TW_NEGONE2, splat(a));}   // a - b, scalar a
+// genuine fused multiply-adds: only where the product is exact, so fused == unfused (see tw_noise.cuh); `a` is never itself a product
+__device__ __forceinline__ f2 fma2(f2 a, float b, f2 c) {return raw_fma(a, splat(b), c);}
+__device__ __forceinline__ f2 fma2(f2 a, float b, float c) {return raw_fma(a, splat(b), splat(c));}
+__device__ __forceinline__ f2 abs2(f2 a) {return make_float2(fabsf(a.x), fabsf(a.y));}
+__device__ __forceinline__ f2 max0_2(f2 a) {return make_float2(fmaxf(a.x, 0.0f), fmaxf(a.y, 0.0f));} // see twn::gmax0
+// floor stays on the XU pipe (FRND): it runs beside the FMA pipe, which the packed arithmetic already saturates
+__device__ __forceinline__ f2 floor2(f2 x) {return make_float2(floorf(x.x), floorf(x.y));}
+
+__device__ __forceinline__ f2 mod289(f2 x)  {f2 const t = floor2(mul2(x, 1.0f/289.0f)); return fma2(t, -289.0f, x);}
+__device__ __forceinline__ f2 permute(f2 x) {return mod289(mul2(fma2(x, 34.0f, 1.0f), x));}
+// glm::mod(a, 289) for integer |a| < 2^22 (see twn::mod_int289): q = floor(a*RN(1/289)) can be one short only when a is a multiple of 289,
+// leaving r = 289, which one conditional subtract folds back to 0.
+__device__ __forceinline__ f2 mod_int289(f2 a) {
+	f2 const r = fma2(floor2(mul2(a, 1.0f/289.0f)), -289.0f, a);
+	return make_float2((r.x >= 289.0f) ? r.x - 289.0f : r.x, (r.y >= 289.0f) ? r.y - 289.0f : r.y);
+}
+__device__ __forceinline__ f2 fract2(f2 x) {return sub2(x, floor2(x));}
+__device__ __forceinline__ f2 tinvsqrt(f2 r) {return rsub2(1.79284291400159f, mul2(r, 0.85373472095314f));}
+__device__ __forceinline__ f2 mix2(f2 x, f2 y, f2 a) {return add2(x, mul2(a, sub2(y, x)));}
+__device__ __forceinline__ f2 fade2(f2 t) { // (t*t*t)*(t*(t*6 - 15) + 10)
+	f2 const t3 = mul2(mul2(t, t), t);
+	return mul2(t3, add2(mul2(t, add2(mul2(t, 6.0f), -15.0f)), 10.0f));
+}
+
+// glm::simplex(vec2) for two positions (v.x = first cell, v.y = second cell of each operand)
+__device__ __forceinline__ f2 simplex2(f2 vx, f2 vy) {
+	float const Cx = 0.211324865405187f, Cy = 0.366025403784439f, Cz = -0.577350269189626f, Cw = 0.024390243902439f;
+	f2 const s = add2(mul2(vx, Cy), mul2(vy, Cy));
+	f2 ix = floor2(add2(vx, s)), iy = floor2(add2(vy, s));
+	f2 const t = add2(mul2(ix, Cx), mul2(iy, Cx));
+	f2 const x0x = add2(sub2(vx, ix), t), x0y = add2(sub2(vy, iy), t);
+	f2 const i1x = make_float2((x0x.x > x0y.x) ? 1.0f : 0.0f, (x0x.y > x0y.y) ? 1.0f : 0.0f);
+	f2 const i1y = rsub2(1.0f, i1x); // (1,0) or (0,1)
+	f2 const x12x = sub2(add2(x0x, Cx), i1x), x12y = sub2(add2(x0y, Cx), i1y), x12z = add2(x0x, Cz), x12w = add2(x0y, Cz);
+	ix = mod_int289(ix); iy = mod_int289(iy);
+	f2 const q0 = permute(iy), q1 = permute(add2(iy, i1y)), q2 = permute(add2(iy, 1.0f));
+	f2 const p0 = permute(add2(q0, ix)), p1 = permute(add2(add2(q1, ix), i1x)), p2 = permute(add2(add2(q2, ix), 1.0f));
+	f2 m0 = max0_2(rsub2(0.5f, add2(mul2(x0x, x0x), mul2(x0y, x0y))));
+	f2 m1 = max0_2(rsub2(0.5f, add2(mul2(x12x, x12x), mul2(x12y, x12y))));
+	f2 m2 = max0_2(rsub2(0.5f, add2(mul2(x12z, x12z), mul2(x12w, x12w))));
+	m0 = mul2(m0, m0); m1 = mul2(m1, m1); m2 = mul2(m2, m2);
+	m0 = mul2(m0, m0); m1 = mul2(m1, m1); m2 = mul2(m2, m2);
+	f2 const X0 = fma2(fract2(mul2(p0, Cw)), 2.0f, -1.0f), X1 = fma2(fract2(mul2(p1, Cw)), 2.0f, -1.0f), X2 = fma2(fract2(mul2(p2, Cw)), 2.0f, -1.0f);
+	f2 const h0 = add2(abs2(X0), -0.5f), h1 = add2(abs2(X1), -0.5f), h2 = add2(abs2(X2), -0.5f);
+	f2 const a0 = sub2(X0, floor2(add2(X0, 0.5f))), a1 = sub2(X1, floor2(add2(X1, 0.5f))), a2 = sub2(X2, floor2(add2(X2, 0.5f)));
+	m0 = mul2(m0, tinvsqrt(add2(mul2(a0, a0), mul2(h0, h0))));
+	m1 = mul2(m1, tinvsqrt(add2(mul2(a1, a1), mul2(h1, h1))));
+	m2 = mul2(m2, tinvsqrt(add2(mul2(a2, a2), mul2(h2, h2))));
+	f2 const gx = add2(mul2(a0, x0x), mul2(h0, x0y)), gy = add2(mul2(a1, x12x), mul2(h1, x12y)), gz = add2(mul2(a2, x12z), mul2(h2, x12w));
+	return mul2(add2(add2(mul2(m0, gx), mul2(m1, gy)), mul2(m2, gz)), 130.0f);
+}
+
+__device__ __forceinline__ void perlin2_corner(f2 ix, f2 iy, f2 &gx, f2 &gy) {
+	f2 const i = permute(add2(permute(ix), iy));
+	float const c41 = 1.0f/41.0f;
+	f2 const q0 = mul2(i, c41);
+	f2 const q = fma2(fma2(q0, -41.0f, i), c41, q0); // i/41, see twn::div41_small (fma(-q0,41,i) == fma(q0,-41,i)); both are genuine fmas
+	f2 const g = fma2(fract2(q), 2.0f, -1.0f);
+	gy = add2(abs2(g), -0.5f);
+	gx = sub2(g, floor2(add2(g, 0.5f)));
+	f2 const n = tinvsqrt(add2(mul2(gx, gx), mul2(gy, gy)));
+	gx = mul2(gx, n); gy = mul2(gy, n);
+}
+
+// glm::perlin(vec2) for two positions
+__device__ __forceinline__ f2 perlin2(f2 Px, f2 Py) {
+	f2 const flx = floor2(Px), fly = floor2(Py);
+	f2 const frx = sub2(Px, flx), fry = sub2(Py, fly);
+	f2 const Pfz = add2(frx, -1.0f), Pfw = add2(fry, -1.0f);
+	f2 const Pix = mod_int289(flx), Piy = mod_int289(fly), Piz = mod_int289(add2(flx, 1.0f)), Piw = mod_int289(add2(fly, 1.0f));
+	f2 g00x, g00y, g10x, g10y, g01x, g01y, g11x, g11y;
+	perlin2_corner(Pix, Piy, g00x, g00y);
+	perlin2_corner(Piz, Piy, g10x, g10y);
+	perlin2_corner(Pix, Piw, g01x, g01y);
+	perlin2_corner(Piz, Piw, g11x, g11y);
+	f2 const n00 = add2(mul2(g00x, frx), mul2(g00y, fry));
+	f2 const n10 = add2(mul2(g10x, Pfz), mul2(g10y, fry));
+	f2 const n01 = add2(mul2(g01x, frx), mul2(g01y, Pfw));
+	f2 const n11 = add2(mul2(g11x, Pfz), mul2(g11y, Pfw));
+	f2 const fdx = fade2(frx), fdy = fade2(fry);
+	f2 const nx0 = mix2(n00, n10, fdx), nx1 = mix2(n01, n11, fdx);
+	return mul2(mix2(nx0, nx1, fdy), 2.3f);
+}
+
+} // namespace twn2
