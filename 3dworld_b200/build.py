@@ -35,7 +35,7 @@ def build(force=False, verbose=False):
     os.makedirs(objdir, exist_ok=True)
     objs = []
     procs = []
-    flags = [f for f in NVCC_FLAGS if f != "--use_fast_math=false"]
+    flags = [f for f in NVCC_FLAGS if f != "--use_fast_math=false"] + os.environ.get("TW_EXTRA_NVCC_FLAGS", "").split()
     for src in SOURCES:
         obj = os.path.join(objdir, src.rsplit(".", 1)[0] + ".o")
         cmd = [nvcc()] + flags + (["-Xptxas", "-v"] if verbose else []) + ["-x", "cu", "-c", os.path.join(CSRC, src), "-o", obj]

@@ -159,6 +159,9 @@ noise_grid_kernel(float *__restrict__ out, unsigned nx, unsigned ny, unsigned y_
 	if (mm) {block_minmax(valid ? z : INFINITY, valid ? z : -INFINITY, mm + 2*tile);}
 }
 
+#ifndef TW_NOISE2_MIN_BLOCKS
+#define TW_NOISE2_MIN_BLOCKS 5
+#endif
 // ---- packed variant: two horizontally adjacent cells per thread on FFMA2/FMUL2/FADD2 (see tw_noise2.cuh) ----
 // |lattice coordinate| < 2^22 for every octave of this fBm call (needed by the packed floor / division-free mod); NaN-safe
 __device__ __forceinline__ bool noise_lattice_in_range(float2 xv, float2 yv, const NoiseParams &N) {
@@ -186,7 +189,7 @@ __device__ __forceinline__ float2 gen_noise2(float2 xv, float2 yv, const NoisePa
 __device__ __forceinline__ float dadd(float a, double b) {return (float)((double)a + b);} // float + double literal, rounded back (src/mesh_gen.cpp:742-745)
 
 template<bool SIMPLEX, bool WARP, int SHAPE>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, TW_NOISE2_MIN_BLOCKS)
 noise_grid2_kernel(float *__restrict__ out, unsigned nx, unsigned ny, unsigned y_off, float mx0_single, float my0_single, const float2 *__restrict__ tile_origins,
 	NoiseParams N, PostParams P, const float *__restrict__ sin_tab, unsigned *__restrict__ mm)
 {

@@ -46,6 +46,19 @@ __device__ __forceinline__ f2 abs2(f2 a) {return make_float2(fabsf(a.x), fabsf(a
 __device__ __forceinline__ f2 max0_2(f2 a) {return make_float2(fmaxf(a.x, 0.0f), fmaxf(a.y, 0.0f));} // see twn::gmax0
 // floor stays on the XU pipe (FRND): it runs beside the FMA pipe, which the packed arithmetic already saturates
 __device__ __forceinline__ f2 floor2(f2 x) {return make_float2(floorf(x.x), floorf(x.y));}
+// floor on the FMA pipe for small arguments (|x| < 2^22): x + M with M = 1.5*2^23 lies in [2^23, 2^24) where ulp = 1, so rounding the sum
+// toward -inf yields floor(x) + M exactly, and subtracting M is exact. Differs from floorf only for x = -0.0 (+0.0 instead of -0.0), which the
+// call sites cannot produce (their arguments are >= +0, or X + 0.5 with X = 2f - 1 >= -1, where -0.5 + 0.5 = +0.0). Used for a few of the
+// 16 floors of an evaluation to balance the XU pipe (FRND, quarter rate) against the FMA pipe. Issued as fma.rm(x, ONE, M) for the reason above.
+__device__ __forceinline__ f2 floor2_small(f2 x) {
+	u64 d; asm("fma.rm.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(pk(x)), "l"(pk(TW_ONE2)), "l"(pk(splat(12582912.0f))));
+	return raw_fma(unpk(d), TW_ONE2, splat(-12582912.0f));
+}
+#ifndef TW_MAGIC_FLOORS
+#define TW_MAGIC_FLOORS 0   // measured on B200: 0 -> 11.99 ms, 3 -> 12.21 ms, 6 -> 12.42 ms per 8192^2 step: the FMA pipe is the tighter one
+#endif
+__device__ __forceinline__ f2 floor2_ox(f2 x) {return (TW_MAGIC_FLOORS >= 3) ? floor2_small(x) : floor2(x);}   // floor(X + 0.5), X in [-1, 1)
+__device__ __forceinline__ f2 floor2_fr(f2 x) {return (TW_MAGIC_FLOORS >= 6) ? floor2_small(x) : floor2(x);}   // floor(p*C.w), p in [0, 289)
 
 __device__ __forceinline__ f2 mod289(f2 x)  {f2 const t = floor2(mul2(x, 1.0f/289.0f)); return fma2(t, -289.0f, x);}
 __device__ __forceinline__ f2 permute(f2 x) {return mod289(mul2(fma2(x, 34.0f, 1.0f), x));}
@@ -81,9 +94,10 @@ __device__ __forceinline__ f2 simplex2(f2 vx, f2 vy) {
 	f2 m2 = max0_2(rsub2(0.5f, add2(mul2(x12z, x12z), mul2(x12w, x12w))));
 	m0 = mul2(m0, m0); m1 = mul2(m1, m1); m2 = mul2(m2, m2);
 	m0 = mul2(m0, m0); m1 = mul2(m1, m1); m2 = mul2(m2, m2);
-	f2 const X0 = fma2(fract2(mul2(p0, Cw)), 2.0f, -1.0f), X1 = fma2(fract2(mul2(p1, Cw)), 2.0f, -1.0f), X2 = fma2(fract2(mul2(p2, Cw)), 2.0f, -1.0f);
+	f2 const t0 = mul2(p0, Cw), t1 = mul2(p1, Cw), t2 = mul2(p2, Cw);
+	f2 const X0 = fma2(sub2(t0, floor2_fr(t0)), 2.0f, -1.0f), X1 = fma2(sub2(t1, floor2_fr(t1)), 2.0f, -1.0f), X2 = fma2(sub2(t2, floor2_fr(t2)), 2.0f, -1.0f);
 	f2 const h0 = add2(abs2(X0), -0.5f), h1 = add2(abs2(X1), -0.5f), h2 = add2(abs2(X2), -0.5f);
-	f2 const a0 = sub2(X0, floor2(add2(X0, 0.5f))), a1 = sub2(X1, floor2(add2(X1, 0.5f))), a2 = sub2(X2, floor2(add2(X2, 0.5f)));
+	f2 const a0 = sub2(X0, floor2_ox(add2(X0, 0.5f))), a1 = sub2(X1, floor2_ox(add2(X1, 0.5f))), a2 = sub2(X2, floor2_ox(add2(X2, 0.5f)));
 	m0 = mul2(m0, tinvsqrt(add2(mul2(a0, a0), mul2(h0, h0))));
 	m1 = mul2(m1, tinvsqrt(add2(mul2(a1, a1), mul2(h1, h1))));
 	m2 = mul2(m2, tinvsqrt(add2(mul2(a2, a2), mul2(h2, h2))));
