@@ -297,12 +297,9 @@ sine_grid_kernel(float *__restrict__ out, unsigned nx, unsigned ny, const float 
 	__shared__ float Xs[SK][ST], Ys[SK][ST];
 	unsigned const x_base = blockIdx.x*ST, y_base = y_off + blockIdx.y*ST;
 	int const tid = threadIdx.x, tx = tid & 15, ty = tid >> 4; // 16 x 16 threads
-	float acc[4][4];
+	float2 acc2[4][2]; // acc2[a][h] = cells (row a, columns 2h and 2h+1 of this thread): packed fp32x2 accumulators (see tw_noise2.cuh)
 #pragma unroll
-	for (int a = 0; a < 4; ++a) {
-#pragma unroll
-		for (int b = 0; b < 4; ++b) {acc[a][b] = 0.0f;}
-	}
+	for (int a = 0; a < 4; ++a) {acc2[a][0] = make_float2(0.0f, 0.0f); acc2[a][1] = make_float2(0.0f, 0.0f);}
 	for (int k0 = start_ix; k0 < F_TABLE; k0 += SK) {
 		int const kn = min(SK, F_TABLE - k0);
 		__syncthreads();
@@ -320,10 +317,12 @@ sine_grid_kernel(float *__restrict__ out, unsigned nx, unsigned ny, const float 
 			for (int b = 0; b < 4; ++b) {xv[b] = Xs[kk][tx + 16*b];}
 			float4 const yv4 = *reinterpret_cast<const float4 *>(&Ys[kk][ty*4]);
 			float const yv[4] = {yv4.x, yv4.y, yv4.z, yv4.w};
+			float2 const x01 = make_float2(xv[0], xv[1]), x23 = make_float2(xv[2], xv[3]);
 #pragma unroll
-			for (int a = 0; a < 4; ++a) {
-#pragma unroll
-				for (int b = 0; b < 4; ++b) {acc[a][b] = acc[a][b] + xv[b]*yv[a];} // zval += xptr[i]*yptr[i]: separate mul and add (-fmad=false)
+			for (int a = 0; a < 4; ++a) { // zval += xptr[i]*yptr[i]: product rounded, then added (two roundings, as the reference); two cells per instruction
+				float2 const ya = twn2::splat(yv[a]);
+				acc2[a][0] = twn2::add2(twn2::mul2(x01, ya), acc2[a][0]);
+				acc2[a][1] = twn2::add2(twn2::mul2(x23, ya), acc2[a][1]);
 			}
 		}
 	}
@@ -337,7 +336,7 @@ sine_grid_kernel(float *__restrict__ out, unsigned nx, unsigned ny, const float 
 		for (int b = 0; b < 4; ++b) {
 			unsigned const x = x_base + tx + 16*b;
 			if (x >= nx) continue;
-			float z = acc[a][b];
+			float z = (b & 1) ? ((b >> 1) ? acc2[a][1].y : acc2[a][0].y) : ((b >> 1) ? acc2[a][1].x : acc2[a][0].x);
 			if (P.shape == 1) {z = (float)((double)fabsf(z) - 2.0);}       // apply_noise_shape_final, src/mesh_gen.cpp:564-571
 			else if (P.shape == 2) {z = (float)(3.5 - (double)fabsf(z));}
 			if (P.need_postproc) {z = postproc_noise_zval(z, P.h);}

@@ -10,6 +10,7 @@
 //   fused epilogue      val += z*zscale; clamp to [-1,1] (:340-341); optional attenuation (atten_at_edges / top / sphere).
 #include "tw_internal.h"
 #include "tw_noise.cuh"
+#include "tw_noise2.cuh"
 
 namespace {
 
@@ -101,17 +102,20 @@ voxel_sine_kernel(float *__restrict__ out, const float *__restrict__ xt, const f
 			xy[k][c] = (x0 + c < E.nx) ? __ldg(xt + (size_t)k*xpitch + x0 + c)*ys[k] : 0.0f;
 		}
 		__syncthreads();
-		float acc[VX];
+		float2 acc2[VX/2]; // packed fp32x2 accumulators: two x columns per instruction (see tw_noise2.cuh)
 #pragma unroll
-		for (int c = 0; c < VX; ++c) {acc[c] = 0.0f;}
+		for (int c = 0; c < VX/2; ++c) {acc2[c] = make_float2(0.0f, 0.0f);}
 #pragma unroll 4
 		for (int k = 0; k < NS; ++k) {
-			float const zv = zs[k][tz];
+			float2 const zv = twn2::splat(zs[k][tz]);
 			float4 const a = *reinterpret_cast<const float4 *>(&xy[k][0]), b = *reinterpret_cast<const float4 *>(&xy[k][4]);
-			float const xyv[VX] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-#pragma unroll
-			for (int c = 0; c < VX; ++c) {acc[c] = acc[c] + xyv[c]*zv;} // val += xv[k]*yv[k]*zv[k]: (xv*yv)*zv then add, no contraction
+			// val += xv[k]*yv[k]*zv[k]: (xv*yv)*zv rounded, then added (no contraction)
+			acc2[0] = twn2::add2(twn2::mul2(make_float2(a.x, a.y), zv), acc2[0]);
+			acc2[1] = twn2::add2(twn2::mul2(make_float2(a.z, a.w), zv), acc2[1]);
+			acc2[2] = twn2::add2(twn2::mul2(make_float2(b.x, b.y), zv), acc2[2]);
+			acc2[3] = twn2::add2(twn2::mul2(make_float2(b.z, b.w), zv), acc2[3]);
 		}
+		float const acc[VX] = {acc2[0].x, acc2[0].y, acc2[1].x, acc2[1].y, acc2[2].x, acc2[2].y, acc2[3].x, acc2[3].y};
 		if (z < E.nz) {
 #pragma unroll
 			for (int c = 0; c < VX; ++c) {
