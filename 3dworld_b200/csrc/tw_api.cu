@@ -439,6 +439,27 @@ int tw_erode(tw_ctx *ctx, float *heightmap, int xsize, int ysize, float min_zval
 	return tw_erode_tiles(ctx, heightmap, 1, xsize, ysize, nullptr, min_zval, num_iters, p);
 }
 
+int tw_erode_parallel(tw_ctx *ctx, float *heightmap, int xsize, int ysize, float min_zval, uint32_t num_iters, const tw_erosion_params *p, uint32_t num_threads) {
+	int rc = check_ctx(ctx); if (rc) return rc;
+	rc = finish_pending(ctx); if (rc) return rc;
+	if (!heightmap || !p) return tw_set_error(ctx, TW_ERR_ARG, "null argument");
+	if (xsize <= 0 || ysize <= 0) return tw_set_error(ctx, TW_ERR_ARG, "empty heightmap");
+	if (num_iters == 0 || p->erode_amount <= 0.0) {ctx->last_erosion_steps = 0; return TW_OK;} // src/erosion.cpp:16
+	size_t const n = (size_t)xsize*ysize;
+	bool const dev = tw_is_device_ptr(heightmap);
+	float *d_map = heightmap;
+	if (!dev) {
+		rc = tw_reserve(ctx, 0, n*sizeof(float)); if (rc) return rc;
+		d_map = (float *)ctx->d_scratch[0];
+		TW_CUDA(ctx, cudaMemcpyAsync(d_map, heightmap, n*sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+	}
+	rc = twi_erode_parallel(ctx, d_map, xsize, ysize, min_zval, num_iters, p, num_threads);
+	if (rc) return rc;
+	if (!dev) {TW_CUDA(ctx, cudaMemcpyAsync(heightmap, d_map, n*sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));}
+	TW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	return TW_OK;
+}
+
 // ------------------------------------------------------------------------------------------------ voxels
 int tw_voxel_fill(tw_ctx *ctx, const tw_voxel_params *vp, const float *rdata420, float *out) {
 	int rc = check_ctx(ctx); if (rc) return rc;

@@ -97,10 +97,14 @@ struct Rng {
 // different times stay converged at the top of the loop. G trades redundant ALU work (G = 32: every lane repeats the ~250-instruction
 // step for ONE map) against memory coalescing and in-flight parallelism (G = 1: no redundancy, but 32 unrelated maps per load
 // instruction and 32x more maps needed to fill the machine); twi_erode picks G from the number of heightmaps.
-template<int G>
+// SHARED (tw_erode_parallel): the reference's multi-threaded mode, `#pragma omp parallel for schedule(dynamic,1)` over the droplets of ONE
+// heightmap (src/erosion.cpp:66): `ntiles` groups play the OpenMP threads, each takes the next droplet index from an atomic counter (the
+// dynamic,1 schedule), reads bypass L1 (the CPU's caches are coherent) and the read-modify-writes are float atomics (the reference's are
+// unsynchronised). One group => exactly the serial order.
+template<int G, bool SHARED = false>
 __global__ void __launch_bounds__(128)
 droplet_kernel(float *__restrict__ padded, unsigned ntiles, int xsize, int ysize, unsigned num_iters, EParams E,
-	const float2 *__restrict__ dir_table, unsigned long long *__restrict__ steps_out, const unsigned *__restrict__ order)
+	const float2 *__restrict__ dir_table, unsigned long long *__restrict__ steps_out, const unsigned *__restrict__ order, unsigned *__restrict__ next_droplet = nullptr)
 {
 	constexpr int TPW = 32/G; // heightmaps per warp
 	int const lane = threadIdx.x & 31, sub = lane % G, grp = lane / G;
@@ -109,7 +113,7 @@ droplet_kernel(float *__restrict__ padded, unsigned ntiles, int xsize, int ysize
 	unsigned const tile = (slot < ntiles) ? (order ? __ldg(order + slot) : slot) : ntiles;
 	unsigned const gmask = (G == 32) ? 0xffffffffu : (((1u << (G & 31)) - 1u) << (grp*G));
 	int const NX = xsize + 2*PAD, NY = ysize + 2*PAD;
-	float *mh = padded + (size_t)((tile < ntiles) ? tile : 0)*NX*NY;
+	float *mh = padded + (SHARED ? (size_t)0 : (size_t)((tile < ntiles) ? tile : 0)*NX*NY);
 	float const Kq=10, Kw=0.001f, Kr=0.9f, Kd=0.02f, Ki=0.1f, minSlope=0.05f, g=20, Kg=g*2;
 	unsigned const MAX_PATH_LEN = 4u*(unsigned)NX*(unsigned)NY;
 	float const erode_amount = E.erode_amount;
@@ -121,6 +125,8 @@ droplet_kernel(float *__restrict__ padded, unsigned ntiles, int xsize, int ysize
 	float xp=0, zp=0, xf=0, zf=0, s=0, v=0, w=1, dx=0, dz=0, h=0, h00=0, h10=0, h01=0, h11=0;
 
 #define HMAP(x, y) mh[(size_t)NX*clampi((y), NY-1) + clampi((x), NX-1)]
+#define HLOAD(ptr)       (SHARED ? __ldcg(ptr) : *(ptr))
+#define HADD(ptr, delta) {if (SHARED) {atomicAdd((ptr), (delta));} else {*(ptr) += (delta);}}
 	// DEPOSIT(H): src/erosion.cpp:42-54; corner c of the 2x2 cell goes to lane c % G (inside cells are distinct => no aliasing between lanes)
 #define DEPOSIT(H) { \
 	_Pragma("unroll") \
@@ -128,20 +134,25 @@ droplet_kernel(float *__restrict__ padded, unsigned ntiles, int xsize, int ysize
 		int const X = xi + (c & 1), Z = zi + (c >> 1); \
 		float const W = ((c & 1) ? xf : (1-xf))*((c >> 1) ? zf : (1-zf)); \
 		float const delta = ds*erode_amount*W; \
-		if ((unsigned)X < (unsigned)NX && (unsigned)Z < (unsigned)NY) {mh[NX*Z + X] += delta;} \
+		if ((unsigned)X < (unsigned)NX && (unsigned)Z < (unsigned)NY) {HADD(&mh[NX*Z + X], delta)} \
 	} \
 	if (G > 1) {__syncwarp(gmask);} \
 	(H) += ds; }
 
 	for (;;) {
 		if (active && !in_droplet) { // next droplet of this group's heightmap (src/erosion.cpp:67-73)
+			if (SHARED) { // schedule(dynamic,1): the group's leader draws the next droplet
+				unsigned nd = 0;
+				if (sub == 0) {nd = atomicAdd(next_droplet, 1u);}
+				iter = __shfl_sync(gmask, nd, grp*G);
+			}
 			if (iter >= num_iters) {active = false;}
 			else {
 				rgen.s1 = (int)iter + 11; rgen.s2 = 79*(int)iter + 121;
 				xi = PAD + (rgen.rand()%xsize);
 				zi = PAD + (rgen.rand()%ysize);
 				xp=xi; zp=zi; xf=0; zf=0; s=0; v=0; w=1; dx=0; dz=0;
-				h=HMAP(xi, zi); h00=h; h10=HMAP(xi+1, zi); h01=HMAP(xi, zi+1); h11=HMAP(xi+1, zi+1);
+				h=HLOAD(&HMAP(xi, zi)); h00=h; h10=HLOAD(&HMAP(xi+1, zi)); h01=HLOAD(&HMAP(xi, zi+1)); h11=HLOAD(&HMAP(xi+1, zi+1));
 				numMoves = 0; in_droplet = true; ++iter;
 			}
 		}
@@ -168,9 +179,9 @@ droplet_kernel(float *__restrict__ padded, unsigned ntiles, int xsize, int ysize
 			float nh00, nh10, nh01, nh11;
 			if ((unsigned)nxi < (unsigned)(NX-1) && (unsigned)nzi < (unsigned)(NY-1)) { // common case: no clamping needed
 				float const *q = mh + (nzi*NX + nxi);
-				nh00 = q[0]; nh10 = q[1]; q += NX; nh01 = q[0]; nh11 = q[1];
+				nh00 = HLOAD(q); nh10 = HLOAD(q + 1); q += NX; nh01 = HLOAD(q); nh11 = HLOAD(q + 1);
 			}
-			else {nh00=HMAP(nxi, nzi); nh10=HMAP(nxi+1, nzi); nh01=HMAP(nxi, nzi+1); nh11=HMAP(nxi+1, nzi+1);}
+			else {nh00=HLOAD(&HMAP(nxi, nzi)); nh10=HLOAD(&HMAP(nxi+1, nzi)); nh01=HLOAD(&HMAP(nxi, nzi+1)); nh11=HLOAD(&HMAP(nxi+1, nzi+1));}
 			float const nh=(nh00*(1-nxf)+nh10*nxf)*(1-nzf)+(nh01*(1-nxf)+nh11*nxf)*nzf;
 			if (smax(smax(nh00, nh10), smax(nh01, nh11)) < E.wpz_minus_half_dxy) {in_droplet = false; continue;} // reached ocean water
 
@@ -212,7 +223,7 @@ droplet_kernel(float *__restrict__ padded, unsigned ntiles, int xsize, int ysize
 						if (!(wgt<=0)) {
 							wgt*=0.1591549430918953f;
 							float const delta=ds*erode_amount*wgt;
-							if (interior) {mh[NX*z + x]-=delta;} else {HMAP(x, z)-=delta;}
+							if (interior) {HADD(&mh[NX*z + x], -delta)} else {HADD(&HMAP(x, z), -delta)}
 						}
 					}
 				}
@@ -225,7 +236,7 @@ droplet_kernel(float *__restrict__ padded, unsigned ntiles, int xsize, int ysize
 							if (wgt<=0) continue;
 							wgt*=0.1591549430918953f;
 							float const delta=ds*erode_amount*wgt;
-							HMAP(x, z)-=delta;
+							HADD(&HMAP(x, z), -delta)
 						}
 					}
 				}
@@ -240,6 +251,8 @@ droplet_kernel(float *__restrict__ padded, unsigned ntiles, int xsize, int ysize
 		}
 	}
 #undef HMAP
+#undef HLOAD
+#undef HADD
 #undef DEPOSIT
 	if (sub == 0 && steps_out && steps) {atomicAdd(steps_out, steps);}
 }
@@ -248,6 +261,12 @@ template<int G>
 void launch_droplets(cudaStream_t st, float *d_pad, unsigned nt, int xsize, int ysize, unsigned num_iters, EParams const &E, const float2 *dir, unsigned long long *d_steps, const unsigned *order) {
 	unsigned const warps_per_block = 2, tiles_per_block = warps_per_block*(32/G);
 	droplet_kernel<G><<<(nt + tiles_per_block - 1)/tiles_per_block, 32*warps_per_block, 0, st>>>(d_pad, nt, xsize, ysize, num_iters, E, dir, d_steps, order);
+}
+
+template<int G>
+void launch_droplets_shared(cudaStream_t st, float *d_pad, unsigned ngroups, int xsize, int ysize, unsigned num_iters, EParams const &E, const float2 *dir, unsigned long long *d_steps, unsigned *d_next) {
+	unsigned const warps_per_block = 2, groups_per_block = warps_per_block*(32/G);
+	droplet_kernel<G, true><<<(ngroups + groups_per_block - 1)/groups_per_block, 32*warps_per_block, 0, st>>>(d_pad, ngroups, xsize, ysize, num_iters, E, dir, d_steps, nullptr, d_next);
 }
 
 // lanes per heightmap: the smallest group that still gives ~12 warps per SM (148 SMs), see the kernel comment
@@ -325,6 +344,45 @@ uint32_t twi_erode_chunk_for(size_t budget, uint32_t ntiles, int xsize, int ysiz
 	if (c > ntiles) c = ntiles;
 	if (c > 65535) c = 65535; // gridDim.z limit
 	return (uint32_t)c;
+}
+
+// tw_erode_parallel: `num_threads` droplets of ONE heightmap in flight (0 = as many groups as keep the GPU busy)
+int twi_erode_parallel(tw_ctx *ctx, float *d_map, int xsize, int ysize, float min_zval, uint32_t num_iters, const tw_erosion_params *p, uint32_t num_threads) {
+	ctx->last_erosion_steps = 0;
+	if (num_iters == 0 || p->erode_amount <= 0.0) return TW_OK; // erosion disabled, src/erosion.cpp:16
+	if (xsize <= 0 || ysize <= 0) return tw_set_error(ctx, TW_ERR_ARG, "tw_erode_parallel: empty heightmap");
+	if (!ctx->d_dir_table) return tw_set_error(ctx, TW_ERR_STATE, "tw_set_sin_table() has not been called");
+	int rc = tw_reserve(ctx, 2, 4096);
+	if (rc) return rc;
+	unsigned long long *d_steps = (unsigned long long *)((char *)ctx->d_scratch[2] + 2048);
+	unsigned *d_next = (unsigned *)(d_steps + 1);
+	TW_CUDA(ctx, cudaMemsetAsync(d_steps, 0, 16, ctx->stream));
+	int const NX = xsize + 2*PAD, NY = ysize + 2*PAD;
+	rc = tw_reserve(ctx, 1, (size_t)NX*NY*sizeof(float));
+	if (rc) return rc;
+	float *d_pad = (float *)ctx->d_scratch[1];
+	EParams const E = make_eparams(p);
+	cudaStream_t const st = ctx->stream;
+	pad_kernel<<<dim3((NX + 255)/256, NY, 1), 256, 0, st>>>(d_map, d_pad, xsize, ysize, NX, NY, E.wpz_minus_half_dxy, nullptr);
+	TW_LAUNCH_CHECK(ctx);
+	unsigned groups = num_threads ? num_threads : 65536u; // auto: the 65536-map operating point of pick_group() (8 lanes per droplet)
+	if (groups > num_iters) {groups = num_iters;}
+	switch (pick_group(groups)) {
+	case 1:  launch_droplets_shared<1 >(st, d_pad, groups, xsize, ysize, num_iters, E, ctx->d_dir_table, d_steps, d_next); break;
+	case 2:  launch_droplets_shared<2 >(st, d_pad, groups, xsize, ysize, num_iters, E, ctx->d_dir_table, d_steps, d_next); break;
+	case 4:  launch_droplets_shared<4 >(st, d_pad, groups, xsize, ysize, num_iters, E, ctx->d_dir_table, d_steps, d_next); break;
+	case 8:  launch_droplets_shared<8 >(st, d_pad, groups, xsize, ysize, num_iters, E, ctx->d_dir_table, d_steps, d_next); break;
+	case 16: launch_droplets_shared<16>(st, d_pad, groups, xsize, ysize, num_iters, E, ctx->d_dir_table, d_steps, d_next); break;
+	default: launch_droplets_shared<32>(st, d_pad, groups, xsize, ysize, num_iters, E, ctx->d_dir_table, d_steps, d_next); break;
+	}
+	TW_LAUNCH_CHECK(ctx);
+	unpad_kernel<<<dim3((xsize + 255)/256, ysize, 1), 256, 0, st>>>(d_pad, d_map, xsize, ysize, NX, NY, nullptr, min_zval);
+	TW_LAUNCH_CHECK(ctx);
+	unsigned long long h_steps = 0;
+	TW_CUDA(ctx, cudaMemcpyAsync(&h_steps, d_steps, sizeof(h_steps), cudaMemcpyDeviceToHost, st));
+	TW_CUDA(ctx, cudaStreamSynchronize(st));
+	ctx->last_erosion_steps = h_steps;
+	return TW_OK;
 }
 
 int twi_erode(tw_ctx *ctx, float *d_maps, uint32_t ntiles, int xsize, int ysize, const float *d_min_zvals, float min_zval_all,

@@ -194,6 +194,16 @@ inline void apply_erosion(float *heightmap, int xsize, int ysize, float min_zval
 	if (rc != TW_OK) {detail::fail(rc, "apply_erosion", c);}
 }
 
+// the same with the reference's OpenMP semantics (`#pragma omp parallel for schedule(dynamic,1)`, src/erosion.cpp:66): num_threads droplets in
+// flight on the one heightmap, order-dependent result like the reference's; num_threads = 1 equals apply_erosion(), 0 = fill the GPU
+inline void apply_erosion_parallel(float *heightmap, int xsize, int ysize, float min_zval, unsigned num_iters, unsigned num_threads = 0) {
+	tw_erosion_params const e = erosion_params_from_globals();
+	if (num_iters == 0 || e.erode_amount <= 0.0) return;
+	tw_ctx *c = ctx();
+	int const rc = tw_erode_parallel(c, heightmap, xsize, ysize, min_zval, num_iters, &e, num_threads);
+	if (rc != TW_OK) {detail::fail(rc, "apply_erosion_parallel", c);}
+}
+
 // Height fill + per-tile erosion of tile_t::create_zvals for a batch of tiles (origins = tile x1,y1 pairs; zvals_out = ntiles*zvsize^2 floats)
 inline void create_zvals_batch(const int32_t *origins_xy, unsigned ntiles, unsigned zvsize, float dx, float dy, unsigned erosion_iters_tt, float *zvals_out, tw_minmax *mm = nullptr) {
 	scene_globals const &g = globals();
