@@ -138,8 +138,25 @@ def cpu_baseline_leg():
     run()
     dt = time.perf_counter() - t0
     what = "unmodified reference objects (oracle/_ref)" if kind == "reference" else "plain-C oracle port"
-    return {"value": nx * ny / dt, "unit": "cells/s", "cores": cores, "kind": kind,
-            "sample": "%s, %dx%d-cell window of the 8192^2 grid, OpenMP %d threads" % (what, nx, ny, cores)}
+    res = {"value": nx * ny / dt, "unit": "cells/s", "cores": cores, "kind": kind,
+           "sample": "%s, %dx%d-cell window of the 8192^2 grid, OpenMP %d threads" % (what, nx, ny, cores)}
+    if kind == "reference":   # secondary: the reference's apply_erosion on one 2048^2 map (its OpenMP droplet loop on all threads, and 1 thread)
+        try:
+            import numpy as np
+            import refapi as R
+            n, iters = 2048, 200000
+            R.setup(mode=1, freq_filter=1, seed=1, zmax_est=2.3, hmap=HM_CFG)
+            z = R.heightgen(-n / 2, -n / 2, R.lib().ref_get_dx(), R.lib().ref_get_dy(), n, n, 0, 1)
+            zmin, zmax = float(z.min()), float(z.max())
+            for label, thr in (("openmp_%d_threads" % cores, cores), ("1_thread", 1)):
+                R.lib().ref_set_threads(thr)
+                t0 = time.perf_counter()
+                R.apply_erosion(z, zmin, iters, erode_amount=1.0, water_plane_z=zmin + 0.2 * (zmax - zmin), zmin=zmin, zmax=zmax, clip_hd1=0.083)
+                res["erosion_2048_map_%s_droplets_per_s" % label] = iters / (time.perf_counter() - t0)
+            R.lib().ref_set_threads(cores)
+        except Exception as e:   # noqa: BLE001 - secondary number only
+            res["erosion_note"] = "reference erosion timing failed: %s" % e
+    return res
 
 
 def main():
@@ -340,6 +357,26 @@ def extra_measurements(tw, scene, ctx, stream, torch):
     res["tiles_separate_calls_s"] = t_gen + t_ero
     res["tiles_fused_cells_per_s"] = nt * zv * zv / t_fused
     res["tiles_fused_droplets_per_s"] = nt * 1000 / t_fused
+    del tiles
+    # one big heightmap (BASELINE config 3 shape, 8192^2 simplex): the serial droplet order (bit-exact, one warp) and the reference's
+    # OpenMP mode (tw_erode_parallel: droplets in flight like `#pragma omp parallel for schedule(dynamic,1)`, order-dependent like the reference)
+    cfg = scene.SceneConfig(mesh_gen_mode=1, mesh_freq_filter=1, mesh_seed=1, hmap=HM_CFG, zmax_est=2.3)
+    ep = cfg.erosion_params()
+    base = torch.empty((N_TILE, N_TILE), dtype=torch.float32, device="cuda")
+    _, (zmin, _zmax) = ctx.heightgen_2d(cfg.heightmap_grid(N_TILE, N_TILE), cfg.height_params(), out=base, want_minmax=True)
+    work = torch.empty_like(base)
+    for name, iters, fn in (("single_map_8192_serial_1000_droplets", 1000, lambda w, n: ctx.erode(w, zmin, n, ep)),
+                            ("single_map_8192_openmp_mode_1e6_droplets", 1000000, lambda w, n: ctx.erode_parallel(w, zmin, n, ep, 0))):
+        for rep in range(2):
+            work.copy_(base)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            fn(work, iters)
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+        res[name + "_s"] = dt
+        res[name + "_per_s"] = iters / dt
+        res[name + "_moves_per_s"] = ctx.last_erosion_steps / dt
     return res
 
 
