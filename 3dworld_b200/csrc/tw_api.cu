@@ -435,6 +435,31 @@ int tw_create_zvals_batch(tw_ctx *ctx, const int32_t *origins_xy, uint32_t ntile
 	return TW_OK;
 }
 
+// ------------------------------------------------------------------------------------------------ point queries
+int tw_eval_points(tw_ctx *ctx, const float *xy, size_t n, const tw_height_params *p, const tw_point_query *q, float *out) {
+	int rc = check_ctx(ctx); if (rc) return rc;
+	rc = finish_pending(ctx); if (rc) return rc;
+	if (!xy || !p || !q || !out) return tw_set_error(ctx, TW_ERR_ARG, "null argument");
+	if (n == 0) return TW_OK;
+	if (!ctx->have_sin) return tw_set_error(ctx, TW_ERR_STATE, "tw_set_sin_table() has not been called");
+	bool const dev_in = tw_is_device_ptr(xy), dev_out = tw_is_device_ptr(out);
+	size_t const in_bytes = (2*n*sizeof(float) + 255) & ~(size_t)255, out_bytes = n*sizeof(float);
+	size_t const need = (dev_in ? 0 : in_bytes) + (dev_out ? 0 : out_bytes);
+	if (need) {rc = tw_reserve(ctx, 0, need); if (rc) return rc;}
+	const float *d_xy = xy; float *d_out = out;
+	char *sp = (char *)ctx->d_scratch[0];
+	if (!dev_in) {
+		d_xy = (const float *)sp; sp += in_bytes;
+		TW_CUDA(ctx, cudaMemcpyAsync((void *)d_xy, xy, 2*n*sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+	}
+	if (!dev_out) {d_out = (float *)sp;}
+	rc = twi_eval_points(ctx, d_xy, n, p, q, d_out);
+	if (rc) return rc;
+	if (!dev_out) {TW_CUDA(ctx, cudaMemcpyAsync(out, d_out, out_bytes, cudaMemcpyDeviceToHost, ctx->stream));}
+	TW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	return TW_OK;
+}
+
 int tw_erode(tw_ctx *ctx, float *heightmap, int xsize, int ysize, float min_zval, uint32_t num_iters, const tw_erosion_params *p) {
 	return tw_erode_tiles(ctx, heightmap, 1, xsize, ysize, nullptr, min_zval, num_iters, p);
 }

@@ -123,6 +123,23 @@ __device__ __forceinline__ float gen_noise(float xv, float yv, const NoiseParams
 }
 
 template<bool SIMPLEX, bool WARP, int SHAPE>
+__device__ __forceinline__ float get_noise_zval(float xval, float yval, const NoiseParams &N, const PostParams &P) { // src/mesh_gen.cpp:734-751
+	float xv = N.xy_scale*xval, yv = N.xy_scale*yval; // :737-738
+	if (WARP) { // domain warping, src/mesh_gen.cpp:740-747 ("xv+5.2" etc. are float+double adds rounded back to float)
+		float const scale = 0.2f;
+		float const dx1 = gen_noise<SIMPLEX, SHAPE>((float)((double)xv + 0.0), (float)((double)yv + 0.0), N);
+		float const dy1 = gen_noise<SIMPLEX, SHAPE>((float)((double)xv + 5.2), (float)((double)yv + 1.3), N);
+		float const wx = xv + scale*dx1, wy = yv + scale*dy1;
+		float const dx2 = gen_noise<SIMPLEX, SHAPE>((float)((double)wx + 1.7), (float)((double)wy + 9.2), N);
+		float const dy2 = gen_noise<SIMPLEX, SHAPE>((float)((double)wx + 8.3), (float)((double)wy + 2.8), N);
+		xv += scale*dx2; yv += scale*dy2;
+	}
+	float z = gen_noise<SIMPLEX, SHAPE>(xv, yv, N);
+	if (P.need_postproc) {z = postproc_noise_zval(z, P.h);}
+	return z*N.hmap_scale;
+}
+
+template<bool SIMPLEX, bool WARP, int SHAPE>
 __global__ void __launch_bounds__(256)
 noise_grid_kernel(float *__restrict__ out, unsigned nx, unsigned ny, unsigned y_off, float mx0_single, float my0_single, const float2 *__restrict__ tile_origins,
 	NoiseParams N, PostParams P, const float *__restrict__ sin_tab, unsigned *__restrict__ mm)
@@ -135,19 +152,7 @@ noise_grid_kernel(float *__restrict__ out, unsigned nx, unsigned ny, unsigned y_
 	if (valid) {
 		// eval_index: xval((x*mdx + mx0)*DX_VAL_INV), src/mesh_gen.cpp:762
 		float const xval = ((float)x*P.mdx + mx0)*P.dx_inv, yval = ((float)y*P.mdy + my0)*P.dy_inv;
-		float xv = N.xy_scale*xval, yv = N.xy_scale*yval; // get_noise_zval, src/mesh_gen.cpp:737-738
-		if (WARP) { // domain warping, src/mesh_gen.cpp:740-747 ("xv+5.2" etc. are float+double adds rounded back to float)
-			float const scale = 0.2f;
-			float const dx1 = gen_noise<SIMPLEX, SHAPE>((float)((double)xv + 0.0), (float)((double)yv + 0.0), N);
-			float const dy1 = gen_noise<SIMPLEX, SHAPE>((float)((double)xv + 5.2), (float)((double)yv + 1.3), N);
-			float const wx = xv + scale*dx1, wy = yv + scale*dy1;
-			float const dx2 = gen_noise<SIMPLEX, SHAPE>((float)((double)wx + 1.7), (float)((double)wy + 9.2), N);
-			float const dy2 = gen_noise<SIMPLEX, SHAPE>((float)((double)wx + 8.3), (float)((double)wy + 2.8), N);
-			xv += scale*dx2; yv += scale*dy2;
-		}
-		z = gen_noise<SIMPLEX, SHAPE>(xv, yv, N);
-		if (P.need_postproc) {z = postproc_noise_zval(z, P.h);}
-		z = z*N.hmap_scale;
+		z = get_noise_zval<SIMPLEX, WARP, SHAPE>(xval, yval, N, P);
 		float smx = 0.0f, smy = 0.0f;
 		if (P.enable_glaciate && P.sine_on) { // enable_glaciate() terms, src/mesh_gen.cpp:647-649, evaluated per cell instead of tabulated
 			smx = P.sm_scale*cosf_lut(sin_tab, ((float)x*P.mdx + mx0)*P.dx_inv*P.sm_freq);
@@ -435,14 +440,7 @@ static int band_copy(tw_ctx *ctx, float *h_out, const float *d_out, unsigned nx,
 
 // h_out_bands != nullptr (single grid only): the grid is issued in row bands and each finished band is copied to the host buffer on a second
 // stream while the next band computes; ctx->stream finally waits for the copies, so an event recorded on it covers the whole result.
-int twi_heightgen(tw_ctx *ctx, const tw_grid2d *g, const tw_height_params *p, int enable_glaciate, int min_start_sin,
-                  const float2 *d_tile_origins, uint32_t ntiles, float *d_out, unsigned *d_mm_ord, float *h_out_bands)
-{
-	unsigned const nx = g->nx, ny = g->ny;
-	float const dx = g->dx, dy = g->dy;
-	float const mx0 = dx*g->x0, my0 = dy*g->y0; // src/mesh_gen.cpp:591
-	if (ntiles == 0) ntiles = 1;
-
+static PostParams make_post_params(const tw_height_params *p, int enable_glaciate, float dx, float dy) {
 	PostParams P;
 	memset(&P, 0, sizeof(P));
 	P.h = p->hmap;
@@ -462,23 +460,41 @@ int twi_heightgen(tw_ctx *ctx, const tw_grid2d *g, const tw_height_params *p, in
 	P.volcano_freq = P.volcano_on ? p->mesh_scale/p->hmap.volcano_width : 0.0f;
 	P.mesh_scale_z_inv = p->mesh_scale_z_inv;
 	P.mdx = dx; P.mdy = dy; P.dx_inv = p->dx_val_inv; P.dy_inv = p->dy_val_inv;
+	return P;
+}
+
+static bool make_noise_params(const tw_height_params *p, NoiseParams &N, bool &simplex) {
+	memset(&N, 0, sizeof(N));
+	int const start = p->start_eval_sin;
+	if (start < 0 || start > F_TABLE) return false;
+	N.octaves = 9 - start/10;
+	N.gen_shape = p->gen_shape;
+	float mag = 1.0f, freq = 1.0f, rx = p->rx, ry = p->ry;
+	for (int i = 0; i < 9; ++i) { // loop-carried constants of gen_noise, src/mesh_gen.cpp:725-728
+		N.mag[i] = mag; N.freq[i] = freq; N.rx[i] = rx; N.ry[i] = ry;
+		mag *= 0.5f; freq *= 1.92f; rx *= 1.5f; ry *= 1.5f;
+	}
+	N.freq_last = N.freq[N.octaves > 0 ? N.octaves - 1 : 0]; N.rsum_last = N.rx[N.octaves > 0 ? N.octaves - 1 : 0] + N.ry[N.octaves > 0 ? N.octaves - 1 : 0];
+	N.xy_scale = 0.0007f*p->mesh_scale; // MESH_SCALE_FACTOR, src/mesh_gen.cpp:23,737
+	simplex = (p->gen_mode == TW_MGEN_SIMPLEX || p->gen_mode == TW_MGEN_SIMPLEX_GPU || p->gen_mode == TW_MGEN_DWARP_GPU);
+	N.hmap_scale = (simplex ? 16.0f : 32.0f)*p->mesh_height*p->mesh_height_scale*p->mesh_scale_z_inv; // get_hmap_scale, :550-553
+	return true;
+}
+
+int twi_heightgen(tw_ctx *ctx, const tw_grid2d *g, const tw_height_params *p, int enable_glaciate, int min_start_sin,
+                  const float2 *d_tile_origins, uint32_t ntiles, float *d_out, unsigned *d_mm_ord, float *h_out_bands)
+{
+	unsigned const nx = g->nx, ny = g->ny;
+	float const dx = g->dx, dy = g->dy;
+	float const mx0 = dx*g->x0, my0 = dy*g->y0; // src/mesh_gen.cpp:591
+	if (ntiles == 0) ntiles = 1;
+
+	PostParams const P = make_post_params(p, enable_glaciate, dx, dy);
 
 	if (p->gen_mode != TW_MGEN_SINE) {
 		NoiseParams N;
-		memset(&N, 0, sizeof(N));
-		int const start = p->start_eval_sin;
-		if (start < 0 || start > F_TABLE) return tw_set_error(ctx, TW_ERR_ARG, "start_eval_sin %d out of range", start);
-		N.octaves = 9 - start/10;
-		N.gen_shape = p->gen_shape;
-		float mag = 1.0f, freq = 1.0f, rx = p->rx, ry = p->ry;
-		for (int i = 0; i < 9; ++i) { // loop-carried constants of gen_noise, src/mesh_gen.cpp:725-728
-			N.mag[i] = mag; N.freq[i] = freq; N.rx[i] = rx; N.ry[i] = ry;
-			mag *= 0.5f; freq *= 1.92f; rx *= 1.5f; ry *= 1.5f;
-		}
-		N.freq_last = N.freq[N.octaves > 0 ? N.octaves - 1 : 0]; N.rsum_last = N.rx[N.octaves > 0 ? N.octaves - 1 : 0] + N.ry[N.octaves > 0 ? N.octaves - 1 : 0];
-		N.xy_scale = 0.0007f*p->mesh_scale; // MESH_SCALE_FACTOR, src/mesh_gen.cpp:23,737
-		bool const simplex = (p->gen_mode == TW_MGEN_SIMPLEX || p->gen_mode == TW_MGEN_SIMPLEX_GPU || p->gen_mode == TW_MGEN_DWARP_GPU);
-		N.hmap_scale = (simplex ? 16.0f : 32.0f)*p->mesh_height*p->mesh_height_scale*p->mesh_scale_z_inv; // get_hmap_scale, :550-553
+		bool simplex = false;
+		if (!make_noise_params(p, N, simplex)) return tw_set_error(ctx, TW_ERR_ARG, "start_eval_sin %d out of range", p->start_eval_sin);
 		bool const warp = (p->gen_mode == TW_MGEN_DWARP_GPU);
 		unsigned const band_rows = band_rows_for(ctx, ny, nx, h_out_bands != nullptr && ntiles == 1);
 		for (unsigned r0 = 0; r0 < ny; r0 += band_rows) {
@@ -535,4 +551,105 @@ int twi_heightgen(tw_ctx *ctx, const tw_grid2d *g, const tw_height_params *p, in
 		if (h_out_bands) {int const rc = band_copy(ctx, h_out_bands, d_out, nx, r0, r1); if (rc) return rc;}
 	}
 	return h_out_bands ? band_join(ctx) : TW_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ point queries
+// eval_mesh_sin_terms (src/mesh_gen.cpp:797-805), eval_mesh_sin_terms_scaled (:807-813) and the procedural branch of get_exact_zval
+// (:816-847) for a batch of arbitrary points: one thread per point; the 90 sine-table rows are read from constant-like global memory
+// (uniform across the warp), the two SINF look-ups per term hit the 256 KB table in L1/L2.
+struct PointParams {
+	int   kind, sine_mode, start, glaciate;
+	float xy_scale, mesh_scale, x_scene_size, y_scene_size;
+	float half_mx, half_my;      // float(MESH_X_SIZE >> 1), float(MESH_Y_SIZE >> 1)
+	float xoff, yoff;            // float(xoff2), float(yoff2) or 0 when no_xyoff
+	float sine_mag, sine_bias, sine_freq; // apply_mesh_sine: hmap.sine_mag, hmap.sine_bias, mesh_scale*hmap.sine_freq
+};
+
+__device__ __forceinline__ float eval_mesh_sin_terms(float xv, float yv, const float *__restrict__ T, const float *__restrict__ tab, int start) {
+	float zval = 0.0f;
+	for (int k = start; k < F_TABLE; ++k) { // zval += stk[0]*SINF(stk[3]*yv + stk[1])*SINF(stk[4]*xv + stk[2]), left to right
+		const float *stk = T + 5*k;
+		float const t = __ldg(stk)*sinf_lut(tab, __ldg(stk + 3)*yv + __ldg(stk + 1));
+		zval += t*sinf_lut(tab, __ldg(stk + 4)*xv + __ldg(stk + 2));
+	}
+	return zval;
+}
+
+template<bool SIMPLEX, bool WARP, int SHAPE>
+__global__ void __launch_bounds__(256)
+points_kernel(const float2 *__restrict__ xy, size_t n, float *__restrict__ out, PointParams Q, NoiseParams N, PostParams P,
+	const float *__restrict__ T, const float *__restrict__ tab)
+{
+	size_t const i = (size_t)blockIdx.x*blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	float2 const pt = __ldg(xy + i);
+	if (Q.kind == TW_PQ_SIN_TERMS) {out[i] = eval_mesh_sin_terms(pt.x, pt.y, T, tab, Q.start); return;}
+	float xval = pt.x, yval = pt.y;
+	if (Q.kind == TW_PQ_EXACT_ZVAL) { // real -> index space, src/mesh_gen.cpp:818-819,826-829 (the "+ 0.5" double add rounds like the float add)
+		xval = (pt.x + Q.x_scene_size)*P.dx_inv + 0.5f + Q.xoff;
+		yval = (pt.y + Q.y_scene_size)*P.dy_inv + 0.5f + Q.yoff;
+	}
+	float const xv = Q.xy_scale*(xval - Q.half_mx), yv = Q.xy_scale*(yval - Q.half_my); // :808
+	float z;
+	if (!Q.sine_mode) {z = get_noise_zval<SIMPLEX, WARP, SHAPE>(xv, yv, N, P);}
+	else {
+		z = eval_mesh_sin_terms(Q.mesh_scale*xv, Q.mesh_scale*yv, T, tab, Q.start)*P.mesh_scale_z_inv;
+		if (P.shape == 1) {z = (float)((double)fabsf(z) - 2.0);}       // apply_noise_shape_final, src/mesh_gen.cpp:564-571
+		else if (P.shape == 2) {z = (float)(3.5 - (double)fabsf(z));}
+		z = postproc_noise_zval(z, P.h);
+	}
+	if (Q.kind == TW_PQ_EXACT_ZVAL) {
+		if (Q.glaciate) { // apply_glaciate, :380-385
+			float const relh = (z + P.zmax_est)*P.zmax_est2_inv;
+			float const g = (P.custom_exp == 0.0f) ? relh*relh*relh : powf(relh, P.custom_exp);
+			z = g*P.zmax_est2 - P.zmax_est;
+		}
+		if (P.sine_on) { // apply_mesh_sine, :373-379
+			float const x = xval - Q.half_mx, y = yval - Q.half_my;
+			z += (Q.sine_mag*cosf_lut(tab, x*Q.sine_freq)*cosf_lut(tab, y*Q.sine_freq) + Q.sine_bias)*P.mesh_scale_z_inv;
+			if (P.volcano_on) {z += volcano_height(x, y, P, tab);}
+		}
+	}
+	out[i] = z;
+}
+
+template<bool SIMPLEX, bool WARP>
+static void launch_points(int shape, unsigned grid, cudaStream_t st, const float2 *xy, size_t n, float *out, const PointParams &Q, const NoiseParams &N,
+	const PostParams &P, const float *T, const float *tab)
+{
+	switch (shape) {
+	case 1:  points_kernel<SIMPLEX, WARP, 1><<<grid, 256, 0, st>>>(xy, n, out, Q, N, P, T, tab); break;
+	case 2:  points_kernel<SIMPLEX, WARP, 2><<<grid, 256, 0, st>>>(xy, n, out, Q, N, P, T, tab); break;
+	default: points_kernel<SIMPLEX, WARP, 0><<<grid, 256, 0, st>>>(xy, n, out, Q, N, P, T, tab); break;
+	}
+}
+
+int twi_eval_points(tw_ctx *ctx, const float *d_xy, size_t n, const tw_height_params *p, const tw_point_query *q, float *d_out) {
+	if (q->kind < TW_PQ_SIN_TERMS || q->kind > TW_PQ_EXACT_ZVAL) return tw_set_error(ctx, TW_ERR_ARG, "tw_eval_points: bad kind %d", q->kind);
+	bool const sine_mode = (p->gen_mode == TW_MGEN_SINE || q->kind == TW_PQ_SIN_TERMS);
+	if (sine_mode && !ctx->have_sine_params) return tw_set_error(ctx, TW_ERR_STATE, "tw_set_sine_params() has not been called");
+	if (p->start_eval_sin < 0 || p->start_eval_sin > F_TABLE) return tw_set_error(ctx, TW_ERR_ARG, "start_eval_sin %d out of range", p->start_eval_sin);
+	if (n > (size_t)0x7fffffff*256) return tw_set_error(ctx, TW_ERR_ARG, "tw_eval_points: too many points");
+	PostParams const P = make_post_params(p, 1, 0.0f, 0.0f);
+	NoiseParams N;
+	bool simplex = true;
+	memset(&N, 0, sizeof(N));
+	if (!sine_mode && !make_noise_params(p, N, simplex)) return tw_set_error(ctx, TW_ERR_ARG, "start_eval_sin out of range");
+	PointParams Q;
+	memset(&Q, 0, sizeof(Q));
+	Q.kind = q->kind; Q.sine_mode = sine_mode; Q.start = p->start_eval_sin; Q.glaciate = (p->glaciate != 0);
+	Q.xy_scale = (q->kind == TW_PQ_EXACT_ZVAL) ? 1.0f : q->xy_scale;
+	Q.mesh_scale = p->mesh_scale; Q.x_scene_size = q->x_scene_size; Q.y_scene_size = q->y_scene_size;
+	Q.half_mx = (float)(q->mesh_x_size >> 1); Q.half_my = (float)(q->mesh_y_size >> 1);
+	Q.xoff = q->no_xyoff ? 0.0f : (float)q->xoff2; Q.yoff = q->no_xyoff ? 0.0f : (float)q->yoff2;
+	Q.sine_mag = p->hmap.sine_mag; Q.sine_bias = p->hmap.sine_bias; Q.sine_freq = p->mesh_scale*p->hmap.sine_freq;
+	unsigned const grid = (unsigned)((n + 255)/256);
+	const float2 *xy = reinterpret_cast<const float2 *>(d_xy);
+	bool const warp = (p->gen_mode == TW_MGEN_DWARP_GPU);
+	if (sine_mode)                           {launch_points<true,  false>(p->gen_shape, grid, ctx->stream, xy, n, d_out, Q, N, P, ctx->d_sine_params, ctx->d_sin_table);}
+	else if (p->gen_mode == TW_MGEN_PERLIN)  {launch_points<false, false>(p->gen_shape, grid, ctx->stream, xy, n, d_out, Q, N, P, ctx->d_sine_params, ctx->d_sin_table);}
+	else if (warp)                           {launch_points<true,  true >(p->gen_shape, grid, ctx->stream, xy, n, d_out, Q, N, P, ctx->d_sine_params, ctx->d_sin_table);}
+	else                                     {launch_points<true,  false>(p->gen_shape, grid, ctx->stream, xy, n, d_out, Q, N, P, ctx->d_sine_params, ctx->d_sin_table);}
+	TW_LAUNCH_CHECK(ctx);
+	return TW_OK;
 }

@@ -36,6 +36,8 @@ struct scene_globals {
 	float zmax_est = 1.0f, custom_glaciate_exp = 0.0f;
 	tw_hmap_params hmap_params = {1000.0f, 0, 0, 0, 1000.0f, 0, 0, 0, 0, 0, 0, 0, 0, 0};
 	int   MESH_X_SIZE = 128, MESH_Y_SIZE = 128;
+	float X_SCENE_SIZE = 4.0f, Y_SCENE_SIZE = 4.0f; // get_exact_zval (src/mesh_gen.cpp:818-819)
+	int   xoff2 = 0, yoff2 = 0;                      // current mesh scroll offset (src/mesh_gen.cpp:826-829)
 	// erosion (src/erosion.cpp:11,98; src/Textures.cpp:1284-1287)
 	float erode_amount = 1.0f, water_plane_z = 0.0f, HALF_DXY = 0.0625f, zmin = -1.0f, zmax = 1.0f, relh_adj_tex = 0.0f, clip_hd1 = 0.5f;
 };
@@ -192,6 +194,37 @@ inline void apply_erosion(float *heightmap, int xsize, int ysize, float min_zval
 	tw_ctx *c = ctx();
 	int const rc = tw_erode(c, heightmap, xsize, ysize, min_zval, num_iters, &e);
 	if (rc != TW_OK) {detail::fail(rc, "apply_erosion", c);}
+}
+
+// ------------------------------------------------------------------------------------------------ point queries (batched)
+// float get_exact_zval(float xval, float yval, bool no_xyoff=0) / eval_mesh_sin_terms(xv, yv) / eval_mesh_sin_terms_scaled(xval, yval, xy_scale)
+// (src/function_registry.h:340-341, src/mesh_gen.cpp:797-847) for n points at once: xy = n (x, y) pairs. The single-point forms below cost a
+// kernel launch per call - callers that place many objects (buildings, scenery) should collect their points and use the batch forms.
+inline void eval_points(int kind, const float *xy, size_t n, float *out, float xy_scale = 1.0f, bool no_xyoff = false) {
+	scene_globals const &g = globals();
+	tw_height_params const p = height_params_from_globals(g.mesh_gen_mode, g.mesh_gen_shape);
+	tw_point_query q;
+	q.kind = kind; q.xy_scale = xy_scale; q.mesh_x_size = g.MESH_X_SIZE; q.mesh_y_size = g.MESH_Y_SIZE;
+	q.x_scene_size = g.X_SCENE_SIZE; q.y_scene_size = g.Y_SCENE_SIZE; q.xoff2 = g.xoff2; q.yoff2 = g.yoff2; q.no_xyoff = no_xyoff;
+	tw_ctx *c = ctx();
+	int const rc = tw_eval_points(c, xy, n, &p, &q, out);
+	if (rc != TW_OK) {detail::fail(rc, "eval_points", c);}
+}
+inline void get_exact_zvals(const float *xy, size_t n, float *zvals_out, bool no_xyoff = false) {eval_points(TW_PQ_EXACT_ZVAL, xy, n, zvals_out, 1.0f, no_xyoff);}
+inline float get_exact_zval(float xval, float yval, bool no_xyoff = false) {
+	float const xy[2] = {xval, yval}; float z = 0.0f;
+	get_exact_zvals(xy, 1, &z, no_xyoff);
+	return z;
+}
+inline float eval_mesh_sin_terms(float xv, float yv) {
+	float const xy[2] = {xv, yv}; float z = 0.0f;
+	eval_points(TW_PQ_SIN_TERMS, xy, 1, &z);
+	return z;
+}
+inline float eval_mesh_sin_terms_scaled(float xval, float yval, float xy_scale) {
+	float const xy[2] = {xval, yval}; float z = 0.0f;
+	eval_points(TW_PQ_SIN_TERMS_SCALED, xy, 1, &z, xy_scale);
+	return z;
 }
 
 // the same with the reference's OpenMP semantics (`#pragma omp parallel for schedule(dynamic,1)`, src/erosion.cpp:66): num_threads droplets in

@@ -172,6 +172,25 @@ TW_API int tw_tile_bounds_batch(tw_ctx *ctx, const float *zvals, uint32_t ntiles
 TW_API int tw_glaciate_mesh(tw_ctx *ctx, float *mesh, int nx, int ny, int xoff2, int yoff2, int mesh_x_size, int mesh_y_size,
                      const tw_height_params *p, tw_minmax *zbottom_ztop);
 
+/* ---- point queries ----
+ * Batched form of the reference's single-point height functions, for callers that place many objects (buildings, scenery, cities):
+ *   TW_PQ_SIN_TERMS         float eval_mesh_sin_terms(float xv, float yv)                          src/mesh_gen.cpp:797-805 (raw sine-table sum)
+ *   TW_PQ_SIN_TERMS_SCALED  float eval_mesh_sin_terms_scaled(float xval, float yval, float xy_scale) src/mesh_gen.cpp:807-813
+ *   TW_PQ_EXACT_ZVAL        float get_exact_zval(float xval, float yval, bool no_xyoff)            src/mesh_gen.cpp:816-847, the procedural
+ *                           branch (no landscape file / tiled-terrain heightmap texture): glaciate + hmap sine bias/volcano applied
+ * xy = n (x, y) pairs, out = n floats; both host or device. GLACIATE is p->glaciate. */
+#define TW_PQ_SIN_TERMS        0
+#define TW_PQ_SIN_TERMS_SCALED 1
+#define TW_PQ_EXACT_ZVAL       2
+typedef struct tw_point_query {
+	int   kind;                       /* TW_PQ_* */
+	float xy_scale;                   /* TW_PQ_SIN_TERMS_SCALED */
+	int   mesh_x_size, mesh_y_size;   /* MESH_X_SIZE, MESH_Y_SIZE (scaled / exact) */
+	float x_scene_size, y_scene_size; /* X_SCENE_SIZE, Y_SCENE_SIZE (exact) */
+	int   xoff2, yoff2, no_xyoff;     /* current mesh scroll offset, and the no_xyoff argument (exact) */
+} tw_point_query;
+TW_API int tw_eval_points(tw_ctx *ctx, const float *xy, size_t n, const tw_height_params *p, const tw_point_query *q, float *out);
+
 /* ---- hydraulic erosion ----
  * Replaces apply_erosion(float *heightmap, int xsize, int ysize, float min_zval, unsigned num_iters) (src/function_registry.h:354,
  * src/erosion.cpp:14-164): in place, row-major x-fastest, droplets applied in the reference's serial order (iter = 0..num_iters-1;

@@ -48,6 +48,11 @@ class TileBounds(C.Structure):
                 ("radius", C.c_float), ("wx1", C.c_int32), ("wy1", C.c_int32), ("wx2", C.c_int32), ("wy2", C.c_int32)]
 
 
+class PointQuery(C.Structure):
+    _fields_ = [("kind", C.c_int), ("xy_scale", C.c_float), ("mesh_x_size", C.c_int), ("mesh_y_size", C.c_int), ("x_scene_size", C.c_float),
+                ("y_scene_size", C.c_float), ("xoff2", C.c_int), ("yoff2", C.c_int), ("no_xyoff", C.c_int)]
+
+
 class Rng(C.Structure):
     _fields_ = [("rseed1", C.c_int64), ("rseed2", C.c_int64)]
 
@@ -99,6 +104,7 @@ def lib():
         L.to_gen_mesh.argtypes = [C.POINTER(Rng), C.POINTER(HeightParams), C.c_int, C.c_int, C.c_float, C.c_float, C.c_int, C.c_int, C.c_int, C.c_int,
                                   C.c_float, C.c_float, C.c_float, C.c_float, C.c_uint, C.POINTER(ErosionParams), vp, vp, vp, vp]
         L.to_tile_bounds.argtypes = [vp, C.c_uint, C.c_uint, C.c_float, C.c_float, C.c_float, C.c_uint, vp]
+        L.to_eval_points.argtypes = [vp, C.c_size_t, C.POINTER(HeightParams), C.POINTER(PointQuery), vp, vp, vp]
         L.to_apply_erosion.argtypes = [vp, C.c_int, C.c_int, C.c_float, C.c_uint, C.POINTER(ErosionParams)]
         L.to_apply_erosion.restype = C.c_ulonglong
         L.to_noise3d_gen_sines.argtypes = [C.c_int, C.c_int, C.c_float, C.c_float, vp]
@@ -172,6 +178,14 @@ def tile_bounds(tiles, wpz_max, dx_val, dy_val, size):
     nt, zv = tiles.shape[0], tiles.shape[1]
     out = (TileBounds * nt)()
     lib().to_tile_bounds(_p(tiles), nt, zv, wpz_max, dx_val, dy_val, size, C.cast(out, C.c_void_p))
+    return out
+
+
+def eval_points(xy, hp, pq, sine_params=None):
+    xy = np.ascontiguousarray(xy, np.float32).reshape(-1, 2)
+    out = np.empty(xy.shape[0], np.float32)
+    sp = np.ascontiguousarray(sine_params if sine_params is not None else np.zeros((90, 5)), np.float32)
+    lib().to_eval_points(_p(xy), xy.shape[0], C.byref(hp), C.byref(pq), _p(sin_table()), _p(sp), _p(out))
     return out
 
 

@@ -113,6 +113,15 @@ def heightgen(x0, y0, dx, dy, nx, ny, cache_values=0, glaciate=1, min_start_sin=
     return out
 
 
+def eval_points(kind, xy, xy_scale=1.0, no_xyoff=0, xoff2=0, yoff2=0):
+    """kind 0/1/2 = eval_mesh_sin_terms / eval_mesh_sin_terms_scaled / get_exact_zval of the reference for every (x, y) row."""
+    xy = np.ascontiguousarray(xy, np.float32).reshape(-1, 2)
+    out = np.empty(xy.shape[0], np.float32)
+    lib().ref_eval_points(int(kind), xy.ctypes.data_as(C.c_void_p), C.c_size_t(xy.shape[0]), C.c_float(xy_scale), int(no_xyoff), int(xoff2), int(yoff2),
+                          out.ctypes.data_as(C.c_void_p))
+    return out
+
+
 def apply_erosion(h, min_zval, num_iters, erode_amount=1.0, water_plane_z=0.0, half_dxy=0.0625, zmin=-1.0, zmax=1.0, relh_adj_tex=0.0, clip_hd1=0.5):
     h = np.array(h, np.float32, order="C", copy=True)
     ys, xs = h.shape

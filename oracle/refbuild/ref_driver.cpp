@@ -33,6 +33,9 @@ float get_noise_zval(float xval, float yval, int mode, int shape);
 float eval_mesh_sin_terms(float xv, float yv);
 void apply_glaciate(float &zval);
 float get_water_z_height();
+float eval_mesh_sin_terms_scaled(float xval, float yval, float xy_scale);
+float get_exact_zval(float xval_in, float yval_in, bool no_xyoff);
+extern int xoff2, yoff2;
 void apply_erosion(float *heightmap, int xsize, int ysize, float min_zval, unsigned num_iters);
 void gen_rx_ry(float &rx, float &ry);
 
@@ -107,6 +110,25 @@ void ref_heightgen(float x0, float y0, float dx, float dy, unsigned nx, unsigned
 float ref_get_noise_zval(float xval, float yval, int mode, int shape) {return get_noise_zval(xval, yval, mode, shape);}
 float ref_eval_mesh_sin_terms(float xv, float yv) {return eval_mesh_sin_terms(xv, yv);}
 float ref_get_water_z_height() {return get_water_z_height();}
+// point queries: eval_mesh_sin_terms_scaled / get_exact_zval, procedural branch (no heightmap texture, no landscape file)
+float ref_eval_mesh_sin_terms_scaled(float xval, float yval, float xy_scale) {return eval_mesh_sin_terms_scaled(xval, yval, xy_scale);}
+// kind 0/1/2 = eval_mesh_sin_terms / eval_mesh_sin_terms_scaled / get_exact_zval for n points (the loop is the driver's; each value is the reference's)
+void ref_eval_points(int kind, const float *xy, size_t n, float xy_scale, int no_xyoff, int xo, int yo, float *out) {
+	int const xs(xoff2), ys(yoff2);
+	xoff2 = xo; yoff2 = yo;
+	for (size_t i = 0; i < n; ++i) {
+		float const x(xy[2*i]), y(xy[2*i+1]);
+		out[i] = (kind == 0) ? eval_mesh_sin_terms(x, y) : ((kind == 1) ? eval_mesh_sin_terms_scaled(x, y, xy_scale) : get_exact_zval(x, y, (no_xyoff != 0)));
+	}
+	xoff2 = xs; yoff2 = ys;
+}
+float ref_get_exact_zval(float xval, float yval, int no_xyoff, int xo, int yo) {
+	int const xs(xoff2), ys(yoff2);
+	xoff2 = xo; yoff2 = yo;
+	float const z(get_exact_zval(xval, yval, (no_xyoff != 0)));
+	xoff2 = xs; yoff2 = ys;
+	return z;
+}
 float ref_glm_simplex2(float x, float y);
 float ref_glm_perlin2 (float x, float y);
 float ref_glm_simplex3(float x, float y, float z);

@@ -84,3 +84,9 @@ void texture_t::load(int, bool, bool, bool) {}
 void texture_t::gl_delete() {}
 void texture_t::free_client_mem() {}
 float heightmap_t::get_heightmap_value(unsigned, unsigned) const {return 0.0;}
+
+// ---- get_exact_zval(): procedural branch only (no tiled-terrain heightmap texture loaded) ----
+char *mh_filename_tt(nullptr);
+bool using_tiled_terrain_hmap_tex() {return 0;}
+bool using_hmap_with_detail() {return 0;}
+float get_tiled_terrain_height_tex(float, float, bool) {return 0.0;}

@@ -633,6 +633,35 @@ unsigned long long to_apply_erosion(float *heightmap, int xsize, int ysize, floa
 	return steps;
 }
 
+
+/* ------------------------------------------------------------------ point queries (ref: src/mesh_gen.cpp:797-847) */
+static float eval_mesh_sin_terms_scaled(float xval, float yval, float xy_scale, int MX, int MY, const tw_height_params *p, const float *tab, const float *T) { /* ref: :807-813 */
+	float const xv = xy_scale*(xval - (float)(MX >> 1)), yv = xy_scale*(yval - (float)(MY >> 1));
+	if (p->gen_mode != TW_MGEN_SINE) {return to_get_noise_zval(xv, yv, p);}
+	float val = to_eval_mesh_sin_terms(p->mesh_scale*xv, p->mesh_scale*yv, tab, T, p->start_eval_sin)*p->mesh_scale_z_inv;
+	apply_noise_shape_final(&val, p->gen_shape, &p->hmap);
+	return val;
+}
+void to_eval_points(const float *xy, size_t n, const tw_height_params *p, const tw_point_query *q, const float *tab, const float *T, float *out) {
+	for (size_t i = 0; i < n; ++i) {
+		float const xin = xy[2*i], yin = xy[2*i + 1];
+		if (q->kind == TW_PQ_SIN_TERMS) {out[i] = to_eval_mesh_sin_terms(xin, yin, tab, T, p->start_eval_sin); continue;}
+		if (q->kind == TW_PQ_SIN_TERMS_SCALED) {out[i] = eval_mesh_sin_terms_scaled(xin, yin, q->xy_scale, q->mesh_x_size, q->mesh_y_size, p, tab, T); continue;}
+		/* get_exact_zval, procedural branch (ref: :816-847) */
+		float xval = (float)((xin + q->x_scene_size)*p->dx_val_inv + 0.5);
+		float yval = (float)((yin + q->y_scene_size)*p->dy_val_inv + 0.5);
+		if (!q->no_xyoff) {xval += q->xoff2; yval += q->yoff2;}
+		float zval = eval_mesh_sin_terms_scaled(xval, yval, 1.0f, q->mesh_x_size, q->mesh_y_size, p, tab, T);
+		if (p->glaciate) { /* apply_glaciate, ref: :380-385 */
+			float const zmax_est = p->zmax_est, zmax_est2 = (float)(2.0*zmax_est), zmax_est2_inv = (float)(1.0/zmax_est2);
+			float const relh = (zval + zmax_est)*zmax_est2_inv;
+			zval = do_glaciate_exp(relh, p->custom_glaciate_exp)*zmax_est2 - zmax_est;
+		}
+		apply_mesh_sine(&zval, (xval - (float)(q->mesh_x_size >> 1)), (yval - (float)(q->mesh_y_size >> 1)), p, tab);
+		out[i] = zval;
+	}
+}
+
 /* ------------------------------------------------------------------ 3-D noise / voxels */
 void to_noise3d_gen_sines(int rs1, int rs2, float mag, float freq, float *rdata) { /* ref: src/upsurface.cpp:16-38 */
 	tw_rng r; to_rng_set(&r, rs1, rs2);

@@ -84,6 +84,19 @@ int main(int argc, char **argv) {
 		tw3d::create_procedural(v, 1.0f, 1.0f, offset, true, 123, 456, (mode >= 3 ? 1 : mode), 0.0f, 2);
 		dump(f, vox);
 
+		// --- point queries: get_exact_zval for a scrolled scene (batch and single-point forms), eval_mesh_sin_terms ---
+		{
+			g.xoff2 = 100; g.yoff2 = -40;
+			tw3d::set_globals(g);
+			float const xy[10] = {0.0f, 0.0f, 1.5f, -2.25f, -3.9f, 3.9f, 100.0f, 250.0f, 0.03125f, 0.0625f};
+			std::vector<float> pz(5);
+			tw3d::get_exact_zvals(xy, 5, pz.data());
+			pz.push_back(tw3d::get_exact_zval(1.5f, -2.25f, true));
+			pz.push_back(tw3d::eval_mesh_sin_terms(0.3f, -7.0f));
+			pz.push_back(tw3d::eval_mesh_sin_terms_scaled(70.0f, 12.5f, 16.0f));
+			dump(f, pz);
+		}
+
 		// --- gen_mesh(): BASELINE config 1 (128x128 sine mesh, mesh_seed 6, glaciate, mesh_freq_filter 2, mesh_height 0.7) + 2000 droplets ---
 		if (mode == 0) {
 			tw3d::scene_globals g1;

@@ -40,7 +40,7 @@ def test_adapter_matches_oracle(exe, tw, scene, oracle, ctx, beq, tmp_path, mode
     assert r.returncode == 0, r.stderr
     data = np.fromfile(path, np.float32)
     W, H, zv = 160, 96, 66
-    sizes = [W * H, W * H, zv * zv, 3 * zv * zv, 24 * 10 * 30] + ([128 * 128, 6] if mode == 0 else [])
+    sizes = [W * H, W * H, zv * zv, 3 * zv * zv, 24 * 10 * 30, 8] + ([128 * 128, 6] if mode == 0 else [])
     assert data.size == sum(sizes)
     parts = np.split(data, np.cumsum(sizes)[:-1])
     cfg = scene.SceneConfig(mesh_gen_mode=mode, mesh_freq_filter=1, mesh_seed=1, hmap=HM_CFG, zmax_est=2.3)
@@ -73,7 +73,15 @@ def test_adapter_matches_oracle(exe, tw, scene, oracle, ctx, beq, tmp_path, mode
     vp.gen_mode, vp.normalize_to_1, vp.rseed1, vp.rseed2, vp.octaves = vmode, 1, 123, 456, 3
     vp.rx, vp.ry = oracle.gen_rx_ry(1, 0, vmode) if vmode != 0 else (0.0, 0.0)
     assert beq(parts[4], oracle.voxel_fill(vp)) == 0
+    # point queries (get_exact_zval scrolled by xoff2/yoff2 = 100/-40, single-point forms)
+    xy = np.array([[0.0, 0.0], [1.5, -2.25], [-3.9, 3.9], [100.0, 250.0], [0.03125, 0.0625]], np.float32)
+    PQ = oracle.PointQuery
+    exp = list(oracle.eval_points(xy, hp, PQ(2, 1.0, 128, 128, 4.0, 4.0, 100, -40, 0), sp))
+    exp += list(oracle.eval_points(xy[1:2], hp, PQ(2, 1.0, 128, 128, 4.0, 4.0, 100, -40, 1), sp))
+    exp += list(oracle.eval_points(np.array([[0.3, -7.0]], np.float32), hp, PQ(0, 1.0, 128, 128, 4.0, 4.0, 100, -40, 0), sp))
+    exp += list(oracle.eval_points(np.array([[70.0, 12.5]], np.float32), hp, PQ(1, 16.0, 128, 128, 4.0, 4.0, 100, -40, 0), sp))
+    assert beq(parts[5], np.array(exp, np.float32)) == 0
     if mode == 0:   # tw3d::gen_mesh == the reference's own gen_mesh() (golden fixture gm_cfg1_eroded)
         h = np.load(os.path.join(ROOT, "tests", "golden", "height.npz"))
-        assert beq(parts[5], h["gm_cfg1_eroded"]) == 0
-        assert beq(parts[6], h["gm_cfg1_eroded_zvals"]) == 0
+        assert beq(parts[6], h["gm_cfg1_eroded"]) == 0
+        assert beq(parts[7], h["gm_cfg1_eroded_zvals"]) == 0

@@ -81,6 +81,27 @@ def test_height_grids(oracle, beq):
     assert beq(z, h["cfg1"]) == 0
 
 
+def point_cases(mod, h):
+    """Yields (name, HeightParams, PointQuery, xy, sine_params, expected) for every query stored in points.npz (mod = oracle or product module)."""
+    for mode in range(5):
+        for shape in range(3):
+            n = "p_m%d_s%d" % (mode, shape)
+            hp = hp_from_args(mod, h[n + "_args"], h[n + "_hmap"])
+            sp = h[n + "_sp"] if (n + "_sp") in h else None
+            for qi in range(4):
+                key = "%s_q%d" % (n, qi)
+                if key + "_xy" not in h:
+                    continue
+                q = h[key + "_query"]
+                pq = mod.PointQuery(int(q[0]), float(q[1]), int(q[2]), int(q[3]), float(q[4]), float(q[5]), int(q[6]), int(q[7]), int(q[8]))
+                yield key, hp, pq, h[key + "_xy"], sp, h[key + "_out"]
+
+
+def test_point_queries(oracle, beq):
+    for key, hp, pq, xy, sp, exp in point_cases(oracle, load("points.npz")):
+        assert beq(oracle.eval_points(xy, hp, pq, sp), exp) == 0, key
+
+
 def test_erosion(oracle, beq):
     e = load("erosion.npz")
     for key_in, keys in (("in0", ["0_%d" % i for i in range(3)]), ("mesh128_in", ["mesh128"])):

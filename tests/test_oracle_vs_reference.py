@@ -47,6 +47,32 @@ def test_heightgen_all_modes(oracle, ref, beq):
                     assert beq(zr, zo) == 0, (mode, shape, ff, custom, ms, x0)
 
 
+def _points(rng, n, span):
+    xy = (rng.uniform(-span, span, (n, 2))).astype(np.float32)
+    xy[: n // 8] = np.round(xy[: n // 8])                      # lattice points / exact cell centres
+    xy[n // 8: n // 6] *= 1000.0                               # far away (large sine-table arguments)
+    return xy
+
+
+def test_point_queries(oracle, ref, beq):
+    """eval_mesh_sin_terms, eval_mesh_sin_terms_scaled and get_exact_zval (procedural branch) of the reference vs the
+    oracle's to_eval_points, every gen mode / shape, scrolled and unscrolled."""
+    rng = np.random.default_rng(5)
+    for mode in (0, 1, 2, 3, 4):
+        for shape in (0, 1, 2):
+            for ff, hmap, gl, custom, ms in ((1, HM_CFG, 1, 0.0, 1.0), (0, None, 0, 0.0, 1.0), (2, HM_ALL, 1, 0.0, 1.0), (1, HM_ALL, 1, 2.5, 4.0)):
+                hp = _hp(oracle, ref, mode, shape, ff, 1, hmap, 2.3, gl, custom, ms)
+                sp = ref.sine_params()
+                n = 300 if mode == 4 else 1000
+                for kind, span, xy_scale, no_xyoff, xo, yo in ((0, 30.0, 1.0, 0, 0, 0), (1, 500.0, 1.0, 0, 0, 0), (1, 500.0, 16.0, 0, 0, 0),
+                                                              (2, 4.0, 1.0, 0, 0, 0), (2, 4.0, 1.0, 0, 640, -1280), (2, 40.0, 1.0, 1, 640, -1280)):
+                    xy = _points(rng, n, span)
+                    pq = oracle.PointQuery(kind, xy_scale, 128, 128, 4.0, 4.0, xo, yo, no_xyoff)
+                    zr = ref.eval_points(kind, xy, xy_scale, no_xyoff, xo, yo)
+                    zo = oracle.eval_points(xy, hp, pq, sp)
+                    assert beq(zr, zo) == 0, (mode, shape, ff, kind, xy_scale, no_xyoff)
+
+
 def test_erosion_serial_order(oracle, ref, beq):
     ref.lib().ref_set_threads(1)
     ref.setup(mode=1, freq_filter=1, seed=1, zmax_est=2.0, hmap=HM_CFG)
