@@ -117,6 +117,7 @@ void tw_destroy(tw_ctx *ctx) {
 	for (int i = 0; i < 3; ++i) {if (ctx->d_scratch[i]) cudaFree(ctx->d_scratch[i]);}
 	if (ctx->d_sin_table) cudaFree(ctx->d_sin_table);
 	if (ctx->d_dir_table) cudaFree(ctx->d_dir_table);
+	if (ctx->d_simplex_lut) cudaFree(ctx->d_simplex_lut);
 	if (ctx->d_sine_params) cudaFree(ctx->d_sine_params);
 	if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
 	if (ctx->async.done) cudaEventDestroy(ctx->async.done);

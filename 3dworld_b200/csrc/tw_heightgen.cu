@@ -175,13 +175,13 @@ __device__ __forceinline__ bool noise_lattice_in_range(float2 xv, float2 yv, con
 }
 
 template<bool SIMPLEX, int SHAPE>
-__device__ __forceinline__ float2 gen_noise2(float2 xv, float2 yv, const NoiseParams &N) { // gen_noise (src/mesh_gen.cpp:706-730) for two cells
+__device__ __forceinline__ float2 gen_noise2(float2 xv, float2 yv, const NoiseParams &N, unsigned L) { // gen_noise (src/mesh_gen.cpp:706-730) for two cells; L: simplex table base (twn2::simplex_lut_base) or 0
 	float2 zval = make_float2(0.0f, 0.0f);
 	if (noise_lattice_in_range(xv, yv, N)) {
 #pragma unroll 1
 		for (int i = 0; i < N.octaves; ++i) {
 			float2 const px = twn2::add2(twn2::mul2(xv, N.freq[i]), N.rx[i]), py = twn2::add2(twn2::mul2(yv, N.freq[i]), N.ry[i]);
-			float2 noise = SIMPLEX ? twn2::simplex2(px, py) : twn2::perlin2(px, py);
+			float2 noise = SIMPLEX ? ((TW_SIMPLEX_LUT > 0) ? twn2::simplex2_lut(px, py, L) : twn2::simplex2(px, py)) : twn2::perlin2(px, py);
 			if (SHAPE == 1) {noise = make_float2((float)((double)fabsf(noise.x) - 0.40), (float)((double)fabsf(noise.y) - 0.40));}
 			if (SHAPE == 2) {noise = make_float2((float)(0.45 - (double)fabsf(noise.x)), (float)(0.45 - (double)fabsf(noise.y)));}
 			zval = twn2::fma2(noise, N.mag[i], zval); // mag is a power of two: exact product
@@ -196,8 +196,17 @@ __device__ __forceinline__ float dadd(float a, double b) {return (float)((double
 template<bool SIMPLEX, bool WARP, int SHAPE>
 __global__ void __launch_bounds__(256, TW_NOISE2_MIN_BLOCKS)
 noise_grid2_kernel(float *__restrict__ out, unsigned nx, unsigned ny, unsigned y_off, float mx0_single, float my0_single, const float2 *__restrict__ tile_origins,
-	NoiseParams N, PostParams P, const float *__restrict__ sin_tab, unsigned *__restrict__ mm)
+	NoiseParams N, PostParams P, const float *__restrict__ sin_tab, unsigned *__restrict__ mm, const float4 *__restrict__ simplex_lut)
 {
+	unsigned L = 0;
+	if (SIMPLEX && TW_SIMPLEX_LUT > 0) { // hash/gradient table -> shared memory, 8 interleaved copies (see tw_noise2.cuh)
+		__shared__ float4 lut_s[twn2::SIMPLEX_LUT_N*twn2::SIMPLEX_LUT_COPIES];
+		int const tid = threadIdx.x + blockDim.x*threadIdx.y;
+		for (int e = tid; e < twn2::SIMPLEX_LUT_N*twn2::SIMPLEX_LUT_COPIES; e += blockDim.x*blockDim.y) {lut_s[e] = __ldg(simplex_lut + e/twn2::SIMPLEX_LUT_COPIES);}
+		__syncthreads();
+		L = twn2::simplex_lut_base(lut_s, threadIdx.x);
+		asm volatile("" : "+r"(L) :: "memory"); // every table load depends on L, and L is defined after the barrier
+	}
 	unsigned const x = 2*(blockIdx.x*blockDim.x + threadIdx.x), y = y_off + blockIdx.y*blockDim.y + threadIdx.y, tile = blockIdx.z;
 	float mx0 = mx0_single, my0 = my0_single;
 	if (tile_origins) {float2 const o = __ldg(tile_origins + tile); mx0 = o.x; my0 = o.y;}
@@ -211,14 +220,14 @@ noise_grid2_kernel(float *__restrict__ out, unsigned nx, unsigned ny, unsigned y
 		float2 xv = mul2(xval, N.xy_scale), yv = splat(N.xy_scale*yval1);             // get_noise_zval, src/mesh_gen.cpp:737-738
 		if (WARP) { // domain warping, src/mesh_gen.cpp:740-747
 			float const scale = 0.2f;
-			float2 const dx1 = gen_noise2<SIMPLEX, SHAPE>(make_float2(dadd(xv.x, 0.0), dadd(xv.y, 0.0)), make_float2(dadd(yv.x, 0.0), dadd(yv.y, 0.0)), N);
-			float2 const dy1 = gen_noise2<SIMPLEX, SHAPE>(make_float2(dadd(xv.x, 5.2), dadd(xv.y, 5.2)), make_float2(dadd(yv.x, 1.3), dadd(yv.y, 1.3)), N);
+			float2 const dx1 = gen_noise2<SIMPLEX, SHAPE>(make_float2(dadd(xv.x, 0.0), dadd(xv.y, 0.0)), make_float2(dadd(yv.x, 0.0), dadd(yv.y, 0.0)), N, L);
+			float2 const dy1 = gen_noise2<SIMPLEX, SHAPE>(make_float2(dadd(xv.x, 5.2), dadd(xv.y, 5.2)), make_float2(dadd(yv.x, 1.3), dadd(yv.y, 1.3)), N, L);
 			float2 const wx = add2(xv, mul2(dx1, scale)), wy = add2(yv, mul2(dy1, scale));
-			float2 const dx2 = gen_noise2<SIMPLEX, SHAPE>(make_float2(dadd(wx.x, 1.7), dadd(wx.y, 1.7)), make_float2(dadd(wy.x, 9.2), dadd(wy.y, 9.2)), N);
-			float2 const dy2 = gen_noise2<SIMPLEX, SHAPE>(make_float2(dadd(wx.x, 8.3), dadd(wx.y, 8.3)), make_float2(dadd(wy.x, 2.8), dadd(wy.y, 2.8)), N);
+			float2 const dx2 = gen_noise2<SIMPLEX, SHAPE>(make_float2(dadd(wx.x, 1.7), dadd(wx.y, 1.7)), make_float2(dadd(wy.x, 9.2), dadd(wy.y, 9.2)), N, L);
+			float2 const dy2 = gen_noise2<SIMPLEX, SHAPE>(make_float2(dadd(wx.x, 8.3), dadd(wx.y, 8.3)), make_float2(dadd(wy.x, 2.8), dadd(wy.y, 2.8)), N, L);
 			xv = add2(xv, mul2(dx2, scale)); yv = add2(yv, mul2(dy2, scale));
 		}
-		float2 const zz = gen_noise2<SIMPLEX, SHAPE>(xv, yv, N);
+		float2 const zz = gen_noise2<SIMPLEX, SHAPE>(xv, yv, N, L);
 		float const smy = (P.enable_glaciate && P.sine_on) ? cosf_lut(sin_tab, ((float)y*P.mdy + my0)*P.dy_inv*P.sm_freq) : 0.0f;
 		z0 = zz.x; z1 = zz.y;
 		if (P.need_postproc) {z0 = postproc_noise_zval(z0, P.h); z1 = postproc_noise_zval(z1, P.h);}
@@ -242,13 +251,25 @@ noise_grid2_kernel(float *__restrict__ out, unsigned nx, unsigned ny, unsigned y
 
 template<bool SIMPLEX, bool WARP>
 void launch_noise2(int shape, dim3 grid, dim3 block, cudaStream_t st, float *out, unsigned nx, unsigned ny, unsigned y_off, float mx0, float my0,
-	const float2 *origins, const NoiseParams &N, const PostParams &P, const float *tab, unsigned *mm)
+	const float2 *origins, const NoiseParams &N, const PostParams &P, const float *tab, unsigned *mm, const float4 *lut)
 {
 	switch (shape) {
-	case 1:  noise_grid2_kernel<SIMPLEX, WARP, 1><<<grid, block, 0, st>>>(out, nx, ny, y_off, mx0, my0, origins, N, P, tab, mm); break;
-	case 2:  noise_grid2_kernel<SIMPLEX, WARP, 2><<<grid, block, 0, st>>>(out, nx, ny, y_off, mx0, my0, origins, N, P, tab, mm); break;
-	default: noise_grid2_kernel<SIMPLEX, WARP, 0><<<grid, block, 0, st>>>(out, nx, ny, y_off, mx0, my0, origins, N, P, tab, mm); break;
+	case 1:  noise_grid2_kernel<SIMPLEX, WARP, 1><<<grid, block, 0, st>>>(out, nx, ny, y_off, mx0, my0, origins, N, P, tab, mm, lut); break;
+	case 2:  noise_grid2_kernel<SIMPLEX, WARP, 2><<<grid, block, 0, st>>>(out, nx, ny, y_off, mx0, my0, origins, N, P, tab, mm, lut); break;
+	default: noise_grid2_kernel<SIMPLEX, WARP, 0><<<grid, block, 0, st>>>(out, nx, ny, y_off, mx0, my0, origins, N, P, tab, mm, lut); break;
 	}
+}
+
+__global__ void simplex_lut_kernel(float4 *__restrict__ lut) {
+	int const k = blockIdx.x*blockDim.x + threadIdx.x;
+	if (k < twn2::SIMPLEX_LUT_N) {lut[k] = twn2::simplex_lut_entry((float)k);}
+}
+static int ensure_simplex_lut(tw_ctx *ctx) {
+	if (ctx->d_simplex_lut) return TW_OK;
+	TW_CUDA(ctx, cudaMalloc(&ctx->d_simplex_lut, twn2::SIMPLEX_LUT_N*sizeof(float4)));
+	simplex_lut_kernel<<<(twn2::SIMPLEX_LUT_N + 127)/128, 128, 0, ctx->stream>>>((float4 *)ctx->d_simplex_lut);
+	TW_LAUNCH_CHECK(ctx);
+	return TW_OK;
 }
 
 // ------------------------------------------------------------------------------------------------ sine-table mode
@@ -496,15 +517,17 @@ int twi_heightgen(tw_ctx *ctx, const tw_grid2d *g, const tw_height_params *p, in
 		bool simplex = false;
 		if (!make_noise_params(p, N, simplex)) return tw_set_error(ctx, TW_ERR_ARG, "start_eval_sin %d out of range", p->start_eval_sin);
 		bool const warp = (p->gen_mode == TW_MGEN_DWARP_GPU);
+		if (simplex) {int const rc = ensure_simplex_lut(ctx); if (rc) return rc;}
+		const float4 *lut = (const float4 *)ctx->d_simplex_lut;
 		unsigned const band_rows = band_rows_for(ctx, ny, nx, h_out_bands != nullptr && ntiles == 1);
 		for (unsigned r0 = 0; r0 < ny; r0 += band_rows) {
 			unsigned const r1 = (ny - r0 < band_rows) ? ny : r0 + band_rows;
 			static bool const use_scalar = (getenv("TW_NOISE_SCALAR") != nullptr); // A/B switch: one cell per thread, scalar FMUL/FADD
 			if (!use_scalar) { // two cells per thread on packed fp32x2 instructions
 				dim3 const block(32, 8, 1), grid((nx + 63)/64, (r1 - r0 + 7)/8, ntiles);
-				if (p->gen_mode == TW_MGEN_PERLIN) {launch_noise2<false, false>(p->gen_shape, grid, block, ctx->stream, d_out, nx, ny, r0, mx0, my0, d_tile_origins, N, P, ctx->d_sin_table, d_mm_ord);}
-				else if (warp) {launch_noise2<true, true >(p->gen_shape, grid, block, ctx->stream, d_out, nx, ny, r0, mx0, my0, d_tile_origins, N, P, ctx->d_sin_table, d_mm_ord);}
-				else           {launch_noise2<true, false>(p->gen_shape, grid, block, ctx->stream, d_out, nx, ny, r0, mx0, my0, d_tile_origins, N, P, ctx->d_sin_table, d_mm_ord);}
+				if (p->gen_mode == TW_MGEN_PERLIN) {launch_noise2<false, false>(p->gen_shape, grid, block, ctx->stream, d_out, nx, ny, r0, mx0, my0, d_tile_origins, N, P, ctx->d_sin_table, d_mm_ord, nullptr);}
+				else if (warp) {launch_noise2<true, true >(p->gen_shape, grid, block, ctx->stream, d_out, nx, ny, r0, mx0, my0, d_tile_origins, N, P, ctx->d_sin_table, d_mm_ord, lut);}
+				else           {launch_noise2<true, false>(p->gen_shape, grid, block, ctx->stream, d_out, nx, ny, r0, mx0, my0, d_tile_origins, N, P, ctx->d_sin_table, d_mm_ord, lut);}
 				TW_LAUNCH_CHECK(ctx);
 				if (h_out_bands) {int const rc = band_copy(ctx, h_out_bands, d_out, nx, r0, r1); if (rc) return rc;}
 				continue;

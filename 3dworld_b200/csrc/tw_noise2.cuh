@@ -105,6 +105,83 @@ __device__ __forceinline__ f2 simplex2(f2 vx, f2 vy) {
 	return mul2(add2(add2(mul2(m0, gx), mul2(m1, gy)), mul2(m2, gz)), 130.0f);
 }
 
+// ---- simplex with tabulated hash/gradient (TW_SIMPLEX_LUT) ----
+// After `i = mod(i, 289)` everything between the lattice index and the gradient is a function of small integers:
+//   q = permute(iy + {0, i1.y, 1})       argument in [0, 290]  -> value in [0, 288]
+//   p = permute(q + ix + {0, i1.x, 1})   argument in [0, 578]  -> value in [0, 288]   (exhaustively: the float arithmetic is exact there)
+//   x = 2*fract(p*C.w) - 1, h = |x| - 0.5, a0 = x - floor(x + 0.5), n = taylorInvSqrt(a0*a0 + h*h)   depend on p only.
+// simplex_lut_entry() evaluates exactly those reference operations once per integer; the kernel keeps the 291-entry table
+// {a0, h, n, permute(k)} in shared memory and replaces 11 packed instructions + 4 floors per corner (level 1: gradient) plus 4 + 2 per
+// corner (level 2: the first permute) by one 16-byte load each. Random indices would collide on the 32 banks, so the table is stored as 8
+// interleaved copies: entry k of copy c sits at float4 index 8*k + c and lane l reads copy l & 7 - the 8 lanes of every quarter-warp phase
+// of an LDS.128 then hit 8 different 16-byte bank groups by construction (conflict-free, 4 cycles per warp load).
+#ifndef TW_SIMPLEX_LUT
+#define TW_SIMPLEX_LUT 2
+#endif
+constexpr int SIMPLEX_LUT_N = 291, SIMPLEX_LUT_COPIES = 8;
+
+__device__ __forceinline__ float4 simplex_lut_entry(float k) { // scalar restatement of twn::simplex2's per-corner gradient and of permute()
+	float const Cw = 0.024390243902439f;
+	float const X = twn::two_f_minus_1(twn::fract(k*Cw));
+	float const h = fabsf(X) - 0.5f, a0 = X - floorf(X + 0.5f);
+	float const n = 1.79284291400159f - 0.85373472095314f*(a0*a0 + h*h);
+	return make_float4(a0, h, n, twn::permute(k));
+}
+
+// Table addressing without integer arithmetic on the index: for an exact small non-negative integer k held in a float,
+// k*128 + 1.5*2^23 is exact (one genuine FFMA2 for both cells) and its bit pattern is 0x4B400000 + 128*k, i.e. a byte offset into the
+// 8-copy table (8 copies * 16 bytes per entry) plus a constant. The constant and the lane's copy are folded into the per-thread base
+// `Lb` (32-bit shared-memory address), so a look-up is one integer add and one LDS - no F2I (XU pipe), no shift, no mask.
+// k is in range by construction (see above; NaN and far-out inputs never get here: noise_lattice_in_range sends them to the scalar path).
+constexpr unsigned SIMPLEX_LUT_MAGIC_BITS = 0x4B400000u; // bits of 12582912.0f = 1.5*2^23
+__device__ __forceinline__ unsigned simplex_lut_base(const float4 *lut_s, unsigned lane) {
+	return (unsigned)__cvta_generic_to_shared(lut_s) + (lane & (SIMPLEX_LUT_COPIES - 1))*16u - SIMPLEX_LUT_MAGIC_BITS;
+}
+__device__ __forceinline__ f2 lut_offsets(f2 k) {return fma2(k, 16.0f*SIMPLEX_LUT_COPIES, 12582912.0f);}
+__device__ __forceinline__ float4 lut_load4(unsigned Lb, float off) {
+	float4 v; asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(Lb + __float_as_uint(off)));
+	return v;
+}
+__device__ __forceinline__ float lut_load_w(unsigned Lb, float off) {
+	float v; asm("ld.shared.f32 %0, [%1+12];" : "=f"(v) : "r"(Lb + __float_as_uint(off)));
+	return v;
+}
+
+// glm::simplex(vec2) for two positions with the table; Lb = simplex_lut_base()
+__device__ __forceinline__ f2 simplex2_lut(f2 vx, f2 vy, unsigned Lb) {
+	float const Cx = 0.211324865405187f, Cy = 0.366025403784439f, Cz = -0.577350269189626f;
+	f2 const s = add2(mul2(vx, Cy), mul2(vy, Cy));
+	f2 ix = floor2(add2(vx, s)), iy = floor2(add2(vy, s));
+	f2 const t = add2(mul2(ix, Cx), mul2(iy, Cx));
+	f2 const x0x = add2(sub2(vx, ix), t), x0y = add2(sub2(vy, iy), t);
+	f2 const i1x = make_float2((x0x.x > x0y.x) ? 1.0f : 0.0f, (x0x.y > x0y.y) ? 1.0f : 0.0f);
+	f2 const i1y = rsub2(1.0f, i1x); // (1,0) or (0,1)
+	f2 const x12x = sub2(add2(x0x, Cx), i1x), x12y = sub2(add2(x0y, Cx), i1y), x12z = add2(x0x, Cz), x12w = add2(x0y, Cz);
+	ix = mod_int289(ix); iy = mod_int289(iy);
+#if TW_SIMPLEX_LUT >= 2
+	f2 const j0 = lut_offsets(iy), j1 = lut_offsets(add2(iy, i1y)), j2 = lut_offsets(add2(iy, 1.0f));
+	f2 const q0 = make_float2(lut_load_w(Lb, j0.x), lut_load_w(Lb, j0.y)), q1 = make_float2(lut_load_w(Lb, j1.x), lut_load_w(Lb, j1.y)),
+	         q2 = make_float2(lut_load_w(Lb, j2.x), lut_load_w(Lb, j2.y));
+#else
+	f2 const q0 = permute(iy), q1 = permute(add2(iy, i1y)), q2 = permute(add2(iy, 1.0f));
+#endif
+	f2 const p0 = permute(add2(q0, ix)), p1 = permute(add2(add2(q1, ix), i1x)), p2 = permute(add2(add2(q2, ix), 1.0f));
+	f2 m0 = max0_2(rsub2(0.5f, add2(mul2(x0x, x0x), mul2(x0y, x0y))));
+	f2 m1 = max0_2(rsub2(0.5f, add2(mul2(x12x, x12x), mul2(x12y, x12y))));
+	f2 m2 = max0_2(rsub2(0.5f, add2(mul2(x12z, x12z), mul2(x12w, x12w))));
+	m0 = mul2(m0, m0); m1 = mul2(m1, m1); m2 = mul2(m2, m2);
+	m0 = mul2(m0, m0); m1 = mul2(m1, m1); m2 = mul2(m2, m2);
+	f2 const k0 = lut_offsets(p0), k1 = lut_offsets(p1), k2 = lut_offsets(p2);
+	float4 const g0a = lut_load4(Lb, k0.x), g0b = lut_load4(Lb, k0.y), g1a = lut_load4(Lb, k1.x), g1b = lut_load4(Lb, k1.y), g2a = lut_load4(Lb, k2.x), g2b = lut_load4(Lb, k2.y);
+	// the table values arrive one cell per register quad, so the products with them are plain scalar FMUL/FADD (same IEEE operations; the
+	// file is compiled with -fmad=false) - re-pairing them for packed instructions would cost more MOVs than the packed form saves
+	m0 = make_float2(m0.x*g0a.z, m0.y*g0b.z); m1 = make_float2(m1.x*g1a.z, m1.y*g1b.z); m2 = make_float2(m2.x*g2a.z, m2.y*g2b.z);
+	f2 const gx = make_float2(g0a.x*x0x.x  + g0a.y*x0y.x,  g0b.x*x0x.y  + g0b.y*x0y.y);
+	f2 const gy = make_float2(g1a.x*x12x.x + g1a.y*x12y.x, g1b.x*x12x.y + g1b.y*x12y.y);
+	f2 const gz = make_float2(g2a.x*x12z.x + g2a.y*x12w.x, g2b.x*x12z.y + g2b.y*x12w.y);
+	return mul2(add2(add2(mul2(m0, gx), mul2(m1, gy)), mul2(m2, gz)), 130.0f);
+}
+
 __device__ __forceinline__ void perlin2_corner(f2 ix, f2 iy, f2 &gx, f2 &gy) {
 	f2 const i = permute(add2(permute(ix), iy));
 	float const c41 = 1.0f/41.0f;
