@@ -195,29 +195,35 @@ __device__ __forceinline__ float dadd(float a, double b) {return (float)((double
 
 template<bool SIMPLEX, bool WARP, int SHAPE>
 __global__ void __launch_bounds__(256, TW_NOISE2_MIN_BLOCKS)
-noise_grid2_kernel(float *__restrict__ out, unsigned nx, unsigned ny, unsigned y_off, float mx0_single, float my0_single, const float2 *__restrict__ tile_origins,
+noise_grid2_kernel(float *__restrict__ out, unsigned nx, unsigned ny, unsigned y_off, unsigned y_end, float mx0_single, float my0_single, const float2 *__restrict__ tile_origins,
 	NoiseParams N, PostParams P, const float *__restrict__ sin_tab, unsigned *__restrict__ mm, const float4 *__restrict__ simplex_lut)
 {
 	unsigned L = 0;
 	if (SIMPLEX && TW_SIMPLEX_LUT > 0) { // hash/gradient table -> shared memory, 8 interleaved copies (see tw_noise2.cuh)
 		__shared__ float4 lut_s[twn2::SIMPLEX_LUT_N*twn2::SIMPLEX_LUT_COPIES];
-		int const tid = threadIdx.x + blockDim.x*threadIdx.y;
-		for (int e = tid; e < twn2::SIMPLEX_LUT_N*twn2::SIMPLEX_LUT_COPIES; e += blockDim.x*blockDim.y) {lut_s[e] = __ldg(simplex_lut + e/twn2::SIMPLEX_LUT_COPIES);}
+		for (int e = threadIdx.x; e < twn2::SIMPLEX_LUT_N*twn2::SIMPLEX_LUT_COPIES; e += blockDim.x) {lut_s[e] = __ldg(simplex_lut + e/twn2::SIMPLEX_LUT_COPIES);}
 		__syncthreads();
 		L = twn2::simplex_lut_base(lut_s, threadIdx.x);
 		asm volatile("" : "+r"(L) :: "memory"); // every table load depends on L, and L is defined after the barrier
 	}
-	unsigned const x = 2*(blockIdx.x*blockDim.x + threadIdx.x), y = y_off + blockIdx.y*blockDim.y + threadIdx.y, tile = blockIdx.z;
+	// cells are numbered row-major over the band [y_off, y_end) of the grid and dealt out in pairs (2t, 2t+1): no lanes idle on widths that are
+	// not a multiple of the block width (258-wide tiles wasted 27 % of a 64x8-cell block grid); a pair may straddle a row end when nx is odd
+	unsigned const tile = blockIdx.z;
+	size_t const c0 = (size_t)y_off*nx + 2*((size_t)blockIdx.x*blockDim.x + threadIdx.x), c_end = (size_t)y_end*nx;
+	unsigned y, x;
+	if (c_end <= 0xffffffffull) {unsigned const c32 = (unsigned)c0; y = c32/nx; x = c32 - y*nx;} // 32-bit division for every grid below 2^32 cells
+	else {y = (unsigned)(c0/nx); x = (unsigned)(c0 - (size_t)y*nx);}
+	unsigned const xb = (x + 1 < nx) ? x + 1 : 0, yb = (x + 1 < nx) ? y : y + 1;
 	float mx0 = mx0_single, my0 = my0_single;
 	if (tile_origins) {float2 const o = __ldg(tile_origins + tile); mx0 = o.x; my0 = o.y;}
-	bool const valid0 = (x < nx && y < ny), valid1 = (x + 1 < nx && y < ny);
+	bool const valid0 = (c0 < c_end), valid1 = (c0 + 1 < c_end);
 	float z0 = 0.0f, z1 = 0.0f;
-	if (valid0) { // the second cell of an odd-width row is computed (at x+1) and dropped
+	if (valid0) { // the second cell of an odd-sized band is computed and dropped
 		using namespace twn2;
-		float2 const xs = make_float2((float)x, (float)(x + 1));
+		float2 const xs = make_float2((float)x, (float)xb), ys = make_float2((float)y, (float)yb);
 		float2 const xval = mul2(add2(mul2(xs, P.mdx), mx0), P.dx_inv);           // (x*mdx + mx0)*DX_VAL_INV, src/mesh_gen.cpp:762
-		float const yval1 = ((float)y*P.mdy + my0)*P.dy_inv;
-		float2 xv = mul2(xval, N.xy_scale), yv = splat(N.xy_scale*yval1);             // get_noise_zval, src/mesh_gen.cpp:737-738
+		float2 const yval = mul2(add2(mul2(ys, P.mdy), my0), P.dy_inv);
+		float2 xv = mul2(xval, N.xy_scale), yv = mul2(yval, N.xy_scale);          // get_noise_zval, src/mesh_gen.cpp:737-738
 		if (WARP) { // domain warping, src/mesh_gen.cpp:740-747
 			float const scale = 0.2f;
 			float2 const dx1 = gen_noise2<SIMPLEX, SHAPE>(make_float2(dadd(xv.x, 0.0), dadd(xv.y, 0.0)), make_float2(dadd(yv.x, 0.0), dadd(yv.y, 0.0)), N, L);
@@ -228,18 +234,19 @@ noise_grid2_kernel(float *__restrict__ out, unsigned nx, unsigned ny, unsigned y
 			xv = add2(xv, mul2(dx2, scale)); yv = add2(yv, mul2(dy2, scale));
 		}
 		float2 const zz = gen_noise2<SIMPLEX, SHAPE>(xv, yv, N, L);
-		float const smy = (P.enable_glaciate && P.sine_on) ? cosf_lut(sin_tab, ((float)y*P.mdy + my0)*P.dy_inv*P.sm_freq) : 0.0f;
 		z0 = zz.x; z1 = zz.y;
 		if (P.need_postproc) {z0 = postproc_noise_zval(z0, P.h); z1 = postproc_noise_zval(z1, P.h);}
 		z0 = z0*N.hmap_scale; z1 = z1*N.hmap_scale;
-		float smx0 = 0.0f, smx1 = 0.0f;
+		float smx0 = 0.0f, smx1 = 0.0f, smy0 = 0.0f, smy1 = 0.0f;
 		if (P.enable_glaciate && P.sine_on) { // enable_glaciate() terms, src/mesh_gen.cpp:647-649
-			smx0 = P.sm_scale*cosf_lut(sin_tab, ((float)x*P.mdx + mx0)*P.dx_inv*P.sm_freq);
-			smx1 = P.sm_scale*cosf_lut(sin_tab, ((float)(x + 1)*P.mdx + mx0)*P.dx_inv*P.sm_freq);
+			smx0 = P.sm_scale*cosf_lut(sin_tab, xval.x*P.sm_freq);
+			smx1 = P.sm_scale*cosf_lut(sin_tab, xval.y*P.sm_freq);
+			smy0 = cosf_lut(sin_tab, yval.x*P.sm_freq);
+			smy1 = (yb == y) ? smy0 : cosf_lut(sin_tab, yval.y*P.sm_freq);
 		}
-		z0 = glaciate_and_bias(z0, smx0, smy, xval.x, yval1, P, sin_tab);
-		z1 = glaciate_and_bias(z1, smx1, smy, xval.y, yval1, P, sin_tab);
-		float *o = out + (size_t)tile*nx*ny + (size_t)y*nx + x;
+		z0 = glaciate_and_bias(z0, smx0, smy0, xval.x, yval.x, P, sin_tab);
+		z1 = glaciate_and_bias(z1, smx1, smy1, xval.y, yval.y, P, sin_tab);
+		float *o = out + (size_t)tile*nx*ny + c0;
 		if (valid1 && ((reinterpret_cast<size_t>(o) & 7) == 0)) {*reinterpret_cast<float2 *>(o) = make_float2(z0, z1);}
 		else {o[0] = z0; if (valid1) {o[1] = z1;}}
 	}
@@ -250,13 +257,13 @@ noise_grid2_kernel(float *__restrict__ out, unsigned nx, unsigned ny, unsigned y
 }
 
 template<bool SIMPLEX, bool WARP>
-void launch_noise2(int shape, dim3 grid, dim3 block, cudaStream_t st, float *out, unsigned nx, unsigned ny, unsigned y_off, float mx0, float my0,
+void launch_noise2(int shape, dim3 grid, dim3 block, cudaStream_t st, float *out, unsigned nx, unsigned ny, unsigned y_off, unsigned y_end, float mx0, float my0,
 	const float2 *origins, const NoiseParams &N, const PostParams &P, const float *tab, unsigned *mm, const float4 *lut)
 {
 	switch (shape) {
-	case 1:  noise_grid2_kernel<SIMPLEX, WARP, 1><<<grid, block, 0, st>>>(out, nx, ny, y_off, mx0, my0, origins, N, P, tab, mm, lut); break;
-	case 2:  noise_grid2_kernel<SIMPLEX, WARP, 2><<<grid, block, 0, st>>>(out, nx, ny, y_off, mx0, my0, origins, N, P, tab, mm, lut); break;
-	default: noise_grid2_kernel<SIMPLEX, WARP, 0><<<grid, block, 0, st>>>(out, nx, ny, y_off, mx0, my0, origins, N, P, tab, mm, lut); break;
+	case 1:  noise_grid2_kernel<SIMPLEX, WARP, 1><<<grid, block, 0, st>>>(out, nx, ny, y_off, y_end, mx0, my0, origins, N, P, tab, mm, lut); break;
+	case 2:  noise_grid2_kernel<SIMPLEX, WARP, 2><<<grid, block, 0, st>>>(out, nx, ny, y_off, y_end, mx0, my0, origins, N, P, tab, mm, lut); break;
+	default: noise_grid2_kernel<SIMPLEX, WARP, 0><<<grid, block, 0, st>>>(out, nx, ny, y_off, y_end, mx0, my0, origins, N, P, tab, mm, lut); break;
 	}
 }
 
@@ -524,10 +531,11 @@ int twi_heightgen(tw_ctx *ctx, const tw_grid2d *g, const tw_height_params *p, in
 			unsigned const r1 = (ny - r0 < band_rows) ? ny : r0 + band_rows;
 			static bool const use_scalar = (getenv("TW_NOISE_SCALAR") != nullptr); // A/B switch: one cell per thread, scalar FMUL/FADD
 			if (!use_scalar) { // two cells per thread on packed fp32x2 instructions
-				dim3 const block(32, 8, 1), grid((nx + 63)/64, (r1 - r0 + 7)/8, ntiles);
-				if (p->gen_mode == TW_MGEN_PERLIN) {launch_noise2<false, false>(p->gen_shape, grid, block, ctx->stream, d_out, nx, ny, r0, mx0, my0, d_tile_origins, N, P, ctx->d_sin_table, d_mm_ord, nullptr);}
-				else if (warp) {launch_noise2<true, true >(p->gen_shape, grid, block, ctx->stream, d_out, nx, ny, r0, mx0, my0, d_tile_origins, N, P, ctx->d_sin_table, d_mm_ord, lut);}
-				else           {launch_noise2<true, false>(p->gen_shape, grid, block, ctx->stream, d_out, nx, ny, r0, mx0, my0, d_tile_origins, N, P, ctx->d_sin_table, d_mm_ord, lut);}
+				size_t const band_cells = (size_t)(r1 - r0)*nx;
+				dim3 const block(256, 1, 1), grid((unsigned)((band_cells + 511)/512), 1, ntiles); // two cells per thread, cells numbered row-major
+				if (p->gen_mode == TW_MGEN_PERLIN) {launch_noise2<false, false>(p->gen_shape, grid, block, ctx->stream, d_out, nx, ny, r0, r1, mx0, my0, d_tile_origins, N, P, ctx->d_sin_table, d_mm_ord, nullptr);}
+				else if (warp) {launch_noise2<true, true >(p->gen_shape, grid, block, ctx->stream, d_out, nx, ny, r0, r1, mx0, my0, d_tile_origins, N, P, ctx->d_sin_table, d_mm_ord, lut);}
+				else           {launch_noise2<true, false>(p->gen_shape, grid, block, ctx->stream, d_out, nx, ny, r0, r1, mx0, my0, d_tile_origins, N, P, ctx->d_sin_table, d_mm_ord, lut);}
 				TW_LAUNCH_CHECK(ctx);
 				if (h_out_bands) {int const rc = band_copy(ctx, h_out_bands, d_out, nx, r0, r1); if (rc) return rc;}
 				continue;
