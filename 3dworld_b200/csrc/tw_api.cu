@@ -1,6 +1,7 @@
 // tw_api.cu - the extern "C" boundary (include/tw3d.h): context management, host/device pointer staging, and dispatch to the kernels.
 // There is deliberately NO CPU path in this library: without a CUDA device tw_create fails and nothing else can be called.
 #include "tw_internal.h"
+#include <algorithm>
 #include <stdarg.h>
 #include <stdlib.h>
 #include <new>
@@ -433,6 +434,68 @@ int tw_create_zvals_batch(tw_ctx *ctx, const int32_t *origins_xy, uint32_t ntile
 	TW_CUDA(ctx, cudaMemcpy(&h_steps, d_steps, sizeof(h_steps), cudaMemcpyDeviceToHost));
 	ctx->last_erosion_steps = h_steps;
 	if (mm) {rc = read_minmax(ctx, d_mm, mm, ntiles); if (rc) return rc;}
+	return TW_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ per-tile normals and ambient occlusion (N1)
+int tw_tile_normals_batch(tw_ctx *ctx, const float *zvals, uint32_t ntiles, uint32_t zvsize, float dx_val, float dy_val, uint8_t *rgba, float *min_normal_z) {
+	int rc = check_ctx(ctx); if (rc) return rc;
+	rc = finish_pending(ctx); if (rc) return rc;
+	if (!zvals || !rgba || ntiles == 0 || zvsize < 2) return tw_set_error(ctx, TW_ERR_ARG, "null/empty argument");
+	if (ntiles > 65535) return tw_set_error(ctx, TW_ERR_ARG, "at most 65535 tiles per call");
+	size_t const n = (size_t)ntiles*zvsize*zvsize, stride = zvsize - 1, out_bytes = (size_t)ntiles*stride*stride*4;
+	bool const dev_in = tw_is_device_ptr(zvals), dev_out = tw_is_device_ptr(rgba);
+	size_t const in_bytes = (n*sizeof(float) + 255) & ~(size_t)255, mn_bytes = ((size_t)ntiles*sizeof(unsigned) + 255) & ~(size_t)255;
+	rc = tw_reserve(ctx, 0, (dev_in ? 0 : in_bytes) + (dev_out ? 0 : out_bytes) + mn_bytes + 256); if (rc) return rc;
+	char *sp = (char *)ctx->d_scratch[0];
+	unsigned *d_mn = (unsigned *)sp; sp += mn_bytes;
+	const float *d_z = zvals;
+	if (!dev_in) {TW_CUDA(ctx, cudaMemcpyAsync(sp, zvals, n*sizeof(float), cudaMemcpyHostToDevice, ctx->stream)); d_z = (const float *)sp; sp += in_bytes;}
+	unsigned char *d_rgba = dev_out ? rgba : (unsigned char *)sp;
+	{
+		std::vector<unsigned> init(ntiles, tw_f2ord(1.0f)); // min_normal_z = 1.0, src/tiled_mesh.cpp:868
+		TW_CUDA(ctx, cudaMemcpyAsync(d_mn, init.data(), ntiles*sizeof(unsigned), cudaMemcpyHostToDevice, ctx->stream));
+		TW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	}
+	rc = twi_tile_normals(ctx, d_z, ntiles, zvsize, dx_val, dy_val, d_rgba, d_mn); if (rc) return rc;
+	if (!dev_out) {TW_CUDA(ctx, cudaMemcpyAsync(rgba, d_rgba, out_bytes, cudaMemcpyDeviceToHost, ctx->stream));}
+	std::vector<unsigned> mn(ntiles);
+	if (min_normal_z) {TW_CUDA(ctx, cudaMemcpyAsync(mn.data(), d_mn, ntiles*sizeof(unsigned), cudaMemcpyDeviceToHost, ctx->stream));}
+	TW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	if (min_normal_z) {for (uint32_t t = 0; t < ntiles; ++t) {min_normal_z[t] = tw_ord2f(mn[t]);}}
+	return TW_OK;
+}
+
+int tw_tile_ao_batch(tw_ctx *ctx, const float *zvals, const int32_t *origins_xy, uint32_t ntiles, int mesh_x_size, int mesh_y_size,
+                     float dx, float dy, uint32_t zvsize, const tw_height_params *p, float half_dxy, uint8_t *ao)
+{
+	int rc = check_ctx(ctx); if (rc) return rc;
+	rc = finish_pending(ctx); if (rc) return rc;
+	if (!zvals || !origins_xy || !p || !ao || ntiles == 0 || zvsize < 2) return tw_set_error(ctx, TW_ERR_ARG, "null/empty argument");
+	uint32_t const ray = 36, stride = zvsize - 1, csz = stride + 2*ray; // AO_RAY_LEN, context_sz (src/tiled_mesh.cpp:43,601)
+	size_t const tile_elems = (size_t)zvsize*zvsize, ctx_elems = (size_t)csz*csz, ao_elems = (size_t)stride*stride;
+	bool const dev_in = tw_is_device_ptr(zvals), dev_out = tw_is_device_ptr(ao);
+	// chunk of tiles whose context grids fit in ~2 GB
+	uint32_t chunk = (uint32_t)std::min<size_t>(ntiles, std::max<size_t>(1, ((size_t)2 << 30)/(ctx_elems*sizeof(float))));
+	if (chunk > 65535) chunk = 65535;
+	size_t const in_bytes = ((size_t)chunk*tile_elems*sizeof(float) + 255) & ~(size_t)255, cz_bytes = ((size_t)chunk*ctx_elems*sizeof(float) + 255) & ~(size_t)255;
+	size_t const ao_bytes = ((size_t)chunk*ao_elems + 255) & ~(size_t)255;
+	rc = tw_reserve(ctx, 0, (dev_in ? 0 : in_bytes) + cz_bytes + (dev_out ? 0 : ao_bytes) + 256); if (rc) return rc;
+	std::vector<int32_t> org(2*(size_t)chunk);
+	for (uint32_t t0 = 0; t0 < ntiles; t0 += chunk) {
+		uint32_t const nt = (ntiles - t0 < chunk) ? ntiles - t0 : chunk;
+		char *sp = (char *)ctx->d_scratch[0];
+		float *d_cz = (float *)sp; sp += cz_bytes;
+		const float *d_z = zvals + (size_t)t0*tile_elems;
+		if (!dev_in) {TW_CUDA(ctx, cudaMemcpyAsync(sp, d_z, (size_t)nt*tile_elems*sizeof(float), cudaMemcpyHostToDevice, ctx->stream)); d_z = (const float *)sp; sp += in_bytes;}
+		unsigned char *d_ao = dev_out ? ao + (size_t)t0*ao_elems : (unsigned char *)sp;
+		for (uint32_t t = 0; t < nt; ++t) {org[2*t] = origins_xy[2*(t0 + t)] - (int32_t)ray; org[2*t + 1] = origins_xy[2*(t0 + t) + 1] - (int32_t)ray;}
+		rc = tw_heightgen_tiles(ctx, org.data(), nt, mesh_x_size, mesh_y_size, dx, dy, csz, p, d_cz, nullptr); // device output: scratch slot 0 is not touched
+		if (rc) return rc;
+		rc = twi_tile_ao(ctx, d_z, d_cz, nt, zvsize, half_dxy, d_ao); if (rc) return rc;
+		if (!dev_out) {TW_CUDA(ctx, cudaMemcpyAsync(ao + (size_t)t0*ao_elems, d_ao, (size_t)nt*ao_elems, cudaMemcpyDeviceToHost, ctx->stream));}
+		TW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	}
 	return TW_OK;
 }
 

@@ -1,7 +1,10 @@
 // tw_tiles.cu - the pieces of the reference's callers that sit right next to the generators (sm_100a):
 //   tile_bounds_kernel     tail of tile_t::create_zvals (src/tiled_mesh.cpp:517-540): 4x4 sub-block min/max (inclusive ends), water bbox
 //   glaciate_mesh_kernel   glaciate() of the ground-mode mesh (src/mesh_gen.cpp:388-404): apply_glaciate + apply_mesh_sine per cell + zbottom/ztop
-// Both are single streaming passes over data that is already resident (4 B/cell read, glaciate also 4 B/cell written): HBM/L2-bound.
+//   tile_normals_kernel    tile_t::upload_normal_texture (src/tiled_mesh.cpp:865-880, get_norm src/tiled_mesh.h:281-284): RGBA8 normal map + min_normal_z
+//   tile_ao_kernel         tile_t::calc_mesh_ao_lighting (src/tiled_mesh.cpp:586-662): 8 directions x 8 steps of growing stride over the
+//                          tile's zvals and the (stride+72)^2 context generated around it
+// All are single streaming passes over data that is already resident (4 B/cell read, glaciate also 4 B/cell written): HBM/L2-bound.
 #include "tw_internal.h"
 
 namespace {
@@ -88,6 +91,59 @@ glaciate_mesh_kernel(float *__restrict__ mesh, GlacParams P, const float *__rest
 	if (mm && (threadIdx.x & 31) == 0 && vmin <= vmax) {atomicMin(mm, tw_f2ord(vmin)); atomicMax(mm + 1, tw_f2ord(vmax));}
 }
 
+
+// One thread per cell of the stride^2 normal map (stride = zvsize-1). get_norm_not_normalized(ix) = (DY_VAL*(z[ix] - z[ix+1]),
+// DX_VAL*(z[ix] - z[ix+zvsize]), dxdy), normalised by pointT::get_norm (src/3DWorld.h:297-300: unchanged when |v| < TOLERANCE), stored as
+// (unsigned char)(127.0*(n + 1.0)) (double arithmetic as in the reference), alpha 0.
+__global__ void __launch_bounds__(256)
+tile_normals_kernel(const float *__restrict__ zvals, unsigned zvsize, float dx_val, float dy_val, float dxdy, uchar4 *__restrict__ rgba, unsigned *__restrict__ min_nz) {
+	unsigned const stride = zvsize - 1, tile = blockIdx.y, i = blockIdx.x*blockDim.x + threadIdx.x;
+	float nzv = INFINITY;
+	if (i < stride*stride) {
+		unsigned const y = i/stride, x = i - y*stride, ix2 = y*zvsize + x;
+		const float *z = zvals + (size_t)tile*zvsize*zvsize;
+		float const z0 = __ldg(z + ix2);
+		float vx = dy_val*(z0 - __ldg(z + ix2 + 1)), vy = dx_val*(z0 - __ldg(z + ix2 + zvsize)), vz = dxdy;
+		float const vmag = __fsqrt_rn(vx*vx + vy*vy + vz*vz);
+		if (!(vmag < 1.0E-12f)) {vx = __fdiv_rn(vx, vmag); vy = __fdiv_rn(vy, vmag); vz = __fdiv_rn(vz, vmag);}
+		uchar4 o;
+		o.x = (unsigned char)(127.0*((double)vx + 1.0)); o.y = (unsigned char)(127.0*((double)vy + 1.0)); o.z = (unsigned char)(127.0*((double)vz + 1.0)); o.w = 0;
+		rgba[(size_t)tile*stride*stride + i] = o;
+		nzv = vz;
+	}
+	for (int o = 16; o > 0; o >>= 1) {nzv = fminf(nzv, __shfl_xor_sync(0xffffffffu, nzv, o));} // min(min_normal_z, norm.z): a NaN never replaces the minimum
+	if (min_nz && (threadIdx.x & 31) == 0 && nzv < INFINITY) {atomicMin(min_nz + tile, tw_f2ord(nzv));}
+}
+
+// One thread per cell of the stride^2 AO map. Heights inside the tile come from zvals, outside from the context grid czv
+// ((stride + 2*AO_RAY_LEN)^2, origin (x1 - AO_RAY_LEN, y1 - AO_RAY_LEN), generated by the same height function); the ray in direction d visits
+// v += step, step += dir (offsets 1, 3, 6, ... 36 cells) with z0 += dz per step, and the first higher point ends it: atten += 8 - s.
+constexpr int AO_DIRS = 8, AO_STEPS = 8, AO_RAY_LEN = AO_STEPS*(AO_STEPS + 1)/2; // src/tiled_mesh.cpp:41-43
+__global__ void __launch_bounds__(256)
+tile_ao_kernel(const float *__restrict__ zvals, const float *__restrict__ czv, unsigned zvsize, float dz, unsigned char *__restrict__ ao) {
+	unsigned const stride = zvsize - 1, csz = stride + 2*AO_RAY_LEN, tile = blockIdx.y, i = blockIdx.x*blockDim.x + threadIdx.x;
+	if (i >= stride*stride) return;
+	int const y = i/stride, x = i - y*stride;
+	const float *z = zvals + (size_t)tile*zvsize*zvsize, *c = czv + (size_t)tile*csz*csz;
+	float const zc = __ldg(z + y*zvsize + x);
+	unsigned atten = 0;
+#pragma unroll
+	for (int d = 0; d < AO_DIRS; ++d) {
+		int const k = (d < 4) ? d : d + 1, dx = k%3 - 1, dy = k/3 - 1; // ao_dirs order: y = -1..1 outer, x = -1..1 inner, skipping (0,0)
+		float z0 = zc;
+		int vx = x, vy = y, sx = dx, sy = dy;
+#pragma unroll
+		for (int s = 0; s < AO_STEPS; ++s) {
+			vx += sx; vy += sy; z0 += dz; sx += dx; sy += dy;
+			bool const inside = ((unsigned)vx < zvsize && (unsigned)vy < zvsize);
+			float const h = inside ? __ldg(z + vy*(int)zvsize + vx) : __ldg(c + (vy + AO_RAY_LEN)*(int)csz + vx + AO_RAY_LEN);
+			if (h > z0) {atten += AO_STEPS - s; break;} // hit a higher point
+		}
+	}
+	float const ao_scale = (float)(1.0 - (double)((float)atten/(float)(AO_DIRS*AO_STEPS)));
+	ao[(size_t)tile*stride*stride + i] = (unsigned char)(255.0*(double)ao_scale);
+}
+
 } // namespace
 
 int twi_tile_bounds(tw_ctx *ctx, const float *d_zvals, uint32_t ntiles, uint32_t zvsize, float wpz_max, void *d_sub /* ntiles*16*24 bytes */) {
@@ -107,6 +163,22 @@ int twi_glaciate_mesh(tw_ctx *ctx, float *d_mesh, int nx, int ny, int xoff2, int
 	P.volcano_freq = P.volcano_on ? p->mesh_scale/p->hmap.volcano_width : 0.0f; P.volcano_height = p->hmap.volcano_height;
 	P.nx = nx; P.ny = ny; P.x_shift = xoff2 - MX/2; P.y_shift = yoff2 - MY/2;
 	glaciate_mesh_kernel<<<dim3((nx + 255)/256, ny), 256, 0, ctx->stream>>>(d_mesh, P, ctx->d_sin_table, d_mm);
+	TW_LAUNCH_CHECK(ctx);
+	return TW_OK;
+}
+
+int twi_tile_normals(tw_ctx *ctx, const float *d_zvals, uint32_t ntiles, uint32_t zvsize, float dx_val, float dy_val, unsigned char *d_rgba, unsigned *d_min_nz_ord) {
+	unsigned const stride = zvsize - 1;
+	tile_normals_kernel<<<dim3((stride*stride + 255)/256, ntiles), 256, 0, ctx->stream>>>(d_zvals, zvsize, dx_val, dy_val, dx_val*dy_val /* dxdy, src/matrix_ops.cpp:80 */,
+		(uchar4 *)d_rgba, d_min_nz_ord);
+	TW_LAUNCH_CHECK(ctx);
+	return TW_OK;
+}
+
+int twi_tile_ao(tw_ctx *ctx, const float *d_zvals, const float *d_czv, uint32_t ntiles, uint32_t zvsize, float half_dxy, unsigned char *d_ao) {
+	unsigned const stride = zvsize - 1;
+	float const dz = (float)(0.5*half_dxy); // src/tiled_mesh.cpp:612
+	tile_ao_kernel<<<dim3((stride*stride + 255)/256, ntiles), 256, 0, ctx->stream>>>(d_zvals, d_czv, zvsize, dz, d_ao);
 	TW_LAUNCH_CHECK(ctx);
 	return TW_OK;
 }

@@ -248,6 +248,21 @@ inline void create_zvals_batch(const int32_t *origins_xy, unsigned ntiles, unsig
 	if (rc != TW_OK) {detail::fail(rc, "create_zvals_batch", c);}
 }
 
+// tile_t::upload_normal_texture (src/tiled_mesh.cpp:865-880, minus the GL upload) and tile_t::calc_mesh_ao_lighting (:586-662) for a batch of
+// finished tiles: normal_data = ntiles*stride^2*4 bytes (RGBA, alpha 0), ao_lighting = ntiles*stride^2 bytes, stride = zvsize-1
+inline void tile_normals(const float *zvals, unsigned ntiles, unsigned zvsize, float dx_val, float dy_val, unsigned char *normal_data, float *min_normal_z = nullptr) {
+	tw_ctx *c = ctx();
+	int const rc = tw_tile_normals_batch(c, zvals, ntiles, zvsize, dx_val, dy_val, normal_data, min_normal_z);
+	if (rc != TW_OK) {detail::fail(rc, "tile_normals", c);}
+}
+inline void tile_ao_lighting(const float *zvals, const int32_t *origins_xy, unsigned ntiles, unsigned zvsize, float dx, float dy, unsigned char *ao_lighting) {
+	scene_globals const &g = globals();
+	tw_height_params const p = height_params_from_globals(g.mesh_gen_mode, g.mesh_gen_shape);
+	tw_ctx *c = ctx();
+	int const rc = tw_tile_ao_batch(c, zvals, origins_xy, ntiles, g.MESH_X_SIZE, g.MESH_Y_SIZE, dx, dy, zvsize, &p, g.HALF_DXY, ao_lighting);
+	if (rc != TW_OK) {detail::fail(rc, "tile_ao_lighting", c);}
+}
+
 // ------------------------------------------------------------------------------------------------ gen_mesh (ground mode)
 // gen_mesh(surface_type=0, keep_sin_table=0, update_zvals=1) for WMODE_GROUND (src/mesh_gen.cpp:257-355): regenerates the sine table from
 // the function-static generator state (pass the same tw_rng across calls), fills mesh_height, estimates zmax_est from a 128x128 probe of the

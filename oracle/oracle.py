@@ -104,6 +104,8 @@ def lib():
         L.to_gen_mesh.argtypes = [C.POINTER(Rng), C.POINTER(HeightParams), C.c_int, C.c_int, C.c_float, C.c_float, C.c_int, C.c_int, C.c_int, C.c_int,
                                   C.c_float, C.c_float, C.c_float, C.c_float, C.c_uint, C.POINTER(ErosionParams), vp, vp, vp, vp]
         L.to_tile_bounds.argtypes = [vp, C.c_uint, C.c_uint, C.c_float, C.c_float, C.c_float, C.c_uint, vp]
+        L.to_tile_normals.argtypes = [vp, C.c_uint, C.c_uint, C.c_float, C.c_float, vp, vp]
+        L.to_tile_ao.argtypes = [vp, vp, C.c_uint, C.c_uint, C.c_float, vp]
         L.to_eval_points.argtypes = [vp, C.c_size_t, C.POINTER(HeightParams), C.POINTER(PointQuery), vp, vp, vp]
         L.to_apply_erosion.argtypes = [vp, C.c_int, C.c_int, C.c_float, C.c_uint, C.POINTER(ErosionParams)]
         L.to_apply_erosion.restype = C.c_ulonglong
@@ -179,6 +181,26 @@ def tile_bounds(tiles, wpz_max, dx_val, dy_val, size):
     out = (TileBounds * nt)()
     lib().to_tile_bounds(_p(tiles), nt, zv, wpz_max, dx_val, dy_val, size, C.cast(out, C.c_void_p))
     return out
+
+
+def tile_normals(tiles, dx_val, dy_val):
+    tiles = np.ascontiguousarray(tiles, np.float32)
+    nt, zv = tiles.shape[0], tiles.shape[1]
+    rgba = np.empty((nt, zv - 1, zv - 1, 4), np.uint8)
+    mnz = np.empty(nt, np.float32)
+    lib().to_tile_normals(_p(tiles), nt, zv, dx_val, dy_val, _p(rgba), _p(mnz))
+    return rgba, mnz
+
+
+def tile_ao(tiles, contexts, half_dxy):
+    """contexts: [nt, stride+72, stride+72] heights generated at origin (x1-36, y1-36) (heightgen_2d of the shifted, enlarged grid)."""
+    tiles = np.ascontiguousarray(tiles, np.float32)
+    contexts = np.ascontiguousarray(contexts, np.float32)
+    nt, zv = tiles.shape[0], tiles.shape[1]
+    assert contexts.shape == (nt, zv - 1 + 72, zv - 1 + 72)
+    ao = np.empty((nt, zv - 1, zv - 1), np.uint8)
+    lib().to_tile_ao(_p(tiles), _p(contexts), nt, zv, half_dxy, _p(ao))
+    return ao
 
 
 def eval_points(xy, hp, pq, sine_params=None):

@@ -113,6 +113,15 @@ def heightgen(x0, y0, dx, dy, nx, ny, cache_values=0, glaciate=1, min_start_sin=
     return out
 
 
+def tile_normals(tile, dx_val, dy_val):
+    tile = np.ascontiguousarray(tile, np.float32)
+    zv = tile.shape[0]
+    rgba = np.empty((zv - 1, zv - 1, 4), np.uint8)
+    mnz = C.c_float(0.0)
+    lib().ref_tile_normals(tile.ctypes.data_as(C.c_void_p), zv, C.c_float(dx_val), C.c_float(dy_val), rgba.ctypes.data_as(C.c_void_p), C.byref(mnz))
+    return rgba, mnz.value
+
+
 def eval_points(kind, xy, xy_scale=1.0, no_xyoff=0, xoff2=0, yoff2=0):
     """kind 0/1/2 = eval_mesh_sin_terms / eval_mesh_sin_terms_scaled / get_exact_zval of the reference for every (x, y) row."""
     xy = np.ascontiguousarray(xy, np.float32).reshape(-1, 2)

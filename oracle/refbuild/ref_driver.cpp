@@ -112,6 +112,23 @@ float ref_eval_mesh_sin_terms(float xv, float yv) {return eval_mesh_sin_terms(xv
 float ref_get_water_z_height() {return get_water_z_height();}
 // point queries: eval_mesh_sin_terms_scaled / get_exact_zval, procedural branch (no heightmap texture, no landscape file)
 float ref_eval_mesh_sin_terms_scaled(float xval, float yval, float xy_scale) {return eval_mesh_sin_terms_scaled(xval, yval, xy_scale);}
+// tile_t::upload_normal_texture's per-cell arithmetic (src/tiled_mesh.cpp:865-880) with the reference's own vector3d::get_norm(), min() and
+// UNROLL_3X from 3DWorld.h; the loop/indexing is the driver's (tiled_mesh.cpp itself cannot be linked), get_norm_not_normalized as src/tiled_mesh.h:281-283
+void ref_tile_normals(const float *zvals, unsigned zvsize, float dx_val, float dy_val, unsigned char *normal_data, float *min_normal_z_out) {
+	unsigned const stride(zvsize - 1);
+	float const dxdy_(dx_val*dy_val);
+	float min_normal_z(1.0);
+	for (unsigned y = 0; y < stride; ++y) {
+		for (unsigned x = 0; x < stride; ++x) {
+			unsigned const ix(y*stride + x), ix2(y*zvsize + x), ix_off(4*ix);
+			vector3d const norm(vector3d(dy_val*(zvals[ix2] - zvals[ix2 + 1]), dx_val*(zvals[ix2] - zvals[ix2 + zvsize]), dxdy_).get_norm());
+			min_normal_z = min(min_normal_z, norm.z);
+			UNROLL_3X(normal_data[ix_off+i_] = (unsigned char)(127.0*(norm[i_] + 1.0)););
+			normal_data[ix_off+3] = 0;
+		}
+	}
+	*min_normal_z_out = min_normal_z;
+}
 // kind 0/1/2 = eval_mesh_sin_terms / eval_mesh_sin_terms_scaled / get_exact_zval for n points (the loop is the driver's; each value is the reference's)
 void ref_eval_points(int kind, const float *xy, size_t n, float xy_scale, int no_xyoff, int xo, int yo, float *out) {
 	int const xs(xoff2), ys(yoff2);

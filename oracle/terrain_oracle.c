@@ -634,6 +634,67 @@ unsigned long long to_apply_erosion(float *heightmap, int xsize, int ysize, floa
 }
 
 
+/* ------------------------------------------------------------------ per-tile normals and AO (ref: src/tiled_mesh.cpp:586-662,865-880; src/tiled_mesh.h:281-284)
+ * tiled_mesh.cpp cannot be linked into oracle/_ref (it pulls in the renderer), so these two loops are restatements; the normal arithmetic
+ * is pinned against the reference's own vector3d::get_norm() through oracle/_ref (ref_tile_normals), the AO loop is integer logic on pinned heights. */
+void to_tile_normals(const float *zvals_all, unsigned ntiles, unsigned zvsize, float dx_val, float dy_val, unsigned char *rgba, float *min_normal_z) {
+	unsigned const stride = zvsize - 1;
+	float const dxdy = dx_val*dy_val; /* ref: src/matrix_ops.cpp:80 */
+	for (unsigned t = 0; t < ntiles; ++t) {
+		const float *zvals = zvals_all + (size_t)t*zvsize*zvsize;
+		unsigned char *out = rgba + (size_t)t*stride*stride*4;
+		float mnz = 1.0f;
+		for (unsigned y = 0; y < stride; ++y) {
+			for (unsigned x = 0; x < stride; ++x) {
+				unsigned const ix = y*stride + x, ix2 = y*zvsize + x;
+				float n[3] = {dy_val*(zvals[ix2] - zvals[ix2 + 1]), dx_val*(zvals[ix2] - zvals[ix2 + zvsize]), dxdy}; /* get_norm_not_normalized */
+				float const vmag = sqrtf(n[0]*n[0] + n[1]*n[1] + n[2]*n[2]);
+				if (!(vmag < 1.0E-12f)) {n[0] /= vmag; n[1] /= vmag; n[2] /= vmag;} /* pointT::get_norm, src/3DWorld.h:297-300 */
+				mnz = std_min(mnz, n[2]);
+				for (int i = 0; i < 3; ++i) {out[4*ix + i] = (unsigned char)(127.0*(n[i] + 1.0));}
+				out[4*ix + 3] = 0;
+			}
+		}
+		if (min_normal_z) {min_normal_z[t] = mnz;}
+	}
+}
+/* czv_all: ntiles context grids of (stride + 72)^2 heights at origin (x1 - 36, y1 - 36) */
+void to_tile_ao(const float *zvals_all, const float *czv_all, unsigned ntiles, unsigned zvsize, float half_dxy, unsigned char *ao) {
+	enum {NUM_AO_DIRS = 8, NUM_AO_STEPS = 8, AO_RAY_LEN = 36};
+	unsigned const stride = zvsize - 1, context_sz = stride + 2*AO_RAY_LEN;
+	int dirs[NUM_AO_DIRS][2], ix = 0;
+	for (int y = -1; y <= 1; ++y) {for (int x = -1; x <= 1; ++x) {if (x != 0 || y != 0) {dirs[ix][0] = x; dirs[ix][1] = y; ++ix;}}}
+	float const dz = (float)(0.5*half_dxy);
+	for (unsigned t = 0; t < ntiles; ++t) {
+		const float *zvals = zvals_all + (size_t)t*zvsize*zvsize, *gen = czv_all + (size_t)t*context_sz*context_sz;
+		float *czv = (float *)malloc((size_t)context_sz*context_sz*sizeof(float));
+		for (int y = 0; y < (int)context_sz; ++y) { /* ref: :624-637 */
+			for (int x = 0; x < (int)context_sz; ++x) {
+				int const xv = x - AO_RAY_LEN, yv = y - AO_RAY_LEN;
+				czv[y*context_sz + x] = (xv >= 0 && yv >= 0 && xv < (int)zvsize && yv < (int)zvsize) ? zvals[yv*zvsize + xv] : gen[y*context_sz + x];
+			}
+		}
+		for (int y = 0; y < (int)stride; ++y) { /* ref: :640-659 */
+			for (int x = 0; x < (int)stride; ++x) {
+				unsigned atten = 0;
+				for (unsigned d = 0; d < NUM_AO_DIRS; ++d) {
+					float z0 = zvals[y*zvsize + x];
+					int sx = dirs[d][0], sy = dirs[d][1], vx = x, vy = y;
+					for (unsigned s = 0; s < NUM_AO_STEPS; ++s) {
+						vx += sx; vy += sy;
+						z0 += dz;
+						sx += dirs[d][0]; sy += dirs[d][1];
+						if (czv[(vy + AO_RAY_LEN)*context_sz + (vx + AO_RAY_LEN)] > z0) {atten += (NUM_AO_STEPS - s); break;}
+					}
+				}
+				float const ao_scale = 1.0 - (float)atten/(float)(NUM_AO_DIRS*NUM_AO_STEPS);
+				ao[(size_t)t*stride*stride + y*stride + x] = (unsigned char)(255.0*ao_scale);
+			}
+		}
+		free(czv);
+	}
+}
+
 /* ------------------------------------------------------------------ point queries (ref: src/mesh_gen.cpp:797-847) */
 static float eval_mesh_sin_terms_scaled(float xval, float yval, float xy_scale, int MX, int MY, const tw_height_params *p, const float *tab, const float *T) { /* ref: :807-813 */
 	float const xv = xy_scale*(xval - (float)(MX >> 1)), yv = xy_scale*(yval - (float)(MY >> 1));

@@ -64,6 +64,9 @@ void to_gen_mesh(tw_rng *sine_rng, tw_height_params *p_inout, int mesh_x_size, i
 void to_tile_bounds(const float *zvals, unsigned ntiles, unsigned zvsize, float wpz_max, float dx_val, float dy_val, unsigned size, tw_tile_bounds *out);
 
 /* apply_erosion, src/erosion.cpp:14-164 (serial droplet order) ; returns total droplet steps */
+/* tile_t::upload_normal_texture / calc_mesh_ao_lighting (src/tiled_mesh.cpp:865-880, 586-662); czv = generated context grids (stride+72)^2 per tile */
+void to_tile_normals(const float *zvals, unsigned ntiles, unsigned zvsize, float dx_val, float dy_val, unsigned char *rgba, float *min_normal_z);
+void to_tile_ao(const float *zvals, const float *czv, unsigned ntiles, unsigned zvsize, float half_dxy, unsigned char *ao);
 /* eval_mesh_sin_terms / eval_mesh_sin_terms_scaled / get_exact_zval (procedural branch) for n points, src/mesh_gen.cpp:797-847 */
 void to_eval_points(const float *xy, size_t n, const tw_height_params *p, const tw_point_query *q, const float *sin_table, const float *sine_params450, float *out);
 unsigned long long to_apply_erosion(float *heightmap, int xsize, int ysize, float min_zval, unsigned num_iters, const tw_erosion_params *p);

@@ -102,3 +102,47 @@ def _oracle_proc_gen_sp(oracle, cfg, hp, w, h, iters, ep, sp):
         return _oracle_proc_gen(oracle, cfg, hp_o, w, h, iters, ep_o)
     finally:
         oracle.heightgen_2d = orig
+
+
+@pytest.mark.parametrize("mode", [0, 1, 4])
+def test_tile_normals_and_ao_golden(tw, ctx, mode):
+    """N1: normal map (the reference's own get_norm arithmetic) and AO (restated ray march on reference heights) of the golden tile."""
+    from test_oracle_golden import tile_case
+    h = np.load(os.path.join(GOLD, "tiles.npz"))
+    n = "m%d" % mode
+    hp, sp, a = tile_case(tw, h, mode)
+    if sp is not None:
+        ctx.set_sine_params(sp)
+    x1, y1, S, zv, dx, dy, half_dxy = int(a[1]), int(a[2]), int(a[3]), int(a[4]), float(a[5]), float(a[6]), float(a[7])
+    tile = h["tile_" + n]
+    rgba, mnz = ctx.tile_normals(tile[None], dx, dy)
+    assert np.array_equal(rgba[0], h["normals_" + n]) and mnz[0] == h["min_normal_z_" + n]
+    ao = ctx.tile_ao(tile[None], [(x1, y1)], (S, S), dx, dy, hp, half_dxy)
+    assert np.array_equal(ao[0], h["ao_" + n])
+
+
+def test_tile_normals_and_ao_batch_vs_oracle(tw, scene, oracle, ctx, beq):
+    """A batch of eroded tiles, host and device pointers, vs the oracle (context grids from the oracle's heightgen)."""
+    import torch
+    cfg = scene.SceneConfig(mesh_gen_mode=1, mesh_freq_filter=1, mesh_seed=1, hmap=HM_CFG, zmax_est=2.3, mesh_size=(128, 128, 1))
+    hp, ep = cfg.height_params(), cfg.erosion_params()
+    S, zv = 128, 130
+    dx, dy = float(cfg.dx_val), float(cfg.dy_val)
+    origins = [(tx * S, ty * S - 640) for ty in range(2) for tx in range(3)]
+    tiles = ctx.create_zvals_batch(origins, cfg.mesh_size, dx, dy, zv, hp, 200, ep, ep.zmin)
+    hp_o = convert(hp, oracle.HeightParams)
+    csz = zv - 1 + 72
+    contexts = np.stack([oracle.heightgen_2d(oracle.Grid2D(x1 - 36 - S // 2, y1 - 36 - S // 2, dx, dy, csz, csz), hp_o, None, 1, 0) for x1, y1 in origins])
+    exp_n, exp_m = oracle.tile_normals(tiles, dx, dy)
+    exp_ao = oracle.tile_ao(tiles, contexts, 0.0625)
+    rgba, mnz = ctx.tile_normals(tiles, dx, dy)
+    assert np.array_equal(rgba, exp_n) and beq(mnz, exp_m) == 0
+    ao = ctx.tile_ao(tiles, origins, cfg.mesh_size, dx, dy, hp, 0.0625)
+    assert np.array_equal(ao, exp_ao)
+    assert ao.min() < ao.max() == 255
+    d_tiles = torch.from_numpy(tiles).cuda()
+    d_rgba = torch.empty((len(origins), zv - 1, zv - 1, 4), dtype=torch.uint8, device="cuda")
+    d_ao = torch.empty((len(origins), zv - 1, zv - 1), dtype=torch.uint8, device="cuda")
+    ctx.tile_normals(d_tiles, dx, dy, out=d_rgba)
+    ctx.tile_ao(d_tiles, origins, cfg.mesh_size, dx, dy, hp, 0.0625, out=d_ao)
+    assert np.array_equal(d_rgba.cpu().numpy(), exp_n) and np.array_equal(d_ao.cpu().numpy(), exp_ao)

@@ -102,6 +102,29 @@ def test_point_queries(oracle, beq):
         assert beq(oracle.eval_points(xy, hp, pq, sp), exp) == 0, key
 
 
+def tile_case(mod, h, mode):
+    """(HeightParams, sine_params, args) of a tiles.npz case: mesh 64x64, scene 4 => DX_VAL 0.125, mesh_freq_filter 1, seed 1, HM_CFG, zmax_est 2.3."""
+    n = "m%d" % mode
+    hp = hp_from_args(mod, [mode, 0, 1, 1], [1000.0, 0, 0, 0, 1000.0, 0, 0, 0, 0, 5.0, 0.001, -4.0, 0, 0])
+    hp.dx_val_inv = hp.dy_val_inv = 8.0
+    return hp, (h["sp_" + n] if mode == 0 else None), h["args_" + n]
+
+
+def test_tile_normals_and_ao(oracle, beq):
+    h = load("tiles.npz")
+    for mode in (0, 1, 4):
+        n = "m%d" % mode
+        hp, sp, a = tile_case(oracle, h, mode)
+        x1, y1, S, zv, dx, dy, half_dxy = int(a[1]), int(a[2]), int(a[3]), int(a[4]), float(a[5]), float(a[6]), float(a[7])
+        tile = oracle.heightgen_2d(oracle.Grid2D(x1 - S // 2, y1 - S // 2, dx, dy, zv, zv), hp, sp, 1, 0)
+        assert beq(tile, h["tile_" + n]) == 0
+        rgba, mnz = oracle.tile_normals(tile[None], dx, dy)
+        assert np.array_equal(rgba[0], h["normals_" + n]) and mnz[0] == h["min_normal_z_" + n]
+        csz = zv - 1 + 72
+        context = oracle.heightgen_2d(oracle.Grid2D(x1 - 36 - S // 2, y1 - 36 - S // 2, dx, dy, csz, csz), hp, sp, 1, 0)
+        assert np.array_equal(oracle.tile_ao(tile[None], context[None], half_dxy)[0], h["ao_" + n])
+
+
 def test_erosion(oracle, beq):
     e = load("erosion.npz")
     for key_in, keys in (("in0", ["0_%d" % i for i in range(3)]), ("mesh128_in", ["mesh128"])):

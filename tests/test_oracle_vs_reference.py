@@ -73,6 +73,23 @@ def test_point_queries(oracle, ref, beq):
                     assert beq(zr, zo) == 0, (mode, shape, ff, kind, xy_scale, no_xyoff)
 
 
+def test_tile_normals(oracle, ref, beq):
+    """the normal-map arithmetic (get_norm via the reference's vector3d, byte quantisation, min_normal_z) vs the oracle."""
+    rng = np.random.default_rng(11)
+    ref.setup(mode=1, freq_filter=1, seed=1, zmax_est=2.0, hmap=HM_CFG)
+    RL = ref.lib()
+    tiles = [ref.heightgen(100.0, -300.0, RL.ref_get_dx(), RL.ref_get_dy(), 66, 66, 0, 1),
+             np.zeros((10, 10), np.float32),                                                # flat: normal (0, 0, 1) -> 127, 127, 254
+             (rng.standard_normal((34, 34)) * 50).astype(np.float32),                       # near-vertical faces
+             (rng.standard_normal((18, 18)) * 1e-4).astype(np.float32)]
+    for dxv, dyv in ((0.0625, 0.0625), (0.25, 0.03125)):
+        for t in tiles:
+            rr, rm = ref.tile_normals(t, dxv, dyv)
+            orr, om = oracle.tile_normals(t[None], dxv, dyv)
+            assert np.array_equal(rr, orr[0]) and np.float32(rm) == om[0]
+    assert np.array_equal(oracle.tile_normals(tiles[1][None], 0.0625, 0.0625)[0][0, 0, 0], [127, 127, 254, 0])
+
+
 def test_erosion_serial_order(oracle, ref, beq):
     ref.lib().ref_set_threads(1)
     ref.setup(mode=1, freq_filter=1, seed=1, zmax_est=2.0, hmap=HM_CFG)
