@@ -181,7 +181,7 @@ __device__ __forceinline__ float2 gen_noise2(float2 xv, float2 yv, const NoisePa
 #pragma unroll 1
 		for (int i = 0; i < N.octaves; ++i) {
 			float2 const px = twn2::add2(twn2::mul2(xv, N.freq[i]), N.rx[i]), py = twn2::add2(twn2::mul2(yv, N.freq[i]), N.ry[i]);
-			float2 noise = SIMPLEX ? ((TW_SIMPLEX_LUT > 0) ? twn2::simplex2_lut(px, py, L) : twn2::simplex2(px, py)) : twn2::perlin2(px, py);
+			float2 noise = SIMPLEX ? ((TW_SIMPLEX_LUT > 0) ? twn2::simplex2_lut(px, py, L) : twn2::simplex2(px, py)) : ((TW_SIMPLEX_LUT > 0) ? twn2::perlin2_lut(px, py, L) : twn2::perlin2(px, py));
 			if (SHAPE == 1) {noise = make_float2((float)((double)fabsf(noise.x) - 0.40), (float)((double)fabsf(noise.y) - 0.40));}
 			if (SHAPE == 2) {noise = make_float2((float)(0.45 - (double)fabsf(noise.x)), (float)(0.45 - (double)fabsf(noise.y)));}
 			zval = twn2::fma2(noise, N.mag[i], zval); // mag is a power of two: exact product
@@ -199,7 +199,7 @@ noise_grid2_kernel(float *__restrict__ out, unsigned nx, unsigned ny, unsigned y
 	NoiseParams N, PostParams P, const float *__restrict__ sin_tab, unsigned *__restrict__ mm, const float4 *__restrict__ simplex_lut)
 {
 	unsigned L = 0;
-	if (SIMPLEX && TW_SIMPLEX_LUT > 0) { // hash/gradient table -> shared memory, 8 interleaved copies (see tw_noise2.cuh)
+	if (TW_SIMPLEX_LUT > 0) { // hash/gradient table (simplex or Perlin flavour) -> shared memory, 8 interleaved copies (see tw_noise2.cuh)
 		__shared__ float4 lut_s[twn2::SIMPLEX_LUT_N*twn2::SIMPLEX_LUT_COPIES];
 		for (int e = threadIdx.x; e < twn2::SIMPLEX_LUT_N*twn2::SIMPLEX_LUT_COPIES; e += blockDim.x) {lut_s[e] = __ldg(simplex_lut + e/twn2::SIMPLEX_LUT_COPIES);}
 		__syncthreads();
@@ -267,13 +267,13 @@ void launch_noise2(int shape, dim3 grid, dim3 block, cudaStream_t st, float *out
 	}
 }
 
-__global__ void simplex_lut_kernel(float4 *__restrict__ lut) {
+__global__ void simplex_lut_kernel(float4 *__restrict__ lut) { // [0, N): simplex table, [N, 2N): Perlin table
 	int const k = blockIdx.x*blockDim.x + threadIdx.x;
-	if (k < twn2::SIMPLEX_LUT_N) {lut[k] = twn2::simplex_lut_entry((float)k);}
+	if (k < twn2::SIMPLEX_LUT_N) {lut[k] = twn2::simplex_lut_entry((float)k); lut[twn2::SIMPLEX_LUT_N + k] = twn2::perlin_lut_entry((float)k);}
 }
 static int ensure_simplex_lut(tw_ctx *ctx) {
 	if (ctx->d_simplex_lut) return TW_OK;
-	TW_CUDA(ctx, cudaMalloc(&ctx->d_simplex_lut, twn2::SIMPLEX_LUT_N*sizeof(float4)));
+	TW_CUDA(ctx, cudaMalloc(&ctx->d_simplex_lut, 2*twn2::SIMPLEX_LUT_N*sizeof(float4)));
 	simplex_lut_kernel<<<(twn2::SIMPLEX_LUT_N + 127)/128, 128, 0, ctx->stream>>>((float4 *)ctx->d_simplex_lut);
 	TW_LAUNCH_CHECK(ctx);
 	return TW_OK;
@@ -524,8 +524,8 @@ int twi_heightgen(tw_ctx *ctx, const tw_grid2d *g, const tw_height_params *p, in
 		bool simplex = false;
 		if (!make_noise_params(p, N, simplex)) return tw_set_error(ctx, TW_ERR_ARG, "start_eval_sin %d out of range", p->start_eval_sin);
 		bool const warp = (p->gen_mode == TW_MGEN_DWARP_GPU);
-		if (simplex) {int const rc = ensure_simplex_lut(ctx); if (rc) return rc;}
-		const float4 *lut = (const float4 *)ctx->d_simplex_lut;
+		{int const rc = ensure_simplex_lut(ctx); if (rc) return rc;}
+		const float4 *lut = (const float4 *)ctx->d_simplex_lut + (simplex ? 0 : twn2::SIMPLEX_LUT_N);
 		unsigned const band_rows = band_rows_for(ctx, ny, nx, h_out_bands != nullptr && ntiles == 1);
 		for (unsigned r0 = 0; r0 < ny; r0 += band_rows) {
 			unsigned const r1 = (ny - r0 < band_rows) ? ny : r0 + band_rows;
@@ -533,7 +533,7 @@ int twi_heightgen(tw_ctx *ctx, const tw_grid2d *g, const tw_height_params *p, in
 			if (!use_scalar) { // two cells per thread on packed fp32x2 instructions
 				size_t const band_cells = (size_t)(r1 - r0)*nx;
 				dim3 const block(256, 1, 1), grid((unsigned)((band_cells + 511)/512), 1, ntiles); // two cells per thread, cells numbered row-major
-				if (p->gen_mode == TW_MGEN_PERLIN) {launch_noise2<false, false>(p->gen_shape, grid, block, ctx->stream, d_out, nx, ny, r0, r1, mx0, my0, d_tile_origins, N, P, ctx->d_sin_table, d_mm_ord, nullptr);}
+				if (p->gen_mode == TW_MGEN_PERLIN) {launch_noise2<false, false>(p->gen_shape, grid, block, ctx->stream, d_out, nx, ny, r0, r1, mx0, my0, d_tile_origins, N, P, ctx->d_sin_table, d_mm_ord, lut);}
 				else if (warp) {launch_noise2<true, true >(p->gen_shape, grid, block, ctx->stream, d_out, nx, ny, r0, r1, mx0, my0, d_tile_origins, N, P, ctx->d_sin_table, d_mm_ord, lut);}
 				else           {launch_noise2<true, false>(p->gen_shape, grid, block, ctx->stream, d_out, nx, ny, r0, r1, mx0, my0, d_tile_origins, N, P, ctx->d_sin_table, d_mm_ord, lut);}
 				TW_LAUNCH_CHECK(ctx);

@@ -214,4 +214,36 @@ __device__ __forceinline__ f2 perlin2(f2 Px, f2 Py) {
 	return mul2(mix2(nx0, nx1, fdy), 2.3f);
 }
 
+// ---- Perlin with the same kind of table: {gx*n, gy*n, 0, permute(k)} for the hashed lattice index k (gradient of glm::perlin(vec2):
+// g = 2*fract(k/41) - 1, gy = |g| - 0.5, gx = g - floor(g + 0.5), both scaled by taylorInvSqrt(gx*gx + gy*gy)), k in [0, 288]; .w as above ----
+__device__ __forceinline__ float4 perlin_lut_entry(float k) {
+	float const g = twn::two_f_minus_1(twn::fract(twn::div41_small(k)));
+	float gy = fabsf(g) - 0.5f, gx = g - floorf(g + 0.5f);
+	float const n = twn::tinvsqrt(gx*gx + gy*gy);
+	gx *= n; gy *= n;
+	return make_float4(gx, gy, 0.0f, twn::permute(k));
+}
+
+// glm::perlin(vec2) for two positions with the table
+__device__ __forceinline__ f2 perlin2_lut(f2 Px, f2 Py, unsigned Lb) {
+	f2 const flx = floor2(Px), fly = floor2(Py);
+	f2 const frx = sub2(Px, flx), fry = sub2(Py, fly);
+	f2 const Pfz = add2(frx, -1.0f), Pfw = add2(fry, -1.0f);
+	f2 const Pix = mod_int289(flx), Piy = mod_int289(fly), Piz = mod_int289(add2(flx, 1.0f)), Piw = mod_int289(add2(fly, 1.0f));
+	f2 const jx = lut_offsets(Pix), jz = lut_offsets(Piz);
+	f2 const qx = make_float2(lut_load_w(Lb, jx.x), lut_load_w(Lb, jx.y)), qz = make_float2(lut_load_w(Lb, jz.x), lut_load_w(Lb, jz.y)); // permute(ix)
+	f2 const k00 = lut_offsets(permute(add2(qx, Piy))), k10 = lut_offsets(permute(add2(qz, Piy)));
+	f2 const k01 = lut_offsets(permute(add2(qx, Piw))), k11 = lut_offsets(permute(add2(qz, Piw)));
+	float4 const a00 = lut_load4(Lb, k00.x), b00 = lut_load4(Lb, k00.y), a10 = lut_load4(Lb, k10.x), b10 = lut_load4(Lb, k10.y);
+	float4 const a01 = lut_load4(Lb, k01.x), b01 = lut_load4(Lb, k01.y), a11 = lut_load4(Lb, k11.x), b11 = lut_load4(Lb, k11.y);
+	// scalar FMUL/FADD with the table values (see simplex2_lut)
+	f2 const n00 = make_float2(a00.x*frx.x + a00.y*fry.x, b00.x*frx.y + b00.y*fry.y);
+	f2 const n10 = make_float2(a10.x*Pfz.x + a10.y*fry.x, b10.x*Pfz.y + b10.y*fry.y);
+	f2 const n01 = make_float2(a01.x*frx.x + a01.y*Pfw.x, b01.x*frx.y + b01.y*Pfw.y);
+	f2 const n11 = make_float2(a11.x*Pfz.x + a11.y*Pfw.x, b11.x*Pfz.y + b11.y*Pfw.y);
+	f2 const fdx = fade2(frx), fdy = fade2(fry);
+	f2 const nx0 = mix2(n00, n10, fdx), nx1 = mix2(n01, n11, fdx);
+	return mul2(mix2(nx0, nx1, fdy), 2.3f);
+}
+
 } // namespace twn2
