@@ -119,6 +119,7 @@ void tw_destroy(tw_ctx *ctx) {
 	if (ctx->d_sin_table) cudaFree(ctx->d_sin_table);
 	if (ctx->d_dir_table) cudaFree(ctx->d_dir_table);
 	if (ctx->d_simplex_lut) cudaFree(ctx->d_simplex_lut);
+	if (ctx->d_glm3_lut) cudaFree(ctx->d_glm3_lut);
 	if (ctx->d_sine_params) cudaFree(ctx->d_sine_params);
 	if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
 	if (ctx->async.done) cudaEventDestroy(ctx->async.done);

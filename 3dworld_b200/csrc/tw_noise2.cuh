@@ -246,4 +246,77 @@ __device__ __forceinline__ f2 perlin2_lut(f2 Px, f2 Py, unsigned Lb) {
 	return mul2(mix2(nx0, nx1, fdy), 2.3f);
 }
 
+// ---- 3-D noise (voxel density) with the same tables, one voxel per thread (scalar arithmetic) ----
+// simplex(vec3): entry k = {P.x*n, P.y*n, P.z*n, permute(k)}, the normalised gradient that glm::simplex(vec3) derives from the hashed index
+// (gtc/noise.inl:680-709: x_, y_, h, the sign fix-up s*sh, taylorInvSqrt); perlin(vec3): entry k = {g.x*n, g.y*n, g.z*n, permute(k)}
+// (gtc/noise.inl:90-118). The lattice indices here come from mod289() (the multiply form), which can return exactly 289 for a multiple of
+// 289, hence 291 entries; callers guard |lattice coordinate| < 2^20 (mod289 then stays within [0, 289]) and use twn::simplex3/perlin3 beyond.
+__device__ __forceinline__ float4 simplex3_lut_entry(float k) {
+	float X, Y, H;
+	twn::simplex3_xyh(k, X, Y, H);
+	float const sh = -twn::step(H, 0.0f);
+	float Px = X + (floorf(X)*2.0f + 1.0f)*sh, Py = Y + (floorf(Y)*2.0f + 1.0f)*sh, Pz = H;
+	float const n = twn::tinvsqrt(Px*Px + Py*Py + Pz*Pz);
+	Px *= n; Py *= n; Pz *= n;
+	return make_float4(Px, Py, Pz, twn::permute(k));
+}
+__device__ __forceinline__ float4 perlin3_lut_entry(float k) {
+	float gx, gy, gz;
+	twn::perlin3_grad(k, gx, gy, gz);
+	return make_float4(gx, gy, gz, twn::permute(k));
+}
+__device__ __forceinline__ float lut_offset1(float k) {return __fmaf_rn(k, 16.0f*SIMPLEX_LUT_COPIES, 12582912.0f);} // exact, see lut_offsets
+
+__device__ __forceinline__ float simplex3_lut(float vx, float vy, float vz, unsigned Lb) {
+	float const Cx = (float)(1.0/6.0), Cy = (float)(1.0/3.0);
+	float const s = vx*Cy + vy*Cy + vz*Cy;
+	float i0 = floorf(vx + s), i1_ = floorf(vy + s), i2_ = floorf(vz + s);
+	float const t = i0*Cx + i1_*Cx + i2_*Cx;
+	float const x0x = vx - i0 + t, x0y = vy - i1_ + t, x0z = vz - i2_ + t;
+	float const gx = twn::step(x0y, x0x), gy = twn::step(x0z, x0y), gz = twn::step(x0x, x0z);
+	float const lx = 1.0f - gx, ly = 1.0f - gy, lz = 1.0f - gz;
+	float const i1x = twn::gmin(gx, lz), i1y = twn::gmin(gy, lx), i1z = twn::gmin(gz, ly);
+	float const i2x = twn::gmax(gx, lz), i2y = twn::gmax(gy, lx), i2z = twn::gmax(gz, ly);
+	float const x1x = x0x - i1x + Cx, x1y = x0y - i1y + Cx, x1z = x0z - i1z + Cx;
+	float const x2x = x0x - i2x + Cy, x2y = x0y - i2y + Cy, x2z = x0z - i2z + Cy;
+	float const x3x = x0x - 0.5f, x3y = x0y - 0.5f, x3z = x0z - 0.5f;
+	i0 = twn::mod289(i0); i1_ = twn::mod289(i1_); i2_ = twn::mod289(i2_);
+	float const q0 = lut_load_w(Lb, lut_offset1(i2_)), q1 = lut_load_w(Lb, lut_offset1(i2_ + i1z)), q2 = lut_load_w(Lb, lut_offset1(i2_ + i2z)),
+	            q3 = lut_load_w(Lb, lut_offset1(i2_ + 1.0f)); // twn::permute(i.z + ...)
+	float const p0 = twn::permute(twn::permute(q0 + i1_)        + i0);
+	float const p1 = twn::permute(twn::permute(q1 + i1_ + i1y)  + i0 + i1x);
+	float const p2 = twn::permute(twn::permute(q2 + i1_ + i2y)  + i0 + i2x);
+	float const p3 = twn::permute(twn::permute(q3 + i1_ + 1.0f) + i0 + 1.0f);
+	float4 const P0 = lut_load4(Lb, lut_offset1(p0)), P1 = lut_load4(Lb, lut_offset1(p1)), P2 = lut_load4(Lb, lut_offset1(p2)), P3 = lut_load4(Lb, lut_offset1(p3));
+	float m0 = twn::gmax0(0.6f - (x0x*x0x + x0y*x0y + x0z*x0z)), m1 = twn::gmax0(0.6f - (x1x*x1x + x1y*x1y + x1z*x1z));
+	float m2 = twn::gmax0(0.6f - (x2x*x2x + x2y*x2y + x2z*x2z)), m3 = twn::gmax0(0.6f - (x3x*x3x + x3y*x3y + x3z*x3z));
+	m0 = m0*m0; m1 = m1*m1; m2 = m2*m2; m3 = m3*m3;
+	float const d0 = P0.x*x0x + P0.y*x0y + P0.z*x0z, d1 = P1.x*x1x + P1.y*x1y + P1.z*x1z;
+	float const d2 = P2.x*x2x + P2.y*x2y + P2.z*x2z, d3 = P3.x*x3x + P3.y*x3y + P3.z*x3z;
+	return 42.0f*(((m0*m0)*d0 + (m1*m1)*d1) + ((m2*m2)*d2 + (m3*m3)*d3));
+}
+
+__device__ __forceinline__ float perlin3_lut(float Px, float Py, float Pz, unsigned Lb) {
+	float const flx = floorf(Px), fly = floorf(Py), flz = floorf(Pz);
+	float const Pi0x = twn::mod289(flx), Pi0y = twn::mod289(fly), Pi0z = twn::mod289(flz);
+	float const Pi1x = twn::mod289(flx + 1.0f), Pi1y = twn::mod289(fly + 1.0f), Pi1z = twn::mod289(flz + 1.0f);
+	float const f0x = Px - flx, f0y = Py - fly, f0z = Pz - flz;
+	float const f1x = f0x - 1.0f, f1y = f0y - 1.0f, f1z = f0z - 1.0f;
+	float const px0 = lut_load_w(Lb, lut_offset1(Pi0x)), px1 = lut_load_w(Lb, lut_offset1(Pi1x)); // twn::permute(Pi.x)
+	float const ixy00 = twn::permute(px0 + Pi0y), ixy10 = twn::permute(px1 + Pi0y), ixy01 = twn::permute(px0 + Pi1y), ixy11 = twn::permute(px1 + Pi1y);
+	float4 g;
+	g = lut_load4(Lb, lut_offset1(twn::permute(ixy00 + Pi0z))); float const n000 = g.x*f0x + g.y*f0y + g.z*f0z;
+	g = lut_load4(Lb, lut_offset1(twn::permute(ixy10 + Pi0z))); float const n100 = g.x*f1x + g.y*f0y + g.z*f0z;
+	g = lut_load4(Lb, lut_offset1(twn::permute(ixy01 + Pi0z))); float const n010 = g.x*f0x + g.y*f1y + g.z*f0z;
+	g = lut_load4(Lb, lut_offset1(twn::permute(ixy11 + Pi0z))); float const n110 = g.x*f1x + g.y*f1y + g.z*f0z;
+	g = lut_load4(Lb, lut_offset1(twn::permute(ixy00 + Pi1z))); float const n001 = g.x*f0x + g.y*f0y + g.z*f1z;
+	g = lut_load4(Lb, lut_offset1(twn::permute(ixy10 + Pi1z))); float const n101 = g.x*f1x + g.y*f0y + g.z*f1z;
+	g = lut_load4(Lb, lut_offset1(twn::permute(ixy01 + Pi1z))); float const n011 = g.x*f0x + g.y*f1y + g.z*f1z;
+	g = lut_load4(Lb, lut_offset1(twn::permute(ixy11 + Pi1z))); float const n111 = g.x*f1x + g.y*f1y + g.z*f1z;
+	float const fx = twn::fade(f0x), fy = twn::fade(f0y), fz = twn::fade(f0z);
+	float const nz0 = twn::mix(n000, n001, fz), nz1 = twn::mix(n100, n101, fz), nz2 = twn::mix(n010, n011, fz), nz3 = twn::mix(n110, n111, fz);
+	float const nyz0 = twn::mix(nz0, nz2, fy), nyz1 = twn::mix(nz1, nz3, fy);
+	return 2.2f*twn::mix(nyz0, nyz1, fx);
+}
+
 } // namespace twn2

@@ -132,24 +132,44 @@ struct GlmParams {
 	int octaves, perlin;
 };
 
-__global__ void __launch_bounds__(128)
-voxel_glm_kernel(float *__restrict__ out, GlmParams G, VoxEpilogue E)
+// One voxel per thread, lanes along z (the layout's fastest dimension); a block walks VGX consecutive x columns so that the 37 KB
+// hash/gradient table (tw_noise2.cuh) is staged once per VGX*blockDim voxels.
+constexpr unsigned VGX = 16;
+template<bool PERLIN>
+__global__ void __launch_bounds__(256)
+voxel_glm_kernel(float *__restrict__ out, GlmParams G, VoxEpilogue E, const float4 *__restrict__ lut)
 {
-	unsigned const z = blockIdx.x*blockDim.x + threadIdx.x, x = blockIdx.y, y = blockIdx.z;
+	__shared__ float4 lut_s[twn2::SIMPLEX_LUT_N*twn2::SIMPLEX_LUT_COPIES];
+	for (int e = threadIdx.x; e < twn2::SIMPLEX_LUT_N*twn2::SIMPLEX_LUT_COPIES; e += blockDim.x) {lut_s[e] = __ldg(lut + e/twn2::SIMPLEX_LUT_COPIES);}
+	__syncthreads();
+	unsigned L = twn2::simplex_lut_base(lut_s, threadIdx.x);
+	asm volatile("" : "+r"(L) :: "memory"); // table loads depend on L, defined after the barrier
+	unsigned const z = blockIdx.x*blockDim.x + threadIdx.x, y = blockIdx.z;
 	if (z >= E.nz) return;
-	// get_pt_at(x,y,z) + offset = (point(x,y,z)*vsz + lo_pos) + offset, src/voxels.h:149, src/voxels.cpp:328
-	float const px = ((float)x*G.vsz[0] + G.lo[0]) + G.off[0];
 	float const py = ((float)y*G.vsz[1] + G.lo[1]) + G.off[1];
 	float const pz = ((float)z*G.vsz[2] + G.lo[2]) + G.off[2];
-	float val = 0.0f, nmag = G.mag, nfreq = G.nfreq0;
-	for (int n = 0; n < G.octaves; ++n) {
-		float const nvx = nfreq*px + G.rx, nvy = nfreq*py + G.ry, nvz = nfreq*pz + G.rz;
-		float const nz_ = G.perlin ? twn::perlin3(nvx, nvy, nvz) : twn::simplex3(nvx, nvy, nvz);
-		val   = val + nmag*nz_;
-		nmag  = nmag*0.5f;
-		nfreq = nfreq*1.92f;
+	for (unsigned x = blockIdx.y*VGX; x < min(E.nx, (blockIdx.y + 1)*VGX); ++x) {
+		// get_pt_at(x,y,z) + offset = (point(x,y,z)*vsz + lo_pos) + offset, src/voxels.h:149, src/voxels.cpp:328
+		float const px = ((float)x*G.vsz[0] + G.lo[0]) + G.off[0];
+		float val = 0.0f, nmag = G.mag, nfreq = G.nfreq0;
+		for (int n = 0; n < G.octaves; ++n) {
+			float const nvx = nfreq*px + G.rx, nvy = nfreq*py + G.ry, nvz = nfreq*pz + G.rz;
+			float nz_;
+			if (fabsf(nvx) + fabsf(nvy) + fabsf(nvz) < 262144.0f) { // lattice coordinates stay below 2^20: table domain (NaN-safe: goes to the literal path)
+				nz_ = PERLIN ? twn2::perlin3_lut(nvx, nvy, nvz, L) : twn2::simplex3_lut(nvx, nvy, nvz, L);
+			}
+			else {nz_ = PERLIN ? twn::perlin3(nvx, nvy, nvz) : twn::simplex3(nvx, nvy, nvz);}
+			val   = val + nmag*nz_;
+			nmag  = nmag*0.5f;
+			nfreq = nfreq*1.92f;
+		}
+		out[z + ((size_t)x + (size_t)y*E.nx)*E.nz] = epilogue(val, x, y, z, E);
 	}
-	out[z + ((size_t)x + (size_t)y*E.nx)*E.nz] = epilogue(val, x, y, z, E);
+}
+
+__global__ void glm3_lut_kernel(float4 *__restrict__ lut) { // [0, N): simplex(vec3) table, [N, 2N): perlin(vec3) table
+	int const k = blockIdx.x*blockDim.x + threadIdx.x;
+	if (k < twn2::SIMPLEX_LUT_N) {lut[k] = twn2::simplex3_lut_entry((float)k); lut[twn2::SIMPLEX_LUT_N + k] = twn2::perlin3_lut_entry((float)k);}
 }
 
 } // namespace
@@ -186,8 +206,15 @@ int twi_voxel_fill(tw_ctx *ctx, const tw_voxel_params *vp, const float *rdata420
 	G.mag = vp->mag; G.nfreq0 = (float)(0.25*vp->freq);
 	G.rx = vp->rx; G.ry = vp->ry; G.rz = vp->rx - vp->ry;
 	G.octaves = vp->octaves; G.perlin = (vp->gen_mode == TW_MGEN_PERLIN);
-	dim3 const grid((nz + 127)/128, nx, ny);
-	voxel_glm_kernel<<<grid, 128, 0, ctx->stream>>>(d_out, G, E);
+	if (!ctx->d_glm3_lut) {
+		TW_CUDA(ctx, cudaMalloc(&ctx->d_glm3_lut, 2*twn2::SIMPLEX_LUT_N*sizeof(float4)));
+		glm3_lut_kernel<<<(twn2::SIMPLEX_LUT_N + 127)/128, 128, 0, ctx->stream>>>((float4 *)ctx->d_glm3_lut);
+		TW_LAUNCH_CHECK(ctx);
+	}
+	unsigned const bz = (nz > 128) ? 256 : 128;
+	dim3 const grid((nz + bz - 1)/bz, (nx + VGX - 1)/VGX, ny);
+	if (G.perlin) {voxel_glm_kernel<true ><<<grid, bz, 0, ctx->stream>>>(d_out, G, E, (const float4 *)ctx->d_glm3_lut + twn2::SIMPLEX_LUT_N);}
+	else          {voxel_glm_kernel<false><<<grid, bz, 0, ctx->stream>>>(d_out, G, E, (const float4 *)ctx->d_glm3_lut);}
 	TW_LAUNCH_CHECK(ctx);
 	return TW_OK;
 }

@@ -27,6 +27,20 @@ def test_voxel_fill_bit_exact(tw, scene, oracle, ctx, beq, mode, dims):
             assert beq(got, exp) == 0, "max abs diff %g" % np.abs(got - exp).max()
 
 
+@pytest.mark.parametrize("mode", [1, 2])
+def test_voxel_glm_table_domain_edges(tw, scene, oracle, ctx, beq, mode):
+    """The GLM kernels read hash/gradient tables while the lattice stays below 2^20 and use the literal arithmetic beyond: grids that sit on
+    multiples of 289 (mod289 returns exactly 289 there), straddle the switch-over, or lie far outside it must all match the oracle."""
+    for freq, off in ((1.0, (289.0 * 4, -289.0 * 8, 289.0 * 12)), (64.0, (16000.0, 0.0, 0.0)), (1.0, (3.0e6, -2.0e6, 1.0e6)), (1000.0, (0.0, 0.0, 0.0))):
+        vp = _vp(tw, scene, mode, 0, 24, 6, 140)
+        vp.freq = freq
+        for d in range(3):
+            vp.offset[d] = off[d]
+        got = ctx.voxel_fill(vp)
+        exp = oracle.voxel_fill(convert(vp, oracle.VoxelParams))
+        assert beq(got, exp) == 0, (freq, off)
+
+
 @pytest.mark.parametrize("atten", [1, 2, 3, 4, 5])
 def test_voxel_atten_modes(tw, scene, oracle, ctx, beq, atten):
     vp = _vp(tw, scene, 0, 2, 33, 20, 48, atten=atten)
