@@ -68,6 +68,10 @@ __device__ __forceinline__ f2 mod_int289(f2 a) {
 	f2 const r = fma2(floor2(mul2(a, 1.0f/289.0f)), -289.0f, a);
 	return make_float2((r.x >= 289.0f) ? r.x - 289.0f : r.x, (r.y >= 289.0f) ? r.y - 289.0f : r.y);
 }
+// Same without the fold: r in [0, 289], with 289 standing for 0 (only for exact multiples of 289). Sufficient wherever r only feeds exact
+// integer arithmetic modulo 289 - permute(r + c) (arguments stay below 2^24, so the float hash is the exact integer hash and
+// permute(289 + c) == permute(c)) - or a table whose entries 289 and 290 repeat 0 and 1 by the same arithmetic. Used by the table variants.
+__device__ __forceinline__ f2 mod_int289_lazy(f2 a) {return fma2(floor2(mul2(a, 1.0f/289.0f)), -289.0f, a);}
 __device__ __forceinline__ f2 fract2(f2 x) {return sub2(x, floor2(x));}
 __device__ __forceinline__ f2 tinvsqrt(f2 r) {return rsub2(1.79284291400159f, mul2(r, 0.85373472095314f));}
 __device__ __forceinline__ f2 mix2(f2 x, f2 y, f2 a) {return add2(x, mul2(a, sub2(y, x)));}
@@ -142,6 +146,10 @@ __device__ __forceinline__ float4 lut_load4(unsigned Lb, float off) {
 	float4 v; asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(Lb + __float_as_uint(off)));
 	return v;
 }
+__device__ __forceinline__ float lut_load_w_addr(unsigned addr) {
+	float v; asm("ld.shared.f32 %0, [%1+12];" : "=f"(v) : "r"(addr));
+	return v;
+}
 __device__ __forceinline__ float lut_load_w(unsigned Lb, float off) {
 	float v; asm("ld.shared.f32 %0, [%1+12];" : "=f"(v) : "r"(Lb + __float_as_uint(off)));
 	return v;
@@ -157,12 +165,17 @@ __device__ __forceinline__ f2 simplex2_lut(f2 vx, f2 vy, unsigned Lb) {
 	f2 const i1x = make_float2((x0x.x > x0y.x) ? 1.0f : 0.0f, (x0x.y > x0y.y) ? 1.0f : 0.0f);
 	f2 const i1y = rsub2(1.0f, i1x); // (1,0) or (0,1)
 	f2 const x12x = sub2(add2(x0x, Cx), i1x), x12y = sub2(add2(x0y, Cx), i1y), x12z = add2(x0x, Cz), x12w = add2(x0y, Cz);
-	ix = mod_int289(ix); iy = mod_int289(iy);
 #if TW_SIMPLEX_LUT >= 2
-	f2 const j0 = lut_offsets(iy), j1 = lut_offsets(add2(iy, i1y)), j2 = lut_offsets(add2(iy, 1.0f));
-	f2 const q0 = make_float2(lut_load_w(Lb, j0.x), lut_load_w(Lb, j0.y)), q1 = make_float2(lut_load_w(Lb, j1.x), lut_load_w(Lb, j1.y)),
-	         q2 = make_float2(lut_load_w(Lb, j2.x), lut_load_w(Lb, j2.y));
+	ix = mod_int289_lazy(ix); iy = mod_int289_lazy(iy);
+	// permute(iy), permute(iy + i1.y), permute(iy + 1): consecutive table entries, so the second and third addresses are the first plus 0/128/256 bytes
+	f2 const j0 = lut_offsets(iy);
+	unsigned const ja = Lb + __float_as_uint(j0.x), jb = Lb + __float_as_uint(j0.y);
+	unsigned const LUT_ENTRY = 16u*SIMPLEX_LUT_COPIES;
+	f2 const q0 = make_float2(lut_load_w_addr(ja), lut_load_w_addr(jb));
+	f2 const q1 = make_float2(lut_load_w_addr(ja + ((x0x.x > x0y.x) ? 0u : LUT_ENTRY)), lut_load_w_addr(jb + ((x0x.y > x0y.y) ? 0u : LUT_ENTRY)));
+	f2 const q2 = make_float2(lut_load_w_addr(ja + LUT_ENTRY), lut_load_w_addr(jb + LUT_ENTRY));
 #else
+	ix = mod_int289(ix); iy = mod_int289(iy);
 	f2 const q0 = permute(iy), q1 = permute(add2(iy, i1y)), q2 = permute(add2(iy, 1.0f));
 #endif
 	f2 const p0 = permute(add2(q0, ix)), p1 = permute(add2(add2(q1, ix), i1x)), p2 = permute(add2(add2(q2, ix), 1.0f));
@@ -229,7 +242,7 @@ __device__ __forceinline__ f2 perlin2_lut(f2 Px, f2 Py, unsigned Lb) {
 	f2 const flx = floor2(Px), fly = floor2(Py);
 	f2 const frx = sub2(Px, flx), fry = sub2(Py, fly);
 	f2 const Pfz = add2(frx, -1.0f), Pfw = add2(fry, -1.0f);
-	f2 const Pix = mod_int289(flx), Piy = mod_int289(fly), Piz = mod_int289(add2(flx, 1.0f)), Piw = mod_int289(add2(fly, 1.0f));
+	f2 const Pix = mod_int289_lazy(flx), Piy = mod_int289_lazy(fly), Piz = mod_int289_lazy(add2(flx, 1.0f)), Piw = mod_int289_lazy(add2(fly, 1.0f));
 	f2 const jx = lut_offsets(Pix), jz = lut_offsets(Piz);
 	f2 const qx = make_float2(lut_load_w(Lb, jx.x), lut_load_w(Lb, jx.y)), qz = make_float2(lut_load_w(Lb, jz.x), lut_load_w(Lb, jz.y)); // permute(ix)
 	f2 const k00 = lut_offsets(permute(add2(qx, Piy))), k10 = lut_offsets(permute(add2(qz, Piy)));
