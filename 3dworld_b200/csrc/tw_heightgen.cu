@@ -165,7 +165,7 @@ noise_grid_kernel(float *__restrict__ out, unsigned nx, unsigned ny, unsigned y_
 }
 
 #ifndef TW_NOISE2_MIN_BLOCKS
-#define TW_NOISE2_MIN_BLOCKS 5
+#define TW_NOISE2_MIN_BLOCKS 3   // 74 KB of table per block (tw_noise2.cuh, level 3) => 3 blocks per SM
 #endif
 // ---- packed variant: two horizontally adjacent cells per thread on FFMA2/FMUL2/FADD2 (see tw_noise2.cuh) ----
 // |lattice coordinate| < 2^22 for every octave of this fBm call (needed by the packed floor / division-free mod); NaN-safe
@@ -200,7 +200,7 @@ noise_grid2_kernel(float *__restrict__ out, unsigned nx, unsigned ny, unsigned y
 {
 	unsigned L = 0;
 	if (TW_SIMPLEX_LUT > 0) { // hash/gradient table (simplex or Perlin flavour) -> shared memory, 8 interleaved copies (see tw_noise2.cuh)
-		__shared__ float4 lut_s[twn2::SIMPLEX_LUT_N*twn2::SIMPLEX_LUT_COPIES];
+		extern __shared__ float4 lut_s[]; // SIMPLEX_LUT_N*SIMPLEX_LUT_COPIES entries (dynamic: 74 KB at level 3)
 		for (int e = threadIdx.x; e < twn2::SIMPLEX_LUT_N*twn2::SIMPLEX_LUT_COPIES; e += blockDim.x) {lut_s[e] = __ldg(simplex_lut + e/twn2::SIMPLEX_LUT_COPIES);}
 		__syncthreads();
 		L = twn2::simplex_lut_base(lut_s, threadIdx.x);
@@ -208,14 +208,21 @@ noise_grid2_kernel(float *__restrict__ out, unsigned nx, unsigned ny, unsigned y
 	}
 	// cells are numbered row-major over the band [y_off, y_end) of the grid and dealt out in pairs (2t, 2t+1): no lanes idle on widths that are
 	// not a multiple of the block width (258-wide tiles wasted 27 % of a 64x8-cell block grid); a pair may straddle a row end when nx is odd
+	// A block walks NOISE2_CHUNKS consecutive 512-cell chunks, so the table is staged once per chunk group (4 for the plain modes, whose 8
+	// evaluations per cell would otherwise be rivalled by the 74 KB fill; 1 for the 40-evaluation warp mode).
 	unsigned const tile = blockIdx.z;
-	size_t const c0 = (size_t)y_off*nx + 2*((size_t)blockIdx.x*blockDim.x + threadIdx.x), c_end = (size_t)y_end*nx;
+	float mx0 = mx0_single, my0 = my0_single;
+	if (tile_origins) {float2 const o = __ldg(tile_origins + tile); mx0 = o.x; my0 = o.y;}
+	size_t const c_end = (size_t)y_end*nx;
+	float lo = INFINITY, hi = -INFINITY;
+	constexpr unsigned NCH = WARP ? 1 : 4;
+#pragma unroll 1
+	for (unsigned ch = 0; ch < NCH; ++ch) {
+	size_t const c0 = (size_t)y_off*nx + 2*(((size_t)blockIdx.x*NCH + ch)*blockDim.x + threadIdx.x);
 	unsigned y, x;
 	if (c_end <= 0xffffffffull) {unsigned const c32 = (unsigned)c0; y = c32/nx; x = c32 - y*nx;} // 32-bit division for every grid below 2^32 cells
 	else {y = (unsigned)(c0/nx); x = (unsigned)(c0 - (size_t)y*nx);}
 	unsigned const xb = (x + 1 < nx) ? x + 1 : 0, yb = (x + 1 < nx) ? y : y + 1;
-	float mx0 = mx0_single, my0 = my0_single;
-	if (tile_origins) {float2 const o = __ldg(tile_origins + tile); mx0 = o.x; my0 = o.y;}
 	bool const valid0 = (c0 < c_end), valid1 = (c0 + 1 < c_end);
 	float z0 = 0.0f, z1 = 0.0f;
 	if (valid0) { // the second cell of an odd-sized band is computed and dropped
@@ -250,20 +257,27 @@ noise_grid2_kernel(float *__restrict__ out, unsigned nx, unsigned ny, unsigned y
 		if (valid1 && ((reinterpret_cast<size_t>(o) & 7) == 0)) {*reinterpret_cast<float2 *>(o) = make_float2(z0, z1);}
 		else {o[0] = z0; if (valid1) {o[1] = z1;}}
 	}
-	if (mm) {
-		float const lo = fminf(valid0 ? z0 : INFINITY, valid1 ? z1 : INFINITY), hi = fmaxf(valid0 ? z0 : -INFINITY, valid1 ? z1 : -INFINITY);
-		block_minmax(lo, hi, mm + 2*tile);
-	}
+	lo = fminf(lo, fminf(valid0 ? z0 : INFINITY, valid1 ? z1 : INFINITY)); hi = fmaxf(hi, fmaxf(valid0 ? z0 : -INFINITY, valid1 ? z1 : -INFINITY));
+	} // chunks
+	if (mm) {block_minmax(lo, hi, mm + 2*tile);}
 }
 
 template<bool SIMPLEX, bool WARP>
 void launch_noise2(int shape, dim3 grid, dim3 block, cudaStream_t st, float *out, unsigned nx, unsigned ny, unsigned y_off, unsigned y_end, float mx0, float my0,
 	const float2 *origins, const NoiseParams &N, const PostParams &P, const float *tab, unsigned *mm, const float4 *lut)
 {
+	size_t const lut_bytes = (TW_SIMPLEX_LUT > 0) ? (size_t)twn2::SIMPLEX_LUT_N*twn2::SIMPLEX_LUT_COPIES*sizeof(float4) : 0;
+	static bool attr_done = false; // per template instantiation: allow more than 48 KB of dynamic shared memory
+	if (!attr_done && lut_bytes > 48*1024) {
+		cudaFuncSetAttribute(noise_grid2_kernel<SIMPLEX, WARP, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lut_bytes);
+		cudaFuncSetAttribute(noise_grid2_kernel<SIMPLEX, WARP, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lut_bytes);
+		cudaFuncSetAttribute(noise_grid2_kernel<SIMPLEX, WARP, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lut_bytes);
+		attr_done = true;
+	}
 	switch (shape) {
-	case 1:  noise_grid2_kernel<SIMPLEX, WARP, 1><<<grid, block, 0, st>>>(out, nx, ny, y_off, y_end, mx0, my0, origins, N, P, tab, mm, lut); break;
-	case 2:  noise_grid2_kernel<SIMPLEX, WARP, 2><<<grid, block, 0, st>>>(out, nx, ny, y_off, y_end, mx0, my0, origins, N, P, tab, mm, lut); break;
-	default: noise_grid2_kernel<SIMPLEX, WARP, 0><<<grid, block, 0, st>>>(out, nx, ny, y_off, y_end, mx0, my0, origins, N, P, tab, mm, lut); break;
+	case 1:  noise_grid2_kernel<SIMPLEX, WARP, 1><<<grid, block, lut_bytes, st>>>(out, nx, ny, y_off, y_end, mx0, my0, origins, N, P, tab, mm, lut); break;
+	case 2:  noise_grid2_kernel<SIMPLEX, WARP, 2><<<grid, block, lut_bytes, st>>>(out, nx, ny, y_off, y_end, mx0, my0, origins, N, P, tab, mm, lut); break;
+	default: noise_grid2_kernel<SIMPLEX, WARP, 0><<<grid, block, lut_bytes, st>>>(out, nx, ny, y_off, y_end, mx0, my0, origins, N, P, tab, mm, lut); break;
 	}
 }
 
@@ -532,7 +546,8 @@ int twi_heightgen(tw_ctx *ctx, const tw_grid2d *g, const tw_height_params *p, in
 			static bool const use_scalar = (getenv("TW_NOISE_SCALAR") != nullptr); // A/B switch: one cell per thread, scalar FMUL/FADD
 			if (!use_scalar) { // two cells per thread on packed fp32x2 instructions
 				size_t const band_cells = (size_t)(r1 - r0)*nx;
-				dim3 const block(256, 1, 1), grid((unsigned)((band_cells + 511)/512), 1, ntiles); // two cells per thread, cells numbered row-major
+				size_t const cells_per_block = 512*(size_t)((p->gen_mode == TW_MGEN_DWARP_GPU) ? 1 : 4); // noise_grid2_kernel: NCH chunks of 256 threads x 2 cells
+				dim3 const block(256, 1, 1), grid((unsigned)((band_cells + cells_per_block - 1)/cells_per_block), 1, ntiles);
 				if (p->gen_mode == TW_MGEN_PERLIN) {launch_noise2<false, false>(p->gen_shape, grid, block, ctx->stream, d_out, nx, ny, r0, r1, mx0, my0, d_tile_origins, N, P, ctx->d_sin_table, d_mm_ord, lut);}
 				else if (warp) {launch_noise2<true, true >(p->gen_shape, grid, block, ctx->stream, d_out, nx, ny, r0, r1, mx0, my0, d_tile_origins, N, P, ctx->d_sin_table, d_mm_ord, lut);}
 				else           {launch_noise2<true, false>(p->gen_shape, grid, block, ctx->stream, d_out, nx, ny, r0, r1, mx0, my0, d_tile_origins, N, P, ctx->d_sin_table, d_mm_ord, lut);}

@@ -119,17 +119,25 @@ __device__ __forceinline__ f2 simplex2(f2 vx, f2 vy) {
 // corner (level 2: the first permute) by one 16-byte load each. Random indices would collide on the 32 banks, so the table is stored as 8
 // interleaved copies: entry k of copy c sits at float4 index 8*k + c and lane l reads copy l & 7 - the 8 lanes of every quarter-warp phase
 // of an LDS.128 then hit 8 different 16-byte bank groups by construction (conflict-free, 4 cycles per warp load).
+// Level 3 folds the second permute into the gradient entries: entry k = {gradient of permute(k), permute(k)} for every reachable argument
+// k = permute(iy') + ix' <= 578, so the gradient is fetched at k directly and the second hash (4 packed instructions + 2 floors per corner)
+// disappears at no extra load; the table grows to 580 entries (74 KB with the 8 copies => 3 blocks of 256 threads per SM, which measured
+// the same as 5 before: the kernel is pipe-bound, not latency-bound).
 #ifndef TW_SIMPLEX_LUT
-#define TW_SIMPLEX_LUT 2
+#define TW_SIMPLEX_LUT 3
 #endif
-constexpr int SIMPLEX_LUT_N = 291, SIMPLEX_LUT_COPIES = 8;
+constexpr int SIMPLEX_LUT_COPIES = 8;
+constexpr int LUT3D_N = 580;                                  // 3-D tables (tw_voxel.cu): same folding of the LAST permute, arguments <= 578
+constexpr int SIMPLEX_LUT_N = (TW_SIMPLEX_LUT >= 3) ? 580 : 291; // 2-D tables
 
 __device__ __forceinline__ float4 simplex_lut_entry(float k) { // scalar restatement of twn::simplex2's per-corner gradient and of permute()
 	float const Cw = 0.024390243902439f;
-	float const X = twn::two_f_minus_1(twn::fract(k*Cw));
+	float const pk = twn::permute(k);
+	float const gi = (TW_SIMPLEX_LUT >= 3) ? pk : k; // level 3: the entry holds the gradient of the hashed index
+	float const X = twn::two_f_minus_1(twn::fract(gi*Cw));
 	float const h = fabsf(X) - 0.5f, a0 = X - floorf(X + 0.5f);
 	float const n = 1.79284291400159f - 0.85373472095314f*(a0*a0 + h*h);
-	return make_float4(a0, h, n, twn::permute(k));
+	return make_float4(a0, h, n, pk);
 }
 
 // Table addressing without integer arithmetic on the index: for an exact small non-negative integer k held in a float,
@@ -178,7 +186,11 @@ __device__ __forceinline__ f2 simplex2_lut(f2 vx, f2 vy, unsigned Lb) {
 	ix = mod_int289(ix); iy = mod_int289(iy);
 	f2 const q0 = permute(iy), q1 = permute(add2(iy, i1y)), q2 = permute(add2(iy, 1.0f));
 #endif
+#if TW_SIMPLEX_LUT >= 3
+	f2 const p0 = add2(q0, ix), p1 = add2(add2(q1, ix), i1x), p2 = add2(add2(q2, ix), 1.0f); // the table is indexed by the argument of the second permute
+#else
 	f2 const p0 = permute(add2(q0, ix)), p1 = permute(add2(add2(q1, ix), i1x)), p2 = permute(add2(add2(q2, ix), 1.0f));
+#endif
 	f2 m0 = max0_2(rsub2(0.5f, add2(mul2(x0x, x0x), mul2(x0y, x0y))));
 	f2 m1 = max0_2(rsub2(0.5f, add2(mul2(x12x, x12x), mul2(x12y, x12y))));
 	f2 m2 = max0_2(rsub2(0.5f, add2(mul2(x12z, x12z), mul2(x12w, x12w))));
@@ -230,11 +242,12 @@ __device__ __forceinline__ f2 perlin2(f2 Px, f2 Py) {
 // ---- Perlin with the same kind of table: {gx*n, gy*n, 0, permute(k)} for the hashed lattice index k (gradient of glm::perlin(vec2):
 // g = 2*fract(k/41) - 1, gy = |g| - 0.5, gx = g - floor(g + 0.5), both scaled by taylorInvSqrt(gx*gx + gy*gy)), k in [0, 288]; .w as above ----
 __device__ __forceinline__ float4 perlin_lut_entry(float k) {
-	float const g = twn::two_f_minus_1(twn::fract(twn::div41_small(k)));
+	float const pk = twn::permute(k);
+	float const g = twn::two_f_minus_1(twn::fract(twn::div41_small((TW_SIMPLEX_LUT >= 3) ? pk : k)));
 	float gy = fabsf(g) - 0.5f, gx = g - floorf(g + 0.5f);
 	float const n = twn::tinvsqrt(gx*gx + gy*gy);
 	gx *= n; gy *= n;
-	return make_float4(gx, gy, 0.0f, twn::permute(k));
+	return make_float4(gx, gy, 0.0f, pk);
 }
 
 // glm::perlin(vec2) for two positions with the table
@@ -245,8 +258,12 @@ __device__ __forceinline__ f2 perlin2_lut(f2 Px, f2 Py, unsigned Lb) {
 	f2 const Pix = mod_int289_lazy(flx), Piy = mod_int289_lazy(fly), Piz = mod_int289_lazy(add2(flx, 1.0f)), Piw = mod_int289_lazy(add2(fly, 1.0f));
 	f2 const jx = lut_offsets(Pix), jz = lut_offsets(Piz);
 	f2 const qx = make_float2(lut_load_w(Lb, jx.x), lut_load_w(Lb, jx.y)), qz = make_float2(lut_load_w(Lb, jz.x), lut_load_w(Lb, jz.y)); // permute(ix)
+#if TW_SIMPLEX_LUT >= 3
+	f2 const k00 = lut_offsets(add2(qx, Piy)), k10 = lut_offsets(add2(qz, Piy)), k01 = lut_offsets(add2(qx, Piw)), k11 = lut_offsets(add2(qz, Piw));
+#else
 	f2 const k00 = lut_offsets(permute(add2(qx, Piy))), k10 = lut_offsets(permute(add2(qz, Piy)));
 	f2 const k01 = lut_offsets(permute(add2(qx, Piw))), k11 = lut_offsets(permute(add2(qz, Piw)));
+#endif
 	float4 const a00 = lut_load4(Lb, k00.x), b00 = lut_load4(Lb, k00.y), a10 = lut_load4(Lb, k10.x), b10 = lut_load4(Lb, k10.y);
 	float4 const a01 = lut_load4(Lb, k01.x), b01 = lut_load4(Lb, k01.y), a11 = lut_load4(Lb, k11.x), b11 = lut_load4(Lb, k11.y);
 	// scalar FMUL/FADD with the table values (see simplex2_lut)
@@ -264,19 +281,21 @@ __device__ __forceinline__ f2 perlin2_lut(f2 Px, f2 Py, unsigned Lb) {
 // (gtc/noise.inl:680-709: x_, y_, h, the sign fix-up s*sh, taylorInvSqrt); perlin(vec3): entry k = {g.x*n, g.y*n, g.z*n, permute(k)}
 // (gtc/noise.inl:90-118). The lattice indices here come from mod289() (the multiply form), which can return exactly 289 for a multiple of
 // 289, hence 291 entries; callers guard |lattice coordinate| < 2^20 (mod289 then stays within [0, 289]) and use twn::simplex3/perlin3 beyond.
-__device__ __forceinline__ float4 simplex3_lut_entry(float k) {
+__device__ __forceinline__ float4 simplex3_lut_entry(float k) { // gradient of the hashed index permute(k) (the last of the three permutes is folded in)
 	float X, Y, H;
-	twn::simplex3_xyh(k, X, Y, H);
+	float const pk = twn::permute(k);
+	twn::simplex3_xyh(pk, X, Y, H);
 	float const sh = -twn::step(H, 0.0f);
 	float Px = X + (floorf(X)*2.0f + 1.0f)*sh, Py = Y + (floorf(Y)*2.0f + 1.0f)*sh, Pz = H;
 	float const n = twn::tinvsqrt(Px*Px + Py*Py + Pz*Pz);
 	Px *= n; Py *= n; Pz *= n;
-	return make_float4(Px, Py, Pz, twn::permute(k));
+	return make_float4(Px, Py, Pz, pk);
 }
 __device__ __forceinline__ float4 perlin3_lut_entry(float k) {
 	float gx, gy, gz;
-	twn::perlin3_grad(k, gx, gy, gz);
-	return make_float4(gx, gy, gz, twn::permute(k));
+	float const pk = twn::permute(k);
+	twn::perlin3_grad(pk, gx, gy, gz);
+	return make_float4(gx, gy, gz, pk);
 }
 __device__ __forceinline__ float lut_offset1(float k) {return __fmaf_rn(k, 16.0f*SIMPLEX_LUT_COPIES, 12582912.0f);} // exact, see lut_offsets
 
@@ -296,10 +315,10 @@ __device__ __forceinline__ float simplex3_lut(float vx, float vy, float vz, unsi
 	i0 = twn::mod289(i0); i1_ = twn::mod289(i1_); i2_ = twn::mod289(i2_);
 	float const q0 = lut_load_w(Lb, lut_offset1(i2_)), q1 = lut_load_w(Lb, lut_offset1(i2_ + i1z)), q2 = lut_load_w(Lb, lut_offset1(i2_ + i2z)),
 	            q3 = lut_load_w(Lb, lut_offset1(i2_ + 1.0f)); // twn::permute(i.z + ...)
-	float const p0 = twn::permute(twn::permute(q0 + i1_)        + i0);
-	float const p1 = twn::permute(twn::permute(q1 + i1_ + i1y)  + i0 + i1x);
-	float const p2 = twn::permute(twn::permute(q2 + i1_ + i2y)  + i0 + i2x);
-	float const p3 = twn::permute(twn::permute(q3 + i1_ + 1.0f) + i0 + 1.0f);
+	float const p0 = twn::permute(q0 + i1_)        + i0;        // arguments of the last permute: the table holds the gradient of permute(argument)
+	float const p1 = twn::permute(q1 + i1_ + i1y)  + i0 + i1x;
+	float const p2 = twn::permute(q2 + i1_ + i2y)  + i0 + i2x;
+	float const p3 = twn::permute(q3 + i1_ + 1.0f) + i0 + 1.0f;
 	float4 const P0 = lut_load4(Lb, lut_offset1(p0)), P1 = lut_load4(Lb, lut_offset1(p1)), P2 = lut_load4(Lb, lut_offset1(p2)), P3 = lut_load4(Lb, lut_offset1(p3));
 	float m0 = twn::gmax0(0.6f - (x0x*x0x + x0y*x0y + x0z*x0z)), m1 = twn::gmax0(0.6f - (x1x*x1x + x1y*x1y + x1z*x1z));
 	float m2 = twn::gmax0(0.6f - (x2x*x2x + x2y*x2y + x2z*x2z)), m3 = twn::gmax0(0.6f - (x3x*x3x + x3y*x3y + x3z*x3z));
@@ -318,14 +337,14 @@ __device__ __forceinline__ float perlin3_lut(float Px, float Py, float Pz, unsig
 	float const px0 = lut_load_w(Lb, lut_offset1(Pi0x)), px1 = lut_load_w(Lb, lut_offset1(Pi1x)); // twn::permute(Pi.x)
 	float const ixy00 = twn::permute(px0 + Pi0y), ixy10 = twn::permute(px1 + Pi0y), ixy01 = twn::permute(px0 + Pi1y), ixy11 = twn::permute(px1 + Pi1y);
 	float4 g;
-	g = lut_load4(Lb, lut_offset1(twn::permute(ixy00 + Pi0z))); float const n000 = g.x*f0x + g.y*f0y + g.z*f0z;
-	g = lut_load4(Lb, lut_offset1(twn::permute(ixy10 + Pi0z))); float const n100 = g.x*f1x + g.y*f0y + g.z*f0z;
-	g = lut_load4(Lb, lut_offset1(twn::permute(ixy01 + Pi0z))); float const n010 = g.x*f0x + g.y*f1y + g.z*f0z;
-	g = lut_load4(Lb, lut_offset1(twn::permute(ixy11 + Pi0z))); float const n110 = g.x*f1x + g.y*f1y + g.z*f0z;
-	g = lut_load4(Lb, lut_offset1(twn::permute(ixy00 + Pi1z))); float const n001 = g.x*f0x + g.y*f0y + g.z*f1z;
-	g = lut_load4(Lb, lut_offset1(twn::permute(ixy10 + Pi1z))); float const n101 = g.x*f1x + g.y*f0y + g.z*f1z;
-	g = lut_load4(Lb, lut_offset1(twn::permute(ixy01 + Pi1z))); float const n011 = g.x*f0x + g.y*f1y + g.z*f1z;
-	g = lut_load4(Lb, lut_offset1(twn::permute(ixy11 + Pi1z))); float const n111 = g.x*f1x + g.y*f1y + g.z*f1z;
+	g = lut_load4(Lb, lut_offset1(ixy00 + Pi0z)); float const n000 = g.x*f0x + g.y*f0y + g.z*f0z;
+	g = lut_load4(Lb, lut_offset1(ixy10 + Pi0z)); float const n100 = g.x*f1x + g.y*f0y + g.z*f0z;
+	g = lut_load4(Lb, lut_offset1(ixy01 + Pi0z)); float const n010 = g.x*f0x + g.y*f1y + g.z*f0z;
+	g = lut_load4(Lb, lut_offset1(ixy11 + Pi0z)); float const n110 = g.x*f1x + g.y*f1y + g.z*f0z;
+	g = lut_load4(Lb, lut_offset1(ixy00 + Pi1z)); float const n001 = g.x*f0x + g.y*f0y + g.z*f1z;
+	g = lut_load4(Lb, lut_offset1(ixy10 + Pi1z)); float const n101 = g.x*f1x + g.y*f0y + g.z*f1z;
+	g = lut_load4(Lb, lut_offset1(ixy01 + Pi1z)); float const n011 = g.x*f0x + g.y*f1y + g.z*f1z;
+	g = lut_load4(Lb, lut_offset1(ixy11 + Pi1z)); float const n111 = g.x*f1x + g.y*f1y + g.z*f1z;
 	float const fx = twn::fade(f0x), fy = twn::fade(f0y), fz = twn::fade(f0z);
 	float const nz0 = twn::mix(n000, n001, fz), nz1 = twn::mix(n100, n101, fz), nz2 = twn::mix(n010, n011, fz), nz3 = twn::mix(n110, n111, fz);
 	float const nyz0 = twn::mix(nz0, nz2, fy), nyz1 = twn::mix(nz1, nz3, fy);

@@ -132,15 +132,16 @@ struct GlmParams {
 	int octaves, perlin;
 };
 
-// One voxel per thread, lanes along z (the layout's fastest dimension); a block walks VGX consecutive x columns so that the 37 KB
-// hash/gradient table (tw_noise2.cuh) is staged once per VGX*blockDim voxels.
-constexpr unsigned VGX = 16;
+// One voxel per thread, lanes along z (the layout's fastest dimension); a block walks VGX consecutive x columns so that the 74 KB
+// hash/gradient table (tw_noise2.cuh: gradient of permute(k) for every reachable argument k of the last permute) is staged once per
+// VGX*blockDim voxels.
+constexpr unsigned VGX = 32;
 template<bool PERLIN>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
 voxel_glm_kernel(float *__restrict__ out, GlmParams G, VoxEpilogue E, const float4 *__restrict__ lut)
 {
-	__shared__ float4 lut_s[twn2::SIMPLEX_LUT_N*twn2::SIMPLEX_LUT_COPIES];
-	for (int e = threadIdx.x; e < twn2::SIMPLEX_LUT_N*twn2::SIMPLEX_LUT_COPIES; e += blockDim.x) {lut_s[e] = __ldg(lut + e/twn2::SIMPLEX_LUT_COPIES);}
+	extern __shared__ float4 lut_s[]; // LUT3D_N*SIMPLEX_LUT_COPIES entries (74 KB)
+	for (int e = threadIdx.x; e < twn2::LUT3D_N*twn2::SIMPLEX_LUT_COPIES; e += blockDim.x) {lut_s[e] = __ldg(lut + e/twn2::SIMPLEX_LUT_COPIES);}
 	__syncthreads();
 	unsigned L = twn2::simplex_lut_base(lut_s, threadIdx.x);
 	asm volatile("" : "+r"(L) :: "memory"); // table loads depend on L, defined after the barrier
@@ -169,7 +170,7 @@ voxel_glm_kernel(float *__restrict__ out, GlmParams G, VoxEpilogue E, const floa
 
 __global__ void glm3_lut_kernel(float4 *__restrict__ lut) { // [0, N): simplex(vec3) table, [N, 2N): perlin(vec3) table
 	int const k = blockIdx.x*blockDim.x + threadIdx.x;
-	if (k < twn2::SIMPLEX_LUT_N) {lut[k] = twn2::simplex3_lut_entry((float)k); lut[twn2::SIMPLEX_LUT_N + k] = twn2::perlin3_lut_entry((float)k);}
+	if (k < twn2::LUT3D_N) {lut[k] = twn2::simplex3_lut_entry((float)k); lut[twn2::LUT3D_N + k] = twn2::perlin3_lut_entry((float)k);}
 }
 
 } // namespace
@@ -207,14 +208,21 @@ int twi_voxel_fill(tw_ctx *ctx, const tw_voxel_params *vp, const float *rdata420
 	G.rx = vp->rx; G.ry = vp->ry; G.rz = vp->rx - vp->ry;
 	G.octaves = vp->octaves; G.perlin = (vp->gen_mode == TW_MGEN_PERLIN);
 	if (!ctx->d_glm3_lut) {
-		TW_CUDA(ctx, cudaMalloc(&ctx->d_glm3_lut, 2*twn2::SIMPLEX_LUT_N*sizeof(float4)));
-		glm3_lut_kernel<<<(twn2::SIMPLEX_LUT_N + 127)/128, 128, 0, ctx->stream>>>((float4 *)ctx->d_glm3_lut);
+		TW_CUDA(ctx, cudaMalloc(&ctx->d_glm3_lut, 2*twn2::LUT3D_N*sizeof(float4)));
+		glm3_lut_kernel<<<(twn2::LUT3D_N + 127)/128, 128, 0, ctx->stream>>>((float4 *)ctx->d_glm3_lut);
 		TW_LAUNCH_CHECK(ctx);
 	}
 	unsigned const bz = (nz > 128) ? 256 : 128;
 	dim3 const grid((nz + bz - 1)/bz, (nx + VGX - 1)/VGX, ny);
-	if (G.perlin) {voxel_glm_kernel<true ><<<grid, bz, 0, ctx->stream>>>(d_out, G, E, (const float4 *)ctx->d_glm3_lut + twn2::SIMPLEX_LUT_N);}
-	else          {voxel_glm_kernel<false><<<grid, bz, 0, ctx->stream>>>(d_out, G, E, (const float4 *)ctx->d_glm3_lut);}
+	size_t const lut_bytes = (size_t)twn2::LUT3D_N*twn2::SIMPLEX_LUT_COPIES*sizeof(float4);
+	static bool attr_done = false;
+	if (!attr_done) {
+		cudaFuncSetAttribute(voxel_glm_kernel<true >, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lut_bytes);
+		cudaFuncSetAttribute(voxel_glm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lut_bytes);
+		attr_done = true;
+	}
+	if (G.perlin) {voxel_glm_kernel<true ><<<grid, bz, lut_bytes, ctx->stream>>>(d_out, G, E, (const float4 *)ctx->d_glm3_lut + twn2::LUT3D_N);}
+	else          {voxel_glm_kernel<false><<<grid, bz, lut_bytes, ctx->stream>>>(d_out, G, E, (const float4 *)ctx->d_glm3_lut);}
 	TW_LAUNCH_CHECK(ctx);
 	return TW_OK;
 }

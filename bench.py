@@ -30,8 +30,8 @@ N_TILE = 8192
 WORKLOAD = "heightgen 8192x8192 tile, mesh_gen_mode 4 (domain-warped simplex), 8 octaves (mesh_freq_filter 1), fp32, glaciate + hmap sine"
 FLOP_PER_CELL = 5200.0    # fp32 pipe operations per cell (FMUL/FADD/FFMA each counted once, floor included): 40 simplex evaluations x ~128 (SASS count of
                           # the scalar kernel's loop) + epilogue; SURVEY.md section 8(d) estimated ~6.8 k with FMA counted twice
-FLOP_EXEC_PER_CELL = 3800.0   # fp32-pipe lane operations the shipped kernel actually executes per cell: the simplex hash/gradient table replaces
-                          # ~1/4 of the reference's arithmetic by shared-memory look-ups (40 evaluations x ~92 + floors + epilogue; ncu: FMA pipe 71 % busy)
+FLOP_EXEC_PER_CELL = 2900.0   # fp32-pipe lane operations the shipped kernel actually executes per cell: the hash/gradient table replaces
+                          # both permutes and the gradient arithmetic by shared-memory look-ups (40 evaluations x ~70 + epilogue; see profiles/ for the pipe utilisation)
 BYTES_PER_CELL = 4.0      # one fp32 store per cell, no reads
 
 
@@ -292,7 +292,7 @@ def main():
                              "frac": FLOP_PER_CELL * cells / (kernel_ms * 1e-3) / alu_peak, "flop_per_cell": FLOP_PER_CELL,
                              "executed_fp32_ops_per_cell": FLOP_EXEC_PER_CELL, "frac_executed": FLOP_EXEC_PER_CELL * cells / (kernel_ms * 1e-3) / alu_peak,
                              "note": "flop_per_cell = the reference algorithm's fp32 operations (what the CPU path executes); the kernel tabulates part of "
-                                     "them, so frac (algorithmic) can approach 1 while the FMA pipe is ~71 % busy (frac_executed)"}},
+                                     "them, so frac (algorithmic) can exceed 1 while the FMA pipe itself is ~70 % busy (frac_executed, profiles/)"}},
     }
     if world == 1:
         if not args.no_extra:   # before the CPU leg, while the GPU clocks are still up
