@@ -438,6 +438,28 @@ int tw_create_zvals_batch(tw_ctx *ctx, const int32_t *origins_xy, uint32_t ntile
 	return TW_OK;
 }
 
+int tw_heightmap_sample_tiles(tw_ctx *ctx, const uint8_t *data16, const tw_hmap_sampler *hs, const int32_t *origins_xy, uint32_t ntiles, uint32_t zvsize, float *out) {
+	int rc = check_ctx(ctx); if (rc) return rc;
+	rc = finish_pending(ctx); if (rc) return rc;
+	if (!data16 || !hs || !origins_xy || !out || ntiles == 0 || zvsize == 0) return tw_set_error(ctx, TW_ERR_ARG, "null/empty argument");
+	if (hs->width <= 0 || hs->height <= 0 || hs->edge_mode < 0 || hs->edge_mode > 2) return tw_set_error(ctx, TW_ERR_ARG, "bad heightmap sampler");
+	if (ntiles > 65535) return tw_set_error(ctx, TW_ERR_ARG, "at most 65535 tiles per call");
+	size_t const img_bytes = ((size_t)2*hs->width*hs->height + 255) & ~(size_t)255, org_bytes = ((size_t)ntiles*8 + 255) & ~(size_t)255;
+	size_t const out_bytes = (size_t)ntiles*zvsize*zvsize*sizeof(float);
+	bool const dev_img = tw_is_device_ptr(data16), dev_out = tw_is_device_ptr(out);
+	rc = tw_reserve(ctx, 0, org_bytes + (dev_img ? 0 : img_bytes) + (dev_out ? 0 : out_bytes) + 256); if (rc) return rc;
+	char *sp = (char *)ctx->d_scratch[0];
+	void *d_org = sp; sp += org_bytes;
+	TW_CUDA(ctx, cudaMemcpyAsync(d_org, origins_xy, (size_t)ntiles*8, cudaMemcpyHostToDevice, ctx->stream));
+	const uint8_t *d_img = data16;
+	if (!dev_img) {TW_CUDA(ctx, cudaMemcpyAsync(sp, data16, (size_t)2*hs->width*hs->height, cudaMemcpyHostToDevice, ctx->stream)); d_img = (const uint8_t *)sp; sp += img_bytes;}
+	float *d_out = dev_out ? out : (float *)sp;
+	rc = twi_hmap_sample_tiles(ctx, d_img, hs, d_org, ntiles, zvsize, d_out); if (rc) return rc;
+	if (!dev_out) {TW_CUDA(ctx, cudaMemcpyAsync(out, d_out, out_bytes, cudaMemcpyDeviceToHost, ctx->stream));}
+	TW_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); // origins_xy is the caller's buffer
+	return TW_OK;
+}
+
 // ------------------------------------------------------------------------------------------------ per-tile normals and ambient occlusion (N1)
 int tw_tile_normals_batch(tw_ctx *ctx, const float *zvals, uint32_t ntiles, uint32_t zvsize, float dx_val, float dy_val, uint8_t *rgba, float *min_normal_z) {
 	int rc = check_ctx(ctx); if (rc) return rc;

@@ -58,3 +58,65 @@ int twi_to_floats_u16(tw_ctx *ctx, const uint8_t *d_data, size_t n, float val_mu
 	TW_LAUNCH_CHECK(ctx);
 	return TW_OK;
 }
+
+// ------------------------------------------------------------------------------------------------ heightmap-texture tiles (N2)
+namespace {
+__device__ __forceinline__ int round_fp(float v) {return (v > 0.0f) ? (int)(v + 0.5f) : (int)(v - 0.5f);} // src/inlines.h:63 (values are small: no x86 overflow semantics needed)
+
+// clamp_no_scale, src/heightmap.cpp:315-341
+__device__ __forceinline__ bool hmap_clamp_no_scale(int &x, int &y, const tw_hmap_sampler &H) {
+	x += H.width/2; y += H.height/2;
+	if (x >= 0 && y >= 0 && x < H.width && y < H.height) return true;
+	switch (H.edge_mode) {
+	case 0: x = max(0, min(H.width - 1, x)); y = max(0, min(H.height - 1, y)); break;
+	case 1: return false;
+	default: {
+		int const xmod = abs(x)%H.width, ymod = abs(y)%H.height, xdiv = x/H.width, ydiv = y/H.height;
+		x = (xdiv & 1) ? (H.width  - xmod - 1) : xmod;
+		y = (ydiv & 1) ? (H.height - ymod - 1) : ymod;
+		}
+	}
+	return true;
+}
+__device__ __forceinline__ float hmap_scale_val(float val, const tw_hmap_sampler &H) { // scale_mh_texture_val, src/mesh_gen.cpp:120
+	return (H.h_scale*H.mesh_file_scale*val + H.mesh_file_tz)*H.mesh_scale_z_inv;
+}
+__device__ __forceinline__ float hmap_raw_height(const uint8_t *__restrict__ d, int x, int y, const tw_hmap_sampler &H) { // get_raw_height
+	size_t const ix = (size_t)H.width*y + x;
+	unsigned const px = __ldg(reinterpret_cast<const unsigned short *>(d) + ix); // little endian: low byte = data[2ix] (fraction), high = data[2ix+1]
+	float const v = (float)((double)(px & 255u)/256.0 + (double)(px >> 8)); // get_heightmap_value: exact in fp32 (16 significant bits)
+	return hmap_scale_val(v, H);
+}
+
+__global__ void __launch_bounds__(256)
+hmap_sample_tiles_kernel(const uint8_t *__restrict__ data16, tw_hmap_sampler H, const int2 *__restrict__ origins, unsigned zvsize, float *__restrict__ out) {
+	unsigned const tile = blockIdx.y, i = blockIdx.x*blockDim.x + threadIdx.x;
+	if (i >= zvsize*zvsize) return;
+	int2 const o = __ldg(origins + tile);
+	int x = o.x + (int)(i % zvsize), y = o.y + (int)(i / zvsize);
+	float z;
+	if (H.mesh_scale < 1.0f) { // interpolate_height(float(x), float(y)), src/heightmap.cpp:394-402
+		float const sx = H.mesh_scale*(float)x, sy = H.mesh_scale*(float)y;
+		int xlo = (int)floorf(sx), ylo = (int)floorf(sy), xhi = (int)ceilf(sx), yhi = (int)ceilf(sy);
+		float const xv = sx - (float)xlo, yv = sy - (float)ylo;
+		bool const ok_lo = hmap_clamp_no_scale(xlo, ylo, H);
+		bool const ok = ok_lo && hmap_clamp_no_scale(xhi, yhi, H); // the reference short-circuits the same way
+		if (!ok) {z = hmap_scale_val(0.0f, H);}
+		else {
+			z = yv*(xv*hmap_raw_height(data16, xhi, yhi, H) + (1.0f - xv)*hmap_raw_height(data16, xlo, yhi, H)) +
+			    (1.0f - yv)*(xv*hmap_raw_height(data16, xhi, ylo, H) + (1.0f - xv)*hmap_raw_height(data16, xlo, ylo, H));
+		}
+	}
+	else { // clamp_xy(x, y): x = round_fp(mesh_scale*(x + 0.0f)), src/heightmap.cpp:309-313
+		x = round_fp(H.mesh_scale*((float)x + 0.0f)); y = round_fp(H.mesh_scale*((float)y + 0.0f));
+		z = hmap_clamp_no_scale(x, y, H) ? hmap_raw_height(data16, x, y, H) : hmap_scale_val(0.0f, H);
+	}
+	out[(size_t)tile*zvsize*zvsize + i] = z;
+}
+} // namespace
+
+int twi_hmap_sample_tiles(tw_ctx *ctx, const uint8_t *d_data16, const tw_hmap_sampler *hs, const void *d_origins, uint32_t ntiles, uint32_t zvsize, float *d_out) {
+	hmap_sample_tiles_kernel<<<dim3((zvsize*zvsize + 255)/256, ntiles), 256, 0, ctx->stream>>>(d_data16, *hs, (const int2 *)d_origins, zvsize, d_out);
+	TW_LAUNCH_CHECK(ctx);
+	return TW_OK;
+}

@@ -38,6 +38,7 @@ struct scene_globals {
 	int   MESH_X_SIZE = 128, MESH_Y_SIZE = 128;
 	float X_SCENE_SIZE = 4.0f, Y_SCENE_SIZE = 4.0f; // get_exact_zval (src/mesh_gen.cpp:818-819)
 	int   xoff2 = 0, yoff2 = 0;                      // current mesh scroll offset (src/mesh_gen.cpp:826-829)
+	float mesh_file_scale = 1.0f, mesh_file_tz = 0.0f; // scale_mh_texture_val (src/mesh_gen.cpp:120), heightmap-texture tiles
 	// erosion (src/erosion.cpp:11,98; src/Textures.cpp:1284-1287)
 	float erode_amount = 1.0f, water_plane_z = 0.0f, HALF_DXY = 0.0625f, zmin = -1.0f, zmax = 1.0f, relh_adj_tex = 0.0f, clip_hd1 = 0.5f;
 };
@@ -246,6 +247,19 @@ inline void create_zvals_batch(const int32_t *origins_xy, unsigned ntiles, unsig
 	// apply_erosion(zvals.data(), zvsize, zvsize, zmin, erosion_iters_tt): min_zval is the global zmin (src/tiled_mesh.cpp:515)
 	int const rc = tw_create_zvals_batch(c, origins_xy, ntiles, g.MESH_X_SIZE, g.MESH_Y_SIZE, dx, dy, zvsize, &p, erosion_iters_tt, &e, g.zmin, zvals_out, mm);
 	if (rc != TW_OK) {detail::fail(rc, "create_zvals_batch", c);}
+}
+
+// heightmap-texture mode of tile_t::create_zvals (src/tiled_mesh.cpp:498-501): zvals[y*zvsize + x] = terrain_hmap_manager.get_clamped_height(x1 + x, y1 + y)
+// for a batch of tiles, from the 16-bit image hmap16 (width*height*2 bytes, the layout heightmap_t keeps); TEX_EDGE_MODE 2 = mirror as compiled in the reference
+inline void create_zvals_from_heightmap(const uint8_t *hmap16, int width, int height, const int32_t *origins_xy, unsigned ntiles, unsigned zvsize, float *zvals_out, int tex_edge_mode = TW_HMAP_EDGE_MIRROR) {
+	scene_globals const &g = globals();
+	tw_hmap_sampler hs;
+	hs.width = width; hs.height = height; hs.edge_mode = tex_edge_mode; hs.mesh_scale = g.mesh_scale;
+	hs.h_scale = 0.0008f*g.mesh_height_scale; // READ_MESH_H_SCALE*mesh_height_scale (src/mesh_gen.cpp:22,120)
+	hs.mesh_file_scale = g.mesh_file_scale; hs.mesh_file_tz = g.mesh_file_tz; hs.mesh_scale_z_inv = g.mesh_scale_z_inv;
+	tw_ctx *c = ctx();
+	int const rc = tw_heightmap_sample_tiles(c, hmap16, &hs, origins_xy, ntiles, zvsize, zvals_out);
+	if (rc != TW_OK) {detail::fail(rc, "create_zvals_from_heightmap", c);}
 }
 
 // tile_t::upload_normal_texture (src/tiled_mesh.cpp:865-880, minus the GL upload) and tile_t::calc_mesh_ao_lighting (:586-662) for a batch of

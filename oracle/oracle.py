@@ -53,6 +53,11 @@ class PointQuery(C.Structure):
                 ("y_scene_size", C.c_float), ("xoff2", C.c_int), ("yoff2", C.c_int), ("no_xyoff", C.c_int)]
 
 
+class HmapSampler(C.Structure):
+    _fields_ = [("width", C.c_int), ("height", C.c_int), ("edge_mode", C.c_int), ("mesh_scale", C.c_float), ("h_scale", C.c_float),
+                ("mesh_file_scale", C.c_float), ("mesh_file_tz", C.c_float), ("mesh_scale_z_inv", C.c_float)]
+
+
 class Rng(C.Structure):
     _fields_ = [("rseed1", C.c_int64), ("rseed2", C.c_int64)]
 
@@ -106,6 +111,7 @@ def lib():
         L.to_tile_bounds.argtypes = [vp, C.c_uint, C.c_uint, C.c_float, C.c_float, C.c_float, C.c_uint, vp]
         L.to_tile_normals.argtypes = [vp, C.c_uint, C.c_uint, C.c_float, C.c_float, vp, vp]
         L.to_tile_ao.argtypes = [vp, vp, C.c_uint, C.c_uint, C.c_float, vp]
+        L.to_hmap_sample_tiles.argtypes = [vp, C.POINTER(HmapSampler), vp, C.c_uint, C.c_uint, vp]
         L.to_eval_points.argtypes = [vp, C.c_size_t, C.POINTER(HeightParams), C.POINTER(PointQuery), vp, vp, vp]
         L.to_apply_erosion.argtypes = [vp, C.c_int, C.c_int, C.c_float, C.c_uint, C.POINTER(ErosionParams)]
         L.to_apply_erosion.restype = C.c_ulonglong
@@ -201,6 +207,14 @@ def tile_ao(tiles, contexts, half_dxy):
     ao = np.empty((nt, zv - 1, zv - 1), np.uint8)
     lib().to_tile_ao(_p(tiles), _p(contexts), nt, zv, half_dxy, _p(ao))
     return ao
+
+
+def hmap_sample_tiles(data16, hs, origins_xy, zvsize):
+    data16 = np.ascontiguousarray(data16, np.uint8)
+    org = np.ascontiguousarray(origins_xy, np.int32).reshape(-1, 2)
+    out = np.empty((org.shape[0], zvsize, zvsize), np.float32)
+    lib().to_hmap_sample_tiles(_p(data16), C.byref(hs), _p(org), org.shape[0], zvsize, _p(out))
+    return out
 
 
 def eval_points(xy, hp, pq, sine_params=None):

@@ -122,6 +122,16 @@ def tile_normals(tile, dx_val, dy_val):
     return rgba, mnz.value
 
 
+def hmap_sample_tile(data16, x1, y1, zvsize, mesh_scale=1.0, mesh_file_scale=1.0, mesh_file_tz=0.0):
+    """terrain_hmap_manager_t::get_clamped_height of the reference over one tile (TEX_EDGE_MODE 2 = mirror, compile-time)."""
+    data16 = np.ascontiguousarray(data16, np.uint8)
+    h, w = data16.shape[0], data16.shape[1]
+    out = np.empty((zvsize, zvsize), np.float32)
+    lib().ref_hmap_sample_tile(data16.ctypes.data_as(C.c_void_p), w, h, int(x1), int(y1), zvsize, C.c_float(mesh_scale), C.c_float(mesh_file_scale),
+                               C.c_float(mesh_file_tz), out.ctypes.data_as(C.c_void_p))
+    return out
+
+
 def eval_points(kind, xy, xy_scale=1.0, no_xyoff=0, xoff2=0, yoff2=0):
     """kind 0/1/2 = eval_mesh_sin_terms / eval_mesh_sin_terms_scaled / get_exact_zval of the reference for every (x, y) row."""
     xy = np.ascontiguousarray(xy, np.float32).reshape(-1, 2)

@@ -15,6 +15,7 @@
 #include "mesh.h"        // gen_mode 3/4 (whose reference implementation needs a GL shader) on the CPU get_noise_zval() path
 #undef class
 #include "upsurface.h"
+#include "heightmap.h"
 #include "sinf.h"
 #include <omp.h>
 
@@ -36,6 +37,7 @@ float get_water_z_height();
 float eval_mesh_sin_terms_scaled(float xval, float yval, float xy_scale);
 float get_exact_zval(float xval_in, float yval_in, bool no_xyoff);
 extern int xoff2, yoff2;
+extern float mesh_file_scale, mesh_file_tz;
 void apply_erosion(float *heightmap, int xsize, int ysize, float min_zval, unsigned num_iters);
 void gen_rx_ry(float &rx, float &ry);
 
@@ -128,6 +130,25 @@ void ref_tile_normals(const float *zvals, unsigned zvsize, float dx_val, float d
 		}
 	}
 	*min_normal_z_out = min_normal_z;
+}
+// terrain_hmap_manager_t::get_clamped_height (src/heightmap.cpp:385-402) over a zvsize^2 tile at (x1, y1), as tile_t::create_zvals' heightmap
+// branch calls it (src/tiled_mesh.cpp:500); the manager's protected heightmap_t is filled with a caller-provided 16-bit image
+struct ref_hmap_mgr_t : public terrain_hmap_manager_t {
+	void set_image(const unsigned char *data16, int w, int h) {hmap.width = w; hmap.height = h; hmap.ncolors = 2; hmap.alloc(); memcpy(hmap.get_data(), data16, 2*(size_t)w*h);}
+	void clear_image() {hmap.free_client_mem();}
+};
+void ref_hmap_sample_tile(const unsigned char *data16, int w, int h, int x1, int y1, unsigned zvsize, float mesh_scale_, float mesh_file_scale_, float mesh_file_tz_, float *out) {
+	float const ms(mesh_scale), mfs(mesh_file_scale), mft(mesh_file_tz);
+	mesh_scale = mesh_scale_; mesh_file_scale = mesh_file_scale_; mesh_file_tz = mesh_file_tz_;
+	{
+		ref_hmap_mgr_t mgr;
+		mgr.set_image(data16, w, h);
+		for (unsigned y = 0; y < zvsize; ++y) {
+			for (unsigned x = 0; x < zvsize; ++x) {out[y*zvsize + x] = mgr.get_clamped_height((x1 + x), (y1 + y));}
+		}
+		mgr.clear_image();
+	}
+	mesh_scale = ms; mesh_file_scale = mfs; mesh_file_tz = mft;
 }
 // kind 0/1/2 = eval_mesh_sin_terms / eval_mesh_sin_terms_scaled / get_exact_zval for n points (the loop is the driver's; each value is the reference's)
 void ref_eval_points(int kind, const float *xy, size_t n, float xy_scale, int no_xyoff, int xo, int yo, float *out) {

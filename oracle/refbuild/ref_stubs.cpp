@@ -82,11 +82,12 @@ bool open_file(FILE *&fp, char const *const fn, std::string const &file_type, ch
 void texture_t::resize(int, int) {}
 void texture_t::load(int, bool, bool, bool) {}
 void texture_t::gl_delete() {}
-void texture_t::free_client_mem() {}
-float heightmap_t::get_heightmap_value(unsigned, unsigned) const {return 0.0;}
+void texture_t::free_client_mem() {delete [] data; data = nullptr;} // client-memory part of src/Textures.cpp:512-518
+void texture_t::alloc() {free_client_mem(); data = new unsigned char[(size_t)width*height*ncolors];} // src/Textures.cpp:486-490 without the GL state
 
 // ---- get_exact_zval(): procedural branch only (no tiled-terrain heightmap texture loaded) ----
 char *mh_filename_tt(nullptr);
 bool using_tiled_terrain_hmap_tex() {return 0;}
 bool using_hmap_with_detail() {return 0;}
 float get_tiled_terrain_height_tex(float, float, bool) {return 0.0;}
+unsigned hmap_filter_width(0); // src/3DWorld.cpp: config value "hmap_filter_width", default 0 (only used for 8-bit heightmaps)

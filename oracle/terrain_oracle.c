@@ -695,6 +695,57 @@ void to_tile_ao(const float *zvals_all, const float *czv_all, unsigned ntiles, u
 	}
 }
 
+/* ------------------------------------------------------------------ heightmap-texture tiles (ref: src/heightmap.cpp:74-77,309-341,385-402; src/mesh_gen.cpp:120) */
+static int round_fp_f(float v) {return (v > 0.0f) ? (int)(v + 0.5f) : (int)(v - 0.5f);} /* ref: src/inlines.h:63 */
+static int hmap_clamp_no_scale(int *x, int *y, const tw_hmap_sampler *H) { /* ref: src/heightmap.cpp:315-341 */
+	*x += H->width/2; *y += H->height/2;
+	if (*x >= 0 && *y >= 0 && *x < H->width && *y < H->height) return 1;
+	switch (H->edge_mode) {
+	case 0:
+		*x = (0 < ((H->width -1 < *x) ? H->width -1 : *x)) ? ((H->width -1 < *x) ? H->width -1 : *x) : 0;
+		*y = (0 < ((H->height-1 < *y) ? H->height-1 : *y)) ? ((H->height-1 < *y) ? H->height-1 : *y) : 0;
+		break;
+	case 1: return 0;
+	default: {
+		int const xmod = abs(*x)%H->width, ymod = abs(*y)%H->height, xdiv = *x/H->width, ydiv = *y/H->height;
+		*x = (xdiv & 1) ? (H->width  - xmod - 1) : xmod;
+		*y = (ydiv & 1) ? (H->height - ymod - 1) : ymod;
+		}
+	}
+	return 1;
+}
+static float hmap_scale_val(float val, const tw_hmap_sampler *H) {return (H->h_scale*H->mesh_file_scale*val + H->mesh_file_tz)*H->mesh_scale_z_inv;}
+static float hmap_raw_height(const unsigned char *data, int x, int y, const tw_hmap_sampler *H) {
+	size_t const ix = (size_t)H->width*y + x;
+	float const v = (float)(data[ix<<1]/256.0 + data[(ix<<1)+1]); /* get_heightmap_value, ncolors == 2 */
+	return hmap_scale_val(v, H);
+}
+void to_hmap_sample_tiles(const unsigned char *data16, const tw_hmap_sampler *H, const int *origins_xy, unsigned ntiles, unsigned zvsize, float *out) {
+	for (unsigned t = 0; t < ntiles; ++t) {
+		for (unsigned yy = 0; yy < zvsize; ++yy) {
+			for (unsigned xx = 0; xx < zvsize; ++xx) {
+				int x = origins_xy[2*t] + (int)xx, y = origins_xy[2*t+1] + (int)yy;
+				float z;
+				if (H->mesh_scale < 1.0) { /* interpolate_height */
+					float const sx = H->mesh_scale*(float)x, sy = H->mesh_scale*(float)y;
+					int xlo = (int)floorf(sx), ylo = (int)floorf(sy), xhi = (int)ceilf(sx), yhi = (int)ceilf(sy);
+					float const xv = sx - xlo, yv = sy - ylo;
+					if (!hmap_clamp_no_scale(&xlo, &ylo, H) || !hmap_clamp_no_scale(&xhi, &yhi, H)) {z = hmap_scale_val(0.0f, H);}
+					else {
+						z = yv*(xv*hmap_raw_height(data16, xhi, yhi, H) + (1.0f-xv)*hmap_raw_height(data16, xlo, yhi, H)) +
+						    (1.0f-yv)*(xv*hmap_raw_height(data16, xhi, ylo, H) + (1.0f-xv)*hmap_raw_height(data16, xlo, ylo, H));
+					}
+				}
+				else {
+					x = round_fp_f(H->mesh_scale*(x + 0.0f)); y = round_fp_f(H->mesh_scale*(y + 0.0f));
+					z = hmap_clamp_no_scale(&x, &y, H) ? hmap_raw_height(data16, x, y, H) : hmap_scale_val(0.0f, H);
+				}
+				out[((size_t)t*zvsize + yy)*zvsize + xx] = z;
+			}
+		}
+	}
+}
+
 /* ------------------------------------------------------------------ point queries (ref: src/mesh_gen.cpp:797-847) */
 static float eval_mesh_sin_terms_scaled(float xval, float yval, float xy_scale, int MX, int MY, const tw_height_params *p, const float *tab, const float *T) { /* ref: :807-813 */
 	float const xv = xy_scale*(xval - (float)(MX >> 1)), yv = xy_scale*(yval - (float)(MY >> 1));

@@ -34,5 +34,13 @@ for mode in (0, 1, 4):
     rgba, mnz = R.tile_normals(tile, dx, dy)
     d["normals_" + n], d["min_normal_z_" + n] = rgba, np.float32(mnz)
     d["ao_" + n] = O.tile_ao(tile[None], context[None], RL.ref_get_half_dxy())[0]
+# heightmap-texture tiles (N2): the reference's terrain_hmap_manager_t::get_clamped_height over a 16-bit image (mirror edges)
+rng = np.random.default_rng(77)
+R.setup(mode=0, freq_filter=1, seed=1, mesh_height_scale=1.5, mesh_scale_z=2.0)
+img = rng.integers(0, 256, (40, 56, 2), dtype=np.uint8)
+d["hmap_img"] = img
+cases = [(1.0, 1.0, 0.0, -20, -15), (0.5, 2.5, -0.75, -60, 30), (2.0, 0.8, 0.0, 100, -90), (0.37, 1.0, 0.1, -1000, 999)]
+d["hmap_cases"] = np.array(cases, np.float64)
+d["hmap_out"] = np.stack([R.hmap_sample_tile(img, int(x1), int(y1), 34, ms, mfs, tz) for ms, mfs, tz, x1, y1 in cases])
 np.savez_compressed(os.path.join(HERE, "tiles.npz"), **d)
 print("wrote tiles.npz", {k: v.shape for k, v in d.items() if k.startswith(("ao", "normals"))}, [float(d["ao_m%d" % m].mean()) for m in (0, 1, 4)])

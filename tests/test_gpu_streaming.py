@@ -2,6 +2,8 @@
 import numpy as np
 import pytest
 
+from cases import convert
+
 pytestmark = pytest.mark.gpu
 
 
@@ -42,3 +44,25 @@ def test_argument_errors(tw, scene, ctx):
     hp.gen_mode = 9
     with pytest.raises(tw.TwError):
         ctx.heightgen_2d(tw.Grid2D(0, 0, 1, 1, 4, 4), hp)
+
+
+def test_heightmap_texture_tiles(tw, oracle, ctx, beq):
+    """N2: heightmap-texture mode of tile_t::create_zvals (get_clamped_height) - golden outputs of the linked reference, then a batch with all
+    three edge modes, host and device pointers, vs the oracle."""
+    import os
+    import torch
+    from test_oracle_golden import hmap_cases
+    h = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "tiles.npz"))
+    for img, hs, org, exp in hmap_cases(tw, h):
+        assert beq(ctx.heightmap_sample_tiles(img, hs, [org], 34)[0], exp) == 0
+    rng = np.random.default_rng(9)
+    img = rng.integers(0, 256, (300, 257, 2), dtype=np.uint8)
+    origins = [(int(x), int(y)) for x, y in rng.integers(-900, 900, (40, 2))]
+    for edge in (0, 1, 2):
+        for ms in (1.0, 0.45, 2.2):
+            hs = tw.HmapSampler(257, 300, edge, ms, 0.0012, 1.7, -0.3, 0.8)
+            exp = oracle.hmap_sample_tiles(img, convert(hs, oracle.HmapSampler), origins, 66)
+            assert beq(ctx.heightmap_sample_tiles(img, hs, origins, 66), exp) == 0
+            d_out = torch.empty((len(origins), 66, 66), dtype=torch.float32, device="cuda")
+            ctx.heightmap_sample_tiles(torch.from_numpy(img).cuda(), hs, origins, 66, out=d_out)
+            assert beq(d_out.cpu().numpy(), exp) == 0

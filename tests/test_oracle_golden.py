@@ -125,6 +125,19 @@ def test_tile_normals_and_ao(oracle, beq):
         assert np.array_equal(oracle.tile_ao(tile[None], context[None], half_dxy)[0], h["ao_" + n])
 
 
+def hmap_cases(mod, h):
+    f32 = np.float32
+    for (ms, mfs, tz, x1, y1), exp in zip(h["hmap_cases"], h["hmap_out"]):
+        img = h["hmap_img"]
+        hs = mod.HmapSampler(img.shape[1], img.shape[0], 2, float(ms), float(f32(0.0008) * f32(1.5)), float(mfs), float(tz), 0.5)
+        yield img, hs, (int(x1), int(y1)), exp
+
+
+def test_heightmap_texture_tiles(oracle, beq):
+    for img, hs, org, exp in hmap_cases(oracle, load("tiles.npz")):
+        assert beq(oracle.hmap_sample_tiles(img, hs, [org], 34)[0], exp) == 0
+
+
 def test_erosion(oracle, beq):
     e = load("erosion.npz")
     for key_in, keys in (("in0", ["0_%d" % i for i in range(3)]), ("mesh128_in", ["mesh128"])):

@@ -90,6 +90,22 @@ def test_tile_normals(oracle, ref, beq):
     assert np.array_equal(oracle.tile_normals(tiles[1][None], 0.0625, 0.0625)[0][0, 0, 0], [127, 127, 254, 0])
 
 
+def test_heightmap_texture_tiles(oracle, ref, beq):
+    """SURVEY 8f row N2: terrain_hmap_manager_t::get_clamped_height (nearest texel, bilinear for mesh_scale < 1, mirror edges) of the linked
+    reference vs the oracle, tiles inside, across and far outside a 16-bit image (odd sizes included)."""
+    rng = np.random.default_rng(3)
+    ref.setup(mode=0, freq_filter=1, seed=1, mesh_height_scale=1.5, mesh_scale_z=2.0)
+    f32 = np.float32
+    for w, h in ((64, 48), (33, 71)):
+        img = rng.integers(0, 256, (h, w, 2), dtype=np.uint8)
+        for ms, mfs, tz in ((1.0, 1.0, 0.0), (0.5, 2.5, -0.75), (0.37, 1.0, 0.1), (2.0, 0.8, 0.0), (3.3, 1.0, 1.0)):
+            hs = oracle.HmapSampler(w, h, 2, ms, float(f32(0.0008) * f32(1.5)), mfs, tz, 0.5)
+            for x1, y1 in ((-10, -9), (-w // 2 - 5, h // 2 - 7), (3 * w + 1, -5 * h - 2), (-1000, 999)):
+                zr = ref.hmap_sample_tile(img, x1, y1, 18, ms, mfs, tz)
+                zo = oracle.hmap_sample_tiles(img, hs, [(x1, y1)], 18)[0]
+                assert beq(zr, zo) == 0, (w, h, ms, x1, y1)
+
+
 def test_erosion_serial_order(oracle, ref, beq):
     ref.lib().ref_set_threads(1)
     ref.setup(mode=1, freq_filter=1, seed=1, zmax_est=2.0, hmap=HM_CFG)
