@@ -44,13 +44,13 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi -lms 100 in the background during the timed region (the profiling recipe's clocks line)."""
+    """nvidia-smi -lms 20 in the background during the timed region (the profiling recipe's clocks line)."""
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, index):
         self.lines = []
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -208,9 +208,9 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local)           # started before the warm-up so that nvidia-smi is already streaming when the timed region begins
     for _ in range(max(args.warmup, 3)):
         step_device()
-    sampler = ClockSampler(local)
     barrier()
     sampler.mark()
     launches0 = ctx.launch_count
