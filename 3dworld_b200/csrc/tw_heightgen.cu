@@ -267,12 +267,14 @@ void launch_noise2(int shape, dim3 grid, dim3 block, cudaStream_t st, float *out
 	const float2 *origins, const NoiseParams &N, const PostParams &P, const float *tab, unsigned *mm, const float4 *lut)
 {
 	size_t const lut_bytes = (TW_SIMPLEX_LUT > 0) ? (size_t)twn2::SIMPLEX_LUT_N*twn2::SIMPLEX_LUT_COPIES*sizeof(float4) : 0;
-	static bool attr_done = false; // per template instantiation: allow more than 48 KB of dynamic shared memory
-	if (!attr_done && lut_bytes > 48*1024) {
-		cudaFuncSetAttribute(noise_grid2_kernel<SIMPLEX, WARP, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lut_bytes);
-		cudaFuncSetAttribute(noise_grid2_kernel<SIMPLEX, WARP, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lut_bytes);
-		cudaFuncSetAttribute(noise_grid2_kernel<SIMPLEX, WARP, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lut_bytes);
-		attr_done = true;
+	// more than 48 KB of dynamic shared memory needs the opt-in; set per launch (a few hundred ns) rather than cached in a static, so that
+	// contexts on several devices in one process all get it
+	if (lut_bytes > 48*1024) {
+		switch (shape) {
+		case 1:  cudaFuncSetAttribute(noise_grid2_kernel<SIMPLEX, WARP, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lut_bytes); break;
+		case 2:  cudaFuncSetAttribute(noise_grid2_kernel<SIMPLEX, WARP, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lut_bytes); break;
+		default: cudaFuncSetAttribute(noise_grid2_kernel<SIMPLEX, WARP, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lut_bytes); break;
+		}
 	}
 	switch (shape) {
 	case 1:  noise_grid2_kernel<SIMPLEX, WARP, 1><<<grid, block, lut_bytes, st>>>(out, nx, ny, y_off, y_end, mx0, my0, origins, N, P, tab, mm, lut); break;

@@ -215,12 +215,8 @@ int twi_voxel_fill(tw_ctx *ctx, const tw_voxel_params *vp, const float *rdata420
 	unsigned const bz = (nz > 128) ? 256 : 128;
 	dim3 const grid((nz + bz - 1)/bz, (nx + VGX - 1)/VGX, ny);
 	size_t const lut_bytes = (size_t)twn2::LUT3D_N*twn2::SIMPLEX_LUT_COPIES*sizeof(float4);
-	static bool attr_done = false;
-	if (!attr_done) {
-		cudaFuncSetAttribute(voxel_glm_kernel<true >, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lut_bytes);
-		cudaFuncSetAttribute(voxel_glm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lut_bytes);
-		attr_done = true;
-	}
+	if (G.perlin) {cudaFuncSetAttribute(voxel_glm_kernel<true >, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lut_bytes);} // > 48 KB opt-in, per launch (any device)
+	else          {cudaFuncSetAttribute(voxel_glm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lut_bytes);}
 	if (G.perlin) {voxel_glm_kernel<true ><<<grid, bz, lut_bytes, ctx->stream>>>(d_out, G, E, (const float4 *)ctx->d_glm3_lut + twn2::LUT3D_N);}
 	else          {voxel_glm_kernel<false><<<grid, bz, lut_bytes, ctx->stream>>>(d_out, G, E, (const float4 *)ctx->d_glm3_lut);}
 	TW_LAUNCH_CHECK(ctx);

@@ -106,3 +106,34 @@ def test_division_free_forms():
         fi = f32(i)
         q0 = fi * c41
         assert fma(fma(-q0, f32(41.0), fi), c41, q0) == fi / f32(41.0)
+
+
+def test_hash_table_arguments_are_exact():
+    """csrc/tw_noise2.cuh tabulates the Ashima hash: `permute(k)` is looked up for k <= 290, the gradient entry is indexed by the argument of the
+    next permute (k <= 578), and mod(i, 289) is left 'lazy' (289 may stand for 0). All of that rests on three facts about the reference's fp32
+    arithmetic, checked here exhaustively with numpy (IEEE round-to-nearest fp32):
+      1. permute(k) = mod289((34k + 1)k) in fp32 equals the exact integer (34k^2 + k) mod 289 for every k in [0, 580): no rounding anywhere;
+      2. hence permute(k + 289) == permute(k), so a lazy 289 (or 290) hashes like 0 (or 1);
+      3. the lazy remainder a - 289*floor(a*RN(1/289)) lies in [0, 289] for |a| < 2^22 and is 289 only for multiples of 289;
+         the 3-D kernels use the same multiply form directly (glm mod289) and guard |a| < 2^20."""
+    f32 = np.float32
+    k = np.arange(0, 580, dtype=np.int64)
+    kf = k.astype(f32)
+    prod = (kf * f32(34.0) + f32(1.0)) * kf                                   # two roundings in the reference; exact because < 2^24
+    assert np.array_equal(prod.astype(np.int64), (34 * k + 1) * k) and prod.max() < 2 ** 24
+    t = np.floor(prod * (f32(1.0) / f32(289.0)))
+    perm = prod - t * f32(289.0)                                              # fma(-t, 289, prod) == this: both exact
+    assert np.array_equal(perm.astype(np.int64), ((34 * k + 1) * k) % 289)
+    assert np.array_equal(perm[289:578], perm[0:289])                         # permute(k + 289) == permute(k)
+    assert perm.max() <= 288 and perm.min() >= 0
+    # arguments reachable in the 2-D kernels: q + ix + 1 with q <= 288, ix <= 289 (lazy) -> <= 578 < table size 580
+    assert 288 + 289 + 1 < 580
+    a = np.arange(-(1 << 22) + 1, 1 << 22, dtype=np.int64)
+    af = a.astype(f32)
+    r = af - np.floor(af * (f32(1.0) / f32(289.0))) * f32(289.0)
+    assert r.min() >= 0 and r.max() <= 289
+    assert np.array_equal(r == 289, (a % 289 == 0) & (r != 0))
+    assert np.array_equal(r.astype(np.int64) % 289, a % 289)
+    # table offsets: k*128 + 1.5*2^23 is exact in fp32 and its bit pattern is 0x4B400000 + 128k
+    off = (kf * f32(128.0) + f32(12582912.0)).view(np.uint32).astype(np.int64)
+    assert np.array_equal(off, 0x4B400000 + 128 * k)
