@@ -6,8 +6,12 @@
 //   sine_tables_kernel   build_arrays sine branch (:604-626) + enable_glaciate cos terms (:640-650); k-major tables, LUT sin/cos
 //   sine_grid_kernel     eval_index sine branch (:766-781): z = sum_k X[k][x]*Y[k][y], sequential fp32 sum, register-tiled 4x4 per thread,
 //                        X/Y panels staged in shared memory; fused shape/postproc/glaciate/sine-bias/volcano + min/max
-//   noise_grid_kernel    eval_index noise branch (:761-764 -> get_noise_zval): per-cell fBm of simplex/perlin, optional domain warp,
-//                        fused postproc/scale/glaciate/sine-bias/volcano + min/max. Pure FP32 ALU work: 4 B/cell of HBM traffic.
+//   noise_grid2_kernel   eval_index noise branch (:761-764 -> get_noise_zval): fBm of simplex/perlin, optional domain warp, two cells per
+//                        thread on packed fp32x2 with the hash/gradient table of tw_noise2.cuh in shared memory; fused postproc/scale/
+//                        glaciate/sine-bias/volcano + min/max. Pure FP32 ALU work: 4 B/cell of HBM traffic. (the shipped kernel)
+//   noise_grid_kernel    the same one cell per thread in scalar arithmetic, no table: A/B reference (env TW_NOISE_SCALAR) and the
+//                        literal fallback for astronomically distant lattice coordinates
+//   points_kernel        eval_mesh_sin_terms / eval_mesh_sin_terms_scaled / get_exact_zval for batches of arbitrary points (:797-847)
 // All arithmetic keeps the reference's rounding sequence (this TU is compiled with -fmad=false; see tw_noise.cuh).
 #include "tw_internal.h"
 #include "tw_noise.cuh"

@@ -1,4 +1,6 @@
-// tw_noise2.cuh - two-cells-per-thread versions of glm::simplex(vec2) / glm::perlin(vec2) on Blackwell's packed fp32x2 instructions
+// tw_noise2.cuh - two-cells-per-thread versions of glm::simplex(vec2) / glm::perlin(vec2) on Blackwell's packed fp32x2 instructions,
+// their table-driven forms (simplex2_lut / perlin2_lut: hash and gradient from a shared-memory table, the shipped path) and the table-driven
+// one-voxel-per-thread 3-D forms (simplex3_lut / perlin3_lut)
 // (FFMA2 / FMUL2, sm_100+: `fma/mul.rn.f32x2`): one instruction performs the same IEEE operation on two independent cells, so the
 // reference's unfused multiply/add arithmetic needs half the issue slots (tools/mb/f32x2b.cu: FFMA2 issues at half rate, i.e. the fp32
 // lane throughput is unchanged - the gain is on the instruction-issue side, which is what bounds the scalar kernel).
@@ -114,7 +116,7 @@ __device__ __forceinline__ f2 simplex2(f2 vx, f2 vy) {
 //   q = permute(iy + {0, i1.y, 1})       argument in [0, 290]  -> value in [0, 288]
 //   p = permute(q + ix + {0, i1.x, 1})   argument in [0, 578]  -> value in [0, 288]   (exhaustively: the float arithmetic is exact there)
 //   x = 2*fract(p*C.w) - 1, h = |x| - 0.5, a0 = x - floor(x + 0.5), n = taylorInvSqrt(a0*a0 + h*h)   depend on p only.
-// simplex_lut_entry() evaluates exactly those reference operations once per integer; the kernel keeps the 291-entry table
+// simplex_lut_entry() evaluates exactly those reference operations once per integer; at levels 1/2 the kernel keeps a 291-entry table
 // {a0, h, n, permute(k)} in shared memory and replaces 11 packed instructions + 4 floors per corner (level 1: gradient) plus 4 + 2 per
 // corner (level 2: the first permute) by one 16-byte load each. Random indices would collide on the 32 banks, so the table is stored as 8
 // interleaved copies: entry k of copy c sits at float4 index 8*k + c and lane l reads copy l & 7 - the 8 lanes of every quarter-warp phase
