@@ -171,6 +171,9 @@ noise_grid_kernel(float *__restrict__ out, unsigned nx, unsigned ny, unsigned y_
 #ifndef TW_NOISE2_MIN_BLOCKS
 #define TW_NOISE2_MIN_BLOCKS 3   // 74 KB of table per block (tw_noise2.cuh, level 3) => 3 blocks per SM
 #endif
+#ifndef TW_NOISE2_THREADS
+#define TW_NOISE2_THREADS 256    // threads per block; (512, 2 blocks) = 32 warps per SM at 64 registers is the next experiment
+#endif
 // ---- packed variant: two horizontally adjacent cells per thread on FFMA2/FMUL2/FADD2 (see tw_noise2.cuh) ----
 // |lattice coordinate| < 2^22 for every octave of this fBm call (needed by the packed floor / division-free mod); NaN-safe
 __device__ __forceinline__ bool noise_lattice_in_range(float2 xv, float2 yv, const NoiseParams &N) {
@@ -198,7 +201,7 @@ __device__ __forceinline__ float2 gen_noise2(float2 xv, float2 yv, const NoisePa
 __device__ __forceinline__ float dadd(float a, double b) {return (float)((double)a + b);} // float + double literal, rounded back (src/mesh_gen.cpp:742-745)
 
 template<bool SIMPLEX, bool WARP, int SHAPE>
-__global__ void __launch_bounds__(256, TW_NOISE2_MIN_BLOCKS)
+__global__ void __launch_bounds__(TW_NOISE2_THREADS, TW_NOISE2_MIN_BLOCKS)
 noise_grid2_kernel(float *__restrict__ out, unsigned nx, unsigned ny, unsigned y_off, unsigned y_end, float mx0_single, float my0_single, const float2 *__restrict__ tile_origins,
 	NoiseParams N, PostParams P, const float *__restrict__ sin_tab, unsigned *__restrict__ mm, const float4 *__restrict__ simplex_lut)
 {
@@ -552,8 +555,8 @@ int twi_heightgen(tw_ctx *ctx, const tw_grid2d *g, const tw_height_params *p, in
 			static bool const use_scalar = (getenv("TW_NOISE_SCALAR") != nullptr); // A/B switch: one cell per thread, scalar FMUL/FADD
 			if (!use_scalar) { // two cells per thread on packed fp32x2 instructions
 				size_t const band_cells = (size_t)(r1 - r0)*nx;
-				size_t const cells_per_block = 512*(size_t)((p->gen_mode == TW_MGEN_DWARP_GPU) ? 1 : 4); // noise_grid2_kernel: NCH chunks of 256 threads x 2 cells
-				dim3 const block(256, 1, 1), grid((unsigned)((band_cells + cells_per_block - 1)/cells_per_block), 1, ntiles);
+				size_t const cells_per_block = 2*TW_NOISE2_THREADS*(size_t)((p->gen_mode == TW_MGEN_DWARP_GPU) ? 1 : 4); // noise_grid2_kernel: NCH chunks of blockDim threads x 2 cells
+				dim3 const block(TW_NOISE2_THREADS, 1, 1), grid((unsigned)((band_cells + cells_per_block - 1)/cells_per_block), 1, ntiles);
 				if (p->gen_mode == TW_MGEN_PERLIN) {launch_noise2<false, false>(p->gen_shape, grid, block, ctx->stream, d_out, nx, ny, r0, r1, mx0, my0, d_tile_origins, N, P, ctx->d_sin_table, d_mm_ord, lut);}
 				else if (warp) {launch_noise2<true, true >(p->gen_shape, grid, block, ctx->stream, d_out, nx, ny, r0, r1, mx0, my0, d_tile_origins, N, P, ctx->d_sin_table, d_mm_ord, lut);}
 				else           {launch_noise2<true, false>(p->gen_shape, grid, block, ctx->stream, d_out, nx, ny, r0, r1, mx0, my0, d_tile_origins, N, P, ctx->d_sin_table, d_mm_ord, lut);}
