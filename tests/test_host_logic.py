@@ -137,3 +137,37 @@ def test_hash_table_arguments_are_exact():
     # table offsets: k*128 + 1.5*2^23 is exact in fp32 and its bit pattern is 0x4B400000 + 128k
     off = (kf * f32(128.0) + f32(12582912.0)).view(np.uint32).astype(np.int64)
     assert np.array_equal(off, 0x4B400000 + 128 * k)
+
+
+def test_ctypes_mirrors_match_the_header_layout(tw, oracle, tmp_path):
+    """The ctypes structures of the binding (and of the oracle's wrapper) must have the size and field offsets the C compiler gives the PODs
+    of include/tw3d.h - a drifted mirror would silently shift every parameter after it."""
+    import ctypes as C
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    pods = {"tw_hmap_params": "HmapParams", "tw_height_params": "HeightParams", "tw_grid2d": "Grid2D", "tw_minmax": "MinMax", "tw_erosion_params": "ErosionParams",
+            "tw_voxel_params": "VoxelParams", "tw_tile_bounds": "TileBounds", "tw_heightmap_info": "HeightmapInfo", "tw_rng": "Rng",
+            "tw_point_query": "PointQuery", "tw_hmap_sampler": "HmapSampler"}
+    lines = ['#include <tw3d.h>', '#include <stdio.h>', '#include <stddef.h>', 'int main(void) {']
+    for c_name, py_name in pods.items():
+        cls = getattr(tw, py_name)
+        lines.append('printf("%s %%zu", sizeof(%s));' % (c_name, c_name))
+        for fname, _ in cls._fields_:
+            lines.append('printf(" %%zu", offsetof(%s, %s));' % (c_name, fname))
+        lines.append('printf("\\n");')
+    lines += ['return 0;', '}']
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = str(tmp_path / "layout")
+    subprocess.check_call(["gcc", "-I", os.path.join(root, "include"), str(src), "-o", exe])
+    out = subprocess.check_output([exe], text=True).strip().splitlines()
+    assert len(out) == len(pods)
+    for line, (c_name, py_name) in zip(out, pods.items()):
+        nums = [int(v) for v in line.split()[1:]]
+        for mod in (tw, oracle):
+            cls = getattr(mod, py_name, None)
+            if cls is None:
+                continue
+            assert C.sizeof(cls) == nums[0], (c_name, mod.__name__)
+            assert [getattr(cls, f).offset for f, _ in cls._fields_] == nums[1:], (c_name, mod.__name__)
