@@ -171,3 +171,20 @@ def test_ctypes_mirrors_match_the_header_layout(tw, oracle, tmp_path):
                 continue
             assert C.sizeof(cls) == nums[0], (c_name, mod.__name__)
             assert [getattr(cls, f).offset for f, _ in cls._fields_] == nums[1:], (c_name, mod.__name__)
+
+
+def test_null_context_is_an_error_not_a_crash(tw):
+    """Status codes instead of assert()/exit(): every entry point checks its context first (include/tw3d.h: TW_ERR_ARG = -3)."""
+    import ctypes as C
+    L = tw.lib
+    g, hp = tw.Grid2D(0, 0, 1, 1, 4, 4), tw.HeightParams()
+    assert L.tw_heightgen_2d(None, C.byref(g), C.byref(hp), 1, 0, None, None) == tw.TW_ERR_ARG
+    assert L.tw_heightgen_2d_poll(None, 0) == tw.TW_ERR_ARG
+    assert L.tw_erode(None, None, 4, 4, 0.0, 10, None) == tw.TW_ERR_ARG
+    assert L.tw_erode_parallel(None, None, 4, 4, 0.0, 10, None, 0) == tw.TW_ERR_ARG
+    assert L.tw_eval_points(None, None, 0, None, None, None) == tw.TW_ERR_ARG
+    assert L.tw_tile_normals_batch(None, None, 0, 0, 0.0, 0.0, None, None) == tw.TW_ERR_ARG
+    assert L.tw_tile_ao_batch(None, None, None, 0, 0, 0, 0.0, 0.0, 0, None, 0.0, None) == tw.TW_ERR_ARG
+    assert L.tw_heightmap_sample_tiles(None, None, None, None, 0, 0, None) == tw.TW_ERR_ARG
+    assert L.tw_voxel_fill(None, None, None, None) == tw.TW_ERR_ARG
+    assert L.tw_sync(None) == tw.TW_ERR_ARG
