@@ -112,7 +112,8 @@ def reference_arm(args):
     if int(os.environ.get("RANK", "0")) != 0:
         return
     cores = os.cpu_count() or 1
-    nx, ny = 1024, 128                      # bounded sample: 131072 cells of the same grid (rows 0..127, cols 0..1023 of the 8192^2 tile)
+    nx, ny = 1024, 1024                     # bounded sample: 1 M cells of the same grid (rows/cols 0..1023 of the 8192^2 tile): 8 rows per thread on a
+                                            # 128-thread host, ~0.1 s per step there - long enough for the OpenMP team to reach a steady rate
     kind, run = cpu_runner(cores, nx, ny)
     for _ in range(args.warmup):
         run()
@@ -133,9 +134,9 @@ def reference_arm(args):
 def cpu_baseline_leg():
     """Bounded CPU sample of the same workload (rank 0, N=1): ~10-20 s of CPU work on all host cores."""
     cores = os.cpu_count() or 1
-    nx, ny = 1024, 256
+    nx, ny = 1024, 1024
     kind, run = cpu_runner(cores, nx, ny)
-    run(16)
+    run(128)
     t0 = time.perf_counter()
     run()
     dt = time.perf_counter() - t0
