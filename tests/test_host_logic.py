@@ -188,3 +188,57 @@ def test_null_context_is_an_error_not_a_crash(tw):
     assert L.tw_heightmap_sample_tiles(None, None, None, None, 0, 0, None) == tw.TW_ERR_ARG
     assert L.tw_voxel_fill(None, None, None, None) == tw.TW_ERR_ARG
     assert L.tw_sync(None) == tw.TW_ERR_ARG
+
+
+def test_table_driven_simplex_equals_glm_on_cpu(oracle):
+    """The shipped noise kernel evaluates glm::simplex(vec2) through a 580-entry table (csrc/tw_noise2.cuh, level 3): gradient entry indexed by
+    permute(iy') + ix', lazy mod289, first hash from the table. This numpy fp32 emulation of exactly that data flow must agree bit for bit with
+    the oracle's literal restatement (pinned against the reference's GLM) - a CPU check of the algorithm, independent of the device tests."""
+    f32 = np.float32
+    Cx, Cy, Cz, Cw = f32(0.211324865405187), f32(0.366025403784439), f32(-0.577350269189626), f32(0.024390243902439)
+
+    def permute(x):
+        v = (x * f32(34.0) + f32(1.0)) * x
+        return v - np.floor(v * (f32(1.0) / f32(289.0))) * f32(289.0)
+
+    k = np.arange(580, dtype=np.int64).astype(f32)
+    pk = permute(k)
+    t = pk * Cw
+    X = (t - np.floor(t)) * f32(2.0) - f32(1.0)
+    H = np.abs(X) - f32(0.5)
+    A0 = X - np.floor(X + f32(0.5))
+    Nn = f32(1.79284291400159) - f32(0.85373472095314) * (A0 * A0 + H * H)
+
+    rng = np.random.default_rng(2)
+    n = 400000
+    v = (rng.standard_normal((n, 2)) * rng.choice([0.5, 3.0, 50.0, 1000.0, 2.0e5], (n, 1))).astype(f32)
+    v[:2000] = (np.round(v[:2000] / 289.0) * 289.0).astype(f32)           # lattice points on multiples of 289: the lazy remainder returns 289
+    vx, vy = v[:, 0].copy(), v[:, 1].copy()
+    s = vx * Cy + vy * Cy
+    ix, iy = np.floor(vx + s), np.floor(vy + s)
+    tt = ix * Cx + iy * Cx
+    x0x, x0y = vx - ix + tt, vy - iy + tt
+    gt = x0x > x0y
+    i1x, i1y = gt.astype(f32), (~gt).astype(f32)
+    x12x, x12y, x12z, x12w = (x0x + Cx) - i1x, (x0y + Cx) - i1y, x0x + Cz, x0y + Cz
+    lazy = lambda a: a - np.floor(a * (f32(1.0) / f32(289.0))) * f32(289.0)   # noqa: E731
+    ixm, iym = lazy(ix), lazy(iy)
+    assert ixm.min() >= 0 and ixm.max() <= 289
+    j0 = iym.astype(np.int64)
+    q0, q1, q2 = pk[j0], pk[j0 + (~gt)], pk[j0 + 1]                        # first hash from the table (entries 289/290 repeat 0/1)
+    k0, k1, k2 = (q0 + ixm).astype(np.int64), (q1 + ixm + i1x).astype(np.int64), (q2 + ixm + f32(1.0)).astype(np.int64)
+    assert max(k0.max(), k1.max(), k2.max()) <= 578
+
+    def m4(a, b):
+        m = f32(0.5) - (a * a + b * b)
+        m = np.where(m < 0, f32(0.0), m).astype(f32)
+        m = m * m
+        return m * m
+    m0, m1, m2 = m4(x0x, x0y) * Nn[k0], m4(x12x, x12y) * Nn[k1], m4(x12z, x12w) * Nn[k2]
+    gx = A0[k0] * x0x + H[k0] * x0y
+    gy = A0[k1] * x12x + H[k1] * x12y
+    gz = A0[k2] * x12z + H[k2] * x12w
+    got = (((m0 * gx) + (m1 * gy)) + (m2 * gz)) * f32(130.0)
+    f = oracle.lib().to_simplex2
+    exp = np.array([f(float(a), float(b)) for a, b in zip(vx[:60000], vy[:60000])], f32)
+    assert np.array_equal(got[:60000].view(np.uint32), exp.view(np.uint32))
