@@ -392,8 +392,8 @@ int tw_create_zvals_batch(tw_ctx *ctx, const int32_t *origins_xy, uint32_t ntile
 	if (const char *e = getenv("TW_PIPE_CHUNKS")) {int const v = atoi(e); if (v >= 1 && v <= 64) want_chunks = (uint32_t)v;}
 	uint32_t chunk = (ntiles >= 4096) ? (ntiles + want_chunks - 1)/want_chunks : ntiles;
 	uint32_t const cap = twi_erode_chunk_for(budget, chunk, (int)zvsize, (int)zvsize);
-	chunk = cap;
-	uint32_t const nchunks = (ntiles + chunk - 1)/chunk;
+	uint32_t const nchunks = (ntiles + cap - 1)/cap;
+	chunk = (ntiles + nchunks - 1)/nchunks; // balanced: 65536 tiles with a 65535-tile cap become 2 x 32768, not 65535 + 1 (every chunk pays a droplet tail)
 	int const nes = (nchunks > 1) ? 2 : 1; // erosion streams / scratch buffers
 	size_t const sbytes = twi_erode_scratch_bytes(chunk, (int)zvsize, (int)zvsize);
 	rc = tw_reserve(ctx, 1, sbytes*nes); if (rc) return rc;
