@@ -110,7 +110,10 @@ typedef struct tw_voxel_params {
 	float atten_val, atten_inner_radius;
 } tw_voxel_params;
 
-/* ---- context ---- */
+/* ---- context ----
+ * No reference counterpart: the reference keeps this state in process globals (sin_table src/sinf.h:11, sinTable src/mesh_gen.cpp:38,
+ * the GL compute shader of mesh_xy_grid_cache_t src/mesh.h:33). One context = one device, one CUDA stream, its scratch buffers and the
+ * uploaded tables; not re-entrant (use one per thread). tw_create fails with TW_ERR_NO_DEVICE when there is no GPU - there is no CPU fallback. */
 TW_API int  tw_abi_version(void);
 TW_API int  tw_create(int device, tw_ctx **out);
 TW_API void tw_destroy(tw_ctx *ctx);
