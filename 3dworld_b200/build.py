@@ -47,7 +47,7 @@ def build(force=False, verbose=False):
             print(out)
         if p.returncode != 0:
             raise RuntimeError("nvcc failed for %s:\n%s" % (src, out))
-    cmd = [nvcc(), "-shared", "-o", LIB] + objs + ["-Xlinker", "--no-undefined", "-lcudart_static", "-lpthread", "-ldl", "-lrt"]
+    cmd = [nvcc(), "-shared", "-Wno-deprecated-gpu-targets", "-o", LIB] + objs + ["-Xlinker", "--no-undefined", "-lcudart_static", "-lpthread", "-ldl", "-lrt"]
     subprocess.check_call(cmd)
     return LIB
 
