@@ -242,3 +242,66 @@ def test_table_driven_simplex_equals_glm_on_cpu(oracle):
     f = oracle.lib().to_simplex2
     exp = np.array([f(float(a), float(b)) for a, b in zip(vx[:60000], vy[:60000])], f32)
     assert np.array_equal(got[:60000].view(np.uint32), exp.view(np.uint32))
+
+
+def test_table_driven_simplex3_equals_glm_on_cpu(oracle):
+    """Same check for the voxel kernels' glm::simplex(vec3) (csrc/tw_noise2.cuh simplex3_lut): lattice indices from glm's multiply-form mod289
+    (which yields exactly 289 for multiples of 289), first permute from the table, second computed, third folded into the gradient entry."""
+    f32 = np.float32
+    c289 = f32(1.0) / f32(289.0)
+    mod289 = lambda x: x - np.floor(x * c289) * f32(289.0)                     # noqa: E731
+    permute = lambda x: mod289((x * f32(34.0) + f32(1.0)) * x)                 # noqa: E731
+    k = np.arange(580, dtype=np.int64).astype(f32)
+    pk = permute(k)
+    n_ = f32(0.142857142857)
+    nsx, nsy, nsz = n_ * f32(2.0) - f32(0.0), n_ * f32(0.5) - f32(1.0), n_ * f32(1.0) - f32(0.0)
+    j = pk - f32(49.0) * np.floor(pk * nsz * nsz)
+    x_ = np.floor(j * nsz)
+    y_ = np.floor(j - f32(7.0) * x_)
+    X, Y = x_ * nsx + nsy, y_ * nsx + nsy
+    H = f32(1.0) - np.abs(X) - np.abs(Y)
+    sh = -(~(f32(0.0) < H)).astype(f32)                                        # -step(h, 0): glm::step(edge = h, x = 0) = (0 < h) ? 0 : 1
+    Px, Py, Pz = X + (np.floor(X) * f32(2.0) + f32(1.0)) * sh, Y + (np.floor(Y) * f32(2.0) + f32(1.0)) * sh, H
+    nn = f32(1.79284291400159) - f32(0.85373472095314) * (Px * Px + Py * Py + Pz * Pz)
+    Px, Py, Pz = Px * nn, Py * nn, Pz * nn
+
+    rng = np.random.default_rng(4)
+    n = 30000
+    v = (rng.standard_normal((n, 3)) * rng.choice([0.5, 3.0, 50.0, 1000.0, 5.0e4], (n, 1))).astype(f32)
+    v[:1500] = (np.round(v[:1500] / 289.0) * 289.0 + rng.uniform(0, 1, (1500, 3))).astype(f32)   # lattice indices on multiples of 289
+    vx, vy, vz = v[:, 0].copy(), v[:, 1].copy(), v[:, 2].copy()
+    Cx, Cy = f32(1.0 / 6.0), f32(1.0 / 3.0)
+    s = vx * Cy + vy * Cy + vz * Cy
+    i0, i1, i2 = np.floor(vx + s), np.floor(vy + s), np.floor(vz + s)
+    t = i0 * Cx + i1 * Cx + i2 * Cx
+    x0x, x0y, x0z = vx - i0 + t, vy - i1 + t, vz - i2 + t
+    step = lambda edge, x: (~(x < edge)).astype(f32)                           # noqa: E731  glm::step
+    gx, gy, gz = step(x0y, x0x), step(x0z, x0y), step(x0x, x0z)
+    lx, ly, lz = f32(1.0) - gx, f32(1.0) - gy, f32(1.0) - gz
+    i1x, i1y, i1z = np.minimum(gx, lz), np.minimum(gy, lx), np.minimum(gz, ly)
+    i2x, i2y, i2z = np.maximum(gx, lz), np.maximum(gy, lx), np.maximum(gz, ly)
+    x1 = (x0x - i1x + Cx, x0y - i1y + Cx, x0z - i1z + Cx)
+    x2 = (x0x - i2x + Cy, x0y - i2y + Cy, x0z - i2z + Cy)
+    x3 = (x0x - f32(0.5), x0y - f32(0.5), x0z - f32(0.5))
+    i0, i1, i2 = mod289(i0), mod289(i1), mod289(i2)
+    assert min(i0.min(), i1.min(), i2.min()) >= 0 and max(i0.max(), i1.max(), i2.max()) <= 289 and (i2 == 289).any()
+    tab = lambda a: pk[a.astype(np.int64)]                                     # noqa: E731  first permute from the table (index <= 290)
+    q0, q1, q2, q3 = tab(i2), tab(i2 + i1z), tab(i2 + i2z), tab(i2 + f32(1.0))
+    k0 = permute(q0 + i1) + i0
+    k1 = permute(q1 + i1 + i1y) + i0 + i1x
+    k2 = permute(q2 + i1 + i2y) + i0 + i2x
+    k3 = permute(q3 + i1 + f32(1.0)) + i0 + f32(1.0)
+    ks = [a.astype(np.int64) for a in (k0, k1, k2, k3)]
+    assert max(a.max() for a in ks) <= 578
+
+    def corner(kk, xx):
+        m = f32(0.6) - (xx[0] * xx[0] + xx[1] * xx[1] + xx[2] * xx[2])
+        m = np.where(m < 0, f32(0.0), m).astype(f32)
+        m = m * m
+        d = Px[kk] * xx[0] + Py[kk] * xx[1] + Pz[kk] * xx[2]
+        return (m * m) * d
+    c0, c1, c2, c3 = corner(ks[0], (x0x, x0y, x0z)), corner(ks[1], x1), corner(ks[2], x2), corner(ks[3], x3)
+    got = f32(42.0) * ((c0 + c1) + (c2 + c3))
+    f = oracle.lib().to_simplex3
+    exp = np.array([f(float(a), float(b), float(c)) for a, b, c in zip(vx, vy, vz)], f32)
+    assert np.array_equal(got.view(np.uint32), exp.view(np.uint32))
