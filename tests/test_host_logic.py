@@ -305,3 +305,44 @@ def test_table_driven_simplex3_equals_glm_on_cpu(oracle):
     f = oracle.lib().to_simplex3
     exp = np.array([f(float(a), float(b), float(c)) for a, b, c in zip(vx, vy, vz)], f32)
     assert np.array_equal(got.view(np.uint32), exp.view(np.uint32))
+
+
+def test_table_driven_perlin2_equals_glm_on_cpu(oracle):
+    """And for glm::perlin(vec2) (perlin2_lut): lazy mod289 of the four lattice indices, first permute from the table, gradient entry
+    {gx*n, gy*n} indexed by permute(ix') + iy' (second permute folded in)."""
+    f32 = np.float32
+    c289 = f32(1.0) / f32(289.0)
+    lazy = lambda a: a - np.floor(a * c289) * f32(289.0)                       # noqa: E731
+    permute = lambda x: lazy((x * f32(34.0) + f32(1.0)) * x)                   # noqa: E731
+    k = np.arange(580, dtype=np.int64).astype(f32)
+    pk = permute(k)
+    q = pk / f32(41.0)                                                         # the device's division-free form equals the IEEE quotient (test_division_free_forms)
+    g = (q - np.floor(q)) * f32(2.0) - f32(1.0)
+    GY = np.abs(g) - f32(0.5)
+    GX = g - np.floor(g + f32(0.5))
+    nn = f32(1.79284291400159) - f32(0.85373472095314) * (GX * GX + GY * GY)
+    GX, GY = GX * nn, GY * nn
+    rng = np.random.default_rng(6)
+    n = 40000
+    P = (rng.standard_normal((n, 2)) * rng.choice([0.5, 3.0, 50.0, 1000.0, 2.0e5], (n, 1))).astype(f32)
+    P[:2000] = (np.round(P[:2000] / 289.0) * 289.0 + rng.uniform(-1, 1, (2000, 2))).astype(f32)
+    Px, Py = P[:, 0].copy(), P[:, 1].copy()
+    flx, fly = np.floor(Px), np.floor(Py)
+    frx, fry = Px - flx, Py - fly
+    Pfz, Pfw = frx - f32(1.0), fry - f32(1.0)
+    Pix, Piy, Piz, Piw = lazy(flx), lazy(fly), lazy(flx + f32(1.0)), lazy(fly + f32(1.0))
+    assert max(Pix.max(), Piz.max(), Piy.max(), Piw.max()) <= 289 and (Piz == 289).any()
+    qx, qz = pk[Pix.astype(np.int64)], pk[Piz.astype(np.int64)]
+    k00, k10, k01, k11 = [(a + b).astype(np.int64) for a, b in ((qx, Piy), (qz, Piy), (qx, Piw), (qz, Piw))]
+    assert max(k00.max(), k10.max(), k01.max(), k11.max()) <= 577
+    n00 = GX[k00] * frx + GY[k00] * fry
+    n10 = GX[k10] * Pfz + GY[k10] * fry
+    n01 = GX[k01] * frx + GY[k01] * Pfw
+    n11 = GX[k11] * Pfz + GY[k11] * Pfw
+    fade = lambda t: (t * t * t) * (t * (t * f32(6.0) - f32(15.0)) + f32(10.0))   # noqa: E731
+    mix = lambda x, y, a: x + a * (y - x)                                      # noqa: E731
+    fdx, fdy = fade(frx), fade(fry)
+    got = mix(mix(n00, n10, fdx), mix(n01, n11, fdx), fdy) * f32(2.3)
+    f = oracle.lib().to_perlin2
+    exp = np.array([f(float(a), float(b)) for a, b in zip(Px, Py)], f32)
+    assert np.array_equal(got.view(np.uint32), exp.view(np.uint32))
