@@ -124,6 +124,11 @@ void tw_destroy(tw_ctx *ctx) {
 	if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
 	if (ctx->async.done) cudaEventDestroy(ctx->async.done);
 	for (int i = 0; i < 2; ++i) {if (ctx->aux_stream[i]) cudaStreamDestroy(ctx->aux_stream[i]);}
+	for (int i = 0; i < 3; ++i) {
+		if (ctx->heavy_stream[i]) cudaStreamDestroy(ctx->heavy_stream[i]);
+		if (ctx->ev_fork[i]) cudaEventDestroy(ctx->ev_fork[i]);
+		if (ctx->ev_join[i]) cudaEventDestroy(ctx->ev_join[i]);
+	}
 	cudaStreamDestroy(ctx->stream);
 	delete ctx;
 }
@@ -422,7 +427,7 @@ int tw_create_zvals_batch(tw_ctx *ctx, const int32_t *origins_xy, uint32_t ntile
 		if (cudaEventCreateWithFlags(&ev[k], cudaEventDisableTiming) != cudaSuccess || cudaEventRecord(ev[k], ctx->stream) != cudaSuccess) {status = tw_set_error(ctx, TW_ERR_CUDA, "event"); break;}
 		cudaStream_t const es = ctx->aux_stream[k % nes];
 		if (cudaStreamWaitEvent(es, ev[k], 0) != cudaSuccess) {status = tw_set_error(ctx, TW_ERR_CUDA, "cudaStreamWaitEvent"); break;}
-		status = twi_erode_enqueue(ctx, es, (char *)ctx->d_scratch[1] + (size_t)(k % nes)*sbytes, chunk, maps, nt, (int)zvsize, (int)zvsize, nullptr, min_zval, erosion_iters, ep, d_steps);
+		status = twi_erode_enqueue(ctx, es, 1 + (int)(k % nes), (char *)ctx->d_scratch[1] + (size_t)(k % nes)*sbytes, chunk, maps, nt, (int)zvsize, (int)zvsize, nullptr, min_zval, erosion_iters, ep, d_steps);
 		if (status) break;
 		if (mm) {status = twi_minmax_tiles(ctx, es, maps, tile_elems, nt, d_mm + 2*(size_t)t0); if (status) break;}
 		if (!dev_out && cudaMemcpyAsync(out + (size_t)t0*tile_elems, maps, (size_t)nt*tile_elems*sizeof(float), cudaMemcpyDeviceToHost, es) != cudaSuccess) {status = tw_set_error(ctx, TW_ERR_CUDA, "D2H");}
@@ -489,6 +494,18 @@ int tw_tile_normals_batch(tw_ctx *ctx, const float *zvals, uint32_t ntiles, uint
 	return TW_OK;
 }
 
+// context grids of `nt` tiles at (x1 - AO_RAY_LEN, y1 - AO_RAY_LEN) into d_cz; skip_inside: leave the zvsize^2 interior unwritten (never read)
+static int gen_ao_contexts(tw_ctx *ctx, const int32_t *origins_xy, uint32_t nt, int mesh_x_size, int mesh_y_size, float dx, float dy, uint32_t zvsize,
+                           const tw_height_params *p, bool skip_inside, std::vector<int32_t> &org, float *d_cz)
+{
+	uint32_t const ray = 36, csz = zvsize - 1 + 2*ray; // AO_RAY_LEN, context_sz (src/tiled_mesh.cpp:43,601)
+	for (uint32_t t = 0; t < nt; ++t) {org[2*t] = origins_xy[2*t] - (int32_t)ray; org[2*t + 1] = origins_xy[2*t + 1] - (int32_t)ray;}
+	if (skip_inside) {ctx->skip_rect[0] = ctx->skip_rect[1] = ray; ctx->skip_rect[2] = ctx->skip_rect[3] = zvsize;}
+	int const rc = tw_heightgen_tiles(ctx, org.data(), nt, mesh_x_size, mesh_y_size, dx, dy, csz, p, d_cz, nullptr); // device output: scratch slot 0 is not touched
+	ctx->skip_rect[0] = ctx->skip_rect[1] = ctx->skip_rect[2] = ctx->skip_rect[3] = 0;
+	return rc;
+}
+
 int tw_tile_ao_batch(tw_ctx *ctx, const float *zvals, const int32_t *origins_xy, uint32_t ntiles, int mesh_x_size, int mesh_y_size,
                      float dx, float dy, uint32_t zvsize, const tw_height_params *p, float half_dxy, uint8_t *ao)
 {
@@ -498,6 +515,7 @@ int tw_tile_ao_batch(tw_ctx *ctx, const float *zvals, const int32_t *origins_xy,
 	uint32_t const ray = 36, stride = zvsize - 1, csz = stride + 2*ray; // AO_RAY_LEN, context_sz (src/tiled_mesh.cpp:43,601)
 	size_t const tile_elems = (size_t)zvsize*zvsize, ctx_elems = (size_t)csz*csz, ao_elems = (size_t)stride*stride;
 	bool const dev_in = tw_is_device_ptr(zvals), dev_out = tw_is_device_ptr(ao);
+	bool const ctx_inside = (p->gen_mode >= TW_MGEN_SIMPLEX_GPU); // use_ao_zvals: the rays test the un-eroded context inside the tile too (src/tiled_mesh.cpp:604)
 	// chunk of tiles whose context grids fit in ~2 GB
 	uint32_t chunk = (uint32_t)std::min<size_t>(ntiles, std::max<size_t>(1, ((size_t)2 << 30)/(ctx_elems*sizeof(float))));
 	if (chunk > 65535) chunk = 65535;
@@ -512,13 +530,64 @@ int tw_tile_ao_batch(tw_ctx *ctx, const float *zvals, const int32_t *origins_xy,
 		const float *d_z = zvals + (size_t)t0*tile_elems;
 		if (!dev_in) {TW_CUDA(ctx, cudaMemcpyAsync(sp, d_z, (size_t)nt*tile_elems*sizeof(float), cudaMemcpyHostToDevice, ctx->stream)); d_z = (const float *)sp; sp += in_bytes;}
 		unsigned char *d_ao = dev_out ? ao + (size_t)t0*ao_elems : (unsigned char *)sp;
-		for (uint32_t t = 0; t < nt; ++t) {org[2*t] = origins_xy[2*(t0 + t)] - (int32_t)ray; org[2*t + 1] = origins_xy[2*(t0 + t) + 1] - (int32_t)ray;}
-		rc = tw_heightgen_tiles(ctx, org.data(), nt, mesh_x_size, mesh_y_size, dx, dy, csz, p, d_cz, nullptr); // device output: scratch slot 0 is not touched
+		rc = gen_ao_contexts(ctx, origins_xy + 2*(size_t)t0, nt, mesh_x_size, mesh_y_size, dx, dy, zvsize, p, !ctx_inside, org, d_cz);
 		if (rc) return rc;
-		rc = twi_tile_ao(ctx, d_z, d_cz, nt, zvsize, half_dxy, d_ao); if (rc) return rc;
+		rc = twi_tile_ao(ctx, d_z, d_cz, nt, zvsize, half_dxy, ctx_inside, d_ao); if (rc) return rc;
 		if (!dev_out) {TW_CUDA(ctx, cudaMemcpyAsync(ao + (size_t)t0*ao_elems, d_ao, (size_t)nt*ao_elems, cudaMemcpyDeviceToHost, ctx->stream));}
 		TW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
 	}
+	return TW_OK;
+}
+
+int tw_create_zvals_ao_batch(tw_ctx *ctx, const int32_t *origins_xy, uint32_t ntiles, int mesh_x_size, int mesh_y_size, float dx, float dy,
+                             uint32_t zvsize, const tw_height_params *p, uint32_t erosion_iters, const tw_erosion_params *ep, float min_zval,
+                             float half_dxy, float *zvals, uint8_t *ao, tw_minmax *mm)
+{
+	int rc = check_ctx(ctx); if (rc) return rc;
+	rc = finish_pending(ctx); if (rc) return rc;
+	if (!origins_xy || !p || !zvals || !ao || ntiles == 0 || zvsize < 2) return tw_set_error(ctx, TW_ERR_ARG, "null/empty argument");
+	uint32_t const ray = 36, stride = zvsize - 1, csz = stride + 2*ray;
+	size_t const tile_elems = (size_t)zvsize*zvsize, ctx_elems = (size_t)csz*csz, ao_elems = (size_t)stride*stride;
+	bool const dev_z = tw_is_device_ptr(zvals), dev_ao = tw_is_device_ptr(ao);
+	bool const ctx_mode = (p->gen_mode >= TW_MGEN_SIMPLEX_GPU); // one generation, zvals cut from the context (src/tiled_mesh.cpp:479-487,505)
+	bool const erode = (erosion_iters > 0 && ep && ep->erode_amount > 0.0);
+	uint32_t chunk = (uint32_t)std::min<size_t>(ntiles, std::max<size_t>(1, ((size_t)2 << 30)/(ctx_elems*sizeof(float))));
+	if (chunk > 65535) chunk = 65535;
+	size_t const z_bytes = ((size_t)chunk*tile_elems*sizeof(float) + 255) & ~(size_t)255, cz_bytes = ((size_t)chunk*ctx_elems*sizeof(float) + 255) & ~(size_t)255;
+	size_t const ao_bytes = ((size_t)chunk*ao_elems + 255) & ~(size_t)255, mm_bytes = ((size_t)chunk*2*sizeof(unsigned) + 255) & ~(size_t)255;
+	rc = tw_reserve(ctx, 0, cz_bytes + mm_bytes + (dev_z ? 0 : z_bytes) + (dev_ao ? 0 : ao_bytes) + 256); if (rc) return rc;
+	std::vector<int32_t> org(2*(size_t)chunk);
+	uint64_t moves = 0;
+	for (uint32_t t0 = 0; t0 < ntiles; t0 += chunk) {
+		uint32_t const nt = (ntiles - t0 < chunk) ? ntiles - t0 : chunk;
+		const int32_t *orgs = origins_xy + 2*(size_t)t0;
+		char *sp = (char *)ctx->d_scratch[0];
+		float *d_cz = (float *)sp; sp += cz_bytes;
+		unsigned *d_mm = (unsigned *)sp; sp += mm_bytes;
+		float *d_z = dev_z ? zvals + (size_t)t0*tile_elems : (float *)sp;
+		if (!dev_z) {sp += z_bytes;}
+		unsigned char *d_ao = dev_ao ? ao + (size_t)t0*ao_elems : (unsigned char *)sp;
+		if (ctx_mode) {
+			rc = gen_ao_contexts(ctx, orgs, nt, mesh_x_size, mesh_y_size, dx, dy, zvsize, p, false, org, d_cz); if (rc) return rc;
+			rc = twi_tile_cut(ctx, d_cz, nt, zvsize, d_z); if (rc) return rc;
+		}
+		else {rc = tw_heightgen_tiles(ctx, orgs, nt, mesh_x_size, mesh_y_size, dx, dy, zvsize, p, d_z, nullptr); if (rc) return rc;}
+		if (erode) {
+			rc = tw_erode_tiles(ctx, d_z, nt, (int)zvsize, (int)zvsize, nullptr, min_zval, erosion_iters, ep); if (rc) return rc; // tile_t::create_zvals: apply_erosion(zvals, ..., zmin, ...)
+			moves += ctx->last_erosion_steps;
+		}
+		if (!ctx_mode) {rc = gen_ao_contexts(ctx, orgs, nt, mesh_x_size, mesh_y_size, dx, dy, zvsize, p, true, org, d_cz); if (rc) return rc;}
+		rc = twi_tile_ao(ctx, d_z, d_cz, nt, zvsize, half_dxy, ctx_mode, d_ao); if (rc) return rc;
+		if (mm) {
+			rc = twi_init_minmax(ctx, d_mm, nt); if (rc) return rc;
+			rc = twi_minmax_tiles(ctx, ctx->stream, d_z, tile_elems, nt, d_mm); if (rc) return rc;
+		}
+		if (!dev_z)  {TW_CUDA(ctx, cudaMemcpyAsync(zvals + (size_t)t0*tile_elems, d_z, (size_t)nt*tile_elems*sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));}
+		if (!dev_ao) {TW_CUDA(ctx, cudaMemcpyAsync(ao + (size_t)t0*ao_elems, d_ao, (size_t)nt*ao_elems, cudaMemcpyDeviceToHost, ctx->stream));}
+		if (mm) {rc = read_minmax(ctx, d_mm, mm + t0, nt); if (rc) return rc;}
+		TW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	}
+	ctx->last_erosion_steps = moves;
 	return TW_OK;
 }
 

@@ -14,6 +14,8 @@
 #include "tw_internal.h"
 #include <float.h>
 #include <stdlib.h>
+#include <string.h>
+#include <algorithm>
 
 namespace {
 
@@ -97,36 +99,111 @@ struct Rng {
 // different times stay converged at the top of the loop. G trades redundant ALU work (G = 32: every lane repeats the ~250-instruction
 // step for ONE map) against memory coalescing and in-flight parallelism (G = 1: no redundancy, but 32 unrelated maps per load
 // instruction and 32x more maps needed to fill the machine); twi_erode picks G from the number of heightmaps.
-// SHARED (tw_erode_parallel): the reference's multi-threaded mode, `#pragma omp parallel for schedule(dynamic,1)` over the droplets of ONE
-// heightmap (src/erosion.cpp:66): `ntiles` groups play the OpenMP threads, each takes the next droplet index from an atomic counter (the
-// dynamic,1 schedule), reads bypass L1 (the CPU's caches are coherent) and the read-modify-writes are float atomics (the reference's are
-// unsynchronised). One group => exactly the serial order.
-template<int G, bool SHARED = false>
+//
+// Where the heights live (MODE):
+//   M_GLOBAL  padded copy in global memory, served by L1/L2: the THROUGHPUT mode - thousands of maps in flight hide the two dependent L2
+//             round trips of a move; a single map runs at ~0.75 us per move.
+//   M_ATOMIC  (tw_erode_parallel) the reference's multi-threaded mode, `#pragma omp parallel for schedule(dynamic,1)` over the droplets of ONE
+//             heightmap (src/erosion.cpp:66): `ntiles` groups play the OpenMP threads, each takes the next droplet index from an atomic counter
+//             (the dynamic,1 schedule), reads bypass L1 (the CPU's caches are coherent) and the read-modify-writes are float atomics (the
+//             reference's are unsynchronised). One group => exactly the serial order.
+//   M_WINDOW  LATENCY mode for maps that do not fit on chip (258^2 tiles, the 8192^2 map): each lane group keeps a WX x WY window of the padded
+//             map around its droplet in SHARED MEMORY. Reads hit the window (29-cycle LDS instead of a ~250-cycle L2 round trip), writes go
+//             through to the window AND to global memory, so the global copy is always current: the window is a pure read cache, any access
+//             outside it simply falls back to global memory, and re-centring is a plain re-load (ld.global.cg) ahead of the droplet's heading.
+//   M_WHOLE   LATENCY mode for maps that fit on chip (130^2 tiles = 76 KB padded; the reference's default mesh_size 128): the whole padded map
+//             is built in shared memory straight from the caller's un-padded tile (the PAD = 4 clamped border, src/erosion.cpp:31-37, is
+//             replicated in shared memory), all droplets walk it there, and the interior is written back once with the min_zval clamp
+//             (:158-162). No padded scratch copy, no pad/unpad kernels: DRAM traffic = read the tile once + write it once.
+enum {M_GLOBAL = 0, M_ATOMIC = 1, M_WINDOW = 2, M_WHOLE = 3};
+
+struct DArgs {
+	float *padded;              // M_GLOBAL / M_ATOMIC / M_WINDOW: padded heightmaps [tile][NY][NX] (M_ATOMIC: the one map)
+	float *maps;                // M_WHOLE: the caller's un-padded heightmaps [tile][ysize][xsize], read once and written once
+	const float *min_zvals;     // M_WHOLE: per-map lower clamp of the write-back (nullptr => min_zval_all)
+	float min_zval_all;
+	unsigned ntiles;            // M_ATOMIC: number of lane groups; otherwise unused
+	unsigned slot0, nslots;     // this launch walks the schedule slots [slot0, slot0 + nslots)
+	int xsize, ysize;
+	unsigned num_iters;
+	EParams E;
+	const float2 *dir_table;
+	unsigned long long *steps_out;
+	const unsigned *order;      // heaviest-first schedule (slot -> map) or nullptr
+	unsigned *next_droplet;     // M_ATOMIC: the dynamic,1 droplet counter
+	int WX, WY, P;              // M_WINDOW / M_WHOLE: window extent and row pitch in floats (M_WHOLE: WX = NX, WY = NY)
+	unsigned win_elems;         // floats of shared memory per lane group
+	unsigned win_min_moves;     // M_WINDOW: a droplet gets a window once it has survived this many moves (ocean droplets die in one)
+};
+
+template<int G, int MODE>
 __global__ void __launch_bounds__(128)
-droplet_kernel(float *__restrict__ padded, unsigned ntiles, int xsize, int ysize, unsigned num_iters, EParams E,
-	const float2 *__restrict__ dir_table, unsigned long long *__restrict__ steps_out, const unsigned *__restrict__ order, unsigned *__restrict__ next_droplet = nullptr)
+droplet_kernel(DArgs const A)
 {
+	constexpr bool SHARED = (MODE == M_ATOMIC), WIN = (MODE == M_WINDOW), WHOLE = (MODE == M_WHOLE);
 	constexpr int TPW = 32/G; // heightmaps per warp
+	extern __shared__ __align__(16) float tw_smem[];
 	int const lane = threadIdx.x & 31, sub = lane % G, grp = lane / G;
-	unsigned const warp = (blockIdx.x*blockDim.x + threadIdx.x) >> 5;
-	unsigned const slot = warp*TPW + grp;                                       // position in the heaviest-first schedule
-	unsigned const tile = (slot < ntiles) ? (order ? __ldg(order + slot) : slot) : ntiles;
+	unsigned const wib = threadIdx.x >> 5;
+	unsigned const gslot = (blockIdx.x*(blockDim.x >> 5) + wib)*TPW + grp;       // position in this launch's part of the heaviest-first schedule
+	bool active = (gslot < A.nslots);
+	unsigned const tile = active ? (A.order ? __ldg(A.order + A.slot0 + gslot) : (A.slot0 + gslot)) : 0u;
 	unsigned const gmask = (G == 32) ? 0xffffffffu : (((1u << (G & 31)) - 1u) << (grp*G));
+	int const xsize = A.xsize, ysize = A.ysize;
 	int const NX = xsize + 2*PAD, NY = ysize + 2*PAD;
-	float *mh = padded + (SHARED ? (size_t)0 : (size_t)((tile < ntiles) ? tile : 0)*NX*NY);
+	float *mh = (MODE == M_WHOLE) ? nullptr : A.padded + (SHARED ? (size_t)0 : (size_t)tile*NX*NY);
 	float const Kq=10, Kw=0.001f, Kr=0.9f, Kd=0.02f, Ki=0.1f, minSlope=0.05f, g=20, Kg=g*2;
 	unsigned const MAX_PATH_LEN = 4u*(unsigned)NX*(unsigned)NY;
-	float const erode_amount = E.erode_amount;
+	float const erode_amount = A.E.erode_amount;
+	EParams const E = A.E;
+	unsigned const num_iters = A.num_iters;
 	unsigned long long steps = 0;
-	bool active = (tile < ntiles), in_droplet = false;
+	bool const have_tile = active;
+	bool in_droplet = false;
 	unsigned iter = 0, numMoves = 0;
 	Rng rgen; rgen.s1 = rgen.s2 = 1;
 	int xi = 0, zi = 0;
 	float xp=0, zp=0, xf=0, zf=0, s=0, v=0, w=1, dx=0, dz=0, h=0, h00=0, h10=0, h01=0, h11=0;
+	// shared-memory window of this lane group
+	int const WX = A.WX, WY = A.WY, P = A.P;
+	float *win = (WIN || WHOLE) ? tw_smem + (size_t)(wib*TPW + grp)*A.win_elems : nullptr;
+	int wx0 = 0, wz0 = 0;           // padded coordinates of the window's first cell
+	bool have_win = WHOLE;
 
-#define HMAP(x, y) mh[(size_t)NX*clampi((y), NY-1) + clampi((x), NX-1)]
-#define HLOAD(ptr)       (SHARED ? __ldcg(ptr) : *(ptr))
-#define HADD(ptr, delta) {if (SHARED) {atomicAdd((ptr), (delta));} else {*(ptr) += (delta);}}
+	if (WHOLE) { // build the padded map in shared memory from the caller's tile (src/erosion.cpp:31-37)
+		if (active) {
+			const float *src = A.maps + (size_t)tile*xsize*ysize;
+#pragma unroll 4
+			for (int y = 0; y < NY; ++y) {
+				const float *row = src + (size_t)clampi(y - PAD, ysize - 1)*xsize;
+				float *dst = win + y*P;
+				for (int x = sub; x < NX; x += G) {dst[x] = __ldcs(row + clampi(x - PAD, xsize - 1));}
+			}
+		}
+		__syncwarp(gmask);
+	}
+
+	// HREAD(x, y): HMAP(x, y) of the reference = clamped read
+	auto hread = [&](int x, int z) -> float {
+		int const cx = clampi(x, NX-1), cz = clampi(z, NY-1);
+		if (WHOLE) {return win[cz*P + cx];}
+		if (WIN && have_win) {
+			unsigned const rx = (unsigned)(cx - wx0), rz = (unsigned)(cz - wz0);
+			if (rx < (unsigned)WX && rz < (unsigned)WY) {return win[rz*P + rx];}
+		}
+		float const *p = mh + ((size_t)NX*cz + cx);
+		return SHARED ? __ldcg(p) : *p;
+	};
+	// hadd(x, z, delta): read-modify-write of the in-array cell (x, z); window modes write through to global memory
+	auto hadd = [&](int x, int z, float delta) {
+		if (WHOLE) {win[z*P + x] += delta; return;}
+		float *p = mh + ((size_t)NX*z + x);
+		if (WIN && have_win) {
+			unsigned const rx = (unsigned)(x - wx0), rz = (unsigned)(z - wz0);
+			if (rx < (unsigned)WX && rz < (unsigned)WY) {float *q = win + (rz*P + rx); float const nv = *q + delta; *q = nv; *p = nv; return;}
+		}
+		if (SHARED) {atomicAdd(p, delta);} else {*p += delta;}
+	};
 	// DEPOSIT(H): src/erosion.cpp:42-54; corner c of the 2x2 cell goes to lane c % G (inside cells are distinct => no aliasing between lanes)
 #define DEPOSIT(H) { \
 	_Pragma("unroll") \
@@ -134,7 +211,7 @@ droplet_kernel(float *__restrict__ padded, unsigned ntiles, int xsize, int ysize
 		int const X = xi + (c & 1), Z = zi + (c >> 1); \
 		float const W = ((c & 1) ? xf : (1-xf))*((c >> 1) ? zf : (1-zf)); \
 		float const delta = ds*erode_amount*W; \
-		if ((unsigned)X < (unsigned)NX && (unsigned)Z < (unsigned)NY) {HADD(&mh[NX*Z + X], delta)} \
+		if ((unsigned)X < (unsigned)NX && (unsigned)Z < (unsigned)NY) {hadd(X, Z, delta);} \
 	} \
 	if (G > 1) {__syncwarp(gmask);} \
 	(H) += ds; }
@@ -143,7 +220,7 @@ droplet_kernel(float *__restrict__ padded, unsigned ntiles, int xsize, int ysize
 		if (active && !in_droplet) { // next droplet of this group's heightmap (src/erosion.cpp:67-73)
 			if (SHARED) { // schedule(dynamic,1): the group's leader draws the next droplet
 				unsigned nd = 0;
-				if (sub == 0) {nd = atomicAdd(next_droplet, 1u);}
+				if (sub == 0) {nd = atomicAdd(A.next_droplet, 1u);}
 				iter = __shfl_sync(gmask, nd, grp*G);
 			}
 			if (iter >= num_iters) {active = false;}
@@ -152,7 +229,7 @@ droplet_kernel(float *__restrict__ padded, unsigned ntiles, int xsize, int ysize
 				xi = PAD + (rgen.rand()%xsize);
 				zi = PAD + (rgen.rand()%ysize);
 				xp=xi; zp=zi; xf=0; zf=0; s=0; v=0; w=1; dx=0; dz=0;
-				h=HLOAD(&HMAP(xi, zi)); h00=h; h10=HLOAD(&HMAP(xi+1, zi)); h01=HLOAD(&HMAP(xi, zi+1)); h11=HLOAD(&HMAP(xi+1, zi+1));
+				h=hread(xi, zi); h00=h; h10=hread(xi+1, zi); h01=hread(xi, zi+1); h11=hread(xi+1, zi+1);
 				numMoves = 0; in_droplet = true; ++iter;
 			}
 		}
@@ -160,13 +237,30 @@ droplet_kernel(float *__restrict__ padded, unsigned ntiles, int xsize, int ysize
 		if (!active) continue;
 		if (numMoves >= MAX_PATH_LEN) {in_droplet = false; continue;} // "droplet path is too long" (src/erosion.cpp:153)
 		++numMoves; ++steps;
+		if (WIN) { // keep the cells one move can touch - brush [xi-1, xi+2], next corners within +-2 of xi - inside the window
+			int const cx = clampi(xi, NX-1), cz = clampi(zi, NY-1);
+			bool const covered = have_win && max(cx - 2, 0) >= wx0 && min(cx + 3, NX-1) < wx0 + WX && max(cz - 2, 0) >= wz0 && min(cz + 3, NY-1) < wz0 + WY;
+			if (!covered && numMoves > A.win_min_moves) { // re-centre ahead of the droplet's heading (dx, dz = unit direction of the last move) and re-load
+				wx0 = max(0, min(cx - WX/2 + __float2int_rn(dx*(float)(WX/2 - 5)), NX - WX));
+				wz0 = max(0, min(cz - WY/2 + __float2int_rn(dz*(float)(WY/2 - 5)), NY - WY));
+				__syncwarp(gmask); // the group's earlier write-throughs are ordered before the loads below
+#pragma unroll 4
+				for (int r = 0; r < WY; ++r) {
+					const float *src = mh + ((size_t)NX*(wz0 + r) + wx0);
+					float *dst = win + r*P;
+					for (int c = sub; c < WX; c += G) {dst[c] = __ldcg(src + c);}
+				}
+				__syncwarp(gmask);
+				have_win = true;
+			}
+		}
 		{ // ---- one move of the droplet (src/erosion.cpp:76-152) ----
 			float const gx=h00+h01-h10-h11, gz=h00+h10-h01-h11;
 			dx=(dx-gx)*Ki+gx;
 			dz=(dz-gz)*Ki+gz;
 			float const dl=__fsqrt_rn(dx*dx+dz*dz);
 			if (dl<=FLT_EPSILON) { // pick random dir: a = rand_float()*TWO_PI, rand_float() = 1e-6*(rand()%1000000)
-				float2 const cs = __ldg(dir_table + (rgen.rand()%1000000));
+				float2 const cs = __ldg(A.dir_table + (rgen.rand()%1000000));
 				dx=cs.x; dz=cs.y;
 			}
 			else {dx=__fdiv_rn(dx, dl); dz=__fdiv_rn(dz, dl);}
@@ -177,11 +271,20 @@ droplet_kernel(float *__restrict__ padded, unsigned ntiles, int xsize, int ysize
 			}
 			float const nxf=nxp-(float)nxi, nzf=nzp-(float)nzi;
 			float nh00, nh10, nh01, nh11;
-			if ((unsigned)nxi < (unsigned)(NX-1) && (unsigned)nzi < (unsigned)(NY-1)) { // common case: no clamping needed
-				float const *q = mh + (nzi*NX + nxi);
-				nh00 = HLOAD(q); nh10 = HLOAD(q + 1); q += NX; nh01 = HLOAD(q); nh11 = HLOAD(q + 1);
+			if (WHOLE || WIN) { // common case: the 2x2 cell lies inside the window (which lies inside the array: no clamping)
+				unsigned const rx = (unsigned)(nxi - wx0), rz = (unsigned)(nzi - wz0);
+				if (have_win && rx < (unsigned)(WX-1) && rz < (unsigned)(WY-1)) {
+					float const *q = win + (rz*P + rx);
+					nh00 = q[0]; nh10 = q[1]; nh01 = q[P]; nh11 = q[P+1];
+				}
+				else {nh00=hread(nxi, nzi); nh10=hread(nxi+1, nzi); nh01=hread(nxi, nzi+1); nh11=hread(nxi+1, nzi+1);}
 			}
-			else {nh00=HLOAD(&HMAP(nxi, nzi)); nh10=HLOAD(&HMAP(nxi+1, nzi)); nh01=HLOAD(&HMAP(nxi, nzi+1)); nh11=HLOAD(&HMAP(nxi+1, nzi+1));}
+			else if ((unsigned)nxi < (unsigned)(NX-1) && (unsigned)nzi < (unsigned)(NY-1)) { // common case: no clamping needed
+				float const *q = mh + (nzi*NX + nxi);
+				if (SHARED) {nh00 = __ldcg(q); nh10 = __ldcg(q + 1); q += NX; nh01 = __ldcg(q); nh11 = __ldcg(q + 1);}
+				else        {nh00 = *q; nh10 = q[1]; q += NX; nh01 = *q; nh11 = q[1];}
+			}
+			else {nh00=hread(nxi, nzi); nh10=hread(nxi+1, nzi); nh01=hread(nxi, nzi+1); nh11=hread(nxi+1, nzi+1);}
 			float const nh=(nh00*(1-nxf)+nh10*nxf)*(1-nzf)+(nh01*(1-nxf)+nh11*nxf)*nzf;
 			if (smax(smax(nh00, nh10), smax(nh01, nh11)) < E.wpz_minus_half_dxy) {in_droplet = false; continue;} // reached ocean water
 
@@ -223,7 +326,7 @@ droplet_kernel(float *__restrict__ padded, unsigned ntiles, int xsize, int ysize
 						if (!(wgt<=0)) {
 							wgt*=0.1591549430918953f;
 							float const delta=ds*erode_amount*wgt;
-							if (interior) {HADD(&mh[NX*z + x], -delta)} else {HADD(&HMAP(x, z), -delta)}
+							if (interior) {hadd(x, z, -delta);} else {hadd(clampi(x, NX-1), clampi(z, NY-1), -delta);}
 						}
 					}
 				}
@@ -236,7 +339,7 @@ droplet_kernel(float *__restrict__ padded, unsigned ntiles, int xsize, int ysize
 							if (wgt<=0) continue;
 							wgt*=0.1591549430918953f;
 							float const delta=ds*erode_amount*wgt;
-							HADD(&HMAP(x, z), -delta)
+							hadd(clampi(x, NX-1), clampi(z, NY-1), -delta);
 						}
 					}
 				}
@@ -250,34 +353,85 @@ droplet_kernel(float *__restrict__ padded, unsigned ntiles, int xsize, int ysize
 			h=nh; h00=nh00; h10=nh10; h01=nh01; h11=nh11;
 		}
 	}
-#undef HMAP
-#undef HLOAD
-#undef HADD
 #undef DEPOSIT
-	if (sub == 0 && steps_out && steps) {atomicAdd(steps_out, steps);}
+	if (WHOLE && have_tile) { // remove padding and clamp to min_zval (src/erosion.cpp:158-162)
+		__syncwarp(gmask);
+		float const mz = A.min_zvals ? __ldg(A.min_zvals + tile) : A.min_zval_all;
+		float *dst = A.maps + (size_t)tile*xsize*ysize;
+#pragma unroll 4
+		for (int y = 0; y < ysize; ++y) {
+			float const *srow = win + (y + PAD)*P + PAD;
+			for (int x = sub; x < xsize; x += G) {dst[(size_t)y*xsize + x] = smax(mz, srow[x]);}
+		}
+	}
+	if (sub == 0 && A.steps_out && steps) {atomicAdd(A.steps_out, steps);}
 }
 
-template<int G>
-void launch_droplets(cudaStream_t st, float *d_pad, unsigned nt, int xsize, int ysize, unsigned num_iters, EParams const &E, const float2 *dir, unsigned long long *d_steps, const unsigned *order) {
-	unsigned const warps_per_block = 2, tiles_per_block = warps_per_block*(32/G);
-	droplet_kernel<G><<<(nt + tiles_per_block - 1)/tiles_per_block, 32*warps_per_block, 0, st>>>(d_pad, nt, xsize, ysize, num_iters, E, dir, d_steps, order);
+template<int G, int MODE>
+void launch_droplets(cudaStream_t st, DArgs const &A, unsigned warps_per_block, size_t smem_per_group) {
+	unsigned const groups_per_block = warps_per_block*(32/G);
+	size_t const smem = smem_per_group*groups_per_block;
+	if (smem > 48*1024) {cudaFuncSetAttribute(droplet_kernel<G, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);}
+	droplet_kernel<G, MODE><<<(A.nslots + groups_per_block - 1)/groups_per_block, 32*warps_per_block, smem, st>>>(A);
 }
 
-template<int G>
-void launch_droplets_shared(cudaStream_t st, float *d_pad, unsigned ngroups, int xsize, int ysize, unsigned num_iters, EParams const &E, const float2 *dir, unsigned long long *d_steps, unsigned *d_next) {
-	unsigned const warps_per_block = 2, groups_per_block = warps_per_block*(32/G);
-	droplet_kernel<G, true><<<(ngroups + groups_per_block - 1)/groups_per_block, 32*warps_per_block, 0, st>>>(d_pad, ngroups, xsize, ysize, num_iters, E, dir, d_steps, nullptr, d_next);
+template<int MODE>
+void launch_droplets_g(int G, cudaStream_t st, DArgs const &A, unsigned warps_per_block, size_t smem_per_group) {
+	switch (G) {
+	case 1:  launch_droplets<1,  MODE>(st, A, warps_per_block, smem_per_group); break;
+	case 2:  launch_droplets<2,  MODE>(st, A, warps_per_block, smem_per_group); break;
+	case 4:  launch_droplets<4,  MODE>(st, A, warps_per_block, smem_per_group); break;
+	case 8:  launch_droplets<8,  MODE>(st, A, warps_per_block, smem_per_group); break;
+	case 16: launch_droplets<16, MODE>(st, A, warps_per_block, smem_per_group); break;
+	default: launch_droplets<32, MODE>(st, A, warps_per_block, smem_per_group); break;
+	}
 }
+
+int env_int(const char *name, int dflt) {const char *e = getenv(name); return e ? atoi(e) : dflt;}
 
 // lanes per heightmap: the smallest group that still gives ~12 warps per SM (148 SMs), see the kernel comment
 int pick_group(unsigned ntiles) {
-	const char *env = getenv("TW_EROSION_LANES");
-	if (env) {int const g = atoi(env); if (g == 1 || g == 2 || g == 4 || g == 8 || g == 16 || g == 32) return g;}
+	int const g = env_int("TW_EROSION_LANES", 0);
+	if (g == 1 || g == 2 || g == 4 || g == 8 || g == 16 || g == 32) return g;
 	// measured on B200 (tools/bench_erosion.py, 258^2 tiles, heaviest-first schedule): 16384 maps: G=32 0.18 s, G=16 0.23 s, G=8 0.27 s;
 	// 65536 maps: G=32 0.53 s, G=16 0.40 s, G=8 0.40 s. With >= ~16k warps the kernel is issue-bound (78 % issue slots at G=32), so sharing a
 	// warp between maps pays; below that it is latency/tail-bound and one warp per map is fastest. => smallest G >= 8 that keeps 16384 warps.
-	for (int g = 8; g < 32; g *= 2) {if ((unsigned long long)ntiles*g >= 32ull*16384ull) return g;}
+	for (int gg = 8; gg < 32; gg *= 2) {if ((unsigned long long)ntiles*gg >= 32ull*16384ull) return gg;}
 	return 32;
+}
+
+// lanes per heightmap of the shared-memory modes: 16 lanes cover the 4x4 brush; 32 keeps one map per warp (default)
+int pick_smem_group() {
+	int const g = env_int("TW_EROSION_SMEM_LANES", 32);
+	return (g == 1 || g == 2 || g == 4 || g == 8 || g == 16) ? g : 32;
+}
+
+constexpr size_t SMEM_MAX_BLOCK = 227u*1024u; // sm_100: 227 KB of dynamic shared memory per block
+
+// row pitch of the whole-map layout: the smallest P >= NX whose four brush rows start >= 4 banks apart (the 4x4 brush is then conflict-free);
+// kept at NX when padding would push the map over the shared-memory budget
+int whole_pitch(int NX, int NY) {
+	for (int P = NX; P < NX + 8; ++P) {
+		bool ok = true;
+		for (int a = 0; a < 4 && ok; ++a) for (int b = a + 1; b < 4 && ok; ++b) {
+			int d = ((b - a)*P) % 32; if (d > 16) d = 32 - d;
+			if (d < 4) ok = false;
+		}
+		// three 1-warp blocks per SM (228 KB per SM, 1 KB reserved per block) are worth more than conflict-free rows
+		bool const fits3_before = ((size_t)NX*NY*4 + 1024)*3 <= 228u*1024u, fits3_after = ((size_t)P*NY*4 + 1024)*3 <= 228u*1024u;
+		if (ok && (size_t)P*NY*4 <= SMEM_MAX_BLOCK && (fits3_after || !fits3_before)) return P;
+	}
+	return NX;
+}
+
+enum {EM_AUTO = 0, EM_GLOBAL = 1, EM_WINDOW = 2, EM_WHOLE = 3};
+int env_mode() { // TW_EROSION_MODE = global | window | whole (tests and tuning; default: chosen from the batch shape)
+	const char *e = getenv("TW_EROSION_MODE");
+	if (!e) return EM_AUTO;
+	if (!strcmp(e, "global")) return EM_GLOBAL;
+	if (!strcmp(e, "window")) return EM_WINDOW;
+	if (!strcmp(e, "whole"))  return EM_WHOLE;
+	return EM_AUTO;
 }
 
 } // namespace
@@ -291,26 +445,66 @@ static EParams make_eparams(const tw_erosion_params *p) {
 	return E;
 }
 
+// ---- which mode walks a batch (see the kernel comment) ----
+// M_WHOLE for batches of on-chip-sized maps small enough that per-map latency, not machine throughput, decides (the streaming case: the
+// reference creates <= 16 tiles per frame, src/tiled_mesh.cpp:2403-2417): 148 SMs x 3 resident 76 KB maps = 444 walkers.
+static bool plan_whole(uint32_t nt, int xsize, int ysize) {
+	int const NX = xsize + 2*PAD, NY = ysize + 2*PAD, mode = env_mode();
+	if ((size_t)whole_pitch(NX, NY)*NY*sizeof(float) > SMEM_MAX_BLOCK) return false;
+	if (mode == EM_WHOLE) return true;
+	return (mode == EM_AUTO && nt <= (uint32_t)env_int("TW_EROSION_WHOLE_MAX", 148*3*4));
+}
+// M_WINDOW for the `heavy` first slots of the heaviest-first schedule (all of them for small batches), M_GLOBAL for the rest
+static uint32_t plan_heavy(uint32_t nt) {
+	int const mode = env_mode();
+	if (mode == EM_GLOBAL) return 0;
+	if (mode == EM_WINDOW) return nt;
+	uint32_t const all_below = (uint32_t)env_int("TW_EROSION_WINDOW_ALL", 148*16), heavy = (uint32_t)env_int("TW_EROSION_HEAVY", 148*8);
+	return (nt <= all_below) ? nt : (heavy < nt ? heavy : nt);
+}
+
+int twi_ensure_heavy(tw_ctx *ctx, int lane) {
+	if (ctx->heavy_stream[lane]) return TW_OK;
+	int lo = 0, hi = 0;
+	TW_CUDA(ctx, cudaDeviceGetStreamPriorityRange(&lo, &hi));
+	TW_CUDA(ctx, cudaStreamCreateWithPriority(&ctx->heavy_stream[lane], cudaStreamNonBlocking, hi)); // the serial chains of the heaviest maps go first
+	TW_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_fork[lane], cudaEventDisableTiming));
+	TW_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_join[lane], cudaEventDisableTiming));
+	return TW_OK;
+}
+
 size_t twi_erode_scratch_bytes(uint32_t chunk, int xsize, int ysize) {
+	if (plan_whole(chunk, xsize, ysize)) return 256; // no padded copy
 	size_t const padded_elems = (size_t)(xsize + 2*PAD)*(ysize + 2*PAD);
 	size_t const pad_bytes = ((size_t)chunk*padded_elems*sizeof(float) + 255) & ~(size_t)255;
 	return pad_bytes + (((size_t)chunk*2 + WORK_BINS)*sizeof(unsigned) + 255 & ~(size_t)255);
 }
 
-// Enqueue pad -> schedule -> droplets -> unpad for nt <= 65535 heightmaps on `st`, using `scratch` (twi_erode_scratch_bytes(capacity,..) bytes).
-// No synchronisation; d_steps (device counter) accumulates the droplet moves.
-int twi_erode_enqueue(tw_ctx *ctx, cudaStream_t st, void *scratch, uint32_t capacity, float *maps, uint32_t nt, int xsize, int ysize,
+// Enqueue the erosion of nt <= 65535 heightmaps on `st`, using `scratch` (twi_erode_scratch_bytes(capacity,..) bytes). `lane` (0..2) selects
+// the context's fork/join stream for the heavy part. No synchronisation; d_steps (device counter) accumulates the droplet moves.
+int twi_erode_enqueue(tw_ctx *ctx, cudaStream_t st, int lane, void *scratch, uint32_t capacity, float *maps, uint32_t nt, int xsize, int ysize,
                       const float *d_min_zvals, float min_zval_all, uint32_t num_iters, const tw_erosion_params *p, unsigned long long *d_steps)
 {
 	int const NX = xsize + 2*PAD, NY = ysize + 2*PAD;
 	size_t const padded_elems = (size_t)NX*NY;
-	EParams const E = make_eparams(p);
+	DArgs A;
+	memset(&A, 0, sizeof(A));
+	A.E = make_eparams(p);
+	A.xsize = xsize; A.ysize = ysize; A.num_iters = num_iters; A.dir_table = ctx->d_dir_table; A.steps_out = d_steps;
+	A.min_zvals = d_min_zvals; A.min_zval_all = min_zval_all;
+	if (plan_whole(nt, xsize, ysize)) { // whole maps in shared memory, straight from / to the caller's tiles
+		A.maps = maps; A.slot0 = 0; A.nslots = nt;
+		A.WX = NX; A.WY = NY; A.P = whole_pitch(NX, NY); A.win_elems = (unsigned)A.P*NY;
+		launch_droplets_g<M_WHOLE>(pick_smem_group(), st, A, 1, (size_t)A.win_elems*sizeof(float));
+		TW_LAUNCH_CHECK(ctx);
+		return TW_OK;
+	}
 	size_t const pad_bytes = ((size_t)capacity*padded_elems*sizeof(float) + 255) & ~(size_t)255;
 	float *d_pad = (float *)scratch;
 	unsigned *d_work = (unsigned *)((char *)scratch + pad_bytes), *d_hist = d_work + capacity, *d_order = d_hist + WORK_BINS;
 	bool const schedule = (nt > 148u*4u); // with few heightmaps everything is resident at once anyway
 	if (schedule) {TW_CUDA(ctx, cudaMemsetAsync(d_work, 0, ((size_t)capacity + WORK_BINS)*sizeof(unsigned), st));}
-	pad_kernel<<<dim3((NX + 255)/256, NY, nt), 256, 0, st>>>(maps, d_pad, xsize, ysize, NX, NY, E.wpz_minus_half_dxy, schedule ? d_work : nullptr);
+	pad_kernel<<<dim3((NX + 255)/256, NY, nt), 256, 0, st>>>(maps, d_pad, xsize, ysize, NX, NY, A.E.wpz_minus_half_dxy, schedule ? d_work : nullptr);
 	TW_LAUNCH_CHECK(ctx);
 	if (schedule) {
 		unsigned const max_work = (unsigned)padded_elems;
@@ -322,15 +516,34 @@ int twi_erode_enqueue(tw_ctx *ctx, cudaStream_t st, void *scratch, uint32_t capa
 		TW_LAUNCH_CHECK(ctx);
 	}
 	else {d_order = nullptr;}
-	switch (pick_group(nt)) {
-	case 1:  launch_droplets<1 >(st, d_pad, nt, xsize, ysize, num_iters, E, ctx->d_dir_table, d_steps, d_order); break;
-	case 2:  launch_droplets<2 >(st, d_pad, nt, xsize, ysize, num_iters, E, ctx->d_dir_table, d_steps, d_order); break;
-	case 4:  launch_droplets<4 >(st, d_pad, nt, xsize, ysize, num_iters, E, ctx->d_dir_table, d_steps, d_order); break;
-	case 8:  launch_droplets<8 >(st, d_pad, nt, xsize, ysize, num_iters, E, ctx->d_dir_table, d_steps, d_order); break;
-	case 16: launch_droplets<16>(st, d_pad, nt, xsize, ysize, num_iters, E, ctx->d_dir_table, d_steps, d_order); break;
-	default: launch_droplets<32>(st, d_pad, nt, xsize, ysize, num_iters, E, ctx->d_dir_table, d_steps, d_order); break;
+	A.padded = d_pad; A.order = d_order;
+	uint32_t const heavy = plan_heavy(nt);
+	bool const fork = (heavy > 0 && heavy < nt);
+	if (heavy > 0) { // latency mode: shared-memory windows for the maps with the longest serial chains
+		DArgs W = A;
+		int const wsz = env_int("TW_EROSION_WIN", 32);
+		W.slot0 = 0; W.nslots = heavy;
+		W.WX = std::min(std::max(wsz, 8), NX); W.WY = std::min(std::max(wsz, 8), NY);
+		W.P = whole_pitch(W.WX, W.WY); W.win_elems = (unsigned)W.P*W.WY;
+		W.win_min_moves = (unsigned)env_int("TW_EROSION_WIN_MIN_MOVES", (nt == 1) ? 0 : 2);
+		cudaStream_t hs = st;
+		if (fork) {
+			int const rc = twi_ensure_heavy(ctx, lane); if (rc) return rc;
+			hs = ctx->heavy_stream[lane];
+			TW_CUDA(ctx, cudaEventRecord(ctx->ev_fork[lane], st));
+			TW_CUDA(ctx, cudaStreamWaitEvent(hs, ctx->ev_fork[lane], 0));
+		}
+		launch_droplets_g<M_WINDOW>(pick_smem_group(), hs, W, 2, (size_t)W.win_elems*sizeof(float));
+		TW_LAUNCH_CHECK(ctx);
+		if (fork) {TW_CUDA(ctx, cudaEventRecord(ctx->ev_join[lane], hs));}
 	}
-	TW_LAUNCH_CHECK(ctx);
+	if (heavy < nt) { // throughput mode for the rest
+		DArgs T = A;
+		T.slot0 = heavy; T.nslots = nt - heavy;
+		launch_droplets_g<M_GLOBAL>(pick_group(nt - heavy), st, T, 2, 0);
+		TW_LAUNCH_CHECK(ctx);
+	}
+	if (fork) {TW_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_join[lane], 0));}
 	unpad_kernel<<<dim3((xsize + 255)/256, ysize, nt), 256, 0, st>>>(d_pad, maps, xsize, ysize, NX, NY, d_min_zvals, min_zval_all);
 	TW_LAUNCH_CHECK(ctx);
 	return TW_OK;
@@ -361,20 +574,17 @@ int twi_erode_parallel(tw_ctx *ctx, float *d_map, int xsize, int ysize, float mi
 	rc = tw_reserve(ctx, 1, (size_t)NX*NY*sizeof(float));
 	if (rc) return rc;
 	float *d_pad = (float *)ctx->d_scratch[1];
-	EParams const E = make_eparams(p);
 	cudaStream_t const st = ctx->stream;
-	pad_kernel<<<dim3((NX + 255)/256, NY, 1), 256, 0, st>>>(d_map, d_pad, xsize, ysize, NX, NY, E.wpz_minus_half_dxy, nullptr);
+	DArgs A;
+	memset(&A, 0, sizeof(A));
+	A.E = make_eparams(p);
+	pad_kernel<<<dim3((NX + 255)/256, NY, 1), 256, 0, st>>>(d_map, d_pad, xsize, ysize, NX, NY, A.E.wpz_minus_half_dxy, nullptr);
 	TW_LAUNCH_CHECK(ctx);
 	unsigned groups = num_threads ? num_threads : 65536u; // auto: the 65536-map operating point of pick_group() (8 lanes per droplet)
 	if (groups > num_iters) {groups = num_iters;}
-	switch (pick_group(groups)) {
-	case 1:  launch_droplets_shared<1 >(st, d_pad, groups, xsize, ysize, num_iters, E, ctx->d_dir_table, d_steps, d_next); break;
-	case 2:  launch_droplets_shared<2 >(st, d_pad, groups, xsize, ysize, num_iters, E, ctx->d_dir_table, d_steps, d_next); break;
-	case 4:  launch_droplets_shared<4 >(st, d_pad, groups, xsize, ysize, num_iters, E, ctx->d_dir_table, d_steps, d_next); break;
-	case 8:  launch_droplets_shared<8 >(st, d_pad, groups, xsize, ysize, num_iters, E, ctx->d_dir_table, d_steps, d_next); break;
-	case 16: launch_droplets_shared<16>(st, d_pad, groups, xsize, ysize, num_iters, E, ctx->d_dir_table, d_steps, d_next); break;
-	default: launch_droplets_shared<32>(st, d_pad, groups, xsize, ysize, num_iters, E, ctx->d_dir_table, d_steps, d_next); break;
-	}
+	A.padded = d_pad; A.ntiles = groups; A.slot0 = 0; A.nslots = groups; A.xsize = xsize; A.ysize = ysize; A.num_iters = num_iters;
+	A.dir_table = ctx->d_dir_table; A.steps_out = d_steps; A.next_droplet = d_next;
+	launch_droplets_g<M_ATOMIC>(pick_group(groups), st, A, 2, 0);
 	TW_LAUNCH_CHECK(ctx);
 	unpad_kernel<<<dim3((xsize + 255)/256, ysize, 1), 256, 0, st>>>(d_pad, d_map, xsize, ysize, NX, NY, nullptr, min_zval);
 	TW_LAUNCH_CHECK(ctx);
@@ -407,7 +617,7 @@ int twi_erode(tw_ctx *ctx, float *d_maps, uint32_t ntiles, int xsize, int ysize,
 	if (rc) return rc;
 	for (uint32_t t0 = 0; t0 < ntiles; t0 += chunk) {
 		uint32_t const nt = (ntiles - t0 < chunk) ? (ntiles - t0) : chunk;
-		rc = twi_erode_enqueue(ctx, ctx->stream, ctx->d_scratch[1], chunk, d_maps + (size_t)t0*xsize*ysize, nt, xsize, ysize,
+		rc = twi_erode_enqueue(ctx, ctx->stream, 0, ctx->d_scratch[1], chunk, d_maps + (size_t)t0*xsize*ysize, nt, xsize, ysize,
 		                       d_min_zvals ? d_min_zvals + t0 : nullptr, min_zval_all, num_iters, p, d_steps);
 		if (rc) return rc;
 	}

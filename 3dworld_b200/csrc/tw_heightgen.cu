@@ -45,6 +45,8 @@ struct PostParams {
 	float volcano_freq;          // mesh_scale/volcano_width
 	float mesh_scale_z_inv;
 	float mdx, mdy, dx_inv, dy_inv; // grid step, DX_VAL_INV, DY_VAL_INV
+	unsigned skip_x0, skip_y0, skip_w, skip_h; // cells [skip_x0, +skip_w) x [skip_y0, +skip_h) of every grid are left unwritten (skip_w == 0: none): the
+	                             // inside of an AO context grid, which calc_mesh_ao_lighting overwrites with the tile's zvals (src/tiled_mesh.cpp:627)
 };
 
 __device__ __forceinline__ float postproc_noise_zval(float z, const tw_hmap_params &h) { // src/mesh_gen.cpp:555-562
@@ -230,7 +232,8 @@ noise_grid2_kernel(float *__restrict__ out, unsigned nx, unsigned ny, unsigned y
 	if (c_end <= 0xffffffffull) {unsigned const c32 = (unsigned)c0; y = c32/nx; x = c32 - y*nx;} // 32-bit division for every grid below 2^32 cells
 	else {y = (unsigned)(c0/nx); x = (unsigned)(c0 - (size_t)y*nx);}
 	unsigned const xb = (x + 1 < nx) ? x + 1 : 0, yb = (x + 1 < nx) ? y : y + 1;
-	bool const valid0 = (c0 < c_end), valid1 = (c0 + 1 < c_end);
+	bool const skip = (x - P.skip_x0 < P.skip_w && y - P.skip_y0 < P.skip_h && xb - P.skip_x0 < P.skip_w && yb - P.skip_y0 < P.skip_h); // both cells unread
+	bool const valid0 = (c0 < c_end) && !skip, valid1 = (c0 + 1 < c_end) && !skip;
 	float z0 = 0.0f, z1 = 0.0f;
 	if (valid0) { // the second cell of an odd-sized band is computed and dropped
 		using namespace twn2;
@@ -540,7 +543,8 @@ int twi_heightgen(tw_ctx *ctx, const tw_grid2d *g, const tw_height_params *p, in
 	float const mx0 = dx*g->x0, my0 = dy*g->y0; // src/mesh_gen.cpp:591
 	if (ntiles == 0) ntiles = 1;
 
-	PostParams const P = make_post_params(p, enable_glaciate, dx, dy);
+	PostParams P = make_post_params(p, enable_glaciate, dx, dy);
+	P.skip_x0 = ctx->skip_rect[0]; P.skip_y0 = ctx->skip_rect[1]; P.skip_w = ctx->skip_rect[2]; P.skip_h = ctx->skip_rect[3];
 
 	if (p->gen_mode != TW_MGEN_SINE) {
 		NoiseParams N;

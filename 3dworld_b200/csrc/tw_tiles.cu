@@ -118,9 +118,12 @@ tile_normals_kernel(const float *__restrict__ zvals, unsigned zvsize, float dx_v
 // One thread per cell of the stride^2 AO map. Heights inside the tile come from zvals, outside from the context grid czv
 // ((stride + 2*AO_RAY_LEN)^2, origin (x1 - AO_RAY_LEN, y1 - AO_RAY_LEN), generated by the same height function); the ray in direction d visits
 // v += step, step += dir (offsets 1, 3, 6, ... 36 cells) with z0 += dz per step, and the first higher point ends it: atten += 8 - s.
+// ctx_inside: the reference's GPU-gen-mode flow (mesh_gen_mode >= MGEN_SIMPLEX_GPU with AO on): create_zvals generated the context ONCE, cut zvals out
+// of it and kept the un-eroded grid in ao_zvals (src/tiled_mesh.cpp:479-487,505); calc_mesh_ao_lighting swaps it in as czv and does NOT substitute
+// zvals inside the tile (:604,620), so every ray sample comes from the un-eroded context and only the ray origin z0 is the (eroded) zval.
 constexpr int AO_DIRS = 8, AO_STEPS = 8, AO_RAY_LEN = AO_STEPS*(AO_STEPS + 1)/2; // src/tiled_mesh.cpp:41-43
 __global__ void __launch_bounds__(256)
-tile_ao_kernel(const float *__restrict__ zvals, const float *__restrict__ czv, unsigned zvsize, float dz, unsigned char *__restrict__ ao) {
+tile_ao_kernel(const float *__restrict__ zvals, const float *__restrict__ czv, unsigned zvsize, float dz, bool ctx_inside, unsigned char *__restrict__ ao) {
 	unsigned const stride = zvsize - 1, csz = stride + 2*AO_RAY_LEN, tile = blockIdx.y, i = blockIdx.x*blockDim.x + threadIdx.x;
 	if (i >= stride*stride) return;
 	int const y = i/stride, x = i - y*stride;
@@ -135,7 +138,7 @@ tile_ao_kernel(const float *__restrict__ zvals, const float *__restrict__ czv, u
 #pragma unroll
 		for (int s = 0; s < AO_STEPS; ++s) {
 			vx += sx; vy += sy; z0 += dz; sx += dx; sy += dy;
-			bool const inside = ((unsigned)vx < zvsize && (unsigned)vy < zvsize);
+			bool const inside = (!ctx_inside && (unsigned)vx < zvsize && (unsigned)vy < zvsize);
 			float const h = inside ? __ldg(z + vy*(int)zvsize + vx) : __ldg(c + (vy + AO_RAY_LEN)*(int)csz + vx + AO_RAY_LEN);
 			if (h > z0) {atten += AO_STEPS - s; break;} // hit a higher point
 		}
@@ -175,10 +178,22 @@ int twi_tile_normals(tw_ctx *ctx, const float *d_zvals, uint32_t ntiles, uint32_
 	return TW_OK;
 }
 
-int twi_tile_ao(tw_ctx *ctx, const float *d_zvals, const float *d_czv, uint32_t ntiles, uint32_t zvsize, float half_dxy, unsigned char *d_ao) {
+int twi_tile_ao(tw_ctx *ctx, const float *d_zvals, const float *d_czv, uint32_t ntiles, uint32_t zvsize, float half_dxy, bool ctx_inside, unsigned char *d_ao) {
 	unsigned const stride = zvsize - 1;
 	float const dz = (float)(0.5*half_dxy); // src/tiled_mesh.cpp:612
-	tile_ao_kernel<<<dim3((stride*stride + 255)/256, ntiles), 256, 0, ctx->stream>>>(d_zvals, d_czv, zvsize, dz, d_ao);
+	tile_ao_kernel<<<dim3((stride*stride + 255)/256, ntiles), 256, 0, ctx->stream>>>(d_zvals, d_czv, zvsize, dz, ctx_inside, d_ao);
+	TW_LAUNCH_CHECK(ctx);
+	return TW_OK;
+}
+
+// zvals = the zvsize^2 interior of the (stride + 72)^2 context grid: zval = ao_zvals[(y + AO_RAY_LEN)*context_sz + (x + AO_RAY_LEN)] (src/tiled_mesh.cpp:505)
+__global__ void tile_cut_kernel(const float *__restrict__ czv, unsigned zvsize, float *__restrict__ zvals) {
+	unsigned const csz = zvsize - 1 + 2*AO_RAY_LEN, x = blockIdx.x*blockDim.x + threadIdx.x, y = blockIdx.y;
+	size_t const tile = blockIdx.z;
+	if (x < zvsize) {zvals[tile*zvsize*zvsize + (size_t)y*zvsize + x] = __ldg(czv + tile*csz*csz + (size_t)(y + AO_RAY_LEN)*csz + x + AO_RAY_LEN);}
+}
+int twi_tile_cut(tw_ctx *ctx, const float *d_czv, uint32_t ntiles, uint32_t zvsize, float *d_zvals) {
+	tile_cut_kernel<<<dim3((zvsize + 127)/128, zvsize, ntiles), 128, 0, ctx->stream>>>(d_czv, zvsize, d_zvals);
 	TW_LAUNCH_CHECK(ctx);
 	return TW_OK;
 }

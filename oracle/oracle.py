@@ -110,7 +110,7 @@ def lib():
                                   C.c_float, C.c_float, C.c_float, C.c_float, C.c_uint, C.POINTER(ErosionParams), vp, vp, vp, vp]
         L.to_tile_bounds.argtypes = [vp, C.c_uint, C.c_uint, C.c_float, C.c_float, C.c_float, C.c_uint, vp]
         L.to_tile_normals.argtypes = [vp, C.c_uint, C.c_uint, C.c_float, C.c_float, vp, vp]
-        L.to_tile_ao.argtypes = [vp, vp, C.c_uint, C.c_uint, C.c_float, vp]
+        L.to_tile_ao.argtypes = [vp, vp, C.c_uint, C.c_uint, C.c_float, C.c_int, vp]
         L.to_hmap_sample_tiles.argtypes = [vp, C.POINTER(HmapSampler), vp, C.c_uint, C.c_uint, vp]
         L.to_eval_points.argtypes = [vp, C.c_size_t, C.POINTER(HeightParams), C.POINTER(PointQuery), vp, vp, vp]
         L.to_apply_erosion.argtypes = [vp, C.c_int, C.c_int, C.c_float, C.c_uint, C.POINTER(ErosionParams)]
@@ -198,14 +198,15 @@ def tile_normals(tiles, dx_val, dy_val):
     return rgba, mnz
 
 
-def tile_ao(tiles, contexts, half_dxy):
-    """contexts: [nt, stride+72, stride+72] heights generated at origin (x1-36, y1-36) (heightgen_2d of the shifted, enlarged grid)."""
+def tile_ao(tiles, contexts, half_dxy, use_ao_zvals=False):
+    """contexts: [nt, stride+72, stride+72] heights generated at origin (x1-36, y1-36) (heightgen_2d of the shifted, enlarged grid).
+    use_ao_zvals: the reference's GPU-gen-mode flow (rays test the un-eroded context inside the tile too)."""
     tiles = np.ascontiguousarray(tiles, np.float32)
     contexts = np.ascontiguousarray(contexts, np.float32)
     nt, zv = tiles.shape[0], tiles.shape[1]
     assert contexts.shape == (nt, zv - 1 + 72, zv - 1 + 72)
     ao = np.empty((nt, zv - 1, zv - 1), np.uint8)
-    lib().to_tile_ao(_p(tiles), _p(contexts), nt, zv, half_dxy, _p(ao))
+    lib().to_tile_ao(_p(tiles), _p(contexts), nt, zv, half_dxy, int(use_ao_zvals), _p(ao))
     return ao
 
 

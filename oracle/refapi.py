@@ -60,6 +60,10 @@ def lib():
         L.ref_voxel_fill.argtypes = [C.c_uint] * 3 + [C.c_void_p] * 3 + [C.c_float, C.c_float, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p]
         L.ref_get_rx_ry.argtypes = [fp, fp]
         L.ref_gen_mesh.argtypes = [C.c_uint, C.POINTER(Erosion), C.c_void_p, C.c_void_p]
+        if hasattr(L, "ref_tile_create_zvals"):   # functions cut out of src/tiled_mesh.cpp at build time (oracle/refbuild/build_ref.sh)
+            L.ref_tile_create_zvals.argtypes = [C.c_uint, C.c_int, C.c_int, C.c_uint, C.POINTER(Erosion), C.c_void_p, C.c_void_p, C.c_void_p]
+            L.ref_tile_ao_lighting.argtypes = [C.c_uint, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p]
+            L.ref_ao_ray_len.restype = C.c_uint
         _lib = L
     return _lib
 
@@ -170,3 +174,37 @@ def gen_mesh(mesh_xy, erosion_iters=0, erode_amount=1.0, relh_adj_tex=0.0, clip_
     p = Erosion(erode_amount, 0.0, 0.0, 0.0, 0.0, relh_adj_tex, clip_hd1)
     lib().ref_gen_mesh(erosion_iters, C.byref(p), out.ctypes.data_as(C.c_void_p), z6.ctypes.data_as(C.c_void_p))
     return out, dict(zip(("zmin", "zmax", "zmax_est", "zbottom", "ztop", "water_plane_z"), (float(v) for v in z6)))
+
+
+def has_tiled_extract():
+    return available() and hasattr(lib(), "ref_tile_create_zvals")
+
+
+def tile_create_zvals(size, x1, y1, erosion_iters=0, ep=None):
+    """The reference's own tile_t::create_zvals() (function body cut out of src/tiled_mesh.cpp:467-546 at build time), CPU gen modes 0-2:
+    returns (zvals [zvsize, zvsize], dict(sub_zmin[4,4], sub_zmax[4,4], mzmin, mzmax, mesh_dz, radius, wbox=(wx1, wy1, wx2, wy2)))."""
+    zv = size + 2
+    z = np.empty((zv, zv), np.float32)
+    b = np.empty(36, np.float32)
+    w = np.empty(4, np.int32)
+    rc = lib().ref_tile_create_zvals(size, int(x1), int(y1), int(erosion_iters), None if ep is None else C.byref(ep), z.ctypes.data_as(C.c_void_p),
+                                     b.ctypes.data_as(C.c_void_p), w.ctypes.data_as(C.c_void_p))
+    assert rc == 0, rc
+    return z, dict(sub_zmin=b[:16].reshape(4, 4).copy(), sub_zmax=b[16:32].reshape(4, 4).copy(), mzmin=float(b[32]), mzmax=float(b[33]), mesh_dz=float(b[34]),
+                   radius=float(b[35]), wbox=tuple(int(v) for v in w))
+
+
+def tile_ao_lighting(size, x1, y1, zvals, ao_context=None, half_dxy=0.0625):
+    """The reference's own tile_t::calc_mesh_ao_lighting() (cut out of src/tiled_mesh.cpp:586-662). ao_context=None: it builds the context
+    itself (zvals inside the tile, eval_index outside; CPU gen modes); otherwise the GPU-mode flow with the stored un-eroded ao_zvals."""
+    zvals = np.ascontiguousarray(zvals, np.float32)
+    assert zvals.shape == (size + 2, size + 2)
+    ao = np.empty((size + 1, size + 1), np.uint8)
+    cz = None
+    if ao_context is not None:
+        cz = np.ascontiguousarray(ao_context, np.float32)
+        assert cz.shape == (size + 1 + 72, size + 1 + 72)
+    rc = lib().ref_tile_ao_lighting(size, int(x1), int(y1), zvals.ctypes.data_as(C.c_void_p), None if cz is None else cz.ctypes.data_as(C.c_void_p),
+                                    C.c_float(half_dxy), ao.ctypes.data_as(C.c_void_p))
+    assert rc == 0, rc
+    return ao

@@ -15,6 +15,25 @@ done
 for f in ref_driver ref_stubs ref_glm; do
   g++ $FLAGS $INC -c "$HERE/$f.cpp" -o "$OUT/$f.o"
 done
+# tiled_mesh.cpp cannot be linked as a whole (it pulls in the engine), but the functions of the path can be compiled on their own: cut them out
+# of the read-only source AT BUILD TIME into a generated TU (oracle/_ref is git-ignored: no reference source is committed) between a prelude and
+# a harness of ours. Cut by function signature, not by line number: the file's header block (includes, constants, extern declarations = everything
+# before its first function definition), get_max_sea_level, get_xy_scale .. tile_t::create_zvals (src/tiled_mesh.cpp:447-546) and
+# tile_t::calc_mesh_ao_lighting (:586-662).
+T=$R/src/tiled_mesh.cpp
+mkdir -p "$OUT/gen"
+{
+  echo "// GENERATED at build time by oracle/refbuild/build_ref.sh from $T - do not commit"
+  cat "$HERE/ref_tiled_prelude.inc"
+  awk '/^[a-z].*\) \{\r?$/ {exit} {print}' "$T"
+  echo 'float get_water_z_height(); bool using_hmap_with_detail(); extern terrain_hmap_manager_t terrain_hmap_manager; // declarations the cut-out functions need (defined in the harness / ref_stubs.cpp)'
+  grep -E '^#define BILINEAR_INTERP' "$T"
+  grep -E '^float get_max_sea_level +\(\)' "$T"
+  awk '/^float get_xy_scale\(\) \{/ {p=1} p {print} p && /^bool tile_t::create_zvals/ {f=1} f && /^}/ {exit}' "$T"
+  awk '/^void tile_t::calc_mesh_ao_lighting\(\) \{/ {p=1} p {print} p && /^}/ {exit}' "$T"
+  cat "$HERE/ref_tiled_harness.inc"
+} > "$OUT/gen/tiled_extract.cpp"
+g++ $FLAGS $INC -I "$HERE" -c "$OUT/gen/tiled_extract.cpp" -o "$OUT/tiled_extract.o"
 g++ -shared -fopenmp -Wl,--gc-sections -Wl,--no-undefined -Wl,--version-script="$HERE/exports.map" -o "$OUT/libref3dworld.so" \
-  "$OUT"/ref_driver.o "$OUT"/ref_stubs.o "$OUT"/ref_glm.o "$OUT"/mesh_gen.o "$OUT"/erosion.o "$OUT"/upsurface.o "$OUT"/heightmap.o
+  "$OUT"/ref_driver.o "$OUT"/ref_stubs.o "$OUT"/ref_glm.o "$OUT"/mesh_gen.o "$OUT"/erosion.o "$OUT"/upsurface.o "$OUT"/heightmap.o "$OUT"/tiled_extract.o
 echo "built $OUT/libref3dworld.so"

@@ -658,8 +658,9 @@ void to_tile_normals(const float *zvals_all, unsigned ntiles, unsigned zvsize, f
 		if (min_normal_z) {min_normal_z[t] = mnz;}
 	}
 }
-/* czv_all: ntiles context grids of (stride + 72)^2 heights at origin (x1 - 36, y1 - 36) */
-void to_tile_ao(const float *zvals_all, const float *czv_all, unsigned ntiles, unsigned zvsize, float half_dxy, unsigned char *ao) {
+/* czv_all: ntiles context grids of (stride + 72)^2 heights at origin (x1 - 36, y1 - 36). use_ao_zvals: the GPU-gen-mode flow, where create_zvals
+   kept the un-eroded context in ao_zvals and calc_mesh_ao_lighting swaps it in WITHOUT substituting zvals inside the tile (ref: :479-487,604) */
+void to_tile_ao(const float *zvals_all, const float *czv_all, unsigned ntiles, unsigned zvsize, float half_dxy, int use_ao_zvals, unsigned char *ao) {
 	enum {NUM_AO_DIRS = 8, NUM_AO_STEPS = 8, AO_RAY_LEN = 36};
 	unsigned const stride = zvsize - 1, context_sz = stride + 2*AO_RAY_LEN;
 	int dirs[NUM_AO_DIRS][2], ix = 0;
@@ -671,7 +672,7 @@ void to_tile_ao(const float *zvals_all, const float *czv_all, unsigned ntiles, u
 		for (int y = 0; y < (int)context_sz; ++y) { /* ref: :624-637 */
 			for (int x = 0; x < (int)context_sz; ++x) {
 				int const xv = x - AO_RAY_LEN, yv = y - AO_RAY_LEN;
-				czv[y*context_sz + x] = (xv >= 0 && yv >= 0 && xv < (int)zvsize && yv < (int)zvsize) ? zvals[yv*zvsize + xv] : gen[y*context_sz + x];
+				czv[y*context_sz + x] = (!use_ao_zvals && xv >= 0 && yv >= 0 && xv < (int)zvsize && yv < (int)zvsize) ? zvals[yv*zvsize + xv] : gen[y*context_sz + x];
 			}
 		}
 		for (int y = 0; y < (int)stride; ++y) { /* ref: :640-659 */

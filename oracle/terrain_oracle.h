@@ -66,7 +66,7 @@ void to_tile_bounds(const float *zvals, unsigned ntiles, unsigned zvsize, float 
 /* apply_erosion, src/erosion.cpp:14-164 (serial droplet order) ; returns total droplet steps */
 /* tile_t::upload_normal_texture / calc_mesh_ao_lighting (src/tiled_mesh.cpp:865-880, 586-662); czv = generated context grids (stride+72)^2 per tile */
 void to_tile_normals(const float *zvals, unsigned ntiles, unsigned zvsize, float dx_val, float dy_val, unsigned char *rgba, float *min_normal_z);
-void to_tile_ao(const float *zvals, const float *czv, unsigned ntiles, unsigned zvsize, float half_dxy, unsigned char *ao);
+void to_tile_ao(const float *zvals, const float *czv, unsigned ntiles, unsigned zvsize, float half_dxy, int use_ao_zvals, unsigned char *ao);
 /* heightmap-texture mode of tile_t::create_zvals: terrain_hmap_manager_t::get_clamped_height over tiles (src/heightmap.cpp:385-402) */
 void to_hmap_sample_tiles(const unsigned char *data16, const tw_hmap_sampler *H, const int *origins_xy, unsigned ntiles, unsigned zvsize, float *out);
 /* eval_mesh_sin_terms / eval_mesh_sin_terms_scaled / get_exact_zval (procedural branch) for n points, src/mesh_gen.cpp:797-847 */

@@ -118,7 +118,58 @@ def test_tile_normals_and_ao_golden(tw, ctx, mode):
     rgba, mnz = ctx.tile_normals(tile[None], dx, dy)
     assert np.array_equal(rgba[0], h["normals_" + n]) and mnz[0] == h["min_normal_z_" + n]
     ao = ctx.tile_ao(tile[None], [(x1, y1)], (S, S), dx, dy, hp, half_dxy)
-    assert np.array_equal(ao[0], h["ao_" + n])
+    assert np.array_equal(ao[0], h["ao_" + n])           # = the reference's own calc_mesh_ao_lighting (tests/golden/make_golden_tiles.py)
+
+
+def test_create_zvals_with_ao_gpu_mode_golden(tw, ctx, beq):
+    """enable_tiled_mesh_ao + mesh_gen_mode 4: tile_t::create_zvals generates the (stride+72)^2 context once, cuts zvals out of it and erodes them;
+    calc_mesh_ao_lighting tests the rays against the UN-eroded context. Golden = the reference's own functions."""
+    from test_oracle_golden import tile_case
+    h = np.load(os.path.join(GOLD, "tiles.npz"))
+    hp, _, a = tile_case(tw, h, 4)
+    x1, y1, S, zv, dx, dy, half_dxy = int(a[1]), int(a[2]), int(a[3]), int(a[4]), float(a[5]), float(a[6]), float(a[7])
+    e = h["ero_m4"]
+    ep = tw.ErosionParams(*[float(v) for v in e[2:]])
+    z, ao = ctx.create_zvals_ao_batch([(x1, y1)], (S, S), dx, dy, zv, hp, 0, ep, float(e[0]), half_dxy)
+    assert beq(z[0], h["tile_m4c"]) == 0 and np.array_equal(ao[0], h["ao_m4c"])
+    z, ao, mm = ctx.create_zvals_ao_batch([(x1, y1)], (S, S), dx, dy, zv, hp, int(e[1]), ep, float(e[0]), half_dxy, want_minmax=True)
+    assert beq(z[0], h["tile_m4e"]) == 0 and np.array_equal(ao[0], h["ao_m4e"])
+    assert (mm[0, 0], mm[0, 1]) == (h["tile_m4e"].min(), h["tile_m4e"].max())
+    # the two-call route gives the same AO when handed the eroded zvals (context regenerated inside tw_tile_ao_batch)
+    assert np.array_equal(ctx.tile_ao(h["tile_m4e"][None], [(x1, y1)], (S, S), dx, dy, hp, half_dxy)[0], h["ao_m4e"])
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2, 3, 4])
+def test_create_zvals_with_ao_batch_vs_oracle(tw, scene, oracle, ctx, beq, mode):
+    """tw_create_zvals_ao_batch over a batch, every gen mode, host and device outputs, vs the oracle's restatement of the two reference flows
+    (which tests/test_oracle_vs_reference.py pins against the reference's own function bodies)."""
+    import torch
+    S, zv = 64, 66
+    cfg = scene.SceneConfig(mesh_gen_mode=mode, mesh_freq_filter=1, mesh_seed=1, hmap=HM_CFG, zmax_est=2.3, mesh_size=(S, S, 1))
+    hp, ep = cfg.height_params(), cfg.erosion_params()
+    sp = None
+    if mode == 0:
+        sp = cfg.sine_params()
+        ctx.set_sine_params(sp)
+    dx, dy, hd = float(cfg.dx_val), float(cfg.dy_val), 0.5 * float(cfg.dx_val + cfg.dy_val)
+    origins = [(tx * S * 9 - 1500, ty * S * 7 + 200) for ty in range(2) for tx in range(4)]
+    hp_o, ep_o = convert(hp, oracle.HeightParams), convert(ep, oracle.ErosionParams)
+    csz = zv - 1 + 72
+    contexts = np.stack([oracle.heightgen_2d(oracle.Grid2D(x1 - 36 - S // 2, y1 - 36 - S // 2, dx, dy, csz, csz), hp_o, sp, 1, 0) for x1, y1 in origins])
+    if mode >= 3:
+        raw = np.ascontiguousarray(contexts[:, 36:36 + zv, 36:36 + zv])
+    else:
+        raw = np.stack([oracle.heightgen_2d(oracle.Grid2D(x1 - S // 2, y1 - S // 2, dx, dy, zv, zv), hp_o, sp, 1, 0) for x1, y1 in origins])
+    exp_z = np.stack([oracle.apply_erosion(t, ep.zmin, 300, ep_o)[0] for t in raw])
+    exp_ao = oracle.tile_ao(exp_z, contexts, hd, use_ao_zvals=(mode >= 3))
+    z, ao = ctx.create_zvals_ao_batch(origins, cfg.mesh_size, dx, dy, zv, hp, 300, ep, ep.zmin, hd)
+    assert beq(z, exp_z) == 0 and np.array_equal(ao, exp_ao)
+    assert (exp_z != raw).any() and ao.min() < 255
+    dz = torch.empty((len(origins), zv, zv), dtype=torch.float32, device="cuda")
+    dao = torch.empty((len(origins), zv - 1, zv - 1), dtype=torch.uint8, device="cuda")
+    ctx.create_zvals_ao_batch(origins, cfg.mesh_size, dx, dy, zv, hp, 300, ep, ep.zmin, hd, out=dz, ao=dao)
+    assert beq(dz.cpu().numpy(), exp_z) == 0 and np.array_equal(dao.cpu().numpy(), exp_ao)
+    assert np.array_equal(ctx.tile_ao(exp_z, origins, cfg.mesh_size, dx, dy, hp, hd), exp_ao)
 
 
 def test_tile_normals_and_ao_batch_vs_oracle(tw, scene, oracle, ctx, beq):

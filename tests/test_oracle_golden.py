@@ -122,7 +122,15 @@ def test_tile_normals_and_ao(oracle, beq):
         assert np.array_equal(rgba[0], h["normals_" + n]) and mnz[0] == h["min_normal_z_" + n]
         csz = zv - 1 + 72
         context = oracle.heightgen_2d(oracle.Grid2D(x1 - 36 - S // 2, y1 - 36 - S // 2, dx, dy, csz, csz), hp, sp, 1, 0)
-        assert np.array_equal(oracle.tile_ao(tile[None], context[None], half_dxy)[0], h["ao_" + n])
+        assert np.array_equal(oracle.tile_ao(tile[None], context[None], half_dxy, use_ao_zvals=(mode >= 3))[0], h["ao_" + n])
+        if mode >= 3:   # create_zvals + calc_mesh_ao_lighting in a GPU gen mode: zvals = interior of the context, erosion, AO against the un-eroded context
+            cut = np.ascontiguousarray(context[36:36 + zv, 36:36 + zv])
+            assert beq(cut, h["tile_" + n + "c"]) == 0
+            e = h["ero_" + n]
+            eroded, _ = oracle.apply_erosion(cut, float(e[0]), int(e[1]), oracle.ErosionParams(*[float(v) for v in e[2:]]))
+            assert beq(eroded, h["tile_" + n + "e"]) == 0
+            assert np.array_equal(oracle.tile_ao(cut[None], context[None], half_dxy, use_ao_zvals=True)[0], h["ao_" + n + "c"])
+            assert np.array_equal(oracle.tile_ao(eroded[None], context[None], half_dxy, use_ao_zvals=True)[0], h["ao_" + n + "e"])
 
 
 def hmap_cases(mod, h):

@@ -179,3 +179,82 @@ def test_gen_mesh_ground_mode(oracle, ref, beq):
         assert beq(zr, zo) == 0, (mode, seed)
         assert all(np.float32(z6r[k]) == np.float32(z6o[k]) for k in z6r), (z6r, z6o)
     ref.lib().ref_set_threads(8)
+
+
+def _need_extract(ref):
+    import pytest
+    if not ref.has_tiled_extract():
+        pytest.skip("oracle/_ref was built without the tiled_mesh.cpp extraction")
+
+
+def test_tile_create_zvals_extracted_reference(oracle, ref, beq):
+    """SURVEY 8a row a11 pinned against the reference's OWN tile_t::create_zvals(): the function body is cut out of src/tiled_mesh.cpp:467-546
+    at build time (oracle/refbuild/build_ref.sh) and compiled unmodified together with setup_height_gen_async/get_xy_scale; it runs
+    build_arrays + eval_index + apply_erosion + the 4x4 sub-block / water-bbox / radius tail. The port = heightgen_2d + apply_erosion +
+    tile_bounds. CPU gen modes 0-2 (modes 3/4 need GL inside build_arrays)."""
+    _need_extract(ref)
+    RL = ref.lib()
+    RL.ref_set_threads(1)
+    for mode, size, mesh in ((1, 64, (64, 64, 1)), (2, 32, (32, 32, 1)), (0, 48, (48, 48, 1)), (1, 128, (128, 128, 1))):
+        for x1, y1, iters in ((0, 0, 0), (5 * size, -3 * size, 300), (-40 * size, 17 * size, 120)):
+            ref.setup(mesh=mesh, mode=mode, freq_filter=1, seed=1, zmax_est=2.0, hmap=HM_CFG)
+            dx, dy = RL.ref_get_dx(), RL.ref_get_dy()
+            hp = oracle.HeightParams()
+            hp.gen_mode, hp.gen_shape, hp.start_eval_sin, hp.glaciate = mode, 0, oracle.compute_scale(1.0, 1), 1
+            hp.mesh_scale = hp.mesh_scale_z_inv = hp.mesh_height_scale = 1.0
+            hp.dx_val_inv, hp.dy_val_inv = 1.0 / np.float32(dx), 1.0 / np.float32(dy)
+            hp.mesh_height, hp.zmax_est = RL.ref_get_mesh_height(), 2.0
+            hp.rx, hp.ry = oracle.gen_rx_ry(1, 0, mode)
+            hp.hmap = oracle.hmap_params(**HM_CFG)
+            sp = ref.sine_params() if mode == 0 else None
+            zv = size + 2
+            raw = oracle.heightgen_2d(oracle.Grid2D(float(x1 - mesh[0] // 2), float(y1 - mesh[1] // 2), dx, dy, zv, zv), hp, sp, 1, 0)
+            lo, hi = float(raw.min()), float(raw.max())
+            wpz = RL.ref_get_water_z_height()
+            # erosion's own water level (droplets stop below it): under the tile / inside its height range; zmin = min_zval of the tile erosion, zmax, clip_hd1 of get_bare_ls_tid
+            ep = ref.Erosion(1.0, (lo - 10.0) if x1 > 0 else (lo + 0.3 * (hi - lo)), 0.5 * (dx + dy), lo - 0.05, hi + 0.3, 0.0, 0.4)
+            zr, br = ref.tile_create_zvals(size, x1, y1, iters, ep)
+            zo = raw
+            if iters:
+                zo, _ = oracle.apply_erosion(raw, ep.zmin, iters, oracle.ErosionParams(*[getattr(ep, f) for f, _ in ep._fields_]))
+                assert (zo != raw).any()
+            assert beq(zr, zo) == 0, (mode, size, x1, y1, iters)
+            bo = oracle.tile_bounds(zo[None], wpz, dx, dy, size)[0]
+            assert np.array_equal(np.array(bo.sub_zmin, np.float32).reshape(4, 4), br["sub_zmin"]) and np.array_equal(np.array(bo.sub_zmax, np.float32).reshape(4, 4), br["sub_zmax"])
+            assert (np.float32(bo.mzmin), np.float32(bo.mzmax), np.float32(bo.mesh_dz), np.float32(bo.radius)) == tuple(np.float32(br[k]) for k in ("mzmin", "mzmax", "mesh_dz", "radius"))
+            if bo.wx2 >= 0:      # some cell below the sea level: the reference's box is in global cell coordinates (x1 + x)
+                assert (x1 + bo.wx1, y1 + bo.wy1, x1 + bo.wx2, y1 + bo.wy2) == br["wbox"]
+            else:                # none: the reference keeps its denormalised start value (x2, y2, x1, y1)
+                assert br["wbox"] == (x1 + size, y1 + size, x1, y1)
+    RL.ref_set_threads(8)
+
+
+def test_tile_ao_lighting_extracted_reference(oracle, ref, beq):
+    """SURVEY 8f row N1 pinned against the reference's OWN tile_t::calc_mesh_ao_lighting() (cut out of src/tiled_mesh.cpp:586-662), both flows:
+    (a) CPU gen modes: it builds the (stride+72)^2 context itself - zvals inside the tile, eval_index outside - from ERODED zvals;
+    (b) GPU gen modes: create_zvals left the UN-eroded context in ao_zvals and the rays test it inside the tile too (only z0 is eroded)."""
+    _need_extract(ref)
+    RL = ref.lib()
+    assert RL.ref_ao_ray_len() == 36
+    for mode, size in ((1, 64), (0, 40), (2, 36), (4, 64), (3, 48)):
+        mesh = (size, size, 1)
+        ref.setup(mesh=mesh, mode=mode, freq_filter=1, seed=1, zmax_est=2.0, hmap=HM_CFG)
+        dx, dy = RL.ref_get_dx(), RL.ref_get_dy()
+        half_dxy = 0.5 * (dx + dy)
+        zv, csz = size + 2, size + 1 + 72
+        for x1, y1 in ((0, 0), (-7 * size, 11 * size)):
+            gx, gy = float(x1 - mesh[0] // 2), float(y1 - mesh[1] // 2)
+            zvals = ref.heightgen(gx, gy, dx, dy, zv, zv, 0, 1)
+            context = ref.heightgen(gx - 36, gy - 36, dx, dy, csz, csz, 0, 1)
+            lo, hi = float(zvals.min()), float(zvals.max())
+            eroded = ref.apply_erosion(zvals, lo, 400, water_plane_z=lo - 10, zmin=lo - 0.1, zmax=hi + 0.1, clip_hd1=0.5)
+            assert (eroded != zvals).any()
+            for z, hd in ((zvals, half_dxy), (eroded, half_dxy), (eroded, 0.02 * half_dxy)):     # the last: nearly horizontal rays => many occluded cells
+                if mode < 3:
+                    ar = ref.tile_ao_lighting(size, x1, y1, z, None, hd)
+                    ao = oracle.tile_ao(z[None], context[None], hd, use_ao_zvals=False)[0]
+                else:
+                    ar = ref.tile_ao_lighting(size, x1, y1, z, context, hd)
+                    ao = oracle.tile_ao(z[None], context[None], hd, use_ao_zvals=True)[0]
+                assert np.array_equal(ar, ao), (mode, size, x1, y1)
+            assert ar.min() < 200 and ar.max() > ar.min()
