@@ -96,7 +96,10 @@ ABI_SYMBOLS = ["tw_abi_version", "tw_create", "tw_destroy", "tw_last_error", "tw
                "tw_build_sin_table", "tw_compute_scale", "tw_gen_sine_params", "tw_gen_rx_ry", "tw_noise3d_gen_sines",
                "tw_water_z_height", "tw_set_sin_table", "tw_set_sine_params", "tw_heightgen_2d", "tw_heightgen_2d_launch",
                "tw_heightgen_2d_poll", "tw_heightgen_tiles", "tw_create_zvals_batch", "tw_tile_bounds_batch", "tw_tile_normals_batch", "tw_tile_ao_batch", "tw_create_zvals_ao_batch", "tw_glaciate_mesh", "tw_eval_points", "tw_erode", "tw_erode_parallel", "tw_erode_tiles", "tw_last_erosion_steps", "tw_voxel_fill",
-               "tw_heightmap_from_floats_u16", "tw_heightmap_to_floats_u16", "tw_proc_gen_heightmap", "tw_heightmap_sample_tiles", "tw_minmax_f32"]
+               "tw_heightmap_from_floats_u16", "tw_heightmap_to_floats_u16", "tw_proc_gen_heightmap", "tw_heightmap_sample_tiles", "tw_minmax_f32",
+               "tw_multi_create", "tw_multi_destroy", "tw_multi_size", "tw_multi_ctx", "tw_multi_last_error", "tw_multi_set_sine_params", "tw_multi_range",
+               "tw_multi_alloc_host", "tw_multi_free_host", "tw_create_zvals_sharded", "tw_heightgen_2d_sharded", "tw_dist_unique_id", "tw_dist_init",
+               "tw_dist_allreduce_minmax", "tw_dist_finalize", "tw_bind_thread_to_device"]
 
 
 def _load():
@@ -155,6 +158,30 @@ def _load():
     L.tw_proc_gen_heightmap.argtypes = [vp, C.c_uint32, C.c_uint32, C.c_float, C.c_float, C.POINTER(HeightParams), C.c_uint32, C.POINTER(ErosionParams), vp, vp,
                                         C.POINTER(HeightmapInfo)]
     L.tw_minmax_f32.argtypes = [vp, vp, C.c_size_t, C.POINTER(MinMax)]
+    # multi-GPU
+    L.tw_multi_create.argtypes = [vp, C.c_int, C.POINTER(vp)]
+    L.tw_multi_destroy.argtypes = [vp]
+    L.tw_multi_destroy.restype = None
+    L.tw_multi_size.argtypes = [vp]
+    L.tw_multi_ctx.argtypes = [vp, C.c_int]
+    L.tw_multi_ctx.restype = vp
+    L.tw_multi_last_error.argtypes = [vp]
+    L.tw_multi_last_error.restype = C.c_char_p
+    L.tw_multi_set_sine_params.argtypes = [vp, vp]
+    L.tw_multi_range.argtypes = [C.c_uint32, C.c_int, C.c_int, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
+    L.tw_multi_range.restype = None
+    L.tw_multi_alloc_host.argtypes = [vp, C.c_int, C.c_size_t, C.POINTER(vp)]
+    L.tw_multi_free_host.argtypes = [vp, vp]
+    L.tw_multi_free_host.restype = None
+    L.tw_create_zvals_sharded.argtypes = [vp, vp, C.c_uint32, C.c_int, C.c_int, C.c_float, C.c_float, C.c_uint32, C.POINTER(HeightParams), C.c_uint32,
+                                          C.POINTER(ErosionParams), C.c_float, vp, vp, C.POINTER(MinMax)]
+    L.tw_heightgen_2d_sharded.argtypes = [vp, C.POINTER(Grid2D), C.POINTER(HeightParams), C.c_int, vp, C.POINTER(MinMax)]
+    L.tw_dist_unique_id.argtypes = [vp]
+    L.tw_dist_init.argtypes = [vp, C.c_int, C.c_int, vp]
+    L.tw_dist_allreduce_minmax.argtypes = [vp, C.POINTER(MinMax)]
+    L.tw_dist_finalize.argtypes = [vp]
+    L.tw_dist_finalize.restype = None
+    L.tw_bind_thread_to_device.argtypes = [C.c_int]
     return L
 
 
@@ -210,6 +237,87 @@ def water_z_height(zmax_est, glaciate=1, custom_glaciate_exp=0.0, water_h_off=0.
     return lib.tw_water_z_height(zmax_est, glaciate, custom_glaciate_exp, water_h_off, water_h_off_rel)
 
 
+def multi_range(n, ndev, i):
+    a, b = C.c_uint32(), C.c_uint32()
+    lib.tw_multi_range(n, ndev, i, C.byref(a), C.byref(b))
+    return a.value, b.value
+
+
+def dist_unique_id():
+    """128-byte NCCL id for Context.dist_init (rank 0 makes it, every rank receives it out of band, e.g. a torch.distributed broadcast)."""
+    buf = C.create_string_buffer(128)
+    rc = lib.tw_dist_unique_id(buf)
+    if rc != TW_OK:
+        raise TwError(rc, "tw_dist_unique_id: libnccl.so.2 not loadable")
+    return buf.raw
+
+
+def bind_thread_to_device(device):
+    return lib.tw_bind_thread_to_device(int(device)) == TW_OK
+
+
+class Multi:
+    """tw_multi: one process driving several GPUs (one tw_ctx + worker thread per device, NCCL z-range reduction inside the library)."""
+
+    def __init__(self, devices):
+        devs = (C.c_int * len(devices))(*devices)
+        h = C.c_void_p()
+        rc = lib.tw_multi_create(C.cast(devs, C.c_void_p), len(devices), C.byref(h))
+        if rc != TW_OK:
+            raise TwError(rc, "tw_multi_create failed")
+        self._h, self.n, self.devices = h, len(devices), list(devices)
+
+    def close(self):
+        if getattr(self, "_h", None) and lib is not None:
+            lib.tw_multi_destroy(self._h)
+        self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != TW_OK:
+            raise TwError(rc, lib.tw_multi_last_error(self._h).decode())
+
+    def set_sine_params(self, sp):
+        sp = np.ascontiguousarray(sp, np.float32)
+        self._check(lib.tw_multi_set_sine_params(self._h, _ptr(sp)))
+
+    def alloc_host(self, i, shape, dtype=np.float32):
+        """numpy view of pinned host memory on device i's NUMA node (freed with free_host)."""
+        n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        p = C.c_void_p()
+        self._check(lib.tw_multi_alloc_host(self._h, i, n, C.byref(p)))
+        arr = np.frombuffer((C.c_char * n).from_address(p.value), dtype=dtype).reshape(shape)
+        arr._tw_ptr = p.value if hasattr(arr, "__dict__") else None
+        return arr, p
+
+    def free_host(self, p):
+        lib.tw_multi_free_host(self._h, p)
+
+    def _bands(self, outs):
+        assert len(outs) == self.n
+        return (C.c_void_p * self.n)(*[_ptr(o).value for o in outs])
+
+    def create_zvals_sharded(self, origins_xy, mesh_size, dx, dy, zvsize, hp, erosion_iters, ep, min_zval, out_bands, want_minmax=False):
+        """out_bands: one array / CUDA tensor per device for its band of tiles (multi_range). Returns (per-tile min/max or None, global (zmin, zmax))."""
+        org = np.ascontiguousarray(origins_xy, np.int32).reshape(-1, 2)
+        nt = org.shape[0]
+        mm = np.empty((nt, 2), np.float32) if want_minmax else None
+        zr = MinMax()
+        self._check(lib.tw_create_zvals_sharded(self._h, _ptr(org), nt, mesh_size[0], mesh_size[1], dx, dy, zvsize, C.byref(hp), erosion_iters, C.byref(ep), min_zval,
+                                                C.cast(self._bands(out_bands), C.c_void_p), _ptr(mm), C.byref(zr)))
+        return mm, (zr.zmin, zr.zmax)
+
+    def heightgen_2d_sharded(self, grid, hp, out_bands, enable_glaciate=1):
+        zr = MinMax()
+        self._check(lib.tw_heightgen_2d_sharded(self._h, C.byref(grid), C.byref(hp), int(enable_glaciate), C.cast(self._bands(out_bands), C.c_void_p), C.byref(zr)))
+        return zr.zmin, zr.zmax
+
+
 class Context:
     """One tw_ctx (device + stream + uploaded tables). All compute goes through the C ABI."""
 
@@ -247,6 +355,16 @@ class Context:
 
     def sync(self):
         self._check(lib.tw_sync(self._h))
+
+    # one process per GPU: the library's own NCCL communicator for the z-range reduction
+    def dist_init(self, nranks, rank, unique_id):
+        buf = C.create_string_buffer(bytes(unique_id), 128)
+        self._check(lib.tw_dist_init(self._h, nranks, rank, buf))
+
+    def dist_allreduce_minmax(self, zmin, zmax):
+        mm = MinMax(zmin, zmax)
+        self._check(lib.tw_dist_allreduce_minmax(self._h, C.byref(mm)))
+        return mm.zmin, mm.zmax
 
     def set_sine_params(self, sp):
         sp = np.ascontiguousarray(sp, np.float32)

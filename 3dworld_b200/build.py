@@ -8,7 +8,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "lib3dworld_b200.so")
-SOURCES = ["tw_api.cu", "tw_heightgen.cu", "tw_erosion.cu", "tw_voxel.cu", "tw_streaming.cu", "tw_tiles.cu", "tw_host.cpp"]
+SOURCES = ["tw_api.cu", "tw_heightgen.cu", "tw_erosion.cu", "tw_voxel.cu", "tw_streaming.cu", "tw_tiles.cu", "tw_multi.cu", "tw_host.cpp"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-fmad=false", "-prec-div=true", "-prec-sqrt=true",
               "-Xcompiler", "-fPIC,-ffp-contract=off,-fno-fast-math,-fvisibility=hidden", "--use_fast_math=false"]
 
@@ -28,10 +28,12 @@ def needs_build():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
-    if not force and not needs_build():
+def build(force=False, verbose=False, lib=None, objdir=None):
+    """lib / objdir (or TW_BUILD_LIB / TW_BUILD_OBJDIR): build a variant somewhere else without touching the shipped library (tools/ab_variants.sh)."""
+    lib = lib or os.environ.get("TW_BUILD_LIB") or LIB
+    if lib == LIB and not force and not needs_build():
         return LIB
-    objdir = os.path.join(HERE, "build")
+    objdir = objdir or os.environ.get("TW_BUILD_OBJDIR") or os.path.join(HERE, "build")
     os.makedirs(objdir, exist_ok=True)
     objs = []
     procs = []
@@ -47,9 +49,10 @@ def build(force=False, verbose=False):
             print(out)
         if p.returncode != 0:
             raise RuntimeError("nvcc failed for %s:\n%s" % (src, out))
-    cmd = [nvcc(), "-shared", "-Wno-deprecated-gpu-targets", "-o", LIB] + objs + ["-Xlinker", "--no-undefined", "-lcudart_static", "-lpthread", "-ldl", "-lrt"]
+    cmd = [nvcc(), "-shared", "-Wno-deprecated-gpu-targets", "-o", lib + ".tmp"] + objs + ["-Xlinker", "--no-undefined", "-lcudart_static", "-lpthread", "-ldl", "-lrt"]
     subprocess.check_call(cmd)
-    return LIB
+    os.replace(lib + ".tmp", lib)   # atomic: a concurrent snapshot of the tree never sees a half-written library
+    return lib
 
 
 if __name__ == "__main__":

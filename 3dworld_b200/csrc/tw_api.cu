@@ -113,6 +113,7 @@ int tw_create(int device, tw_ctx **out) {
 
 void tw_destroy(tw_ctx *ctx) {
 	if (!ctx) return;
+	if (ctx->dist) tw_dist_finalize(ctx);
 	cudaSetDevice(ctx->device);
 	cudaStreamSynchronize(ctx->stream);
 	for (int i = 0; i < 3; ++i) {if (ctx->d_scratch[i]) cudaFree(ctx->d_scratch[i]);}

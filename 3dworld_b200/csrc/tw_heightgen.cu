@@ -173,6 +173,9 @@ noise_grid_kernel(float *__restrict__ out, unsigned nx, unsigned ny, unsigned y_
 #ifndef TW_NOISE2_MIN_BLOCKS
 #define TW_NOISE2_MIN_BLOCKS 3   // 74 KB of table per block (tw_noise2.cuh, level 3) => 3 blocks per SM
 #endif
+#ifndef TW_NOISE2_PERSISTENT
+#define TW_NOISE2_PERSISTENT 0   // k > 0: single grids launch at most k waves of resident blocks, each striding over the chunk groups (table staged once per block)
+#endif
 #ifndef TW_NOISE2_THREADS
 #define TW_NOISE2_THREADS 256    // threads per block; (512, 2 blocks) = 32 warps per SM at 64 registers is the next experiment
 #endif
@@ -200,6 +203,30 @@ __device__ __forceinline__ float2 gen_noise2(float2 xv, float2 yv, const NoisePa
 	return zval;
 }
 
+#ifndef TW_NOISE2_DUAL
+#define TW_NOISE2_DUAL 0   // 1: the two independent fBm evaluations of each domain-warp stage (dx1|dy1, dx2|dy2) share one octave loop (2x the ILP per thread)
+#endif
+// two independent gen_noise2 evaluations in one octave loop: same operations per evaluation, interleaved by the compiler
+template<bool SIMPLEX, int SHAPE>
+__device__ __forceinline__ void gen_noise2_dual(float2 xa, float2 ya, float2 xb, float2 yb, const NoiseParams &N, unsigned L, float2 &za, float2 &zb) {
+	if (TW_SIMPLEX_LUT > 0 && noise_lattice_in_range(xa, ya, N) && noise_lattice_in_range(xb, yb, N)) {
+		float2 zva = make_float2(0.0f, 0.0f), zvb = make_float2(0.0f, 0.0f);
+#pragma unroll 1
+		for (int i = 0; i < N.octaves; ++i) {
+			float const f = N.freq[i], rx = N.rx[i], ry = N.ry[i], mag = N.mag[i];
+			float2 const pxa = twn2::add2(twn2::mul2(xa, f), rx), pya = twn2::add2(twn2::mul2(ya, f), ry);
+			float2 const pxb = twn2::add2(twn2::mul2(xb, f), rx), pyb = twn2::add2(twn2::mul2(yb, f), ry);
+			float2 na = SIMPLEX ? twn2::simplex2_lut(pxa, pya, L) : twn2::perlin2_lut(pxa, pya, L);
+			float2 nb = SIMPLEX ? twn2::simplex2_lut(pxb, pyb, L) : twn2::perlin2_lut(pxb, pyb, L);
+			if (SHAPE == 1) {na = make_float2((float)((double)fabsf(na.x) - 0.40), (float)((double)fabsf(na.y) - 0.40)); nb = make_float2((float)((double)fabsf(nb.x) - 0.40), (float)((double)fabsf(nb.y) - 0.40));}
+			if (SHAPE == 2) {na = make_float2((float)(0.45 - (double)fabsf(na.x)), (float)(0.45 - (double)fabsf(na.y))); nb = make_float2((float)(0.45 - (double)fabsf(nb.x)), (float)(0.45 - (double)fabsf(nb.y)));}
+			zva = twn2::fma2(na, mag, zva); zvb = twn2::fma2(nb, mag, zvb);
+		}
+		za = zva; zb = zvb;
+	}
+	else {za = gen_noise2<SIMPLEX, SHAPE>(xa, ya, N, L); zb = gen_noise2<SIMPLEX, SHAPE>(xb, yb, N, L);}
+}
+
 __device__ __forceinline__ float dadd(float a, double b) {return (float)((double)a + b);} // float + double literal, rounded back (src/mesh_gen.cpp:742-745)
 
 template<bool SIMPLEX, bool WARP, int SHAPE>
@@ -225,9 +252,14 @@ noise_grid2_kernel(float *__restrict__ out, unsigned nx, unsigned ny, unsigned y
 	size_t const c_end = (size_t)y_end*nx;
 	float lo = INFINITY, hi = -INFINITY;
 	constexpr unsigned NCH = WARP ? 1 : 4;
+	// blocks stride over the chunk groups of the band: with gridDim.x == number of groups every block does exactly one (the default); a smaller
+	// grid (TW_NOISE2_PERSISTENT: one wave of resident blocks) keeps the staged table for many chunks
+	size_t const ngroups = ((c_end - (size_t)y_off*nx + 1)/2 + (size_t)blockDim.x*NCH - 1)/((size_t)blockDim.x*NCH);
+#pragma unroll 1
+	for (size_t grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
 #pragma unroll 1
 	for (unsigned ch = 0; ch < NCH; ++ch) {
-	size_t const c0 = (size_t)y_off*nx + 2*(((size_t)blockIdx.x*NCH + ch)*blockDim.x + threadIdx.x);
+	size_t const c0 = (size_t)y_off*nx + 2*((grp*NCH + ch)*blockDim.x + threadIdx.x);
 	unsigned y, x;
 	if (c_end <= 0xffffffffull) {unsigned const c32 = (unsigned)c0; y = c32/nx; x = c32 - y*nx;} // 32-bit division for every grid below 2^32 cells
 	else {y = (unsigned)(c0/nx); x = (unsigned)(c0 - (size_t)y*nx);}
@@ -243,11 +275,20 @@ noise_grid2_kernel(float *__restrict__ out, unsigned nx, unsigned ny, unsigned y
 		float2 xv = mul2(xval, N.xy_scale), yv = mul2(yval, N.xy_scale);          // get_noise_zval, src/mesh_gen.cpp:737-738
 		if (WARP) { // domain warping, src/mesh_gen.cpp:740-747
 			float const scale = 0.2f;
-			float2 const dx1 = gen_noise2<SIMPLEX, SHAPE>(make_float2(dadd(xv.x, 0.0), dadd(xv.y, 0.0)), make_float2(dadd(yv.x, 0.0), dadd(yv.y, 0.0)), N, L);
-			float2 const dy1 = gen_noise2<SIMPLEX, SHAPE>(make_float2(dadd(xv.x, 5.2), dadd(xv.y, 5.2)), make_float2(dadd(yv.x, 1.3), dadd(yv.y, 1.3)), N, L);
+			float2 dx1, dy1, dx2, dy2;
+			if (TW_NOISE2_DUAL) {gen_noise2_dual<SIMPLEX, SHAPE>(make_float2(dadd(xv.x, 0.0), dadd(xv.y, 0.0)), make_float2(dadd(yv.x, 0.0), dadd(yv.y, 0.0)),
+			                                                     make_float2(dadd(xv.x, 5.2), dadd(xv.y, 5.2)), make_float2(dadd(yv.x, 1.3), dadd(yv.y, 1.3)), N, L, dx1, dy1);}
+			else {
+				dx1 = gen_noise2<SIMPLEX, SHAPE>(make_float2(dadd(xv.x, 0.0), dadd(xv.y, 0.0)), make_float2(dadd(yv.x, 0.0), dadd(yv.y, 0.0)), N, L);
+				dy1 = gen_noise2<SIMPLEX, SHAPE>(make_float2(dadd(xv.x, 5.2), dadd(xv.y, 5.2)), make_float2(dadd(yv.x, 1.3), dadd(yv.y, 1.3)), N, L);
+			}
 			float2 const wx = add2(xv, mul2(dx1, scale)), wy = add2(yv, mul2(dy1, scale));
-			float2 const dx2 = gen_noise2<SIMPLEX, SHAPE>(make_float2(dadd(wx.x, 1.7), dadd(wx.y, 1.7)), make_float2(dadd(wy.x, 9.2), dadd(wy.y, 9.2)), N, L);
-			float2 const dy2 = gen_noise2<SIMPLEX, SHAPE>(make_float2(dadd(wx.x, 8.3), dadd(wx.y, 8.3)), make_float2(dadd(wy.x, 2.8), dadd(wy.y, 2.8)), N, L);
+			if (TW_NOISE2_DUAL) {gen_noise2_dual<SIMPLEX, SHAPE>(make_float2(dadd(wx.x, 1.7), dadd(wx.y, 1.7)), make_float2(dadd(wy.x, 9.2), dadd(wy.y, 9.2)),
+			                                                     make_float2(dadd(wx.x, 8.3), dadd(wx.y, 8.3)), make_float2(dadd(wy.x, 2.8), dadd(wy.y, 2.8)), N, L, dx2, dy2);}
+			else {
+				dx2 = gen_noise2<SIMPLEX, SHAPE>(make_float2(dadd(wx.x, 1.7), dadd(wx.y, 1.7)), make_float2(dadd(wy.x, 9.2), dadd(wy.y, 9.2)), N, L);
+				dy2 = gen_noise2<SIMPLEX, SHAPE>(make_float2(dadd(wx.x, 8.3), dadd(wx.y, 8.3)), make_float2(dadd(wy.x, 2.8), dadd(wy.y, 2.8)), N, L);
+			}
 			xv = add2(xv, mul2(dx2, scale)); yv = add2(yv, mul2(dy2, scale));
 		}
 		float2 const zz = gen_noise2<SIMPLEX, SHAPE>(xv, yv, N, L);
@@ -269,6 +310,7 @@ noise_grid2_kernel(float *__restrict__ out, unsigned nx, unsigned ny, unsigned y
 	}
 	lo = fminf(lo, fminf(valid0 ? z0 : INFINITY, valid1 ? z1 : INFINITY)); hi = fmaxf(hi, fmaxf(valid0 ? z0 : -INFINITY, valid1 ? z1 : -INFINITY));
 	} // chunks
+	} // chunk groups
 	if (mm) {block_minmax(lo, hi, mm + 2*tile);}
 }
 
@@ -560,7 +602,11 @@ int twi_heightgen(tw_ctx *ctx, const tw_grid2d *g, const tw_height_params *p, in
 			if (!use_scalar) { // two cells per thread on packed fp32x2 instructions
 				size_t const band_cells = (size_t)(r1 - r0)*nx;
 				size_t const cells_per_block = 2*TW_NOISE2_THREADS*(size_t)((p->gen_mode == TW_MGEN_DWARP_GPU) ? 1 : 4); // noise_grid2_kernel: NCH chunks of blockDim threads x 2 cells
-				dim3 const block(TW_NOISE2_THREADS, 1, 1), grid((unsigned)((band_cells + cells_per_block - 1)/cells_per_block), 1, ntiles);
+				unsigned gx = (unsigned)((band_cells + cells_per_block - 1)/cells_per_block);
+#if TW_NOISE2_PERSISTENT
+				{unsigned const wave = 148u*TW_NOISE2_MIN_BLOCKS*TW_NOISE2_PERSISTENT; if (ntiles == 1 && gx > wave) gx = wave;} // TW_NOISE2_PERSISTENT waves' worth of resident blocks
+#endif
+				dim3 const block(TW_NOISE2_THREADS, 1, 1), grid(gx, 1, ntiles);
 				if (p->gen_mode == TW_MGEN_PERLIN) {launch_noise2<false, false>(p->gen_shape, grid, block, ctx->stream, d_out, nx, ny, r0, r1, mx0, my0, d_tile_origins, N, P, ctx->d_sin_table, d_mm_ord, lut);}
 				else if (warp) {launch_noise2<true, true >(p->gen_shape, grid, block, ctx->stream, d_out, nx, ny, r0, r1, mx0, my0, d_tile_origins, N, P, ctx->d_sin_table, d_mm_ord, lut);}
 				else           {launch_noise2<true, false>(p->gen_shape, grid, block, ctx->stream, d_out, nx, ny, r0, r1, mx0, my0, d_tile_origins, N, P, ctx->d_sin_table, d_mm_ord, lut);}

@@ -39,6 +39,7 @@ struct tw_ctx {
 	void  *h_pinned = nullptr;
 	size_t pinned_bytes = 0;
 	tw_async_state async;
+	void *dist = nullptr;        // tw_dist_state (tw_multi.cu): NCCL communicator of the one-process-per-GPU mode
 	unsigned skip_rect[4] = {0, 0, 0, 0}; // x0, y0, w, h of the cells twi_heightgen's packed noise kernels leave unwritten (set around AO context generation only)
 };
 

@@ -30,8 +30,9 @@ N_TILE = 8192
 WORKLOAD = "heightgen 8192x8192 tile, mesh_gen_mode 4 (domain-warped simplex), 8 octaves (mesh_freq_filter 1), fp32, glaciate + hmap sine"
 FLOP_PER_CELL = 5200.0    # fp32 pipe operations per cell (FMUL/FADD/FFMA each counted once, floor included): 40 simplex evaluations x ~128 (SASS count of
                           # the scalar kernel's loop) + epilogue; SURVEY.md section 8(d) estimated ~6.8 k with FMA counted twice
-FLOP_EXEC_PER_CELL = 2900.0   # fp32-pipe lane operations the shipped kernel actually executes per cell: the hash/gradient table replaces
-                          # both permutes and the gradient arithmetic by shared-memory look-ups (40 evaluations x ~70 + epilogue; see profiles/ for the pipe utilisation)
+FLOP_EXEC_PER_CELL = 2968.5   # fallback only: fp32 FMUL/FADD/FFMA lane operations the shipped kernel executes per cell. bench.py takes the number from
+                          # profiles/roofline_r02.json (ncu per-opcode executed counts of the SASS view, written by tools/ncu_summary.py --opcodes); this
+                          # constant is the round-1 capture's value (profiles/ncu_noise_grid2_l3_kernel_r01.json re-read with the same script)
 BYTES_PER_CELL = 4.0      # one fp32 store per cell, no reads
 
 
@@ -83,6 +84,47 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(rows[0][1]), "power_w_max": max(float(r[2]) for r in rows), "reasons": reasons, "samples": len(rows)}
 
 
+def host_cpu_info():
+    """Threads the CPU legs may really use (scheduler affinity capped by the cgroup CPU quota - NOT os.cpu_count(), which is the host's total
+    even when this process is confined to a slice of it), plus CPU model and physical core count."""
+    try:
+        aff = len(os.sched_getaffinity(0))
+    except AttributeError:
+        aff = os.cpu_count() or 1
+    quota = None
+    for path in ("/sys/fs/cgroup/cpu.max", "/sys/fs/cgroup/cpu/cpu.cfs_quota_us"):
+        try:
+            txt = open(path).read().split()
+            if path.endswith("cpu.max"):
+                if txt[0] != "max":
+                    quota = float(txt[0]) / float(txt[1])
+            else:
+                q = float(txt[0])
+                if q > 0:
+                    quota = q / float(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            break
+        except Exception:
+            continue
+    threads = max(1, min(aff, int(quota + 0.999)) if quota else aff)
+    model, phys, logical = "unknown", set(), 0
+    try:
+        pid = cid = None
+        for ln in open("/proc/cpuinfo"):
+            if ln.startswith("model name") and model == "unknown":
+                model = ln.split(":", 1)[1].strip()
+            elif ln.startswith("processor"):
+                logical += 1
+            elif ln.startswith("physical id"):
+                pid = ln.split(":", 1)[1].strip()
+            elif ln.startswith("core id"):
+                cid = ln.split(":", 1)[1].strip()
+                phys.add((pid, cid))
+    except Exception:
+        pass
+    return {"threads_used": threads, "affinity_cpus": aff, "cgroup_quota_cpus": quota, "logical_cpus": logical or (os.cpu_count() or 1),
+            "physical_cores": len(phys) or None, "cpu_model": model}
+
+
 def cpu_runner(cores, nx, ny):
     """The reference's own CPU path for the workload on an nx x ny window (build_arrays + enable_glaciate + eval_index over the grid):
     the unmodified reference objects (oracle/_ref) when the prebuilt library is present, else the plain-C oracle port."""
@@ -111,7 +153,8 @@ def reference_arm(args):
     """bench.py --impl reference: the reference's CPU implementation of the path on all host cores, bounded sample per step."""
     if int(os.environ.get("RANK", "0")) != 0:
         return
-    cores = os.cpu_count() or 1
+    hc = host_cpu_info()
+    cores = hc["threads_used"]
     nx, ny = 1024, 1024                     # bounded sample: 1 M cells of the same grid (rows/cols 0..1023 of the 8192^2 tile): 8 rows per thread on a
                                             # 128-thread host, ~0.1 s per step there - long enough for the OpenMP team to reach a steady rate
     kind, run = cpu_runner(cores, nx, ny)
@@ -122,18 +165,23 @@ def reference_arm(args):
         run()
     dt = time.perf_counter() - t0
     value = nx * ny * args.steps / dt
-    sample = "%dx%d-cell window of the 8192^2 grid per step, %d host threads" % (nx, ny, cores)
+    sample = ("%dx%d-cell window (rows/cols 0..%d) of the 8192^2 grid per step, %d OpenMP threads on %s (%s physical cores, %d logical, affinity %d); "
+              "a per-cell RATE on a bounded sample of the same grid, not the whole 8192^2 step" % (nx, ny, nx - 1, cores, hc["cpu_model"], hc["physical_cores"], hc["logical_cpus"], hc["affinity_cpus"]))
     print(json.dumps({
         "impl": "reference", "metric": "height cells/s @8192^2 8-octave domain-warp", "value": value, "unit": "cells/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": {"workload": WORKLOAD, "sample": sample},
-        "cpu_baseline": {"value": value, "unit": "cells/s", "cores": cores, "kind": kind, "sample": sample},
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "sample": sample, "cells_per_step": nx * ny, "same_grid_bounded_sample": True},
+        "cpu_baseline": dict({"value": value, "unit": "cells/s", "cores": cores, "kind": kind, "sample": sample}, **{k: hc[k] for k in ("cpu_model", "physical_cores", "logical_cpus", "affinity_cpus", "cgroup_quota_cpus")}),
         "e2e": {"value": value, "unit": "cells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
 
-def cpu_baseline_leg():
-    """Bounded CPU sample of the same workload (rank 0, N=1): ~10-20 s of CPU work on all host cores."""
-    cores = os.cpu_count() or 1
+def cpu_baseline_leg(gpu_map_8192=None):
+    """Bounded CPU samples of the same workloads (rank 0, N=1), the unmodified reference objects (oracle/_ref) when present, on the threads this
+    process may really use: the headline (config 2) plus configs 3, 4 and 5 AT THE SAME CONFIGURATION as the GPU rows (gpu_map_8192 = the GPU's
+    8192^2 simplex map, bit-identical to what the reference would generate, so the erosion input is the same)."""
+    hc = host_cpu_info()
+    cores = hc["threads_used"]
     nx, ny = 1024, 1024
     kind, run = cpu_runner(cores, nx, ny)
     run(128)
@@ -143,22 +191,57 @@ def cpu_baseline_leg():
     what = "unmodified reference objects (oracle/_ref)" if kind == "reference" else "plain-C oracle port"
     res = {"value": nx * ny / dt, "unit": "cells/s", "cores": cores, "kind": kind,
            "sample": "%s, %dx%d-cell window of the 8192^2 grid, OpenMP %d threads" % (what, nx, ny, cores)}
-    if kind == "reference":   # secondary: the reference's apply_erosion on one 2048^2 map (its OpenMP droplet loop on all threads, and 1 thread)
-        try:
-            import numpy as np
-            import refapi as R
-            n, iters = 2048, 200000
-            R.setup(mode=1, freq_filter=1, seed=1, zmax_est=2.3, hmap=HM_CFG)
-            z = R.heightgen(-n / 2, -n / 2, R.lib().ref_get_dx(), R.lib().ref_get_dy(), n, n, 0, 1)
-            zmin, zmax = float(z.min()), float(z.max())
-            for label, thr in (("openmp_%d_threads" % cores, cores), ("1_thread", 1)):
-                R.lib().ref_set_threads(thr)
+    res.update({k: hc[k] for k in ("cpu_model", "physical_cores", "logical_cpus", "affinity_cpus", "cgroup_quota_cpus")})
+    if kind != "reference":
+        return res
+    try:
+        import refapi as R
+        RL = R.lib()
+        # ---- config 3: apply_erosion on the 8192^2 map, 1000 / 1e5 (/ 1e6) droplets; 1 thread = the deterministic order the GPU reproduces bit for bit,
+        #      all threads = the reference's shipped OpenMP loop (racy, order-dependent output: a speed number only)
+        R.setup(mode=1, freq_filter=1, seed=1, zmax_est=2.3, hmap=HM_CFG)
+        if gpu_map_8192 is not None:
+            z = gpu_map_8192
+        else:
+            z = R.heightgen(-N_TILE / 2, -N_TILE / 2, RL.ref_get_dx(), RL.ref_get_dy(), N_TILE, N_TILE, 0, 1)
+        scene = importlib.import_module("3dworld_b200.scene")
+        ep = scene.SceneConfig(mesh_gen_mode=1, mesh_freq_filter=1, mesh_seed=1, hmap=HM_CFG, zmax_est=2.3).erosion_params()
+        zmin = float(z.min())
+        c3 = {"config": "apply_erosion on the 8192^2 8-octave simplex map (BASELINE config 3), same input and parameters as the GPU rows"}
+        for label, thr, counts in (("1_thread", 1, (1000, 100000)), ("openmp_%d_threads" % cores, cores, (1000, 100000, 1000000))):
+            RL.ref_set_threads(thr)
+            for n in counts:
                 t0 = time.perf_counter()
-                R.apply_erosion(z, zmin, iters, erode_amount=1.0, water_plane_z=zmin + 0.2 * (zmax - zmin), zmin=zmin, zmax=zmax, clip_hd1=0.083)
-                res["erosion_2048_map_%s_droplets_per_s" % label] = iters / (time.perf_counter() - t0)
-            R.lib().ref_set_threads(cores)
-        except Exception as e:   # noqa: BLE001 - secondary number only
-            res["erosion_note"] = "reference erosion timing failed: %s" % e
+                R.apply_erosion(z, zmin, n, erode_amount=ep.erode_amount, water_plane_z=ep.water_plane_z, half_dxy=ep.half_dxy, zmin=ep.zmin, zmax=ep.zmax,
+                                relh_adj_tex=ep.relh_adj_tex, clip_hd1=ep.clip_hd1)
+                c3["droplets_per_s_%s_%d_droplets" % (label, n)] = n / (time.perf_counter() - t0)
+        RL.ref_set_threads(cores)
+        res["config3_erosion_8192"] = c3
+        del z
+        # ---- config 4: 512^3 sine voxel density (noise_gen_3d + the create_procedural loop), all threads
+        vcfg = scene.SceneConfig(scene_size=(16.0, 16.0, 4.0), mesh_size=(128, 128, 64))
+        vp = scene.voxel_landscape_params(vcfg, 512, 512, 512)
+        nyv = 128                                # bounded: a 512 x 128 x 512 slab of the same grid (the loop is uniform in y)
+        t0 = time.perf_counter()
+        R.voxel_fill(512, nyv, 512, list(vp.lo_pos), list(vp.vsz), list(vp.offset), vp.mag, vp.freq, vp.normalize_to_1, vp.rseed1, vp.rseed2, 0, vp.zscale)
+        res["config4_voxels_512"] = {"voxels_per_s": 512 * nyv * 512 / (time.perf_counter() - t0), "sample": "512x%dx512 slab of the 512^3 grid, sine mode, %d threads" % (nyv, cores)}
+        # ---- config 5: per tile = 258^2 8-octave domain-warp generation + 1000 droplets (tile_t::create_zvals semantics); a sample of tiles spread over the 65536
+        R.setup(mode=4, freq_filter=1, seed=1, zmax_est=2.3, hmap=HM_CFG, mesh=(256, 256, 1))
+        cfg5 = scene.SceneConfig(mesh_gen_mode=4, mesh_freq_filter=1, mesh_seed=1, hmap=HM_CFG, zmax_est=2.3, mesh_size=(256, 256, 1))
+        ep5 = cfg5.erosion_params()
+        sample_tiles = [(tx * 256, ty * 256) for ty in range(4, 256, 36) for tx in range(7, 256, 62)]
+        dx, dy = RL.ref_get_dx(), RL.ref_get_dy()
+        t0 = time.perf_counter()
+        for x1, y1 in sample_tiles:
+            tz = R.heightgen(float(x1 - 128), float(y1 - 128), dx, dy, 258, 258, 0, 1)
+            R.apply_erosion(tz, ep5.zmin, 1000, erode_amount=ep5.erode_amount, water_plane_z=ep5.water_plane_z, half_dxy=ep5.half_dxy, zmin=ep5.zmin, zmax=ep5.zmax,
+                            relh_adj_tex=ep5.relh_adj_tex, clip_hd1=ep5.clip_hd1)
+        dt5 = time.perf_counter() - t0
+        res["config5_tiled_terrain"] = {"tiles_per_s": len(sample_tiles) / dt5, "cells_per_s": len(sample_tiles) * 258 * 258 / dt5, "droplets_per_s": len(sample_tiles) * 1000 / dt5,
+                                        "seconds_extrapolated_65536_tiles": 65536 * dt5 / len(sample_tiles),
+                                        "sample": "%d of the 65536 tiles (every 36th tile row, every 62nd column), generation + erosion per tile, %d threads" % (len(sample_tiles), cores)}
+    except Exception as e:   # noqa: BLE001 - secondary numbers only
+        res["secondary_note"] = "reference secondary timing failed: %s: %s" % (type(e).__name__, e)
     return res
 
 
@@ -184,7 +267,12 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     tw = importlib.import_module("3dworld_b200")
     scene = importlib.import_module("3dworld_b200.scene")
+    numa_bound = tw.bind_thread_to_device(local)   # pinned host buffers allocated below land on the GPU's own NUMA node (GPU0-3 / GPU4-7 hang off different sockets)
     ctx = tw.Context(local)
+    if world > 1:   # the library's own communicator: the z-range reduction of the path is an ncclAllReduce inside lib3dworld_b200.so, not a torch call
+        uid = [tw.dist_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        ctx.dist_init(world, rank, uid[0])
     stream = torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda", local))   # time on the stream the kernels are launched on
 
     cfg = scene.SceneConfig(mesh_gen_mode=4, mesh_freq_filter=1, mesh_seed=1, hmap=HM_CFG, zmax_est=2.3)
@@ -194,14 +282,13 @@ def main():
     cells = N_TILE * N_TILE
     d_out = torch.empty((N_TILE, N_TILE), dtype=torch.float32, device="cuda")
     mm = tw.MinMax()
-    zr = torch.zeros(2, dtype=torch.float32, device="cuda")
+    zrange = [0.0, 0.0]
 
     def step_device():
         ctx.heightgen_2d_launch(g, hp, 1, 0, d_out, mm)
         ctx.heightgen_2d_poll(wait=True)
         if world > 1:                       # global z-range (get_heightmap_z_range over all tiles): the only collective of the path
-            zr[0], zr[1] = -mm.zmin, mm.zmax
-            dist.all_reduce(zr, op=dist.ReduceOp.MAX)
+            zrange[0], zrange[1] = ctx.dist_allreduce_minmax(mm.zmin, mm.zmax)
 
     def barrier():
         torch.cuda.synchronize()
@@ -277,42 +364,72 @@ def main():
     hbm_peak, peak_kind, sm_max_mhz = peaks()
     kernel_ms = ms / args.steps            # one dominant kernel (noise_grid_kernel) per step
     achieved_gbs = BYTES_PER_CELL * cells / (kernel_ms * 1e-3) / 1e9
-    traffic = None
-    prof = os.path.join(ROOT, "profiles", "roofline_r01.json")
-    if os.path.exists(prof):
-        pj = json.load(open(prof))
-        traffic = pj.get("noise_grid2_kernel", pj.get("noise_grid_kernel", {})).get("dram_bytes_per_launch")
+    traffic, exec_ops, prof_src = None, FLOP_EXEC_PER_CELL, None
+    for prof in ("roofline_r02.json", "roofline_r01.json"):   # per-launch numbers of the dominant kernel from the committed ncu --set full capture (tools/ncu_summary.py)
+        pp = os.path.join(ROOT, "profiles", prof)
+        if os.path.exists(pp):
+            pj = json.load(open(pp))
+            k = pj.get("noise_grid2_kernel", pj.get("noise_grid_kernel", {}))
+            traffic = k.get("dram_bytes_per_launch")
+            exec_ops = k.get("fp32_mul_add_fma_lane_ops_per_unit", exec_ops)
+            prof_src = "profiles/" + prof
+            break
     sm_mhz = clocks.get("sm_mhz") or sm_max_mhz
     alu_peak = 148 * 128 * sm_mhz * 1e6   # fp32 lane-instructions/s at the clock observed during the run
     out = {
         "metric": "height cells/s @8192^2 8-octave domain-warp", "value": value, "unit": "cells/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "cells_per_step_per_gpu": cells, "parallelism": "tile-row per rank, no data-path collective (%d rank%s)" % (world, "s" if world > 1 else ""),
+        "config": {"workload": WORKLOAD, "cells_per_step_per_gpu": cells, "parallelism": "tile-row per rank, no data-path collective; z range = ncclAllReduce inside the library (%d rank%s)" % (world, "s" if world > 1 else ""),
+                   "host_numa_bound": bool(numa_bound),
                    "l2": "output 268 MB per step > 126 MB L2; the kernel reads no input arrays", "bit_exact_vs_reference": True},
         "gpu_launches": launches,
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "cells/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
                 "path": "tw_heightgen_2d_launch/poll with a pinned host output buffer"},
         "roofline": {"bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": achieved_gbs / hbm_peak, "traffic": traffic,
-                     "peak_kind": peak_kind, "kernel": "noise_grid2_kernel<simplex,warp> (two cells per thread, packed fp32x2, hash/gradient table in shared memory)", "algorithmic_bytes_per_cell": BYTES_PER_CELL,
+                     "peak_kind": peak_kind, "traffic_source": prof_src, "kernel": "noise_grid2_kernel<simplex,warp> (two cells per thread, packed fp32x2, hash/gradient table in shared memory)", "algorithmic_bytes_per_cell": BYTES_PER_CELL,
                      "note": "the kernel is FP32-pipe bound by construction (4 B/cell vs ~5.2 k fp32 operations/cell; SURVEY.md 8d): see 'alu' and profiles/",
                      "alu": {"achieved_fp32_ops_per_s": FLOP_PER_CELL * cells / (kernel_ms * 1e-3), "peak_fp32_lane_instr_per_s": alu_peak,
                              "frac": FLOP_PER_CELL * cells / (kernel_ms * 1e-3) / alu_peak, "flop_per_cell": FLOP_PER_CELL,
-                             "executed_fp32_ops_per_cell": FLOP_EXEC_PER_CELL, "frac_executed": FLOP_EXEC_PER_CELL * cells / (kernel_ms * 1e-3) / alu_peak,
+                             "executed_fp32_ops_per_cell": exec_ops, "frac_executed": exec_ops * cells / (kernel_ms * 1e-3) / alu_peak, "executed_ops_source": prof_src,
                              "note": "flop_per_cell = the reference algorithm's fp32 operations (what the CPU path executes); the kernel tabulates part of "
                                      "them, so frac (algorithmic) can exceed 1 while the FMA pipe itself is ~70 % busy (frac_executed, profiles/)"}},
     }
+    gpu_map = None
     if world == 1:
         if not args.no_extra:   # before the CPU leg, while the GPU clocks are still up
             try:
                 out["extra"] = extra_measurements(tw, scene, ctx, stream, torch)
+                gpu_map = out["extra"].pop("_map_8192", None)
             except Exception as e:          # noqa: BLE001 - secondary rows must not take the headline line down
                 out["extra"] = {"error": "%s: %s" % (type(e).__name__, e)}
             cfg5 = run_config5()
-        out["cpu_baseline"] = cpu_baseline_leg()
+        out["cpu_baseline"] = cpu_baseline_leg(gpu_map)
     if cfg5 is not None:
         out["config5_tiled_terrain"] = cfg5
+    # ---- the other two thirds of BASELINE.json's metric as first-class top-level scalars (the driver's record keeps only scalars of this level) ----
+    out["hbm_roofline_frac"] = achieved_gbs / hbm_peak
+    ex = out.get("extra") or {}
+    if "single_map_8192_serial_1000_droplets_per_s" in ex:
+        out["erosion_iters_per_s"] = ex["single_map_8192_serial_1000_droplets_per_s"]                 # config 3: 8192^2 map, 1000 droplets, the reference's serial order (bit-exact)
+        out["erosion_iters_per_s_1e5_droplets"] = ex.get("single_map_8192_serial_100000_droplets_per_s")
+        out["erosion_iters_per_s_openmp_mode_1e6_droplets"] = ex.get("single_map_8192_openmp_mode_1e6_droplets_per_s")
+        out["erosion_us_per_move"] = ex.get("single_map_8192_serial_100000_droplets_us_per_move")
+    if "voxel_sine_512_voxels_per_s" in ex:
+        out["voxels_per_s"] = ex["voxel_sine_512_voxels_per_s"]                                         # config 4
+    if cfg5 and "seconds" in cfg5:
+        out["config5_seconds"] = cfg5["seconds"]                                                        # config 5: 65536 tiles of 258^2, generation + 1000 droplets per tile
+        out["config5_cells_per_s"] = cfg5["cells_per_s"]
+        out["config5_erosion_iters_per_s"] = cfg5["droplets_per_s"]
+        if "strong_scaling_efficiency" in cfg5:
+            out["strong_scaling_speedup"] = cfg5["strong_scaling_speedup"]
+            out["strong_scaling_efficiency"] = cfg5["strong_scaling_efficiency"]
+    cb = out.get("cpu_baseline") or {}
+    c3 = cb.get("config3_erosion_8192") or {}
+    if c3 and out.get("erosion_iters_per_s"):
+        out["cpu_erosion_iters_per_s_1_thread"] = c3.get("droplets_per_s_1_thread_1000_droplets")
+        out["cpu_erosion_iters_per_s_1e5_droplets_1_thread"] = c3.get("droplets_per_s_1_thread_100000_droplets")
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
@@ -332,6 +449,20 @@ def config5_strong(tw, scene, ctx, torch, dist, rank, world, barrier, device="cu
     local = [0.0, 0.0, 1.0]                 # seconds of the timed pass, droplet moves, ok flag
     err = None
     tiles = None
+    t_single = None
+    if world > 1:                            # the N = 1 denominator of the strong-scaling efficiency, measured in THIS run: rank 0 does all tiles alone
+        if rank == 0:
+            try:
+                all_org = [((t % side) * 256, (t // side) * 256) for t in range(total)]
+                full = torch.empty((total, zv, zv), dtype=torch.float32, device=device)
+                ctx.create_zvals_batch(all_org, cfg.mesh_size, dxv, dyv, zv, hp, iters, ep, ep.zmin, out=full)   # warm-up (scratch allocation)
+                s0 = time.perf_counter()
+                ctx.create_zvals_batch(all_org, cfg.mesh_size, dxv, dyv, zv, hp, iters, ep, ep.zmin, out=full)
+                t_single = time.perf_counter() - s0
+                del full, all_org
+            except Exception as e:          # noqa: BLE001
+                t_single = None
+        barrier()
     try:
         tiles = torch.empty((t1 - t0, zv, zv), dtype=torch.float32, device=device)
         ctx.create_zvals_batch(origins, cfg.mesh_size, dxv, dyv, zv, hp, iters, ep, ep.zmin, out=tiles)   # warm-up pass (scratch allocation)
@@ -357,9 +488,12 @@ def config5_strong(tw, scene, ctx, torch, dist, rank, world, barrier, device="cu
     del tiles
     if ok < 1.0 or secs <= 0.0:
         return {"error": err or "a rank failed", "scaling": "strong"}
-    return {"workload": "%d tiles of 258^2 (65536^2 terrain), mode 4 8-octave + %d droplets per tile, fused tw_create_zvals_batch" % (total, iters),
-            "scaling": "strong", "tiles_per_rank": t1 - t0, "seconds": secs, "cells_per_s": total * zv * zv / secs,
-            "droplets_per_s": total * iters / secs, "droplet_moves_per_s": steps / secs}
+    res = {"workload": "%d tiles of 258^2 (65536^2 terrain), mode 4 8-octave + %d droplets per tile, fused tw_create_zvals_batch" % (total, iters),
+           "scaling": "strong", "tiles_per_rank": t1 - t0, "seconds": secs, "cells_per_s": total * zv * zv / secs,
+           "droplets_per_s": total * iters / secs, "droplet_moves_per_s": steps / secs}
+    if t_single:
+        res.update({"seconds_1_gpu_same_run": t_single, "strong_scaling_speedup": t_single / secs, "strong_scaling_efficiency": t_single / secs / world})
+    return res
 
 
 def extra_measurements(tw, scene, ctx, stream, torch):
@@ -436,7 +570,9 @@ def extra_measurements(tw, scene, ctx, stream, torch):
     base = torch.empty((N_TILE, N_TILE), dtype=torch.float32, device="cuda")
     _, (zmin, _zmax) = ctx.heightgen_2d(cfg.heightmap_grid(N_TILE, N_TILE), cfg.height_params(), out=base, want_minmax=True)
     work = torch.empty_like(base)
+    res["_map_8192"] = base.cpu().numpy()    # the CPU leg erodes the same map (popped by main(), never printed)
     for name, iters, fn in (("single_map_8192_serial_1000_droplets", 1000, lambda w, n: ctx.erode(w, zmin, n, ep)),
+                            ("single_map_8192_serial_100000_droplets", 100000, lambda w, n: ctx.erode(w, zmin, n, ep)),
                             ("single_map_8192_openmp_mode_1e6_droplets", 1000000, lambda w, n: ctx.erode_parallel(w, zmin, n, ep, 0))):
         for rep in range(2):
             work.copy_(base)
@@ -448,6 +584,7 @@ def extra_measurements(tw, scene, ctx, stream, torch):
         res[name + "_s"] = dt
         res[name + "_per_s"] = iters / dt
         res[name + "_moves_per_s"] = ctx.last_erosion_steps / dt
+        res[name + "_us_per_move"] = 1e6 * dt / max(1, ctx.last_erosion_steps)
     return res
 
 

@@ -287,6 +287,46 @@ TW_API int tw_heightmap_sample_tiles(tw_ctx *ctx, const uint8_t *data16, const t
 /* min/max over a float array (get_heightmap_z_range, src/map_view.cpp:399-407) */
 TW_API int tw_minmax_f32(tw_ctx *ctx, const float *vals, size_t n, tw_minmax *mm);
 
+
+/* ---------------------------------------------------------------------------------------------------------------------------------------
+ * Multi-GPU. The reference is one process with OpenMP threads and has no distributed layer; what it has is the tile loop of
+ * tile_draw_t::update (src/tiled_mesh.cpp:2367-2417) and the global z range get_heightmap_z_range (src/map_view.cpp:399-407). Tiles and row
+ * bands are pure functions of global cell coordinates + seed and every tile is eroded on its own, so the path shards with no data-path
+ * collective; the one reduction is the 2-float min/max, done INSIDE the library with ncclAllReduce over NVLink. libnccl.so.2 is loaded at run
+ * time (dlopen) only when a multi-GPU entry point is used: the single-GPU library has no NCCL dependency.
+ *
+ * (1) one process driving all GPUs of the box - what a 3DWorld integration (a single-process engine) would use: */
+typedef struct tw_multi tw_multi;  /* one tw_ctx + stream set per device, an NCCL communicator over them (ncclCommInitAll), one host worker thread per device */
+TW_API int  tw_multi_create(const int *devices, int ndev, tw_multi **out);   /* devices == NULL: devices 0..ndev-1; tables (tw_set_sin_table) are set up on every device */
+TW_API void tw_multi_destroy(tw_multi *m);
+TW_API int  tw_multi_size(const tw_multi *m);
+TW_API tw_ctx *tw_multi_ctx(tw_multi *m, int i);                              /* the per-device context, for single-device calls */
+TW_API const char *tw_multi_last_error(const tw_multi *m);
+TW_API int  tw_multi_set_sine_params(tw_multi *m, const float *sine_params450);
+/* the partition every sharded call uses: device i owns tiles / rows [n*i/ndev, n*(i+1)/ndev) - contiguous bands */
+TW_API void tw_multi_range(uint32_t n, int ndev, int i, uint32_t *begin, uint32_t *end);
+/* pinned host memory on the NUMA node of device i's PCIe root (allocated from a thread bound to the GPU's local CPUs): output buffers of the
+ * sharded calls should come from here - 8 concurrent device->host streams into memory of the wrong socket cost a third of the end-to-end rate */
+TW_API int  tw_multi_alloc_host(tw_multi *m, int i, size_t bytes, void **ptr);
+TW_API void tw_multi_free_host(tw_multi *m, void *ptr);
+/* tile_t::create_zvals for a batch of tiles dealt out over the devices (tw_create_zvals_batch on each device's band, concurrently).
+ * out_bands: ndev pointers, one per band (host or device memory of ANY kind, e.g. from tw_multi_alloc_host, or device i's own memory), band i =
+ * tiles tw_multi_range(ntiles, ndev, i); mm (optional, HOST, ntiles); zrange (optional, HOST) = min/max over ALL tiles, reduced with ncclAllReduce. */
+TW_API int  tw_create_zvals_sharded(tw_multi *m, const int32_t *origins_xy, uint32_t ntiles, int mesh_x_size, int mesh_y_size, float dx, float dy,
+                             uint32_t zvsize, const tw_height_params *p, uint32_t erosion_iters, const tw_erosion_params *ep, float min_zval,
+                             float *const *out_bands, tw_minmax *mm, tw_minmax *zrange);
+/* mesh_xy_grid_cache_t::build_arrays + eval_index over ONE nx*ny grid split into ndev row bands (heightmap_t::proc_gen's fill, sharded):
+ * band i = rows tw_multi_range(g->ny, ndev, i), out_bands[i] receives rows*nx floats; zrange as above. */
+TW_API int  tw_heightgen_2d_sharded(tw_multi *m, const tw_grid2d *g, const tw_height_params *p, int enable_glaciate, float *const *out_bands, tw_minmax *zrange);
+/* (2) one process per GPU (torchrun / mpirun style): rank 0 makes an id, every rank passes it to tw_dist_init on its own context */
+TW_API int  tw_dist_unique_id(char id128[128]);
+TW_API int  tw_dist_init(tw_ctx *ctx, int nranks, int rank, const char id128[128]);
+TW_API int  tw_dist_allreduce_minmax(tw_ctx *ctx, tw_minmax *inout);          /* global z range over all ranks (blocking) */
+TW_API void tw_dist_finalize(tw_ctx *ctx);
+/* binds the CALLING thread to the CPUs local to `device` (sysfs local_cpulist of its PCI function), so that pinned buffers it allocates next
+ * are NUMA-local to that GPU; returns TW_OK or TW_ERR_ARG when the topology is not exposed (then nothing changes) */
+TW_API int  tw_bind_thread_to_device(int device);
+
 #ifdef __cplusplus
 }
 #endif

@@ -11,11 +11,10 @@ names=()
 while [ $# -ge 2 ]; do
   name=$1; flags=$2; shift 2
   echo "== building $name: $flags"
-  TW_EXTRA_NVCC_FLAGS="$flags" python 3dworld_b200/build.py --force > /dev/null
-  cp 3dworld_b200/lib3dworld_b200.so "tools/ab/lib_$name.so"
+  TW_EXTRA_NVCC_FLAGS="$flags" TW_BUILD_LIB="$PWD/tools/ab/lib_$name.so" TW_BUILD_OBJDIR="$PWD/tools/ab/obj_$name" python 3dworld_b200/build.py --force > /dev/null
+  rm -rf "tools/ab/obj_$name"
   names+=("$name")
 done
-python 3dworld_b200/build.py --force > /dev/null   # leave the default build in place
 echo "run on the GPU box:"
-echo "gpurun --timeout 900 -- 'for v in ${names[*]}; do cp tools/ab/lib_\$v.so 3dworld_b200/lib3dworld_b200.so; echo == \$v; python -m pytest tests/test_gpu_heightgen.py -x -q | tail -1; python bench.py --kernel-only --steps 10 --warmup 3 | cut -c1-160; done'"
+echo "gpurun --timeout 900 -- 'cp 3dworld_b200/lib3dworld_b200.so /tmp/lib_shipped.so; for v in ${names[*]}; do cp tools/ab/lib_\$v.so 3dworld_b200/lib3dworld_b200.so; echo == \$v; python -m pytest tests/test_gpu_heightgen.py -x -q | tail -1; python bench.py --kernel-only --steps 10 --warmup 3 | cut -c1-160; done'"
 echo "(remove tools/ab/ afterwards: every library adds ~7 MB to each push)"
