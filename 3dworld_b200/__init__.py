@@ -99,7 +99,7 @@ ABI_SYMBOLS = ["tw_abi_version", "tw_create", "tw_destroy", "tw_last_error", "tw
                "tw_heightmap_from_floats_u16", "tw_heightmap_to_floats_u16", "tw_proc_gen_heightmap", "tw_heightmap_sample_tiles", "tw_minmax_f32",
                "tw_multi_create", "tw_multi_destroy", "tw_multi_size", "tw_multi_ctx", "tw_multi_last_error", "tw_multi_set_sine_params", "tw_multi_range",
                "tw_multi_alloc_host", "tw_multi_free_host", "tw_create_zvals_sharded", "tw_heightgen_2d_sharded", "tw_dist_unique_id", "tw_dist_init",
-               "tw_dist_allreduce_minmax", "tw_dist_finalize", "tw_bind_thread_to_device"]
+               "tw_dist_allreduce_minmax", "tw_dist_finalize", "tw_bind_thread_to_device", "tw_erode_sweeps", "tw_erode_sweeps_sharded"]
 
 
 def _load():
@@ -176,6 +176,8 @@ def _load():
     L.tw_create_zvals_sharded.argtypes = [vp, vp, C.c_uint32, C.c_int, C.c_int, C.c_float, C.c_float, C.c_uint32, C.POINTER(HeightParams), C.c_uint32,
                                           C.POINTER(ErosionParams), C.c_float, vp, vp, C.POINTER(MinMax)]
     L.tw_heightgen_2d_sharded.argtypes = [vp, C.POINTER(Grid2D), C.POINTER(HeightParams), C.c_int, vp, C.POINTER(MinMax)]
+    L.tw_erode_sweeps.argtypes = [vp, vp, C.c_int, C.c_int, C.c_float, C.c_uint32, C.POINTER(ErosionParams), C.c_uint32, C.c_int, C.POINTER(C.c_uint64)]
+    L.tw_erode_sweeps_sharded.argtypes = [vp, vp, C.c_int, C.c_int, C.c_float, C.c_uint32, C.POINTER(ErosionParams), C.c_uint32, C.c_int, C.POINTER(C.c_uint64)]
     L.tw_dist_unique_id.argtypes = [vp]
     L.tw_dist_init.argtypes = [vp, C.c_int, C.c_int, vp]
     L.tw_dist_allreduce_minmax.argtypes = [vp, C.POINTER(MinMax)]
@@ -311,6 +313,12 @@ class Multi:
         self._check(lib.tw_create_zvals_sharded(self._h, _ptr(org), nt, mesh_size[0], mesh_size[1], dx, dy, zvsize, C.byref(hp), erosion_iters, C.byref(ep), min_zval,
                                                 C.cast(self._bands(out_bands), C.c_void_p), _ptr(mm), C.byref(zr)))
         return mm, (zr.zmin, zr.zmax)
+
+    def erode_sweeps_sharded(self, bands, xsize, ysize, min_zval, num_iters, ep, sweep, halo):
+        """Coherent batched erosion of one map held as row bands (in place; one band per device: numpy arrays or that device's CUDA tensors)."""
+        moves = C.c_uint64()
+        self._check(lib.tw_erode_sweeps_sharded(self._h, C.cast(self._bands(bands), C.c_void_p), xsize, ysize, min_zval, num_iters, C.byref(ep), sweep, halo, C.byref(moves)))
+        return moves.value
 
     def heightgen_2d_sharded(self, grid, hp, out_bands, enable_glaciate=1):
         zr = MinMax()
@@ -483,6 +491,13 @@ class Context:
         ys, xs = h.shape
         self._check(lib.tw_erode_parallel(self._h, _ptr(h), xs, ys, min_zval, num_iters, C.byref(ep), num_threads))
         return h
+
+    def erode_sweeps(self, h, min_zval, num_iters, ep, sweep, halo):
+        """The coherent batched erosion on one device (see tw_erode_sweeps); in place, returns the droplet moves."""
+        ys, xs = h.shape
+        moves = C.c_uint64()
+        self._check(lib.tw_erode_sweeps(self._h, _ptr(h), xs, ys, min_zval, num_iters, C.byref(ep), sweep, halo, C.byref(moves)))
+        return moves.value
 
     def erode_tiles(self, tiles, num_iters, ep, min_zvals=None, min_zval_all=0.0):
         nt, ys, xs = tiles.shape

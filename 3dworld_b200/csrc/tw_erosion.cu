@@ -115,7 +115,19 @@ struct Rng {
 //             is built in shared memory straight from the caller's un-padded tile (the PAD = 4 clamped border, src/erosion.cpp:31-37, is
 //             replicated in shared memory), all droplets walk it there, and the interior is written back once with the min_zval clamp
 //             (:158-162). No padded scratch copy, no pad/unpad kernels: DRAM traffic = read the tile once + write it once.
-enum {M_GLOBAL = 0, M_ATOMIC = 1, M_WINDOW = 2, M_WHOLE = 3};
+//   M_FROZEN  (tw_erode_sweeps*) the coherent batched variant for ONE map sharded over GPUs (north_star "halo exchange between erosion
+//             sweeps"; no reference counterpart): the droplets of a sweep all read the map as it was at the start of the sweep and accumulate
+//             their deposits/erosions into a 64-bit FIXED-POINT delta buffer (2^-40 units, integer atomics: associative, hence independent of
+//             thread order AND of how the rows are split over devices); the host adds the deltas to the map between sweeps. A droplet must
+//             still see its OWN writes (the walk relies on that feedback: a droplet in a pit fills it and stops - on a frozen map it would
+//             bounce for thousands of moves): it keeps a private VIEW x VIEW window in shared memory = sweep-start heights + its own writes,
+//             re-read from the sweep-start map (re-centred ahead of its heading, exactly as M_WINDOW does) whenever it walks out of it. A device stores the
+//             padded rows [row0, row0 + rows) (its band +- halo), walks only droplets that start in its own rows [own0, own1), and a droplet
+//             ends once it is more than halo_rule rows from its start row (so it never leaves the band +- halo) - a rule of the algorithm
+//             itself, applied on one GPU too, which makes the sharded result bit-identical to the single-GPU one.
+enum {M_GLOBAL = 0, M_ATOMIC = 1, M_WINDOW = 2, M_WHOLE = 3, M_FROZEN = 4};
+constexpr int TW_SWEEP_VIEW = 32; // M_FROZEN: side of a droplet's private view (part of the algorithm's definition, see tw3d.h)
+constexpr double FIXED_ONE = 1099511627776.0; // 2^40 delta units per height unit
 
 struct DArgs {
 	float *padded;              // M_GLOBAL / M_ATOMIC / M_WINDOW: padded heightmaps [tile][NY][NX] (M_ATOMIC: the one map)
@@ -134,13 +146,19 @@ struct DArgs {
 	int WX, WY, P;              // M_WINDOW / M_WHOLE: window extent and row pitch in floats (M_WHOLE: WX = NX, WY = NY)
 	unsigned win_elems;         // floats of shared memory per lane group
 	unsigned win_min_moves;     // M_WINDOW: a droplet gets a window once it has survived this many moves (ocean droplets die in one)
+	// M_FROZEN: this device's band of the padded map
+	long long *delta;           // fixed-point deltas, same layout as `padded` (rows [row0, row0 + band rows))
+	int row0, own0, own1;       // first stored padded row; droplets starting in padded rows [own0, own1) are walked here
+	int halo_rule;              // a droplet ends when |zi - start row| exceeds this
+	unsigned it0, it1;          // droplets [it0, it1) = this sweep
 };
 
 template<int G, int MODE>
 __global__ void __launch_bounds__(128)
 droplet_kernel(DArgs const A)
 {
-	constexpr bool SHARED = (MODE == M_ATOMIC), WIN = (MODE == M_WINDOW), WHOLE = (MODE == M_WHOLE);
+	constexpr bool SHARED = (MODE == M_ATOMIC), FROZEN = (MODE == M_FROZEN), WIN = (MODE == M_WINDOW || MODE == M_FROZEN), WHOLE = (MODE == M_WHOLE);
+	// M_FROZEN shares M_WINDOW's machinery: the window is the droplet's PRIVATE view (sweep-start heights + its own writes); see hadd
 	constexpr int TPW = 32/G; // heightmaps per warp
 	extern __shared__ __align__(16) float tw_smem[];
 	int const lane = threadIdx.x & 31, sub = lane % G, grp = lane / G;
@@ -151,7 +169,10 @@ droplet_kernel(DArgs const A)
 	unsigned const gmask = (G == 32) ? 0xffffffffu : (((1u << (G & 31)) - 1u) << (grp*G));
 	int const xsize = A.xsize, ysize = A.ysize;
 	int const NX = xsize + 2*PAD, NY = ysize + 2*PAD;
-	float *mh = (MODE == M_WHOLE) ? nullptr : A.padded + (SHARED ? (size_t)0 : (size_t)tile*NX*NY);
+	float *mh = (MODE == M_WHOLE) ? nullptr : (FROZEN ? A.padded - (ptrdiff_t)A.row0*NX : A.padded + (SHARED ? (size_t)0 : (size_t)tile*NX*NY)); // FROZEN: indexed by global padded row
+	long long *dl64 = FROZEN ? A.delta - (ptrdiff_t)A.row0*NX : nullptr;
+	unsigned const fz_stride = FROZEN ? A.nslots : 0u;
+	int zstart = 0;
 	float const Kq=10, Kw=0.001f, Kr=0.9f, Kd=0.02f, Ki=0.1f, minSlope=0.05f, g=20, Kg=g*2;
 	unsigned const MAX_PATH_LEN = 4u*(unsigned)NX*(unsigned)NY;
 	float const erode_amount = A.E.erode_amount;
@@ -160,7 +181,7 @@ droplet_kernel(DArgs const A)
 	unsigned long long steps = 0;
 	bool const have_tile = active;
 	bool in_droplet = false;
-	unsigned iter = 0, numMoves = 0;
+	unsigned iter = (MODE == M_FROZEN) ? A.it0 + gslot : 0u, numMoves = 0; // M_FROZEN: group g walks droplets it0 + g, it0 + g + groups, ... of the sweep
 	Rng rgen; rgen.s1 = rgen.s2 = 1;
 	int xi = 0, zi = 0;
 	float xp=0, zp=0, xf=0, zf=0, s=0, v=0, w=1, dx=0, dz=0, h=0, h00=0, h10=0, h01=0, h11=0;
@@ -200,7 +221,15 @@ droplet_kernel(DArgs const A)
 		float *p = mh + ((size_t)NX*z + x);
 		if (WIN && have_win) {
 			unsigned const rx = (unsigned)(x - wx0), rz = (unsigned)(z - wz0);
-			if (rx < (unsigned)WX && rz < (unsigned)WY) {float *q = win + (rz*P + rx); float const nv = *q + delta; *q = nv; *p = nv; return;}
+			if (rx < (unsigned)WX && rz < (unsigned)WY) {
+				float *q = win + (rz*P + rx); float const nv = *q + delta; *q = nv; // the droplet sees its own write
+				if (!FROZEN) {*p = nv; return;}                                     // M_WINDOW: write through
+			}
+		}
+		if (FROZEN) { // everybody else sees it after the sweep: fixed-point accumulation; NaN / inf / absurd deltas contribute nothing (same rule in the oracle)
+			long long const q = (fabsf(delta) < 1048576.0f) ? __double2ll_rn((double)delta*FIXED_ONE) : 0ll;
+			if (q) {atomicAdd((unsigned long long *)(dl64 + ((size_t)NX*z + x)), (unsigned long long)q);}
+			return;
 		}
 		if (SHARED) {atomicAdd(p, delta);} else {*p += delta;}
 	};
@@ -223,24 +252,29 @@ droplet_kernel(DArgs const A)
 				if (sub == 0) {nd = atomicAdd(A.next_droplet, 1u);}
 				iter = __shfl_sync(gmask, nd, grp*G);
 			}
-			if (iter >= num_iters) {active = false;}
+			if (iter >= (FROZEN ? A.it1 : num_iters)) {active = false;}
 			else {
 				rgen.s1 = (int)iter + 11; rgen.s2 = 79*(int)iter + 121;
 				xi = PAD + (rgen.rand()%xsize);
 				zi = PAD + (rgen.rand()%ysize);
-				xp=xi; zp=zi; xf=0; zf=0; s=0; v=0; w=1; dx=0; dz=0;
-				h=hread(xi, zi); h00=h; h10=hread(xi+1, zi); h01=hread(xi, zi+1); h11=hread(xi+1, zi+1);
-				numMoves = 0; in_droplet = true; ++iter;
+				if (FROZEN && (zi < A.own0 || zi >= A.own1)) {iter += fz_stride;} // another device's droplet
+				else {
+					xp=xi; zp=zi; xf=0; zf=0; s=0; v=0; w=1; dx=0; dz=0;
+					h=hread(xi, zi); h00=h; h10=hread(xi+1, zi); h01=hread(xi, zi+1); h11=hread(xi+1, zi+1);
+					numMoves = 0; in_droplet = true; zstart = zi;
+					if (FROZEN) {iter += fz_stride; have_win = false;} else {++iter;} // M_FROZEN: a new droplet knows nothing of the previous one's writes
+				}
 			}
 		}
 		if (!__any_sync(0xffffffffu, active)) break;
-		if (!active) continue;
+		if (!active || !in_droplet) continue;
+		if (FROZEN && (unsigned)(zi - zstart + A.halo_rule) > 2u*(unsigned)A.halo_rule) {in_droplet = false; continue;} // left the band +- halo: the droplet ends (rule of the batched algorithm)
 		if (numMoves >= MAX_PATH_LEN) {in_droplet = false; continue;} // "droplet path is too long" (src/erosion.cpp:153)
 		++numMoves; ++steps;
 		if (WIN) { // keep the cells one move can touch - brush [xi-1, xi+2], next corners within +-2 of xi - inside the window
 			int const cx = clampi(xi, NX-1), cz = clampi(zi, NY-1);
 			bool const covered = have_win && max(cx - 2, 0) >= wx0 && min(cx + 3, NX-1) < wx0 + WX && max(cz - 2, 0) >= wz0 && min(cz + 3, NY-1) < wz0 + WY;
-			if (!covered && numMoves > A.win_min_moves) { // re-centre ahead of the droplet's heading (dx, dz = unit direction of the last move) and re-load
+			if (!covered && (FROZEN || numMoves > A.win_min_moves)) { // re-centre ahead of the droplet's heading (dx, dz = unit direction of the last move) and re-load
 				wx0 = max(0, min(cx - WX/2 + __float2int_rn(dx*(float)(WX/2 - 5)), NX - WX));
 				wz0 = max(0, min(cz - WY/2 + __float2int_rn(dz*(float)(WY/2 - 5)), NY - WY));
 				__syncwarp(gmask); // the group's earlier write-throughs are ordered before the loads below
@@ -248,7 +282,7 @@ droplet_kernel(DArgs const A)
 				for (int r = 0; r < WY; ++r) {
 					const float *src = mh + ((size_t)NX*(wz0 + r) + wx0);
 					float *dst = win + r*P;
-					for (int c = sub; c < WX; c += G) {dst[c] = __ldcg(src + c);}
+					for (int c = sub; c < WX; c += G) {dst[c] = FROZEN ? __ldg(src + c) : __ldcg(src + c);}
 				}
 				__syncwarp(gmask);
 				have_win = true;
@@ -367,6 +401,8 @@ droplet_kernel(DArgs const A)
 	if (sub == 0 && A.steps_out && steps) {atomicAdd(A.steps_out, steps);}
 }
 
+constexpr size_t SMEM_MAX_BLOCK = 227u*1024u; // sm_100: 227 KB of dynamic shared memory per block
+
 template<int G, int MODE>
 void launch_droplets(cudaStream_t st, DArgs const &A, unsigned warps_per_block, size_t smem_per_group) {
 	unsigned const groups_per_block = warps_per_block*(32/G);
@@ -377,6 +413,7 @@ void launch_droplets(cudaStream_t st, DArgs const &A, unsigned warps_per_block, 
 
 template<int MODE>
 void launch_droplets_g(int G, cudaStream_t st, DArgs const &A, unsigned warps_per_block, size_t smem_per_group) {
+	while (G < 32 && (size_t)(32/G)*warps_per_block*smem_per_group > SMEM_MAX_BLOCK) {G *= 2;} // fewer maps per warp until their windows fit in one block's shared memory
 	switch (G) {
 	case 1:  launch_droplets<1,  MODE>(st, A, warps_per_block, smem_per_group); break;
 	case 2:  launch_droplets<2,  MODE>(st, A, warps_per_block, smem_per_group); break;
@@ -406,7 +443,6 @@ int pick_smem_group() {
 	return (g == 1 || g == 2 || g == 4 || g == 8 || g == 16) ? g : 32;
 }
 
-constexpr size_t SMEM_MAX_BLOCK = 227u*1024u; // sm_100: 227 KB of dynamic shared memory per block
 
 // row pitch of the whole-map layout: the smallest P >= NX whose four brush rows start >= 4 banks apart (the 4x4 brush is then conflict-free);
 // kept at NX when padding would push the map over the shared-memory budget
@@ -446,20 +482,26 @@ static EParams make_eparams(const tw_erosion_params *p) {
 }
 
 // ---- which mode walks a batch (see the kernel comment) ----
-// M_WHOLE for batches of on-chip-sized maps small enough that per-map latency, not machine throughput, decides (the streaming case: the
-// reference creates <= 16 tiles per frame, src/tiled_mesh.cpp:2403-2417): 148 SMs x 3 resident 76 KB maps = 444 walkers.
+// M_WHOLE for batches of on-chip-sized maps up to 4 waves of resident walkers (148 SMs x 3 resident 76 KB maps = 444; the streaming case - the
+// reference creates <= 16 tiles per frame, src/tiled_mesh.cpp:2403-2417). Measured (profiles/erosion_modes_r02.txt): same speed as M_GLOBAL up to
+// 1776 tiles of 130^2 (0.081 s both; a 128^2 map 0.67 vs 0.74 us per move) with no padded scratch copy and no pad/unpad passes - each tile is read
+// once and written once; at 8192 tiles the global mode's thousands of resident warps win 2x, so larger batches go there.
 static bool plan_whole(uint32_t nt, int xsize, int ysize) {
 	int const NX = xsize + 2*PAD, NY = ysize + 2*PAD, mode = env_mode();
 	if ((size_t)whole_pitch(NX, NY)*NY*sizeof(float) > SMEM_MAX_BLOCK) return false;
 	if (mode == EM_WHOLE) return true;
 	return (mode == EM_AUTO && nt <= (uint32_t)env_int("TW_EROSION_WHOLE_MAX", 148*3*4));
 }
-// M_WINDOW for the `heavy` first slots of the heaviest-first schedule (all of them for small batches), M_GLOBAL for the rest
+// M_WINDOW for the `heavy` first slots of the heaviest-first schedule, M_GLOBAL for the rest. MEASURED on B200 (tools/bench_erosion_modes.py,
+// profiles/erosion_modes_r02.txt): the window never pays - a single 8192^2 map walks at 0.77 us per move from L1/L2 and at 1.3-1.8 us through the
+// window; 8192 tiles of 258^2 take 0.085 s (global) vs 0.144 s (window). One move is ~233 dependent instructions of ONE warp at ~6 cycles each:
+// the serial chain is bound by instruction latency, not by where the heights live, and the window's bookkeeping adds instructions to it. So the
+// default is 0 (never); the mode stays selectable (TW_EROSION_MODE=window, TW_EROSION_HEAVY, TW_EROSION_WINDOW_ALL) and parity-tested.
 static uint32_t plan_heavy(uint32_t nt) {
 	int const mode = env_mode();
 	if (mode == EM_GLOBAL) return 0;
 	if (mode == EM_WINDOW) return nt;
-	uint32_t const all_below = (uint32_t)env_int("TW_EROSION_WINDOW_ALL", 148*16), heavy = (uint32_t)env_int("TW_EROSION_HEAVY", 148*8);
+	uint32_t const all_below = (uint32_t)env_int("TW_EROSION_WINDOW_ALL", 0), heavy = (uint32_t)env_int("TW_EROSION_HEAVY", 0);
 	return (nt <= all_below) ? nt : (heavy < nt ? heavy : nt);
 }
 
@@ -625,5 +667,77 @@ int twi_erode(tw_ctx *ctx, float *d_maps, uint32_t ntiles, int xsize, int ysize,
 	TW_CUDA(ctx, cudaMemcpyAsync(&h_steps, d_steps, sizeof(h_steps), cudaMemcpyDeviceToHost, ctx->stream));
 	TW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
 	ctx->last_erosion_steps = h_steps;
+	return TW_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ coherent batched erosion (tw_erode_sweeps*)
+// Building blocks of the sweep algorithm (M_FROZEN above) for one device's band of the padded map; everything is enqueued on ctx->stream.
+namespace {
+// P[Y - E0][X] = U[clamp(Y - PAD) - u0][clamp(X - PAD)]: the clamped PAD border of src/erosion.cpp:31-37 for the stored rows [E0, E0 + rows)
+__global__ void sweep_pad_kernel(const float *__restrict__ U, int u0, int xsize, int ysize, int E0, int rows, int NX, float *__restrict__ P) {
+	int const X = blockIdx.x*blockDim.x + threadIdx.x, r = blockIdx.y;
+	if (X >= NX || r >= rows) return;
+	int const sy = clampi(E0 + r - PAD, ysize - 1), sx = clampi(X - PAD, xsize - 1);
+	P[(size_t)r*NX + X] = __ldg(U + (size_t)(sy - u0)*xsize + sx);
+}
+__global__ void sweep_add_kernel(long long *__restrict__ D, const long long *__restrict__ R, size_t n) { // deltas received from a neighbour: integer sum, exact
+	size_t const i = (size_t)blockIdx.x*blockDim.x + threadIdx.x;
+	if (i < n) {D[i] += R[i];}
+}
+__global__ void sweep_apply_kernel(float *__restrict__ P, long long *__restrict__ D, size_t n) { // map += deltas (one conversion, one fp32 add per cell), deltas = 0
+	size_t const i = (size_t)blockIdx.x*blockDim.x + threadIdx.x;
+	if (i < n) {
+		long long const d = D[i];
+		if (d) {P[i] = P[i] + (float)((double)d*(1.0/FIXED_ONE)); D[i] = 0;}
+		else   {P[i] = P[i] + 0.0f;} // the oracle adds unconditionally: -0.0 + 0.0 = +0.0
+	}
+}
+// out[y - y0][x] = max(min_zval, P[(y + PAD) - E0][x + PAD]) for the owned un-padded rows [y0, y1) (src/erosion.cpp:158-162)
+__global__ void sweep_unpad_kernel(const float *__restrict__ P, int E0, int NX, int xsize, int y0, int y1, float min_zval, float *__restrict__ out) {
+	int const x = blockIdx.x*blockDim.x + threadIdx.x, y = y0 + blockIdx.y;
+	if (x >= xsize || y >= y1) return;
+	out[(size_t)(y - y0)*xsize + x] = smax(min_zval, P[(size_t)(y + PAD - E0)*NX + x + PAD]);
+}
+} // namespace
+
+int twi_sweep_pad(tw_ctx *ctx, const float *U, int u0, int xsize, int ysize, int E0, int rows, float *P) {
+	int const NX = xsize + 2*PAD;
+	sweep_pad_kernel<<<dim3((NX + 255)/256, rows), 256, 0, ctx->stream>>>(U, u0, xsize, ysize, E0, rows, NX, P);
+	TW_LAUNCH_CHECK(ctx);
+	return TW_OK;
+}
+int twi_sweep_view() {return TW_SWEEP_VIEW;}
+int twi_sweep_walk(tw_ctx *ctx, float *P, long long *D, int xsize, int ysize, int E0, int own0, int own1, int halo_rule, unsigned it0, unsigned it1,
+                   const tw_erosion_params *p, unsigned long long *d_steps)
+{
+	if (!ctx->d_dir_table) return tw_set_error(ctx, TW_ERR_STATE, "tw_set_sin_table() has not been called");
+	DArgs A;
+	memset(&A, 0, sizeof(A));
+	A.E = make_eparams(p);
+	A.padded = P; A.delta = D; A.row0 = E0; A.own0 = own0; A.own1 = own1; A.halo_rule = halo_rule; A.it0 = it0; A.it1 = it1;
+	A.xsize = xsize; A.ysize = ysize; A.dir_table = ctx->d_dir_table; A.steps_out = d_steps;
+	constexpr unsigned G = 8;
+	unsigned const per_sweep = it1 - it0;
+	unsigned groups = std::min(per_sweep, 148u*12u*(32u/G)); // one droplet per group at a time; a few waves' worth of 8-lane groups
+	A.slot0 = 0; A.nslots = groups;
+	A.WX = std::min(TW_SWEEP_VIEW, xsize + 2*PAD); A.WY = std::min(TW_SWEEP_VIEW, ysize + 2*PAD);
+	A.P = whole_pitch(A.WX, A.WY); A.win_elems = (unsigned)A.P*A.WY;
+	launch_droplets<G, M_FROZEN>(ctx->stream, A, 2, (size_t)A.win_elems*sizeof(float));
+	TW_LAUNCH_CHECK(ctx);
+	return TW_OK;
+}
+int twi_sweep_add(tw_ctx *ctx, long long *D, const long long *R, size_t n) {
+	sweep_add_kernel<<<(unsigned)((n + 255)/256), 256, 0, ctx->stream>>>(D, R, n);
+	TW_LAUNCH_CHECK(ctx);
+	return TW_OK;
+}
+int twi_sweep_apply(tw_ctx *ctx, float *P, long long *D, size_t n) {
+	sweep_apply_kernel<<<(unsigned)((n + 255)/256), 256, 0, ctx->stream>>>(P, D, n);
+	TW_LAUNCH_CHECK(ctx);
+	return TW_OK;
+}
+int twi_sweep_unpad(tw_ctx *ctx, const float *P, int E0, int xsize, int y0, int y1, float min_zval, float *out) {
+	sweep_unpad_kernel<<<dim3((xsize + 255)/256, y1 - y0), 256, 0, ctx->stream>>>(P, E0, xsize + 2*PAD, xsize, y0, y1, min_zval, out);
+	TW_LAUNCH_CHECK(ctx);
 	return TW_OK;
 }

@@ -101,6 +101,14 @@ size_t   twi_erode_scratch_bytes(uint32_t chunk, int xsize, int ysize);
 uint32_t twi_erode_chunk_for(size_t budget, uint32_t ntiles, int xsize, int ysize);
 int twi_erode_enqueue(tw_ctx *ctx, cudaStream_t st, int lane, void *scratch, uint32_t capacity, float *maps, uint32_t nt, int xsize, int ysize,
                       const float *d_min_zvals, float min_zval_all, uint32_t num_iters, const tw_erosion_params *p, unsigned long long *d_steps);
+// coherent batched erosion (tw_erode_sweeps*): per-band building blocks, all enqueued on ctx->stream
+int twi_sweep_pad(tw_ctx *ctx, const float *U, int u0, int xsize, int ysize, int E0, int rows, float *P);
+int twi_sweep_view();
+int twi_sweep_walk(tw_ctx *ctx, float *P, long long *D, int xsize, int ysize, int E0, int own0, int own1, int halo_rule, unsigned it0, unsigned it1,
+                   const tw_erosion_params *p, unsigned long long *d_steps);
+int twi_sweep_add(tw_ctx *ctx, long long *D, const long long *R, size_t n);
+int twi_sweep_apply(tw_ctx *ctx, float *P, long long *D, size_t n);
+int twi_sweep_unpad(tw_ctx *ctx, const float *P, int E0, int xsize, int y0, int y1, float min_zval, float *out);
 int twi_tile_bounds(tw_ctx *ctx, const float *d_zvals, uint32_t ntiles, uint32_t zvsize, float wpz_max, void *d_sub);
 int twi_glaciate_mesh(tw_ctx *ctx, float *d_mesh, int nx, int ny, int xoff2, int yoff2, int MX, int MY, const tw_height_params *p, unsigned *d_mm);
 int twi_voxel_fill(tw_ctx *ctx, const tw_voxel_params *vp, const float *rdata420, float *d_out);

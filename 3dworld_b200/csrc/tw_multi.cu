@@ -303,3 +303,158 @@ extern "C" int tw_heightgen_2d_sharded(tw_multi *m, const tw_grid2d *g, const tw
 		return tw_heightgen_2d(m->ctx[i], &b, p, enable_glaciate, 0, out_bands[i], &local[i]);
 	}, local, zrange);
 }
+
+// ------------------------------------------------------------------------------------------------ coherent erosion of ONE map sharded over the devices
+// tw_erode_sweeps / tw_erode_sweeps_sharded (include/tw3d.h): the batched droplet algorithm of droplet_kernel<M_FROZEN> on row bands, with ONE grouped
+// NCCL exchange per sweep: after the droplets of a sweep have been walked, neighbours swap the fixed-point deltas of the 2*halo rows around their
+// common border (each side's own rows next to the border + its halo copy of the other side's rows), add what they receive (integer sums: exact), and
+// apply the deltas to their band +- halo - after which every device's halo is current again without a second exchange.
+namespace {
+struct SweepBand {
+	int y0 = 0, y1 = 0;       // owned un-padded rows
+	int R0 = 0, R1 = 0;       // owned padded rows
+	int E0 = 0, E1 = 0;       // stored padded rows (band +- halo)
+	int u0 = 0, u1 = 0;       // un-padded rows needed to build them
+	float *U = nullptr, *P = nullptr;
+	long long *D = nullptr, *Rlo = nullptr, *Rhi = nullptr;
+	unsigned long long *d_steps = nullptr;
+	float *d_out = nullptr;   // staging of the result when the caller's band is host memory
+};
+int clampi_h(int v, int hi) {return v < 0 ? 0 : (v > hi ? hi : v);}
+}
+
+static int erode_sweeps_core(int n, tw_ctx **ctxs, ncclComm_t *comms, float *const *bands, int xsize, int ysize, float min_zval, uint32_t num_iters,
+                             const tw_erosion_params *ep, uint32_t sweep, int halo, uint64_t *moves, char *err, size_t errlen)
+{
+#define SW_FAIL(status, ...) do {snprintf(err, errlen, __VA_ARGS__); rc = (status); goto done;} while (0)
+#define SW_CUDA(call) do {cudaError_t e_ = (call); if (e_ != cudaSuccess) SW_FAIL(TW_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e_));} while (0)
+	int rc = TW_OK;
+	int const PADR = 4, NX = xsize + 2*PADR, NY = ysize + 2*PADR;
+	std::vector<SweepBand> B(n);
+	std::string nerr;
+	NcclApi *N = (n > 1) ? nccl_api(nerr) : nullptr;
+	if (moves) *moves = 0;
+	if (num_iters == 0 || ep->erode_amount <= 0.0) return TW_OK; // src/erosion.cpp:16
+	int const view = twi_sweep_view();
+	if (sweep == 0 || halo < view + 12 || xsize <= 0 || ysize <= 0) {snprintf(err, errlen, "sweep must be > 0 and halo >= %d (view + 12)", view + 12); return TW_ERR_ARG;}
+	if (n > 1 && !N) {snprintf(err, errlen, "%s", nerr.c_str()); return TW_ERR_STATE;}
+	for (int i = 0; i < n; ++i) {
+		uint32_t a, b;
+		tw_multi_range((uint32_t)ysize, n, i, &a, &b);
+		SweepBand &s = B[i];
+		s.y0 = (int)a; s.y1 = (int)b;
+		if (n > 1 && s.y1 - s.y0 < 2*halo + 2*PADR) {snprintf(err, errlen, "bands of %d rows are too thin for a halo of %d rows", s.y1 - s.y0, halo); return TW_ERR_ARG;}
+		s.R0 = (i == 0) ? 0 : s.y0 + PADR; s.R1 = (i == n - 1) ? NY : s.y1 + PADR;
+		s.E0 = std::max(0, s.R0 - halo); s.E1 = std::min(NY, s.R1 + halo);
+		s.u0 = clampi_h(s.E0 - PADR, ysize - 1); s.u1 = clampi_h(s.E1 - 1 - PADR, ysize - 1) + 1;
+	}
+	for (int i = 0; i < n; ++i) { // buffers + the caller's band into the un-padded staging rows
+		SweepBand &s = B[i];
+		size_t const band = (size_t)(s.E1 - s.E0)*NX;
+		SW_CUDA(cudaSetDevice(ctxs[i]->device));
+		SW_CUDA(cudaMalloc(&s.U, (size_t)(s.u1 - s.u0)*xsize*sizeof(float)));
+		SW_CUDA(cudaMalloc(&s.P, band*sizeof(float)));
+		SW_CUDA(cudaMalloc(&s.D, band*sizeof(long long)));
+		SW_CUDA(cudaMalloc(&s.d_steps, sizeof(unsigned long long)));
+		if (n > 1) {SW_CUDA(cudaMalloc(&s.Rlo, (size_t)2*halo*NX*sizeof(long long))); SW_CUDA(cudaMalloc(&s.Rhi, (size_t)2*halo*NX*sizeof(long long)));}
+		SW_CUDA(cudaMemsetAsync(s.D, 0, band*sizeof(long long), ctxs[i]->stream));
+		SW_CUDA(cudaMemsetAsync(s.d_steps, 0, sizeof(unsigned long long), ctxs[i]->stream));
+		SW_CUDA(cudaMemcpyAsync(s.U + (size_t)(s.y0 - s.u0)*xsize, bands[i], (size_t)(s.y1 - s.y0)*xsize*sizeof(float), cudaMemcpyDefault, ctxs[i]->stream));
+	}
+	if (n > 1) { // initial halo of HEIGHTS: rows [u0, y0) come from the lower neighbour, [y1, u1) from the upper one
+		N->GroupStart();
+		for (int i = 0; i < n; ++i) {
+			SweepBand &s = B[i];
+			cudaStream_t const st = ctxs[i]->stream;
+			if (i > 0) {
+				N->Send(s.U + (size_t)(s.y0 - s.u0)*xsize, (size_t)(B[i-1].u1 - s.y0)*xsize, ncclFloat, i - 1, comms[i], st);
+				N->Recv(s.U, (size_t)(s.y0 - s.u0)*xsize, ncclFloat, i - 1, comms[i], st);
+			}
+			if (i < n - 1) {
+				N->Send(s.U + (size_t)(B[i+1].u0 - s.u0)*xsize, (size_t)(s.y1 - B[i+1].u0)*xsize, ncclFloat, i + 1, comms[i], st);
+				N->Recv(s.U + (size_t)(s.y1 - s.u0)*xsize, (size_t)(s.u1 - s.y1)*xsize, ncclFloat, i + 1, comms[i], st);
+			}
+		}
+		if (N->GroupEnd() != ncclSuccess) SW_FAIL(TW_ERR_CUDA, "NCCL halo exchange (heights) failed");
+	}
+	for (int i = 0; i < n; ++i) {
+		SW_CUDA(cudaSetDevice(ctxs[i]->device));
+		rc = twi_sweep_pad(ctxs[i], B[i].U, B[i].u0, xsize, ysize, B[i].E0, B[i].E1 - B[i].E0, B[i].P);
+		if (rc) SW_FAIL(rc, "%s", tw_last_error(ctxs[i]));
+	}
+	for (uint32_t it0 = 0; it0 < num_iters; it0 += sweep) {
+		uint32_t const it1 = (num_iters - it0 < sweep) ? num_iters : it0 + sweep;
+		for (int i = 0; i < n; ++i) { // every device walks the droplets of this sweep that start in its own rows, on its frozen band
+			SW_CUDA(cudaSetDevice(ctxs[i]->device));
+			rc = twi_sweep_walk(ctxs[i], B[i].P, B[i].D, xsize, ysize, B[i].E0, B[i].R0, B[i].R1, halo - view - PADR, it0, it1, ep, B[i].d_steps);
+			if (rc) SW_FAIL(rc, "%s", tw_last_error(ctxs[i]));
+		}
+		if (n > 1) { // THE halo exchange of the sweep: 2*halo rows of deltas around every internal border, both directions, one NCCL group
+			size_t const cnt = (size_t)2*halo*NX;
+			N->GroupStart();
+			for (int i = 0; i < n; ++i) {
+				SweepBand &s = B[i];
+				cudaStream_t const st = ctxs[i]->stream;
+				if (i < n - 1) {N->Send(s.D + (size_t)(s.R1 - halo - s.E0)*NX, cnt, ncclInt64, i + 1, comms[i], st); N->Recv(s.Rhi, cnt, ncclInt64, i + 1, comms[i], st);}
+				if (i > 0)     {N->Send(s.D + (size_t)(s.R0 - halo - s.E0)*NX, cnt, ncclInt64, i - 1, comms[i], st); N->Recv(s.Rlo, cnt, ncclInt64, i - 1, comms[i], st);}
+			}
+			if (N->GroupEnd() != ncclSuccess) SW_FAIL(TW_ERR_CUDA, "NCCL halo exchange (deltas) failed");
+			for (int i = 0; i < n; ++i) {
+				SweepBand &s = B[i];
+				SW_CUDA(cudaSetDevice(ctxs[i]->device));
+				if (i < n - 1) {rc = twi_sweep_add(ctxs[i], s.D + (size_t)(s.R1 - halo - s.E0)*NX, s.Rhi, cnt); if (rc) SW_FAIL(rc, "%s", tw_last_error(ctxs[i]));}
+				if (i > 0)     {rc = twi_sweep_add(ctxs[i], s.D + (size_t)(s.R0 - halo - s.E0)*NX, s.Rlo, cnt); if (rc) SW_FAIL(rc, "%s", tw_last_error(ctxs[i]));}
+			}
+		}
+		for (int i = 0; i < n; ++i) {
+			SW_CUDA(cudaSetDevice(ctxs[i]->device));
+			rc = twi_sweep_apply(ctxs[i], B[i].P, B[i].D, (size_t)(B[i].E1 - B[i].E0)*NX);
+			if (rc) SW_FAIL(rc, "%s", tw_last_error(ctxs[i]));
+		}
+	}
+	for (int i = 0; i < n; ++i) { // remove the padding, clamp, hand the band back
+		SweepBand &s = B[i];
+		SW_CUDA(cudaSetDevice(ctxs[i]->device));
+		bool const dev = tw_is_device_ptr(bands[i]);
+		float *out = bands[i];
+		size_t const bytes = (size_t)(s.y1 - s.y0)*xsize*sizeof(float);
+		if (!dev) {SW_CUDA(cudaMalloc(&s.d_out, bytes)); out = s.d_out;}
+		rc = twi_sweep_unpad(ctxs[i], s.P, s.E0, xsize, s.y0, s.y1, min_zval, out);
+		if (rc) SW_FAIL(rc, "%s", tw_last_error(ctxs[i]));
+		if (!dev) {SW_CUDA(cudaMemcpyAsync(bands[i], s.d_out, bytes, cudaMemcpyDeviceToHost, ctxs[i]->stream));}
+	}
+	for (int i = 0; i < n; ++i) {
+		unsigned long long h = 0;
+		SW_CUDA(cudaSetDevice(ctxs[i]->device));
+		SW_CUDA(cudaMemcpyAsync(&h, B[i].d_steps, sizeof(h), cudaMemcpyDeviceToHost, ctxs[i]->stream));
+		SW_CUDA(cudaStreamSynchronize(ctxs[i]->stream));
+		if (moves) *moves += h;
+	}
+done:
+	for (int i = 0; i < n; ++i) {
+		SweepBand &s = B[i];
+		cudaSetDevice(ctxs[i]->device);
+		cudaStreamSynchronize(ctxs[i]->stream);
+		if (s.U) cudaFree(s.U); if (s.P) cudaFree(s.P); if (s.D) cudaFree(s.D); if (s.Rlo) cudaFree(s.Rlo); if (s.Rhi) cudaFree(s.Rhi);
+		if (s.d_steps) cudaFree(s.d_steps); if (s.d_out) cudaFree(s.d_out);
+	}
+	return rc;
+#undef SW_FAIL
+#undef SW_CUDA
+}
+
+extern "C" int tw_erode_sweeps(tw_ctx *ctx, float *heightmap, int xsize, int ysize, float min_zval, uint32_t num_iters, const tw_erosion_params *p,
+                               uint32_t sweep, int halo, uint64_t *moves)
+{
+	if (!ctx || !heightmap || !p) return TW_ERR_ARG;
+	float *bands[1] = {heightmap};
+	tw_ctx *ctxs[1] = {ctx};
+	return erode_sweeps_core(1, ctxs, nullptr, bands, xsize, ysize, min_zval, num_iters, p, sweep, halo, moves, ctx->err, sizeof(ctx->err));
+}
+
+extern "C" int tw_erode_sweeps_sharded(tw_multi *m, float *const *bands, int xsize, int ysize, float min_zval, uint32_t num_iters, const tw_erosion_params *p,
+                                       uint32_t sweep, int halo, uint64_t *moves)
+{
+	if (!m || !bands || !p) return TW_ERR_ARG;
+	return erode_sweeps_core(m->n, m->ctx.data(), m->comm.empty() ? nullptr : m->comm.data(), bands, xsize, ysize, min_zval, num_iters, p, sweep, halo, moves, m->err, sizeof(m->err));
+}

@@ -318,6 +318,22 @@ TW_API int  tw_create_zvals_sharded(tw_multi *m, const int32_t *origins_xy, uint
 /* mesh_xy_grid_cache_t::build_arrays + eval_index over ONE nx*ny grid split into ndev row bands (heightmap_t::proc_gen's fill, sharded):
  * band i = rows tw_multi_range(g->ny, ndev, i), out_bands[i] receives rows*nx floats; zrange as above. */
 TW_API int  tw_heightgen_2d_sharded(tw_multi *m, const tw_grid2d *g, const tw_height_params *p, int enable_glaciate, float *const *out_bands, tw_minmax *zrange);
+/* Coherent erosion of ONE heightmap that is too big for / spread over several GPUs (SURVEY.md 8e "optional coherent variant"; the single-grid
+ * caller is heightmap_t::run_erosion, src/heightmap.cpp:153-187). The reference's droplet order cannot be kept across devices (every droplet
+ * sees all earlier writes), so this is its BATCHED variant, defined independently of the device count: droplets are processed in sweeps of
+ * `sweep` droplets; all droplets of a sweep read the map as it was when the sweep began; their deposits / erosions (same per-move arithmetic as
+ * src/erosion.cpp:76-152) are accumulated in 64-bit fixed point (2^-40 height units: integer sums do not depend on order) and added to the map
+ * after the sweep; a droplet still sees its OWN writes through a private 32x32 view (sweep-start heights + its writes; re-read and re-centred
+ * ahead of its heading when it walks out of it - without that feedback a droplet in a pit never fills it); it ends once it is more than
+ * halo-36 rows away from its start row (halo >= 44). Row bands as tw_multi_range(ysize, ndev, i); each
+ * device keeps its band +- halo rows and after every sweep neighbours exchange the deltas of the 2*halo rows around their border in ONE grouped
+ * ncclSend/ncclRecv over NVLink (width*2*halo*8 bytes per neighbour). The result is bit-identical for every device count (tw_erode_sweeps ==
+ * tw_erode_sweeps_sharded), which is what the parity tests check, next to the CPU oracle of the same algorithm. bands[i]: the band's rows in
+ * place (device i's memory or host memory); moves (optional) = droplet moves. */
+TW_API int  tw_erode_sweeps(tw_ctx *ctx, float *heightmap, int xsize, int ysize, float min_zval, uint32_t num_iters, const tw_erosion_params *p,
+                     uint32_t sweep, int halo, uint64_t *moves);
+TW_API int  tw_erode_sweeps_sharded(tw_multi *m, float *const *bands, int xsize, int ysize, float min_zval, uint32_t num_iters, const tw_erosion_params *p,
+                             uint32_t sweep, int halo, uint64_t *moves);
 /* (2) one process per GPU (torchrun / mpirun style): rank 0 makes an id, every rank passes it to tw_dist_init on its own context */
 TW_API int  tw_dist_unique_id(char id128[128]);
 TW_API int  tw_dist_init(tw_ctx *ctx, int nranks, int rank, const char id128[128]);

@@ -115,6 +115,8 @@ def lib():
         L.to_eval_points.argtypes = [vp, C.c_size_t, C.POINTER(HeightParams), C.POINTER(PointQuery), vp, vp, vp]
         L.to_apply_erosion.argtypes = [vp, C.c_int, C.c_int, C.c_float, C.c_uint, C.POINTER(ErosionParams)]
         L.to_apply_erosion.restype = C.c_ulonglong
+        L.to_erode_sweeps.argtypes = [vp, C.c_int, C.c_int, C.c_float, C.c_uint, C.POINTER(ErosionParams), C.c_uint, C.c_int]
+        L.to_erode_sweeps.restype = C.c_ulonglong
         L.to_noise3d_gen_sines.argtypes = [C.c_int, C.c_int, C.c_float, C.c_float, vp]
         L.to_noise3d_get_val_pt.argtypes = [vp, vp, C.c_float, C.c_float, C.c_float]
         L.to_noise3d_get_val_pt.restype = C.c_float
@@ -230,6 +232,14 @@ def apply_erosion(h, min_zval, num_iters, ep):
     h = np.array(h, np.float32, order="C", copy=True)
     ys, xs = h.shape
     steps = lib().to_apply_erosion(_p(h), xs, ys, min_zval, num_iters, C.byref(ep))
+    return h, int(steps)
+
+
+def erode_sweeps(h, min_zval, num_iters, ep, sweep, halo):
+    """The coherent batched erosion of tw_erode_sweeps (frozen map per sweep, fixed-point deltas, halo rule); returns (map, moves)."""
+    h = np.array(h, np.float32, order="C", copy=True)
+    ys, xs = h.shape
+    steps = lib().to_erode_sweeps(_p(h), xs, ys, min_zval, num_iters, C.byref(ep), sweep, halo)
     return h, int(steps)
 
 

@@ -631,7 +631,141 @@ unsigned long long to_apply_erosion(float *heightmap, int xsize, int ysize, floa
 	}
 	free(mh);
 	return steps;
+#undef DEPOSIT_AT
+#undef DEPOSIT
+#undef HMAP
 }
+
+/* ------------------------------------------------------------------ coherent batched erosion (tw_erode_sweeps; NO reference counterpart)
+ * The per-move arithmetic is apply_erosion's (above). What differs is what a droplet can see, so that the result does not depend on how the map
+ * is split over devices: droplets [k*sweep, (k+1)*sweep) read the map as it was when sweep k began; their deposits go to a 64-bit fixed-point
+ * delta buffer (2^-40 units: integer sums are order-independent) that is added to the map after the sweep; a droplet does see its OWN writes
+ * through a private VIEW x VIEW window (sweep-start heights + its writes), re-read and re-centred ahead of its heading when it walks out of it;
+ * and it ends once it is more than halo - VIEW - 4 rows from its start row. Mirrors droplet_kernel<M_FROZEN> in csrc/tw_erosion.cu. */
+#define SWEEP_VIEW 32
+typedef struct {float *mh; long long *dfix; int NX, NY; float win[SWEEP_VIEW*SWEEP_VIEW]; int WX, WY, wx0, wz0, have;} sweep_state;
+static float sw_read(const sweep_state *S, int x, int z) {
+	int const cx = CLAMPI(x, S->NX-1), cz = CLAMPI(z, S->NY-1);
+	if (S->have) {unsigned const rx = (unsigned)(cx - S->wx0), rz = (unsigned)(cz - S->wz0); if (rx < (unsigned)S->WX && rz < (unsigned)S->WY) return S->win[rz*S->WX + rx];}
+	return S->mh[(size_t)S->NX*cz + cx];
+}
+static void sw_add(sweep_state *S, int x, int z, float delta) { /* (x, z) inside the array */
+	if (S->have) {unsigned const rx = (unsigned)(x - S->wx0), rz = (unsigned)(z - S->wz0); if (rx < (unsigned)S->WX && rz < (unsigned)S->WY) {S->win[rz*S->WX + rx] += delta;}}
+	if (fabsf(delta) < 1048576.0f) {S->dfix[(size_t)S->NX*z + x] += llrint((double)delta*1099511627776.0);}
+}
+unsigned long long to_erode_sweeps(float *heightmap, int xsize, int ysize, float min_zval, unsigned num_iters, const tw_erosion_params *ep, unsigned sweep, int halo)
+{
+	float const erode_amount = ep->erode_amount;
+	if (num_iters == 0 || erode_amount <= 0.0 || sweep == 0 || halo < SWEEP_VIEW + 12) return 0;
+	float const Kq=10, Kw=0.001f, Kr=0.9f, Kd=0.02f, Ki=0.1f, minSlope=0.05f, g=20, Kg=g*2;
+	int const PAD = 4, NX = xsize+2*PAD, NY = ysize+2*PAD, halo_rule = halo - SWEEP_VIEW - PAD;
+	unsigned const MAX_PATH_LEN = 4*NX*NY;
+	sweep_state S;
+	S.mh = (float *)malloc((size_t)NX*NY*sizeof(float));
+	S.dfix = (long long *)calloc((size_t)NX*NY, sizeof(long long));
+	S.NX = NX; S.NY = NY; S.WX = (SWEEP_VIEW < NX) ? SWEEP_VIEW : NX; S.WY = (SWEEP_VIEW < NY) ? SWEEP_VIEW : NY; S.have = 0; S.wx0 = S.wz0 = 0;
+	unsigned long long steps = 0;
+	for (int y = 0; y < NY; ++y) {
+		int const yy = CLAMPI(y-PAD, ysize-1);
+		for (int x = 0; x < NX; ++x) {S.mh[(size_t)y*NX + x] = heightmap[CLAMPI(x-PAD, xsize-1) + (size_t)yy*xsize];}
+	}
+#define SW_DEPOSIT_AT(X, Z, W) {float const delta = ds*erode_amount*(W); if (!((X) < 0 || (Z) < 0 || (X) >= NX || (Z) >= NY)) {sw_add(&S, (X), (Z), delta);}}
+#define SW_DEPOSIT(H) \
+	SW_DEPOSIT_AT(xi  , zi  , (1-xf)*(1-zf)) \
+	SW_DEPOSIT_AT(xi+1, zi  ,    xf *(1-zf)) \
+	SW_DEPOSIT_AT(xi  , zi+1, (1-xf)*   zf ) \
+	SW_DEPOSIT_AT(xi+1, zi+1,    xf *   zf ) \
+	(H)+=ds;
+	float const tp = two_pi();
+	for (int iter = 0; iter < (int)num_iters; ++iter) {
+		if (iter > 0 && (unsigned)iter % sweep == 0) { /* end of a sweep: map += deltas */
+			for (size_t i = 0; i < (size_t)NX*NY; ++i) {S.mh[i] = S.mh[i] + (float)((double)S.dfix[i]*(1.0/1099511627776.0)); S.dfix[i] = 0;}
+		}
+		tw_rng rgen; to_rng_set(&rgen, iter+11, 79*iter+121);
+		int xi = PAD + (to_rng_rand(&rgen)%xsize);
+		int zi = PAD + (to_rng_rand(&rgen)%ysize);
+		int const zstart = zi;
+		S.have = 0; /* a new droplet knows nothing of the previous one's writes */
+		float xp=xi, zp=zi, xf=0, zf=0, s=0, v=0, w=1, dx=0, dz=0;
+		float h=sw_read(&S, xi, zi), h00=h, h10=sw_read(&S, xi+1, zi), h01=sw_read(&S, xi, zi+1), h11=sw_read(&S, xi+1, zi+1);
+		unsigned numMoves = 0;
+		for (; numMoves < MAX_PATH_LEN; ++numMoves) {
+			if ((unsigned)(zi - zstart + halo_rule) > 2u*(unsigned)halo_rule) break; /* too far from the start row: the droplet ends */
+			++steps;
+			{ /* keep the cells this move can touch inside the private view (same policy as droplet_kernel<M_WINDOW>) */
+				int const cx = CLAMPI(xi, NX-1), cz = CLAMPI(zi, NY-1);
+				int const lx = (cx-2 > 0) ? cx-2 : 0, hx = (cx+3 < NX-1) ? cx+3 : NX-1, lz = (cz-2 > 0) ? cz-2 : 0, hz = (cz+3 < NY-1) ? cz+3 : NY-1;
+				int const covered = S.have && lx >= S.wx0 && hx < S.wx0 + S.WX && lz >= S.wz0 && hz < S.wz0 + S.WY;
+				if (!covered) {
+					float const tx = dx*(float)(S.WX/2 - 5), tz = dz*(float)(S.WY/2 - 5);
+					int const bx = (tx != tx) ? 0 : (int)lrintf(tx), bz = (tz != tz) ? 0 : (int)lrintf(tz); /* round to nearest even; NaN -> 0 */
+					int ox = cx - S.WX/2 + bx, oz = cz - S.WY/2 + bz;
+					if (ox > NX - S.WX) ox = NX - S.WX; if (ox < 0) ox = 0;
+					if (oz > NY - S.WY) oz = NY - S.WY; if (oz < 0) oz = 0;
+					S.wx0 = ox; S.wz0 = oz;
+					for (int r = 0; r < S.WY; ++r) {for (int c = 0; c < S.WX; ++c) {S.win[r*S.WX + c] = S.mh[(size_t)NX*(oz + r) + ox + c];}}
+					S.have = 1;
+				}
+			}
+			float gx=h00+h01-h10-h11, gz=h00+h10-h01-h11;
+			dx=(dx-gx)*Ki+gx;
+			dz=(dz-gz)*Ki+gz;
+			float dl=sqrtf(dx*dx+dz*dz);
+			if (dl<=FLT_EPSILON) {float a=to_rng_rand_float(&rgen)*tp; dx=cosf(a); dz=sinf(a);}
+			else {dx/=dl; dz/=dl;}
+			float nxp=xp+dx, nzp=zp+dz;
+			int nxi=(int)floorf(nxp), nzi=(int)floorf(nzp);
+			float nxf=nxp-nxi, nzf=nzp-nzi;
+			float nh00=sw_read(&S, nxi, nzi), nh10=sw_read(&S, nxi+1, nzi), nh01=sw_read(&S, nxi, nzi+1), nh11=sw_read(&S, nxi+1, nzi+1);
+			float nh=(nh00*(1-nxf)+nh10*nxf)*(1-nzf)+(nh01*(1-nxf)+nh11*nxf)*nzf;
+			if (std_max(std_max(nh00, nh10), std_max(nh01, nh11)) < ep->water_plane_z - ep->half_dxy) break;
+			int const outside = (xi < 0 || zi < 0 || xi >= NX || zi >= NY);
+			if (nh>=h || outside) {
+				float ds=(nh-h)+0.001f;
+				if (ds>=s || outside) {ds=s; SW_DEPOSIT(h) s=0; break;}
+				SW_DEPOSIT(h)
+				s-=ds;
+				v=0;
+			}
+			float dh=h-nh;
+			float q=std_max(dh, minSlope)*v*w*Kq;
+			float ds=s-q;
+			if (ds>=0) {ds*=Kd; SW_DEPOSIT(dh) s-=ds;}
+			else {
+				ds*=-Kr;
+				ds=std_min(ds, dh*0.99f);
+				{float const relh = ep->relh_adj_tex + (nh - ep->zmin)/(ep->zmax - ep->zmin); ds = (float)(ds*((relh > ep->clip_hd1) ? 0.5 : 2.0));}
+				for (int z=zi-1; z<=zi+2; ++z) {
+					float zo=z-zp, zo2=zo*zo;
+					for (int x=xi-1; x<=xi+2; ++x) {
+						float xo=x-xp;
+						float wgt=1-(xo*xo+zo2)*0.25f;
+						if (wgt<=0) continue;
+						wgt*=0.1591549430918953f;
+						float const delta=ds*erode_amount*wgt;
+						sw_add(&S, CLAMPI(x, NX-1), CLAMPI(z, NY-1), -delta);
+					}
+				}
+				dh-=ds;
+				s+=ds;
+			}
+			v=sqrtf(v*v+Kg*dh);
+			w*=1-Kw;
+			xp=nxp; zp=nzp; xi=nxi; zi=nzi; xf=nxf; zf=nzf;
+			h=nh; h00=nh00; h10=nh10; h01=nh01; h11=nh11;
+		}
+	}
+	for (size_t i = 0; i < (size_t)NX*NY; ++i) {S.mh[i] = S.mh[i] + (float)((double)S.dfix[i]*(1.0/1099511627776.0));}
+	for (int y = 0; y < ysize; ++y) {
+		for (int x = 0; x < xsize; ++x) {heightmap[(size_t)y*xsize + x] = std_max(min_zval, S.mh[(size_t)(y+PAD)*NX + x+PAD]);}
+	}
+	free(S.mh); free(S.dfix);
+	return steps;
+#undef SW_DEPOSIT_AT
+#undef SW_DEPOSIT
+}
+#undef CLAMPI
+#undef HMAP_INDEX
 
 
 /* ------------------------------------------------------------------ per-tile normals and AO (ref: src/tiled_mesh.cpp:586-662,865-880; src/tiled_mesh.h:281-284)

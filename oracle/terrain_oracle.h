@@ -72,6 +72,7 @@ void to_hmap_sample_tiles(const unsigned char *data16, const tw_hmap_sampler *H,
 /* eval_mesh_sin_terms / eval_mesh_sin_terms_scaled / get_exact_zval (procedural branch) for n points, src/mesh_gen.cpp:797-847 */
 void to_eval_points(const float *xy, size_t n, const tw_height_params *p, const tw_point_query *q, const float *sin_table, const float *sine_params450, float *out);
 unsigned long long to_apply_erosion(float *heightmap, int xsize, int ysize, float min_zval, unsigned num_iters, const tw_erosion_params *p);
+unsigned long long to_erode_sweeps(float *heightmap, int xsize, int ysize, float min_zval, unsigned num_iters, const tw_erosion_params *p, unsigned sweep, int halo);
 
 /* noise_gen_3d, src/upsurface.cpp:16-85 */
 void  to_noise3d_gen_sines(int rs1, int rs2, float mag, float freq, float *rdata420);

@@ -102,3 +102,50 @@ print("rank", rank, "ok")
         procs = [subprocess.Popen([sys.executable, "-c", code, str(r), idf], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True) for r in range(2)]
         outs = [p.communicate(timeout=300)[0] for p in procs]
     assert all(p.returncode == 0 for p in procs), outs
+
+
+@pytest.mark.parametrize("n,m,iters,sweep,halo", [(300, 200, 4000, 256, 48), (512, 512, 20000, 1000, 64), (130, 97, 777, 50, 44), (200, 260, 3000, 3000, 100), (20, 30, 500, 7, 44)])
+def test_erode_sweeps_single_device_equals_oracle(tw, scene, oracle, ctx, beq, n, m, iters, sweep, halo):
+    """The coherent batched erosion (frozen map per sweep, 64-bit fixed-point deltas, halo rule) on one GPU == the CPU oracle of the same
+    algorithm, bit for bit (integer accumulation makes it independent of the order in which the GPU walks the droplets of a sweep)."""
+    from cases import convert
+    cfg = scene.SceneConfig(mesh_gen_mode=1, mesh_freq_filter=1, mesh_seed=1, hmap=HM_CFG, zmax_est=2.0)
+    z = ctx.heightgen_2d(cfg.heightmap_grid(n, m), cfg.height_params())
+    zmin, zmax = float(z.min()), float(z.max())
+    for ep in (tw.ErosionParams(1.0, zmin - 10, 0.0625, zmin - 0.1, zmax + 0.1, 0.0, 0.5), tw.ErosionParams(1.0, zmin + 0.2 * (zmax - zmin), 0.0625, zmin - 0.1, zmax + 0.1, 0.0, 2.0)):
+        zc, moves = oracle.erode_sweeps(z, zmin, iters, convert(ep, oracle.ErosionParams), sweep, halo)
+        zg = z.copy()
+        got_moves = ctx.erode_sweeps(zg, zmin, iters, ep, sweep, halo)
+        assert beq(zg, zc) == 0, "max abs diff %g" % np.nanmax(np.abs(zg - zc))
+        assert got_moves == moves
+        assert (zc != z).sum() > 100
+    assert np.isfinite(zc).all()     # NaN deltas are dropped by the fixed-point accumulation (the reference's serial order can poison cells, SURVEY.md section 7)
+
+
+@pytest.mark.parametrize("ndev", [2, 4])
+def test_erode_sweeps_sharded_equals_single_device(tw, scene, oracle, ctx, beq, ndev):
+    """Row bands over ndev GPUs with one grouped ncclSend/ncclRecv of the border deltas per sweep == the one-GPU run, bit for bit; droplets that
+    cross band borders and reach the halo rule are included (halo 44 = the minimum, view 32 + 12)."""
+    import torch
+    if _ndev() < ndev:
+        pytest.skip("needs %d GPUs" % ndev)
+    cfg = scene.SceneConfig(mesh_gen_mode=1, mesh_freq_filter=1, mesh_seed=1, hmap=HM_CFG, zmax_est=2.0)
+    ep = cfg.erosion_params()
+    m = tw.Multi(list(range(ndev)))
+    try:
+        for (nx, ny, iters, sweep, halo) in ((700, 640, 30000, 2048, 44), (1024, 1536, 60000, 8192, 64)):
+            z = ctx.heightgen_2d(cfg.heightmap_grid(nx, ny), cfg.height_params())
+            zmin = float(z.min())
+            one = z.copy()
+            moves1 = ctx.erode_sweeps(one, zmin, iters, ep, sweep, halo)
+            ranges = [tw.multi_range(ny, ndev, i) for i in range(ndev)]
+            host_bands = [np.ascontiguousarray(z[a:b]) for a, b in ranges]
+            moves = m.erode_sweeps_sharded(host_bands, nx, ny, zmin, iters, ep, sweep, halo)
+            assert beq(np.concatenate(host_bands), one) == 0 and moves == moves1
+            dev_bands = [torch.from_numpy(np.ascontiguousarray(z[a:b])).to("cuda:%d" % i) for i, (a, b) in enumerate(ranges)]
+            m.erode_sweeps_sharded(dev_bands, nx, ny, zmin, iters, ep, sweep, halo)
+            assert beq(np.concatenate([d.cpu().numpy() for d in dev_bands]), one) == 0
+            border = ranges[0][1]
+            assert (one[border - 8:border + 8] != z[border - 8:border + 8]).any()      # erosion did happen across the first border
+    finally:
+        m.close()
