@@ -294,7 +294,6 @@ class Multi:
         p = C.c_void_p()
         self._check(lib.tw_multi_alloc_host(self._h, i, n, C.byref(p)))
         arr = np.frombuffer((C.c_char * n).from_address(p.value), dtype=dtype).reshape(shape)
-        arr._tw_ptr = p.value if hasattr(arr, "__dict__") else None
         return arr, p
 
     def free_host(self, p):

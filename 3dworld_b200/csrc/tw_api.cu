@@ -49,7 +49,7 @@ int twi_ensure_aux_streams(tw_ctx *ctx) {
 	int lo = 0, hi = 0; // the latency-bound droplet kernels / band copies get the higher priority
 	TW_CUDA(ctx, cudaDeviceGetStreamPriorityRange(&lo, &hi));
 	bool const prio = !(getenv("TW_PIPE_NOPRIO"));
-	for (int i = 0; i < 2; ++i) {TW_CUDA(ctx, cudaStreamCreateWithPriority(&ctx->aux_stream[i], cudaStreamNonBlocking, prio ? hi : lo));}
+	for (int i = 0; i < 3; ++i) {TW_CUDA(ctx, cudaStreamCreateWithPriority(&ctx->aux_stream[i], cudaStreamNonBlocking, prio ? hi : lo));}
 	return TW_OK;
 }
 
@@ -58,7 +58,7 @@ namespace {
 // slot-2 layout (small device scalars)
 constexpr size_t OFF_MM = 0, OFF_BAD = 64, OFF_TILES = 4096;
 
-int check_ctx(tw_ctx *ctx) {
+int check_ctx(tw_ctx *ctx) { // NOTE: makes ctx->device the calling thread's current CUDA device and leaves it so (documented in tw3d.h: one context per thread)
 	if (!ctx) return TW_ERR_ARG;
 	cudaError_t e = cudaSetDevice(ctx->device);
 	if (e != cudaSuccess) return tw_set_error(ctx, TW_ERR_CUDA, "cudaSetDevice(%d): %s", ctx->device, cudaGetErrorString(e));
@@ -124,8 +124,8 @@ void tw_destroy(tw_ctx *ctx) {
 	if (ctx->d_sine_params) cudaFree(ctx->d_sine_params);
 	if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
 	if (ctx->async.done) cudaEventDestroy(ctx->async.done);
-	for (int i = 0; i < 2; ++i) {if (ctx->aux_stream[i]) cudaStreamDestroy(ctx->aux_stream[i]);}
-	for (int i = 0; i < 3; ++i) {
+	for (int i = 0; i < 3; ++i) {if (ctx->aux_stream[i]) cudaStreamDestroy(ctx->aux_stream[i]);}
+	for (int i = 0; i < 4; ++i) {
 		if (ctx->heavy_stream[i]) cudaStreamDestroy(ctx->heavy_stream[i]);
 		if (ctx->ev_fork[i]) cudaEventDestroy(ctx->ev_fork[i]);
 		if (ctx->ev_join[i]) cudaEventDestroy(ctx->ev_join[i]);
@@ -275,6 +275,7 @@ int tw_tile_bounds_batch(tw_ctx *ctx, const float *zvals, uint32_t ntiles, uint3
 	int rc = check_ctx(ctx); if (rc) return rc;
 	rc = finish_pending(ctx); if (rc) return rc;
 	if (!zvals || !out || ntiles == 0 || zvsize < 4) return tw_set_error(ctx, TW_ERR_ARG, "null/empty argument");
+	if (4*(zvsize/4) >= zvsize) return tw_set_error(ctx, TW_ERR_ARG, "zvsize %u: the last sub-block would end at cell %u (the reference asserts x_end < zvsize, src/tiled_mesh.cpp:520)", zvsize, 4*(zvsize/4));
 	if (ntiles > 65535) return tw_set_error(ctx, TW_ERR_ARG, "at most 65535 tiles per call");
 	size_t const n = (size_t)ntiles*zvsize*zvsize;
 	struct Sub {float zmin, zmax; int wx1, wy1, wx2, wy2;};
@@ -388,25 +389,41 @@ int tw_create_zvals_batch(tw_ctx *ctx, const int32_t *origins_xy, uint32_t ntile
 	rc = twi_ensure_aux_streams(ctx); if (rc) return rc;
 	float *d_out = out;
 	if (!dev_out) {rc = tw_reserve(ctx, 0, n*sizeof(float)); if (rc) return rc; d_out = (float *)ctx->d_scratch[0];}
-	// chunking: measured on B200 (tools/bench_pipeline.py) every extra chunk adds its own droplet tail (the heaviest tile of a chunk is a
-	// serial chain of ~1e5 moves), which outweighs the generation/erosion overlap; so one chunk unless memory forces more (TW_PIPE_CHUNKS overrides)
+	// The pipeline. Work per tile is heavy-tailed (ocean tiles: 1000 droplets x 1 move; mountain tiles: 1e5 moves in one serial chain), and a chain
+	// cannot be sped up (csrc/tw_erosion.cu, plan_heavy), so the chains must START EARLY: (1) a coarse pre-pass evaluates the height function on an
+	// 8x8 sample of every tile (4 M evaluations for 65536 tiles, < 1 ms) and counts the samples above the ocean-stop level - the same predictor the
+	// erosion schedule uses, on 64 instead of 70756 cells; (2) the tiles are sorted heaviest first; (3) generation and erosion run chunk by chunk in
+	// THAT order: generation of chunk k+1 (main stream) overlaps the droplet walks of chunks <= k (three high-priority streams; chunk 0, which holds
+	// every long chain, has one to itself), so the long chains run under the generation of everything else and the last chunk to finish is the
+	// lightest one. Tiles are generated / eroded in schedule order but stored at their caller-visible index (tile_perm). TW_PIPE_CHUNKS overrides
+	// the chunk count (1 = the plain sequence); small batches use one chunk.
 	size_t free_b = 0, total_b = 0;
 	TW_CUDA(ctx, cudaMemGetInfo(&free_b, &total_b));
-	size_t budget = (free_b + ctx->scratch_bytes[1])/3/2;
+	size_t budget = (free_b + ctx->scratch_bytes[1])/3/3;
 	if (budget < ((size_t)512 << 20)) budget = (size_t)512 << 20;
-	uint32_t want_chunks = 1;
+	uint32_t want_chunks = (ntiles >= 4096) ? 8 : 1;
 	if (const char *e = getenv("TW_PIPE_CHUNKS")) {int const v = atoi(e); if (v >= 1 && v <= 64) want_chunks = (uint32_t)v;}
-	uint32_t chunk = (ntiles >= 4096) ? (ntiles + want_chunks - 1)/want_chunks : ntiles;
+	uint32_t chunk = (ntiles + want_chunks - 1)/want_chunks;
 	uint32_t const cap = twi_erode_chunk_for(budget, chunk, (int)zvsize, (int)zvsize);
 	uint32_t const nchunks = (ntiles + cap - 1)/cap;
-	chunk = (ntiles + nchunks - 1)/nchunks; // balanced: 65536 tiles with a 65535-tile cap become 2 x 32768, not 65535 + 1 (every chunk pays a droplet tail)
-	int const nes = (nchunks > 1) ? 2 : 1; // erosion streams / scratch buffers
-	size_t const sbytes = twi_erode_scratch_bytes(chunk, (int)zvsize, (int)zvsize);
+	chunk = (ntiles + nchunks - 1)/nchunks; // balanced
+	bool const reorder = (nchunks > 1 && !getenv("TW_PIPE_NO_REORDER"));
+	int const nes = (nchunks > 2) ? 3 : (int)nchunks; // erosion streams / scratch buffers
+	size_t const sbytes = (twi_erode_scratch_bytes(chunk, (int)zvsize, (int)zvsize) + 255) & ~(size_t)255;
 	rc = tw_reserve(ctx, 1, sbytes*nes); if (rc) return rc;
-	size_t const mm_bytes = (size_t)ntiles*2*sizeof(unsigned), org_bytes = (size_t)ntiles*sizeof(float2);
-	rc = tw_reserve(ctx, 2, OFF_TILES + mm_bytes + org_bytes); if (rc) return rc;
-	unsigned *d_mm = (unsigned *)((char *)ctx->d_scratch[2] + OFF_TILES);
-	float2 *d_org = (float2 *)((char *)ctx->d_scratch[2] + OFF_TILES + mm_bytes);
+	// slot 2: [small scalars | per-tile min/max | origins | sorted origins | work | order | hist(256) | coarse samples]
+	uint32_t const CS = 8, cstep = (zvsize >= CS) ? zvsize/CS : 1;
+	size_t const mm_bytes = ((size_t)ntiles*2*sizeof(unsigned) + 255) & ~(size_t)255, org_bytes = ((size_t)ntiles*sizeof(float2) + 255) & ~(size_t)255;
+	size_t const u_bytes = ((size_t)ntiles*sizeof(unsigned) + 255) & ~(size_t)255, coarse_bytes = reorder ? (((size_t)ntiles*CS*CS*sizeof(float) + 255) & ~(size_t)255) : 0;
+	rc = tw_reserve(ctx, 2, OFF_TILES + mm_bytes + 2*org_bytes + 2*u_bytes + 1024 + coarse_bytes); if (rc) return rc;
+	char *s2 = (char *)ctx->d_scratch[2] + OFF_TILES;
+	unsigned *d_mm = (unsigned *)s2; s2 += mm_bytes;
+	float2 *d_org = (float2 *)s2; s2 += org_bytes;
+	float2 *d_org_sorted = (float2 *)s2; s2 += org_bytes;
+	unsigned *d_work = (unsigned *)s2; s2 += u_bytes;
+	unsigned *d_order = (unsigned *)s2; s2 += u_bytes;
+	unsigned *d_hist = (unsigned *)s2; s2 += 1024;
+	float *d_coarse = (float *)s2;
 	unsigned long long *d_steps = (unsigned long long *)((char *)ctx->d_scratch[2] + 2048);
 	{
 		std::vector<float2> org(ntiles);
@@ -414,29 +431,49 @@ int tw_create_zvals_batch(tw_ctx *ctx, const int32_t *origins_xy, uint32_t ntile
 			float const x0 = (float)(origins_xy[2*t] - mesh_x_size/2), y0 = (float)(origins_xy[2*t+1] - mesh_y_size/2);
 			org[t] = make_float2(dx*x0, dy*y0);
 		}
-		TW_CUDA(ctx, cudaMemcpyAsync(d_org, org.data(), org_bytes, cudaMemcpyHostToDevice, ctx->stream));
+		TW_CUDA(ctx, cudaMemcpyAsync(d_org, org.data(), (size_t)ntiles*sizeof(float2), cudaMemcpyHostToDevice, ctx->stream));
 		TW_CUDA(ctx, cudaMemsetAsync(d_steps, 0, sizeof(unsigned long long), ctx->stream));
 		TW_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); // org is a local vector; the aux streams must also see d_steps zeroed
+	}
+	const float2 *d_gen_org = d_org;
+	const unsigned *d_perm = nullptr;
+	if (reorder) { // (1) + (2): coarse estimate, heaviest-first order of the WHOLE batch
+		tw_grid2d gc = g; gc.dx = dx*(float)cstep; gc.dy = dy*(float)cstep; gc.nx = CS; gc.ny = CS;
+		for (uint32_t t0 = 0; t0 < ntiles; t0 += 65535) {
+			uint32_t const nt = (ntiles - t0 < 65535) ? ntiles - t0 : 65535;
+			rc = twi_heightgen(ctx, &gc, p, 1, 0, d_org + t0, nt, d_coarse + (size_t)t0*CS*CS, nullptr); if (rc) return rc;
+		}
+		rc = twi_coarse_work(ctx, d_coarse, CS*CS, ntiles, ep->water_plane_z - ep->half_dxy, d_work); if (rc) return rc;
+		TW_CUDA(ctx, cudaMemsetAsync(d_hist, 0, 1024, ctx->stream));
+		rc = twi_order_by_work(ctx, ctx->stream, d_work, ntiles, CS*CS, d_hist, d_order); if (rc) return rc;
+		rc = twi_gather_origins(ctx, d_org, d_order, ntiles, d_org_sorted); if (rc) return rc;
+		d_gen_org = d_org_sorted; d_perm = d_order;
 	}
 	std::vector<cudaEvent_t> ev(nchunks, nullptr);
 	int status = TW_OK;
 	for (uint32_t k = 0; k < nchunks && status == TW_OK; ++k) {
 		uint32_t const t0 = k*chunk, nt = (ntiles - t0 < chunk) ? (ntiles - t0) : chunk;
-		float *maps = d_out + (size_t)t0*tile_elems;
-		status = twi_heightgen(ctx, &g, p, 1, 0, d_org + t0, nt, maps, nullptr);           // generation on ctx->stream
+		// schedule slots [t0, t0 + nt): with a permutation every kernel addresses `d_out` through it; without, the chunk is a contiguous slice
+		float *maps = d_perm ? d_out : d_out + (size_t)t0*tile_elems;
+		const unsigned *perm_k = d_perm ? d_perm + t0 : nullptr;
+		ctx->tile_perm = perm_k;
+		status = twi_heightgen(ctx, &g, p, 1, 0, d_gen_org + t0, nt, maps, nullptr);           // generation on ctx->stream
+		ctx->tile_perm = nullptr;
 		if (status) break;
 		if (cudaEventCreateWithFlags(&ev[k], cudaEventDisableTiming) != cudaSuccess || cudaEventRecord(ev[k], ctx->stream) != cudaSuccess) {status = tw_set_error(ctx, TW_ERR_CUDA, "event"); break;}
-		cudaStream_t const es = ctx->aux_stream[k % nes];
+		int const lane = (nes < 3) ? (int)(k % nes) : ((k == 0) ? 0 : 1 + (int)((k - 1) & 1)); // the heaviest chunk keeps a stream (and a scratch buffer) to itself
+		cudaStream_t const es = ctx->aux_stream[lane];
 		if (cudaStreamWaitEvent(es, ev[k], 0) != cudaSuccess) {status = tw_set_error(ctx, TW_ERR_CUDA, "cudaStreamWaitEvent"); break;}
-		status = twi_erode_enqueue(ctx, es, 1 + (int)(k % nes), (char *)ctx->d_scratch[1] + (size_t)(k % nes)*sbytes, chunk, maps, nt, (int)zvsize, (int)zvsize, nullptr, min_zval, erosion_iters, ep, d_steps);
+		status = twi_erode_enqueue(ctx, es, 1 + lane, (char *)ctx->d_scratch[1] + (size_t)lane*sbytes, chunk, maps, nt, (int)zvsize, (int)zvsize, nullptr, min_zval, erosion_iters, ep, d_steps, perm_k);
 		if (status) break;
-		if (mm) {status = twi_minmax_tiles(ctx, es, maps, tile_elems, nt, d_mm + 2*(size_t)t0); if (status) break;}
-		if (!dev_out && cudaMemcpyAsync(out + (size_t)t0*tile_elems, maps, (size_t)nt*tile_elems*sizeof(float), cudaMemcpyDeviceToHost, es) != cudaSuccess) {status = tw_set_error(ctx, TW_ERR_CUDA, "D2H");}
+		if (mm) {status = twi_minmax_tiles(ctx, es, maps, tile_elems, nt, d_perm ? d_mm : d_mm + 2*(size_t)t0, perm_k); if (status) break;}
+		if (!dev_out && !d_perm && cudaMemcpyAsync(out + (size_t)t0*tile_elems, maps, (size_t)nt*tile_elems*sizeof(float), cudaMemcpyDeviceToHost, es) != cudaSuccess) {status = tw_set_error(ctx, TW_ERR_CUDA, "D2H");}
 	}
-	cudaError_t e0 = cudaStreamSynchronize(ctx->stream), e1 = cudaStreamSynchronize(ctx->aux_stream[0]), e2 = cudaStreamSynchronize(ctx->aux_stream[1]);
+	cudaError_t e0 = cudaStreamSynchronize(ctx->stream), e1 = cudaStreamSynchronize(ctx->aux_stream[0]), e2 = cudaStreamSynchronize(ctx->aux_stream[1]), e3 = cudaStreamSynchronize(ctx->aux_stream[2]);
 	for (cudaEvent_t e : ev) {if (e) cudaEventDestroy(e);}
 	if (status) return status;
-	if (e0 != cudaSuccess || e1 != cudaSuccess || e2 != cudaSuccess) return tw_set_error(ctx, TW_ERR_CUDA, "tile pipeline: %s", cudaGetErrorString(e0 != cudaSuccess ? e0 : (e1 != cudaSuccess ? e1 : e2)));
+	if (e0 != cudaSuccess || e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) return tw_set_error(ctx, TW_ERR_CUDA, "tile pipeline: %s", cudaGetErrorString(e0 != cudaSuccess ? e0 : (e1 != cudaSuccess ? e1 : (e2 != cudaSuccess ? e2 : e3))));
+	if (!dev_out && d_perm) {TW_CUDA(ctx, cudaMemcpy(out, d_out, n*sizeof(float), cudaMemcpyDeviceToHost));} // schedule order scatters a chunk over the whole buffer: one copy at the end
 	unsigned long long h_steps = 0;
 	TW_CUDA(ctx, cudaMemcpy(&h_steps, d_steps, sizeof(h_steps), cudaMemcpyDeviceToHost));
 	ctx->last_erosion_steps = h_steps;

@@ -27,18 +27,22 @@ __device__ __forceinline__ int clampi(int v, int hi) {return max(min(v, hi), 0);
 
 struct EParams {
 	float erode_amount, wpz_minus_half_dxy, zmin, zrange, relh_adj_tex, clip_hd1;
+	float rock_min;   // get_bare_ls_tid(nh) == ROCK_TEX  <=>  nh >= rock_min (see make_eparams); rock_exact == 0: evaluate the reference expression per move
+	int   rock_exact;
 };
 
 // Also counts, per heightmap, the cells above the ocean-stop level (src/erosion.cpp:98): droplets that start below it die in one move, the
 // others walk downhill, so this count predicts the heightmap's total droplet work (correlation 0.95 on the BASELINE terrain) and is used to
 // schedule the heaviest heightmaps first (the work per heightmap is heavy-tailed: median 3, mean 26, max > 140 moves per droplet).
-__global__ void pad_kernel(const float *__restrict__ in, float *__restrict__ out, int xsize, int ysize, int NX, int NY, float work_level, unsigned *__restrict__ work) {
+// perm (optional): heightmap z of this batch lives at slot perm[z] of `in` (the tile pipeline's schedule order -> caller's tile index)
+__global__ void pad_kernel(const float *__restrict__ in, float *__restrict__ out, int xsize, int ysize, int NX, int NY, float work_level, unsigned *__restrict__ work,
+	const unsigned *__restrict__ perm = nullptr) {
 	int const x = blockIdx.x*blockDim.x + threadIdx.x, y = blockIdx.y;
-	size_t const tile = blockIdx.z;
+	size_t const tile = blockIdx.z, src_tile = perm ? __ldg(perm + blockIdx.z) : blockIdx.z;
 	bool above = false;
 	if (x < NX) {
 		int const sx = clampi(x - PAD, xsize - 1), sy = clampi(y - PAD, ysize - 1);
-		float const v = __ldg(in + tile*xsize*ysize + (size_t)sy*xsize + sx);
+		float const v = __ldg(in + src_tile*xsize*ysize + (size_t)sy*xsize + sx);
 		out[tile*NX*NY + (size_t)y*NX + x] = v;
 		above = !(v < work_level);
 	}
@@ -71,13 +75,13 @@ __global__ void order_scatter_kernel(const unsigned *__restrict__ work, unsigned
 }
 
 __global__ void unpad_kernel(const float *__restrict__ padded, float *__restrict__ out, int xsize, int ysize, int NX, int NY,
-	const float *__restrict__ min_zvals, float min_zval_all)
+	const float *__restrict__ min_zvals, float min_zval_all, const unsigned *__restrict__ perm = nullptr)
 {
 	int const x = blockIdx.x*blockDim.x + threadIdx.x, y = blockIdx.y;
-	size_t const tile = blockIdx.z;
+	size_t const tile = blockIdx.z, dst_tile = perm ? __ldg(perm + blockIdx.z) : blockIdx.z;
 	if (x >= xsize) return;
 	float const mz = min_zvals ? __ldg(min_zvals + tile) : min_zval_all;
-	out[tile*xsize*ysize + (size_t)y*xsize + x] = smax(mz, padded[tile*NX*NY + (size_t)(y + PAD)*NX + x + PAD]);
+	out[dst_tile*xsize*ysize + (size_t)y*xsize + x] = smax(mz, padded[tile*NX*NY + (size_t)(y + PAD)*NX + x + PAD]);
 }
 
 // rand_gen_t core (src/rand_gen.h:22-26) in 32-bit: all intermediates fit (Schrage factorisation), states stay in [0, 2^31)
@@ -142,6 +146,7 @@ struct DArgs {
 	const float2 *dir_table;
 	unsigned long long *steps_out;
 	const unsigned *order;      // heaviest-first schedule (slot -> map) or nullptr
+	const unsigned *perm;       // M_WHOLE: map t of this batch lives at slot perm[t] of `maps` (nullptr: slot t)
 	unsigned *next_droplet;     // M_ATOMIC: the dynamic,1 droplet counter
 	int WX, WY, P;              // M_WINDOW / M_WHOLE: window extent and row pitch in floats (M_WHOLE: WX = NX, WY = NY)
 	unsigned win_elems;         // floats of shared memory per lane group
@@ -161,8 +166,11 @@ droplet_kernel(DArgs const A)
 	// M_FROZEN shares M_WINDOW's machinery: the window is the droplet's PRIVATE view (sweep-start heights + its own writes); see hadd
 	constexpr int TPW = 32/G; // heightmaps per warp
 	extern __shared__ __align__(16) float tw_smem[];
-	int const lane = threadIdx.x & 31, sub = lane % G, grp = lane / G;
-	unsigned const wib = threadIdx.x >> 5;
+	// the thread index is passed through a warp shuffle once: a shuffle result cannot be rematerialised, so ptxas keeps lane / sub in registers instead of
+	// re-reading SR_TID.X (S2R, ~25 cycles) three times per move on the droplet's serial chain, as the round-1 SASS did
+	unsigned const tid_once = (unsigned)__shfl_sync(0xffffffffu, (int)threadIdx.x, (int)(threadIdx.x & 31));
+	int const lane = tid_once & 31, sub = lane % G, grp = lane / G;
+	unsigned const wib = tid_once >> 5;
 	unsigned const gslot = (blockIdx.x*(blockDim.x >> 5) + wib)*TPW + grp;       // position in this launch's part of the heaviest-first schedule
 	bool active = (gslot < A.nslots);
 	unsigned const tile = active ? (A.order ? __ldg(A.order + A.slot0 + gslot) : (A.slot0 + gslot)) : 0u;
@@ -193,7 +201,7 @@ droplet_kernel(DArgs const A)
 
 	if (WHOLE) { // build the padded map in shared memory from the caller's tile (src/erosion.cpp:31-37)
 		if (active) {
-			const float *src = A.maps + (size_t)tile*xsize*ysize;
+			const float *src = A.maps + (size_t)(A.perm ? __ldg(A.perm + tile) : tile)*xsize*ysize;
 #pragma unroll 4
 			for (int y = 0; y < NY; ++y) {
 				const float *row = src + (size_t)clampi(y - PAD, ysize - 1)*xsize;
@@ -215,10 +223,14 @@ droplet_kernel(DArgs const A)
 		float const *p = mh + ((size_t)NX*cz + cx);
 		return SHARED ? __ldcg(p) : *p;
 	};
-	// hadd(x, z, delta): read-modify-write of the in-array cell (x, z); window modes write through to global memory
-	auto hadd = [&](int x, int z, float delta) {
-		if (WHOLE) {win[z*P + x] += delta; return;}
+	// hadd(x, z, delta, pred): read-modify-write of the in-array cell (x, z) where pred holds. In the plain modes EVERY lane computes the address and loads
+	// (x, z are valid for all lanes) and only the store is predicated: no divergent region around the 4 deposit / 16 brush lanes, which in the round-1
+	// kernel cost a BSSY/BSYNC pair and two branches per read-modify-write on the droplet's serial chain. Window modes write through to global memory.
+	auto hadd = [&](int x, int z, float delta, bool pred) {
+		if (WHOLE) {float *q = win + (z*P + x); float const nv = *q + delta; if (pred) {*q = nv;} return;}
 		float *p = mh + ((size_t)NX*z + x);
+		if (MODE == M_GLOBAL) {float const nv = *p + delta; if (pred) {*p = nv;} return;}
+		if (!pred) return;
 		if (WIN && have_win) {
 			unsigned const rx = (unsigned)(x - wx0), rz = (unsigned)(z - wz0);
 			if (rx < (unsigned)WX && rz < (unsigned)WY) {
@@ -234,13 +246,17 @@ droplet_kernel(DArgs const A)
 		if (SHARED) {atomicAdd(p, delta);} else {*p += delta;}
 	};
 	// DEPOSIT(H): src/erosion.cpp:42-54; corner c of the 2x2 cell goes to lane c % G (inside cells are distinct => no aliasing between lanes)
+	// corner c of the 2x2 cell: lanes c, c + DG, ... of the group with DG = min(G, 4); lanes >= 4 of a wide group shadow lanes 0-3 with the store predicated off
 #define DEPOSIT(H) { \
+	constexpr int DG = (G < 4) ? G : 4; \
 	_Pragma("unroll") \
-	for (int c = sub; c < 4; c += G) { \
+	for (int c0 = 0; c0 < 4; c0 += DG) { \
+		int const c = c0 + (sub & (DG - 1)); \
 		int const X = xi + (c & 1), Z = zi + (c >> 1); \
 		float const W = ((c & 1) ? xf : (1-xf))*((c >> 1) ? zf : (1-zf)); \
 		float const delta = ds*erode_amount*W; \
-		if ((unsigned)X < (unsigned)NX && (unsigned)Z < (unsigned)NY) {hadd(X, Z, delta);} \
+		bool const inside = ((unsigned)X < (unsigned)NX && (unsigned)Z < (unsigned)NY); \
+		hadd(clampi(X, NX-1), clampi(Z, NY-1), delta, inside && (G <= 4 || sub < 4)); \
 	} \
 	if (G > 1) {__syncwarp(gmask);} \
 	(H) += ds; }
@@ -347,21 +363,24 @@ droplet_kernel(DArgs const A)
 				ds*=-Kr;
 				ds=smin(ds, dh*0.99f);
 				{ // get_bare_ls_tid(nh) == ROCK_TEX ? 0.5 : 2.0 (src/Textures.cpp:1284-1287); x0.5 / x2 are exact in fp32
-					float const relh = E.relh_adj_tex + __fdiv_rn(nh - E.zmin, E.zrange);
-					ds *= (relh > E.clip_hd1) ? 0.5f : 2.0f;
+					bool rock;
+					if (E.rock_exact) {rock = (nh >= E.rock_min);} // the reference predicate is monotone in nh: one compare against its host-found threshold
+					else {float const relh = E.relh_adj_tex + __fdiv_rn(nh - E.zmin, E.zrange); rock = (relh > E.clip_hd1);}
+					ds *= rock ? 0.5f : 2.0f;
 				}
 				bool const interior = ((unsigned)(xi - 1) < (unsigned)(NX - 3) && (unsigned)(zi - 1) < (unsigned)(NY - 3));
-				if (interior || G == 1) { // 16 distinct cells dealt to the lanes of the group (G == 1: the reference's serial loop, clamped)
+				if (interior || G == 1) { // 16 distinct cells dealt to the lanes of the group (G == 1: the reference's serial loop, clamped); uniform control flow, predicated stores
+					constexpr int BG = (G < 16) ? G : 16;
 #pragma unroll
-					for (int c = sub; c < 16; c += G) {
+					for (int c0 = 0; c0 < 16; c0 += BG) {
+						int const c = c0 + (sub & (BG - 1));
 						int const x = xi + (c & 3) - 1, z = zi + (c >> 2) - 1;
 						float const zo=(float)z-zp, zo2=zo*zo, xo=(float)x-xp;
 						float wgt=1-(xo*xo+zo2)*0.25f;
-						if (!(wgt<=0)) {
-							wgt*=0.1591549430918953f;
-							float const delta=ds*erode_amount*wgt;
-							if (interior) {hadd(x, z, -delta);} else {hadd(clampi(x, NX-1), clampi(z, NY-1), -delta);}
-						}
+						bool const on = !(wgt<=0) && (G <= 16 || sub < 16);
+						wgt*=0.1591549430918953f;
+						float const delta=ds*erode_amount*wgt;
+						if (interior) {hadd(x, z, -delta, on);} else {hadd(clampi(x, NX-1), clampi(z, NY-1), -delta, on);}
 					}
 				}
 				else if (sub == 0) { // border: clamped indices may alias, keep the reference's serial order
@@ -373,7 +392,7 @@ droplet_kernel(DArgs const A)
 							if (wgt<=0) continue;
 							wgt*=0.1591549430918953f;
 							float const delta=ds*erode_amount*wgt;
-							hadd(clampi(x, NX-1), clampi(z, NY-1), -delta);
+							hadd(clampi(x, NX-1), clampi(z, NY-1), -delta, true);
 						}
 					}
 				}
@@ -391,7 +410,7 @@ droplet_kernel(DArgs const A)
 	if (WHOLE && have_tile) { // remove padding and clamp to min_zval (src/erosion.cpp:158-162)
 		__syncwarp(gmask);
 		float const mz = A.min_zvals ? __ldg(A.min_zvals + tile) : A.min_zval_all;
-		float *dst = A.maps + (size_t)tile*xsize*ysize;
+		float *dst = A.maps + (size_t)(A.perm ? __ldg(A.perm + tile) : tile)*xsize*ysize;
 #pragma unroll 4
 		for (int y = 0; y < ysize; ++y) {
 			float const *srow = win + (y + PAD)*P + PAD;
@@ -472,12 +491,44 @@ int env_mode() { // TW_EROSION_MODE = global | window | whole (tests and tuning;
 
 } // namespace
 
+// get_bare_ls_tid(z) == ROCK_TEX  <=>  relh_adj_tex + (z - zmin)/(zmax - zmin) > clip_hd1 (src/Textures.cpp:1284-1287), evaluated in fp32 with the
+// reference's operation order. For zmax > zmin every step (rounded subtraction of a constant, rounded division by a positive constant, rounded addition
+// of a constant) is monotone non-decreasing in z, so the predicate is a step function of z: false below some float T, true from T on. T is found on the
+// host by bisection over the ordered bit patterns of ALL floats (-inf .. +inf) with the same IEEE operations (this file is compiled without FMA
+// contraction or fast-math, host side included); the kernel then tests z >= T - one compare instead of FADD, FCHK + MUFU.RCP + 5 FFMA (+ slow path), FADD,
+// FSETP on the droplet's dependency chain. NaN z: both forms are false. Anything not provably monotone (zmax <= zmin, NaN parameters) keeps the expression.
+static inline bool rock_pred(float z, float adj, float zmin, float zrange, float clip) {
+	volatile float d = z - zmin;      // volatile: no algebraic simplification across the three rounded steps
+	volatile float q = d/zrange;
+	volatile float r = adj + q;
+	return r > clip;
+}
+static inline float ord2float(uint32_t u) { // order-preserving bijection uint32 -> float (inverse of tw_f2ord), NaNs excluded by the search range
+	uint32_t const b = (u & 0x80000000u) ? (u & 0x7fffffffu) : ~u;
+	float f; memcpy(&f, &b, 4); return f;
+}
 static EParams make_eparams(const tw_erosion_params *p) {
 	EParams E;
 	E.erode_amount = p->erode_amount;
 	E.wpz_minus_half_dxy = p->water_plane_z - p->half_dxy;
 	E.zmin = p->zmin; E.zrange = p->zmax - p->zmin;
 	E.relh_adj_tex = p->relh_adj_tex; E.clip_hd1 = p->clip_hd1;
+	E.rock_min = 0.0f; E.rock_exact = 0;
+	if (E.zrange > 0.0f && E.zrange < INFINITY && E.zmin == E.zmin && fabsf(E.zmin) < INFINITY && E.relh_adj_tex == E.relh_adj_tex && E.clip_hd1 == E.clip_hd1) {
+		uint32_t const lo_u = tw_f2ord(-INFINITY), hi_u = tw_f2ord(INFINITY); // ordered keys: lo_u < hi_u, every float in between is a non-NaN
+		if (!rock_pred(INFINITY, E.relh_adj_tex, E.zmin, E.zrange, E.clip_hd1)) {E.rock_min = NAN; E.rock_exact = 1;} // never rock: z >= NaN is always false
+		else {
+			uint32_t lo = lo_u, hi = hi_u; // invariant: pred(hi) true; smallest true key in [lo, hi]
+			while (lo < hi) {
+				uint32_t const mid = lo + (hi - lo)/2;
+				if (rock_pred(ord2float(mid), E.relh_adj_tex, E.zmin, E.zrange, E.clip_hd1)) {hi = mid;} else {lo = mid + 1;}
+			}
+			E.rock_min = ord2float(hi); E.rock_exact = 1;
+			// -0.0 and +0.0 are distinct keys but equal floats: if the step sits between them, z >= +0.0 also accepts -0.0 - keep the expression then
+			if (E.rock_min == 0.0f && rock_pred(-0.0f, E.relh_adj_tex, E.zmin, E.zrange, E.clip_hd1) != rock_pred(0.0f, E.relh_adj_tex, E.zmin, E.zrange, E.clip_hd1)) {E.rock_exact = 0;}
+		}
+	}
+	if (getenv("TW_EROSION_NO_ROCK_THRESHOLD")) {E.rock_exact = 0;}
 	return E;
 }
 
@@ -525,7 +576,8 @@ size_t twi_erode_scratch_bytes(uint32_t chunk, int xsize, int ysize) {
 // Enqueue the erosion of nt <= 65535 heightmaps on `st`, using `scratch` (twi_erode_scratch_bytes(capacity,..) bytes). `lane` (0..2) selects
 // the context's fork/join stream for the heavy part. No synchronisation; d_steps (device counter) accumulates the droplet moves.
 int twi_erode_enqueue(tw_ctx *ctx, cudaStream_t st, int lane, void *scratch, uint32_t capacity, float *maps, uint32_t nt, int xsize, int ysize,
-                      const float *d_min_zvals, float min_zval_all, uint32_t num_iters, const tw_erosion_params *p, unsigned long long *d_steps)
+                      const float *d_min_zvals, float min_zval_all, uint32_t num_iters, const tw_erosion_params *p, unsigned long long *d_steps,
+                      const unsigned *d_perm)
 {
 	int const NX = xsize + 2*PAD, NY = ysize + 2*PAD;
 	size_t const padded_elems = (size_t)NX*NY;
@@ -535,7 +587,7 @@ int twi_erode_enqueue(tw_ctx *ctx, cudaStream_t st, int lane, void *scratch, uin
 	A.xsize = xsize; A.ysize = ysize; A.num_iters = num_iters; A.dir_table = ctx->d_dir_table; A.steps_out = d_steps;
 	A.min_zvals = d_min_zvals; A.min_zval_all = min_zval_all;
 	if (plan_whole(nt, xsize, ysize)) { // whole maps in shared memory, straight from / to the caller's tiles
-		A.maps = maps; A.slot0 = 0; A.nslots = nt;
+		A.maps = maps; A.slot0 = 0; A.nslots = nt; A.perm = d_perm;
 		A.WX = NX; A.WY = NY; A.P = whole_pitch(NX, NY); A.win_elems = (unsigned)A.P*NY;
 		launch_droplets_g<M_WHOLE>(pick_smem_group(), st, A, 1, (size_t)A.win_elems*sizeof(float));
 		TW_LAUNCH_CHECK(ctx);
@@ -546,17 +598,9 @@ int twi_erode_enqueue(tw_ctx *ctx, cudaStream_t st, int lane, void *scratch, uin
 	unsigned *d_work = (unsigned *)((char *)scratch + pad_bytes), *d_hist = d_work + capacity, *d_order = d_hist + WORK_BINS;
 	bool const schedule = (nt > 148u*4u); // with few heightmaps everything is resident at once anyway
 	if (schedule) {TW_CUDA(ctx, cudaMemsetAsync(d_work, 0, ((size_t)capacity + WORK_BINS)*sizeof(unsigned), st));}
-	pad_kernel<<<dim3((NX + 255)/256, NY, nt), 256, 0, st>>>(maps, d_pad, xsize, ysize, NX, NY, A.E.wpz_minus_half_dxy, schedule ? d_work : nullptr);
+	pad_kernel<<<dim3((NX + 255)/256, NY, nt), 256, 0, st>>>(maps, d_pad, xsize, ysize, NX, NY, A.E.wpz_minus_half_dxy, schedule ? d_work : nullptr, d_perm);
 	TW_LAUNCH_CHECK(ctx);
-	if (schedule) {
-		unsigned const max_work = (unsigned)padded_elems;
-		order_hist_kernel<<<(nt + 255)/256, 256, 0, st>>>(d_work, nt, max_work, d_hist);
-		TW_LAUNCH_CHECK(ctx);
-		order_scan_kernel<<<1, 32, 0, st>>>(d_hist);
-		TW_LAUNCH_CHECK(ctx);
-		order_scatter_kernel<<<(nt + 255)/256, 256, 0, st>>>(d_work, nt, max_work, d_hist, d_order);
-		TW_LAUNCH_CHECK(ctx);
-	}
+	if (schedule) {int const rc = twi_order_by_work(ctx, st, d_work, nt, (unsigned)padded_elems, d_hist, d_order); if (rc) return rc;}
 	else {d_order = nullptr;}
 	A.padded = d_pad; A.order = d_order;
 	uint32_t const heavy = plan_heavy(nt);
@@ -586,7 +630,18 @@ int twi_erode_enqueue(tw_ctx *ctx, cudaStream_t st, int lane, void *scratch, uin
 		TW_LAUNCH_CHECK(ctx);
 	}
 	if (fork) {TW_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_join[lane], 0));}
-	unpad_kernel<<<dim3((xsize + 255)/256, ysize, nt), 256, 0, st>>>(d_pad, maps, xsize, ysize, NX, NY, d_min_zvals, min_zval_all);
+	unpad_kernel<<<dim3((xsize + 255)/256, ysize, nt), 256, 0, st>>>(d_pad, maps, xsize, ysize, NX, NY, d_min_zvals, min_zval_all, d_perm);
+	TW_LAUNCH_CHECK(ctx);
+	return TW_OK;
+}
+
+// heaviest-first order of nt items by their work estimate (counting sort, 256 bins); d_hist256 is zeroed by the caller
+int twi_order_by_work(tw_ctx *ctx, cudaStream_t st, const unsigned *d_work, uint32_t nt, unsigned max_work, unsigned *d_hist256, unsigned *d_order) {
+	order_hist_kernel<<<(nt + 255)/256, 256, 0, st>>>(d_work, nt, max_work, d_hist256);
+	TW_LAUNCH_CHECK(ctx);
+	order_scan_kernel<<<1, 32, 0, st>>>(d_hist256);
+	TW_LAUNCH_CHECK(ctx);
+	order_scatter_kernel<<<(nt + 255)/256, 256, 0, st>>>(d_work, nt, max_work, d_hist256, d_order);
 	TW_LAUNCH_CHECK(ctx);
 	return TW_OK;
 }

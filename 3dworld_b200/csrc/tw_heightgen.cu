@@ -45,6 +45,9 @@ struct PostParams {
 	float volcano_freq;          // mesh_scale/volcano_width
 	float mesh_scale_z_inv;
 	float mdx, mdy, dx_inv, dy_inv; // grid step, DX_VAL_INV, DY_VAL_INV
+	const unsigned *tile_perm;   // tile batches: tile z of the launch is written to slot tile_perm[z] of `out` (nullptr: slot z) - the heaviest-first pipeline generates in
+	                             // schedule order but stores every tile at its caller-visible index
+	unsigned ngroups;            // packed noise kernels: number of chunk groups (blockDim x NCH x 2 cells each) in the band being generated
 	unsigned skip_x0, skip_y0, skip_w, skip_h; // cells [skip_x0, +skip_w) x [skip_y0, +skip_h) of every grid are left unwritten (skip_w == 0: none): the
 	                             // inside of an AO context grid, which calc_mesh_ao_lighting overwrites with the tile's zvals (src/tiled_mesh.cpp:627)
 };
@@ -254,12 +257,12 @@ noise_grid2_kernel(float *__restrict__ out, unsigned nx, unsigned ny, unsigned y
 	constexpr unsigned NCH = WARP ? 1 : 4;
 	// blocks stride over the chunk groups of the band: with gridDim.x == number of groups every block does exactly one (the default); a smaller
 	// grid (TW_NOISE2_PERSISTENT: one wave of resident blocks) keeps the staged table for many chunks
-	size_t const ngroups = ((c_end - (size_t)y_off*nx + 1)/2 + (size_t)blockDim.x*NCH - 1)/((size_t)blockDim.x*NCH);
+	// P.ngroups = chunk groups of this band (host-computed: a 64-bit division per thread here cost 2.5 % of the whole kernel)
 #pragma unroll 1
-	for (size_t grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
+	for (unsigned grp = blockIdx.x; grp < P.ngroups; grp += gridDim.x) {
 #pragma unroll 1
 	for (unsigned ch = 0; ch < NCH; ++ch) {
-	size_t const c0 = (size_t)y_off*nx + 2*((grp*NCH + ch)*blockDim.x + threadIdx.x);
+	size_t const c0 = (size_t)y_off*nx + 2*(((size_t)grp*NCH + ch)*blockDim.x + threadIdx.x);
 	unsigned y, x;
 	if (c_end <= 0xffffffffull) {unsigned const c32 = (unsigned)c0; y = c32/nx; x = c32 - y*nx;} // 32-bit division for every grid below 2^32 cells
 	else {y = (unsigned)(c0/nx); x = (unsigned)(c0 - (size_t)y*nx);}
@@ -304,7 +307,7 @@ noise_grid2_kernel(float *__restrict__ out, unsigned nx, unsigned ny, unsigned y
 		}
 		z0 = glaciate_and_bias(z0, smx0, smy0, xval.x, yval.x, P, sin_tab);
 		z1 = glaciate_and_bias(z1, smx1, smy1, xval.y, yval.y, P, sin_tab);
-		float *o = out + (size_t)tile*nx*ny + c0;
+		float *o = out + (size_t)(P.tile_perm ? __ldg(P.tile_perm + tile) : tile)*nx*ny + c0;
 		if (valid1 && ((reinterpret_cast<size_t>(o) & 7) == 0)) {*reinterpret_cast<float2 *>(o) = make_float2(z0, z1);}
 		else {o[0] = z0; if (valid1) {o[1] = z1;}}
 	}
@@ -464,14 +467,27 @@ __global__ void minmax_kernel(const float *__restrict__ v, size_t n, unsigned *m
 	block_minmax(vmin, vmax, mm);
 }
 
-// one block per heightmap: min/max of tile t -> mm[2t], mm[2t+1] (ordered-uint encoding)
-__global__ void minmax_tiles_kernel(const float *__restrict__ v, size_t tile_elems, unsigned *mm) {
-	const float *t = v + (size_t)blockIdx.x*tile_elems;
-	if (threadIdx.x == 0) {mm[2*blockIdx.x] = 0xffffffffu; mm[2*blockIdx.x + 1] = 0u;}
+// one block per heightmap: min/max of tile t -> mm[2t], mm[2t+1] (ordered-uint encoding); perm: block b handles tile perm[b] of v and mm
+__global__ void minmax_tiles_kernel(const float *__restrict__ v, size_t tile_elems, unsigned *mm, const unsigned *__restrict__ perm) {
+	size_t const tile = perm ? __ldg(perm + blockIdx.x) : blockIdx.x;
+	const float *t = v + tile*tile_elems;
+	if (threadIdx.x == 0) {mm[2*tile] = 0xffffffffu; mm[2*tile + 1] = 0u;}
 	__syncthreads();
 	float vmin = INFINITY, vmax = -INFINITY;
 	for (size_t i = threadIdx.x; i < tile_elems; i += blockDim.x) {float const z = __ldg(t + i); vmin = fminf(vmin, z); vmax = fmaxf(vmax, z);}
-	block_minmax(vmin, vmax, mm + 2*blockIdx.x);
+	block_minmax(vmin, vmax, mm + 2*tile);
+}
+// coarse work estimate of the tile pipeline: number of the C*C coarse samples of a tile above the ocean-stop level, gathered origins in schedule order
+__global__ void coarse_work_kernel(const float *__restrict__ coarse, unsigned cells, unsigned nt, float level, unsigned *__restrict__ work) {
+	unsigned const t = blockIdx.x*blockDim.x + threadIdx.x;
+	if (t >= nt) return;
+	unsigned n = 0;
+	for (unsigned i = 0; i < cells; ++i) {n += !(__ldg(coarse + (size_t)t*cells + i) < level);}
+	work[t] = n;
+}
+__global__ void gather_origins_kernel(const float2 *__restrict__ org, const unsigned *__restrict__ order, unsigned nt, float2 *__restrict__ out) {
+	unsigned const t = blockIdx.x*blockDim.x + threadIdx.x;
+	if (t < nt) {out[t] = org[order[t]];}
 }
 
 template<bool SIMPLEX, bool WARP>
@@ -493,8 +509,18 @@ int twi_init_minmax(tw_ctx *ctx, unsigned *d_mm_ord, uint32_t n) {
 	return TW_OK;
 }
 
-int twi_minmax_tiles(tw_ctx *ctx, cudaStream_t st, const float *d_vals, size_t tile_elems, uint32_t nt, unsigned *d_mm_ord) {
-	minmax_tiles_kernel<<<nt, 256, 0, st>>>(d_vals, tile_elems, d_mm_ord);
+int twi_minmax_tiles(tw_ctx *ctx, cudaStream_t st, const float *d_vals, size_t tile_elems, uint32_t nt, unsigned *d_mm_ord, const unsigned *d_perm) {
+	minmax_tiles_kernel<<<nt, 256, 0, st>>>(d_vals, tile_elems, d_mm_ord, d_perm);
+	TW_LAUNCH_CHECK(ctx);
+	return TW_OK;
+}
+int twi_coarse_work(tw_ctx *ctx, const float *d_coarse, unsigned cells, uint32_t nt, float level, unsigned *d_work) {
+	coarse_work_kernel<<<(nt + 127)/128, 128, 0, ctx->stream>>>(d_coarse, cells, nt, level, d_work);
+	TW_LAUNCH_CHECK(ctx);
+	return TW_OK;
+}
+int twi_gather_origins(tw_ctx *ctx, const void *d_org, const unsigned *d_order, uint32_t nt, void *d_out) {
+	gather_origins_kernel<<<(nt + 255)/256, 256, 0, ctx->stream>>>((const float2 *)d_org, d_order, nt, (float2 *)d_out);
 	TW_LAUNCH_CHECK(ctx);
 	return TW_OK;
 }
@@ -587,6 +613,8 @@ int twi_heightgen(tw_ctx *ctx, const tw_grid2d *g, const tw_height_params *p, in
 
 	PostParams P = make_post_params(p, enable_glaciate, dx, dy);
 	P.skip_x0 = ctx->skip_rect[0]; P.skip_y0 = ctx->skip_rect[1]; P.skip_w = ctx->skip_rect[2]; P.skip_h = ctx->skip_rect[3];
+	P.tile_perm = ctx->tile_perm;
+	if (P.tile_perm && (p->gen_mode == TW_MGEN_SINE || getenv("TW_NOISE_SCALAR"))) return tw_set_error(ctx, TW_ERR_STATE, "internal: tile_perm is only wired into the packed noise kernels");
 
 	if (p->gen_mode != TW_MGEN_SINE) {
 		NoiseParams N;
@@ -603,6 +631,7 @@ int twi_heightgen(tw_ctx *ctx, const tw_grid2d *g, const tw_height_params *p, in
 				size_t const band_cells = (size_t)(r1 - r0)*nx;
 				size_t const cells_per_block = 2*TW_NOISE2_THREADS*(size_t)((p->gen_mode == TW_MGEN_DWARP_GPU) ? 1 : 4); // noise_grid2_kernel: NCH chunks of blockDim threads x 2 cells
 				unsigned gx = (unsigned)((band_cells + cells_per_block - 1)/cells_per_block);
+				P.ngroups = gx;
 #if TW_NOISE2_PERSISTENT
 				{unsigned const wave = 148u*TW_NOISE2_MIN_BLOCKS*TW_NOISE2_PERSISTENT; if (ntiles == 1 && gx > wave) gx = wave;} // TW_NOISE2_PERSISTENT waves' worth of resident blocks
 #endif

@@ -118,6 +118,9 @@ class mesh_xy_grid_cache_t {
 	mutable std::vector<float> vals;
 	mutable std::mutex mtx;
 	mutable bool have_vals = false, job_running = false;
+	mutable tw_ctx *job_ctx = nullptr;      // the context the pending job was launched on: a job launched on the main thread (build_arrays no_wait +
+	                                        // enable_glaciate) is collected on THAT context even when eval_index runs on an OpenMP worker, whose own
+	                                        // thread-local context has nothing pending and would report TW_OK at once
 	mutable int vals_min_start = 0; mutable bool vals_glaciate = false;
 	tw_grid2d grid = {0, 0, 1, 1, 0, 0};
 	int gen_mode = TW_MGEN_SINE, gen_shape = 0;
@@ -129,15 +132,15 @@ class mesh_xy_grid_cache_t {
 		tw_ctx *c = ctx();
 		int rc = tw_heightgen_2d_launch(c, &grid, &p, glaciate, min_start_sin, vals.data(), nullptr);
 		if (rc != TW_OK) {detail::fail(rc, "build_arrays", c);}
-		job_running = true; vals_glaciate = glaciate; vals_min_start = min_start_sin;
+		job_running = true; job_ctx = c; vals_glaciate = glaciate; vals_min_start = min_start_sin;
 		if (wait) {collect(true);}
 	}
-	bool collect(bool wait) const {
-		tw_ctx *c = ctx();
+	bool collect(bool wait) const { // always called with mtx held
+		tw_ctx *c = job_ctx ? job_ctx : ctx();
 		int const rc = tw_heightgen_2d_poll(c, wait ? 1 : 0);
 		if (rc == TW_ERR_NOT_READY) return false;
 		if (rc != TW_OK) {detail::fail(rc, "eval_index", c);}
-		job_running = false; have_vals = true;
+		job_running = false; have_vals = true; job_ctx = nullptr;
 		return true;
 	}
 public:
@@ -159,7 +162,10 @@ public:
 			async_requested = true; // launched by enable_glaciate(), which setup_height_gen_async always calls next (src/tiled_mesh.cpp:462)
 			return 0;
 		}
-		if (cache_values) {have_vals = false; launch(false, 0, true); /* cached_vals hold un-glaciated values (src/mesh_gen.cpp:633) */}
+		// cache_values: the reference fills cached_vals with un-glaciated values here (src/mesh_gen.cpp:627-636); every caller then calls enable_glaciate()
+		// and reads through eval_index, which applies the glaciation per cell - so the grid is evaluated once, lazily, in the state eval_index asks for,
+		// instead of once un-glaciated now and once more glaciated on the first eval_index
+		(void)cache_values;
 		return 1;
 	}
 	void enable_glaciate() {
@@ -171,7 +177,9 @@ public:
 		assert(x < grid.nx && y < grid.ny); // src/mesh_gen.cpp:756
 		(void)use_cache;
 		int const mss = (gen_mode == TW_MGEN_SINE) ? min_start_sin : 0;
-		if (!(have_vals && !job_running && vals_glaciate == do_glaciate && vals_min_start == mss)) {
+		bool ready;
+		{std::lock_guard<std::mutex> lock(mtx); ready = (have_vals && !job_running && vals_glaciate == do_glaciate && vals_min_start == mss);} // flags are only read under the mutex
+		if (!ready) {
 			std::lock_guard<std::mutex> lock(mtx);
 			if (job_running) {collect(true);}
 			if (!(have_vals && vals_glaciate == do_glaciate && vals_min_start == mss)) {have_vals = false; launch(do_glaciate, mss, true);}

@@ -113,7 +113,10 @@ typedef struct tw_voxel_params {
 /* ---- context ----
  * No reference counterpart: the reference keeps this state in process globals (sin_table src/sinf.h:11, sinTable src/mesh_gen.cpp:38,
  * the GL compute shader of mesh_xy_grid_cache_t src/mesh.h:33). One context = one device, one CUDA stream, its scratch buffers and the
- * uploaded tables; not re-entrant (use one per thread). tw_create fails with TW_ERR_NO_DEVICE when there is no GPU - there is no CPU fallback. */
+ * uploaded tables; not re-entrant (use one per thread). tw_create fails with TW_ERR_NO_DEVICE when there is no GPU - there is no CPU fallback.
+ * Every call makes the context's device the calling thread's current CUDA device (cudaSetDevice) and leaves it so.
+ * Host output buffers: asynchronous entry points (tw_heightgen_2d_launch) overlap the device->host copy with compute only when the buffer is
+ * page-locked (cudaHostAlloc / cudaHostRegister / tw_multi_alloc_host); with pageable memory the copy - and therefore the launch call - blocks. */
 TW_API int  tw_abi_version(void);
 TW_API int  tw_create(int device, tw_ctx **out);
 TW_API void tw_destroy(tw_ctx *ctx);
