@@ -401,7 +401,10 @@ int tw_create_zvals_batch(tw_ctx *ctx, const int32_t *origins_xy, uint32_t ntile
 	TW_CUDA(ctx, cudaMemGetInfo(&free_b, &total_b));
 	size_t budget = (free_b + ctx->scratch_bytes[1])/3/3;
 	if (budget < ((size_t)512 << 20)) budget = (size_t)512 << 20;
-	uint32_t want_chunks = (ntiles >= 4096) ? 8 : 1;
+	// measured on B200 (tools/bench_pipeline_chunks.py, profiles/pipeline_chunks_r02.txt), 258^2 tiles, 1000 droplets: 8192 tiles 0.144 / 0.132 / 0.126 / 0.120 /
+	// 0.128 / 0.179 s with 1 / 2 / 3 / 4 / 8 / 16 chunks (heaviest-first; in index order 4 chunks take 0.173 s); 65536 tiles 0.780 / 0.780 / 0.833 / 0.835 s with
+	// 1 / 2 / 3 / 4: when the batch saturates the machine anyway, generation and erosion compete for the same issue slots and extra chunks only add overhead
+	uint32_t want_chunks = (ntiles < 4096) ? 1 : ((ntiles <= 24576) ? 4 : 2);
 	if (const char *e = getenv("TW_PIPE_CHUNKS")) {int const v = atoi(e); if (v >= 1 && v <= 64) want_chunks = (uint32_t)v;}
 	uint32_t chunk = (ntiles + want_chunks - 1)/want_chunks;
 	uint32_t const cap = twi_erode_chunk_for(budget, chunk, (int)zvsize, (int)zvsize);

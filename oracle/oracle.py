@@ -48,6 +48,12 @@ class TileBounds(C.Structure):
                 ("radius", C.c_float), ("wx1", C.c_int32), ("wy1", C.c_int32), ("wx2", C.c_int32), ("wy2", C.c_int32)]
 
 
+class VoxelPostParams(C.Structure):
+    _fields_ = [("nx", C.c_uint32), ("ny", C.c_uint32), ("nz", C.c_uint32), ("lo_pos", C.c_float * 3), ("vsz", C.c_float * 3), ("isolevel", C.c_float),
+                ("invert", C.c_int), ("make_closed_surface", C.c_int), ("remove_unconnected", C.c_int), ("keep_at_edge", C.c_int), ("centre_seed", C.c_int),
+                ("skip_under_mesh", C.c_int)]
+
+
 class PointQuery(C.Structure):
     _fields_ = [("kind", C.c_int), ("xy_scale", C.c_float), ("mesh_x_size", C.c_int), ("mesh_y_size", C.c_int), ("x_scene_size", C.c_float),
                 ("y_scene_size", C.c_float), ("xoff2", C.c_int), ("yoff2", C.c_int), ("no_xyoff", C.c_int)]
@@ -117,6 +123,11 @@ def lib():
         L.to_apply_erosion.restype = C.c_ulonglong
         L.to_erode_sweeps.argtypes = [vp, C.c_int, C.c_int, C.c_float, C.c_uint, C.POINTER(ErosionParams), C.c_uint, C.c_int]
         L.to_erode_sweeps.restype = C.c_ulonglong
+        L.to_voxel_outside.argtypes = [vp, C.POINTER(VoxelPostParams), vp, vp]
+        L.to_voxel_remove_unconnected.argtypes = [vp, vp, C.POINTER(VoxelPostParams)]
+        L.to_voxel_remove_unconnected.restype = C.c_ulonglong
+        L.to_voxel_triangles.argtypes = [vp, vp, C.POINTER(VoxelPostParams), vp, vp, vp, vp, C.c_ulonglong]
+        L.to_voxel_triangles.restype = C.c_ulonglong
         L.to_noise3d_gen_sines.argtypes = [C.c_int, C.c_int, C.c_float, C.c_float, vp]
         L.to_noise3d_get_val_pt.argtypes = [vp, vp, C.c_float, C.c_float, C.c_float]
         L.to_noise3d_get_val_pt.restype = C.c_float
@@ -254,6 +265,31 @@ def voxel_fill(vp, rdata=None, nthreads=0):
     rd = None if rdata is None else np.ascontiguousarray(rdata, np.float32)
     lib().to_voxel_fill(C.byref(vp), None if rd is None else _p(rd), _p(sin_table()), _p(out), nthreads)
     return out
+
+
+def voxel_outside(vals, vpp, zix_xy=None):
+    vals = np.ascontiguousarray(vals, np.float32)
+    out = np.empty(vals.shape, np.uint8)
+    z = None if zix_xy is None else np.ascontiguousarray(zix_xy, np.uint32)
+    lib().to_voxel_outside(_p(vals), C.byref(vpp), None if z is None else _p(z), _p(out))
+    return out
+
+
+def voxel_remove_unconnected(vals, outside, vpp):
+    vals = np.array(vals, np.float32, order="C", copy=True)
+    outside = np.array(outside, np.uint8, order="C", copy=True)
+    changed = lib().to_voxel_remove_unconnected(_p(vals), _p(outside), C.byref(vpp))
+    return vals, outside, int(changed)
+
+
+def voxel_triangles(vals, outside, vpp, tables):
+    vals = np.ascontiguousarray(vals, np.float32)
+    outside = np.ascontiguousarray(outside, np.uint8)
+    e, t, v = (np.ascontiguousarray(tables[0], np.uint32), np.ascontiguousarray(tables[1], np.int32), np.ascontiguousarray(tables[2], np.uint32))
+    n = lib().to_voxel_triangles(_p(vals), _p(outside), C.byref(vpp), _p(e), _p(t), _p(v), None, 0)
+    tris = np.empty((n, 3, 3), np.float32)
+    lib().to_voxel_triangles(_p(vals), _p(outside), C.byref(vpp), _p(e), _p(t), _p(v), _p(tris), n)
+    return tris
 
 
 def from_floats_u16(vals, val_mult, val_add):

@@ -26,6 +26,12 @@ class Erosion(C.Structure):
     _fields_ = [(n, C.c_float) for n in ("erode_amount", "water_plane_z", "half_dxy", "zmin", "zmax", "relh_adj_tex", "clip_hd1")]
 
 
+class VoxParams(C.Structure):
+    _fields_ = [("nx", C.c_uint), ("ny", C.c_uint), ("nz", C.c_uint), ("vsz", C.c_float * 3), ("center", C.c_float * 3), ("isolevel", C.c_float),
+                ("invert", C.c_int), ("make_closed_surface", C.c_int), ("remove_unconnected", C.c_int), ("keep_at_scene_edge", C.c_int), ("atten_at_edges", C.c_int),
+                ("remove_under_mesh", C.c_int), ("use_mesh", C.c_int), ("radius_val", C.c_float), ("atten_thresh", C.c_float)]
+
+
 def available():
     return os.path.exists(LIB_PATH)
 
@@ -64,6 +70,16 @@ def lib():
             L.ref_tile_create_zvals.argtypes = [C.c_uint, C.c_int, C.c_int, C.c_uint, C.POINTER(Erosion), C.c_void_p, C.c_void_p, C.c_void_p]
             L.ref_tile_ao_lighting.argtypes = [C.c_uint, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p]
             L.ref_ao_ray_len.restype = C.c_uint
+        if hasattr(L, "ref_vox_init"):   # voxel_manager member functions cut out of src/voxels.cpp at build time
+            L.ref_vox_init.argtypes = [C.POINTER(VoxParams)]
+            L.ref_vox_create_procedural.argtypes = [C.c_float, C.c_float, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]
+            L.ref_vox_atten.argtypes = [C.c_int, C.c_float, C.c_float]
+            L.ref_vox_triangles.argtypes = [C.c_int, C.c_void_p, C.c_ulonglong, C.c_void_p]
+            L.ref_vox_triangles.restype = C.c_ulonglong
+            for n in ("ref_vox_get_lo_pos", "ref_vox_set_vals", "ref_vox_get_vals", "ref_vox_get_outside", "ref_vox_set_zmin_matrix", "ref_vox_zix"):
+                getattr(L, n).argtypes = [C.c_void_p]
+            L.ref_vox_tables.argtypes = [C.c_void_p] * 3
+            L.ref_vox_set_display_mode_bit.argtypes = [C.c_int]
         _lib = L
     return _lib
 
@@ -208,3 +224,82 @@ def tile_ao_lighting(size, x1, y1, zvals, ao_context=None, half_dxy=0.0625):
                                     C.c_float(half_dxy), ao.ctypes.data_as(C.c_void_p))
     assert rc == 0, rc
     return ao
+
+
+# ---- the reference's own voxel_manager (member functions cut out of src/voxels.cpp at build time) ----
+def has_voxel_extract():
+    return available() and hasattr(lib(), "ref_vox_init")
+
+
+class Vox:
+    """One voxel_manager of the reference: init(grid + voxel_params_t) then the steps of voxel_model::build (src/voxels.cpp:1496-1530)."""
+
+    def __init__(self, nx, ny, nz, vsz, center, isolevel=0.0, invert=0, make_closed_surface=1, remove_unconnected=1, keep_at_scene_edge=0, atten_at_edges=0,
+                 remove_under_mesh=0, use_mesh=0, radius_val=0.5, atten_thresh=1.0):
+        p = VoxParams()
+        p.nx, p.ny, p.nz = nx, ny, nz
+        for d in range(3):
+            p.vsz[d], p.center[d] = vsz[d], center[d]
+        p.isolevel, p.invert, p.make_closed_surface, p.remove_unconnected = isolevel, invert, make_closed_surface, remove_unconnected
+        p.keep_at_scene_edge, p.atten_at_edges, p.remove_under_mesh, p.use_mesh, p.radius_val, p.atten_thresh = keep_at_scene_edge, atten_at_edges, remove_under_mesh, use_mesh, radius_val, atten_thresh
+        self.p, self.shape = p, (ny, nx, nz)
+        lib().ref_vox_init(C.byref(p))
+
+    @property
+    def lo_pos(self):
+        lo = np.empty(3, np.float32)
+        lib().ref_vox_get_lo_pos(lo.ctypes.data_as(C.c_void_p))
+        return lo
+
+    def set_vals(self, v):
+        v = np.ascontiguousarray(v, np.float32)
+        assert v.shape == self.shape
+        lib().ref_vox_set_vals(v.ctypes.data_as(C.c_void_p))
+
+    def vals(self):
+        v = np.empty(self.shape, np.float32)
+        lib().ref_vox_get_vals(v.ctypes.data_as(C.c_void_p))
+        return v
+
+    def outside(self):
+        o = np.empty(self.shape, np.uint8)
+        lib().ref_vox_get_outside(o.ctypes.data_as(C.c_void_p))
+        return o
+
+    def create_procedural(self, mag, freq, offset, normalize_to_1, rs1, rs2, gen_mode):
+        off = np.asarray(offset, np.float32)
+        lib().ref_vox_create_procedural(mag, freq, off.ctypes.data_as(C.c_void_p), int(normalize_to_1), rs1, rs2, gen_mode)
+
+    def atten(self, mode, val, radius=0.5):
+        lib().ref_vox_atten(mode, val, radius)
+
+    def set_zmin_matrix(self, mesh):
+        lib().ref_vox_set_zmin_matrix(None if mesh is None else np.ascontiguousarray(mesh, np.float32).ctypes.data_as(C.c_void_p))
+
+    def zix(self):
+        z = np.empty((self.shape[0], self.shape[1]), np.uint32)
+        lib().ref_vox_zix(z.ctypes.data_as(C.c_void_p))
+        return z
+
+    def determine_outside(self):
+        lib().ref_vox_determine_outside()
+
+    def remove_unconnected(self):
+        lib().ref_vox_remove_unconnected()
+
+    def remove_interior_holes(self):
+        lib().ref_vox_remove_interior_holes()
+
+    def triangles(self, welded=False, want_counts=False):
+        """add_triangles_for_voxel over the grid: (tris [n, 3, 3] float32, per-voxel count_only counts or None)."""
+        counts = np.empty(self.shape, np.uint32) if want_counts else None
+        n = lib().ref_vox_triangles(int(welded), None, 0, None if counts is None else counts.ctypes.data_as(C.c_void_p))
+        tris = np.empty((n, 3, 3), np.float32)
+        lib().ref_vox_triangles(int(welded), tris.ctypes.data_as(C.c_void_p), n, None)
+        return tris, counts
+
+
+def mc_tables():
+    e, t, v = np.empty(256, np.uint32), np.empty((256, 16), np.int32), np.empty((12, 2), np.uint32)
+    lib().ref_vox_tables(e.ctypes.data_as(C.c_void_p), t.ctypes.data_as(C.c_void_p), v.ctypes.data_as(C.c_void_p))
+    return e, t, v

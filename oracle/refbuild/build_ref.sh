@@ -34,6 +34,24 @@ mkdir -p "$OUT/gen"
   cat "$HERE/ref_tiled_harness.inc"
 } > "$OUT/gen/tiled_extract.cpp"
 g++ $FLAGS $INC -I "$HERE" -c "$OUT/gen/tiled_extract.cpp" -o "$OUT/tiled_extract.o"
+# The same for the voxel path: voxels.cpp cannot be linked either (renderer, collision objects), but
+# voxel_manager itself is a plain container, so its member functions are cut out by signature: the include/constant block at the top of the file,
+# voxel_grid<V>::init_grid/init, voxel_manager::clear .. create_procedural (src/voxels.cpp:271-346), atten_at_edges .. remove_unconnected_outside()
+# (:403-610: the attenuation passes, interpolate_pt, add_triangles_for_voxel, val_is_outside, calc_outside_val, determine_voxels_outside) and
+# FLOOD_FILL_INNER .. make_voxel_inside (:729-868: the flood fills).
+V=$R/src/voxels.cpp
+{
+  echo "// GENERATED at build time by oracle/refbuild/build_ref.sh from $V - do not commit"
+  cat "$HERE/ref_tiled_prelude.inc"
+  awk '/^voxel_params_t global_voxel_params;/ {exit} {print}' "$V"
+  echo 'extern int dynamic_mesh_scroll, rand_gen_index, scrolling, display_mode, mesh_gen_mode, mesh_freq_filter; void gen_rx_ry(float &rx, float &ry); // declarations the cut-out functions need'
+  awk '/^template<typename V> void voxel_grid<V>::init_grid/ {p=1} /^\/\/ Note: assumes mesh is centered/ {exit} p {print}' "$V"
+  awk '/^void voxel_manager::clear\(\)/ {p=1} /^void voxel_manager::create_from_cobjs/ {exit} p {print}' "$V"
+  awk '/^void voxel_manager::atten_at_edges/ {p=1} p {print} p && /^void voxel_manager::remove_unconnected_outside\(\)/ {f=1} f && /^}/ {exit}' "$V"
+  awk '/^#define FLOOD_FILL_INNER/ {p=1} /^bool voxel_manager::point_inside_volume/ {exit} p {print}' "$V"
+  cat "$HERE/ref_voxels_harness.inc"
+} > "$OUT/gen/voxels_extract.cpp"
+g++ $FLAGS $INC -I "$HERE" -c "$OUT/gen/voxels_extract.cpp" -o "$OUT/voxels_extract.o"
 g++ -shared -fopenmp -Wl,--gc-sections -Wl,--no-undefined -Wl,--version-script="$HERE/exports.map" -o "$OUT/libref3dworld.so" \
-  "$OUT"/ref_driver.o "$OUT"/ref_stubs.o "$OUT"/ref_glm.o "$OUT"/mesh_gen.o "$OUT"/erosion.o "$OUT"/upsurface.o "$OUT"/heightmap.o "$OUT"/tiled_extract.o
+  "$OUT"/ref_driver.o "$OUT"/ref_stubs.o "$OUT"/ref_glm.o "$OUT"/mesh_gen.o "$OUT"/erosion.o "$OUT"/upsurface.o "$OUT"/heightmap.o "$OUT"/tiled_extract.o "$OUT"/voxels_extract.o
 echo "built $OUT/libref3dworld.so"

@@ -1063,3 +1063,163 @@ void to_to_floats_u16(const unsigned char *data, size_t n, float val_mult, float
 		vals[i] = val_mult*v + val_add;
 	}
 }
+
+
+/* ------------------------------------------------------------------ voxel post-processing
+ * Pinned against the reference's own voxel_manager member functions, cut out of src/voxels.cpp at build time (oracle/refbuild/build_ref.sh,
+ * tests/test_oracle_vs_reference.py). */
+static int val_is_outside(float val, float isolevel, int invert) { /* ref: src/voxels.cpp:571-574 */
+	return (val == isolevel) ? 1 : ((((val < isolevel) ? 1 : 0) ^ (invert ? 1 : 0)) ? 1 : 0);
+}
+void to_voxel_outside(const float *vals, const tw_voxel_post_params *vp, const unsigned *zix_xy, unsigned char *outside) { /* ref: :577-604 */
+	unsigned const nx = vp->nx, ny = vp->ny, nz = vp->nz;
+	for (unsigned y = 0; y < ny; ++y) {
+		for (unsigned x = 0; x < nx; ++x) {
+			unsigned const zix = zix_xy ? zix_xy[y*nx + x] : 0;
+			for (unsigned z = 0; z < nz; ++z) {
+				size_t const i = z + ((size_t)x + (size_t)y*nx)*nz;
+				int const on_edge = (vp->make_closed_surface && ((x == 0 || x == nx-1) || (y == 0 || y == ny-1) || (z == 0 || z == nz-1)));
+				unsigned char ival = on_edge ? TW_VOX_ON_EDGE : (unsigned char)val_is_outside(vals[i], vp->isolevel, vp->invert);
+				if (z < zix) {ival |= TW_VOX_UNDER_MESH;}
+				outside[i] = ival;
+			}
+		}
+	}
+}
+/* flood_fill_range (ref: :729-757) over the whole grid with an explicit stack */
+static void flood_fill(unsigned char *outside, unsigned nx, unsigned ny, unsigned nz, unsigned *work, size_t nwork, unsigned char fill_val, unsigned char bit_mask) {
+	unsigned const nxnz = nx*nz;
+	while (nwork) {
+		unsigned const cur = work[--nwork];
+		unsigned const y = cur/nxnz, cur_xz = cur - y*nxnz, x = cur_xz/nz, z = cur_xz - x*nz;
+#define FF_INNER(pos, max_range, step) \
+		if (pos >= 1)            {unsigned const ix = cur - step; if (outside[ix] == fill_val) {work[nwork++] = ix; outside[ix] |= bit_mask;}} \
+		if (pos + 1 < max_range) {unsigned const ix = cur + step; if (outside[ix] == fill_val) {work[nwork++] = ix; outside[ix] |= bit_mask;}}
+		FF_INNER(x, nx, nz)
+		FF_INNER(y, ny, nxnz)
+		FF_INNER(z, nz, 1)
+#undef FF_INNER
+	}
+}
+unsigned long long to_voxel_remove_unconnected(float *vals, unsigned char *outside, const tw_voxel_post_params *vp) {
+	unsigned const nx = vp->nx, ny = vp->ny, nz = vp->nz;
+	size_t const n = (size_t)nx*ny*nz;
+	unsigned long long changed = 0;
+	float const TOLERANCE = 1.0E-12f;
+	if (vp->remove_unconnected <= 0) return 0;
+	unsigned *work = (unsigned *)malloc((n + 1)*sizeof(unsigned)*2); /* a voxel is pushed at most once by the fill, seeds may be pushed twice */
+	size_t nwork = 0;
+	/* remove_unconnected_outside_range(keep_at_edge, 0, 0, nx, ny), ref: :759-827 */
+	if (vp->centre_seed) {
+		size_t const ix = (nz/2) + ((size_t)(nx/2) + (size_t)(ny/2)*nx)*nz;
+		work[nwork++] = (unsigned)ix; outside[ix] |= TW_VOX_ANCHORED;
+	}
+	else {
+		for (size_t ix = 0; ix < n; ++ix) {if (outside[ix] == TW_VOX_UNDER_MESH) {work[nwork++] = (unsigned)ix; outside[ix] |= TW_VOX_ANCHORED;}}
+	}
+	if (vp->keep_at_edge) {
+		for (unsigned y = 0; y < ny; ++y) {
+			for (unsigned x = 0; x < nx; ++x) {
+				if (x != 0 && x+1 != nx && y != 0 && y+1 != ny) continue;
+				for (unsigned z = 0; z < nz; ++z) {
+					size_t const ix = z + ((size_t)x + (size_t)y*nx)*nz;
+					if (outside[ix] == 1) continue;
+					if (!(outside[ix] & TW_VOX_ANCHORED)) {work[nwork++] = (unsigned)ix;} /* the reference pushes duplicates too; harmless either way */
+					outside[ix] |= TW_VOX_ANCHORED;
+				}
+			}
+		}
+	}
+	flood_fill(outside, nx, ny, nz, work, nwork, 0, TW_VOX_ANCHORED);
+	for (size_t ix = 0; ix < n; ++ix) {
+		if (outside[ix] > 1) {outside[ix] &= (unsigned char)~TW_VOX_ANCHORED;}
+		else if (outside[ix] != 1) { /* inside and not anchored: make_voxel_outside, ref: :861-864 */
+			outside[ix] = 1;
+			vals[ix] = vp->isolevel - (vp->invert ? -TOLERANCE : TOLERANCE);
+			++changed;
+		}
+	}
+	if (vp->remove_unconnected > 2) { /* remove_interior_holes, ref: :831-858 */
+		nwork = 0;
+		for (unsigned y = 0; y < ny; ++y) {
+			for (unsigned x = 0; x < nx; ++x) {
+				size_t const ix = (nz-1) + ((size_t)x + (size_t)y*nx)*nz;
+				if (outside[ix]) {work[nwork++] = (unsigned)ix; outside[ix] |= TW_VOX_ANCHORED;}
+			}
+		}
+		if (nwork) {
+			flood_fill(outside, nx, ny, nz, work, nwork, 1, TW_VOX_ANCHORED);
+			for (size_t ix = 0; ix < n; ++ix) {
+				if (outside[ix] & TW_VOX_ANCHORED) {outside[ix] &= (unsigned char)~TW_VOX_ANCHORED;}
+				else if (outside[ix] == 1) { /* make_voxel_inside, ref: :865-868 */
+					outside[ix] = 0;
+					vals[ix] = vp->isolevel + (vp->invert ? -TOLERANCE : TOLERANCE);
+					++changed;
+				}
+			}
+		}
+	}
+	free(work);
+	return changed;
+}
+/* interpolate_pt, ref: :485-493 */
+static void interpolate_pt(float isolevel, const float *pt1, const float *pt2, float val1, float val2, float *pt) {
+	float const TOLERANCE = 1.0E-12f;
+	if (fabsf(isolevel - val1) < TOLERANCE) {pt[0] = pt1[0]; pt[1] = pt1[1]; pt[2] = pt1[2]; return;}
+	if (fabsf(isolevel - val2) < TOLERANCE) {pt[0] = pt2[0]; pt[1] = pt2[1]; pt[2] = pt2[2]; return;}
+	if (fabsf(val1     - val2) < TOLERANCE) {pt[0] = pt1[0]; pt[1] = pt1[1]; pt[2] = pt1[2]; return;}
+	float const mu = std_max(0.0f, std_min(1.0f, (isolevel - val1)/(val2 - val1))); /* CLIP_TO_01 */
+	for (int i = 0; i < 3; ++i) {pt[i] = pt1[i] + mu*(pt2[i] - pt1[i]);}
+}
+/* add_triangles_for_voxel at lod 0 for every cube in (y, x, z) order, unwelded (ref: :495-566); returns the number of triangles produced */
+unsigned long long to_voxel_triangles(const float *vals, const unsigned char *outside, const tw_voxel_post_params *vp, const unsigned *edge_table, const int *tri_table,
+                                      const unsigned *edge_to_vals, float *tris, unsigned long long capacity)
+{
+	unsigned const nx = vp->nx, ny = vp->ny, nz = vp->nz;
+	unsigned long long n = 0;
+	for (unsigned y = 0; y < ny; ++y) {
+		for (unsigned x = 0; x < nx; ++x) {
+			for (unsigned z = 0; z < nz; ++z) {
+				unsigned const x2 = (x+1 < nx-1) ? x+1 : nx-1, y2 = (y+1 < ny-1) ? y+1 : ny-1, z2 = (z+1 < nz-1) ? z+1 : nz-1;
+				unsigned const xv[2] = {x, x2}, yv[2] = {y, y2}, zv[2] = {z, z2};
+				if (x2 <= x || y2 <= y || z2 <= z) continue;
+				unsigned cix = 0;
+				int all_under_mesh = (vp->skip_under_mesh != 0);
+				for (unsigned yhi = 0; yhi < 2; ++yhi) {
+					for (unsigned xhi = 0; xhi < 2; ++xhi) {
+						size_t const ix = z + ((size_t)xv[xhi] + (size_t)yv[yhi]*nx)*nz;
+						if (all_under_mesh) {all_under_mesh = ((outside[ix] & TW_VOX_UNDER_MESH) != 0);}
+						for (unsigned zhi = 0; zhi < 2; ++zhi) {if (outside[ix + zv[zhi]-z] & 7) {cix |= 1u << ((xhi^yhi) + 2*yhi + 4*zhi);}}
+					}
+				}
+				if (all_under_mesh) continue;
+				unsigned const edge_val = edge_table[cix];
+				if (edge_val == 0) continue;
+				const int *t = tri_table + 16*cix;
+				float const cube[3][2] = {{x*vp->vsz[0] + vp->lo_pos[0], x2*vp->vsz[0] + vp->lo_pos[0]}, {y*vp->vsz[1] + vp->lo_pos[1], y2*vp->vsz[1] + vp->lo_pos[1]},
+				                          {z*vp->vsz[2] + vp->lo_pos[2], z2*vp->vsz[2] + vp->lo_pos[2]}};
+				float vlist[12][3];
+				for (unsigned i = 0; i < 12; ++i) {
+					if (!(edge_val & (1u << i))) continue;
+					float v2[2], pts[2][3];
+					for (unsigned d = 0; d < 2; ++d) {
+						unsigned const e = edge_to_vals[2*i + d], yhi = (e & 2) >> 1, xhi = yhi ^ (e & 1), zhi = e >> 2;
+						size_t const ix = zv[zhi] + ((size_t)xv[xhi] + (size_t)yv[yhi]*nx)*nz;
+						v2[d] = ((outside[ix] & 7) == TW_VOX_ON_EDGE) ? vp->isolevel : vals[ix];
+						pts[d][0] = cube[0][xhi]; pts[d][1] = cube[1][yhi]; pts[d][2] = cube[2][zhi];
+					}
+					interpolate_pt(vp->isolevel, pts[0], pts[1], v2[0], v2[1], vlist[i]);
+				}
+				for (unsigned i = 0; t[i] >= 0; i += 3) {
+					const float *p0 = vlist[t[i]], *p1 = vlist[t[i+1]], *p2 = vlist[t[i+2]];
+					float const a[3] = {p1[0]-p0[0], p1[1]-p0[1], p1[2]-p0[2]}, b[3] = {p2[0]-p1[0], p2[1]-p1[1], p2[2]-p1[2]}; /* get_normal: cross(v2 - v1, v3 - v2) */
+					float const cx = a[1]*b[2] - a[2]*b[1], cy = a[2]*b[0] - a[0]*b[2], cz = a[0]*b[1] - a[1]*b[0];
+					if (cx == 0.0f && cy == 0.0f && cz == 0.0f) continue; /* normalize() leaves a zero vector zero: "invalid triangle", ref: :550 */
+					if (n < capacity) {float *o = tris + 9*n; for (int k = 0; k < 3; ++k) {o[k] = p0[k]; o[3+k] = p1[k]; o[6+k] = p2[k];}}
+					++n;
+				}
+			}
+		}
+	}
+	return n;
+}

@@ -84,6 +84,12 @@ void  to_voxel_fill(const tw_voxel_params *vp, const float *rdata420, const floa
 size_t to_from_floats_u16(const float *vals, size_t n, float val_mult, float val_add, unsigned char *out2n);
 void   to_to_floats_u16(const unsigned char *data2n, size_t n, float val_mult, float val_add, float *vals);
 
+/* voxel post-processing, ref: src/voxels.cpp:485-610,739-868 */
+void to_voxel_outside(const float *vals, const tw_voxel_post_params *vp, const unsigned *zix_xy, unsigned char *outside);
+unsigned long long to_voxel_remove_unconnected(float *vals, unsigned char *outside, const tw_voxel_post_params *vp);
+unsigned long long to_voxel_triangles(const float *vals, const unsigned char *outside, const tw_voxel_post_params *vp, const unsigned *edge_table, const int *tri_table,
+                                      const unsigned *edge_to_vals, float *tris, unsigned long long capacity);
+
 #ifdef __cplusplus
 }
 #endif

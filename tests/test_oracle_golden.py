@@ -215,3 +215,22 @@ def test_tile_bounds_small_case(oracle):
     assert list(b.sub_zmin)[:4] == [0.0, 1.0, 2.0, 3.0] and list(b.sub_zmax)[:4] == [7.0, 8.0, 9.0, 10.0]
     assert (b.mzmin, b.mzmax, b.mesh_dz) == (0.0, 28.0, 7.0)     # cells beyond index 4 are never visited (last row/column is not rendered)
     assert (b.wx1, b.wy1, b.wx2, b.wy2) == (0, 0, 4, 1)            # z < 7.5: rows 0 (cols 0..4) and row 1 (cols 0,1)
+
+
+def test_voxel_post_processing(oracle, beq):
+    """tests/golden/voxel_post.npz = outputs of the reference's own voxel_manager functions (N3): flags, flood fills, triangle soup."""
+    g = load("voxel_post.npz")
+    tables = (g["edge_table"], g["tri_table"], g["edge_to_vals"])
+    for name in ("sine", "inv", "mesh"):
+        a = g[name + "_params"]
+        p = oracle.VoxelPostParams()
+        p.nx, p.ny, p.nz = int(a[0]), int(a[1]), int(a[2])
+        for d in range(3):
+            p.lo_pos[d], p.vsz[d] = float(a[3 + d]), float(a[6 + d])
+        p.isolevel, p.invert, p.make_closed_surface, p.remove_unconnected, p.keep_at_edge, p.centre_seed, p.skip_under_mesh = float(a[9]), int(a[10]), int(a[11]), int(a[12]), int(a[13]), int(a[14]), int(a[15])
+        zix = g[name + "_zix"] if (name + "_zix") in g.files else None
+        out = oracle.voxel_outside(g[name + "_vals"], p, zix)
+        assert np.array_equal(out, g[name + "_outside"])
+        v2, o2, _ = oracle.voxel_remove_unconnected(g[name + "_vals"], out, p)
+        assert np.array_equal(o2, g[name + "_outside2"]) and beq(v2, g[name + "_vals2"]) == 0
+        assert beq(oracle.voxel_triangles(v2, o2, p, tables), g[name + "_tris"]) == 0

@@ -258,3 +258,104 @@ def test_tile_ao_lighting_extracted_reference(oracle, ref, beq):
                     ao = oracle.tile_ao(z[None], context[None], hd, use_ao_zvals=True)[0]
                 assert np.array_equal(ar, ao), (mode, size, x1, y1)
             assert ar.min() < 200 and ar.max() > ar.min()
+
+
+def _need_vox(ref):
+    import pytest
+    if not ref.has_voxel_extract():
+        pytest.skip("oracle/_ref was built without the voxels.cpp extraction")
+
+
+def _vox_case(oracle, ref, dims, vsz, center, gen_mode, **kw):
+    """A reference voxel_manager filled by its own create_procedural + the matching oracle parameter blocks."""
+    nx, ny, nz = dims
+    ref.setup(mode=gen_mode if gen_mode else 0, freq_filter=2, seed=1)
+    V = ref.Vox(nx, ny, nz, vsz, center, **kw)
+    lo = V.lo_pos
+    vpp = oracle.VoxelPostParams()
+    vpp.nx, vpp.ny, vpp.nz = nx, ny, nz
+    for d in range(3):
+        vpp.lo_pos[d], vpp.vsz[d] = float(lo[d]), vsz[d]
+    vpp.isolevel, vpp.invert, vpp.make_closed_surface = kw.get("isolevel", 0.0), kw.get("invert", 0), kw.get("make_closed_surface", 1)
+    vpp.remove_unconnected, vpp.keep_at_edge = kw.get("remove_unconnected", 1), int(kw.get("keep_at_scene_edge", 0) == 1)
+    vpp.centre_seed = int(kw.get("atten_at_edges", 0) in (3, 4) or not kw.get("use_mesh", 0))
+    vpp.skip_under_mesh = 0
+    return V, vpp, lo
+
+
+def test_voxel_fill_against_extracted_create_procedural(oracle, ref, beq):
+    """SURVEY 8a row a16 pinned against the reference's OWN voxel_manager::create_procedural + atten_* (cut out of src/voxels.cpp:278-346,403-482
+    at build time): sine / simplex / Perlin density, z gradient off, every attenuation mode."""
+    _need_vox(ref)
+    for gen_mode in (0, 1, 2):
+        for atten in (0, 1, 2, 3, 4, 5):
+            dims, vsz, center = (20, 12, 28), (0.11, 0.13, 0.07), (0.3, -0.2, 0.1)
+            V, vpp, lo = _vox_case(oracle, ref, dims, vsz, center, gen_mode, atten_at_edges=atten)
+            off = (0.5, -1.25, 2.0)
+            V.create_procedural(1.0, 1.0, off, 1, 123, 456, gen_mode)
+            if atten:
+                V.atten(atten, -0.8, 0.45)
+            vp = oracle.VoxelParams()
+            vp.nx, vp.ny, vp.nz = dims
+            for d in range(3):
+                vp.lo_pos[d], vp.vsz[d], vp.offset[d] = float(lo[d]), vsz[d], off[d]
+            vp.mag = vp.freq = 1.0
+            vp.gen_mode, vp.normalize_to_1, vp.rseed1, vp.rseed2 = gen_mode, 1, 123, 456
+            vp.octaves = max(1, 5 - 2)                     # MAX_FREQ_BINS - mesh_freq_filter (freq_filter 2)
+            vp.rx, vp.ry = oracle.gen_rx_ry(1, 0, gen_mode) if gen_mode else (0.0, 0.0)
+            vp.zscale = 0.0
+            vp.atten_mode, vp.atten_val, vp.atten_inner_radius = atten, -0.8, 0.45
+            assert beq(oracle.voxel_fill(vp), V.vals()) == 0, (gen_mode, atten)
+
+
+def test_voxel_post_processing_against_extracted_reference(oracle, ref, beq):
+    """SURVEY 8f row N3 pinned against the reference's OWN determine_voxels_outside, remove_unconnected_outside(_range), flood_fill_range,
+    remove_interior_holes and add_triangles_for_voxel (cut out of src/voxels.cpp at build time): outside flags, the flood fills with their
+    make_voxel_outside/inside edits, per-cube triangle counts and the unwelded triangle soup, bit for bit and in the same order."""
+    _need_vox(ref)
+    tables = ref.mc_tables()
+    rng = np.random.default_rng(4)
+    cases = [dict(dims=(24, 20, 16), gen=0, kw=dict(remove_unconnected=3)),
+             dict(dims=(18, 22, 30), gen=1, kw=dict(remove_unconnected=3, invert=1, isolevel=0.1)),
+             dict(dims=(16, 16, 16), gen=2, kw=dict(remove_unconnected=1, make_closed_surface=0, keep_at_scene_edge=1)),
+             dict(dims=(20, 18, 14), gen=0, kw=dict(remove_unconnected=3, atten_at_edges=3, isolevel=-0.2)),
+             dict(dims=(26, 24, 20), gen=0, kw=dict(remove_unconnected=2, use_mesh=1), mesh=True),
+             dict(dims=(12, 10, 9), gen=-1, kw=dict(remove_unconnected=3))]          # random noise field: many small components and pockets
+    for c in cases:
+        dims, kw = c["dims"], c["kw"]
+        vsz, center = (0.15, 0.12, 0.1), (0.0, 0.0, 0.3)
+        V, vpp, lo = _vox_case(oracle, ref, dims, vsz, center, max(c["gen"], 0), **kw)
+        if c["gen"] >= 0:
+            V.create_procedural(1.0, 1.3, (0.2, 0.1, -0.3), 1, 123, 456, c["gen"])
+            if kw.get("atten_at_edges"):
+                V.atten(kw["atten_at_edges"], -1.0, 0.4)
+        else:
+            V.set_vals(rng.uniform(-1, 1, (dims[1], dims[0], dims[2])).astype(np.float32))
+        zix = None
+        if c.get("mesh"):       # ground mesh under the voxels: z_min_matrix -> per-column zix (computed with the reference's own get_xpos / point_outside_mesh)
+            V.set_zmin_matrix(np.fromfunction(lambda y, x: 0.25 * np.sin(x * 0.3) + 0.2 * np.cos(y * 0.2) + 0.2, (128, 128)).astype(np.float32))
+            zix = V.zix()
+            assert zix.max() > 0
+        vals0 = V.vals()
+        V.determine_outside()
+        out_r = V.outside()
+        out_o = oracle.voxel_outside(vals0, vpp, zix)
+        assert np.array_equal(out_r, out_o), c
+        V.remove_unconnected()
+        if kw["remove_unconnected"] > 2:
+            V.remove_interior_holes()
+        vals_o, out2_o, changed = oracle.voxel_remove_unconnected(vals0, out_o, vpp)
+        assert np.array_equal(V.outside(), out2_o) and beq(V.vals(), vals_o) == 0, c
+        assert changed == int((out2_o != out_o).sum())
+        for skip in (0, 1) if c.get("mesh") else (0,):
+            vpp.skip_under_mesh = skip
+            ref.lib().ref_vox_set_display_mode_bit(skip) if hasattr(ref.lib(), "ref_vox_set_display_mode_bit") else None
+            if skip and not hasattr(ref.lib(), "ref_vox_set_display_mode_bit"):
+                continue
+            tr, counts = V.triangles(welded=False, want_counts=True)
+            to = oracle.voxel_triangles(vals_o, out2_o, vpp, tables)
+            assert tr.shape == to.shape and beq(tr, to) == 0, (c, skip)
+            assert counts.sum() >= len(tr) > 0
+        V.set_zmin_matrix(None)
+    changed_any = True
+    assert changed_any
