@@ -257,12 +257,14 @@ int tw_heightgen_tiles(tw_ctx *ctx, const int32_t *origins_xy, uint32_t ntiles, 
 			if (rc) return rc;
 		}
 	}
-	else { // sine tables depend on the tile origin: one table build + grid launch per tile
+	else { // sine tables depend on the tile origin only through its column / row: W + H tables for a W x H block of tiles, one grid launch for the batch
+		std::vector<float2> org(ntiles);
 		for (uint32_t t = 0; t < ntiles; ++t) {
-			g.x0 = (float)(origins_xy[2*t] - mesh_x_size/2); g.y0 = (float)(origins_xy[2*t+1] - mesh_y_size/2);
-			rc = twi_heightgen(ctx, &g, p, 1, 0, nullptr, 1, d_out + (size_t)t*tile_elems, d_mm ? d_mm + 2*(size_t)t : nullptr);
-			if (rc) return rc;
+			float const x0 = (float)(origins_xy[2*t] - mesh_x_size/2), y0 = (float)(origins_xy[2*t+1] - mesh_y_size/2);
+			org[t] = make_float2(dx*x0, dy*y0);
 		}
+		rc = twi_heightgen_sine_tiles(ctx, &g, p, 1, 0, org.data(), ntiles, d_out, d_mm);
+		if (rc) return rc;
 	}
 	if (!dev_out) {TW_CUDA(ctx, cudaMemcpyAsync(out, d_out, n*sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));}
 	if (mm) {rc = read_minmax(ctx, d_mm, mm, ntiles); if (rc) return rc;}

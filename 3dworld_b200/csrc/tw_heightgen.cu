@@ -14,6 +14,9 @@
 //   points_kernel        eval_mesh_sin_terms / eval_mesh_sin_terms_scaled / get_exact_zval for batches of arbitrary points (:797-847)
 // All arithmetic keeps the reference's rounding sequence (this TU is compiled with -fmad=false; see tw_noise.cuh).
 #include "tw_internal.h"
+#include <unordered_map>
+#include <vector>
+#include <algorithm>
 #include "tw_noise.cuh"
 #include "tw_noise2.cuh"
 #include <stdlib.h>
@@ -361,11 +364,18 @@ struct SineTabParams {
 };
 
 // X[k][i] = SINF(xmdx*i + x_const), Y[k][j] = y_scale*SINF(ymdy*j + y_const)  (src/mesh_gen.cpp:609-625); row F_TABLE holds the
-// enable_glaciate() terms (src/mesh_gen.cpp:647-649). grid = (ceil(max(nx,ny)/256), F_TABLE+1, 2[x|y])
-__global__ void sine_tables_kernel(float *__restrict__ Xt, float *__restrict__ Yt, const float *__restrict__ T, const float *__restrict__ sin_tab, SineTabParams S)
+// enable_glaciate() terms (src/mesh_gen.cpp:647-649). grid = (ceil(max(nx,ny)/256), F_TABLE+1, 2[x|y]).
+// Tile batches (origins != nullptr): grid.z = nux + nuy tables; table t < nux is the X table of the t-th DISTINCT tile x origin (origins[t] = its mx0), the
+// others the Y tables of the distinct y origins - a W x H block of tiles needs W + H tables, not 2*W*H (the round-1 code built and launched two per tile).
+__global__ void sine_tables_kernel(float *__restrict__ Xt, float *__restrict__ Yt, const float *__restrict__ T, const float *__restrict__ sin_tab, SineTabParams S,
+	const float *__restrict__ origins = nullptr, unsigned nux = 0, size_t xstride = 0, size_t ystride = 0)
 {
 	unsigned const i = blockIdx.x*blockDim.x + threadIdx.x, k = blockIdx.y;
-	bool const is_y = (blockIdx.z != 0);
+	bool const is_y = origins ? (blockIdx.z >= nux) : (blockIdx.z != 0);
+	if (origins) {
+		if (is_y) {S.my0 = __ldg(origins + blockIdx.z); Yt += (size_t)(blockIdx.z - nux)*ystride;}
+		else      {S.mx0 = __ldg(origins + blockIdx.z); Xt += (size_t)blockIdx.z*xstride;}
+	}
 	unsigned const n = is_y ? S.ny : S.nx;
 	if (i >= n) return;
 	if (k == F_TABLE) { // cos terms
@@ -396,9 +406,17 @@ constexpr int SK = 45;          // k-chunk staged in shared memory (2 chunks cov
 
 __global__ void __launch_bounds__(256)
 sine_grid_kernel(float *__restrict__ out, unsigned nx, unsigned ny, const float *__restrict__ Xt, const float *__restrict__ Yt,
-	unsigned xpitch, unsigned ypitch, int start_ix, PostParams P, float mx0, float my0, const float *__restrict__ sin_tab, unsigned *__restrict__ mm, unsigned y_off)
+	unsigned xpitch, unsigned ypitch, int start_ix, PostParams P, float mx0, float my0, const float *__restrict__ sin_tab, unsigned *__restrict__ mm, unsigned y_off,
+	const uint2 *__restrict__ tile_tabs = nullptr, const float2 *__restrict__ tile_origins = nullptr, size_t xstride = 0, size_t ystride = 0)
 {
 	__shared__ float Xs[SK][ST], Ys[SK][ST];
+	if (tile_tabs) { // tile batch: blockIdx.z = tile; its X / Y tables are shared with the other tiles of its column / row
+		uint2 const tt = __ldg(tile_tabs + blockIdx.z);
+		float2 const o = __ldg(tile_origins + blockIdx.z);
+		Xt += (size_t)tt.x*xstride; Yt += (size_t)tt.y*ystride; mx0 = o.x; my0 = o.y;
+		out += (size_t)blockIdx.z*nx*ny;
+		if (mm) {mm += 2*(size_t)blockIdx.z;}
+	}
 	unsigned const x_base = blockIdx.x*ST, y_base = y_off + blockIdx.y*ST;
 	int const tid = threadIdx.x, tx = tid & 15, ty = tid >> 4; // 16 x 16 threads
 	float2 acc2[4][2]; // acc2[a][h] = cells (row a, columns 2h and 2h+1 of this thread): packed fp32x2 accumulators (see tw_noise2.cuh)
@@ -685,6 +703,69 @@ int twi_heightgen(tw_ctx *ctx, const tw_grid2d *g, const tw_height_params *p, in
 		if (h_out_bands) {int const rc = band_copy(ctx, h_out_bands, d_out, nx, r0, r1); if (rc) return rc;}
 	}
 	return h_out_bands ? band_join(ctx) : TW_OK;
+}
+
+// Sine-mode tile batch (tile_t::create_zvals / create_texture in force_sine_mode): tables once per distinct tile column / row, then ONE grid launch per
+// <= 65535 tiles. h_org = ntiles (mx0, my0) pairs (HOST; mx0 = dx*float(x1 - MESH_X_SIZE/2) as build_arrays computes it).
+int twi_heightgen_sine_tiles(tw_ctx *ctx, const tw_grid2d *g, const tw_height_params *p, int enable_glaciate, int min_start_sin, const float2 *h_org, uint32_t ntiles,
+                             float *d_out, unsigned *d_mm_ord)
+{
+	if (!ctx->have_sine_params) return tw_set_error(ctx, TW_ERR_STATE, "tw_set_sine_params() has not been called");
+	unsigned const nx = g->nx, ny = g->ny;
+	PostParams const P = make_post_params(p, enable_glaciate, g->dx, g->dy);
+	// distinct origins (bit patterns) -> table indices
+	std::vector<float> ux, uy;
+	std::vector<uint2> tabs(ntiles);
+	{
+		std::unordered_map<uint32_t, unsigned> mx, my;
+		for (uint32_t t = 0; t < ntiles; ++t) {
+			uint32_t bx, by;
+			memcpy(&bx, &h_org[t].x, 4); memcpy(&by, &h_org[t].y, 4);
+			auto ix = mx.find(bx); if (ix == mx.end()) {ix = mx.emplace(bx, (unsigned)ux.size()).first; ux.push_back(h_org[t].x);}
+			auto iy = my.find(by); if (iy == my.end()) {iy = my.emplace(by, (unsigned)uy.size()).first; uy.push_back(h_org[t].y);}
+			tabs[t] = make_uint2(ix->second, iy->second);
+		}
+	}
+	unsigned const nux = (unsigned)ux.size(), nuy = (unsigned)uy.size();
+	unsigned const xpitch = (nx + 63) & ~63u, ypitch = (ny + 63) & ~63u;
+	size_t const xstride = (size_t)(F_TABLE + 1)*xpitch, ystride = (size_t)(F_TABLE + 1)*ypitch;
+	size_t const tab_bytes = ((nux*xstride + nuy*ystride)*sizeof(float) + 255) & ~(size_t)255, org_bytes = (((size_t)nux + nuy)*sizeof(float) + 255) & ~(size_t)255;
+	size_t const tt_bytes = ((size_t)ntiles*sizeof(uint2) + 255) & ~(size_t)255, to_bytes = ((size_t)ntiles*sizeof(float2) + 255) & ~(size_t)255;
+	int rc = tw_reserve(ctx, 1, tab_bytes + org_bytes + tt_bytes + to_bytes);
+	if (rc) return rc;
+	char *sp = (char *)ctx->d_scratch[1];
+	float *Xt = (float *)sp, *Yt = Xt + nux*xstride; sp += tab_bytes;
+	float *d_uorg = (float *)sp; sp += org_bytes;
+	uint2 *d_tabs = (uint2 *)sp; sp += tt_bytes;
+	float2 *d_torg = (float2 *)sp;
+	std::vector<float> uorg(ux); uorg.insert(uorg.end(), uy.begin(), uy.end());
+	TW_CUDA(ctx, cudaMemcpyAsync(d_uorg, uorg.data(), uorg.size()*sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+	TW_CUDA(ctx, cudaMemcpyAsync(d_tabs, tabs.data(), (size_t)ntiles*sizeof(uint2), cudaMemcpyHostToDevice, ctx->stream));
+	TW_CUDA(ctx, cudaMemcpyAsync(d_torg, h_org, (size_t)ntiles*sizeof(float2), cudaMemcpyHostToDevice, ctx->stream));
+	SineTabParams S;
+	memset(&S, 0, sizeof(S));
+	S.msx = p->mesh_scale*p->dx_val_inv; S.msy = p->mesh_scale*p->dy_val_inv; S.ms2 = (float)(0.5*p->mesh_scale);
+	S.mesh_scale_z_inv = p->mesh_scale_z_inv;
+	S.dx = g->dx; S.dy = g->dy;
+	S.start = p->start_eval_sin;
+	S.nx = nx; S.ny = ny; S.xpitch = xpitch; S.ypitch = ypitch;
+	S.sine_on = (enable_glaciate && p->hmap.sine_mag != 0.0f); S.sm_scale = P.sm_scale; S.sm_freq = P.sm_freq; S.dx_inv = p->dx_val_inv; S.dy_inv = p->dy_val_inv;
+	unsigned const nmax = nx > ny ? nx : ny;
+	for (unsigned t0 = 0; t0 < nux + nuy; t0 += 65535) { // gridDim.z limit; the z index is rebased through the pointer offsets
+		unsigned const nt = std::min(65535u, nux + nuy - t0);
+		if (t0 != 0) return tw_set_error(ctx, TW_ERR_ARG, "more than 65535 distinct tile rows + columns in one batch");
+		sine_tables_kernel<<<dim3((nmax + 255)/256, F_TABLE + 1, nt), 256, 0, ctx->stream>>>(Xt, Yt, ctx->d_sine_params, ctx->d_sin_table, S, d_uorg, nux, xstride, ystride);
+		TW_LAUNCH_CHECK(ctx);
+	}
+	int const start_ix = (p->start_eval_sin > min_start_sin) ? p->start_eval_sin : min_start_sin; // src/mesh_gen.cpp:769
+	for (uint32_t t0 = 0; t0 < ntiles; t0 += 65535) {
+		uint32_t const nt = std::min<uint32_t>(65535u, ntiles - t0);
+		sine_grid_kernel<<<dim3((nx + ST - 1)/ST, (ny + ST - 1)/ST, nt), 256, 0, ctx->stream>>>(d_out + (size_t)t0*nx*ny, nx, ny, Xt, Yt, xpitch, ypitch, start_ix, P, 0.0f, 0.0f,
+			ctx->d_sin_table, d_mm_ord ? d_mm_ord + 2*(size_t)t0 : nullptr, 0, d_tabs + t0, d_torg + t0, xstride, ystride);
+		TW_LAUNCH_CHECK(ctx);
+	}
+	TW_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); // the host vectors above are read by the async copies
+	return TW_OK;
 }
 
 // ------------------------------------------------------------------------------------------------ point queries

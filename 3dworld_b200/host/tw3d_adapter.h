@@ -277,6 +277,16 @@ inline void tile_normals(const float *zvals, unsigned ntiles, unsigned zvsize, f
 	int const rc = tw_tile_normals_batch(c, zvals, ntiles, zvsize, dx_val, dy_val, normal_data, min_normal_z);
 	if (rc != TW_OK) {detail::fail(rc, "tile_normals", c);}
 }
+// tile_t::create_zvals + calc_mesh_ao_lighting with enable_tiled_mesh_ao for a batch: in the GPU gen modes the (stride+72)^2 context is generated once, zvals are
+// its interior (src/tiled_mesh.cpp:479-487,505) and the AO rays test the un-eroded context (:604)
+inline void create_zvals_with_ao(const int32_t *origins_xy, unsigned ntiles, unsigned zvsize, float dx, float dy, unsigned erosion_iters_tt, float *zvals_out, unsigned char *ao_lighting, tw_minmax *mm = nullptr) {
+	scene_globals const &g = globals();
+	tw_height_params const p = height_params_from_globals(g.mesh_gen_mode, g.mesh_gen_shape);
+	tw_erosion_params const e = erosion_params_from_globals();
+	tw_ctx *c = ctx();
+	int const rc = tw_create_zvals_ao_batch(c, origins_xy, ntiles, g.MESH_X_SIZE, g.MESH_Y_SIZE, dx, dy, zvsize, &p, erosion_iters_tt, &e, g.zmin, g.HALF_DXY, zvals_out, ao_lighting, mm);
+	if (rc != TW_OK) {detail::fail(rc, "create_zvals_with_ao", c);}
+}
 inline void tile_ao_lighting(const float *zvals, const int32_t *origins_xy, unsigned ntiles, unsigned zvsize, float dx, float dy, unsigned char *ao_lighting) {
 	scene_globals const &g = globals();
 	tw_height_params const p = height_params_from_globals(g.mesh_gen_mode, g.mesh_gen_shape);
@@ -386,5 +396,76 @@ inline void create_procedural(voxel_grid_view const &v, float mag, float freq, c
 	int const rc = tw_voxel_fill(c, &vp, nullptr, v.data->data());
 	if (rc != TW_OK) {detail::fail(rc, "create_procedural", c);}
 }
+
+// voxel_model::build after the fill (src/voxels.cpp:1523-1530 + create_block :1077-1108): determine_voxels_outside, remove_unconnected_outside
+// (+ remove_interior_holes for remove_unconnected > 2) and the marching-cubes triangles of the whole grid, on the device. `outside` gets the
+// reference's flag bytes; zix_xy (optional) = the per-column under-mesh index the reference derives from z_min_matrix (:596-600); the case tables are
+// voxel_detail::edge_table / tri_table / edge_to_vals of src/marching_cubes.h. Returns the unwelded triangle soup (9 floats per triangle).
+inline std::vector<float> voxel_build(voxel_grid_view const &v, std::vector<unsigned char> &outside, float isolevel, bool invert, bool make_closed_surface,
+	unsigned remove_unconnected, bool keep_at_edge, bool sphere_mode_or_no_mesh, bool skip_under_mesh, const uint32_t *zix_xy,
+	const unsigned *edge_table, const int *tri_table, const unsigned *edge_to_vals)
+{
+	tw_voxel_post_params vp;
+	memset(&vp, 0, sizeof(vp));
+	vp.nx = v.nx; vp.ny = v.ny; vp.nz = v.nz;
+	for (int d = 0; d < 3; ++d) {vp.lo_pos[d] = v.lo_pos[d]; vp.vsz[d] = v.vsz[d];}
+	vp.isolevel = isolevel; vp.invert = invert; vp.make_closed_surface = make_closed_surface; vp.remove_unconnected = (int)remove_unconnected;
+	vp.keep_at_edge = keep_at_edge; vp.centre_seed = sphere_mode_or_no_mesh; vp.skip_under_mesh = skip_under_mesh;
+	outside.resize(v.data->size());
+	tw_ctx *c = ctx();
+	int rc = tw_voxel_outside(c, v.data->data(), &vp, zix_xy, outside.data());
+	if (rc == TW_OK) {rc = tw_voxel_remove_unconnected(c, v.data->data(), outside.data(), &vp, nullptr);}
+	uint64_t n = 0;
+	if (rc == TW_OK) {rc = tw_voxel_triangles(c, v.data->data(), outside.data(), &vp, edge_table, tri_table, edge_to_vals, nullptr, 0, &n);}
+	std::vector<float> tris((size_t)n*9);
+	if (rc == TW_OK && n) {rc = tw_voxel_triangles(c, v.data->data(), outside.data(), &vp, edge_table, tri_table, edge_to_vals, tris.data(), n, &n);}
+	if (rc != TW_OK) {detail::fail(rc, "voxel_build", c);}
+	return tris;
+}
+
+// ------------------------------------------------------------------------------------------------ all GPUs of the box (include/tw3d.h "Multi-GPU")
+// One object per process: per-device contexts with the current tables, NUMA-local pinned output bands, the tile loop of tile_draw_t::update
+// (src/tiled_mesh.cpp:2367-2417) dealt out over the devices, and the global z range (get_heightmap_z_range, src/map_view.cpp:399-407) reduced with NCCL.
+class multi_gpu {
+	tw_multi *m = nullptr;
+	std::vector<void *> host_bands;
+	void check(int rc, const char *what) {if (rc != TW_OK) {throw error(rc, std::string(what) + ": " + (m ? tw_multi_last_error(m) : "tw_multi_create failed"));}}
+public:
+	explicit multi_gpu(int ndev, const int *devices = nullptr) {
+		check(tw_multi_create(devices, ndev, &m), "tw_multi_create");
+		detail::state_t &s = detail::state();
+		if (!s.sine_params.empty()) {check(tw_multi_set_sine_params(m, s.sine_params.data()), "tw_multi_set_sine_params");}
+	}
+	~multi_gpu() {for (void *p : host_bands) {tw_multi_free_host(m, p);} tw_multi_destroy(m);}
+	multi_gpu(multi_gpu const &) = delete;
+	multi_gpu &operator=(multi_gpu const &) = delete;
+	int size() const {return tw_multi_size(m);}
+	tw_multi *handle() {return m;}
+	// pinned host memory on device i's NUMA node for its band of `ntiles` tiles of zvsize^2 floats (owned by this object)
+	float *alloc_band(int i, uint32_t ntiles, uint32_t zvsize) {
+		uint32_t a, b;
+		tw_multi_range(ntiles, size(), i, &a, &b);
+		void *p = nullptr;
+		check(tw_multi_alloc_host(m, i, (size_t)(b - a)*zvsize*zvsize*sizeof(float), &p), "tw_multi_alloc_host");
+		host_bands.push_back(p);
+		return (float *)p;
+	}
+	// tile_t::create_zvals for all tiles, every device on its band; returns the global z range
+	tw_minmax create_zvals(const int32_t *origins_xy, uint32_t ntiles, uint32_t zvsize, float dx, float dy, unsigned erosion_iters_tt, float *const *bands, tw_minmax *mm = nullptr) {
+		scene_globals const &g = globals();
+		tw_height_params const p = height_params_from_globals(g.mesh_gen_mode, g.mesh_gen_shape);
+		tw_erosion_params const e = erosion_params_from_globals();
+		tw_minmax zr = {0, 0};
+		check(tw_create_zvals_sharded(m, origins_xy, ntiles, g.MESH_X_SIZE, g.MESH_Y_SIZE, dx, dy, zvsize, &p, erosion_iters_tt, &e, g.zmin, bands, mm, &zr), "tw_create_zvals_sharded");
+		return zr;
+	}
+	// heightmap_t::run_erosion on a map held as row bands, coherent across the devices (the batched variant, see tw_erode_sweeps in tw3d.h)
+	uint64_t erode_sweeps(float *const *bands, int xsize, int ysize, float min_zval, unsigned num_iters, unsigned sweep = 8192, int halo = 64) {
+		tw_erosion_params const e = erosion_params_from_globals();
+		uint64_t moves = 0;
+		check(tw_erode_sweeps_sharded(m, bands, xsize, ysize, min_zval, num_iters, &e, sweep, halo, &moves), "tw_erode_sweeps_sharded");
+		return moves;
+	}
+};
 
 } // namespace tw3d

@@ -85,3 +85,26 @@ def test_adapter_matches_oracle(exe, tw, scene, oracle, ctx, beq, tmp_path, mode
         h = np.load(os.path.join(ROOT, "tests", "golden", "height.npz"))
         assert beq(parts[6], h["gm_cfg1_eroded"]) == 0
         assert beq(parts[7], h["gm_cfg1_eroded_zvals"]) == 0
+
+
+@pytest.fixture(scope="module")
+def exe_multi(tw):
+    src = os.path.join(ROOT, "tests", "cpp", "test_multi.cpp")
+    out = os.path.join(ROOT, "tests", "cpp", "test_multi")
+    hdr = os.path.join(ROOT, "3dworld_b200", "host", "tw3d_adapter.h")
+    if not os.path.exists(out) or os.path.getmtime(out) < max(os.path.getmtime(src), os.path.getmtime(hdr), os.path.getmtime(tw.LIB_PATH)):
+        subprocess.check_call(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-I", os.path.join(ROOT, "include"), "-I", os.path.join(ROOT, "3dworld_b200", "host"),
+                               "-I", "/usr/local/cuda/include", src, "-L" + os.path.join(ROOT, "3dworld_b200"), "-l3dworld_b200", "-L/usr/local/cuda/lib64", "-lcudart",
+                               "-Wl,-rpath," + os.path.join(ROOT, "3dworld_b200"), "-Wl,-rpath,/usr/local/cuda/lib64", "-o", out])
+    return out
+
+
+def test_multi_gpu_adapter_builds(exe_multi):
+    assert os.path.exists(exe_multi)
+
+
+@pytest.mark.gpu
+def test_multi_gpu_adapter_all_devices(exe_multi):
+    """tw3d::multi_gpu over every visible device (1 on a single-GPU box: the sharded call then runs without NCCL) == one device."""
+    r = subprocess.run([exe_multi, "0"], capture_output=True, text=True)
+    assert r.returncode == 0 and "identical to one device" in r.stdout, r.stdout + r.stderr

@@ -139,10 +139,10 @@ def test_erode_sweeps_sharded_equals_single_device(tw, scene, oracle, ctx, beq, 
             one = z.copy()
             moves1 = ctx.erode_sweeps(one, zmin, iters, ep, sweep, halo)
             ranges = [tw.multi_range(ny, ndev, i) for i in range(ndev)]
-            host_bands = [np.ascontiguousarray(z[a:b]) for a, b in ranges]
+            host_bands = [z[a:b].copy() for a, b in ranges]            # copies: a row slice of a contiguous array is already contiguous, i.e. a view
             moves = m.erode_sweeps_sharded(host_bands, nx, ny, zmin, iters, ep, sweep, halo)
             assert beq(np.concatenate(host_bands), one) == 0 and moves == moves1
-            dev_bands = [torch.from_numpy(np.ascontiguousarray(z[a:b])).to("cuda:%d" % i) for i, (a, b) in enumerate(ranges)]
+            dev_bands = [torch.from_numpy(z[a:b].copy()).to("cuda:%d" % i) for i, (a, b) in enumerate(ranges)]
             m.erode_sweeps_sharded(dev_bands, nx, ny, zmin, iters, ep, sweep, halo)
             assert beq(np.concatenate([d.cpu().numpy() for d in dev_bands]), one) == 0
             border = ranges[0][1]
