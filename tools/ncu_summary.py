@@ -111,9 +111,11 @@ def main():
             d["stall_cycles_per_issue"] = {k: v for k, v in sorted(stalls.items(), key=lambda kv: -kv[1] if isinstance(kv[1], float) else 0)[:8]}
         rd, wr = d.get("dram__bytes_read.sum"), d.get("dram__bytes_write.sum")
         if isinstance(rd, float) and isinstance(wr, float):
-            u = (d.get("_units", {}).get("dram__bytes_read.sum", "byte") or "byte").lower()
-            mult = {"byte": 1, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}.get(u, 1)
-            d["dram_bytes_per_launch"] = (rd + wr) * mult
+            def to_bytes(v, key):   # ncu scales every metric on its own (the read side can be in Kbyte while the write side is in Mbyte)
+                u = (d.get("_units", {}).get(key, "byte") or "byte").lower()
+                return v * {"byte": 1, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9, "tbyte": 1e12}.get(u, 1)
+            d["dram_read_bytes"], d["dram_write_bytes"] = to_bytes(rd, "dram__bytes_read.sum"), to_bytes(wr, "dram__bytes_write.sum")
+            d["dram_bytes_per_launch"] = d["dram_read_bytes"] + d["dram_write_bytes"]
         if args.opcodes:
             d["opcode_mix"] = opcode_mix(args.rep, args.kernel)
         if args.units:
