@@ -328,6 +328,28 @@ TW_API int tw_voxel_remove_unconnected(tw_ctx *ctx, float *vals, uint8_t *outsid
 TW_API int tw_voxel_triangles(tw_ctx *ctx, const float *vals, const uint8_t *outside, const tw_voxel_post_params *vp, const uint32_t *edge_table256,
                        const int32_t *tri_table256x16, const uint32_t *edge_to_vals12x2, float *tris, uint64_t capacity, uint64_t *ntris);
 
+/* ---- mesh shadows of tiles: calc_mesh_shadows (src/visibility.cpp:411-517) for a batch of tiles with the neighbour chaining of
+ * tile_t::calc_shadows_for_light (src/tiled_mesh.cpp:664-692) ---- */
+typedef struct tw_shadow_params {
+	float lpos[3];                       /* get_light_pos(l) */
+	float x_scene_size, y_scene_size;    /* X_SCENE_SIZE, Y_SCENE_SIZE */
+	float dx_val, dy_val, dx_val_inv, dy_val_inv;
+	int   xy_sum_size;                   /* XY_SUM_SIZE = MESH_X_SIZE + MESH_Y_SIZE (src/matrix_ops.cpp) */
+	float zmin, zmax;                    /* the globals the line clip of trace_shadow_path uses (:424) */
+	int   no_shadow;                     /* l == LIGHT_MOON && combined_gu (:511) */
+} tw_shadow_params;
+#define TW_MESH_SHADOW 0x02              /* MESH_SHADOW, src/3DWorld.h:1403 */
+#define TW_MESH_MIN_Z  (-1.0E6f)         /* MESH_MIN_Z, src/mesh.h:9: "no incoming shadow height" */
+/* smask (ntiles*zvsize^2 bytes) = 0 / MESH_SHADOW per cell as calc_mesh_shadows leaves it; every tile traces 2*zvsize rays from its x edge and 2*zvsize from its
+ * y edge toward the light's shadow direction (Bresenham walk, one thread per ray) carrying the running shadow height. tile_xy = the tiles' grid coordinates
+ * (x1/size, y1/size): a tile whose neighbour TOWARD the light (x + (lpos.x < 0 ? -1 : 1), resp. y) is in the batch starts its rays from that neighbour's outgoing
+ * shadow heights (sh_in = the neighbour's sh_out, :680-686), so the batch is processed in dependency waves. sh_out_x / sh_out_y (optional, ntiles*zvsize floats each,
+ * host or device) receive the outgoing heights (MESH_MIN_Z where no shadowed ray left the tile). Where two rays write the same sh_out entry the later ray in the
+ * reference's sequential order (run_x rays by y, then run_y rays by x) wins - the reference runs the two loops as OpenMP sections, i.e. with a race; its
+ * 1-thread order is reproduced. zvals / smask: host or device. */
+TW_API int tw_tile_shadows_batch(tw_ctx *ctx, const float *zvals, const int32_t *tile_xy, uint32_t ntiles, uint32_t zvsize, const tw_shadow_params *sp,
+                          uint8_t *smask, float *sh_out_x, float *sh_out_y);
+
 /* ---------------------------------------------------------------------------------------------------------------------------------------
  * Multi-GPU. The reference is one process with OpenMP threads and has no distributed layer; what it has is the tile loop of
  * tile_draw_t::update (src/tiled_mesh.cpp:2367-2417) and the global z range get_heightmap_z_range (src/map_view.cpp:399-407). Tiles and row

@@ -54,6 +54,11 @@ class VoxelPostParams(C.Structure):
                 ("skip_under_mesh", C.c_int)]
 
 
+class ShadowParams(C.Structure):
+    _fields_ = [("lpos", C.c_float * 3), ("x_scene_size", C.c_float), ("y_scene_size", C.c_float), ("dx_val", C.c_float), ("dy_val", C.c_float), ("dx_val_inv", C.c_float),
+                ("dy_val_inv", C.c_float), ("xy_sum_size", C.c_int), ("zmin", C.c_float), ("zmax", C.c_float), ("no_shadow", C.c_int)]
+
+
 class PointQuery(C.Structure):
     _fields_ = [("kind", C.c_int), ("xy_scale", C.c_float), ("mesh_x_size", C.c_int), ("mesh_y_size", C.c_int), ("x_scene_size", C.c_float),
                 ("y_scene_size", C.c_float), ("xoff2", C.c_int), ("yoff2", C.c_int), ("no_xyoff", C.c_int)]
@@ -123,6 +128,8 @@ def lib():
         L.to_apply_erosion.restype = C.c_ulonglong
         L.to_erode_sweeps.argtypes = [vp, C.c_int, C.c_int, C.c_float, C.c_uint, C.POINTER(ErosionParams), C.c_uint, C.c_int]
         L.to_erode_sweeps.restype = C.c_ulonglong
+        L.to_calc_mesh_shadows.argtypes = [C.POINTER(ShadowParams), vp, vp, C.c_int, C.c_int, vp, vp, vp, vp]
+        L.to_tile_shadows_batch.argtypes = [vp, vp, C.c_uint, C.c_uint, C.POINTER(ShadowParams), vp, vp, vp]
         L.to_voxel_outside.argtypes = [vp, C.POINTER(VoxelPostParams), vp, vp]
         L.to_voxel_remove_unconnected.argtypes = [vp, vp, C.POINTER(VoxelPostParams)]
         L.to_voxel_remove_unconnected.restype = C.c_ulonglong
@@ -265,6 +272,28 @@ def voxel_fill(vp, rdata=None, nthreads=0):
     rd = None if rdata is None else np.ascontiguousarray(rdata, np.float32)
     lib().to_voxel_fill(C.byref(vp), None if rd is None else _p(rd), _p(sin_table()), _p(out), nthreads)
     return out
+
+
+def calc_mesh_shadows(sp, mh, sh_in_x=None, sh_in_y=None):
+    """calc_mesh_shadows of one tile: returns (smask, sh_out_x, sh_out_y); sh_out start at MESH_MIN_Z."""
+    mh = np.ascontiguousarray(mh, np.float32)
+    ys, xs = mh.shape
+    smask = np.empty((ys, xs), np.uint8)
+    ox, oy = np.full(xs, -1.0e6, np.float32), np.full(ys, -1.0e6, np.float32)
+    six = None if sh_in_x is None else np.ascontiguousarray(sh_in_x, np.float32)
+    siy = None if sh_in_y is None else np.ascontiguousarray(sh_in_y, np.float32)
+    lib().to_calc_mesh_shadows(C.byref(sp), _p(mh), _p(smask), xs, ys, None if six is None else _p(six), None if siy is None else _p(siy), _p(ox), _p(oy))
+    return smask, ox, oy
+
+
+def tile_shadows_batch(tiles, tile_xy, sp):
+    tiles = np.ascontiguousarray(tiles, np.float32)
+    nt, zv = tiles.shape[0], tiles.shape[1]
+    txy = np.ascontiguousarray(tile_xy, np.int32).reshape(-1, 2)
+    smask = np.empty((nt, zv, zv), np.uint8)
+    ox, oy = np.empty((nt, zv), np.float32), np.empty((nt, zv), np.float32)
+    lib().to_tile_shadows_batch(_p(tiles), _p(txy), nt, zv, C.byref(sp), _p(smask), _p(ox), _p(oy))
+    return smask, ox, oy
 
 
 def voxel_outside(vals, vpp, zix_xy=None):

@@ -80,6 +80,8 @@ def lib():
                 getattr(L, n).argtypes = [C.c_void_p]
             L.ref_vox_tables.argtypes = [C.c_void_p] * 3
             L.ref_vox_set_display_mode_bit.argtypes = [C.c_int]
+        if hasattr(L, "ref_calc_mesh_shadows"):   # mesh_shadow_gen / calc_mesh_shadows cut out of src/visibility.cpp at build time
+            L.ref_calc_mesh_shadows.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         _lib = L
     return _lib
 
@@ -303,3 +305,21 @@ def mc_tables():
     e, t, v = np.empty(256, np.uint32), np.empty((256, 16), np.int32), np.empty((12, 2), np.uint32)
     lib().ref_vox_tables(e.ctypes.data_as(C.c_void_p), t.ctypes.data_as(C.c_void_p), v.ctypes.data_as(C.c_void_p))
     return e, t, v
+
+
+def has_shadow_extract():
+    return available() and hasattr(lib(), "ref_calc_mesh_shadows")
+
+
+def calc_mesh_shadows(lpos, mh, zmin, zmax, sh_in_x=None, sh_in_y=None):
+    """The reference's own calc_mesh_shadows (LIGHT_SUN) on one tile, scene constants from setup(); run with ref_set_threads(1). Returns (smask, sh_out_x, sh_out_y)."""
+    mh = np.ascontiguousarray(mh, np.float32)
+    ys, xs = mh.shape
+    smask = np.empty((ys, xs), np.uint8)
+    ox, oy = np.full(xs, -1.0e6, np.float32), np.full(ys, -1.0e6, np.float32)
+    lp = np.asarray(lpos, np.float32)
+    six = None if sh_in_x is None else np.ascontiguousarray(sh_in_x, np.float32)
+    siy = None if sh_in_y is None else np.ascontiguousarray(sh_in_y, np.float32)
+    p = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)
+    lib().ref_calc_mesh_shadows(p(lp), p(mh), p(smask), xs, ys, zmin, zmax, p(six), p(siy), p(ox), p(oy))
+    return smask, ox, oy

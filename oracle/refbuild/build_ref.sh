@@ -52,6 +52,19 @@ V=$R/src/voxels.cpp
   cat "$HERE/ref_voxels_harness.inc"
 } > "$OUT/gen/voxels_extract.cpp"
 g++ $FLAGS $INC -I "$HERE" -c "$OUT/gen/voxels_extract.cpp" -o "$OUT/voxels_extract.o"
+# Mesh shadows: class mesh_shadow_gen + calc_mesh_shadows from src/visibility.cpp (:411-517) and the line clip they call
+# (TEST_CLIP_T + do_line_clip, src/Math3d.cpp:1029-1034,1070-1086), cut out by signature; both files pull in the engine as a whole.
+{
+  echo "// GENERATED at build time by oracle/refbuild/build_ref.sh from $R/src/visibility.cpp and $R/src/Math3d.cpp - do not commit"
+  echo '#include "3DWorld.h"'
+  echo '#include "mesh.h"'
+  echo 'extern float zmin, zmax; extern bool combined_gu; extern int XY_SUM_SIZE;'
+  awk '/^#define TEST_CLIP_T/ {p=1} p {print} p && !/\\\r?$/ {exit}' "$R/src/Math3d.cpp"
+  awk '/^bool do_line_clip\(point &v1, point &v2, float const d\[3\]\[2\]\) \{/ {p=1} p {print} p && /^}/ {exit}' "$R/src/Math3d.cpp"
+  awk '/^class mesh_shadow_gen \{/ {p=1} /^void calc_visibility/ {exit} p {print}' "$R/src/visibility.cpp"
+  cat "$HERE/ref_shadow_harness.inc"
+} > "$OUT/gen/shadow_extract.cpp"
+g++ $FLAGS $INC -I "$HERE" -c "$OUT/gen/shadow_extract.cpp" -o "$OUT/shadow_extract.o"
 g++ -shared -fopenmp -Wl,--gc-sections -Wl,--no-undefined -Wl,--version-script="$HERE/exports.map" -o "$OUT/libref3dworld.so" \
-  "$OUT"/ref_driver.o "$OUT"/ref_stubs.o "$OUT"/ref_glm.o "$OUT"/mesh_gen.o "$OUT"/erosion.o "$OUT"/upsurface.o "$OUT"/heightmap.o "$OUT"/tiled_extract.o "$OUT"/voxels_extract.o
+  "$OUT"/ref_driver.o "$OUT"/ref_stubs.o "$OUT"/ref_glm.o "$OUT"/mesh_gen.o "$OUT"/erosion.o "$OUT"/upsurface.o "$OUT"/heightmap.o "$OUT"/tiled_extract.o "$OUT"/voxels_extract.o "$OUT"/shadow_extract.o
 echo "built $OUT/libref3dworld.so"

@@ -1223,3 +1223,128 @@ unsigned long long to_voxel_triangles(const float *vals, const unsigned char *ou
 	}
 	return n;
 }
+
+
+/* ------------------------------------------------------------------ mesh shadows
+ * Pinned against the reference's own mesh_shadow_gen / calc_mesh_shadows / do_line_clip, cut out of src/visibility.cpp and src/Math3d.cpp at build time. */
+typedef struct {float x, y, z;} sh_pt;
+static int sh_region(sh_pt v, float d[3][2]) { /* get_region, ref: src/inlines.h:522-528 */
+	int region = 0;
+	if (v.x < d[0][0]) {region |= 0x01;} else if (v.x >= d[0][1]) {region |= 0x02;}
+	if (v.y < d[1][0]) {region |= 0x04;} else if (v.y >= d[1][1]) {region |= 0x08;}
+	if (v.z < d[2][0]) {region |= 0x10;} else if (v.z >= d[2][1]) {region |= 0x20;}
+	return region;
+}
+static int sh_line_clip(sh_pt *v1, sh_pt *v2, float d[3][2]) { /* do_line_clip, ref: src/Math3d.cpp:1029-1034,1070-1086 */
+	float const TOLERANCE = 1.0E-12f;
+	int const region1 = sh_region(*v1, d), region2 = sh_region(*v2, d);
+	if (region1 & region2) return 0;
+	int const region3 = region1 | region2;
+	if (region3 == 0) return 1;
+	float tmin = 0.0f, tmax = 1.0f;
+	sh_pt const dv = {v2->x - v1->x, v2->y - v1->y, v2->z - v1->z};
+#define SH_CLIP(reg, va, vb, vd, vc) if (region3 & (reg)) {float const t = ((va) - (vb))/(vd); if ((vc) > 0.0) {if (t > tmin) tmin = t;} else {if (t < tmax) tmax = t;} if (tmin >= tmax) return 0;}
+	SH_CLIP(0x01, d[0][0], v1->x, dv.x,  dv.x)
+	SH_CLIP(0x02, d[0][1], v1->x, dv.x, -dv.x)
+	SH_CLIP(0x04, d[1][0], v1->y, dv.y,  dv.y)
+	SH_CLIP(0x08, d[1][1], v1->y, dv.y, -dv.y)
+	SH_CLIP(0x10, d[2][0], v1->z, dv.z,  dv.z)
+	SH_CLIP(0x20, d[2][1], v1->z, dv.z, -dv.z)
+#undef SH_CLIP
+	if (tmax > TOLERANCE) {v2->x = v1->x + dv.x*tmax; v2->y = v1->y + dv.y*tmax; v2->z = v1->z + dv.z*tmax;}
+	if ((double)tmin < (1.0 - TOLERANCE)) {v1->x += dv.x*tmin; v1->y += dv.y*tmin; v1->z += dv.z*tmin;}
+	return 1;
+}
+typedef struct {const tw_shadow_params *sp; const float *mh, *sh_in_x, *sh_in_y; float *sh_out_x, *sh_out_y; unsigned char *smask; int xsize, ysize; sh_pt dir; float dist;} sh_gen;
+static void sh_trace(const sh_gen *G, sh_pt v1) { /* mesh_shadow_gen::trace_shadow_path, ref: src/visibility.cpp:421-477 */
+	const tw_shadow_params *sp = G->sp;
+	int const xsize = G->xsize, ysize = G->ysize;
+	sh_pt v2 = {v1.x + G->dir.x*G->dist, v1.y + G->dir.y*G->dist, v1.z + 0.0f};
+	float d[3][2] = {{-sp->x_scene_size, -sp->x_scene_size + sp->dx_val*xsize}, {-sp->y_scene_size, -sp->y_scene_size + sp->dy_val*ysize}, {sp->zmin, sp->zmax}};
+	if (!sh_line_clip(&v1, &v2, d)) return;
+	int const xa = (int)((v1.x + sp->x_scene_size)*sp->dx_val_inv + 0.5), ya = (int)((v1.y + sp->y_scene_size)*sp->dy_val_inv + 0.5);
+	int const xb = (int)((v2.x + sp->x_scene_size)*sp->dx_val_inv + 0.5), yb = (int)((v2.y + sp->y_scene_size)*sp->dy_val_inv + 0.5);
+	int const dx = xb - xa, dy = yb - ya;
+	int const dim = (fabsf(G->dir.x) < fabsf(G->dir.y));
+	double const dir_ratio = G->dir.z/(dim ? G->dir.y : G->dir.x);
+	int inited = 0;
+	sh_pt cur = {0, 0, 0};
+	int x = xa, y = ya, dx1 = 0, dy1 = 0, dx2 = 0, dy2 = 0;
+	if (dx < 0) {dx1 = -1; dx2 = -1;} else if (dx > 0) {dx1 = 1; dx2 = 1;}
+	if (dy < 0) {dy1 = -1;} else if (dy > 0) {dy1 = 1;}
+	int longest = abs(dx), shortest = abs(dy);
+	if (longest <= shortest) {
+		int const t = longest; longest = shortest; shortest = t;
+		if (dy < 0) {dy2 = -1;} else if (dy > 0) {dy2 = 1;}
+		dx2 = 0;
+	}
+	int numerator = longest >> 1;
+	for (int i = 0; i <= longest; i++) {
+		if (x >= 0 && y >= 0 && x < xsize && y < ysize) {
+			sh_pt const pt = {-sp->x_scene_size + sp->dx_val*x, -sp->y_scene_size + sp->dy_val*y, G->mh[y*xsize + x]};
+			if (G->sh_in_y != NULL && x == xa && G->sh_in_y[y] > TW_MESH_MIN_Z) {cur.x = pt.x; cur.y = pt.y; cur.z = G->sh_in_y[y]; inited = 1;}
+			else if (G->sh_in_x != NULL && y == ya && G->sh_in_x[x] > TW_MESH_MIN_Z) {cur.x = pt.x; cur.y = pt.y; cur.z = G->sh_in_x[x]; inited = 1;}
+			float const shadow_z = (float)(((dim ? pt.y : pt.x) - (dim ? cur.y : cur.x))*dir_ratio + cur.z);
+			if (inited && shadow_z > pt.z) {
+				G->smask[y*xsize + x] |= TW_MESH_SHADOW;
+				if (G->sh_out_y != NULL && x == xb) {G->sh_out_y[y] = shadow_z;}
+				if (G->sh_out_x != NULL && y == yb) {G->sh_out_x[x] = shadow_z;}
+			}
+			else {cur = pt;}
+			inited = 1;
+		}
+		numerator += shortest;
+		if (numerator >= longest) {numerator -= longest; x += dx1; y += dy1;} else {x += dx2; y += dy2;}
+	}
+}
+void to_calc_mesh_shadows(const tw_shadow_params *sp, const float *mh, unsigned char *smask, int xsize, int ysize, const float *sh_in_x, const float *sh_in_y,
+                          float *sh_out_x, float *sh_out_y)
+{ /* calc_mesh_shadows + mesh_shadow_gen::run, ref: src/visibility.cpp:478-517 (run_x then run_y: the 1-thread order of the two OpenMP sections) */
+	float const TOLERANCE = 1.0E-12f;
+	int const all_shadowed = (!sp->no_shadow && sp->lpos[2] < sp->zmin);
+	for (int i = 0; i < xsize*ysize; ++i) {smask[i] = all_shadowed ? TW_MESH_SHADOW : 0;}
+	if (sp->no_shadow) return;
+	if (sp->lpos[0] == 0.0 && sp->lpos[1] == 0.0) return;
+	sh_gen G = {sp, mh, sh_in_x, sh_in_y, sh_out_x, sh_out_y, smask, xsize, ysize, {0, 0, 0}, 0.0f};
+	float const vmag = sqrtf(sp->lpos[0]*sp->lpos[0] + sp->lpos[1]*sp->lpos[1] + sp->lpos[2]*sp->lpos[2]);
+	sh_pt n = {sp->lpos[0], sp->lpos[1], sp->lpos[2]};
+	if (!(vmag < TOLERANCE)) {n.x = sp->lpos[0]/vmag; n.y = sp->lpos[1]/vmag; n.z = sp->lpos[2]/vmag;} /* get_norm */
+	G.dir.x = -n.x; G.dir.y = -n.y; G.dir.z = -n.z;
+	G.dist = (float)(2.0*sp->xy_sum_size/sqrtf(G.dir.x*G.dir.x + G.dir.y*G.dir.y));
+	{
+		float const xval = -sp->x_scene_size + sp->dx_val*((G.dir.x > 0) ? 0 : xsize);
+		for (int y = 0; y < 2*ysize; ++y) {sh_pt const v = {xval, (float)(-sp->y_scene_size + 0.5*sp->dy_val*y), 0.0f}; sh_trace(&G, v);}
+	}
+	{
+		float const yval = -sp->y_scene_size + sp->dy_val*((G.dir.y > 0) ? 0 : ysize);
+		for (int x = 0; x < 2*xsize; ++x) {sh_pt const v = {(float)(-sp->x_scene_size + 0.5*sp->dx_val*x), yval, 0.0f}; sh_trace(&G, v);}
+	}
+}
+/* tile_t::calc_shadows_for_light for a batch (ref: src/tiled_mesh.cpp:664-692): a tile takes sh_in from the sh_out of its neighbours toward the light when they are in
+ * the batch (d = 0: x neighbour's sh_out[1] -> sh_in_y; d = 1: y neighbour's sh_out[0] -> sh_in_x); tiles are processed so that neighbours come first */
+void to_tile_shadows_batch(const float *zvals, const int *tile_xy, unsigned ntiles, unsigned zvsize, const tw_shadow_params *sp, unsigned char *smask,
+                           float *sh_out_x, float *sh_out_y)
+{
+	int const sx = (sp->lpos[0] < 0.0) ? -1 : 1, sy = (sp->lpos[1] < 0.0) ? -1 : 1;
+	float *ox = (float *)malloc((size_t)ntiles*zvsize*sizeof(float)), *oy = (float *)malloc((size_t)ntiles*zvsize*sizeof(float));
+	int *done = (int *)calloc(ntiles, sizeof(int));
+	for (size_t i = 0; i < (size_t)ntiles*zvsize; ++i) {ox[i] = TW_MESH_MIN_Z; oy[i] = TW_MESH_MIN_Z;} /* sh_out[l][!d].resize(zvsize, MESH_MIN_Z), :677 */
+	for (unsigned pass = 0, ndone = 0; ndone < ntiles && pass <= ntiles; ++pass) {
+		for (unsigned t = 0; t < ntiles; ++t) {
+			if (done[t]) continue;
+			int nbx = -1, nby = -1, wait = 0;
+			for (unsigned u = 0; u < ntiles; ++u) {
+				if (tile_xy[2*u] == tile_xy[2*t] + sx && tile_xy[2*u+1] == tile_xy[2*t+1]) {nbx = (int)u;}
+				if (tile_xy[2*u] == tile_xy[2*t] && tile_xy[2*u+1] == tile_xy[2*t+1] + sy) {nby = (int)u;}
+			}
+			if ((nbx >= 0 && !done[nbx]) || (nby >= 0 && !done[nby])) {wait = 1;}
+			if (wait) continue;
+			to_calc_mesh_shadows(sp, zvals + (size_t)t*zvsize*zvsize, smask + (size_t)t*zvsize*zvsize, (int)zvsize, (int)zvsize,
+			                     (nby >= 0) ? ox + (size_t)nby*zvsize : NULL, (nbx >= 0) ? oy + (size_t)nbx*zvsize : NULL, ox + (size_t)t*zvsize, oy + (size_t)t*zvsize);
+			done[t] = 1; ++ndone;
+		}
+	}
+	if (sh_out_x) {memcpy(sh_out_x, ox, (size_t)ntiles*zvsize*sizeof(float));}
+	if (sh_out_y) {memcpy(sh_out_y, oy, (size_t)ntiles*zvsize*sizeof(float));}
+	free(ox); free(oy); free(done);
+}

@@ -84,6 +84,11 @@ void  to_voxel_fill(const tw_voxel_params *vp, const float *rdata420, const floa
 size_t to_from_floats_u16(const float *vals, size_t n, float val_mult, float val_add, unsigned char *out2n);
 void   to_to_floats_u16(const unsigned char *data2n, size_t n, float val_mult, float val_add, float *vals);
 
+/* mesh shadows, ref: src/visibility.cpp:411-517, src/Math3d.cpp:1029-1086, src/tiled_mesh.cpp:664-692 */
+void to_calc_mesh_shadows(const tw_shadow_params *sp, const float *mh, unsigned char *smask, int xsize, int ysize, const float *sh_in_x, const float *sh_in_y,
+                          float *sh_out_x, float *sh_out_y);
+void to_tile_shadows_batch(const float *zvals, const int *tile_xy, unsigned ntiles, unsigned zvsize, const tw_shadow_params *sp, unsigned char *smask,
+                           float *sh_out_x, float *sh_out_y);
 /* voxel post-processing, ref: src/voxels.cpp:485-610,739-868 */
 void to_voxel_outside(const float *vals, const tw_voxel_post_params *vp, const unsigned *zix_xy, unsigned char *outside);
 unsigned long long to_voxel_remove_unconnected(float *vals, unsigned char *outside, const tw_voxel_post_params *vp);

@@ -359,3 +359,77 @@ def test_voxel_post_processing_against_extracted_reference(oracle, ref, beq):
         V.set_zmin_matrix(None)
     changed_any = True
     assert changed_any
+
+
+def test_mesh_shadows_against_extracted_reference(oracle, ref, beq):
+    """SURVEY 8f row N4 pinned against the reference's OWN mesh_shadow_gen / calc_mesh_shadows / do_line_clip (cut out of src/visibility.cpp:411-517 and
+    src/Math3d.cpp at build time): shadow mask and outgoing shadow heights of one tile for light directions in every octant, steep and grazing, with and
+    without incoming heights from neighbour tiles; 1 OpenMP thread (the reference's two sections race on sh_out otherwise)."""
+    import pytest
+    if not ref.has_shadow_extract():
+        pytest.skip("oracle/_ref was built without the visibility.cpp extraction")
+    RL = ref.lib()
+    RL.ref_set_threads(1)
+    rng = np.random.default_rng(9)
+    for mesh, zv in (((64, 64, 1), 66), ((128, 128, 1), 130), ((32, 48, 1), 40)):
+        ref.setup(mesh=mesh, mode=1, freq_filter=1, seed=1, zmax_est=2.0, hmap=HM_CFG)
+        dx, dy = RL.ref_get_dx(), RL.ref_get_dy()
+        z = ref.heightgen(-zv / 2, -zv / 2, dx, dy, zv, zv, 0, 1)
+        zlo, zhi = float(z.min()) - 0.5, float(z.max()) + 0.5
+        sp = oracle.ShadowParams()
+        sp.x_scene_size, sp.y_scene_size, sp.dx_val, sp.dy_val = 4.0, 4.0, dx, dy
+        sp.dx_val_inv, sp.dy_val_inv = 1.0 / np.float32(dx), 1.0 / np.float32(dy)
+        sp.xy_sum_size, sp.zmin, sp.zmax, sp.no_shadow = mesh[0] + mesh[1], zlo, zhi, 0
+        lights = [(3.0, 2.0, 1.0), (-4.0, 1.0, 0.5), (1.0, -5.0, 0.7), (-2.0, -2.0, 3.0), (0.3, 6.0, 0.2), (5.0, 0.0, 1.0), (0.0, -3.0, 2.0), (0.0, 0.0, 5.0), (2.0, 1.0, zlo - 1.0)]
+        for lp in lights:
+            for d in range(3):
+                sp.lpos[d] = lp[d]
+            for with_in in (0, 1):
+                six = siy = None
+                if with_in:   # heights a neighbour tile would hand over: some entries "none" (MESH_MIN_Z), some above the terrain
+                    six = np.where(rng.random(zv) < 0.3, -1.0e6, z[0] + rng.uniform(-0.2, 0.6, zv)).astype(np.float32)
+                    siy = np.where(rng.random(zv) < 0.3, -1.0e6, z[:, 0] + rng.uniform(-0.2, 0.6, zv)).astype(np.float32)
+                mr, oxr, oyr = ref.calc_mesh_shadows(lp, z, zlo, zhi, six, siy)
+                mo, oxo, oyo = oracle.calc_mesh_shadows(sp, z, six, siy)
+                assert np.array_equal(mr, mo), (mesh, lp, with_in, int((mr != mo).sum()))
+                assert beq(oxr, oxo) == 0 and beq(oyr, oyo) == 0, (mesh, lp, with_in)
+        assert 0 < (mo == 2).sum()
+    RL.ref_set_threads(8)
+
+
+def test_mesh_shadow_chaining_against_extracted_reference(oracle, ref, beq):
+    """tile_t::calc_shadows_for_light's chaining (src/tiled_mesh.cpp:664-692): a 3x3 block of tiles processed toward-the-light-first, each tile's sh_in = the sh_out of
+    its neighbours toward the light, done here by hand with the reference's own calc_mesh_shadows per tile, vs the oracle's batch function."""
+    import pytest
+    if not ref.has_shadow_extract():
+        pytest.skip("oracle/_ref was built without the visibility.cpp extraction")
+    RL = ref.lib()
+    RL.ref_set_threads(1)
+    S, zv = 32, 34
+    ref.setup(mesh=(S, S, 1), mode=1, freq_filter=1, seed=1, zmax_est=2.0, hmap=HM_CFG)
+    dx, dy = RL.ref_get_dx(), RL.ref_get_dy()
+    txy = [(tx, ty) for ty in range(-1, 2) for tx in range(2, 5)]
+    tiles = np.stack([ref.heightgen(tx * S - S // 2, ty * S - S // 2, dx, dy, zv, zv, 0, 1) for tx, ty in txy]) * 3.0
+    zlo, zhi = float(tiles.min()) - 0.5, float(tiles.max()) + 0.5
+    sp = oracle.ShadowParams()
+    sp.x_scene_size, sp.y_scene_size, sp.dx_val, sp.dy_val = 4.0, 4.0, dx, dy
+    sp.dx_val_inv, sp.dy_val_inv = 1.0 / np.float32(dx), 1.0 / np.float32(dy)
+    sp.xy_sum_size, sp.zmin, sp.zmax, sp.no_shadow = 2 * S, zlo, zhi, 0
+    for lp in ((3.0, 2.0, 0.4), (-4.0, 1.0, 0.3), (1.0, -5.0, 0.5), (-2.0, -3.0, 0.6)):
+        for d in range(3):
+            sp.lpos[d] = lp[d]
+        sx, sy = (-1 if lp[0] < 0 else 1), (-1 if lp[1] < 0 else 1)
+        idx = {t: i for i, t in enumerate(txy)}
+        done, masks = {}, {}
+        order = sorted(range(len(txy)), key=lambda i: -(sx * txy[i][0] + sy * txy[i][1]))     # closest to the light first
+        for i in order:
+            nbx, nby = idx.get((txy[i][0] + sx, txy[i][1])), idx.get((txy[i][0], txy[i][1] + sy))
+            six = done[nby][0] if nby is not None else None      # y neighbour's sh_out[0]
+            siy = done[nbx][1] if nbx is not None else None      # x neighbour's sh_out[1]
+            m, ox, oy = ref.calc_mesh_shadows(lp, tiles[i], zlo, zhi, six, siy)
+            done[i], masks[i] = (ox, oy), m
+        mo, oxo, oyo = oracle.tile_shadows_batch(tiles, txy, sp)
+        for i in range(len(txy)):
+            assert np.array_equal(masks[i], mo[i]) and beq(done[i][0], oxo[i]) == 0 and beq(done[i][1], oyo[i]) == 0, (lp, i)
+        assert any((done[i][0] > -1e5).any() or (done[i][1] > -1e5).any() for i in range(len(txy)))   # shadows did cross tile borders
+    RL.ref_set_threads(8)
