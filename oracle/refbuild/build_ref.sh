@@ -64,7 +64,10 @@ g++ $FLAGS $INC -I "$HERE" -c "$OUT/gen/voxels_extract.cpp" -o "$OUT/voxels_extr
   awk '/^class mesh_shadow_gen \{/ {p=1} /^void calc_visibility/ {exit} p {print}' "$R/src/visibility.cpp"
   cat "$HERE/ref_shadow_harness.inc"
 } > "$OUT/gen/shadow_extract.cpp"
-g++ $FLAGS $INC -I "$HERE" -c "$OUT/gen/shadow_extract.cpp" -o "$OUT/shadow_extract.o"
+# Built WITHOUT -fopenmp: mesh_shadow_gen::run (src/visibility.cpp:497-503) runs run_x() and run_y() as two concurrent OpenMP sections that both store into
+# sh_out_x/sh_out_y (last writer wins, unsynchronised), so the reference's own result is timing dependent in the cells both passes reach. The pinned semantics are
+# the serial ones (run_x then run_y) -- one of the outcomes the reference can produce, and the only reproducible one.
+g++ ${FLAGS/-fopenmp/} $INC -I "$HERE" -c "$OUT/gen/shadow_extract.cpp" -o "$OUT/shadow_extract.o"
 g++ -shared -fopenmp -Wl,--gc-sections -Wl,--no-undefined -Wl,--version-script="$HERE/exports.map" -o "$OUT/libref3dworld.so" \
   "$OUT"/ref_driver.o "$OUT"/ref_stubs.o "$OUT"/ref_glm.o "$OUT"/mesh_gen.o "$OUT"/erosion.o "$OUT"/upsurface.o "$OUT"/heightmap.o "$OUT"/tiled_extract.o "$OUT"/voxels_extract.o "$OUT"/shadow_extract.o
 echo "built $OUT/libref3dworld.so"

@@ -28,8 +28,10 @@ def test_tile_shadows_vs_oracle(tw, scene, oracle, ctx, beq, S, side):
     if side == 5:
         txy = [t for i, t in enumerate(txy) if i % 4 != 1]          # a batch with holes: missing neighbours mean "no incoming heights"
     origins = [(tx * S, ty * S) for tx, ty in txy]
-    tiles = ctx.heightgen_tiles(origins, cfg.mesh_size, float(cfg.dx_val), float(cfg.dy_val), zv, cfg.height_params()) * np.float32(3.0)
+    tiles = ctx.heightgen_tiles(origins, cfg.mesh_size, float(cfg.dx_val), float(cfg.dy_val), zv, cfg.height_params())
+    tiles = ((tiles - np.float32(tiles.mean())) * np.float32(3.0)).astype(np.float32)      # around 0: the rays run at z = 0 and are clipped against [zmin, zmax]
     zlo, zhi = float(tiles.min()) - 0.5, float(tiles.max()) + 0.5
+    assert zlo < 0.0 < zhi
     for lp in ((3.0, 2.0, 0.4), (-4.0, 1.0, 0.3), (1.0, -5.0, 0.5), (-2.0, -3.0, 2.0), (0.2, 6.0, 0.15), (5.0, 0.0, 1.0), (0.0, 0.0, 5.0), (2.0, 1.0, zlo - 1.0)):
         sp = _params(tw, cfg, S, zlo, zhi, lp)
         mo, oxo, oyo = oracle.tile_shadows_batch(tiles, txy, convert(sp, oracle.ShadowParams))

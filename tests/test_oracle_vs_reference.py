@@ -371,11 +371,14 @@ def test_mesh_shadows_against_extracted_reference(oracle, ref, beq):
     RL = ref.lib()
     RL.ref_set_threads(1)
     rng = np.random.default_rng(9)
+    left_tile = 0
     for mesh, zv in (((64, 64, 1), 66), ((128, 128, 1), 130), ((32, 48, 1), 40)):
         ref.setup(mesh=mesh, mode=1, freq_filter=1, seed=1, zmax_est=2.0, hmap=HM_CFG)
         dx, dy = RL.ref_get_dx(), RL.ref_get_dy()
         z = ref.heightgen(-zv / 2, -zv / 2, dx, dy, zv, zv, 0, 1)
+        z = (z - np.float32(z.mean())) * np.float32(2.0)          # around 0: the rays run at z = 0 and are clipped against [zmin, zmax] (src/visibility.cpp:424)
         zlo, zhi = float(z.min()) - 0.5, float(z.max()) + 0.5
+        assert zlo < 0.0 < zhi
         sp = oracle.ShadowParams()
         sp.x_scene_size, sp.y_scene_size, sp.dx_val, sp.dy_val = 4.0, 4.0, dx, dy
         sp.dx_val_inv, sp.dy_val_inv = 1.0 / np.float32(dx), 1.0 / np.float32(dy)
@@ -393,7 +396,11 @@ def test_mesh_shadows_against_extracted_reference(oracle, ref, beq):
                 mo, oxo, oyo = oracle.calc_mesh_shadows(sp, z, six, siy)
                 assert np.array_equal(mr, mo), (mesh, lp, with_in, int((mr != mo).sum()))
                 assert beq(oxr, oxo) == 0 and beq(oyr, oyo) == 0, (mesh, lp, with_in)
+                if lp[2] < 1.0 and lp[2] > zlo and (lp[0] or lp[1]):
+                    assert 0 < (mo == 2).sum() < mo.size, (mesh, lp)     # a real, partial shadow
+                    left_tile += int((oxo > -1e5).any() or (oyo > -1e5).any())
         assert 0 < (mo == 2).sum()
+    assert left_tile > 4         # shadows that run off the tile hand heights to the neighbours (sh_out)
     RL.ref_set_threads(8)
 
 
@@ -409,12 +416,15 @@ def test_mesh_shadow_chaining_against_extracted_reference(oracle, ref, beq):
     ref.setup(mesh=(S, S, 1), mode=1, freq_filter=1, seed=1, zmax_est=2.0, hmap=HM_CFG)
     dx, dy = RL.ref_get_dx(), RL.ref_get_dy()
     txy = [(tx, ty) for ty in range(-1, 2) for tx in range(2, 5)]
-    tiles = np.stack([ref.heightgen(tx * S - S // 2, ty * S - S // 2, dx, dy, zv, zv, 0, 1) for tx, ty in txy]) * 3.0
+    tiles = np.stack([ref.heightgen(tx * S - S // 2, ty * S - S // 2, dx, dy, zv, zv, 0, 1) for tx, ty in txy])
+    tiles = ((tiles - np.float32(tiles.mean())) * np.float32(3.0)).astype(np.float32)
     zlo, zhi = float(tiles.min()) - 0.5, float(tiles.max()) + 0.5
+    assert zlo < 0.0 < zhi
     sp = oracle.ShadowParams()
     sp.x_scene_size, sp.y_scene_size, sp.dx_val, sp.dy_val = 4.0, 4.0, dx, dy
     sp.dx_val_inv, sp.dy_val_inv = 1.0 / np.float32(dx), 1.0 / np.float32(dy)
     sp.xy_sum_size, sp.zmin, sp.zmax, sp.no_shadow = 2 * S, zlo, zhi, 0
+    chained = 0
     for lp in ((3.0, 2.0, 0.4), (-4.0, 1.0, 0.3), (1.0, -5.0, 0.5), (-2.0, -3.0, 0.6)):
         for d in range(3):
             sp.lpos[d] = lp[d]
@@ -431,5 +441,10 @@ def test_mesh_shadow_chaining_against_extracted_reference(oracle, ref, beq):
         mo, oxo, oyo = oracle.tile_shadows_batch(tiles, txy, sp)
         for i in range(len(txy)):
             assert np.array_equal(masks[i], mo[i]) and beq(done[i][0], oxo[i]) == 0 and beq(done[i][1], oyo[i]) == 0, (lp, i)
-        assert any((done[i][0] > -1e5).any() or (done[i][1] > -1e5).any() for i in range(len(txy)))   # shadows did cross tile borders
+        # sh_out is only written where x == xb / y == yb is inside the tile, i.e. for rays leaving through the x = 0 / y = 0 edge (src/visibility.cpp:461-462): light from +x / +y
+        if lp[0] > 0 or lp[1] > 0:
+            assert any((done[i][0] > -1e5).any() or (done[i][1] > -1e5).any() for i in range(len(txy)))   # shadows did cross tile borders
+            alone = [ref.calc_mesh_shadows(lp, tiles[i], zlo, zhi, None, None)[0] for i in range(len(txy))]
+            chained += sum(int(not np.array_equal(alone[i], masks[i])) for i in range(len(txy)))
+    assert chained > 0          # the handed-over heights changed some neighbour's mask
     RL.ref_set_threads(8)
