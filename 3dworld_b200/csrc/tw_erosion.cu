@@ -276,9 +276,10 @@ droplet_kernel(DArgs const A)
 				if (FROZEN && (zi < A.own0 || zi >= A.own1)) {iter += fz_stride;} // another device's droplet
 				else {
 					xp=xi; zp=zi; xf=0; zf=0; s=0; v=0; w=1; dx=0; dz=0;
+					if (FROZEN) {have_win = false;} // M_FROZEN: a new droplet knows nothing of the previous one's writes - its first reads included
 					h=hread(xi, zi); h00=h; h10=hread(xi+1, zi); h01=hread(xi, zi+1); h11=hread(xi+1, zi+1);
 					numMoves = 0; in_droplet = true; zstart = zi;
-					if (FROZEN) {iter += fz_stride; have_win = false;} else {++iter;} // M_FROZEN: a new droplet knows nothing of the previous one's writes
+					if (FROZEN) {iter += fz_stride;} else {++iter;}
 				}
 			}
 		}

@@ -329,15 +329,16 @@ static int erode_sweeps_core(int n, tw_ctx **ctxs, ncclComm_t *comms, float *con
 #define SW_FAIL(status, ...) do {snprintf(err, errlen, __VA_ARGS__); rc = (status); goto done;} while (0)
 #define SW_CUDA(call) do {cudaError_t e_ = (call); if (e_ != cudaSuccess) SW_FAIL(TW_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e_));} while (0)
 	int rc = TW_OK;
+	bool local = false;
 	int const PADR = 4, NX = xsize + 2*PADR, NY = ysize + 2*PADR;
 	std::vector<SweepBand> B(n);
 	std::string nerr;
-	NcclApi *N = (n > 1) ? nccl_api(nerr) : nullptr;
+	NcclApi *N = (n > 1 && comms) ? nccl_api(nerr) : nullptr;
 	if (moves) *moves = 0;
 	if (num_iters == 0 || ep->erode_amount <= 0.0) return TW_OK; // src/erosion.cpp:16
 	int const view = twi_sweep_view();
 	if (sweep == 0 || halo < view + 12 || xsize <= 0 || ysize <= 0) {snprintf(err, errlen, "sweep must be > 0 and halo >= %d (view + 12)", view + 12); return TW_ERR_ARG;}
-	if (n > 1 && !N) {snprintf(err, errlen, "%s", nerr.c_str()); return TW_ERR_STATE;}
+	if (n > 1 && comms && !N) {snprintf(err, errlen, "%s", nerr.c_str()); return TW_ERR_STATE;}
 	for (int i = 0; i < n; ++i) {
 		uint32_t a, b;
 		tw_multi_range((uint32_t)ysize, n, i, &a, &b);
@@ -361,7 +362,15 @@ static int erode_sweeps_core(int n, tw_ctx **ctxs, ncclComm_t *comms, float *con
 		SW_CUDA(cudaMemsetAsync(s.d_steps, 0, sizeof(unsigned long long), ctxs[i]->stream));
 		SW_CUDA(cudaMemcpyAsync(s.U + (size_t)(s.y0 - s.u0)*xsize, bands[i], (size_t)(s.y1 - s.y0)*xsize*sizeof(float), cudaMemcpyDefault, ctxs[i]->stream));
 	}
-	if (n > 1) { // initial halo of HEIGHTS: rows [u0, y0) come from the lower neighbour, [y1, u1) from the upper one
+	local = (n > 1 && comms == nullptr); // all bands on ONE device (tw_erode_sweeps_banded): neighbours exchange with device-to-device copies on the one stream
+	if (local) {
+		for (int i = 0; i < n; ++i) {
+			SweepBand &s = B[i];
+			if (i > 0)     SW_CUDA(cudaMemcpyAsync(s.U, B[i-1].U + (size_t)(s.u0 - B[i-1].u0)*xsize, (size_t)(s.y0 - s.u0)*xsize*sizeof(float), cudaMemcpyDeviceToDevice, ctxs[i]->stream));
+			if (i < n - 1) SW_CUDA(cudaMemcpyAsync(s.U + (size_t)(s.y1 - s.u0)*xsize, B[i+1].U + (size_t)(s.y1 - B[i+1].u0)*xsize, (size_t)(s.u1 - s.y1)*xsize*sizeof(float), cudaMemcpyDeviceToDevice, ctxs[i]->stream));
+		}
+	}
+	else if (n > 1) { // initial halo of HEIGHTS: rows [u0, y0) come from the lower neighbour, [y1, u1) from the upper one
 		N->GroupStart();
 		for (int i = 0; i < n; ++i) {
 			SweepBand &s = B[i];
@@ -391,6 +400,14 @@ static int erode_sweeps_core(int n, tw_ctx **ctxs, ncclComm_t *comms, float *con
 		}
 		if (n > 1) { // THE halo exchange of the sweep: 2*halo rows of deltas around every internal border, both directions, one NCCL group
 			size_t const cnt = (size_t)2*halo*NX;
+			if (local) { // every copy reads the senders' un-summed deltas: all copies are enqueued before the first add below (one stream)
+				for (int i = 0; i < n; ++i) {
+					SweepBand &s = B[i];
+					if (i < n - 1) SW_CUDA(cudaMemcpyAsync(s.Rhi, B[i+1].D + (size_t)(B[i+1].R0 - halo - B[i+1].E0)*NX, cnt*sizeof(long long), cudaMemcpyDeviceToDevice, ctxs[i]->stream));
+					if (i > 0)     SW_CUDA(cudaMemcpyAsync(s.Rlo, B[i-1].D + (size_t)(B[i-1].R1 - halo - B[i-1].E0)*NX, cnt*sizeof(long long), cudaMemcpyDeviceToDevice, ctxs[i]->stream));
+				}
+			}
+			else {
 			N->GroupStart();
 			for (int i = 0; i < n; ++i) {
 				SweepBand &s = B[i];
@@ -399,6 +416,7 @@ static int erode_sweeps_core(int n, tw_ctx **ctxs, ncclComm_t *comms, float *con
 				if (i > 0)     {N->Send(s.D + (size_t)(s.R0 - halo - s.E0)*NX, cnt, ncclInt64, i - 1, comms[i], st); N->Recv(s.Rlo, cnt, ncclInt64, i - 1, comms[i], st);}
 			}
 			if (N->GroupEnd() != ncclSuccess) SW_FAIL(TW_ERR_CUDA, "NCCL halo exchange (deltas) failed");
+			}
 			for (int i = 0; i < n; ++i) {
 				SweepBand &s = B[i];
 				SW_CUDA(cudaSetDevice(ctxs[i]->device));
@@ -450,6 +468,14 @@ extern "C" int tw_erode_sweeps(tw_ctx *ctx, float *heightmap, int xsize, int ysi
 	float *bands[1] = {heightmap};
 	tw_ctx *ctxs[1] = {ctx};
 	return erode_sweeps_core(1, ctxs, nullptr, bands, xsize, ysize, min_zval, num_iters, p, sweep, halo, moves, ctx->err, sizeof(ctx->err));
+}
+
+extern "C" int tw_erode_sweeps_banded(tw_ctx *ctx, float *const *bands, int nbands, int xsize, int ysize, float min_zval, uint32_t num_iters, const tw_erosion_params *p,
+                                      uint32_t sweep, int halo, uint64_t *moves)
+{
+	if (!ctx || !bands || !p || nbands < 1 || nbands > 1024) return TW_ERR_ARG;
+	std::vector<tw_ctx *> ctxs((size_t)nbands, ctx);
+	return erode_sweeps_core(nbands, ctxs.data(), nullptr, bands, xsize, ysize, min_zval, num_iters, p, sweep, halo, moves, ctx->err, sizeof(ctx->err));
 }
 
 extern "C" int tw_erode_sweeps_sharded(tw_multi *m, float *const *bands, int xsize, int ysize, float min_zval, uint32_t num_iters, const tw_erosion_params *p,

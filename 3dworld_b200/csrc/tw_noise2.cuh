@@ -147,23 +147,38 @@ __device__ __forceinline__ float4 simplex_lut_entry(float k) { // scalar restate
 // 8-copy table (8 copies * 16 bytes per entry) plus a constant. The constant and the lane's copy are folded into the per-thread base
 // `Lb` (32-bit shared-memory address), so a look-up is one integer add and one LDS - no F2I (XU pipe), no shift, no mask.
 // k is in range by construction (see above; NaN and far-out inputs never get here: noise_lattice_in_range sends them to the scalar path).
+// TW_LUT_DENORM (default): the magic number is a DENORMAL. k*(128*2^-149) + (A*2^-149) is exact for integers k*128 + A < 2^23, and the bit pattern of the
+// denormal result IS the integer 128*k + A. With A = the shared-memory address of the lane's copy of entry 0 (< 2^18), one genuine FFMA2 turns the two
+// cells' indices into their two LDS addresses - no integer add at all (fp32 denormals run at full rate on the FMA pipe; nothing here is compiled with -ftz).
+// Without it (TW_LUT_DENORM=0, the round-1 form): magic 1.5*2^23, bits 0x4B400000 + 128*k, and one IADD per look-up to rebase.
+#ifndef TW_LUT_DENORM
+#define TW_LUT_DENORM 1
+#endif
 constexpr unsigned SIMPLEX_LUT_MAGIC_BITS = 0x4B400000u; // bits of 12582912.0f = 1.5*2^23
+constexpr unsigned LUT_ENTRY_BYTES = 16u*SIMPLEX_LUT_COPIES;
 __device__ __forceinline__ unsigned simplex_lut_base(const float4 *lut_s, unsigned lane) {
-	return (unsigned)__cvta_generic_to_shared(lut_s) + (lane & (SIMPLEX_LUT_COPIES - 1))*16u - SIMPLEX_LUT_MAGIC_BITS;
+	unsigned const a = (unsigned)__cvta_generic_to_shared(lut_s) + (lane & (SIMPLEX_LUT_COPIES - 1))*16u;
+	return TW_LUT_DENORM ? a : a - SIMPLEX_LUT_MAGIC_BITS;
 }
-__device__ __forceinline__ f2 lut_offsets(f2 k) {return fma2(k, 16.0f*SIMPLEX_LUT_COPIES, 12582912.0f);}
+// offsets for two cells; with TW_LUT_DENORM their bits are the LDS addresses themselves
+__device__ __forceinline__ f2 lut_offsets(f2 k, unsigned Lb) {
+	if (TW_LUT_DENORM) {return raw_fma(k, splat(__uint_as_float(LUT_ENTRY_BYTES)), splat(__uint_as_float(Lb)));}
+	return fma2(k, 16.0f*SIMPLEX_LUT_COPIES, 12582912.0f);
+}
+__device__ __forceinline__ unsigned lut_addr(unsigned Lb, float off) {return TW_LUT_DENORM ? __float_as_uint(off) : Lb + __float_as_uint(off);}
 __device__ __forceinline__ float4 lut_load4(unsigned Lb, float off) {
-	float4 v; asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(Lb + __float_as_uint(off)));
+	float4 v; asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(lut_addr(Lb, off)));
 	return v;
 }
 __device__ __forceinline__ float lut_load_w_addr(unsigned addr) {
 	float v; asm("ld.shared.f32 %0, [%1+12];" : "=f"(v) : "r"(addr));
 	return v;
 }
-__device__ __forceinline__ float lut_load_w(unsigned Lb, float off) {
-	float v; asm("ld.shared.f32 %0, [%1+12];" : "=f"(v) : "r"(Lb + __float_as_uint(off)));
+__device__ __forceinline__ float lut_load_w_addr_next(unsigned addr) { // .w of the following entry
+	float v; asm("ld.shared.f32 %0, [%1+140];" : "=f"(v) : "r"(addr));
 	return v;
 }
+__device__ __forceinline__ float lut_load_w(unsigned Lb, float off) {return lut_load_w_addr(lut_addr(Lb, off));}
 
 // glm::simplex(vec2) for two positions with the table; Lb = simplex_lut_base()
 __device__ __forceinline__ f2 simplex2_lut(f2 vx, f2 vy, unsigned Lb) {
@@ -178,12 +193,17 @@ __device__ __forceinline__ f2 simplex2_lut(f2 vx, f2 vy, unsigned Lb) {
 #if TW_SIMPLEX_LUT >= 2
 	ix = mod_int289_lazy(ix); iy = mod_int289_lazy(iy);
 	// permute(iy), permute(iy + i1.y), permute(iy + 1): consecutive table entries, so the second and third addresses are the first plus 0/128/256 bytes
-	f2 const j0 = lut_offsets(iy);
-	unsigned const ja = Lb + __float_as_uint(j0.x), jb = Lb + __float_as_uint(j0.y);
-	unsigned const LUT_ENTRY = 16u*SIMPLEX_LUT_COPIES;
+	f2 const j0 = lut_offsets(iy, Lb);
+	unsigned const ja = lut_addr(Lb, j0.x), jb = lut_addr(Lb, j0.y);
+	static_assert(LUT_ENTRY_BYTES == 128, "lut_load_w_addr_next hard-codes the entry pitch");
 	f2 const q0 = make_float2(lut_load_w_addr(ja), lut_load_w_addr(jb));
-	f2 const q1 = make_float2(lut_load_w_addr(ja + ((x0x.x > x0y.x) ? 0u : LUT_ENTRY)), lut_load_w_addr(jb + ((x0x.y > x0y.y) ? 0u : LUT_ENTRY)));
-	f2 const q2 = make_float2(lut_load_w_addr(ja + LUT_ENTRY), lut_load_w_addr(jb + LUT_ENTRY));
+#if TW_LUT_DENORM
+	f2 const j1 = raw_fma(i1y, splat(__uint_as_float(LUT_ENTRY_BYTES)), j0); // entry iy + i1.y: one packed FMA instead of two selects and two adds
+	f2 const q1 = make_float2(lut_load_w_addr(__float_as_uint(j1.x)), lut_load_w_addr(__float_as_uint(j1.y)));
+#else
+	f2 const q1 = make_float2(lut_load_w_addr(ja + ((x0x.x > x0y.x) ? 0u : LUT_ENTRY_BYTES)), lut_load_w_addr(jb + ((x0x.y > x0y.y) ? 0u : LUT_ENTRY_BYTES)));
+#endif
+	f2 const q2 = make_float2(lut_load_w_addr_next(ja), lut_load_w_addr_next(jb));
 #else
 	ix = mod_int289(ix); iy = mod_int289(iy);
 	f2 const q0 = permute(iy), q1 = permute(add2(iy, i1y)), q2 = permute(add2(iy, 1.0f));
@@ -198,7 +218,7 @@ __device__ __forceinline__ f2 simplex2_lut(f2 vx, f2 vy, unsigned Lb) {
 	f2 m2 = max0_2(rsub2(0.5f, add2(mul2(x12z, x12z), mul2(x12w, x12w))));
 	m0 = mul2(m0, m0); m1 = mul2(m1, m1); m2 = mul2(m2, m2);
 	m0 = mul2(m0, m0); m1 = mul2(m1, m1); m2 = mul2(m2, m2);
-	f2 const k0 = lut_offsets(p0), k1 = lut_offsets(p1), k2 = lut_offsets(p2);
+	f2 const k0 = lut_offsets(p0, Lb), k1 = lut_offsets(p1, Lb), k2 = lut_offsets(p2, Lb);
 	float4 const g0a = lut_load4(Lb, k0.x), g0b = lut_load4(Lb, k0.y), g1a = lut_load4(Lb, k1.x), g1b = lut_load4(Lb, k1.y), g2a = lut_load4(Lb, k2.x), g2b = lut_load4(Lb, k2.y);
 	// the table values arrive one cell per register quad, so the products with them are plain scalar FMUL/FADD (same IEEE operations; the
 	// file is compiled with -fmad=false) - re-pairing them for packed instructions would cost more MOVs than the packed form saves
@@ -258,13 +278,13 @@ __device__ __forceinline__ f2 perlin2_lut(f2 Px, f2 Py, unsigned Lb) {
 	f2 const frx = sub2(Px, flx), fry = sub2(Py, fly);
 	f2 const Pfz = add2(frx, -1.0f), Pfw = add2(fry, -1.0f);
 	f2 const Pix = mod_int289_lazy(flx), Piy = mod_int289_lazy(fly), Piz = mod_int289_lazy(add2(flx, 1.0f)), Piw = mod_int289_lazy(add2(fly, 1.0f));
-	f2 const jx = lut_offsets(Pix), jz = lut_offsets(Piz);
+	f2 const jx = lut_offsets(Pix, Lb), jz = lut_offsets(Piz, Lb);
 	f2 const qx = make_float2(lut_load_w(Lb, jx.x), lut_load_w(Lb, jx.y)), qz = make_float2(lut_load_w(Lb, jz.x), lut_load_w(Lb, jz.y)); // permute(ix)
 #if TW_SIMPLEX_LUT >= 3
-	f2 const k00 = lut_offsets(add2(qx, Piy)), k10 = lut_offsets(add2(qz, Piy)), k01 = lut_offsets(add2(qx, Piw)), k11 = lut_offsets(add2(qz, Piw));
+	f2 const k00 = lut_offsets(add2(qx, Piy), Lb), k10 = lut_offsets(add2(qz, Piy), Lb), k01 = lut_offsets(add2(qx, Piw), Lb), k11 = lut_offsets(add2(qz, Piw), Lb);
 #else
-	f2 const k00 = lut_offsets(permute(add2(qx, Piy))), k10 = lut_offsets(permute(add2(qz, Piy)));
-	f2 const k01 = lut_offsets(permute(add2(qx, Piw))), k11 = lut_offsets(permute(add2(qz, Piw)));
+	f2 const k00 = lut_offsets(permute(add2(qx, Piy)), Lb), k10 = lut_offsets(permute(add2(qz, Piy)), Lb);
+	f2 const k01 = lut_offsets(permute(add2(qx, Piw)), Lb), k11 = lut_offsets(permute(add2(qz, Piw)), Lb);
 #endif
 	float4 const a00 = lut_load4(Lb, k00.x), b00 = lut_load4(Lb, k00.y), a10 = lut_load4(Lb, k10.x), b10 = lut_load4(Lb, k10.y);
 	float4 const a01 = lut_load4(Lb, k01.x), b01 = lut_load4(Lb, k01.y), a11 = lut_load4(Lb, k11.x), b11 = lut_load4(Lb, k11.y);
@@ -299,7 +319,9 @@ __device__ __forceinline__ float4 perlin3_lut_entry(float k) {
 	twn::perlin3_grad(pk, gx, gy, gz);
 	return make_float4(gx, gy, gz, pk);
 }
-__device__ __forceinline__ float lut_offset1(float k) {return __fmaf_rn(k, 16.0f*SIMPLEX_LUT_COPIES, 12582912.0f);} // exact, see lut_offsets
+__device__ __forceinline__ float lut_offset1(float k, unsigned Lb) { // exact, see lut_offsets
+	return TW_LUT_DENORM ? __fmaf_rn(k, __uint_as_float(LUT_ENTRY_BYTES), __uint_as_float(Lb)) : __fmaf_rn(k, 16.0f*SIMPLEX_LUT_COPIES, 12582912.0f);
+}
 
 __device__ __forceinline__ float simplex3_lut(float vx, float vy, float vz, unsigned Lb) {
 	float const Cx = (float)(1.0/6.0), Cy = (float)(1.0/3.0);
@@ -315,13 +337,13 @@ __device__ __forceinline__ float simplex3_lut(float vx, float vy, float vz, unsi
 	float const x2x = x0x - i2x + Cy, x2y = x0y - i2y + Cy, x2z = x0z - i2z + Cy;
 	float const x3x = x0x - 0.5f, x3y = x0y - 0.5f, x3z = x0z - 0.5f;
 	i0 = twn::mod289(i0); i1_ = twn::mod289(i1_); i2_ = twn::mod289(i2_);
-	float const q0 = lut_load_w(Lb, lut_offset1(i2_)), q1 = lut_load_w(Lb, lut_offset1(i2_ + i1z)), q2 = lut_load_w(Lb, lut_offset1(i2_ + i2z)),
-	            q3 = lut_load_w(Lb, lut_offset1(i2_ + 1.0f)); // twn::permute(i.z + ...)
+	float const q0 = lut_load_w(Lb, lut_offset1(i2_, Lb)), q1 = lut_load_w(Lb, lut_offset1(i2_ + i1z, Lb)), q2 = lut_load_w(Lb, lut_offset1(i2_ + i2z, Lb)),
+	            q3 = lut_load_w(Lb, lut_offset1(i2_ + 1.0f, Lb)); // twn::permute(i.z + ...)
 	float const p0 = twn::permute(q0 + i1_)        + i0;        // arguments of the last permute: the table holds the gradient of permute(argument)
 	float const p1 = twn::permute(q1 + i1_ + i1y)  + i0 + i1x;
 	float const p2 = twn::permute(q2 + i1_ + i2y)  + i0 + i2x;
 	float const p3 = twn::permute(q3 + i1_ + 1.0f) + i0 + 1.0f;
-	float4 const P0 = lut_load4(Lb, lut_offset1(p0)), P1 = lut_load4(Lb, lut_offset1(p1)), P2 = lut_load4(Lb, lut_offset1(p2)), P3 = lut_load4(Lb, lut_offset1(p3));
+	float4 const P0 = lut_load4(Lb, lut_offset1(p0, Lb)), P1 = lut_load4(Lb, lut_offset1(p1, Lb)), P2 = lut_load4(Lb, lut_offset1(p2, Lb)), P3 = lut_load4(Lb, lut_offset1(p3, Lb));
 	float m0 = twn::gmax0(0.6f - (x0x*x0x + x0y*x0y + x0z*x0z)), m1 = twn::gmax0(0.6f - (x1x*x1x + x1y*x1y + x1z*x1z));
 	float m2 = twn::gmax0(0.6f - (x2x*x2x + x2y*x2y + x2z*x2z)), m3 = twn::gmax0(0.6f - (x3x*x3x + x3y*x3y + x3z*x3z));
 	m0 = m0*m0; m1 = m1*m1; m2 = m2*m2; m3 = m3*m3;
@@ -336,17 +358,17 @@ __device__ __forceinline__ float perlin3_lut(float Px, float Py, float Pz, unsig
 	float const Pi1x = twn::mod289(flx + 1.0f), Pi1y = twn::mod289(fly + 1.0f), Pi1z = twn::mod289(flz + 1.0f);
 	float const f0x = Px - flx, f0y = Py - fly, f0z = Pz - flz;
 	float const f1x = f0x - 1.0f, f1y = f0y - 1.0f, f1z = f0z - 1.0f;
-	float const px0 = lut_load_w(Lb, lut_offset1(Pi0x)), px1 = lut_load_w(Lb, lut_offset1(Pi1x)); // twn::permute(Pi.x)
+	float const px0 = lut_load_w(Lb, lut_offset1(Pi0x, Lb)), px1 = lut_load_w(Lb, lut_offset1(Pi1x, Lb)); // twn::permute(Pi.x)
 	float const ixy00 = twn::permute(px0 + Pi0y), ixy10 = twn::permute(px1 + Pi0y), ixy01 = twn::permute(px0 + Pi1y), ixy11 = twn::permute(px1 + Pi1y);
 	float4 g;
-	g = lut_load4(Lb, lut_offset1(ixy00 + Pi0z)); float const n000 = g.x*f0x + g.y*f0y + g.z*f0z;
-	g = lut_load4(Lb, lut_offset1(ixy10 + Pi0z)); float const n100 = g.x*f1x + g.y*f0y + g.z*f0z;
-	g = lut_load4(Lb, lut_offset1(ixy01 + Pi0z)); float const n010 = g.x*f0x + g.y*f1y + g.z*f0z;
-	g = lut_load4(Lb, lut_offset1(ixy11 + Pi0z)); float const n110 = g.x*f1x + g.y*f1y + g.z*f0z;
-	g = lut_load4(Lb, lut_offset1(ixy00 + Pi1z)); float const n001 = g.x*f0x + g.y*f0y + g.z*f1z;
-	g = lut_load4(Lb, lut_offset1(ixy10 + Pi1z)); float const n101 = g.x*f1x + g.y*f0y + g.z*f1z;
-	g = lut_load4(Lb, lut_offset1(ixy01 + Pi1z)); float const n011 = g.x*f0x + g.y*f1y + g.z*f1z;
-	g = lut_load4(Lb, lut_offset1(ixy11 + Pi1z)); float const n111 = g.x*f1x + g.y*f1y + g.z*f1z;
+	g = lut_load4(Lb, lut_offset1(ixy00 + Pi0z, Lb)); float const n000 = g.x*f0x + g.y*f0y + g.z*f0z;
+	g = lut_load4(Lb, lut_offset1(ixy10 + Pi0z, Lb)); float const n100 = g.x*f1x + g.y*f0y + g.z*f0z;
+	g = lut_load4(Lb, lut_offset1(ixy01 + Pi0z, Lb)); float const n010 = g.x*f0x + g.y*f1y + g.z*f0z;
+	g = lut_load4(Lb, lut_offset1(ixy11 + Pi0z, Lb)); float const n110 = g.x*f1x + g.y*f1y + g.z*f0z;
+	g = lut_load4(Lb, lut_offset1(ixy00 + Pi1z, Lb)); float const n001 = g.x*f0x + g.y*f0y + g.z*f1z;
+	g = lut_load4(Lb, lut_offset1(ixy10 + Pi1z, Lb)); float const n101 = g.x*f1x + g.y*f0y + g.z*f1z;
+	g = lut_load4(Lb, lut_offset1(ixy01 + Pi1z, Lb)); float const n011 = g.x*f0x + g.y*f1y + g.z*f1z;
+	g = lut_load4(Lb, lut_offset1(ixy11 + Pi1z, Lb)); float const n111 = g.x*f1x + g.y*f1y + g.z*f1z;
 	float const fx = twn::fade(f0x), fy = twn::fade(f0y), fz = twn::fade(f0z);
 	float const nz0 = twn::mix(n000, n001, fz), nz1 = twn::mix(n100, n101, fz), nz2 = twn::mix(n010, n011, fz), nz3 = twn::mix(n110, n111, fz);
 	float const nyz0 = twn::mix(nz0, nz2, fy), nyz1 = twn::mix(nz1, nz3, fy);

@@ -63,7 +63,6 @@ __global__ void shadow_rays_kernel(const float *__restrict__ zvals, unsigned cha
 	if (ray >= 4*n) return;
 	int const tile = wave_tiles[blockIdx.y];
 	const float *mh = zvals + (size_t)tile*n*n;
-	unsigned char *sm = smask + (size_t)tile*n*n;
 	const float *sh_in_x = (nb_y[tile] >= 0) ? ox + (size_t)nb_y[tile]*n : nullptr; // the y neighbour's sh_out[0] (src/tiled_mesh.cpp:680-686 with d = 1)
 	const float *sh_in_y = (nb_x[tile] >= 0) ? oy + (size_t)nb_x[tile]*n : nullptr; // the x neighbour's sh_out[1] (d = 0)
 	unsigned long long *out_x = kx + (size_t)tile*n, *out_y = ky + (size_t)tile*n;
@@ -94,8 +93,8 @@ __global__ void shadow_rays_kernel(const float *__restrict__ zvals, unsigned cha
 			else if (sh_in_x != nullptr && y == ya && sh_in_x[x] > TW_MESH_MIN_Z) {cur.x = pt.x; cur.y = pt.y; cur.z = sh_in_x[x]; inited = true;}
 			float const shadow_z = (float)((double)((S.dim ? pt.y : pt.x) - (S.dim ? cur.y : cur.x))*S.dir_ratio + (double)cur.z);
 			if (inited && shadow_z > pt.z) { // shadowed
-				size_t const c = (size_t)y*n + x;
-				atomicOr((unsigned *)(sm + (c & ~(size_t)3)) , (unsigned)TW_MESH_SHADOW << ((unsigned)(c & 3)*8u));
+				size_t const c = (size_t)tile*n*n + (size_t)y*n + x; // byte index in the whole (4-byte aligned) mask: a tile of odd size starts mid-word
+				atomicOr((unsigned *)(smask + (c & ~(size_t)3)), (unsigned)TW_MESH_SHADOW << ((unsigned)(c & 3)*8u));
 				if (x == xb) {atomicMax(out_y + y, seq | __float_as_uint(shadow_z));}
 				if (y == yb) {atomicMax(out_x + x, seq | __float_as_uint(shadow_z));}
 			}

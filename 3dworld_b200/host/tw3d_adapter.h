@@ -295,6 +295,24 @@ inline void tile_ao_lighting(const float *zvals, const int32_t *origins_xy, unsi
 	if (rc != TW_OK) {detail::fail(rc, "tile_ao_lighting", c);}
 }
 
+// calc_mesh_shadows(l, lpos, mh, smask, xsize, ysize, sh_in_x, sh_in_y, sh_out_x, sh_out_y) (src/visibility.cpp:508-517) for ALL tiles a light change dirties, in
+// one call: tile_t::calc_shadows_for_light's chain (src/tiled_mesh.cpp:664-692: each tile starts from the sh_out of its neighbours toward the light) becomes dependency
+// waves on the device. tile_xy = (x1/size, y1/size) per tile; smask = ntiles*zvsize^2 bytes (0 / MESH_SHADOW); sh_out_* optional (ntiles*zvsize floats each).
+// no_shadow = (l == LIGHT_MOON && combined_gu). Globals read: X/Y_SCENE_SIZE, DX/DY_VAL(+_INV), XY_SUM_SIZE = MESH_X_SIZE + MESH_Y_SIZE, zmin, zmax.
+inline void calc_mesh_shadows(const float lpos[3], const float *zvals, const int32_t *tile_xy, unsigned ntiles, unsigned zvsize, float dx_val, float dy_val,
+                              unsigned char *smask, float *sh_out_x = nullptr, float *sh_out_y = nullptr, bool no_shadow = false) {
+	scene_globals const &g = globals();
+	tw_shadow_params sp;
+	for (int d = 0; d < 3; ++d) {sp.lpos[d] = lpos[d];}
+	sp.x_scene_size = g.X_SCENE_SIZE; sp.y_scene_size = g.Y_SCENE_SIZE;
+	sp.dx_val = dx_val; sp.dy_val = dy_val; sp.dx_val_inv = 1.0f/dx_val; sp.dy_val_inv = 1.0f/dy_val; // set_scene_constants: DX_VAL_INV = 1.0/DX_VAL
+	sp.xy_sum_size = g.MESH_X_SIZE + g.MESH_Y_SIZE;
+	sp.zmin = g.zmin; sp.zmax = g.zmax; sp.no_shadow = no_shadow ? 1 : 0;
+	tw_ctx *c = ctx();
+	int const rc = tw_tile_shadows_batch(c, zvals, tile_xy, ntiles, zvsize, &sp, smask, sh_out_x, sh_out_y);
+	if (rc != TW_OK) {detail::fail(rc, "calc_mesh_shadows", c);}
+}
+
 // ------------------------------------------------------------------------------------------------ gen_mesh (ground mode)
 // gen_mesh(surface_type=0, keep_sin_table=0, update_zvals=1) for WMODE_GROUND (src/mesh_gen.cpp:257-355): regenerates the sine table from
 // the function-static generator state (pass the same tw_rng across calls), fills mesh_height, estimates zmax_est from a 128x128 probe of the

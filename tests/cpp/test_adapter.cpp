@@ -18,6 +18,29 @@ int main(int argc, char **argv) {
 		catch (tw3d::error const &e) {printf("no device: status %d\n", e.status); return (e.status == TW_ERR_NO_DEVICE) ? 0 : 2;}
 		return 0;
 	}
+	if (argc >= 4 && std::string(argv[1]) == "shadows") { // test_adapter shadows <in.bin> <out.bin>: tests/golden/shadows.npz through tw3d::calc_mesh_shadows
+		// in: int32 ntiles, zvsize, nlights; float32 params[7] (X/Y_SCENE_SIZE, DX/DY_VAL, XY_SUM_SIZE, zmin, zmax); int32 tile_xy[2*ntiles]; float32 lights[3*nlights]; float32 tiles
+		FILE *in = fopen(argv[2], "rb"), *out = fopen(argv[3], "wb");
+		if (!in || !out) return 1;
+		int32_t hdr[3]; float prm[7];
+		if (fread(hdr, 4, 3, in) != 3 || fread(prm, 4, 7, in) != 7) return 1;
+		size_t const nt = hdr[0], zv = hdr[1], nl = hdr[2];
+		std::vector<int32_t> txy(2*nt); std::vector<float> lights(3*nl), tiles(nt*zv*zv), ox(nt*zv), oy(nt*zv);
+		std::vector<unsigned char> smask(nt*zv*zv);
+		if (fread(txy.data(), 4, txy.size(), in) != txy.size() || fread(lights.data(), 4, lights.size(), in) != lights.size() || fread(tiles.data(), 4, tiles.size(), in) != tiles.size()) return 1;
+		try {
+			tw3d::scene_globals g;
+			g.X_SCENE_SIZE = prm[0]; g.Y_SCENE_SIZE = prm[1]; g.MESH_X_SIZE = g.MESH_Y_SIZE = (int)prm[4]/2; g.zmin = prm[5]; g.zmax = prm[6];
+			tw3d::set_globals(g);
+			for (size_t l = 0; l < nl; ++l) {
+				tw3d::calc_mesh_shadows(&lights[3*l], tiles.data(), txy.data(), (unsigned)nt, (unsigned)zv, prm[2], prm[3], smask.data(), ox.data(), oy.data());
+				fwrite(smask.data(), 1, smask.size(), out); fwrite(ox.data(), 4, ox.size(), out); fwrite(oy.data(), 4, oy.size(), out);
+			}
+		}
+		catch (tw3d::error const &e) {fprintf(stderr, "error %d: %s\n", e.status, e.what()); return 3;}
+		fclose(in); fclose(out);
+		return 0;
+	}
 	if (argc < 3) {fprintf(stderr, "usage: test_adapter <mode> <out.bin>\n"); return 1;}
 	int const mode = atoi(argv[1]);
 	FILE *f = fopen(argv[2], "wb");

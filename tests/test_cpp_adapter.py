@@ -99,6 +99,28 @@ def exe_multi(tw):
     return out
 
 
+@pytest.mark.gpu
+def test_adapter_mesh_shadows_golden(exe, tmp_path, beq):
+    """tw3d::calc_mesh_shadows (the reference's calc_mesh_shadows signature, batched over tiles) on the committed reference fixture."""
+    g = np.load(os.path.join(ROOT, "tests", "golden", "shadows.npz"))
+    tiles, txy, lights, prm = g["tiles"], g["tile_xy"], g["lights"], g["params"].astype(np.float32)
+    nt, zv = tiles.shape[0], tiles.shape[1]
+    src, dst = str(tmp_path / "in.bin"), str(tmp_path / "out.bin")
+    with open(src, "wb") as f:
+        f.write(np.array([nt, zv, len(lights)], np.int32).tobytes() + prm.tobytes() + txy.astype(np.int32).tobytes() + lights.astype(np.float32).tobytes() + tiles.tobytes())
+    r = subprocess.run([exe, "shadows", src, dst], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    raw = open(dst, "rb").read()
+    per = nt * zv * zv + 2 * 4 * nt * zv
+    assert len(raw) == per * len(lights)
+    for li in range(len(lights)):
+        blk = raw[li * per:(li + 1) * per]
+        m = np.frombuffer(blk[:nt * zv * zv], np.uint8).reshape(nt, zv, zv)
+        o = np.frombuffer(blk[nt * zv * zv:], np.float32).reshape(2, nt, zv)
+        assert np.array_equal(m, g["smask_%d" % li]), li
+        assert beq(o[0], g["sh_out_x_%d" % li]) == 0 and beq(o[1], g["sh_out_y_%d" % li]) == 0, li
+
+
 def test_multi_gpu_adapter_builds(exe_multi):
     assert os.path.exists(exe_multi)
 

@@ -122,7 +122,30 @@ def test_erode_sweeps_single_device_equals_oracle(tw, scene, oracle, ctx, beq, n
     assert np.isfinite(zc).all()     # NaN deltas are dropped by the fixed-point accumulation (the reference's serial order can poison cells)
 
 
-@pytest.mark.parametrize("ndev", [2, 4])
+@pytest.mark.parametrize("nbands", [2, 3, 4, 5, 8])
+def test_erode_sweeps_banded_equals_single_band(tw, scene, ctx, beq, nbands):
+    """The band decomposition of tw_erode_sweeps_sharded (halo copies, per-sweep exchange of the border deltas, middle bands with two neighbours) with all
+    bands on ONE device, so that every band count is covered by the single-GPU suite: same bits as the undivided run."""
+    import torch
+    cfg = scene.SceneConfig(mesh_gen_mode=1, mesh_freq_filter=1, mesh_seed=1, hmap=HM_CFG, zmax_est=2.0)
+    ep = cfg.erosion_params()
+    for (nx, ny, iters, sweep, halo) in ((300, 100 * nbands, 20000, 1024, 44), (333, 140 * nbands + 3, 20000, 4096, 64)):
+        z = ctx.heightgen_2d(cfg.heightmap_grid(nx, ny), cfg.height_params())
+        zmin = float(z.min())
+        one = z.copy()
+        moves1 = ctx.erode_sweeps(one, zmin, iters, ep, sweep, halo)
+        ranges = [tw.multi_range(ny, nbands, i) for i in range(nbands)]
+        bands = [z[a:b].copy() for a, b in ranges]
+        assert ctx.erode_sweeps_banded(bands, nx, ny, zmin, iters, ep, sweep, halo) == moves1
+        assert beq(np.concatenate(bands), one) == 0
+        dbands = [torch.from_numpy(z[a:b].copy()).cuda() for a, b in ranges]
+        ctx.erode_sweeps_banded(dbands, nx, ny, zmin, iters, ep, sweep, halo)
+        assert beq(np.concatenate([d.cpu().numpy() for d in dbands]), one) == 0
+        for a, _ in ranges[1:]:
+            assert (one[a - 8:a + 8] != z[a - 8:a + 8]).any()       # erosion happened across every border
+
+
+@pytest.mark.parametrize("ndev", [2, 4, 8])
 def test_erode_sweeps_sharded_equals_single_device(tw, scene, oracle, ctx, beq, ndev):
     """Row bands over ndev GPUs with one grouped ncclSend/ncclRecv of the border deltas per sweep == the one-GPU run, bit for bit; droplets that
     cross band borders and reach the halo rule are included (halo 44 = the minimum, view 32 + 12)."""
@@ -133,7 +156,7 @@ def test_erode_sweeps_sharded_equals_single_device(tw, scene, oracle, ctx, beq, 
     ep = cfg.erosion_params()
     m = tw.Multi(list(range(ndev)))
     try:
-        for (nx, ny, iters, sweep, halo) in ((700, 640, 30000, 2048, 44), (1024, 1536, 60000, 8192, 64)):
+        for (nx, ny, iters, sweep, halo) in ((700, max(640, 100 * ndev), 30000, 2048, 44), (1024, max(1536, 140 * ndev), 60000, 8192, 64)):     # bands >= 2*halo + 8 rows
             z = ctx.heightgen_2d(cfg.heightmap_grid(nx, ny), cfg.height_params())
             zmin = float(z.min())
             one = z.copy()

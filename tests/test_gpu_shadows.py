@@ -47,3 +47,18 @@ def test_tile_shadows_vs_oracle(tw, scene, oracle, ctx, beq, S, side):
     assert np.array_equal(dm.cpu().numpy(), mo)
     sp.no_shadow = 1
     assert not ctx.tile_shadows(tiles, txy, sp)[0].any()
+
+
+def test_tile_shadows_golden(tw, ctx, beq):
+    """tests/golden/shadows.npz: the reference's own calc_mesh_shadows over a chained 3x3 block of tiles (made by tests/golden/make_golden_shadows.py)."""
+    import os
+    from test_oracle_golden import shadow_params
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "shadows.npz"))
+    txy = [tuple(int(v) for v in t) for t in g["tile_xy"]]
+    shadowed = 0
+    for li, lp in enumerate(g["lights"]):
+        m, ox, oy = ctx.tile_shadows(g["tiles"], txy, shadow_params(tw.ShadowParams, g["params"], lp))
+        assert np.array_equal(m, g["smask_%d" % li]), li
+        assert beq(ox, g["sh_out_x_%d" % li]) == 0 and beq(oy, g["sh_out_y_%d" % li]) == 0, li
+        shadowed += int((m == 2).sum())
+    assert shadowed > 1000

@@ -234,3 +234,24 @@ def test_voxel_post_processing(oracle, beq):
         v2, o2, _ = oracle.voxel_remove_unconnected(g[name + "_vals"], out, p)
         assert np.array_equal(o2, g[name + "_outside2"]) and beq(v2, g[name + "_vals2"]) == 0
         assert beq(oracle.voxel_triangles(v2, o2, p, tables), g[name + "_tris"]) == 0
+
+
+def shadow_params(P, a, lp):
+    """tests/golden/shadows.npz 'params' = X/Y_SCENE_SIZE, DX/DY_VAL, XY_SUM_SIZE, zmin, zmax."""
+    sp = P()
+    sp.x_scene_size, sp.y_scene_size, sp.dx_val, sp.dy_val = float(a[0]), float(a[1]), float(a[2]), float(a[3])
+    sp.dx_val_inv, sp.dy_val_inv = 1.0 / np.float32(a[2]), 1.0 / np.float32(a[3])
+    sp.xy_sum_size, sp.zmin, sp.zmax, sp.no_shadow = int(a[4]), float(a[5]), float(a[6]), 0
+    for d in range(3):
+        sp.lpos[d] = float(lp[d])
+    return sp
+
+
+def test_mesh_shadows(oracle, beq):
+    """tests/golden/shadows.npz = the reference's own calc_mesh_shadows over a 3x3 block of tiles chained as tile_t::calc_shadows_for_light chains them (N4)."""
+    g = load("shadows.npz")
+    txy = [tuple(int(v) for v in t) for t in g["tile_xy"]]
+    for li, lp in enumerate(g["lights"]):
+        m, ox, oy = oracle.tile_shadows_batch(g["tiles"], txy, shadow_params(oracle.ShadowParams, g["params"], lp))
+        assert np.array_equal(m, g["smask_%d" % li]), li
+        assert beq(ox, g["sh_out_x_%d" % li]) == 0 and beq(oy, g["sh_out_y_%d" % li]) == 0, li
