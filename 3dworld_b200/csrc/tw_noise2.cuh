@@ -28,12 +28,27 @@ typedef unsigned long long u64;
 // fma(x, ONE, y) and every packed SUBTRACT as fma(y, -ONE, x) with ONE read from constant memory at run time: the products x*1 and y*(-1)
 // are exact, so the result is the IEEE sum, and because the multiplier is opaque there is no mul+add pattern left to contract.
 // The bit-exact parity tests (tests/test_gpu_heightgen.py) are the guard for this.
+// ONE scalar each, broadcast to both halves: ptxas then keeps the multiplier in a UNIFORM register (FFMA2 R, R, UR.F32, R) and the packed add reads two vector
+// register pairs, not three. Measured on B200 (tools/mb/pipes.cu): FFMA2 with three vector-register operands issues every 3 cycles, with two every 2 - the
+// register file feeds one 64-bit operand per lane and cycle, and an add whose "1" sits in a vector register pair paid that third read.
+#ifndef TW_ONE_UNIFORM
+#define TW_ONE_UNIFORM 1
+#endif
+#if TW_ONE_UNIFORM
+__constant__ float TW_ONE_S    =  1.0f;
+__constant__ float TW_NEGONE_S = -1.0f;
+#define TW_ONE2    make_float2(TW_ONE_S, TW_ONE_S)
+#define TW_NEGONE2 make_float2(TW_NEGONE_S, TW_NEGONE_S)
+#else
 __constant__ float2 TW_ONE2    = { 1.0f,  1.0f};
 __constant__ float2 TW_NEGONE2 = {-1.0f, -1.0f};
+#endif
 
 __device__ __forceinline__ u64 pk(f2 a) {u64 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a.x), "f"(a.y)); return r;}
 __device__ __forceinline__ f2 unpk(u64 r) {f2 a; asm("mov.b64 {%0, %1}, %2;" : "=f"(a.x), "=f"(a.y) : "l"(r)); return a;}
 __device__ __forceinline__ f2 splat(float v) {return make_float2(v, v);}
+__device__ __forceinline__ f2 tof2(f2 v) {return v;}
+__device__ __forceinline__ f2 tof2(float v) {return make_float2(v, v);}
 __device__ __forceinline__ f2 raw_fma(f2 a, f2 b, f2 c) {u64 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(pk(a)), "l"(pk(b)), "l"(pk(c))); return unpk(d);}
 __device__ __forceinline__ f2 mul2(f2 a, f2 b) {u64 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(pk(a)), "l"(pk(b))); return unpk(d);}
 __device__ __forceinline__ f2 mul2(f2 a, float b) {return mul2(a, splat(b));}
@@ -41,6 +56,14 @@ __device__ __forceinline__ f2 add2(f2 a, f2 b) {return raw_fma(a, TW_ONE2, b);} 
 __device__ __forceinline__ f2 add2(f2 a, float b) {return raw_fma(a, TW_ONE2, splat(b));}
 __device__ __forceinline__ f2 sub2(f2 a, f2 b) {return raw_fma(b, TW_NEGONE2, a);}              // a - b
 __device__ __forceinline__ f2 rsub2(float a, f2 b) {return raw_fma(b, TW_NEGONE2, splat(a));}   // a - b, scalar a
+// PLAIN packed add / subtract (FADD2, two vector operands): ONLY where neither operand is the direct result of a packed multiply - there is then no mul+add
+// pattern for ptxas to contract, and the instruction reads two register pairs instead of the three of fma(x, ONE, y). Measured on B200 (tools/mb/pipes.cu):
+// a packed instruction with three vector-register operands issues every 3 cycles, with two every 2 (the register file feeds one 64-bit operand per lane and
+// cycle), so every add that can be plain saves a third of its issue time. The bit-exact parity tests guard the "no product operand" rule.
+__device__ __forceinline__ f2 padd2(f2 a, f2 b) {u64 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(pk(a)), "l"(pk(b))); return unpk(d);}
+__device__ __forceinline__ f2 padd2(f2 a, float b) {return padd2(a, splat(b));}
+__device__ __forceinline__ f2 psub2(f2 a, f2 b) {u64 d; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(pk(a)), "l"(pk(b))); return unpk(d);}
+__device__ __forceinline__ f2 prsub2(float a, f2 b) {return psub2(splat(a), b);}
 // genuine fused multiply-adds: only where the product is exact, so fused == unfused (see tw_noise.cuh); `a` is never itself a product
 __device__ __forceinline__ f2 fma2(f2 a, float b, f2 c) {return raw_fma(a, splat(b), c);}
 __device__ __forceinline__ f2 fma2(f2 a, float b, float c) {return raw_fma(a, splat(b), splat(c));}
@@ -76,7 +99,7 @@ __device__ __forceinline__ f2 mod_int289(f2 a) {
 __device__ __forceinline__ f2 mod_int289_lazy(f2 a) {return fma2(floor2(mul2(a, 1.0f/289.0f)), -289.0f, a);}
 __device__ __forceinline__ f2 fract2(f2 x) {return sub2(x, floor2(x));}
 __device__ __forceinline__ f2 tinvsqrt(f2 r) {return rsub2(1.79284291400159f, mul2(r, 0.85373472095314f));}
-__device__ __forceinline__ f2 mix2(f2 x, f2 y, f2 a) {return add2(x, mul2(a, sub2(y, x)));}
+__device__ __forceinline__ f2 mix2(f2 x, f2 y, f2 a) {return add2(x, mul2(a, psub2(y, x)));} // x, y are sums at every call site: plain subtract
 __device__ __forceinline__ f2 fade2(f2 t) { // (t*t*t)*(t*(t*6 - 15) + 10)
 	f2 const t3 = mul2(mul2(t, t), t);
 	return mul2(t3, add2(mul2(t, add2(mul2(t, 6.0f), -15.0f)), 10.0f));
@@ -184,12 +207,12 @@ __device__ __forceinline__ float lut_load_w(unsigned Lb, float off) {return lut_
 __device__ __forceinline__ f2 simplex2_lut(f2 vx, f2 vy, unsigned Lb) {
 	float const Cx = 0.211324865405187f, Cy = 0.366025403784439f, Cz = -0.577350269189626f;
 	f2 const s = add2(mul2(vx, Cy), mul2(vy, Cy));
-	f2 ix = floor2(add2(vx, s)), iy = floor2(add2(vy, s));
+	f2 ix = floor2(padd2(vx, s)), iy = floor2(padd2(vy, s)); // vx, vy, s are sums, not products: plain adds (see padd2)
 	f2 const t = add2(mul2(ix, Cx), mul2(iy, Cx));
-	f2 const x0x = add2(sub2(vx, ix), t), x0y = add2(sub2(vy, iy), t);
+	f2 const x0x = padd2(psub2(vx, ix), t), x0y = padd2(psub2(vy, iy), t);
 	f2 const i1x = make_float2((x0x.x > x0y.x) ? 1.0f : 0.0f, (x0x.y > x0y.y) ? 1.0f : 0.0f);
-	f2 const i1y = rsub2(1.0f, i1x); // (1,0) or (0,1)
-	f2 const x12x = sub2(add2(x0x, Cx), i1x), x12y = sub2(add2(x0y, Cx), i1y), x12z = add2(x0x, Cz), x12w = add2(x0y, Cz);
+	f2 const i1y = prsub2(1.0f, i1x); // (1,0) or (0,1)
+	f2 const x12x = psub2(padd2(x0x, Cx), i1x), x12y = psub2(padd2(x0y, Cx), i1y), x12z = padd2(x0x, Cz), x12w = padd2(x0y, Cz);
 #if TW_SIMPLEX_LUT >= 2
 	ix = mod_int289_lazy(ix); iy = mod_int289_lazy(iy);
 	// permute(iy), permute(iy + i1.y), permute(iy + 1): consecutive table entries, so the second and third addresses are the first plus 0/128/256 bytes
@@ -209,13 +232,13 @@ __device__ __forceinline__ f2 simplex2_lut(f2 vx, f2 vy, unsigned Lb) {
 	f2 const q0 = permute(iy), q1 = permute(add2(iy, i1y)), q2 = permute(add2(iy, 1.0f));
 #endif
 #if TW_SIMPLEX_LUT >= 3
-	f2 const p0 = add2(q0, ix), p1 = add2(add2(q1, ix), i1x), p2 = add2(add2(q2, ix), 1.0f); // the table is indexed by the argument of the second permute
+	f2 const p0 = padd2(q0, ix), p1 = padd2(padd2(q1, ix), i1x), p2 = padd2(padd2(q2, ix), 1.0f); // the table is indexed by the argument of the second permute (q: table values, ix: an fma result)
 #else
 	f2 const p0 = permute(add2(q0, ix)), p1 = permute(add2(add2(q1, ix), i1x)), p2 = permute(add2(add2(q2, ix), 1.0f));
 #endif
-	f2 m0 = max0_2(rsub2(0.5f, add2(mul2(x0x, x0x), mul2(x0y, x0y))));
-	f2 m1 = max0_2(rsub2(0.5f, add2(mul2(x12x, x12x), mul2(x12y, x12y))));
-	f2 m2 = max0_2(rsub2(0.5f, add2(mul2(x12z, x12z), mul2(x12w, x12w))));
+	f2 m0 = max0_2(prsub2(0.5f, add2(mul2(x0x, x0x), mul2(x0y, x0y))));     // inner sums: products -> the opaque form; 0.5 - sum: plain
+	f2 m1 = max0_2(prsub2(0.5f, add2(mul2(x12x, x12x), mul2(x12y, x12y))));
+	f2 m2 = max0_2(prsub2(0.5f, add2(mul2(x12z, x12z), mul2(x12w, x12w))));
 	m0 = mul2(m0, m0); m1 = mul2(m1, m1); m2 = mul2(m2, m2);
 	m0 = mul2(m0, m0); m1 = mul2(m1, m1); m2 = mul2(m2, m2);
 	f2 const k0 = lut_offsets(p0, Lb), k1 = lut_offsets(p1, Lb), k2 = lut_offsets(p2, Lb);
@@ -275,13 +298,13 @@ __device__ __forceinline__ float4 perlin_lut_entry(float k) {
 // glm::perlin(vec2) for two positions with the table
 __device__ __forceinline__ f2 perlin2_lut(f2 Px, f2 Py, unsigned Lb) {
 	f2 const flx = floor2(Px), fly = floor2(Py);
-	f2 const frx = sub2(Px, flx), fry = sub2(Py, fly);
-	f2 const Pfz = add2(frx, -1.0f), Pfw = add2(fry, -1.0f);
-	f2 const Pix = mod_int289_lazy(flx), Piy = mod_int289_lazy(fly), Piz = mod_int289_lazy(add2(flx, 1.0f)), Piw = mod_int289_lazy(add2(fly, 1.0f));
+	f2 const frx = psub2(Px, flx), fry = psub2(Py, fly); // sums and floors, no products: plain (see padd2)
+	f2 const Pfz = padd2(frx, -1.0f), Pfw = padd2(fry, -1.0f);
+	f2 const Pix = mod_int289_lazy(flx), Piy = mod_int289_lazy(fly), Piz = mod_int289_lazy(padd2(flx, 1.0f)), Piw = mod_int289_lazy(padd2(fly, 1.0f));
 	f2 const jx = lut_offsets(Pix, Lb), jz = lut_offsets(Piz, Lb);
 	f2 const qx = make_float2(lut_load_w(Lb, jx.x), lut_load_w(Lb, jx.y)), qz = make_float2(lut_load_w(Lb, jz.x), lut_load_w(Lb, jz.y)); // permute(ix)
 #if TW_SIMPLEX_LUT >= 3
-	f2 const k00 = lut_offsets(add2(qx, Piy), Lb), k10 = lut_offsets(add2(qz, Piy), Lb), k01 = lut_offsets(add2(qx, Piw), Lb), k11 = lut_offsets(add2(qz, Piw), Lb);
+	f2 const k00 = lut_offsets(padd2(qx, Piy), Lb), k10 = lut_offsets(padd2(qz, Piy), Lb), k01 = lut_offsets(padd2(qx, Piw), Lb), k11 = lut_offsets(padd2(qz, Piw), Lb);
 #else
 	f2 const k00 = lut_offsets(permute(add2(qx, Piy)), Lb), k10 = lut_offsets(permute(add2(qz, Piy)), Lb);
 	f2 const k01 = lut_offsets(permute(add2(qx, Piw)), Lb), k11 = lut_offsets(permute(add2(qz, Piw)), Lb);

@@ -22,15 +22,15 @@ for a, t in ins:
     m = re.search(r"BRA.*?(0x[0-9a-f]+)", t)
     if m and int(m.group(1), 16) < a:
         body = [(x, u) for x, u in ins if int(m.group(1), 16) <= x <= a]
-        if 100 < len(body) < 400 and sum(1 for _, u in body if "FFMA2" in u or "FMUL2" in u) > 40:
+        if 100 < len(body) < 400 and sum(1 for _, u in body if "FFMA2" in u or "FMUL2" in u or "FADD2" in u) > 40:
             loops.append(body)
 body = loops[0]
 hist = collections.Counter(re.sub(r"^@!?U?P\d\s+", "", t).split()[0].split(".")[0] for _, t in body)
 out = ["SASS excerpt (cuobjdump -sass 3dworld_b200/lib3dworld_b200.so, sm_100a) of noise_grid2_kernel<simplex, warp, shape 0>: ONE octave loop of gen_noise2",
        "(= one fBm octave for a pair of cells; the kernel contains %d such loops, one per gen_noise2 call of the domain warp). Loop 0x%04x .. 0x%04x, %d instructions:" % (len(loops), body[0][0], body[-1][0], len(body)),
        "  " + ", ".join("%s %d" % kv for kv in hist.most_common()),
-       "FMA-pipe issue cycles per loop iteration and warp: 2 x (FFMA2 + FMUL2) + FMUL + FADD + FFMA = %d; packed instructions are the reference's unfused multiplies / adds for two cells"
-       % (2 * (hist["FFMA2"] + hist["FMUL2"]) + hist["FMUL"] + hist["FADD"] + hist["FFMA"]),
-       "(every packed add is fma(x, ONE, y) with ONE from constant memory, see csrc/tw_noise2.cuh); LDS = hash / gradient table look-ups; FRND = floor().", ""]
+       "FMA-pipe issue cycles per loop iteration and warp: 2 x (FFMA2 + FMUL2 + FADD2) + FMUL + FADD + FFMA = %d; packed instructions are the reference's unfused multiplies / adds for two cells"
+       % (2 * (hist["FFMA2"] + hist["FMUL2"] + hist["FADD2"]) + hist["FMUL"] + hist["FADD"] + hist["FFMA"]),
+       "(a packed add of two products is fma(x, ONE, y) with an opaque ONE, every other packed add a plain FADD2, see csrc/tw_noise2.cuh); LDS = hash / gradient table look-ups; FRND = floor().", ""]
 out += ["        /*%04x*/  %s ;" % (x, t) for x, t in body]
 open(sys.argv[1] if len(sys.argv) > 1 else "/dev/stdout", "w").write("\n".join(out) + "\n")
