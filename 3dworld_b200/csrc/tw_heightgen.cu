@@ -209,6 +209,9 @@ __device__ __forceinline__ float2 gen_noise2(float2 xv, float2 yv, const NoisePa
 	return zval;
 }
 
+#ifndef TW_NOISE2_WARP_CHUNKS
+#define TW_NOISE2_WARP_CHUNKS 4 // 512-cell chunks a block of the domain-warp kernel walks per 74 KB table fill. Measured on B200, 8192^2 headline: 1 -> 7.25 ms, 2 -> 7.04, 4 -> 6.94, 6 -> 6.93, 8 -> 6.92, 16 -> 6.97
+#endif
 #ifndef TW_NOISE2_DUAL
 #define TW_NOISE2_DUAL 0   // 1: the two independent fBm evaluations of each domain-warp stage (dx1|dy1, dx2|dy2) share one octave loop (2x the ILP per thread)
 #endif
@@ -257,7 +260,7 @@ noise_grid2_kernel(float *__restrict__ out, unsigned nx, unsigned ny, unsigned y
 	if (tile_origins) {float2 const o = __ldg(tile_origins + tile); mx0 = o.x; my0 = o.y;}
 	size_t const c_end = (size_t)y_end*nx;
 	float lo = INFINITY, hi = -INFINITY;
-	constexpr unsigned NCH = WARP ? 1 : 4;
+	constexpr unsigned NCH = WARP ? TW_NOISE2_WARP_CHUNKS : 4;
 	// blocks stride over the chunk groups of the band: with gridDim.x == number of groups every block does exactly one (the default); a smaller
 	// grid (TW_NOISE2_PERSISTENT: one wave of resident blocks) keeps the staged table for many chunks
 	// P.ngroups = chunk groups of this band (host-computed: a 64-bit division per thread here cost 2.5 % of the whole kernel)
@@ -647,7 +650,7 @@ int twi_heightgen(tw_ctx *ctx, const tw_grid2d *g, const tw_height_params *p, in
 			static bool const use_scalar = (getenv("TW_NOISE_SCALAR") != nullptr); // A/B switch: one cell per thread, scalar FMUL/FADD
 			if (!use_scalar) { // two cells per thread on packed fp32x2 instructions
 				size_t const band_cells = (size_t)(r1 - r0)*nx;
-				size_t const cells_per_block = 2*TW_NOISE2_THREADS*(size_t)((p->gen_mode == TW_MGEN_DWARP_GPU) ? 1 : 4); // noise_grid2_kernel: NCH chunks of blockDim threads x 2 cells
+				size_t const cells_per_block = 2*TW_NOISE2_THREADS*(size_t)((p->gen_mode == TW_MGEN_DWARP_GPU) ? TW_NOISE2_WARP_CHUNKS : 4); // noise_grid2_kernel: NCH chunks of blockDim threads x 2 cells
 				unsigned gx = (unsigned)((band_cells + cells_per_block - 1)/cells_per_block);
 				P.ngroups = gx;
 #if TW_NOISE2_PERSISTENT

@@ -64,6 +64,18 @@ __device__ __forceinline__ f2 padd2(f2 a, f2 b) {u64 d; asm("add.rn.f32x2 %0, %1
 __device__ __forceinline__ f2 padd2(f2 a, float b) {return padd2(a, splat(b));}
 __device__ __forceinline__ f2 psub2(f2 a, f2 b) {u64 d; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(pk(a)), "l"(pk(b))); return unpk(d);}
 __device__ __forceinline__ f2 prsub2(float a, f2 b) {return psub2(splat(a), b);}
+// A product that is going to be ADDED to another product or sum: a*b as fma(a, b, -0) with an OPAQUE -0 (read from constant memory: ptxas keeps it in a
+// uniform register, the addend slot takes one). a*b + (-0) is the IEEE product itself (sign of zero included), the consumer can then be a plain FADD2 - no
+// mul+add pair for ptxas to contract - and every instruction of the sum reads two vector register pairs: fma, fma, add = 6 issue cycles where
+// mul, mul, fma(x, ONE, y) took 7 (the last one reads three pairs).
+#ifndef TW_OPAQUE_ZERO
+#define TW_OPAQUE_ZERO 0   // measured equal on B200 (7.25 ms either way: the 32-bit -0 operand costs the register-file cycle the third pair did), kept as an A/B switch
+#endif
+__constant__ float TW_NEGZERO_S = -0.0f;
+__device__ __forceinline__ f2 mulz2(f2 a, f2 b) {return raw_fma(a, b, make_float2(TW_NEGZERO_S, TW_NEGZERO_S));}
+// a*b + c*d and a*b + c (c not a product), unfused
+__device__ __forceinline__ f2 sumprod2(f2 a, f2 b, f2 c, f2 d) {return TW_OPAQUE_ZERO ? padd2(mulz2(a, b), mulz2(c, d)) : add2(mul2(a, b), mul2(c, d));}
+__device__ __forceinline__ f2 sumprod2(f2 a, float b, f2 c, float d) {return sumprod2(a, splat(b), c, splat(d));}
 // genuine fused multiply-adds: only where the product is exact, so fused == unfused (see tw_noise.cuh); `a` is never itself a product
 __device__ __forceinline__ f2 fma2(f2 a, float b, f2 c) {return raw_fma(a, splat(b), c);}
 __device__ __forceinline__ f2 fma2(f2 a, float b, float c) {return raw_fma(a, splat(b), splat(c));}
@@ -177,6 +189,10 @@ __device__ __forceinline__ float4 simplex_lut_entry(float k) { // scalar restate
 #ifndef TW_LUT_DENORM
 #define TW_LUT_DENORM 1
 #endif
+#ifndef TW_HASH_Q1_ARITH
+#define TW_HASH_Q1_ARITH 0   // 1: the middle corner's hash by exact integer arithmetic instead of a third table load. Measured on B200: 7.02 ms vs 6.94 ms - the
+                             // shared-memory pipe (78 % busy) is not what the kernel waits for; the extra three-operand packed instruction on the hash chain is.
+#endif
 constexpr unsigned SIMPLEX_LUT_MAGIC_BITS = 0x4B400000u; // bits of 12582912.0f = 1.5*2^23
 constexpr unsigned LUT_ENTRY_BYTES = 16u*SIMPLEX_LUT_COPIES;
 __device__ __forceinline__ unsigned simplex_lut_base(const float4 *lut_s, unsigned lane) {
@@ -206,9 +222,9 @@ __device__ __forceinline__ float lut_load_w(unsigned Lb, float off) {return lut_
 // glm::simplex(vec2) for two positions with the table; Lb = simplex_lut_base()
 __device__ __forceinline__ f2 simplex2_lut(f2 vx, f2 vy, unsigned Lb) {
 	float const Cx = 0.211324865405187f, Cy = 0.366025403784439f, Cz = -0.577350269189626f;
-	f2 const s = add2(mul2(vx, Cy), mul2(vy, Cy));
+	f2 const s = sumprod2(vx, Cy, vy, Cy);
 	f2 ix = floor2(padd2(vx, s)), iy = floor2(padd2(vy, s)); // vx, vy, s are sums, not products: plain adds (see padd2)
-	f2 const t = add2(mul2(ix, Cx), mul2(iy, Cx));
+	f2 const t = sumprod2(ix, Cx, iy, Cx);
 	f2 const x0x = padd2(psub2(vx, ix), t), x0y = padd2(psub2(vy, iy), t);
 	f2 const i1x = make_float2((x0x.x > x0y.x) ? 1.0f : 0.0f, (x0x.y > x0y.y) ? 1.0f : 0.0f);
 	f2 const i1y = prsub2(1.0f, i1x); // (1,0) or (0,1)
@@ -220,7 +236,9 @@ __device__ __forceinline__ f2 simplex2_lut(f2 vx, f2 vy, unsigned Lb) {
 	unsigned const ja = lut_addr(Lb, j0.x), jb = lut_addr(Lb, j0.y);
 	static_assert(LUT_ENTRY_BYTES == 128, "lut_load_w_addr_next hard-codes the entry pitch");
 	f2 const q0 = make_float2(lut_load_w_addr(ja), lut_load_w_addr(jb));
-#if TW_LUT_DENORM
+#if TW_HASH_Q1_ARITH && TW_SIMPLEX_LUT >= 3
+	// no load for q1 (see p1 below)
+#elif TW_LUT_DENORM
 	f2 const j1 = raw_fma(i1y, splat(__uint_as_float(LUT_ENTRY_BYTES)), j0); // entry iy + i1.y: one packed FMA instead of two selects and two adds
 	f2 const q1 = make_float2(lut_load_w_addr(__float_as_uint(j1.x)), lut_load_w_addr(__float_as_uint(j1.y)));
 #else
@@ -231,14 +249,20 @@ __device__ __forceinline__ f2 simplex2_lut(f2 vx, f2 vy, unsigned Lb) {
 	ix = mod_int289(ix); iy = mod_int289(iy);
 	f2 const q0 = permute(iy), q1 = permute(add2(iy, i1y)), q2 = permute(add2(iy, 1.0f));
 #endif
-#if TW_SIMPLEX_LUT >= 3
+#if TW_SIMPLEX_LUT >= 3 && TW_HASH_Q1_ARITH
+	// q1 = permute(iy + i1.y) is q0 or q2, so the three table indices are p0 = q0 + ix, p2 = q2 + ix + 1 and p1 = i1.y ? q2 + ix : q0 + ix + 1 (i1.x = 1 - i1.y).
+	// All of these are small non-negative integers, exact in fp32 in any order: with d = q2 - q0 and e = p0 + 1, p2 = e + d and p1 = e + i1.y*(d - 1)
+	// (a product by 0 or 1 plus an integer: fused or not, the same number). Two table loads fewer per pair of cells - the shared-memory pipe is the
+	// second-busiest unit of this kernel - for one more packed instruction.
+	f2 const p0 = padd2(q0, ix), dq = psub2(q2, q0), e1 = padd2(p0, 1.0f), p2 = padd2(e1, dq), p1 = raw_fma(i1y, padd2(dq, -1.0f), e1);
+#elif TW_SIMPLEX_LUT >= 3
 	f2 const p0 = padd2(q0, ix), p1 = padd2(padd2(q1, ix), i1x), p2 = padd2(padd2(q2, ix), 1.0f); // the table is indexed by the argument of the second permute (q: table values, ix: an fma result)
 #else
 	f2 const p0 = permute(add2(q0, ix)), p1 = permute(add2(add2(q1, ix), i1x)), p2 = permute(add2(add2(q2, ix), 1.0f));
 #endif
-	f2 m0 = max0_2(prsub2(0.5f, add2(mul2(x0x, x0x), mul2(x0y, x0y))));     // inner sums: products -> the opaque form; 0.5 - sum: plain
-	f2 m1 = max0_2(prsub2(0.5f, add2(mul2(x12x, x12x), mul2(x12y, x12y))));
-	f2 m2 = max0_2(prsub2(0.5f, add2(mul2(x12z, x12z), mul2(x12w, x12w))));
+	f2 m0 = max0_2(prsub2(0.5f, sumprod2(x0x, x0x, x0y, x0y)));     // inner sums: products -> the opaque form; 0.5 - sum: plain
+	f2 m1 = max0_2(prsub2(0.5f, sumprod2(x12x, x12x, x12y, x12y)));
+	f2 m2 = max0_2(prsub2(0.5f, sumprod2(x12z, x12z, x12w, x12w)));
 	m0 = mul2(m0, m0); m1 = mul2(m1, m1); m2 = mul2(m2, m2);
 	m0 = mul2(m0, m0); m1 = mul2(m1, m1); m2 = mul2(m2, m2);
 	f2 const k0 = lut_offsets(p0, Lb), k1 = lut_offsets(p1, Lb), k2 = lut_offsets(p2, Lb);
@@ -249,7 +273,7 @@ __device__ __forceinline__ f2 simplex2_lut(f2 vx, f2 vy, unsigned Lb) {
 	f2 const gx = make_float2(g0a.x*x0x.x  + g0a.y*x0y.x,  g0b.x*x0x.y  + g0b.y*x0y.y);
 	f2 const gy = make_float2(g1a.x*x12x.x + g1a.y*x12y.x, g1b.x*x12x.y + g1b.y*x12y.y);
 	f2 const gz = make_float2(g2a.x*x12z.x + g2a.y*x12w.x, g2b.x*x12z.y + g2b.y*x12w.y);
-	return mul2(add2(add2(mul2(m0, gx), mul2(m1, gy)), mul2(m2, gz)), 130.0f);
+	return mul2(TW_OPAQUE_ZERO ? padd2(sumprod2(m0, gx, m1, gy), mulz2(m2, gz)) : add2(add2(mul2(m0, gx), mul2(m1, gy)), mul2(m2, gz)), 130.0f);
 }
 
 __device__ __forceinline__ void perlin2_corner(f2 ix, f2 iy, f2 &gx, f2 &gy) {
