@@ -87,6 +87,7 @@ def main():
     ap.add_argument("-o", "--out", default="")
     ap.add_argument("--note", default="")
     ap.add_argument("--opcodes", action="store_true", help="add the executed per-opcode mix from the SASS view (slow for big kernels)")
+    ap.add_argument("--roofline", help="also write the bench.py roofline input (profiles/roofline_rNN.json) from the first matched kernel")
     ap.add_argument("--units", type=float, default=0.0, help="work units of one launch (cells, voxels, droplet moves): adds per-unit figures")
     args = ap.parse_args()
     hdr, units, body = raw_rows(args.rep)
@@ -132,6 +133,17 @@ def main():
             break
     if not res:
         sys.exit("no kernel matched %r" % args.kernel)
+    if args.roofline:   # the per-launch numbers bench.py quotes (roofline.traffic, executed fp32 operations per cell)
+        d = res[0]
+        keys = ("kernel", "report", "gpu__time_duration.sum", "dram_read_bytes", "dram_write_bytes", "dram_bytes_per_launch", "dram_bytes_per_unit", "units_per_launch",
+                "warp_instructions_per_unit", "fp32_mul_add_fma_lane_ops_per_unit", "fp32_lane_ops_per_unit")
+        entry = {k: d[k] for k in keys if k in d}
+        if args.units:
+            entry["algorithmic_bytes_per_launch"] = int(4 * args.units)
+        json.dump({"_comment": "per-launch numbers of the dominant kernel of the headline step, written from the ncu --set full capture by tools/ncu_summary.py --roofline "
+                               "(same capture as the ncu_*.json summary next to it); bench.py quotes dram_bytes_per_launch as roofline.traffic and "
+                               "fp32_mul_add_fma_lane_ops_per_unit as the executed fp32 operations per cell",
+                   "noise_grid2_kernel": entry}, open(args.roofline, "w"), indent=1)
     text = json.dumps(res if args.all else res[0], indent=1)
     if args.out:
         open(args.out, "w").write(text + "\n")
