@@ -317,6 +317,9 @@ droplet_kernel(DArgs const A)
 			else {dx=__fdiv_rn(dx, dl); dz=__fdiv_rn(dz, dl);}
 			float const nxp=xp+dx, nzp=zp+dz;
 			int nxi=__float2int_rd(nxp), nzi=__float2int_rd(nzp); // (int)floor(.)
+			// M_FROZEN: a droplet whose next position is not a finite in-range number ends here (rule of the batched algorithm, same in the oracle): the reference would
+			// read the map at the clamp of INT_MIN, i.e. row 0 - a row a device that holds only its band +- halo does not have
+			if (FROZEN && !(fabsf(nxp) < 2147483648.0f && fabsf(nzp) < 2147483648.0f)) {in_droplet = false; continue;}
 			if (!(fabsf(nxp) < 2147483648.0f && fabsf(nzp) < 2147483648.0f)) { // NaN / out of int range: x86 cvttss2si yields INT_MIN -> "outside" next step
 				nxi=tw_x86_f2i(floorf(nxp)); nzi=tw_x86_f2i(floorf(nzp));
 			}

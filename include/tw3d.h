@@ -387,7 +387,8 @@ TW_API int  tw_heightgen_2d_sharded(tw_multi *m, const tw_grid2d *g, const tw_he
  * src/erosion.cpp:76-152) are accumulated in 64-bit fixed point (2^-40 height units: integer sums do not depend on order) and added to the map
  * after the sweep; a droplet still sees its OWN writes through a private 32x32 view (sweep-start heights + its writes; re-read and re-centred
  * ahead of its heading when it walks out of it - without that feedback a droplet in a pit never fills it); it ends once it is more than
- * halo-36 rows away from its start row (halo >= 44). Row bands as tw_multi_range(ysize, ndev, i); each
+ * halo-36 rows away from its start row (halo >= 44), or when its next position is not a finite number (a NaN of its own making; the reference would go on
+ * to read the map's first row there, which a device holding one band does not have). Row bands as tw_multi_range(ysize, ndev, i); each
  * device keeps its band +- halo rows and after every sweep neighbours exchange the deltas of the 2*halo rows around their border in ONE grouped
  * ncclSend/ncclRecv over NVLink (width*2*halo*8 bytes per neighbour). The result is bit-identical for every device count (tw_erode_sweeps ==
  * tw_erode_sweeps_sharded), which is what the parity tests check, next to the CPU oracle of the same algorithm. bands[i]: the band's rows in

@@ -641,7 +641,7 @@ unsigned long long to_apply_erosion(float *heightmap, int xsize, int ysize, floa
  * is split over devices: droplets [k*sweep, (k+1)*sweep) read the map as it was when sweep k began; their deposits go to a 64-bit fixed-point
  * delta buffer (2^-40 units: integer sums are order-independent) that is added to the map after the sweep; a droplet does see its OWN writes
  * through a private VIEW x VIEW window (sweep-start heights + its writes), re-read and re-centred ahead of its heading when it walks out of it;
- * and it ends once it is more than halo - VIEW - 4 rows from its start row. Mirrors droplet_kernel<M_FROZEN> in csrc/tw_erosion.cu. */
+ * and it ends once it is more than halo - VIEW - 4 rows from its start row or its next position is not finite. Mirrors droplet_kernel<M_FROZEN> in csrc/tw_erosion.cu. */
 #define SWEEP_VIEW 32
 typedef struct {float *mh; long long *dfix; int NX, NY; float win[SWEEP_VIEW*SWEEP_VIEW]; int WX, WY, wx0, wz0, have;} sweep_state;
 static float sw_read(const sweep_state *S, int x, int z) {
@@ -714,6 +714,7 @@ unsigned long long to_erode_sweeps(float *heightmap, int xsize, int ysize, float
 			if (dl<=FLT_EPSILON) {float a=to_rng_rand_float(&rgen)*tp; dx=cosf(a); dz=sinf(a);}
 			else {dx/=dl; dz/=dl;}
 			float nxp=xp+dx, nzp=zp+dz;
+			if (!(fabsf(nxp) < 2147483648.0f && fabsf(nzp) < 2147483648.0f)) break; /* not a finite in-range position (a NaN in the droplet's own view): the droplet ends; rule of the batched algorithm */
 			int nxi=(int)floorf(nxp), nzi=(int)floorf(nzp);
 			float nxf=nxp-nxi, nzf=nzp-nzi;
 			float nh00=sw_read(&S, nxi, nzi), nh10=sw_read(&S, nxi+1, nzi), nh01=sw_read(&S, nxi, nzi+1), nh11=sw_read(&S, nxi+1, nzi+1);

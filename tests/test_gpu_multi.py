@@ -129,7 +129,8 @@ def test_erode_sweeps_banded_equals_single_band(tw, scene, ctx, beq, nbands):
     import torch
     cfg = scene.SceneConfig(mesh_gen_mode=1, mesh_freq_filter=1, mesh_seed=1, hmap=HM_CFG, zmax_est=2.0)
     ep = cfg.erosion_params()
-    for (nx, ny, iters, sweep, halo) in ((300, 100 * nbands, 20000, 1024, 44), (333, 140 * nbands + 3, 20000, 4096, 64)):
+    # the 700-wide case has droplets whose own writes make their next position NaN: they must end (rule of the algorithm), not read the map's row 0 from a band
+    for (nx, ny, iters, sweep, halo) in ((300, 100 * nbands, 20000, 1024, 44), (333, 140 * nbands + 3, 20000, 4096, 64), (700, max(640, 100 * nbands), 30000, 2048, 44)):
         z = ctx.heightgen_2d(cfg.heightmap_grid(nx, ny), cfg.height_params())
         zmin = float(z.min())
         one = z.copy()
