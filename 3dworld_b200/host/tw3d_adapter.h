@@ -41,6 +41,9 @@ struct scene_globals {
 	float mesh_file_scale = 1.0f, mesh_file_tz = 0.0f; // scale_mh_texture_val (src/mesh_gen.cpp:120), heightmap-texture tiles
 	// erosion (src/erosion.cpp:11,98; src/Textures.cpp:1284-1287)
 	float erode_amount = 1.0f, water_plane_z = 0.0f, HALF_DXY = 0.0625f, zmin = -1.0f, zmax = 1.0f, relh_adj_tex = 0.0f, clip_hd1 = 0.5f;
+	float zbottom = 0.0f, ztop = 0.0f;                  // set_zvals (src/mesh_gen.cpp:494-504); gen_mesh leaves them alone on a flat mesh, as the reference does
+	// sine-table recurrence of gen_mesh (src/mesh_gen.cpp:34,226-231; config keywords mesh_start_mag / mesh_start_freq / mesh_mag_mult / mesh_freq_mult)
+	float MESH_START_MAG = 0.02f, MESH_START_FREQ = 240.0f, MESH_MAG_MULT = 2.0f, MESH_FREQ_MULT = 0.5f;
 };
 
 namespace detail {
@@ -56,7 +59,7 @@ namespace detail {
 	struct state_t {
 		scene_globals g;
 		std::vector<float> sin_table, sine_params;
-		unsigned generation = 0; // bumped by set_globals so that thread-local contexts re-upload the tables
+		unsigned generation = 0; // bumped by set_globals WHEN IT IS GIVEN A TABLE, so that thread-local contexts re-upload the tables (scalars are read per call)
 	};
 	inline state_t &state() {static state_t s; return s;}
 	struct tls_ctx {
@@ -89,7 +92,7 @@ inline void set_globals(scene_globals const &g, const float *sin_table = nullptr
 	s.g = g;
 	if (sin_table) {s.sin_table.assign(sin_table, sin_table + TW_SIN_TABLE_SIZE);}
 	if (sinTable)  {s.sine_params.assign(sinTable, sinTable + TW_F_TABLE_SIZE*5);}
-	++s.generation;
+	if (sin_table || sinTable) {++s.generation;}
 }
 inline scene_globals const &globals() {return detail::state().g;}
 
@@ -329,7 +332,7 @@ inline gen_mesh_result gen_mesh(float *mesh_height /* MESH_Y_SIZE x MESH_X_SIZE,
 	if (dy_val == 0.0f) {dy_val = 1.0f/g.DY_VAL_INV;}
 	std::vector<float> sinTable(TW_F_TABLE_SIZE*5);
 	tw_gen_sine_params(&sine_rng, g.MESH_HEIGHT*g.mesh_height_scale, MX, MY, x_scene_size, y_scene_size, g.mesh_seed, g.mesh_rgen_index, g.mesh_gen_mode,
-	                   0.02f, 240.0f, 2.0f, 0.5f, sinTable.data());
+	                   g.MESH_START_MAG, g.MESH_START_FREQ, g.MESH_MAG_MULT, g.MESH_FREQ_MULT, sinTable.data());
 	set_globals(g, nullptr, sinTable.data());
 	tw_ctx *c = ctx();
 	tw_height_params p = height_params_from_globals(g.mesh_gen_mode, g.mesh_gen_shape);
@@ -339,7 +342,11 @@ inline gen_mesh_result gen_mesh(float *mesh_height /* MESH_Y_SIZE x MESH_X_SIZE,
 	if (rc != TW_OK) {detail::fail(rc, "gen_mesh", c);}
 	float zmin = mm.zmin, zmax = mm.zmax;                        // calc_zminmax
 	float zmax_est = (zmax < -zmin) ? -zmin : zmax;              // set_zmax_est(max(zmax, -zmin))
-	if (zmax == zmin) {zmax_est = zmax_est + 1.0E-6;}
+	gen_mesh_result r;
+	if (zmax == zmin) { // flat mesh: estimate_zminmax returns BEFORE set_zvals (src/mesh_gen.cpp:463-466): zmin/zmax stay the measured pair, zbottom/ztop/water_plane_z keep their old values
+		zmax_est = zmax_est + 1.0E-6;
+		r.zbottom = g.zbottom; r.ztop = g.ztop; r.zmin = zmin; r.zmax = zmax; r.zmax_est = zmax_est; r.water_plane_z = g.water_plane_z;
+	}
 	else {
 		float const XY_SCENE_SIZE(0.5f*(x_scene_size + y_scene_size));
 		float const rm_scale(1000.0*XY_SCENE_SIZE/g.mesh_scale);
@@ -350,18 +357,18 @@ inline gen_mesh_result gen_mesh(float *mesh_height /* MESH_Y_SIZE x MESH_X_SIZE,
 		for (float v : h) {float const a(std::fabs(v)); zmax_est = (zmax_est < a) ? a : zmax_est;}
 		if (g.mesh_gen_mode != TW_MGEN_SINE) {zmax_est *= 1.2;}
 		zmax_est = 1.1*zmax_est;
+		r.zbottom = zmin; r.ztop = zmax;                              // set_zvals
+		r.zmin = -zmax_est; r.zmax = zmax_est; r.zmax_est = zmax_est;
+		r.water_plane_z = tw_water_z_height(zmax_est, g.GLACIATE, g.custom_glaciate_exp, water_h_off, water_h_off_rel);
 	}
-	gen_mesh_result r;
-	r.zbottom = zmin; r.ztop = zmax;                              // set_zvals
-	r.zmin = -zmax_est; r.zmax = zmax_est; r.zmax_est = zmax_est;
-	r.water_plane_z = tw_water_z_height(zmax_est, g.GLACIATE, g.custom_glaciate_exp, water_h_off, water_h_off_rel);
-	g.zmax_est = zmax_est; g.zmin = r.zmin; g.zmax = r.zmax; g.water_plane_z = r.water_plane_z;
+	g.zmax_est = zmax_est; g.zmin = r.zmin; g.zmax = r.zmax; g.water_plane_z = r.water_plane_z; g.zbottom = r.zbottom; g.ztop = r.ztop;
 	set_globals(g);
 	p.zmax_est = zmax_est;
 	if (g.GLACIATE) { // gen_terrain_map -> glaciate()
 		rc = tw_glaciate_mesh(c, mesh_height, MX, MY, xoff2, yoff2, MX, MY, &p, &mm);
 		if (rc != TW_OK) {detail::fail(rc, "glaciate", c);}
-		r.zbottom = mm.zmin; r.ztop = mm.zmax;
+		r.zbottom = mm.zmin; r.ztop = mm.zmax;                    // glaciate() recomputes them (calc_zminmax + the zbottom/ztop update, :399-403)
+		g.zbottom = r.zbottom; g.ztop = r.ztop; set_globals(g);
 	}
 	apply_erosion(mesh_height, MX, MY, r.zbottom, erosion_iters);
 	return r;
