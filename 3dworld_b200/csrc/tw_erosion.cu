@@ -12,6 +12,7 @@
 // Bit-exactness: IEEE sqrt/div, no FMA contraction (-fmad=false), std::min/max argument order preserved (NaN semantics),
 // the random-direction fallback (:84-87) reads cos/sin from a 1e6-entry table built with the HOST libm (rand_float() has only 1e6 values).
 #include "tw_internal.h"
+#include <cooperative_groups.h>
 #include <float.h>
 #include <stdlib.h>
 #include <string.h>
@@ -129,7 +130,37 @@ struct Rng {
 //             padded rows [row0, row0 + rows) (its band +- halo), walks only droplets that start in its own rows [own0, own1), and a droplet
 //             ends once it is more than halo_rule rows from its start row (so it never leaves the band +- halo) - a rule of the algorithm
 //             itself, applied on one GPU too, which makes the sharded result bit-identical to the single-GPU one.
-enum {M_GLOBAL = 0, M_ATOMIC = 1, M_WINDOW = 2, M_WHOLE = 3, M_FROZEN = 4};
+//   M_SPEC    (twi_erode_spec) the reference's SERIAL droplet order on ONE big map, executed speculatively in parallel and committed in order - exact, bit for
+//             bit the serial result. A window of B consecutive droplets is in flight. Every droplet is walked by one warp against the COMMITTED map, seeing its
+//             own writes through a private view (the M_FROZEN machinery) and keeping what it did to itself: a log of (cell, final value) for the cells it changed
+//             and the list of 4x4-cell tiles it touched (read or written). After each round of walks the tiles are stamped with the lowest droplet index that
+//             touched them; a droplet CONFLICTS if a lower-indexed droplet of the window touched one of its tiles. The prefix of the window up to the first
+//             conflict is committed (the logs are copied into the map: disjoint tiles, so any order), droplets whose tiles were touched by a committed one are
+//             walked again against the new map, the window slides. The head of the window never conflicts, so every round commits at least one droplet; on an
+//             8192^2 map the first conflict among random droplets sits a few hundred droplets in (birthday bound on ~1e6 tiles). A droplet that outgrows its log
+//             / tile list / view count, or whose position becomes non-finite (the reference then reads the map's corner), is walked IN PLACE on the map when it
+//             is the head of the window (the plain M_GLOBAL walk of one droplet, alone on the device).
+enum {M_GLOBAL = 0, M_ATOMIC = 1, M_WINDOW = 2, M_WHOLE = 3, M_FROZEN = 4, M_SPEC = 5};
+enum {SP_EMPTY = 0, SP_DIRTY = 1, SP_VALID = 2, SP_HUGE = 3, SP_INPLACE = 4, SP_WALKING = 5}; // state of a window slot
+constexpr unsigned SP_STATE_WORDS = 32; // saved registers of a suspended walk
+#ifndef TW_SPEC_TILE_SHIFT
+#define TW_SPEC_TILE_SHIFT 2
+#endif
+constexpr int SP_TILE_SHIFT = TW_SPEC_TILE_SHIFT; // conflict tiles of (1 << shift)^2 cells, >= 4x4 (a move's 4 x 4 footprint then spans at most 2 x 2 tiles)
+static_assert(SP_TILE_SHIFT >= 2, "a move may touch at most 2 x 2 tiles");
+constexpr unsigned SP_NONE = 0xffffffffu;
+struct SpecArgs { // M_SPEC: the window of in-flight droplets (slot = droplet index % B)
+	unsigned B, W, T, R;            // slots, log entries / tile ids / view segments per slot
+	unsigned *it, *status, *nlog, *ntiles, *nseg, *minw, *steps; // [B]
+	unsigned *cells; float *vals;   // [B][W] log: packed cell (z << 16 | x) and its final value
+	unsigned *tiles;                // [B][T] touched tile ids (duplicates allowed)
+	unsigned *seg;                  // [B][R] end of each flush segment in the log (a cell appears at most once per segment; later segments win)
+	unsigned *stamps;               // [tile] lowest droplet index that touched the tile this round (SP_NONE: none)
+	unsigned *state;                // [B][SP_STATE_WORDS] registers of a walk suspended after `cap` moves in one round (a round must not wait for a 900-move droplet)
+	unsigned *ctl;                  // {lo[0], lo[1], first conflict, done, in-place round, statistics ...}
+	unsigned round, cap;
+	int TNX;                        // tiles per row
+};
 constexpr int TW_SWEEP_VIEW = 32; // M_FROZEN: side of a droplet's private view (part of the algorithm's definition, see tw3d.h)
 constexpr double FIXED_ONE = 1099511627776.0; // 2^40 delta units per height unit
 
@@ -156,13 +187,15 @@ struct DArgs {
 	int row0, own0, own1;       // first stored padded row; droplets starting in padded rows [own0, own1) are walked here
 	int halo_rule;              // a droplet ends when |zi - start row| exceeds this
 	unsigned it0, it1;          // droplets [it0, it1) = this sweep
+	SpecArgs S;                 // M_SPEC; M_GLOBAL with S.ctl != nullptr: walk the window's head in place if it is SP_HUGE
 };
 
 template<int G, int MODE>
 __global__ void __launch_bounds__(128)
 droplet_kernel(DArgs const A)
 {
-	constexpr bool SHARED = (MODE == M_ATOMIC), FROZEN = (MODE == M_FROZEN), WIN = (MODE == M_WINDOW || MODE == M_FROZEN), WHOLE = (MODE == M_WHOLE);
+	constexpr bool SHARED = (MODE == M_ATOMIC), FROZEN = (MODE == M_FROZEN), SPEC = (MODE == M_SPEC), WIN = (MODE == M_WINDOW || MODE == M_FROZEN || MODE == M_SPEC), WHOLE = (MODE == M_WHOLE);
+	static_assert(!SPEC || G == 32, "M_SPEC: one droplet per warp");
 	// M_FROZEN shares M_WINDOW's machinery: the window is the droplet's PRIVATE view (sweep-start heights + its own writes); see hadd
 	constexpr int TPW = 32/G; // heightmaps per warp
 	extern __shared__ __align__(16) float tw_smem[];
@@ -177,7 +210,7 @@ droplet_kernel(DArgs const A)
 	unsigned const gmask = (G == 32) ? 0xffffffffu : (((1u << (G & 31)) - 1u) << (grp*G));
 	int const xsize = A.xsize, ysize = A.ysize;
 	int const NX = xsize + 2*PAD, NY = ysize + 2*PAD;
-	float *mh = (MODE == M_WHOLE) ? nullptr : (FROZEN ? A.padded - (ptrdiff_t)A.row0*NX : A.padded + (SHARED ? (size_t)0 : (size_t)tile*NX*NY)); // FROZEN: indexed by global padded row
+	float *mh = (MODE == M_WHOLE) ? nullptr : (FROZEN ? A.padded - (ptrdiff_t)A.row0*NX : A.padded + ((SHARED || SPEC) ? (size_t)0 : (size_t)tile*NX*NY)); // FROZEN: indexed by global padded row; M_SPEC: every slot walks the ONE map
 	long long *dl64 = FROZEN ? A.delta - (ptrdiff_t)A.row0*NX : nullptr;
 	unsigned const fz_stride = FROZEN ? A.nslots : 0u;
 	int zstart = 0;
@@ -185,19 +218,100 @@ droplet_kernel(DArgs const A)
 	unsigned const MAX_PATH_LEN = 4u*(unsigned)NX*(unsigned)NY;
 	float const erode_amount = A.E.erode_amount;
 	EParams const E = A.E;
-	unsigned const num_iters = A.num_iters;
+	unsigned num_iters = A.num_iters;
 	unsigned long long steps = 0;
 	bool const have_tile = active;
 	bool in_droplet = false;
 	unsigned iter = (MODE == M_FROZEN) ? A.it0 + gslot : 0u, numMoves = 0; // M_FROZEN: group g walks droplets it0 + g, it0 + g + groups, ... of the sweep
+	// M_SPEC: this warp's slot of the window; the log it writes
+	unsigned sp_nlog = 0, sp_nseg = 0, sp_ntiles = 0;
+	int sp_ax = -1, sp_az = -1, sp_bx = -1, sp_bz = -1; // tile rectangle of the previous move (most moves stay inside it)
+	bool sp_overflow = false, sp_started = false, sp_tile0 = false, sp_nonfinite = false, sp_resume = false;
+	unsigned sp_launch_moves = 0;
+	unsigned sp_why = 0; // statistics: why the walk outgrew its log (bit 0 log, 1 views, 2 tiles, 3 write outside the view, 4 non-finite near the corner)
+	unsigned *sp_cells = nullptr, *sp_tiles = nullptr, *sp_seg = nullptr; float *sp_vals = nullptr;
+	bool sp_inplace = false; // M_SPEC: this warp walks the window's HEAD directly on the map (nothing earlier is uncommitted, so its writes are final as they happen)
+	if (SPEC) {
+		unsigned const lo = A.S.ctl[A.S.round & 1u];
+		unsigned const st0 = active ? A.S.status[gslot] : SP_EMPTY;
+		if (!active || A.S.it[gslot] >= num_iters) return;
+		iter = A.S.it[gslot];
+		bool const head = (iter == lo);
+		// walk this slot's droplet if it needs walking: fresh (SP_DIRTY), suspended (SP_WALKING), or outsized and now at the head (SP_HUGE)
+		if (!(st0 == SP_DIRTY || st0 == SP_WALKING || (st0 == SP_HUGE && head))) return;
+		sp_resume = (st0 == SP_WALKING);
+		sp_inplace = head && !sp_resume; // (a suspended head goes on the way it started: its state word says which)
+		sp_cells = A.S.cells + (size_t)gslot*A.S.W; sp_vals = A.S.vals + (size_t)gslot*A.S.W; sp_tiles = A.S.tiles + (size_t)gslot*A.S.T; sp_seg = A.S.seg + (size_t)gslot*A.S.R;
+	}
 	Rng rgen; rgen.s1 = rgen.s2 = 1;
 	int xi = 0, zi = 0;
 	float xp=0, zp=0, xf=0, zf=0, s=0, v=0, w=1, dx=0, dz=0, h=0, h00=0, h10=0, h01=0, h11=0;
 	// shared-memory window of this lane group
 	int const WX = A.WX, WY = A.WY, P = A.P;
 	float *win = (WIN || WHOLE) ? tw_smem + (size_t)(wib*TPW + grp)*A.win_elems : nullptr;
+	unsigned *sp_dirty = SPEC ? reinterpret_cast<unsigned *>(win + (size_t)P*WY) : nullptr; // M_SPEC: one word of dirty bits per view row (WX <= 32), after the view
 	int wx0 = 0, wz0 = 0;           // padded coordinates of the window's first cell
 	bool have_win = WHOLE;
+	// M_SPEC: append the view's changed cells to the droplet's log as one segment (row-major; a cell at most once per segment) and clear the dirty bits
+	auto sp_flush = [&]() {
+		if (!SPEC || !have_win) return;
+		__syncwarp();
+		for (int r = 0; r < WY; ++r) {
+			unsigned const word = sp_dirty[r];
+			if (word == 0u) continue; // warp-uniform
+			bool const mine = (lane < WX) && ((word >> lane) & 1u);
+			unsigned const pos = sp_nlog + __popc(word & ((1u << lane) - 1u));
+			if (mine && pos < A.S.W) {sp_cells[pos] = ((unsigned)(wz0 + r) << 16) | (unsigned)(wx0 + lane); sp_vals[pos] = win[r*P + lane];}
+			sp_nlog += __popc(word);
+		}
+		__syncwarp();
+		if (lane < WY) {sp_dirty[lane] = 0u;}
+		if (sp_nlog > A.S.W || sp_nseg >= A.S.R) {sp_overflow = true; sp_why |= (sp_nlog > A.S.W) ? 1u : 2u; sp_nlog = min(sp_nlog, A.S.W);}
+		else {if (lane == 0) {sp_seg[sp_nseg] = sp_nlog;} ++sp_nseg;}
+		__syncwarp();
+	};
+	// M_SPEC: after a view (re)load from the committed map, put the droplet's own earlier writes back on top, segment by segment (later segments win)
+	auto sp_overlay = [&]() {
+		if (!SPEC) return;
+		unsigned b = 0;
+		for (unsigned sgi = 0; sgi < sp_nseg; ++sgi) {
+			unsigned const e = sp_seg[sgi];
+			for (unsigned k = b + lane; k < e; k += 32) {
+				unsigned const c = sp_cells[k];
+				unsigned const rx = (c & 0xffffu) - (unsigned)wx0, rz = (c >> 16) - (unsigned)wz0;
+				if (rx < (unsigned)WX && rz < (unsigned)WY) {win[rz*P + rx] = sp_vals[k];}
+			}
+			b = e;
+			__syncwarp();
+		}
+	};
+
+	auto load_view = [&]() { // the WX x WY cells at (wx0, wz0) of the (committed / sweep-start / current) map -> shared memory
+		__syncwarp(gmask); // the group's earlier write-throughs are ordered before the loads below
+#pragma unroll 4
+		for (int r = 0; r < WY; ++r) {
+			const float *src = mh + ((size_t)NX*(wz0 + r) + wx0);
+			float *dst = win + r*P;
+			for (int c = sub; c < WX; c += G) {dst[c] = FROZEN ? __ldg(src + c) : __ldcg(src + c);}
+		}
+		__syncwarp(gmask);
+		have_win = true;
+		sp_overlay();
+	};
+	if (SPEC && sp_resume) { // pick a suspended walk up again: registers from the slot's state, the view re-read from the committed map + the droplet's own log
+		const unsigned *q = A.S.state + (size_t)gslot*SP_STATE_WORDS;
+		xi = (int)q[0]; zi = (int)q[1]; wx0 = (int)q[2]; wz0 = (int)q[3]; numMoves = q[4]; rgen.s1 = (int)q[5]; rgen.s2 = (int)q[6];
+		sp_ax = (int)q[7]; sp_az = (int)q[8]; sp_bx = (int)q[9]; sp_bz = (int)q[10];
+		unsigned const fl = q[11]; sp_tile0 = (fl & 2u) != 0u; sp_nonfinite = (fl & 4u) != 0u; sp_inplace = (fl & 8u) != 0u;
+		steps = q[12];
+		xp = __uint_as_float(q[13]); zp = __uint_as_float(q[14]); xf = __uint_as_float(q[15]); zf = __uint_as_float(q[16]); s = __uint_as_float(q[17]); v = __uint_as_float(q[18]);
+		w = __uint_as_float(q[19]); dx = __uint_as_float(q[20]); dz = __uint_as_float(q[21]); h = __uint_as_float(q[22]);
+		h00 = __uint_as_float(q[23]); h10 = __uint_as_float(q[24]); h01 = __uint_as_float(q[25]); h11 = __uint_as_float(q[26]);
+		sp_nlog = A.S.nlog[gslot]; sp_nseg = A.S.nseg[gslot]; sp_ntiles = A.S.ntiles[gslot];
+		in_droplet = true; sp_started = true; ++iter;
+		if (lane < WY) {sp_dirty[lane] = 0u;}
+		if (fl & 1u) {load_view();}
+	}
 
 	if (WHOLE) { // build the padded map in shared memory from the caller's tile (src/erosion.cpp:31-37)
 		if (active) {
@@ -231,6 +345,13 @@ droplet_kernel(DArgs const A)
 		float *p = mh + ((size_t)NX*z + x);
 		if (MODE == M_GLOBAL) {float const nv = *p + delta; if (pred) {*p = nv;} return;}
 		if (!pred) return;
+		if (SPEC && sp_inplace) {*p = *p + delta; return;} // the head of the window: straight into the map
+		if (SPEC) { // the write stays private: view + dirty bit (the log is written when the view moves on or the droplet ends)
+			unsigned const rx = (unsigned)(x - wx0), rz = (unsigned)(z - wz0);
+			if (have_win && rx < (unsigned)WX && rz < (unsigned)WY) {float *q = win + (rz*P + rx); *q = *q + delta; atomicOr(sp_dirty + rz, 1u << rx);}
+			else {sp_overflow = true; sp_why |= 8u;} // cannot happen (the view covers every cell a move touches); if it did, the droplet is walked in place instead
+			return;
+		}
 		if (WIN && have_win) {
 			unsigned const rx = (unsigned)(x - wx0), rz = (unsigned)(z - wz0);
 			if (rx < (unsigned)WX && rz < (unsigned)WY) {
@@ -268,7 +389,20 @@ droplet_kernel(DArgs const A)
 				if (sub == 0) {nd = atomicAdd(A.next_droplet, 1u);}
 				iter = __shfl_sync(gmask, nd, grp*G);
 			}
-			if (iter >= (FROZEN ? A.it1 : num_iters)) {active = false;}
+			if (SPEC && sp_started) { // the slot's one droplet has ended: close the log
+				sp_flush();
+				if (lane == 0) {
+					A.S.nlog[gslot] = sp_nlog; A.S.nseg[gslot] = sp_nseg; A.S.ntiles[gslot] = sp_ntiles; A.S.steps[gslot] = (unsigned)steps;
+					A.S.status[gslot] = sp_inplace ? ((sp_overflow || A.S.ctl[14] != 0u) ? SP_INPLACE : SP_VALID) : (sp_overflow ? SP_HUGE : SP_VALID);
+					if (sp_inplace) {A.S.ctl[14] = 0u; sp_nlog = 0; sp_nseg = 0;} // nothing to commit: the map has it all already
+					if (sp_inplace) {atomicAdd(A.S.ctl + 5, 1u);}
+					atomicAdd(A.S.ctl + 6, 1u); if (sp_overflow) {atomicAdd(A.S.ctl + 7, 1u);} // statistics: walks, walks that outgrew their log
+					for (unsigned b = 0; b < 5; ++b) {if (sp_why & (1u << b)) {atomicAdd(A.S.ctl + 8 + b, 1u);}}
+					atomicMax(A.S.ctl + 13, numMoves);
+				}
+				active = false;
+			}
+			else if (iter >= (FROZEN ? A.it1 : num_iters)) {active = false;}
 			else {
 				rgen.s1 = (int)iter + 11; rgen.s2 = 79*(int)iter + 121;
 				xi = PAD + (rgen.rand()%xsize);
@@ -277,6 +411,7 @@ droplet_kernel(DArgs const A)
 				else {
 					xp=xi; zp=zi; xf=0; zf=0; s=0; v=0; w=1; dx=0; dz=0;
 					if (FROZEN) {have_win = false;} // M_FROZEN: a new droplet knows nothing of the previous one's writes - its first reads included
+					if (SPEC) {sp_started = true; if (lane < WY) {sp_dirty[lane] = 0u;}}
 					h=hread(xi, zi); h00=h; h10=hread(xi+1, zi); h01=hread(xi, zi+1); h11=hread(xi+1, zi+1);
 					numMoves = 0; in_droplet = true; zstart = zi;
 					if (FROZEN) {iter += fz_stride;} else {++iter;}
@@ -287,22 +422,51 @@ droplet_kernel(DArgs const A)
 		if (!active || !in_droplet) continue;
 		if (FROZEN && (unsigned)(zi - zstart + A.halo_rule) > 2u*(unsigned)A.halo_rule) {in_droplet = false; continue;} // left the band +- halo: the droplet ends (rule of the batched algorithm)
 		if (numMoves >= MAX_PATH_LEN) {in_droplet = false; continue;} // "droplet path is too long" (src/erosion.cpp:153)
-		++numMoves; ++steps;
-		if (WIN) { // keep the cells one move can touch - brush [xi-1, xi+2], next corners within +-2 of xi - inside the window
+		if (SPEC && sp_overflow && !sp_inplace) {in_droplet = false; continue;} // outgrew its log: it will be walked in place as the head, no point in finishing this walk
+		if (SPEC && sp_launch_moves >= (sp_inplace ? 2u*A.S.cap : A.S.cap)) { // enough for this round (the in-place head moves at twice the speed): the walk goes on in the next one (a round must not wait for a 900-move droplet)
+			unsigned const had_win = have_win ? 1u : 0u;
+			sp_flush();
+			if (lane == 0) {
+				unsigned *q = A.S.state + (size_t)gslot*SP_STATE_WORDS;
+				q[0] = (unsigned)xi; q[1] = (unsigned)zi; q[2] = (unsigned)wx0; q[3] = (unsigned)wz0; q[4] = numMoves; q[5] = (unsigned)rgen.s1; q[6] = (unsigned)rgen.s2;
+				q[7] = (unsigned)sp_ax; q[8] = (unsigned)sp_az; q[9] = (unsigned)sp_bx; q[10] = (unsigned)sp_bz;
+				q[11] = had_win | (sp_tile0 ? 2u : 0u) | (sp_nonfinite ? 4u : 0u) | (sp_inplace ? 8u : 0u);
+				q[12] = (unsigned)steps;
+				q[13] = __float_as_uint(xp); q[14] = __float_as_uint(zp); q[15] = __float_as_uint(xf); q[16] = __float_as_uint(zf); q[17] = __float_as_uint(s); q[18] = __float_as_uint(v);
+				q[19] = __float_as_uint(w); q[20] = __float_as_uint(dx); q[21] = __float_as_uint(dz); q[22] = __float_as_uint(h);
+				q[23] = __float_as_uint(h00); q[24] = __float_as_uint(h10); q[25] = __float_as_uint(h01); q[26] = __float_as_uint(h11);
+				A.S.nlog[gslot] = sp_nlog; A.S.nseg[gslot] = sp_nseg; A.S.ntiles[gslot] = sp_ntiles;
+				A.S.status[gslot] = (sp_overflow && !sp_inplace) ? SP_HUGE : SP_WALKING;
+				if (sp_overflow && sp_inplace) {A.S.ctl[14] = 1u;} // the head's tile list is incomplete: remember it across the suspension
+			}
+			return;
+		}
+		++numMoves; ++steps; ++sp_launch_moves;
+		if (WIN && !(SPEC && sp_inplace)) { // keep the cells one move can touch - brush [xi-1, xi+2], next corners within +-2 of xi - inside the window
 			int const cx = clampi(xi, NX-1), cz = clampi(zi, NY-1);
 			bool const covered = have_win && max(cx - 2, 0) >= wx0 && min(cx + 3, NX-1) < wx0 + WX && max(cz - 2, 0) >= wz0 && min(cz + 3, NY-1) < wz0 + WY;
-			if (!covered && (FROZEN || numMoves > A.win_min_moves)) { // re-centre ahead of the droplet's heading (dx, dz = unit direction of the last move) and re-load
+			if (!covered && (FROZEN || SPEC || numMoves > A.win_min_moves)) { // re-centre ahead of the droplet's heading (dx, dz = unit direction of the last move) and re-load
+				sp_flush();
 				wx0 = max(0, min(cx - WX/2 + __float2int_rn(dx*(float)(WX/2 - 5)), NX - WX));
 				wz0 = max(0, min(cz - WY/2 + __float2int_rn(dz*(float)(WY/2 - 5)), NY - WY));
-				__syncwarp(gmask); // the group's earlier write-throughs are ordered before the loads below
-#pragma unroll 4
-				for (int r = 0; r < WY; ++r) {
-					const float *src = mh + ((size_t)NX*(wz0 + r) + wx0);
-					float *dst = win + r*P;
-					for (int c = sub; c < WX; c += G) {dst[c] = FROZEN ? __ldg(src + c) : __ldcg(src + c);}
+				load_view();
+			}
+		}
+		if (SPEC && !sp_nonfinite) { // the conflict tiles this move can read or write (after a non-finite position: only cell (0, 0) is read any more, nothing written)
+			int const qx = clampi(xi, NX-1), qz = clampi(zi, NY-1); // (a droplet that has left the map sits at INT_MIN: clamp before the +-)
+			// exactly the cells a move at (xi, zi) can read or write: the 2 x 2 cells at the next position (nxi in xi-1 .. xi+1), the deposit at xi .. xi+1, the brush xi-1 .. xi+2
+			int const ax = clampi(qx - 1, NX-1) >> SP_TILE_SHIFT, bx = clampi(qx + 2, NX-1) >> SP_TILE_SHIFT, az = clampi(qz - 1, NY-1) >> SP_TILE_SHIFT, bz = clampi(qz + 2, NY-1) >> SP_TILE_SHIFT;
+			if (ax == 0 && az == 0) {sp_tile0 = true;}
+			if (ax != sp_ax || az != sp_az || bx != sp_bx || bz != sp_bz) {
+				sp_ax = ax; sp_az = az; sp_bx = bx; sp_bz = bz;
+				if (sp_ntiles + 4 > A.S.T) {sp_overflow = true; sp_why |= 4u;} // (in place: the walk goes on, see below)
+				else {
+					if (lane < 4) {
+						int const tx = (lane & 1) ? bx : ax, tz = (lane & 2) ? bz : az; // up to 2 x 2 tiles; duplicates are harmless
+						sp_tiles[sp_ntiles + lane] = (unsigned)(tz*A.S.TNX + tx);
+					}
+					sp_ntiles += 4;
 				}
-				__syncwarp(gmask);
-				have_win = true;
 			}
 		}
 		{ // ---- one move of the droplet (src/erosion.cpp:76-152) ----
@@ -320,6 +484,20 @@ droplet_kernel(DArgs const A)
 			// M_FROZEN: a droplet whose next position is not a finite in-range number ends here (rule of the batched algorithm, same in the oracle): the reference would
 			// read the map at the clamp of INT_MIN, i.e. row 0 - a row a device that holds only its band +- halo does not have
 			if (FROZEN && !(fabsf(nxp) < 2147483648.0f && fabsf(nzp) < 2147483648.0f)) {in_droplet = false; continue;}
+			if (SPEC && !(fabsf(nxp) < 2147483648.0f && fabsf(nzp) < 2147483648.0f)) {
+				// a NaN of the droplet's own making (2 % of the droplets on the BASELINE terrain): the reference goes on to read the map at the clamp of INT_MIN - cell
+				// (0, 0), four times - before the droplet ends as "outside" on its next move. That cell comes straight from the committed map (hread's fall-back), so
+				// tile 0 joins the droplet's tiles; only if the droplet itself has been there (its own write may sit in its log, not in the map) it is walked in place.
+				if (!sp_nonfinite) { // (the droplet passes here once more on its last move, from "outside")
+					sp_nonfinite = true;
+					if (sp_tile0 && !sp_inplace) {sp_overflow = true; sp_why |= 16u; in_droplet = false; continue;}
+					if (sp_ntiles + 4 > A.S.T) {sp_overflow = true; sp_why |= 4u; if (!sp_inplace) {in_droplet = false; continue;}}
+					else {
+						if (lane < 4) {sp_tiles[sp_ntiles + lane] = 0u;}
+						sp_ntiles += 4;
+					}
+				}
+			}
 			if (!(fabsf(nxp) < 2147483648.0f && fabsf(nzp) < 2147483648.0f)) { // NaN / out of int range: x86 cvttss2si yields INT_MIN -> "outside" next step
 				nxi=tw_x86_f2i(floorf(nxp)); nzi=tw_x86_f2i(floorf(nzp));
 			}
@@ -483,13 +661,14 @@ int whole_pitch(int NX, int NY) {
 	return NX;
 }
 
-enum {EM_AUTO = 0, EM_GLOBAL = 1, EM_WINDOW = 2, EM_WHOLE = 3};
-int env_mode() { // TW_EROSION_MODE = global | window | whole (tests and tuning; default: chosen from the batch shape)
+enum {EM_AUTO = 0, EM_GLOBAL = 1, EM_WINDOW = 2, EM_WHOLE = 3, EM_SPEC = 4};
+int env_mode() { // TW_EROSION_MODE = global | window | whole | spec (tests and tuning; default: chosen from the batch shape)
 	const char *e = getenv("TW_EROSION_MODE");
 	if (!e) return EM_AUTO;
 	if (!strcmp(e, "global")) return EM_GLOBAL;
 	if (!strcmp(e, "window")) return EM_WINDOW;
 	if (!strcmp(e, "whole"))  return EM_WHOLE;
+	if (!strcmp(e, "spec"))   return EM_SPEC;
 	return EM_AUTO;
 }
 
@@ -696,6 +875,158 @@ int twi_erode_parallel(tw_ctx *ctx, float *d_map, int xsize, int ysize, float mi
 	return TW_OK;
 }
 
+// ------------------------------------------------------------------------------------------------ M_SPEC: exact serial order, speculatively parallel
+namespace {
+__global__ void spec_init_kernel(SpecArgs S, unsigned num_iters, size_t ntile_stamps) {
+	size_t const i = (size_t)blockIdx.x*blockDim.x + threadIdx.x;
+	if (i < ntile_stamps) {S.stamps[i] = SP_NONE;}
+	if (i < S.B) {
+		unsigned const s = (unsigned)i;
+		S.it[s] = s; S.status[s] = (s < num_iters) ? SP_DIRTY : SP_EMPTY; // slot s starts with droplet s
+		S.nlog[s] = 0; S.ntiles[s] = 0; S.nseg[s] = 0; S.minw[s] = SP_NONE; S.steps[s] = 0;
+	}
+	if (i == 0) {S.ctl[0] = 0; S.ctl[1] = 0; S.ctl[2] = SP_NONE; S.ctl[3] = 0; S.ctl[4] = 0; for (int k = 5; k < 16; ++k) {S.ctl[k] = 0;}}
+}
+// The bookkeeping of one round: ONE thread-block cluster of 8 x 1024 threads = 256 warps, one warp per slot, cluster.sync() between the phases (a hardware
+// barrier: the blocks of a cluster are co-scheduled, so unlike a grid-wide barrier it cannot dead-lock). Every slot's chain of dependent loads runs beside
+// the others'; as three kernels this cost three launches per round, as one block 8-16 slots per warp one after the other.
+//   stamp     every walked, uncommitted droplet (finished or suspended) stamps its tiles with its index; the lowest index wins
+//   validate  a droplet conflicts if a lower-indexed droplet of the window touched one of its tiles; f = the first droplet that cannot be committed
+//   commit    the prefix [lo, f): the logs go into the map (disjoint tiles: any order), the slots get their next droplets; behind f, droplets whose tiles a
+//             committed droplet touched are walked again from the start; every stamping droplet takes its stamps back
+constexpr unsigned SPEC_CLUSTER = 8, SPEC_MAX_SLOTS = SPEC_CLUSTER*32;
+__global__ void __cluster_dims__(SPEC_CLUSTER, 1, 1) __launch_bounds__(1024) spec_round_kernel(SpecArgs S, unsigned num_iters, float *__restrict__ padded, int NX, unsigned long long *__restrict__ steps_total) {
+	namespace cg = cooperative_groups;
+	cg::cluster_group cluster = cg::this_cluster();
+	unsigned const s = (blockIdx.x*blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+	unsigned const lo = S.ctl[S.round & 1u], hi = (num_iters - lo < S.B) ? num_iters : lo + S.B, hs = lo % S.B;
+	bool const mine = (s < S.B);
+	unsigned const st = mine ? S.status[s] : SP_EMPTY, it = mine ? S.it[s] : SP_NONE, nt = mine ? S.ntiles[s] : 0u;
+	bool const live = mine && st != SP_EMPTY && it < num_iters, stamps = live && (st == SP_VALID || st == SP_WALKING);
+	bool const inplace_round = (lo < num_iters && S.status[hs] == SP_INPLACE && S.it[hs] == lo); // in-place head with an incomplete tile list: everything else is stale
+	const unsigned *t = S.tiles + (size_t)s*S.T;
+	// ctl[2] (first uncommittable droplet) was reset by the previous round's kernel (or the init kernel)
+	if (stamps) {for (unsigned k = lane; k < nt; k += 32) {atomicMin(S.stamps + t[k], it);}} // ---- stamp
+	cluster.sync();
+	unsigned m = SP_NONE;
+	if (live) { // ---- validate
+		if (inplace_round) {if (lane == 0 && it != lo) {atomicMin(S.ctl + 2, lo + 1u);}}
+		else if (!stamps) {if (lane == 0) {atomicMin(S.ctl + 2, it);}} // not walked yet, or outsized and waiting to become the head
+		else {
+			for (unsigned k = lane; k < nt; k += 32) {m = min(m, S.stamps[t[k]]);}
+			for (int o = 16; o; o >>= 1) {m = min(m, __shfl_xor_sync(0xffffffffu, m, o));}
+			if (lane == 0 && (m < it || st == SP_WALKING)) {atomicMin(S.ctl + 2, it);} // an unfinished walk cannot be committed either
+		}
+	}
+	cluster.sync();
+	unsigned const f = min(S.ctl[2], hi);
+	if (stamps) {for (unsigned k = lane; k < nt; k += 32) {S.stamps[t[k]] = SP_NONE;}} // take the stamps back: the array is clean for the next round
+	if (live) { // ---- commit / invalidate
+		if (it < f) {
+			if (st == SP_VALID) {
+				const unsigned *cells = S.cells + (size_t)s*S.W; const float *vals = S.vals + (size_t)s*S.W; const unsigned *seg = S.seg + (size_t)s*S.R;
+				unsigned b = 0;
+				for (unsigned g = 0, ng = S.nseg[s]; g < ng; ++g) { // segment by segment: a cell logged twice gets its later value
+					unsigned const e = seg[g];
+					for (unsigned k = b + lane; k < e; k += 32) {unsigned const cc = cells[k]; padded[(size_t)(cc >> 16)*NX + (cc & 0xffffu)] = vals[k];}
+					b = e;
+					__syncwarp();
+				}
+			}
+			if (lane == 0) {
+				if (st == SP_VALID || st == SP_INPLACE) {atomicAdd(steps_total, (unsigned long long)S.steps[s]);}
+				unsigned const nit = it + S.B; S.it[s] = nit; S.status[s] = (nit < num_iters) ? SP_DIRTY : SP_EMPTY;
+			}
+		}
+		else if (stamps && lane == 0 && (inplace_round || m < f)) {S.status[s] = SP_DIRTY;} // finished or not: walked again from the start
+	}
+	cluster.sync(); // everybody has read ctl[2] and the head's header
+	if (s == 0 && lane == 0) {S.ctl[(S.round + 1u) & 1u] = f; S.ctl[2] = SP_NONE; if (f >= num_iters) {S.ctl[3] = 1u;}}
+}
+
+bool spec_eligible(uint32_t nt, int xsize, int ysize, uint32_t num_iters) {
+	int const mode = env_mode();
+	size_t const NX = (size_t)xsize + 2*PAD, NY = (size_t)ysize + 2*PAD;
+	if (nt != 1 || NX > 65535 || NY > 65535) return false;
+	if (mode == EM_SPEC) return true;
+	// auto: the first conflict among random droplets sits ~sqrt(2*tiles/36) droplets into the window (each touches a dozen of the 4x4 tiles): worth it from a few
+	// thousand tiles on, and only when there are enough droplets to fill a few rounds
+	return (mode == EM_AUTO && NX*NY >= ((size_t)1 << 18) && num_iters >= 64);
+}
+} // namespace
+
+// One heightmap, the reference's serial droplet order, bit for bit (see M_SPEC at the top). Synchronises: the host polls the window's "done" flag.
+int twi_erode_spec(tw_ctx *ctx, float *d_map, int xsize, int ysize, const float *d_min_zvals, float min_zval, uint32_t num_iters, const tw_erosion_params *p, unsigned long long *d_steps) {
+	cudaStream_t const st = ctx->stream;
+	int const NX = xsize + 2*PAD, NY = ysize + 2*PAD;
+	SpecArgs S;
+	memset(&S, 0, sizeof(S));
+	S.B = (unsigned)std::max(32, std::min(env_int("TW_SPEC_WINDOW", 256), (int)SPEC_MAX_SLOTS)); S.B &= ~31u; // <= 256: the round kernel is one cluster with a warp per slot
+	S.W = (unsigned)std::max(64, env_int("TW_SPEC_LOG", 8192));
+	S.T = (unsigned)std::max(16, env_int("TW_SPEC_TILES", 4096)) & ~3u;
+	S.R = (unsigned)std::max(2, env_int("TW_SPEC_VIEWS", 256));
+	S.TNX = ((NX - 1) >> SP_TILE_SHIFT) + 1;
+	size_t const ntile = (size_t)S.TNX*(((NY - 1) >> SP_TILE_SHIFT) + 1);
+	auto al = [](size_t b) {return (b + 255) & ~(size_t)255;};
+	size_t const pad_b = al((size_t)NX*NY*sizeof(float)), slot_b = al((size_t)S.B*sizeof(unsigned));
+	S.cap = (unsigned)std::max(1, env_int("TW_SPEC_MOVES", 64));
+	size_t const total = pad_b + 7*slot_b + 2*al((size_t)S.B*S.W*4) + al((size_t)S.B*S.T*4) + al((size_t)S.B*S.R*4) + al((size_t)S.B*SP_STATE_WORDS*4) + al(ntile*4) + 256;
+	int rc = tw_reserve(ctx, 1, total);
+	if (rc) return rc;
+	char *q = (char *)ctx->d_scratch[1];
+	float *d_pad = (float *)q; q += pad_b;
+	unsigned **slot_arrays[7] = {&S.it, &S.status, &S.nlog, &S.ntiles, &S.nseg, &S.minw, &S.steps};
+	for (auto a : slot_arrays) {*a = (unsigned *)q; q += slot_b;}
+	S.cells = (unsigned *)q; q += al((size_t)S.B*S.W*4);
+	S.vals = (float *)q; q += al((size_t)S.B*S.W*4);
+	S.tiles = (unsigned *)q; q += al((size_t)S.B*S.T*4);
+	S.seg = (unsigned *)q; q += al((size_t)S.B*S.R*4);
+	S.state = (unsigned *)q; q += al((size_t)S.B*SP_STATE_WORDS*4);
+	S.stamps = (unsigned *)q; q += al(ntile*4);
+	S.ctl = (unsigned *)q;
+	rc = tw_reserve_pinned(ctx, 64);
+	if (rc) return rc;
+	volatile unsigned *h_done = (volatile unsigned *)ctx->h_pinned;
+
+	DArgs A;
+	memset(&A, 0, sizeof(A));
+	A.E = make_eparams(p);
+	A.xsize = xsize; A.ysize = ysize; A.num_iters = num_iters; A.dir_table = ctx->d_dir_table;
+	A.padded = d_pad; A.slot0 = 0;
+	pad_kernel<<<dim3((NX + 255)/256, NY, 1), 256, 0, st>>>(d_map, d_pad, xsize, ysize, NX, NY, A.E.wpz_minus_half_dxy, nullptr, nullptr);
+	TW_LAUNCH_CHECK(ctx);
+	size_t const init_n = std::max(ntile, (size_t)S.B);
+	spec_init_kernel<<<(unsigned)((init_n + 255)/256), 256, 0, st>>>(S, num_iters, ntile);
+	TW_LAUNCH_CHECK(ctx);
+	DArgs W = A; // the speculative walkers: one warp per slot, a private 32 x 32 view + 32 words of dirty bits each
+	W.nslots = S.B; W.steps_out = nullptr;
+	W.WX = std::min(32, NX); W.WY = std::min(32, NY); W.P = whole_pitch(W.WX, W.WY); W.win_elems = (unsigned)(W.P*W.WY + 32);
+	unsigned const min_rounds = (num_iters + S.B - 1)/S.B, max_rounds = 2*num_iters + 64;
+	unsigned spec_rounds = 0;
+	for (unsigned round = 0;; ++round) {
+		if (round > max_rounds) return tw_set_error(ctx, TW_ERR_STATE, "speculative erosion made no progress (%u rounds)", round);
+		S.round = round; W.S = S;
+		launch_droplets<32, M_SPEC>(st, W, 4, (size_t)W.win_elems*sizeof(float));
+		spec_round_kernel<<<SPEC_CLUSTER, 1024, 0, st>>>(S, num_iters, d_pad, NX, d_steps);
+		TW_LAUNCH_CHECK(ctx);
+		if (round + 1 >= min_rounds && (round & 7u) == 7u) { // poll "done" every 8 rounds (not before the window can have covered all droplets): the rounds in between are queued back to back
+			TW_CUDA(ctx, cudaMemcpyAsync((void *)h_done, S.ctl + 3, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+			TW_CUDA(ctx, cudaStreamSynchronize(st));
+			if (*h_done) {spec_rounds = round + 1; break;}
+		}
+	}
+	unpad_kernel<<<dim3((xsize + 255)/256, ysize, 1), 256, 0, st>>>(d_pad, d_map, xsize, ysize, NX, NY, d_min_zvals, min_zval, nullptr);
+	TW_LAUNCH_CHECK(ctx);
+	if (getenv("TW_SPEC_STATS")) {
+		unsigned h[16];
+		TW_CUDA(ctx, cudaMemcpyAsync(h, S.ctl, sizeof(h), cudaMemcpyDeviceToHost, st));
+		TW_CUDA(ctx, cudaStreamSynchronize(st));
+		fprintf(stderr, "tw spec: %u droplets, window %u: %u rounds (%.1f commits per round), %u walks (%.2f per droplet), %u outgrew their log (log %u, views %u, tiles %u, outside view %u, non-finite at the corner %u), %u walked in place; longest walk %u moves\n",
+		        num_iters, S.B, spec_rounds, (double)num_iters/spec_rounds, h[6], (double)h[6]/num_iters, h[7], h[8], h[9], h[10], h[11], h[12], h[5], h[13]);
+	}
+	return TW_OK;
+}
+
 int twi_erode(tw_ctx *ctx, float *d_maps, uint32_t ntiles, int xsize, int ysize, const float *d_min_zvals, float min_zval_all,
               uint32_t num_iters, const tw_erosion_params *p)
 {
@@ -707,6 +1038,15 @@ int twi_erode(tw_ctx *ctx, float *d_maps, uint32_t ntiles, int xsize, int ysize,
 	if (rc) return rc;
 	unsigned long long *d_steps = (unsigned long long *)((char *)ctx->d_scratch[2] + 2048);
 	TW_CUDA(ctx, cudaMemsetAsync(d_steps, 0, sizeof(unsigned long long), ctx->stream));
+	if (spec_eligible(ntiles, xsize, ysize, num_iters)) { // one big map: the serial order, walked speculatively in parallel and committed in order (M_SPEC)
+		rc = twi_erode_spec(ctx, d_maps, xsize, ysize, d_min_zvals, min_zval_all, num_iters, p, d_steps);
+		if (rc) return rc;
+		unsigned long long h_steps = 0;
+		TW_CUDA(ctx, cudaMemcpyAsync(&h_steps, d_steps, sizeof(h_steps), cudaMemcpyDeviceToHost, ctx->stream));
+		TW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+		ctx->last_erosion_steps = h_steps;
+		return TW_OK;
+	}
 	// process heightmaps in chunks so that the padded scratch stays within a third of the free device memory (each chunk has its own
 	// heaviest-first schedule and its own tail, so fewer, larger chunks are better)
 	size_t free_b = 0, total_b = 0;

@@ -432,7 +432,8 @@ def main():
     out["hbm_roofline_frac"] = achieved_gbs / hbm_peak
     ex = out.get("extra") or {}
     if "single_map_8192_serial_1000_droplets_per_s" in ex:
-        out["erosion_iters_per_s"] = ex["single_map_8192_serial_1000_droplets_per_s"]                 # config 3: 8192^2 map, 1000 droplets, the reference's serial order (bit-exact)
+        out["erosion_iters_per_s"] = ex["single_map_8192_serial_1000_droplets_per_s"]                 # config 3: 8192^2 map, 1000 droplets, the reference's serial order (bit-exact; speculative parallel walks committed in order)
+        out["erosion_iters_per_s_one_warp_walk"] = ex.get("single_map_8192_one_warp_walk_1000_droplets_per_s")   # the same order walked droplet after droplet by one warp (round 1's path)
         out["erosion_iters_per_s_1e5_droplets"] = ex.get("single_map_8192_serial_100000_droplets_per_s")
         out["erosion_iters_per_s_openmp_mode_1e6_droplets"] = ex.get("single_map_8192_openmp_mode_1e6_droplets_per_s")
         out["erosion_us_per_move"] = ex.get("single_map_8192_serial_100000_droplets_us_per_move")
@@ -591,8 +592,16 @@ def extra_measurements(tw, scene, ctx, stream, torch):
     _, (zmin, _zmax) = ctx.heightgen_2d(cfg.heightmap_grid(N_TILE, N_TILE), cfg.height_params(), out=base, want_minmax=True)
     work = torch.empty_like(base)
     res["_map_8192"] = base.cpu().numpy()    # the CPU leg erodes the same map (popped by main(), never printed)
+    def one_warp(w, n):       # the plain serial walk (one warp, droplet after droplet): what round 1 shipped, kept as the comparison
+        os.environ["TW_EROSION_MODE"] = "global"
+        try:
+            ctx.erode(w, zmin, n, ep)
+        finally:
+            os.environ.pop("TW_EROSION_MODE", None)
+    # "serial" = the reference's serial droplet ORDER, bit for bit; the default path walks the droplets speculatively in parallel and commits them in that order (M_SPEC)
     for name, iters, fn in (("single_map_8192_serial_1000_droplets", 1000, lambda w, n: ctx.erode(w, zmin, n, ep)),
                             ("single_map_8192_serial_100000_droplets", 100000, lambda w, n: ctx.erode(w, zmin, n, ep)),
+                            ("single_map_8192_one_warp_walk_1000_droplets", 1000, one_warp),
                             ("single_map_8192_openmp_mode_1e6_droplets", 1000000, lambda w, n: ctx.erode_parallel(w, zmin, n, ep, 0))):
         for rep in range(2):
             work.copy_(base)

@@ -14,7 +14,7 @@ pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 ENV_KEYS = ("TW_EROSION_MODE", "TW_EROSION_LANES", "TW_EROSION_SMEM_LANES", "TW_EROSION_WIN", "TW_EROSION_WIN_MIN_MOVES", "TW_EROSION_WHOLE_MAX",
-            "TW_EROSION_WINDOW_ALL", "TW_EROSION_HEAVY", "TW_PIPE_CHUNKS")
+            "TW_EROSION_WINDOW_ALL", "TW_EROSION_HEAVY", "TW_PIPE_CHUNKS", "TW_SPEC_WINDOW", "TW_SPEC_LOG", "TW_SPEC_TILES", "TW_SPEC_VIEWS")
 
 
 @pytest.fixture(autouse=True)
@@ -233,3 +233,40 @@ def test_golden_voxel_fixture_on_gpu(tw, ctx, beq):
             vp.rx, vp.ry = (float(x) for x in v["v%d_rxry" % mode])
             vp.zscale = zs
             assert beq(ctx.voxel_fill(vp), v[name]) == 0, name
+
+
+@pytest.mark.parametrize("n,m,iters,env", [
+    (130, 97, 700, {}),                                                  # a small map: almost every droplet conflicts with an earlier one -> constant re-walking, short prefixes
+    (300, 200, 3000, dict(TW_SPEC_WINDOW="256")),
+    (512, 512, 5000, {}),
+    (258, 258, 1000, dict(TW_SPEC_WINDOW="64")),
+    (200, 260, 2000, dict(TW_SPEC_LOG="64", TW_SPEC_TILES="16")),       # logs / tile lists that overflow all the time: outsized droplets walked in place as the window's head
+    (200, 260, 2000, dict(TW_SPEC_VIEWS="2")),                            # at most two views per droplet: long walks go in place
+    (20, 30, 300, {}),                                                   # smaller than the private view
+    (1000, 700, 20000, dict(TW_SPEC_WINDOW="4096")),
+])
+def test_speculative_serial_order_equals_serial(tw, scene, oracle, ctx, beq, monkeypatch, n, m, iters, env):
+    """M_SPEC (droplets walked speculatively in parallel, committed in the reference's order) == the serial reference order, bit for bit,
+    moves included - on maps small enough that the speculation machinery (conflicts, re-walks, in-place heads, view reloads with the droplet's own
+    log laid back on top) is exercised constantly."""
+    monkeypatch.setenv("TW_EROSION_MODE", "spec")
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    cfg, z = _terrain(scene, ctx, n, m)
+    zmin, eps = _eparams(tw, z)
+    for ep in eps:
+        zc, steps = oracle.apply_erosion(z, zmin, iters, convert(ep, oracle.ErosionParams))
+        got = ctx.erode(z.copy(), zmin, iters, ep)
+        assert beq(got, zc) == 0, "%d cells differ" % beq(got, zc)
+        assert ctx.last_erosion_steps == steps
+
+
+def test_speculative_is_the_default_for_one_big_map(tw, scene, oracle, ctx, beq, monkeypatch):
+    """No environment override: a 1024^2 map with >= 64 droplets takes the M_SPEC path (spec_eligible) and equals the serial order; the forced global mode agrees."""
+    cfg, z = _terrain(scene, ctx, 1024, 1024)
+    zmin, eps = _eparams(tw, z)
+    ep = eps[1]
+    zc, steps = oracle.apply_erosion(z, zmin, 20000, convert(ep, oracle.ErosionParams))
+    assert beq(ctx.erode(z.copy(), zmin, 20000, ep), zc) == 0 and ctx.last_erosion_steps == steps
+    monkeypatch.setenv("TW_EROSION_MODE", "global")
+    assert beq(ctx.erode(z.copy(), zmin, 20000, ep), zc) == 0 and ctx.last_erosion_steps == steps
