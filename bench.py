@@ -414,7 +414,7 @@ def main():
                              "frac": FLOP_PER_CELL * cells / (kernel_ms * 1e-3) / alu_peak, "flop_per_cell": FLOP_PER_CELL,
                              "executed_fp32_ops_per_cell": exec_ops, "frac_executed": exec_ops * cells / (kernel_ms * 1e-3) / alu_peak, "executed_ops_source": prof_src,
                              "note": "flop_per_cell = the reference algorithm's fp32 operations (what the CPU path executes); the kernel tabulates part of "
-                                     "them, so frac (algorithmic) can exceed 1 while the FMA pipe itself is ~70 % busy (frac_executed, profiles/)"}},
+                                     "them, so frac (algorithmic) can exceed 1 while the FMA pipe itself is ~80 % busy (frac_executed, profiles/)"}},
     }
     gpu_map = None
     if world == 1:
