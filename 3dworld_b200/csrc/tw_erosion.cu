@@ -154,7 +154,7 @@ struct SpecArgs { // M_SPEC: the window of in-flight droplets (slot = droplet in
 	unsigned *it, *status, *nlog, *ntiles, *nseg, *minw, *steps; // [B]
 	unsigned *cells; float *vals;   // [B][W] log: packed cell (z << 16 | x) and its final value
 	unsigned *tiles;                // [B][T] touched tile ids (duplicates allowed)
-	unsigned *seg;                  // [B][R] end of each flush segment in the log (a cell appears at most once per segment; later segments win)
+	unsigned *seg;                  // [B][R][3] per flush segment: its end in the log, the bounding box of its cells (a cell appears at most once per segment; later segments win)
 	unsigned *stamps;               // [tile] lowest droplet index that touched the tile this round (SP_NONE: none)
 	unsigned *state;                // [B][SP_STATE_WORDS] registers of a walk suspended after `cap` moves in one round (a round must not wait for a 900-move droplet)
 	unsigned *ctl;                  // {lo[0], lo[1], first conflict, done, in-place round, statistics ...}
@@ -241,7 +241,7 @@ droplet_kernel(DArgs const A)
 		if (!(st0 == SP_DIRTY || st0 == SP_WALKING || (st0 == SP_HUGE && head))) return;
 		sp_resume = (st0 == SP_WALKING);
 		sp_inplace = head && !sp_resume; // (a suspended head goes on the way it started: its state word says which)
-		sp_cells = A.S.cells + (size_t)gslot*A.S.W; sp_vals = A.S.vals + (size_t)gslot*A.S.W; sp_tiles = A.S.tiles + (size_t)gslot*A.S.T; sp_seg = A.S.seg + (size_t)gslot*A.S.R;
+		sp_cells = A.S.cells + (size_t)gslot*A.S.W; sp_vals = A.S.vals + (size_t)gslot*A.S.W; sp_tiles = A.S.tiles + (size_t)gslot*A.S.T; sp_seg = A.S.seg + (size_t)gslot*A.S.R*3;
 	}
 	Rng rgen; rgen.s1 = rgen.s2 = 1;
 	int xi = 0, zi = 0;
@@ -256,6 +256,7 @@ droplet_kernel(DArgs const A)
 	auto sp_flush = [&]() {
 		if (!SPEC || !have_win) return;
 		__syncwarp();
+		unsigned orw = 0; int zlo = -1, zhi = -1;
 		for (int r = 0; r < WY; ++r) {
 			unsigned const word = sp_dirty[r];
 			if (word == 0u) continue; // warp-uniform
@@ -263,26 +264,48 @@ droplet_kernel(DArgs const A)
 			unsigned const pos = sp_nlog + __popc(word & ((1u << lane) - 1u));
 			if (mine && pos < A.S.W) {sp_cells[pos] = ((unsigned)(wz0 + r) << 16) | (unsigned)(wx0 + lane); sp_vals[pos] = win[r*P + lane];}
 			sp_nlog += __popc(word);
+			orw |= word; if (zlo < 0) {zlo = r;} zhi = r;
 		}
 		__syncwarp();
 		if (lane < WY) {sp_dirty[lane] = 0u;}
-		if (sp_nlog > A.S.W || sp_nseg >= A.S.R) {sp_overflow = true; sp_why |= (sp_nlog > A.S.W) ? 1u : 2u; sp_nlog = min(sp_nlog, A.S.W);}
-		else {if (lane == 0) {sp_seg[sp_nseg] = sp_nlog;} ++sp_nseg;}
+		if (orw != 0u) { // one segment: its end in the log and the bounding box of its cells (sp_overlay only looks at segments that reach into the view)
+			if (sp_nlog > A.S.W || sp_nseg >= A.S.R) {sp_overflow = true; sp_why |= (sp_nlog > A.S.W) ? 1u : 2u; sp_nlog = min(sp_nlog, A.S.W);}
+			else {
+				if (lane == 0) {
+					sp_seg[3*sp_nseg] = sp_nlog;
+					sp_seg[3*sp_nseg + 1] = (unsigned)(wx0 + __ffs(orw) - 1) | ((unsigned)(wx0 + 31 - __clz(orw)) << 16);
+					sp_seg[3*sp_nseg + 2] = (unsigned)(wz0 + zlo) | ((unsigned)(wz0 + zhi) << 16);
+				}
+				++sp_nseg;
+			}
+		}
 		__syncwarp();
 	};
-	// M_SPEC: after a view (re)load from the committed map, put the droplet's own earlier writes back on top, segment by segment (later segments win)
+	// M_SPEC: after a view (re)load from the committed map, put the droplet's own earlier writes back on top: the segments whose bounding box reaches into the view,
+	// in the order they were written (later segments win). A steadily moving droplet has dozens of segments but only the last one or two matter.
 	auto sp_overlay = [&]() {
 		if (!SPEC) return;
-		unsigned b = 0;
-		for (unsigned sgi = 0; sgi < sp_nseg; ++sgi) {
-			unsigned const e = sp_seg[sgi];
-			for (unsigned k = b + lane; k < e; k += 32) {
-				unsigned const c = sp_cells[k];
-				unsigned const rx = (c & 0xffffu) - (unsigned)wx0, rz = (c >> 16) - (unsigned)wz0;
-				if (rx < (unsigned)WX && rz < (unsigned)WY) {win[rz*P + rx] = sp_vals[k];}
+		unsigned prev_end = 0;
+		for (unsigned base = 0; base < sp_nseg; base += 32) {
+			unsigned const idx = base + lane;
+			bool const in = (idx < sp_nseg);
+			unsigned const e = in ? sp_seg[3*idx] : 0u, bx = in ? sp_seg[3*idx + 1] : 0u, bz = in ? sp_seg[3*idx + 2] : 0u;
+			unsigned start = __shfl_up_sync(0xffffffffu, e, 1);
+			if (lane == 0) {start = prev_end;}
+			bool const hit = in && (int)(bx & 0xffffu) < wx0 + WX && (int)(bx >> 16) >= wx0 && (int)(bz & 0xffffu) < wz0 + WY && (int)(bz >> 16) >= wz0;
+			unsigned mask = __ballot_sync(0xffffffffu, hit);
+			while (mask) {
+				int const l = __ffs(mask) - 1;
+				mask &= mask - 1u;
+				unsigned const b = __shfl_sync(0xffffffffu, start, l), ee = __shfl_sync(0xffffffffu, e, l);
+				for (unsigned k = b + lane; k < ee; k += 32) {
+					unsigned const c = sp_cells[k];
+					unsigned const rx = (c & 0xffffu) - (unsigned)wx0, rz = (c >> 16) - (unsigned)wz0;
+					if (rx < (unsigned)WX && rz < (unsigned)WY) {win[rz*P + rx] = sp_vals[k];}
+				}
+				__syncwarp();
 			}
-			b = e;
-			__syncwarp();
+			prev_end = __shfl_sync(0xffffffffu, e, (int)min(31u, sp_nseg - 1u - base));
 		}
 	};
 
@@ -924,10 +947,10 @@ __global__ void __cluster_dims__(SPEC_CLUSTER, 1, 1) __launch_bounds__(1024) spe
 	if (live) { // ---- commit / invalidate
 		if (it < f) {
 			if (st == SP_VALID) {
-				const unsigned *cells = S.cells + (size_t)s*S.W; const float *vals = S.vals + (size_t)s*S.W; const unsigned *seg = S.seg + (size_t)s*S.R;
+				const unsigned *cells = S.cells + (size_t)s*S.W; const float *vals = S.vals + (size_t)s*S.W; const unsigned *seg = S.seg + (size_t)s*S.R*3;
 				unsigned b = 0;
 				for (unsigned g = 0, ng = S.nseg[s]; g < ng; ++g) { // segment by segment: a cell logged twice gets its later value
-					unsigned const e = seg[g];
+					unsigned const e = seg[3*g]; // (end of the segment, bounding box x, bounding box z)
 					for (unsigned k = b + lane; k < e; k += 32) {unsigned const cc = cells[k]; padded[(size_t)(cc >> 16)*NX + (cc & 0xffffu)] = vals[k];}
 					b = e;
 					__syncwarp();
@@ -970,7 +993,7 @@ int twi_erode_spec(tw_ctx *ctx, float *d_map, int xsize, int ysize, const float 
 	auto al = [](size_t b) {return (b + 255) & ~(size_t)255;};
 	size_t const pad_b = al((size_t)NX*NY*sizeof(float)), slot_b = al((size_t)S.B*sizeof(unsigned));
 	S.cap = (unsigned)std::max(1, env_int("TW_SPEC_MOVES", 64));
-	size_t const total = pad_b + 7*slot_b + 2*al((size_t)S.B*S.W*4) + al((size_t)S.B*S.T*4) + al((size_t)S.B*S.R*4) + al((size_t)S.B*SP_STATE_WORDS*4) + al(ntile*4) + 256;
+	size_t const total = pad_b + 7*slot_b + 2*al((size_t)S.B*S.W*4) + al((size_t)S.B*S.T*4) + al((size_t)S.B*S.R*12) + al((size_t)S.B*SP_STATE_WORDS*4) + al(ntile*4) + 256;
 	int rc = tw_reserve(ctx, 1, total);
 	if (rc) return rc;
 	char *q = (char *)ctx->d_scratch[1];
@@ -980,7 +1003,7 @@ int twi_erode_spec(tw_ctx *ctx, float *d_map, int xsize, int ysize, const float 
 	S.cells = (unsigned *)q; q += al((size_t)S.B*S.W*4);
 	S.vals = (float *)q; q += al((size_t)S.B*S.W*4);
 	S.tiles = (unsigned *)q; q += al((size_t)S.B*S.T*4);
-	S.seg = (unsigned *)q; q += al((size_t)S.B*S.R*4);
+	S.seg = (unsigned *)q; q += al((size_t)S.B*S.R*12);
 	S.state = (unsigned *)q; q += al((size_t)S.B*SP_STATE_WORDS*4);
 	S.stamps = (unsigned *)q; q += al(ntile*4);
 	S.ctl = (unsigned *)q;
