@@ -224,6 +224,57 @@ int tw_heightgen_2d(tw_ctx *ctx, const tw_grid2d *g, const tw_height_params *p, 
 	return tw_heightgen_2d_poll(ctx, 1);
 }
 
+// tile_t::create_texture, terrain part (include/tw3d.h): the jitter noise grid of every tile (force-sine-mode build_arrays at 80x the cell size, start index >= 50,
+// no glaciate) with the batched sine-tile generator, then one thread per texel
+int tw_tile_weights_batch(tw_ctx *ctx, const float *zvals, const int32_t *origins_xy, uint32_t ntiles, int mesh_x_size, int mesh_y_size, float dx, float dy,
+                          uint32_t zvsize, const tw_height_params *p, const tw_weight_params *wp, const float *tile_params, uint8_t *weights, uint8_t *has_any_grass)
+{
+	int rc = check_ctx(ctx); if (rc) return rc;
+	rc = finish_pending(ctx); if (rc) return rc;
+	if (!zvals || !origins_xy || !p || !wp || !tile_params || !weights || ntiles == 0 || zvsize < 3) return tw_set_error(ctx, TW_ERR_ARG, "tw_tile_weights_batch: null argument, no tiles or zvsize < 3");
+	tw_weight_params W = *wp;
+	int seen[5] = {0, 0, 0, 0, 0};
+	for (int i = 0; i < 5; ++i) {
+		if (W.tex_class[i] < 0 || W.tex_class[i] > 4 || seen[W.tex_class[i]]++) return tw_set_error(ctx, TW_ERR_ARG, "tex_class must name each ground texture exactly once (get_texture_ixs asserts it)");
+		W.class_ix[W.tex_class[i]] = i;
+	}
+	if (!(W.zmax > W.zmin)) return tw_set_error(ctx, TW_ERR_ARG, "zmax must exceed zmin");
+	uint32_t const stride = zvsize - 1;
+	size_t const zn = (size_t)ntiles*zvsize*zvsize, tn = (size_t)ntiles*stride*stride;
+	bool const dev_z = tw_is_device_ptr(zvals), dev_w = tw_is_device_ptr(weights), dev_f = has_any_grass && tw_is_device_ptr(has_any_grass), dev_p = tw_is_device_ptr(tile_params);
+	auto al = [](size_t b) {return (b + 255) & ~(size_t)255;};
+	rc = tw_reserve(ctx, 0, al(tn*sizeof(float)) + (dev_z ? 0 : al(zn*sizeof(float))) + (dev_w ? 0 : al(tn*4)) + al(ntiles) + (dev_p ? 0 : al((size_t)ntiles*8*sizeof(float))) + 256);
+	if (rc) return rc;
+	char *q = (char *)ctx->d_scratch[0];
+	float *d_rand = (float *)q; q += al(tn*sizeof(float));
+	const float *d_z = zvals;
+	if (!dev_z) {TW_CUDA(ctx, cudaMemcpyAsync(q, zvals, zn*sizeof(float), cudaMemcpyHostToDevice, ctx->stream)); d_z = (const float *)q; q += al(zn*sizeof(float));}
+	uint8_t *d_w = weights;
+	if (!dev_w) {d_w = (uint8_t *)q; q += al(tn*4);}
+	uint8_t *d_f = dev_f ? has_any_grass : (uint8_t *)q; q += al(ntiles);
+	const float *d_p = tile_params;
+	if (!dev_p) {TW_CUDA(ctx, cudaMemcpyAsync(q, tile_params, (size_t)ntiles*8*sizeof(float), cudaMemcpyHostToDevice, ctx->stream)); d_p = (const float *)q;}
+	if (has_any_grass) {TW_CUDA(ctx, cudaMemsetAsync(d_f, 0, ntiles, ctx->stream));}
+	// height_gen.build_arrays((x1 - MESH_X_SIZE/2), (y1 - MESH_Y_SIZE/2), MESH_NOISE_FREQ*DX_VAL, MESH_NOISE_FREQ*DY_VAL, tsize, tsize, 0, 1) (src/tiled_mesh.cpp:1103)
+	float const MESH_NOISE_FREQ = 80.0f;
+	tw_grid2d g; g.x0 = 0; g.y0 = 0; g.dx = MESH_NOISE_FREQ*dx; g.dy = MESH_NOISE_FREQ*dy; g.nx = stride; g.ny = stride;
+	std::vector<float2> org(ntiles);
+	for (uint32_t t = 0; t < ntiles; ++t) {
+		float const x0 = (float)(origins_xy[2*t] - mesh_x_size/2), y0 = (float)(origins_xy[2*t+1] - mesh_y_size/2);
+		org[t] = make_float2(g.dx*x0, g.dy*y0);
+	}
+	tw_height_params ps = *p;
+	ps.gen_mode = TW_MGEN_SINE; ps.gen_shape = 0; // force_sine_mode: gen_mode = MGEN_SINE, gen_shape = 0 (src/mesh_gen.cpp:592-593)
+	rc = twi_heightgen_sine_tiles(ctx, &g, &ps, 0, 50, org.data(), ntiles, d_rand, nullptr);
+	if (rc) return rc;
+	rc = twi_tile_weights(ctx, d_z, d_rand, ntiles, zvsize, d_p, &W, d_w, has_any_grass ? d_f : nullptr);
+	if (rc) return rc;
+	if (!dev_w) {TW_CUDA(ctx, cudaMemcpyAsync(weights, d_w, tn*4, cudaMemcpyDeviceToHost, ctx->stream));}
+	if (has_any_grass && !dev_f) {TW_CUDA(ctx, cudaMemcpyAsync(has_any_grass, d_f, ntiles, cudaMemcpyDeviceToHost, ctx->stream));}
+	TW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	return TW_OK;
+}
+
 int tw_heightgen_tiles(tw_ctx *ctx, const int32_t *origins_xy, uint32_t ntiles, int mesh_x_size, int mesh_y_size, float dx, float dy,
                        uint32_t zvsize, const tw_height_params *p, float *out, tw_minmax *mm)
 {

@@ -197,3 +197,34 @@ int twi_tile_cut(tw_ctx *ctx, const float *d_czv, uint32_t ntiles, uint32_t zvsi
 	TW_LAUNCH_CHECK(ctx);
 	return TW_OK;
 }
+
+// ------------------------------------------------------------------------------------------------ terrain weights texture (tw_tile_weights_batch)
+#include "tw_weights.cuh"
+namespace {
+// one thread per texel; rand = the force-sine-mode noise grid of the tile (stride^2, un-scaled); flags[tile] |= "a texel has grass"
+__global__ void tile_weights_kernel(const float *__restrict__ zvals, const float *__restrict__ rand, unsigned zvsize, const float *__restrict__ tile_params, tw_weight_params W,
+	uchar4 *__restrict__ out, unsigned char *__restrict__ flags)
+{
+	unsigned const stride = zvsize - 1, x = blockIdx.x*blockDim.x + threadIdx.x, y = blockIdx.y, tile = blockIdx.z;
+	bool grass = false;
+	if (x < stride) {
+		unsigned char rgba[4];
+		float const rand_offset = W.noise_scale*__ldg(rand + ((size_t)tile*stride + y)*stride + x);
+		grass = tww::weights_texel(zvals + (size_t)tile*zvsize*zvsize, zvsize, x, y, rand_offset, tile_params + (size_t)tile*8, W, rgba);
+		out[((size_t)tile*stride + y)*stride + x] = make_uchar4(rgba[0], rgba[1], rgba[2], rgba[3]);
+	}
+	if (flags && __any_sync(0xffffffffu, grass) && (threadIdx.x & 31) == 0) {flags[tile] = 1;} // benign race: every writer stores 1
+}
+}
+
+int twi_tile_weights(tw_ctx *ctx, const float *d_zvals, const float *d_rand, uint32_t ntiles, uint32_t zvsize, const float *d_tile_params, const tw_weight_params *W, uint8_t *d_out, uint8_t *d_flags) {
+	unsigned const stride = zvsize - 1;
+	for (uint32_t t0 = 0; t0 < ntiles; t0 += 65535) { // gridDim.z limit
+		uint32_t const nt = (ntiles - t0 < 65535) ? ntiles - t0 : 65535;
+		tile_weights_kernel<<<dim3((stride + 127)/128, stride, nt), 128, 0, ctx->stream>>>(d_zvals + (size_t)t0*zvsize*zvsize, d_rand + (size_t)t0*stride*stride, zvsize,
+			d_tile_params + (size_t)t0*8, *W, (uchar4 *)d_out + (size_t)t0*stride*stride, d_flags ? d_flags + t0 : nullptr);
+		TW_LAUNCH_CHECK(ctx);
+	}
+	return TW_OK;
+}
+

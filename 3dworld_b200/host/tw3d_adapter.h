@@ -316,6 +316,32 @@ inline void calc_mesh_shadows(const float lpos[3], const float *zvals, const int
 	if (rc != TW_OK) {detail::fail(rc, "calc_mesh_shadows", c);}
 }
 
+// tile_t::create_texture's terrain part (src/tiled_mesh.cpp:1071-1248) for a batch of tiles: mesh_weight_data (RGBA = {sand, dirt, grass, rock}, stride^2 texels per
+// tile) and has_any_grass. The caller passes what the reference reads from engine tables: h_dirt[] and lttex_dirt[].id (as TW_TEX_* classes), sthresh, the biome corners
+// params[y][x].{grass, dirt} of every tile (grass[4] then dirt[4]), get_water_z_height(), vegetation, relh_adj_tex, mesh_gen_shape / mesh_scale_z (noise_scale),
+// water_is_lava || DISABLE_WATER == 2. Texels inside cities / over tunnels / under buildings and the tree pass stay with the caller (it overwrites them afterwards).
+struct weight_tables {float h_dirt[5]; int tex_class[5]; float sthresh[2][2]; float water_level, vegetation; bool snow_to_rock; int mesh_gen_shape; float mesh_scale_z;};
+inline void create_texture_weights(const float *zvals, const int32_t *origins_xy, unsigned ntiles, unsigned zvsize, float dx_val, float dy_val, weight_tables const &wt,
+                                   const float *tile_params, unsigned char *mesh_weight_data, unsigned char *has_any_grass = nullptr) {
+	scene_globals const &g = globals();
+	tw_height_params const p = height_params_from_globals(g.mesh_gen_mode, g.mesh_gen_shape);
+	tw_weight_params W;
+	memset(&W, 0, sizeof(W));
+	for (int i = 0; i < 5; ++i) {W.h_dirt[i] = wt.h_dirt[i]; W.tex_class[i] = wt.tex_class[i];}
+	for (int a = 0; a < 2; ++a) {for (int b = 0; b < 2; ++b) {W.sthresh[a][b] = wt.sthresh[a][b];}}
+	W.zmin = g.zmin; W.zmax = g.zmax; W.relh_adj_tex = g.relh_adj_tex; W.water_level = wt.water_level;
+	float const MESH_NOISE_SCALE = 0.003;
+	W.noise_scale = ((wt.mesh_gen_shape == 2) ? 2.0 : 1.0)*MESH_NOISE_SCALE*wt.mesh_scale_z;          // src/tiled_mesh.cpp:1085-1088, same types
+	float const SQRT2 = sqrt(2.0);                                                                     // src/3DWorld.h:132
+	W.vnz_scale = (g.mesh_gen_mode == TW_MGEN_DWARP_GPU) ? SQRT2 : 1.0;
+	W.vegetation = wt.vegetation; W.snow_to_rock = wt.snow_to_rock ? 1 : 0;
+	W.dx_val = dx_val; W.dy_val = dy_val; W.dxdy = dx_val*dy_val;
+	W.xy_mult = 1.0/float(zvsize - 2);                                                                 // size = zvsize - 2
+	tw_ctx *c = ctx();
+	int const rc = tw_tile_weights_batch(c, zvals, origins_xy, ntiles, g.MESH_X_SIZE, g.MESH_Y_SIZE, dx_val, dy_val, zvsize, &p, &W, tile_params, mesh_weight_data, has_any_grass);
+	if (rc != TW_OK) {detail::fail(rc, "create_texture_weights", c);}
+}
+
 // ------------------------------------------------------------------------------------------------ gen_mesh (ground mode)
 // gen_mesh(surface_type=0, keep_sin_table=0, update_zvals=1) for WMODE_GROUND (src/mesh_gen.cpp:257-355): regenerates the sine table from
 // the function-static generator state (pass the same tw_rng across calls), fills mesh_height, estimates zmax_est from a 128x128 probe of the

@@ -59,6 +59,12 @@ class ShadowParams(C.Structure):
                 ("dy_val_inv", C.c_float), ("xy_sum_size", C.c_int), ("zmin", C.c_float), ("zmax", C.c_float), ("no_shadow", C.c_int)]
 
 
+class WeightParams(C.Structure):
+    _fields_ = [("h_dirt", C.c_float * 5), ("tex_class", C.c_int * 5), ("class_ix", C.c_int * 5), ("sthresh", (C.c_float * 2) * 2), ("zmin", C.c_float), ("zmax", C.c_float),
+                ("relh_adj_tex", C.c_float), ("water_level", C.c_float), ("noise_scale", C.c_float), ("vnz_scale", C.c_float), ("vegetation", C.c_float), ("snow_to_rock", C.c_int),
+                ("dx_val", C.c_float), ("dy_val", C.c_float), ("dxdy", C.c_float), ("xy_mult", C.c_float)]
+
+
 class PointQuery(C.Structure):
     _fields_ = [("kind", C.c_int), ("xy_scale", C.c_float), ("mesh_x_size", C.c_int), ("mesh_y_size", C.c_int), ("x_scene_size", C.c_float),
                 ("y_scene_size", C.c_float), ("xoff2", C.c_int), ("yoff2", C.c_int), ("no_xyoff", C.c_int)]
@@ -333,3 +339,30 @@ def to_floats_u16(data, val_mult, val_add):
     out = np.empty(data.size // 2, np.float32)
     lib().to_to_floats_u16(_p(data), out.size, val_mult, val_add, _p(out))
     return out
+
+
+def weights_noise(hp, sine_params, origins_xy, mesh_size, dx, dy, stride):
+    """The jitter noise grids of tile_t::create_texture: build_arrays(x1 - MESH_X_SIZE/2, y1 - MESH_Y_SIZE/2, 80*DX_VAL, 80*DY_VAL, stride, stride, 0, force_sine_mode=1),
+    eval_index(x, y, 50) - un-scaled, one [stride, stride] grid per tile."""
+    import copy
+    h = copy.copy(hp)
+    h.gen_mode, h.gen_shape = 0, 0                           # force_sine_mode: gen_mode = MGEN_SINE, gen_shape = 0 (src/mesh_gen.cpp:592-593)
+    fx, fy = np.float32(80.0) * np.float32(dx), np.float32(80.0) * np.float32(dy)
+    out = []
+    for x1, y1 in origins_xy:
+        g = Grid2D(float(x1 - mesh_size[0] // 2), float(y1 - mesh_size[1] // 2), float(fx), float(fy), stride, stride)
+        out.append(heightgen_2d(g, h, sine_params, 0, 50))
+    return np.stack(out)
+
+
+def tile_weights(zvals, rand, tile_params, wp):
+    """to_tile_weights: zvals [nt, zv, zv], rand [nt, zv-1, zv-1] (weights_noise), tile_params [nt, 8] -> (rgba [nt, zv-1, zv-1, 4] uint8, has_any_grass [nt] uint8)."""
+    z = np.ascontiguousarray(zvals, np.float32)
+    nt, zv = z.shape[0], z.shape[1]
+    r = np.ascontiguousarray(rand, np.float32)
+    tp = np.ascontiguousarray(tile_params, np.float32).reshape(nt, 8)
+    out = np.empty((nt, zv - 1, zv - 1, 4), np.uint8)
+    flags = np.empty(nt, np.uint8)
+    lib().to_tile_weights(_p(z), _p(r), nt, zv, _p(tp), C.byref(wp), _p(out), _p(flags))
+    return out, flags
+

@@ -323,3 +323,34 @@ def calc_mesh_shadows(lpos, mh, zmin, zmax, sh_in_x=None, sh_in_y=None):
     p = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)
     lib().ref_calc_mesh_shadows(p(lp), p(mh), p(smask), xs, ys, zmin, zmax, p(six), p(siy), p(ox), p(oy))
     return smask, ox, oy
+
+
+def has_texture_extract():
+    return available() and hasattr(lib(), "ref_tile_create_texture")
+
+
+def tex_ids():
+    """The engine's texture ids in the order {sand, dirt, ground (grass), rock, snow}."""
+    out = (C.c_int * 5)()
+    lib().ref_tex_ids(out)
+    return [int(v) for v in out]
+
+
+def tile_create_texture(size, x1, y1, zvals, params8, h_dirt, tex_id_order, vegetation, relh_adj_tex, zmin, zmax, snow_to_rock=0):
+    """The reference's own tile_t::create_texture (terrain-only path: no cities / buildings / tunnels / trees) on caller-provided zvals; scene constants
+    (DX_VAL, mesh_gen_mode / shape, sine tables, water level) from setup(). params8 = biome corners [y][x]{grass, dirt}; h_dirt / tex_id_order = the
+    texture-height table. Returns (weights [stride, stride, 4] uint8 = {sand, dirt, grass, rock}, has_any_grass)."""
+    L = lib()
+    zv = np.ascontiguousarray(zvals, np.float32)
+    assert zv.shape == (size + 2, size + 2)
+    st = size + 1
+    out = np.empty((st, st, 4), np.uint8)
+    p8 = np.ascontiguousarray(params8, np.float32).reshape(8)
+    hd = np.ascontiguousarray(h_dirt, np.float32).reshape(5)
+    ids = (C.c_int * 5)(*[int(v) for v in tex_id_order])
+    hag = C.c_int(0)
+    L.ref_tile_create_texture.argtypes = [C.c_uint, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int, C.c_void_p, C.c_void_p]
+    rc = L.ref_tile_create_texture(size, x1, y1, zv.ctypes.data, p8.ctypes.data, hd.ctypes.data, C.cast(ids, C.c_void_p), vegetation, relh_adj_tex, zmin, zmax, int(snow_to_rock), out.ctypes.data, C.cast(C.byref(hag), C.c_void_p))
+    if rc != 0:
+        raise RuntimeError("ref_tile_create_texture failed: %d" % rc)
+    return out, int(hag.value)

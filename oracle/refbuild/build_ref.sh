@@ -31,6 +31,14 @@ mkdir -p "$OUT/gen"
   grep -E '^float get_max_sea_level +\(\)' "$T"
   awk '/^float get_xy_scale\(\) \{/ {p=1} p {print} p && /^bool tile_t::create_zvals/ {f=1} f && /^}/ {exit}' "$T"
   awk '/^void tile_t::calc_mesh_ao_lighting\(\) \{/ {p=1} p {print} p && /^}/ {exit}' "$T"
+  # terrain weights texture: get_texture_ixs + tile_t::create_texture (src/tiled_mesh.cpp:1049-1352) and what it calls in
+  # src/Textures.cpp - update_lttex_ix + get_tids (:1289-1312) with TEXTURE_SMOOTH (:12); h_dirt / clip_hd1 are that file's globals, defined here
+  echo 'float h_dirt[NTEX_DIRT], clip_hd1; extern bool water_is_lava; extern int DISABLE_WATER; extern float vegetation; extern ttex lttex_dirt[NTEX_DIRT];'
+  grep -E '^float const TEXTURE_SMOOTH' "$R/src/Textures.cpp"
+  awk '/^void update_lttex_ix\(int &ix\)/ {p=1} p {print} p && /^void get_tids\(/ {f=1} f && /^}/ {exit}' "$R/src/Textures.cpp"
+  awk '/^void get_texture_ixs\(/ {p=1} p {print} p && /^}/ {exit}' "$T"
+  awk '/^bool check_region_int\(/ {p=1} p {print} p && /^}/ {exit}' "$T"
+  awk '/^void tile_t::create_texture\(mesh_xy_grid_cache_t &height_gen\) \{/ {p=1} p {print} p && /^}/ {exit}' "$T"
   cat "$HERE/ref_tiled_harness.inc"
 } > "$OUT/gen/tiled_extract.cpp"
 g++ $FLAGS $INC -I "$HERE" -c "$OUT/gen/tiled_extract.cpp" -o "$OUT/tiled_extract.o"

@@ -1349,3 +1349,125 @@ void to_tile_shadows_batch(const float *zvals, const int *tile_xy, unsigned ntil
 	if (sh_out_y) {memcpy(sh_out_y, oy, (size_t)ntiles*zvsize*sizeof(float));}
 	free(ox); free(oy); free(done);
 }
+
+/* ------------------------------------------------------------------------------------------------ terrain weights texture
+ * tile_t::create_texture, src/tiled_mesh.cpp:1071-1248, for terrain without cities / tunnels / buildings (check_mesh_mask == check_city == 0, no exclude cubes,
+ * check_buildings == 0), restated loop for loop. Unsuffixed literals are doubles in the reference and here. Pinned against the function itself, cut out of the
+ * reference at build time (tests/test_oracle_vs_reference.py::test_tile_weights_against_extracted_create_texture). */
+static void tw_update_lttex_ix(int *ix, const tw_weight_params *W) { /* src/Textures.cpp:1289-1292 */
+	if (W->snow_to_rock && W->tex_class[*ix] == TW_TEX_SNOW) {--*ix;}
+	if (W->vegetation == 0.0 && W->tex_class[*ix] == TW_TEX_GROUND) {++*ix;}
+}
+static void tw_get_tids(float relh, int *k1, int *k2, float *t, const tw_weight_params *W) { /* src/Textures.cpp:1294-1312 */
+	float const TEXTURE_SMOOTH = 0.01; /* :12 */
+	const float *h_dirt = W->h_dirt;
+	if      (relh < h_dirt[0]) {*k1 = 0;}
+	else if (relh < h_dirt[1]) {*k1 = 1;}
+	else if (relh < h_dirt[2]) {*k1 = 2;}
+	else if (relh < h_dirt[3]) {*k1 = 3;}
+	else                       {*k1 = 4;}
+	if (*k1 < 5-1 && (h_dirt[*k1] - relh) < TEXTURE_SMOOTH) {
+		if (t) {*t = 1.0 - (h_dirt[*k1] - relh)/TEXTURE_SMOOTH;}
+		*k2 = *k1+1;
+		tw_update_lttex_ix(k1, W);
+		tw_update_lttex_ix(k2, W);
+	}
+	else {
+		tw_update_lttex_ix(k1, W);
+		*k2 = *k1;
+	}
+}
+#define TW_CLIP_TO_01(x) std_max(0.0f, std_min(1.0f, (x)))
+#define TW_BILINEAR(c, x, y) ((y)*((x)*(c)[3] + (1.0f-(x))*(c)[2]) + (1.0f-(y))*((x)*(c)[1] + (1.0f-(x))*(c)[0])) /* BILINEAR_INTERP, :189; c = [y][x] */
+void to_tile_weights(const float *zvals_all, const float *rand_all, unsigned ntiles, unsigned zvsize, const float *tile_params, const tw_weight_params *W, unsigned char *rgba,
+                     unsigned char *has_any_grass_out)
+{
+	unsigned const tsize = zvsize - 1;
+	int sand_tex_ix = -1, dirt_tex_ix = -1, grass_tex_ix = -1, rock_tex_ix = -1;
+	for (int i = 0; i < 5; ++i) { /* get_texture_ixs, :1049-1062 */
+		if (W->tex_class[i] == TW_TEX_SAND) sand_tex_ix = i;
+		if (W->tex_class[i] == TW_TEX_DIRT) dirt_tex_ix = i;
+		if (W->tex_class[i] == TW_TEX_GROUND) grass_tex_ix = i;
+		if (W->tex_class[i] == TW_TEX_ROCK) rock_tex_ix = i;
+	}
+	float const (*sthresh)[2] = W->sthresh;
+	float const zmin = W->zmin, zmax = W->zmax, relh_adj_tex = W->relh_adj_tex, water_level = W->water_level, vegetation = W->vegetation;
+	float const xy_mult = W->xy_mult;
+	float const dz_inv = 1.0f/(zmax - zmin);
+	float const steep_mult_grass = 1.0f/(sthresh[0][1] - sthresh[0][0]);
+	float const steep_mult_snow  = 1.0f/(sthresh[1][1] - sthresh[1][0]);
+	float const steep_mult_rock  = 1.0f/(0.8f*sthresh[0][0] - 0.5f*sthresh[0][0]);
+	float const vnz_scale = W->vnz_scale;
+	for (unsigned tile = 0; tile < ntiles; ++tile) {
+		const float *zvals = zvals_all + (size_t)tile*zvsize*zvsize, *rand_vals = rand_all + (size_t)tile*tsize*tsize, *prm = tile_params + (size_t)tile*8;
+		unsigned char *mesh_weight_data = rgba + (size_t)tile*tsize*tsize*4;
+		int has_any_grass = 0;
+		for (unsigned y = 0; y < tsize; ++y) {
+			float const yv = (float)y*xy_mult;
+			for (unsigned x = 0; x < tsize; ++x) {
+				unsigned const ix_val = y*tsize + x, off = 4*ix_val, ix = y*zvsize + x;
+				float weights[5] = {0, 0, 0, 0, 0};
+				float const mh00 = zvals[ix], mh01 = zvals[ix+1], mh10 = zvals[ix+zvsize], mh11 = zvals[ix+zvsize+1];
+				float const mhmin = std_min(std_min(mh00, mh01), std_min(mh10, mh11)), mhmax = std_max(std_max(mh00, mh01), std_max(mh10, mh11));
+				float const rand_offset = W->noise_scale*rand_vals[y*tsize + x]; /* rand_vals[] = noise_scale*height_gen.eval_index(x, y, 50), :1120 */
+				float const relh1 = relh_adj_tex + (mhmin - zmin)*dz_inv + rand_offset, relh2 = relh_adj_tex + (mhmax - zmin)*dz_inv + rand_offset;
+				int k1, k2, k3, k4;
+				tw_get_tids(relh1, &k1, &k2, NULL, W);
+				tw_get_tids(relh2, &k3, &k4, NULL, W);
+				int const same_tid = (k1 == k4);
+				float t = 0.0;
+				k2 = k4;
+				if (!same_tid) {
+					float const relh = relh_adj_tex + (mh00 - zmin)*dz_inv;
+					tw_get_tids(relh, &k1, &k2, &t, W);
+				}
+				float weight_scale = 1.0;
+				int const grass = (W->tex_class[k1] == TW_TEX_GROUND || W->tex_class[k2] == TW_TEX_GROUND), snow = (W->tex_class[k2] == TW_TEX_SNOW);
+				has_any_grass |= grass;
+				if (grass || snow) {
+					float const *const sti = sthresh[snow];
+					float const nx = W->dy_val*(zvals[ix] - zvals[ix + 1]), ny = W->dx_val*(zvals[ix] - zvals[ix + zvsize]), nz = W->dxdy; /* get_norm_not_normalized, src/tiled_mesh.h:281 */
+					float vnz = vnz_scale*nz/sqrtf(nx*nx + ny*ny + nz*nz);
+					if (grass && vnz > sti[1]) {vnz = TW_CLIP_TO_01(1.0f + 20.0f*rand_offset);}
+					if (vnz < sti[1]) {
+						if (grass) {
+							float rock_weight = (W->tex_class[k1] == TW_TEX_GROUND || W->tex_class[k2] == TW_TEX_ROCK) ? t : 0.0;
+							float const steepness = 1.0 - TW_CLIP_TO_01((vnz - 0.5f*sti[0])*steep_mult_rock);
+							rock_weight  = rock_weight*(1.0 - steepness) + steepness;
+							weight_scale = TW_CLIP_TO_01((vnz - sti[0])*steep_mult_grass);
+							weights[rock_tex_ix] += (1.0 - weight_scale)*rock_weight;
+							weights[dirt_tex_ix] += (1.0 - weight_scale)*(1.0 - rock_weight);
+						}
+						else {
+							weight_scale = TW_CLIP_TO_01(2.0f*(vnz - sti[0])*steep_mult_snow);
+							weights[rock_tex_ix] += 1.0 - weight_scale;
+						}
+					}
+				}
+				weights[k2] += weight_scale*t;
+				weights[k1] += weight_scale*(1.0 - t);
+				float const xv = (float)x*xy_mult;
+				if (vegetation > 0.0) {
+					float const dirt_scale = TW_BILINEAR(prm + 4, xv, yv);
+					if (dirt_scale < 1.0) {
+						weights[sand_tex_ix] += (1.0 - dirt_scale)*weights[dirt_tex_ix];
+						weights[dirt_tex_ix] *= dirt_scale;
+					}
+				}
+				if (grass) {
+					float grass_scale = (mhmin < water_level) ? 0.0f : TW_BILINEAR(prm, xv, yv);
+					if (grass_scale < 1.0) {
+						float const gscale = TW_CLIP_TO_01(2.5f*(grass_scale - 0.5f) + 0.5f);
+						weights[sand_tex_ix ] += (1.0 - gscale)*weights[grass_tex_ix];
+						weights[grass_tex_ix] *= gscale;
+					}
+				}
+				for (unsigned i = 0; i < 5-1; ++i) {
+					mesh_weight_data[off+i] = ((weights[i] <= 0.01) ? 0 : ((weights[i] >= 0.99) ? 255 : (unsigned char)(255.0*weights[i])));
+				}
+			}
+		}
+		if (has_any_grass_out) {has_any_grass_out[tile] = (unsigned char)has_any_grass;}
+	}
+}
+

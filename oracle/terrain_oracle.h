@@ -89,6 +89,9 @@ void to_calc_mesh_shadows(const tw_shadow_params *sp, const float *mh, unsigned 
                           float *sh_out_x, float *sh_out_y);
 void to_tile_shadows_batch(const float *zvals, const int *tile_xy, unsigned ntiles, unsigned zvsize, const tw_shadow_params *sp, unsigned char *smask,
                            float *sh_out_x, float *sh_out_y);
+/* terrain weights texture, ref: src/tiled_mesh.cpp:1071-1248 (terrain part), src/Textures.cpp:1289-1312; rand = the un-scaled jitter noise grids */
+void to_tile_weights(const float *zvals, const float *rand, unsigned ntiles, unsigned zvsize, const float *tile_params, const tw_weight_params *wp, unsigned char *rgba,
+                     unsigned char *has_any_grass);
 /* voxel post-processing, ref: src/voxels.cpp:485-610,739-868 */
 void to_voxel_outside(const float *vals, const tw_voxel_post_params *vp, const unsigned *zix_xy, unsigned char *outside);
 unsigned long long to_voxel_remove_unconnected(float *vals, unsigned char *outside, const tw_voxel_post_params *vp);

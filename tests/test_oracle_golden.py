@@ -255,3 +255,39 @@ def test_mesh_shadows(oracle, beq):
         m, ox, oy = oracle.tile_shadows_batch(g["tiles"], txy, shadow_params(oracle.ShadowParams, g["params"], lp))
         assert np.array_equal(m, g["smask_%d" % li]), li
         assert beq(ox, g["sh_out_x_%d" % li]) == 0 and beq(oy, g["sh_out_y_%d" % li]) == 0, li
+
+
+def weights_golden_case(HP, WP, hmap_params, g, n, ci):
+    """HeightParams / WeightParams of one case of tests/golden/weights.npz (the scene tests/golden/make_golden_weights.py set up in the reference)."""
+    mode, S, dx, dy, zmin, zmax, water, start, mesh_height = [float(v) for v in g["scal_" + n]]
+    c = g["case_%s_%d" % (n, ci)]
+    hp = HP()
+    hp.gen_mode, hp.gen_shape, hp.start_eval_sin, hp.glaciate = int(mode), 0, int(start), 1
+    hp.mesh_scale, hp.mesh_scale_z_inv = 1.0, 1.0
+    hp.dx_val_inv, hp.dy_val_inv = 1.0 / np.float32(dx), 1.0 / np.float32(dy)
+    hp.mesh_height, hp.mesh_height_scale, hp.zmax_est, hp.custom_glaciate_exp = mesh_height, 1.0, 2.3, 0.0
+    hp.hmap = hmap_params
+    wp = WP()
+    for i in range(5):
+        wp.h_dirt[i], wp.tex_class[i] = float(c[i]), int(c[5 + i])
+    wp.sthresh[0][0], wp.sthresh[0][1], wp.sthresh[1][0], wp.sthresh[1][1] = 0.68, 0.86, 0.48, 0.72
+    wp.zmin, wp.zmax, wp.relh_adj_tex, wp.vegetation, wp.snow_to_rock = zmin, zmax, float(c[10]), float(c[11]), int(c[12])
+    wp.water_level = water
+    wp.noise_scale = np.float32(1.0 * float(np.float32(0.003)) * 1.0)
+    wp.vnz_scale = float(np.float32(np.sqrt(2.0))) if int(mode) == 4 else 1.0          # SQRT2 = sqrt(2.0) as a float (src/3DWorld.h:132)
+    wp.dx_val, wp.dy_val, wp.dxdy = dx, dy, float(np.float32(dx) * np.float32(dy))
+    wp.xy_mult = np.float32(1.0 / float(np.float32(S)))
+    return hp, wp, int(S), dx, dy
+
+
+def test_terrain_weights_texture(oracle):
+    """tests/golden/weights.npz = the reference's own tile_t::create_texture (terrain part) on reference tiles, gen modes 1 and 4, three parameter sets (N4)."""
+    from cases import HM_CFG
+    g = load("weights.npz")
+    for n in ("m1", "m4"):
+        for ci in range(3):
+            hp, wp, S, dx, dy = weights_golden_case(oracle.HeightParams, oracle.WeightParams, oracle.hmap_params(**HM_CFG), g, n, ci)
+            rand = oracle.weights_noise(hp, g["sine_params_" + n], [tuple(int(v) for v in o) for o in g["origins_" + n]], (S, S), dx, dy, S + 1)
+            w, flags = oracle.tile_weights(g["tiles_" + n], rand, g["corners_" + n], wp)
+            assert np.array_equal(w, g["weights_%s_%d" % (n, ci)]), (n, ci, int((w != g["weights_%s_%d" % (n, ci)]).sum()))
+            assert np.array_equal(flags, g["grass_%s_%d" % (n, ci)])

@@ -448,3 +448,66 @@ def test_mesh_shadow_chaining_against_extracted_reference(oracle, ref, beq):
             chained += sum(int(not np.array_equal(alone[i], masks[i])) for i in range(len(txy)))
     assert chained > 0          # the handed-over heights changed some neighbour's mask
     RL.ref_set_threads(8)
+
+
+def _weight_cases(ref, P, z, dx, dy, size, shape):
+    """Parameter sets for the terrain weights texture: the reference's default tables with the z range placed so that every ground texture, the smooth bands
+    between them, steep grass / steep snow and the water line all occur; then snow -> rock, no vegetation, a permuted texture table."""
+    ids = ref.tex_ids()                                     # engine ids in the order {sand, dirt, ground, rock, snow}
+    lo, hi = float(z.min()), float(z.max())
+    base = dict(h_dirt=[0.40, 0.44, 0.60, 0.75, 1.0], order=[0, 1, 2, 3, 4], zmin=lo - 0.05 * (hi - lo), zmax=hi + 0.05 * (hi - lo), relh_adj_tex=0.0, vegetation=1.0,
+                snow_to_rock=0, corners=[1.0, 0.7, 0.3, 0.9, 0.0, 0.6, 1.2, 0.4])
+    cases = [base, dict(base, relh_adj_tex=-0.08, corners=[0.2, 0.5, 0.55, 0.45, 1.0, 1.0, 0.1, 0.9]), dict(base, snow_to_rock=1), dict(base, vegetation=0.0),
+             dict(base, h_dirt=[0.2, 0.5, 0.62, 0.7, 1.0], order=[1, 0, 2, 4, 3], relh_adj_tex=0.03)]
+    for c in cases:
+        wp = P()
+        for i in range(5):
+            wp.h_dirt[i] = c["h_dirt"][i]
+            wp.tex_class[i] = c["order"][i]
+        wp.sthresh[0][0], wp.sthresh[0][1], wp.sthresh[1][0], wp.sthresh[1][1] = 0.68, 0.86, 0.48, 0.72      # src/mesh_gen.cpp:44
+        wp.zmin, wp.zmax, wp.relh_adj_tex, wp.vegetation, wp.snow_to_rock = c["zmin"], c["zmax"], c["relh_adj_tex"], c["vegetation"], c["snow_to_rock"]
+        wp.water_level = float(ref.lib().ref_get_water_z_height())
+        wp.noise_scale = np.float32((2.0 if shape == 2 else 1.0) * float(np.float32(0.003)) * 1.0)         # mesh_scale_z = 1
+        wp.vnz_scale = 1.0
+        wp.dx_val, wp.dy_val, wp.dxdy = dx, dy, float(np.float32(dx) * np.float32(dy))
+        wp.xy_mult = np.float32(1.0 / float(np.float32(size)))
+        yield c, wp, [ids[k] for k in c["order"]]
+
+
+def test_tile_weights_against_extracted_create_texture(oracle, ref):
+    """to_tile_weights (the oracle of tw_tile_weights_batch, SURVEY 8f N4) == the reference's own tile_t::create_texture, cut out of src/tiled_mesh.cpp at build time
+    (with get_tids / update_lttex_ix from src/Textures.cpp), on reference-generated tiles: every RGBA byte and has_any_grass."""
+    import pytest
+    if not ref.has_texture_extract():
+        pytest.skip("oracle/_ref was built without the create_texture extraction")
+    RL = ref.lib()
+    RL.ref_set_threads(1)
+    seen, blended = np.zeros(4, np.int64), 0
+    for mode, S, shape in ((1, 64, 0), (0, 32, 0), (2, 48, 2)):
+        zv = S + 2
+        ref.setup(mesh=(S, S, 1), mode=mode, freq_filter=1, seed=1, zmax_est=2.3, hmap=HM_CFG, shape=shape)
+        dx, dy = RL.ref_get_dx(), RL.ref_get_dy()
+        sp = ref.sine_params()
+        hp = oracle.HeightParams()
+        hp.gen_mode, hp.gen_shape, hp.start_eval_sin, hp.glaciate = mode, shape, oracle.compute_scale(1.0, 1), 1
+        hp.mesh_scale, hp.mesh_scale_z_inv = 1.0, 1.0
+        hp.dx_val_inv, hp.dy_val_inv = 1.0 / np.float32(dx), 1.0 / np.float32(dy)
+        hp.mesh_height, hp.mesh_height_scale = RL.ref_get_mesh_height(), 1.0
+        hp.zmax_est, hp.custom_glaciate_exp = 2.3, 0.0
+        hp.rx, hp.ry = oracle.gen_rx_ry(1, 0, mode)
+        hp.hmap = oracle.hmap_params(**HM_CFG)
+        for (x1, y1) in ((3 * S, -5 * S), (-2 * S, 7 * S)):
+            z = ref.heightgen(x1 - S // 2, y1 - S // 2, dx, dy, zv, zv, 0, 1)
+            z = ((z - np.float32(z.mean())) * np.float32(1.0 / max(1e-6, float(z.std()))) * np.float32(0.4)).astype(np.float32)      # a few cells of relief per cell: slopes on both sides of sthresh
+            rand = oracle.weights_noise(hp, sp, [(x1, y1)], (S, S), dx, dy, S + 1)
+            for c, wp, ids in _weight_cases(ref, oracle.WeightParams, z, dx, dy, S, shape):
+                corners_ref = [v for i in range(4) for v in (c["corners"][i], c["corners"][4 + i])]     # the harness takes {grass, dirt} per corner, the API grass[4] then dirt[4]
+                w_ref, hag_ref = ref.tile_create_texture(S, x1, y1, z, corners_ref, c["h_dirt"], ids, c["vegetation"], c["relh_adj_tex"], c["zmin"], c["zmax"], c["snow_to_rock"])
+                w, hag = oracle.tile_weights(z[None], rand, [c["corners"]], wp)
+                assert np.array_equal(w[0], w_ref), (mode, x1, c, int((w[0] != w_ref).sum()))
+                assert int(hag[0]) == hag_ref
+                seen += [(w_ref[..., k] > 0).sum() for k in range(4)]
+                blended += len(np.unique(w_ref.reshape(-1, 4), axis=0))
+    assert (seen > 500).all(), seen                                                 # every channel (sand, dirt, grass, rock) occurs
+    assert blended > 2000, blended                                                  # and mostly as blends, not pure textures
+    RL.ref_set_threads(8)
