@@ -972,9 +972,10 @@ bool spec_eligible(uint32_t nt, int xsize, int ysize, uint32_t num_iters) {
 	size_t const NX = (size_t)xsize + 2*PAD, NY = (size_t)ysize + 2*PAD;
 	if (nt != 1 || NX > 65535 || NY > 65535) return false;
 	if (mode == EM_SPEC) return true;
-	// auto: the first conflict among random droplets sits ~sqrt(2*tiles/36) droplets into the window (each touches a dozen of the 4x4 tiles): worth it from a few
-	// thousand tiles on, and only when there are enough droplets to fill a few rounds
-	return (mode == EM_AUTO && NX*NY >= ((size_t)1 << 18) && num_iters >= 64);
+	// auto: a round costs ~150 us and commits the window up to the first conflict. With t tiles of 4x4 cells and ~30 tiles per droplet the first conflict among
+	// random droplets sits ~sqrt(2*t/900) droplets in: ~12 on a 1024^2 map (twice the one-warp walk's 3.5e4 droplets/s), ~6 on 512^2 (no gain), 25-45 measured
+	// on 8192^2 (4x). Hence: from 2^20 cells on, and only when there are enough droplets to fill a few rounds
+	return (mode == EM_AUTO && NX*NY >= ((size_t)1 << 20) && num_iters >= 64);
 }
 } // namespace
 

@@ -223,7 +223,7 @@ TW_API int tw_eval_points(tw_ctx *ctx, const float *xy, size_t n, const tw_heigh
  * Replaces apply_erosion(float *heightmap, int xsize, int ysize, float min_zval, unsigned num_iters) (src/function_registry.h:354,
  * src/erosion.cpp:14-164): in place, row-major x-fastest, droplets applied in the reference's serial order (iter = 0..num_iters-1;
  * this is the OMP_NUM_THREADS=1 order, the only deterministic one - SURVEY.md section 0). Early-out as the reference when
- * num_iters==0 or erode_amount<=0. One big map (>= 2^18 padded cells, >= 64 droplets) is walked speculatively - a window of consecutive droplets in
+ * num_iters==0 or erode_amount<=0. One big map (>= 2^20 padded cells, >= 64 droplets) is walked speculatively - a window of consecutive droplets in
  * flight, each against the committed map with a private view and a write log, committed strictly in order; droplets whose cells an earlier droplet
  * touched are walked again - which gives the serial result bit for bit at ~4x the speed of walking one droplet after the other (DESIGN.md section 6,
  * M_SPEC; TW_EROSION_MODE=global selects the plain walk). */
