@@ -78,4 +78,7 @@ g++ $FLAGS $INC -I "$HERE" -c "$OUT/gen/voxels_extract.cpp" -o "$OUT/voxels_extr
 g++ ${FLAGS/-fopenmp/} $INC -I "$HERE" -c "$OUT/gen/shadow_extract.cpp" -o "$OUT/shadow_extract.o"
 g++ -shared -fopenmp -Wl,--gc-sections -Wl,--no-undefined -Wl,--version-script="$HERE/exports.map" -o "$OUT/libref3dworld.so" \
   "$OUT"/ref_driver.o "$OUT"/ref_stubs.o "$OUT"/ref_glm.o "$OUT"/mesh_gen.o "$OUT"/erosion.o "$OUT"/upsurface.o "$OUT"/heightmap.o "$OUT"/tiled_extract.o "$OUT"/voxels_extract.o "$OUT"/shadow_extract.o
+# the generated translation units contain reference source text: they exist only for the duration of this build (TW_KEEP_GEN=1 keeps them for debugging);
+# what stays in oracle/_ref/ (git-ignored) are objects and the shared library
+if [ -z "$TW_KEEP_GEN" ]; then rm -rf "$OUT/gen"; fi
 echo "built $OUT/libref3dworld.so"
