@@ -118,6 +118,33 @@ float tw_water_z_height(float zmax_est, int glaciate, float custom_glaciate_exp,
 	return wpz*zmax_est2 - zmax_est + water_h_off;
 }
 
+// init_terrain_mesh() + gen_tex_height_tables() (src/mesh_gen.cpp:407-431, src/Textures.cpp:1757-1761): the relative-height thresholds of the five ground textures
+// (mesh_tids_dirt / mesh_rh_dirt, :42-43) moved with the water level, h_dirt[i] = pow(zval, glaciate_exp), clip_hd1 = 0.90*h_dirt[1] + 0.10*h_dirt[0]
+void tw_gen_tex_height_tables(float water_h_off_rel, float temperature, float glaciate_exp, float h_dirt[5], int tex_class[5], float *clip_hd1) {
+	float const W_PLANE_Z = 0.42;                                                   // src/mesh_gen.cpp:19
+	float const mesh_rh_dirt[5] = {0.40, 0.44, 0.60, 0.75, 1.0};                    // :43
+	int   const mesh_tids_dirt[5] = {TW_TEX_SAND, TW_TEX_DIRT, TW_TEX_GROUND, TW_TEX_ROCK, TW_TEX_SNOW}; // :42
+	float const t(W_PLANE_Z + water_h_off_rel);
+	float const lo((t < 1.0f) ? t : 1.0f);
+	float const rel_wpz((0.0f < lo) ? lo : 0.0f);                                   // get_rel_wpz(): CLIP_TO_01(W_PLANE_Z + water_h_off_rel), :362
+	for (unsigned i = 0; i < 5; ++i) {
+		float const def_h(mesh_rh_dirt[i]);
+		float h;
+		if (mesh_rh_dirt[i] < W_PLANE_Z) {h = def_h*rel_wpz/W_PLANE_Z;}             // below water
+		else { // above water
+			float const rel_h((def_h - W_PLANE_Z)/(1.0f - W_PLANE_Z));
+			h = rel_wpz + rel_h*(1.0 - rel_wpz);
+			if (mesh_tids_dirt[i] == TW_TEX_SNOW) {
+				h = (def_h < h) ? def_h : h;                                        // min(h, def_h): snow can't get lower when water lowers
+				if (temperature > 40.0) h += 0.01*(temperature - 40.0);             // less snow with increasing temperature
+			}
+		}
+		if (tex_class) {tex_class[i] = mesh_tids_dirt[i];}
+		h_dirt[i] = std::pow(h, glaciate_exp);                                      // pow(float, float) -> float
+	}
+	if (clip_hd1) {*clip_hd1 = (0.90*h_dirt[1] + 0.10*h_dirt[0]);}
+}
+
 // 1e6-entry direction table for the erosion random-direction fallback (src/erosion.cpp:84-87):
 // a = rgen.rand_float()*TWO_PI with rand_float() = 0.000001*(rand()%1000000); dx=cosf(a); dz=sinf(a)
 void twi_build_dir_table(float *cs2x1e6) {

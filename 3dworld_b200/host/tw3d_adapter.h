@@ -320,6 +320,7 @@ inline void calc_mesh_shadows(const float lpos[3], const float *zvals, const int
 // tile) and has_any_grass. The caller passes what the reference reads from engine tables: h_dirt[] and lttex_dirt[].id (as TW_TEX_* classes), sthresh, the biome corners
 // params[y][x].{grass, dirt} of every tile (grass[4] then dirt[4]), get_water_z_height(), vegetation, relh_adj_tex, mesh_gen_shape / mesh_scale_z (noise_scale),
 // water_is_lava || DISABLE_WATER == 2. Texels inside cities / over tunnels / under buildings and the tree pass stay with the caller (it overwrites them afterwards).
+// (h_dirt / tex_class: the engine's own tables, or tw_gen_tex_height_tables(water_h_off_rel, temperature, glaciate_exp, ...) = init_terrain_mesh + gen_tex_height_tables)
 struct weight_tables {float h_dirt[5]; int tex_class[5]; float sthresh[2][2]; float water_level, vegetation; bool snow_to_rock; int mesh_gen_shape; float mesh_scale_z;};
 inline void create_texture_weights(const float *zvals, const int32_t *origins_xy, unsigned ntiles, unsigned zvsize, float dx_val, float dy_val, weight_tables const &wt,
                                    const float *tile_params, unsigned char *mesh_weight_data, unsigned char *has_any_grass = nullptr) {

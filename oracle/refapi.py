@@ -354,3 +354,12 @@ def tile_create_texture(size, x1, y1, zvals, params8, h_dirt, tex_id_order, vege
     if rc != 0:
         raise RuntimeError("ref_tile_create_texture failed: %d" % rc)
     return out, int(hag.value)
+
+
+def init_terrain_mesh(water_h_off_rel=0.0, temperature=20.0, glaciate_exp=3.0):
+    """The reference's init_terrain_mesh() (linked) + gen_tex_height_tables() (cut out of src/Textures.cpp at build time): (h_dirt[5], texture ids[5], lttex zvals[5], clip_hd1)."""
+    L = lib()
+    h, ids, zv, clip = (C.c_float * 5)(), (C.c_int * 5)(), (C.c_float * 5)(), C.c_float()
+    L.ref_init_terrain_mesh.argtypes = [C.c_float, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.ref_init_terrain_mesh(water_h_off_rel, temperature, glaciate_exp, C.cast(h, C.c_void_p), C.cast(ids, C.c_void_p), C.cast(zv, C.c_void_p), C.cast(C.byref(clip), C.c_void_p))
+    return np.array(h, np.float32), [int(v) for v in ids], np.array(zv, np.float32), np.float32(clip.value)

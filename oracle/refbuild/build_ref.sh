@@ -36,6 +36,8 @@ mkdir -p "$OUT/gen"
   echo 'float h_dirt[NTEX_DIRT], clip_hd1; extern bool water_is_lava; extern int DISABLE_WATER; extern float vegetation; extern ttex lttex_dirt[NTEX_DIRT];'
   grep -E '^float const TEXTURE_SMOOTH' "$R/src/Textures.cpp"
   awk '/^void update_lttex_ix\(int &ix\)/ {p=1} p {print} p && /^void get_tids\(/ {f=1} f && /^}/ {exit}' "$R/src/Textures.cpp"
+  echo 'extern float glaciate_exp;'
+  awk '/^void gen_tex_height_tables\(\) \{/ {p=1} p {print} p && /^}/ {exit}' "$R/src/Textures.cpp"   # :1757-1761, called by init_terrain_mesh (mesh_gen.o)
   awk '/^void get_texture_ixs\(/ {p=1} p {print} p && /^}/ {exit}' "$T"
   awk '/^bool check_region_int\(/ {p=1} p {print} p && /^}/ {exit}' "$T"
   awk '/^void tile_t::create_texture\(mesh_xy_grid_cache_t &height_gen\) \{/ {p=1} p {print} p && /^}/ {exit}' "$T"

@@ -511,3 +511,24 @@ def test_tile_weights_against_extracted_create_texture(oracle, ref):
     assert (seen > 500).all(), seen                                                 # every channel (sand, dirt, grass, rock) occurs
     assert blended > 2000, blended                                                  # and mostly as blends, not pure textures
     RL.ref_set_threads(8)
+
+
+def test_tex_height_tables_host_function_against_reference(tw, scene, ref, beq):
+    """tw_gen_tex_height_tables (host side of the C ABI) == the reference's init_terrain_mesh() (linked from mesh_gen.o) + gen_tex_height_tables()
+    (cut out of src/Textures.cpp at build time): h_dirt[5], the texture order and clip_hd1, over water levels, temperatures and glaciate exponents; scene.py's
+    clip_hd1 (what the erosion parameters use) agrees too."""
+    import pytest
+    if not (ref.has_texture_extract() and hasattr(ref.lib(), "ref_init_terrain_mesh")):
+        pytest.skip("oracle/_ref was built without the Textures.cpp extraction")
+    ids = ref.tex_ids()
+    for rel in (0.0, -0.42, -0.3, -0.1, 0.07, 0.25, 0.58, 0.7):
+        for temp in (20.0, 40.0, 41.5, 75.0):
+            for gexp in (3.0, 1.0, 2.5):
+                h_ref, id_ref, _, clip_ref = ref.init_terrain_mesh(rel, temp, gexp)
+                h, cls, clip = tw.gen_tex_height_tables(rel, temp, gexp)
+                assert beq(np.array(h, np.float32), h_ref) == 0, (rel, temp, gexp, h, h_ref)
+                assert [ids[c] for c in cls] == id_ref
+                assert np.float32(clip) == clip_ref
+    for rel in (0.0, 0.1, -0.2):
+        cfg = scene.SceneConfig(water_h_off_rel=rel, glaciate=1)
+        assert np.float32(cfg.clip_hd1()) == ref.init_terrain_mesh(rel, 20.0, 3.0)[3]
