@@ -267,6 +267,18 @@ def erode_sweeps(h, min_zval, num_iters, ep, sweep, halo):
     return h, int(steps)
 
 
+def erode_spec_model(h, min_zval, num_iters, ep, window, cap, tile_shift=2, sched_seed=0):
+    """to_erode_spec_model: the sequential model of the product's speculative serial-order erosion; returns (map, moves, (rounds, walks, wasted walks, in-place walks))."""
+    h = np.array(h, np.float32, order="C", copy=True)
+    ys, xs = h.shape
+    stats = (C.c_ulonglong * 4)()
+    L = lib()
+    L.to_erode_spec_model.restype = C.c_ulonglong
+    L.to_erode_spec_model.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_uint, C.c_void_p, C.c_uint, C.c_uint, C.c_int, C.c_uint, C.c_void_p]
+    steps = L.to_erode_spec_model(h.ctypes.data, xs, ys, min_zval, num_iters, C.cast(C.byref(ep), C.c_void_p), window, cap, tile_shift, sched_seed, C.cast(stats, C.c_void_p))
+    return h, int(steps), tuple(int(v) for v in stats)
+
+
 def noise3d_gen_sines(rs1, rs2, mag, freq):
     out = np.empty(420, np.float32)
     lib().to_noise3d_gen_sines(rs1, rs2, mag, freq, _p(out))

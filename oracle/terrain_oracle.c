@@ -1471,3 +1471,210 @@ void to_tile_weights(const float *zvals_all, const float *rand_all, unsigned nti
 	}
 }
 
+/* ------------------------------------------------------------------------------------------------ M_SPEC protocol model (test infrastructure)
+ * An executable statement of the PROTOCOL behind twi_erode_spec (csrc/tw_erosion.cu): the reference's serial droplet order, walked speculatively
+ * and committed in order. Sequential C, nothing shared with the CUDA code: a window of B droplets, every walker reads the committed map through a private overlay of
+ * its own writes and records the conflict tiles it touches; per round the walkers run in a PSEUDO-RANDOM order for at most `cap` moves each (suspension), the head of
+ * the window walks directly on the map; then stamp (lowest toucher per tile) / validate / commit the prefix up to the first conflict / re-walk what a committed droplet
+ * touched. tests/test_oracle_golden.py::test_spec_protocol_model checks that, whatever the window, cap, tile size and schedule, the result is to_apply_erosion's, bit for
+ * bit - on maps small enough that almost every droplet conflicts. The per-move arithmetic is to_apply_erosion's (src/erosion.cpp:76-152). */
+#ifndef CLAMPI
+#define CLAMPI(v, hi) (((v) < (hi)) ? (((v) > 0) ? (v) : 0) : (hi))
+#endif
+typedef struct {
+	unsigned it; int status;                 /* 0 empty, 1 dirty (to be walked from the start), 2 valid (finished, uncommitted), 5 walking (suspended) */
+	int inplace;                             /* walked as the head: directly on the map */
+	int started, xi, zi; unsigned numMoves;
+	float xp, zp, xf, zf, s, v, w, dx, dz, h, h00, h10, h01, h11;
+	tw_rng rgen;
+	size_t nov; unsigned *ov_cell; float *ov_val; int *ov_pos;   /* overlay of the walker's own writes: list + per-cell position (-1: none) */
+	size_t ntile, cap_tile; unsigned *tiles;
+	unsigned long long steps;
+} spm_walker;
+typedef struct {float *mh; int NX, NY, xsize, ysize, shift, TNX; const tw_erosion_params *ep; unsigned MAX_PATH_LEN;} spm_ctx;
+
+static float spm_read(const spm_ctx *C, spm_walker *W, int x, int y) {
+	size_t const ix = (size_t)C->NX*CLAMPI(y, C->NY-1) + CLAMPI(x, C->NX-1);
+	if (!W->inplace && W->ov_pos[ix] >= 0) return W->ov_val[W->ov_pos[ix]];
+	return C->mh[ix];
+}
+static void spm_add(const spm_ctx *C, spm_walker *W, size_t ix, float delta) { /* heightmap[ix] += delta, privately unless this is the head */
+	if (W->inplace) {C->mh[ix] += delta; return;}
+	if (W->ov_pos[ix] < 0) {W->ov_pos[ix] = (int)W->nov; W->ov_cell[W->nov] = (unsigned)ix; W->ov_val[W->nov] = C->mh[ix]; ++W->nov;}
+	W->ov_val[W->ov_pos[ix]] += delta;
+}
+static void spm_touch(const spm_ctx *C, spm_walker *W, int xi, int zi) { /* the tiles of [xi-1, xi+2] x [zi-1, zi+2]: every cell this move can read or write */
+	int const qx = CLAMPI(xi, C->NX-1), qz = CLAMPI(zi, C->NY-1);
+	int const ax = CLAMPI(qx-1, C->NX-1) >> C->shift, bx = CLAMPI(qx+2, C->NX-1) >> C->shift, az = CLAMPI(qz-1, C->NY-1) >> C->shift, bz = CLAMPI(qz+2, C->NY-1) >> C->shift;
+	for (int tz = az; tz <= bz; ++tz) for (int tx = ax; tx <= bx; ++tx) {
+		unsigned const t = (unsigned)(tz*C->TNX + tx);
+		int dup = 0;
+		for (size_t k = (W->ntile > 8) ? W->ntile - 8 : 0; k < W->ntile; ++k) {if (W->tiles[k] == t) {dup = 1;}}
+		if (dup) continue;
+		if (W->ntile == W->cap_tile) {W->cap_tile *= 2; W->tiles = (unsigned *)realloc(W->tiles, W->cap_tile*sizeof(unsigned));}
+		W->tiles[W->ntile++] = t;
+	}
+}
+static void spm_reset(const spm_ctx *C, spm_walker *W) { /* forget a walk */
+	for (size_t k = 0; k < W->nov; ++k) {W->ov_pos[W->ov_cell[k]] = -1;}
+	W->nov = 0; W->ntile = 0; W->started = 0; W->steps = 0; W->inplace = 0;
+	(void)C;
+}
+/* walks at most `cap` moves; returns 1 when the droplet has ended */
+static int spm_walk(const spm_ctx *C, spm_walker *W, unsigned cap) {
+	float const Kq=10, Kw=0.001f, Kr=0.9f, Kd=0.02f, Ki=0.1f, minSlope=0.05f, g=20, Kg=g*2;
+	int const PAD = 4, NX = C->NX, NY = C->NY;
+	const tw_erosion_params *ep = C->ep;
+	float const erode_amount = ep->erode_amount, tp = two_pi();
+	if (!W->started) {
+		to_rng_set(&W->rgen, (int)W->it+11, 79*(int)W->it+121);
+		W->xi = PAD + (to_rng_rand(&W->rgen)%C->xsize);
+		W->zi = PAD + (to_rng_rand(&W->rgen)%C->ysize);
+		W->xp=W->xi; W->zp=W->zi; W->xf=0; W->zf=0; W->s=0; W->v=0; W->w=1; W->dx=0; W->dz=0;
+		spm_touch(C, W, W->xi, W->zi);
+		W->h=spm_read(C, W, W->xi, W->zi); W->h00=W->h; W->h10=spm_read(C, W, W->xi+1, W->zi); W->h01=spm_read(C, W, W->xi, W->zi+1); W->h11=spm_read(C, W, W->xi+1, W->zi+1);
+		W->numMoves = 0; W->started = 1;
+	}
+	int xi=W->xi, zi=W->zi; float xp=W->xp, zp=W->zp, xf=W->xf, zf=W->zf, s=W->s, v=W->v, w=W->w, dx=W->dx, dz=W->dz, h=W->h, h00=W->h00, h10=W->h10, h01=W->h01, h11=W->h11;
+	int ended = 0;
+	unsigned moved = 0;
+#define SPM_DEPOSIT_AT(X, Z, WGT) {float const delta = ds*erode_amount*(WGT); if (!((X) < 0 || (Z) < 0 || (X) >= NX || (Z) >= NY)) {spm_add(C, W, (size_t)NX*CLAMPI((Z), NY-1) + CLAMPI((X), NX-1), delta);}}
+#define SPM_DEPOSIT(H) SPM_DEPOSIT_AT(xi, zi, (1-xf)*(1-zf)) SPM_DEPOSIT_AT(xi+1, zi, xf*(1-zf)) SPM_DEPOSIT_AT(xi, zi+1, (1-xf)*zf) SPM_DEPOSIT_AT(xi+1, zi+1, xf*zf) (H)+=ds;
+	for (;;) {
+		if (W->numMoves >= C->MAX_PATH_LEN) {ended = 1; break;}
+		if (moved >= cap) break; /* suspended */
+		++W->numMoves; ++moved; ++W->steps;
+		spm_touch(C, W, xi, zi);
+		float gx=h00+h01-h10-h11, gz=h00+h10-h01-h11;
+		dx=(dx-gx)*Ki+gx;
+		dz=(dz-gz)*Ki+gz;
+		float dl=sqrtf(dx*dx+dz*dz);
+		if (dl<=FLT_EPSILON) {float a=to_rng_rand_float(&W->rgen)*tp; dx=cosf(a); dz=sinf(a);}
+		else {dx/=dl; dz/=dl;}
+		float nxp=xp+dx, nzp=zp+dz;
+		int nxi, nzi;
+		if (fabsf(nxp) < 2147483648.0f && fabsf(nzp) < 2147483648.0f) {nxi=(int)floorf(nxp); nzi=(int)floorf(nzp);}
+		else {nxi = nzi = (-2147483647 - 1); if (fabsf(nxp) < 2147483648.0f) {nxi=(int)floorf(nxp);} if (fabsf(nzp) < 2147483648.0f) {nzi=(int)floorf(nzp);} /* x86 cvttss2si */
+			if (W->ntile == W->cap_tile) {W->cap_tile *= 2; W->tiles = (unsigned *)realloc(W->tiles, W->cap_tile*sizeof(unsigned));}
+			W->tiles[W->ntile++] = 0u; /* the reference reads cell (0, 0) next */
+		}
+		float nxf=nxp-nxi, nzf=nzp-nzi;
+		float nh00=spm_read(C, W, nxi, nzi), nh10=spm_read(C, W, (nxi == (-2147483647 - 1)) ? nxi : nxi+1, nzi), nh01=spm_read(C, W, nxi, (nzi == (-2147483647 - 1)) ? nzi : nzi+1),
+		      nh11=spm_read(C, W, (nxi == (-2147483647 - 1)) ? nxi : nxi+1, (nzi == (-2147483647 - 1)) ? nzi : nzi+1);
+		float nh=(nh00*(1-nxf)+nh10*nxf)*(1-nzf)+(nh01*(1-nxf)+nh11*nxf)*nzf;
+		if (std_max(std_max(nh00, nh10), std_max(nh01, nh11)) < ep->water_plane_z - ep->half_dxy) {ended = 1; break;}
+		int const outside = (xi < 0 || zi < 0 || xi >= NX || zi >= NY);
+		if (nh>=h || outside) {
+			float ds=(nh-h)+0.001f;
+			if (ds>=s || outside) {ds=s; SPM_DEPOSIT(h) s=0; ended = 1; break;}
+			SPM_DEPOSIT(h)
+			s-=ds;
+			v=0;
+		}
+		float dh=h-nh;
+		float q=std_max(dh, minSlope)*v*w*Kq;
+		float ds=s-q;
+		if (ds>=0) {ds*=Kd; SPM_DEPOSIT(dh) s-=ds;}
+		else {
+			ds*=-Kr;
+			ds=std_min(ds, dh*0.99f);
+			{float const relh = ep->relh_adj_tex + (nh - ep->zmin)/(ep->zmax - ep->zmin); ds = (float)(ds*((relh > ep->clip_hd1) ? 0.5 : 2.0));}
+			for (int z=zi-1; z<=zi+2; ++z) {
+				float zo=z-zp, zo2=zo*zo;
+				for (int x=xi-1; x<=xi+2; ++x) {
+					float xo=x-xp;
+					float wgt=1-(xo*xo+zo2)*0.25f;
+					if (wgt<=0) continue;
+					wgt*=0.1591549430918953f;
+					float const delta=ds*erode_amount*wgt;
+					spm_add(C, W, (size_t)NX*CLAMPI(z, NY-1) + CLAMPI(x, NX-1), -delta);
+				}
+			}
+			dh-=ds;
+			s+=ds;
+		}
+		v=sqrtf(v*v+Kg*dh);
+		w*=1-Kw;
+		xp=nxp; zp=nzp; xi=nxi; zi=nzi; xf=nxf; zf=nzf;
+		h=nh; h00=nh00; h10=nh10; h01=nh01; h11=nh11;
+	}
+	W->xi=xi; W->zi=zi; W->xp=xp; W->zp=zp; W->xf=xf; W->zf=zf; W->s=s; W->v=v; W->w=w; W->dx=dx; W->dz=dz; W->h=h; W->h00=h00; W->h10=h10; W->h01=h01; W->h11=h11;
+	return ended;
+}
+/* returns the droplet moves (of the walks that were committed); stats[0..3] (optional) = rounds, walks started, walks thrown away, droplets walked in place */
+unsigned long long to_erode_spec_model(float *heightmap, int xsize, int ysize, float min_zval, unsigned num_iters, const tw_erosion_params *ep,
+                                       unsigned B, unsigned cap, int tile_shift, unsigned sched_seed, unsigned long long *stats)
+{
+	if (num_iters == 0 || ep->erode_amount <= 0.0 || B == 0 || cap == 0) return 0;
+	int const PAD = 4, NX = xsize+2*PAD, NY = ysize+2*PAD;
+	spm_ctx C;
+	C.NX = NX; C.NY = NY; C.xsize = xsize; C.ysize = ysize; C.shift = tile_shift; C.TNX = ((NX-1) >> tile_shift) + 1; C.ep = ep; C.MAX_PATH_LEN = 4u*(unsigned)NX*(unsigned)NY;
+	C.mh = (float *)malloc((size_t)NX*NY*sizeof(float));
+	for (int y = 0; y < NY; ++y) {for (int x = 0; x < NX; ++x) {C.mh[(size_t)y*NX + x] = heightmap[CLAMPI(x-PAD, xsize-1) + (size_t)CLAMPI(y-PAD, ysize-1)*xsize];}}
+	size_t const ntile = (size_t)C.TNX*(((NY-1) >> tile_shift) + 1);
+	unsigned *stamps = (unsigned *)malloc(ntile*sizeof(unsigned));
+	for (size_t t = 0; t < ntile; ++t) {stamps[t] = 0xffffffffu;}
+	spm_walker *Wk = (spm_walker *)calloc(B, sizeof(spm_walker));
+	for (unsigned s = 0; s < B; ++s) {
+		spm_walker *W = &Wk[s];
+		W->it = s; W->status = (s < num_iters) ? 1 : 0;
+		W->ov_cell = (unsigned *)malloc((size_t)NX*NY*sizeof(unsigned)); W->ov_val = (float *)malloc((size_t)NX*NY*sizeof(float)); W->ov_pos = (int *)malloc((size_t)NX*NY*sizeof(int));
+		for (size_t i = 0; i < (size_t)NX*NY; ++i) {W->ov_pos[i] = -1;}
+		W->cap_tile = 64; W->tiles = (unsigned *)malloc(W->cap_tile*sizeof(unsigned));
+	}
+	unsigned long long steps = 0, rounds = 0, walks = 0, wasted = 0, inplace = 0;
+	unsigned lo = 0, rnd = sched_seed*2654435761u + 12345u;
+	unsigned *order = (unsigned *)malloc(B*sizeof(unsigned));
+	while (lo < num_iters) {
+		++rounds;
+		unsigned const hi = (num_iters - lo < B) ? num_iters : lo + B;
+		/* ---- walk, in a pseudo-random order of the slots (the GPU's walkers run concurrently: the head's in-place writes land before, between or after the others' reads) */
+		for (unsigned s = 0; s < B; ++s) {order[s] = s;}
+		for (unsigned s = B; s > 1; --s) {rnd = rnd*1664525u + 1013904223u; unsigned const j = (rnd >> 8) % s, t = order[s-1]; order[s-1] = order[j]; order[j] = t;}
+		for (unsigned k = 0; k < B; ++k) {
+			spm_walker *W = &Wk[order[k]];
+			if (W->it >= num_iters || !(W->status == 1 || W->status == 5)) continue;
+			if (W->status == 1) {spm_reset(&C, W); ++walks; W->inplace = (W->it == lo); if (W->inplace) {++inplace;}}
+			W->status = spm_walk(&C, W, W->inplace ? 2*cap : cap) ? 2 : 5;
+		}
+		/* ---- stamp */
+		for (unsigned s = 0; s < B; ++s) {
+			spm_walker *W = &Wk[s];
+			if (W->it >= num_iters || !(W->status == 2 || W->status == 5)) continue;
+			for (size_t k = 0; k < W->ntile; ++k) {if (W->it < stamps[W->tiles[k]]) {stamps[W->tiles[k]] = W->it;}}
+		}
+		/* ---- validate: the first droplet that cannot be committed */
+		unsigned f = hi;
+		unsigned *minw = order; /* reuse */
+		for (unsigned s = 0; s < B; ++s) {
+			spm_walker *W = &Wk[s];
+			minw[s] = 0xffffffffu;
+			if (W->it >= num_iters || W->status == 0) continue;
+			if (!(W->status == 2 || W->status == 5)) {if (W->it < f) {f = W->it;} continue;}
+			for (size_t k = 0; k < W->ntile; ++k) {if (stamps[W->tiles[k]] < minw[s]) {minw[s] = stamps[W->tiles[k]];}}
+			if ((minw[s] < W->it || W->status == 5) && W->it < f) {f = W->it;}
+		}
+		/* ---- commit the prefix [lo, f), re-walk what a committed droplet touched, take the stamps back */
+		for (unsigned s = 0; s < B; ++s) {
+			spm_walker *W = &Wk[s];
+			if (W->it >= num_iters || W->status == 0) continue;
+			if (W->status == 2 || W->status == 5) {for (size_t k = 0; k < W->ntile; ++k) {stamps[W->tiles[k]] = 0xffffffffu;}}
+			if (W->it < f) {
+				if (!W->inplace) {for (size_t k = 0; k < W->nov; ++k) {C.mh[W->ov_cell[k]] = W->ov_val[k];}}
+				steps += W->steps;
+				spm_reset(&C, W);
+				W->it += B; W->status = (W->it < num_iters) ? 1 : 0;
+			}
+			else if ((W->status == 2 || W->status == 5) && minw[s] < f) {W->status = 1; ++wasted;}
+		}
+		if (rounds > 64ull*num_iters*(1ull + C.MAX_PATH_LEN/cap)) {free(order); order = NULL; break;} /* no progress (cannot happen: a finished head is never in conflict, and the head finishes) */
+		lo = f;
+	}
+	int const ok = (order != NULL);
+	for (int y = 0; y < ysize; ++y) {for (int x = 0; x < xsize; ++x) {heightmap[(size_t)y*xsize + x] = std_max(min_zval, C.mh[(size_t)(y+PAD)*NX + x+PAD]);}}
+	for (unsigned s = 0; s < B; ++s) {free(Wk[s].ov_cell); free(Wk[s].ov_val); free(Wk[s].ov_pos); free(Wk[s].tiles);}
+	free(Wk); free(stamps); free(order); free(C.mh);
+	if (stats) {stats[0] = rounds; stats[1] = walks; stats[2] = wasted; stats[3] = inplace;}
+	return ok ? steps : ~0ull;
+}
+

@@ -74,6 +74,10 @@ void to_eval_points(const float *xy, size_t n, const tw_height_params *p, const 
 unsigned long long to_apply_erosion(float *heightmap, int xsize, int ysize, float min_zval, unsigned num_iters, const tw_erosion_params *p);
 unsigned long long to_erode_sweeps(float *heightmap, int xsize, int ysize, float min_zval, unsigned num_iters, const tw_erosion_params *p, unsigned sweep, int halo);
 
+/* the protocol of the product's speculative serial-order erosion (M_SPEC) as a sequential model: must equal to_apply_erosion for every window / cap / tile size / schedule */
+unsigned long long to_erode_spec_model(float *heightmap, int xsize, int ysize, float min_zval, unsigned num_iters, const tw_erosion_params *ep,
+                                       unsigned B, unsigned cap, int tile_shift, unsigned sched_seed, unsigned long long *stats);
+
 /* noise_gen_3d, src/upsurface.cpp:16-85 */
 void  to_noise3d_gen_sines(int rs1, int rs2, float mag, float freq, float *rdata420);
 float to_noise3d_get_val_pt(const float *rdata420, const float *sin_table, float x, float y, float z);

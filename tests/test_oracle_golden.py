@@ -291,3 +291,23 @@ def test_terrain_weights_texture(oracle):
             w, flags = oracle.tile_weights(g["tiles_" + n], rand, g["corners_" + n], wp)
             assert np.array_equal(w, g["weights_%s_%d" % (n, ci)]), (n, ci, int((w != g["weights_%s_%d" % (n, ci)]).sum()))
             assert np.array_equal(flags, g["grass_%s_%d" % (n, ci)])
+
+
+def test_spec_protocol_model(oracle, beq):
+    """The protocol of the product's speculative serial-order erosion (M_SPEC) as a sequential model in the oracle: whatever the window, the moves
+    allowed per round, the conflict-tile size and the order in which the walkers (and the in-place head among them) run, the result is the serial reference order's, bit
+    for bit, moves included - on maps so small that almost every droplet conflicts with an earlier one."""
+    g = load("erosion.npz")
+    rng = np.random.default_rng(5)
+    yy, xx = np.mgrid[0:57, 0:83].astype(np.float32)
+    z = (np.sin(xx * 0.21) * np.cos(yy * 0.17) * 0.8 + 0.3 * np.sin(xx * 0.05 + yy * 0.09) + 0.05 * rng.standard_normal((57, 83))).astype(np.float32)
+    zmin, zmax = float(z.min()), float(z.max())
+    total_wasted = total_inplace = 0
+    for ep in (oracle.ErosionParams(1.0, zmin - 10, 0.0625, zmin - 0.1, zmax + 0.1, 0.0, 0.5), oracle.ErosionParams(1.0, zmin + 0.2 * (zmax - zmin), 0.0625, zmin - 0.1, zmax + 0.1, 0.0, 2.0)):
+        want, steps = oracle.apply_erosion(z, zmin, 400, ep)
+        for window, cap, shift, seed in ((1, 1000000, 2, 0), (7, 3, 2, 1), (32, 1, 2, 2), (32, 16, 3, 3), (64, 64, 2, 4), (256, 8, 4, 5), (16, 1000000, 2, 6), (500, 5, 2, 7)):
+            got, moves, (rounds, walks, wasted, inplace) = oracle.erode_spec_model(z, zmin, 400, ep, window, cap, shift, seed)
+            assert moves == steps and beq(got, want) == 0, (window, cap, shift, seed, moves, steps)
+            assert walks == 400 + wasted and rounds >= 1
+            total_wasted, total_inplace = total_wasted + wasted, total_inplace + inplace
+    assert total_wasted > 200 and total_inplace > 200            # conflicts and in-place heads did occur
