@@ -33,4 +33,4 @@ out = ["SASS excerpt (cuobjdump -sass 3dworld_b200/lib3dworld_b200.so, sm_100a) 
        % (2 * (hist["FFMA2"] + hist["FMUL2"] + hist["FADD2"]) + hist["FMUL"] + hist["FADD"] + hist["FFMA"]),
        "(a packed add of two products is fma(x, ONE, y) with an opaque ONE, every other packed add a plain FADD2, see csrc/tw_noise2.cuh); LDS = hash / gradient table look-ups; FRND = floor().", ""]
 out += ["        /*%04x*/  %s ;" % (x, t) for x, t in body]
-open(sys.argv[1] if len(sys.argv) > 1 else "/dev/stdout", "w").write("\n".join(out) + "\n")
+open(sys.argv[1] if len(sys.argv) > 1 and not sys.argv[1].startswith("-") else "/dev/stdout", "w").write("\n".join(out) + "\n")
