@@ -346,3 +346,21 @@ def test_table_driven_perlin2_equals_glm_on_cpu(oracle):
     f = oracle.lib().to_perlin2
     exp = np.array([f(float(a), float(b)) for a, b in zip(Px, Py)], f32)
     assert np.array_equal(got.view(np.uint32), exp.view(np.uint32))
+
+
+def test_denormal_table_addressing_is_exact():
+    """The noise kernels turn a small integer k (held in a float) into the shared-memory address of table entry k with ONE fused multiply-add on denormals
+    (csrc/tw_noise2.cuh, TW_LUT_DENORM): fma(k, 128*2^-149, A*2^-149) must have the bit pattern 128*k + A for every reachable k (<= 578; 3-D tables the same)
+    and every base address A below 2^18 (the lane's copy of entry 0). Checked here in IEEE fp32 on the host: the product k*128 (< 2^17) and the sum with A (< 2^19)
+    are exact multiples of 2^-149 below 2^23*2^-149, i.e. representable denormals, so the fused and the unfused evaluation agree and nothing rounds."""
+    k = np.arange(0, 600, dtype=np.float32)
+    entry = np.array([128], np.uint32).view(np.float32)[0]                  # 128 * 2^-149
+    for A in (0, 16, 112, 1024 + 48, 74 * 1024 + 96, (1 << 18) - 16):
+        a = np.array([A], np.uint32).view(np.float32)[0]
+        unfused = (k * entry + a).astype(np.float32)                        # two roundings, both exact
+        fused = np.array([np.float32(np.float64(kk) * np.float64(entry) + np.float64(a)) for kk in k], np.float32)   # exact product and sum in fp64, one rounding
+        want = (128 * k.astype(np.uint32) + A).astype(np.uint32)
+        assert np.array_equal(unfused.view(np.uint32), want) and np.array_equal(fused.view(np.uint32), want), A
+    step = np.float32(1.0) * entry                                          # the middle corner: address of entry k + i1.y = fma(i1.y, 128*2^-149, address of entry k)
+    base = (np.float32(17.0) * entry + np.array([4096 + 32], np.uint32).view(np.float32)[0]).astype(np.float32)
+    assert (base + step).astype(np.float32).view(np.uint32) == 128 * 18 + 4096 + 32 and (base + np.float32(0.0) * entry).astype(np.float32).view(np.uint32) == 128 * 17 + 4096 + 32
